@@ -1,0 +1,424 @@
+/*
+ * duckdb_mb_gpu.h — C ABI of libduckdb_mb_gpu.so, the B200 (sm_100a) implementation of the
+ * result/ingest boundary of the MoonBit DuckDB bindings f4ah6o/duckdb.mbt.
+ *
+ * Three layers, all `extern "C"`, plain pointers and sizes, no torch / C++ types:
+ *
+ *   L0  device API   dmb_dev_*        raw device pointers + a cudaStream_t (as void*); one launch
+ *                                     converts a whole chunk batch.  bench.py `value`, ncu.
+ *   L1  host API     duckdb_mb_gpu_*  HOST DuckDB-shaped chunk vectors in, Arrow C Data / typed
+ *                                     columns / reference packed blobs out; pinned staging and
+ *                                     cudaMemcpyAsync on streams inside.  bench.py `e2e`.
+ *   L2  drop-in      duckdb_mb_arrow_* / duckdb_mb_bytes_to_double — the exact symbols the
+ *                                     reference's MoonBit `extern "C"` declarations bind
+ *                                     (src/duckdb_arrow_native.mbt:9-104), served from an L1 result.
+ *
+ * Every entry cites the reference interface (file:line under /root/reference) it replaces.
+ */
+#ifndef DUCKDB_MB_GPU_H
+#define DUCKDB_MB_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "moonbit_standin.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMB_VECTOR_SIZE 2048 /* DuckDB STANDARD_VECTOR_SIZE; chunks hold <= 2048 rows */
+#define DMB_VALIDITY_WORDS 32 /* uint64 words per full vector */
+
+/* ---- DuckDB type ids (duckdb.h DUCKDB_TYPE; the reference mirrors the numbering in
+ *      src/duckdb_parsing.mbt:8-52 and switches on it in src/duckdb_native.c:271-303,553-662) */
+enum dmb_type {
+  DMB_TYPE_INVALID = 0,
+  DMB_TYPE_BOOLEAN = 1,
+  DMB_TYPE_TINYINT = 2,
+  DMB_TYPE_SMALLINT = 3,
+  DMB_TYPE_INTEGER = 4,
+  DMB_TYPE_BIGINT = 5,
+  DMB_TYPE_UTINYINT = 6,
+  DMB_TYPE_USMALLINT = 7,
+  DMB_TYPE_UINTEGER = 8,
+  DMB_TYPE_UBIGINT = 9,
+  DMB_TYPE_FLOAT = 10,
+  DMB_TYPE_DOUBLE = 11,
+  DMB_TYPE_TIMESTAMP = 12,
+  DMB_TYPE_DATE = 13,
+  DMB_TYPE_TIME = 14,
+  DMB_TYPE_INTERVAL = 15,
+  DMB_TYPE_HUGEINT = 16,
+  DMB_TYPE_VARCHAR = 17,
+  DMB_TYPE_BLOB = 18,
+  DMB_TYPE_DECIMAL = 19,
+  DMB_TYPE_TIMESTAMP_S = 20,
+  DMB_TYPE_TIMESTAMP_MS = 21,
+  DMB_TYPE_TIMESTAMP_NS = 22,
+  DMB_TYPE_UUID = 27,
+  DMB_TYPE_TIME_TZ = 30,
+  DMB_TYPE_TIMESTAMP_TZ = 31,
+  DMB_TYPE_UHUGEINT = 32,
+  DMB_TYPE_TIME_NS = 39
+};
+
+/* ---- physical payload of a flat vector (duckdb_vector_get_data; reference reads them at
+ *      src/duckdb_native.c:553-662) */
+enum dmb_phys {
+  DMB_PHYS_BOOL = 0, /* 1 B, 0/1 */
+  DMB_PHYS_I8 = 1,
+  DMB_PHYS_I16 = 2,
+  DMB_PHYS_I32 = 3,
+  DMB_PHYS_I64 = 4,
+  DMB_PHYS_U8 = 5,
+  DMB_PHYS_U16 = 6,
+  DMB_PHYS_U32 = 7,
+  DMB_PHYS_U64 = 8,
+  DMB_PHYS_F32 = 9,
+  DMB_PHYS_F64 = 10,
+  DMB_PHYS_I128 = 11,     /* duckdb_hugeint {uint64 lower, int64 upper} */
+  DMB_PHYS_U128 = 12,     /* duckdb_uhugeint / UUID */
+  DMB_PHYS_INTERVAL = 13, /* {int32 months, int32 days, int64 micros} */
+  DMB_PHYS_STRING = 14,   /* duckdb_string_t, 16 B */
+  DMB_PHYS_COUNT = 15
+};
+
+/* ---- what a fixed-width column is converted to (kernels K2/K3/K4) */
+enum dmb_dst {
+  DMB_DST_SAME = 0,       /* Arrow primitive of the same width; NULL slots zeroed            */
+  DMB_DST_I32_TRUNC = 1,  /* (int32_t)duckdb_value_int64      src/duckdb_native.c:2379-2387   */
+  DMB_DST_I64 = 2,        /* duckdb_value_int64               src/duckdb_native.c:2413-2419   */
+  DMB_DST_F64 = 3,        /* duckdb_value_double              src/duckdb_native.c:2445-2451   */
+  DMB_DST_BOOL_BYTE = 4,  /* duckdb_value_boolean ? 1 : 0     src/duckdb_native.c:2537-2543   */
+  DMB_DST_BOOL_BITS = 5,  /* Arrow bit-packed bool values                                     */
+  DMB_DST_I128 = 6,       /* DECIMAL int16/32/64 -> Arrow decimal128 (sign-extend)            */
+  DMB_DST_I32_SAT = 7,    /* typed Value::Int: Int32-saturating  src/duckdb_parsing.mbt:203-237 */
+  DMB_DST_TS_US_FROM_S = 8,   /* typed Value::Timestamp micros   src/duckdb_parsing.mbt:375-398 */
+  DMB_DST_TS_US_FROM_MS = 9,
+  DMB_DST_TS_US_FROM_NS = 10, /* floor(ns/1000): fraction truncated to 6 digits :402-417      */
+  DMB_DST_MONTH_DAY_NANO = 11, /* INTERVAL -> Arrow month_day_nano_interval                   */
+  DMB_DST_DATE_REF = 12,  /* typed Value::Date through the reference's date_to_days, incl. its
+                             pre-1970 leap-day defect      src/duckdb_parsing.mbt:318-338      */
+  DMB_DST_COUNT = 13
+};
+
+#define DMB_OP(phys, dst) (((int32_t)(phys) << 8) | (int32_t)(dst))
+#define DMB_OP_VALIDITY_ONLY 0x7f00 /* job writes only validity outputs (string columns) */
+
+/* one flat vector of one chunk inside a device-resident column slab */
+typedef struct dmb_vec_desc {
+  uint64_t data_off; /* byte offset of the vector payload in the column slab (16-B aligned) */
+  int64_t val_off;   /* offset in uint64 words of the validity mask in the validity slab,
+                        or -1: duckdb_vector_get_validity returned NULL = all valid
+                        (reference: src/duckdb_native.c:530-533) */
+} dmb_vec_desc;
+
+/* ---- one fixed-width output column of a batch (device pointers) */
+typedef struct dmb_fixed_job {
+  const void *in_data;         /* column slab */
+  const uint64_t *in_validity; /* validity slab (may be NULL when every val_off is -1) */
+  const dmb_vec_desc *vecs;    /* [nchunks] */
+  void *out_values;            /* contiguous output values (256-B aligned)             */
+  uint64_t *out_validity;      /* Arrow LSB bitmap, ceil(n/64) words, or NULL            */
+  uint8_t *out_valid_bytes;    /* reference byte-per-row validity (1=valid), or NULL
+                                  (src/duckdb_native.c:2594-2606)                        */
+  unsigned long long *null_count; /* device counter, incremented; or NULL               */
+  int32_t op;                  /* DMB_OP(phys, dst) */
+  int32_t reserved;
+} dmb_fixed_job;
+
+/* duckdb_string_t, 16 bytes (reference reads it at src/duckdb_native.c:597-603) */
+typedef struct dmb_string_t {
+  uint32_t length;
+  union {
+    struct { char inlined[12]; } inl;               /* length <= 12 */
+    struct { char prefix[4]; uint64_t ptr; } ptr;   /* length  > 12: host heap pointer */
+  } value;
+} dmb_string_t;
+
+enum dmb_string_mode {
+  DMB_STR_ARROW_UTF8 = 0,  /* int32 offsets[n+1] + data; NULL rows have zero length          */
+  DMB_STR_ARROW_LARGE = 1, /* int64 offsets                                                  */
+  DMB_STR_REF_BLOB = 2     /* reference NUL-terminated concatenation, strlen semantics
+                              (src/duckdb_native.c:2474-2510): int32 offsets[n+1] + data where
+                              every row contributes strnlen(s)+1 bytes and a NULL row a lone \0 */
+};
+
+/* ---- one VARCHAR/BLOB output column of a batch (device pointers) */
+typedef struct dmb_string_job {
+  const dmb_string_t *in;      /* slab of string_t */
+  const uint64_t *in_validity;
+  const dmb_vec_desc *vecs;    /* data_off in bytes into `in` */
+  const uint8_t *heap_dev;     /* device copy of the string heap                          */
+  uint64_t heap_host_base;     /* host address the `ptr` fields are relative to: the kernel
+                                  rebases dev = heap_dev + (ptr - heap_host_base)          */
+  uint64_t heap_len;
+  void *out_offsets;           /* int32[n+1] or int64[n+1]                                 */
+  uint8_t *out_data;
+  uint64_t *out_validity;      /* Arrow bitmap or NULL                                     */
+  uint8_t *out_valid_bytes;    /* byte-per-row or NULL                                     */
+  unsigned long long *null_count;
+  unsigned long long *total_bytes; /* device: final data length                            */
+  int32_t mode;
+  int32_t reserved;
+} dmb_string_job;
+
+/* =====================================================================================
+ * L0 — device API.  All pointers are device pointers unless said otherwise; `stream` is a
+ * cudaStream_t.  Return 0 on success, negative on error (duckdb_mb_gpu_last_error()).
+ * ===================================================================================== */
+
+/* K1+K2+K3+K4 fused: every fixed-width column of a chunk batch in ONE launch.
+ *   jobs_dev  device array [njobs]; jobs_host is the host mirror of the same array.  One launch
+ *             covers each run of equal `op`, so sort jobs by op: a batch costs one launch per
+ *             distinct conversion
+ *   counts    device uint32[nchunks] rows per chunk (duckdb_data_chunk_get_size, <= 2048)
+ *   row_off   device int64[nchunks+1] exclusive scan of counts
+ * Replaces the per-cell loops src/duckdb_native.c:2379-2387,2413-2419,2445-2451,2537-2543,
+ * 2597-2606 and the per-cell validity test :520-535. */
+int32_t dmb_dev_fixed_batch(const dmb_fixed_job *jobs_dev, const dmb_fixed_job *jobs_host,
+                            int32_t njobs, const uint32_t *counts, const int64_t *row_off,
+                            int64_t nchunks, int64_t nrows, void *stream);
+
+/* host-side op table: output bytes per value of DMB_OP(phys,dst) (0 = bit-packed), -1 if the
+ * pair is not supported; bytes per value of a physical type */
+int32_t dmb_op_out_width(int32_t op);
+int32_t dmb_phys_width(int32_t phys);
+
+/* K5: string_t -> utf8 offsets + data, single pass (block scan + decoupled look-back).
+ *   scratch   device, >= dmb_dev_string_scratch_bytes(nchunks) bytes, zeroed by the call
+ * Replaces src/duckdb_native.c:597-603 (string_t read) and :2474-2510 / :2699-2755. */
+size_t dmb_dev_string_scratch_bytes(int64_t nchunks);
+/* error flags raised by the last string launch on `scratch` (0 = none); synchronises `stream` */
+int32_t dmb_dev_string_error(const void *scratch, void *stream);
+int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_t *counts,
+                             const int64_t *row_off, int64_t nchunks, int64_t nrows,
+                             void *scratch, void *stream);
+
+/* K6 reverse (Arrow -> DataChunk vectors), the bulk door behind the appender
+ * (reference row-at-a-time path: src/duckdb_native.c:1100-1235; chunk door :2029-2132). */
+typedef struct dmb_rev_fixed_job {
+  const void *in_values;        /* Arrow values buffer (already offset to the slice start) */
+  const uint8_t *in_validity;   /* Arrow bitmap bytes or NULL                              */
+  int64_t in_bit_offset;        /* Arrow array offset (bits into in_validity / bool values) */
+  void *out_data;               /* vector slab: chunk k at k*2048*W bytes                  */
+  uint64_t *out_validity;       /* validity slab: chunk k at k*32 words                    */
+  unsigned long long *null_count;
+  int32_t op;                   /* DMB_REV_* */
+  int32_t reserved;
+} dmb_rev_fixed_job;
+
+enum dmb_rev_op {
+  DMB_REV_COPY1 = 0, DMB_REV_COPY2 = 1, DMB_REV_COPY4 = 2, DMB_REV_COPY8 = 3, DMB_REV_COPY16 = 4,
+  DMB_REV_BITS_TO_BOOL = 5,   /* Arrow bool bits -> DuckDB bool bytes                      */
+  DMB_REV_I128_TO_I64 = 6,    /* decimal128 -> DECIMAL(<=18) int64                          */
+  DMB_REV_I128_TO_I32 = 7,
+  DMB_REV_I128_TO_I16 = 8,
+  DMB_REV_COUNT = 9
+};
+
+int32_t dmb_dev_rev_fixed_batch(const dmb_rev_fixed_job *jobs, int32_t njobs, int64_t nrows,
+                                void *stream);
+
+typedef struct dmb_rev_string_job {
+  const void *in_offsets;       /* int32 (or int64 when large) offsets, at the slice start */
+  const uint8_t *in_data;       /* device copy of the Arrow data buffer                    */
+  const uint8_t *in_validity;
+  int64_t in_bit_offset;
+  uint64_t data_host_base;      /* host address of the Arrow data buffer: pointer string_t
+                                   reference it in place                   */
+  dmb_string_t *out;            /* string_t slab: chunk k at k*2048 entries                */
+  uint64_t *out_validity;
+  unsigned long long *null_count;
+  int32_t large_offsets;
+  int32_t reserved;
+} dmb_rev_string_job;
+
+int32_t dmb_dev_rev_string_batch(const dmb_rev_string_job *job, int64_t nrows, void *stream);
+
+/* byte-per-row validity (MoonBit Array[Bool], src/duckdb_arrow_native.mbt:646-650) -> per-chunk
+ * uint64 masks via warp ballots */
+int32_t dmb_dev_valid_bytes_to_masks(const uint8_t *valid_bytes, uint64_t *out_validity,
+                                     unsigned long long *null_count, int64_t nrows, void *stream);
+
+/* bench/test helper: assemble DuckDB-shaped string_t on the device from lengths and heap
+ * offsets (not part of the product path) */
+int32_t dmb_dev_make_string_t(const uint32_t *lengths, const uint64_t *heap_off,
+                              const uint8_t *heap_dev, uint64_t heap_host_base, dmb_string_t *out,
+                              int64_t n, void *stream);
+
+/* =====================================================================================
+ * L1 — host API.
+ * ===================================================================================== */
+
+typedef struct duckdb_mb_gpu_ctx duckdb_mb_gpu_ctx;       /* one per GPU: streams, pinned ring   */
+typedef struct duckdb_mb_arrow_result duckdb_mb_arrow_result; /* same handle name as the reference
+                                                              (src/duckdb_native.c:2211-2217)    */
+
+/* thread-local last error (the reference keeps one process-global string,
+ * src/duckdb_native.c:22-40,240-246; SURVEY.md §5 asks for thread safety) */
+const char *duckdb_mb_gpu_last_error(void);
+
+int32_t duckdb_mb_gpu_device_count(void);
+duckdb_mb_gpu_ctx *duckdb_mb_gpu_ctx_create(int32_t device);
+void duckdb_mb_gpu_ctx_destroy(duckdb_mb_gpu_ctx *ctx);
+int32_t duckdb_mb_gpu_ctx_sync(duckdb_mb_gpu_ctx *ctx);
+
+/* pinned host memory for callers that can place chunk vectors / Arrow buffers in it
+ * (staging then needs no bounce copy) */
+void *duckdb_mb_gpu_host_alloc(size_t bytes);
+void duckdb_mb_gpu_host_free(void *p);
+
+/* One column of a host chunk batch: the pointers duckdb_vector_get_data /
+ * duckdb_vector_get_validity return for each chunk (src/duckdb_native.c:529-530,547). */
+typedef struct dmb_host_column {
+  const char *name;
+  int32_t type_id;       /* enum dmb_type */
+  int32_t phys;          /* enum dmb_phys (DECIMAL: by width) */
+  int32_t dec_width;
+  int32_t dec_scale;
+  const void *const *data;          /* [nchunks] */
+  const uint64_t *const *validity;  /* [nchunks], entries may be NULL; the array may be NULL */
+  /* VARCHAR/BLOB: a contiguous host region containing every non-inlined string of the column
+   * (copied wholesale, pointers rebased on the device), or heap_len == 0: the stager compacts
+   * the pointed-to bytes into pinned memory itself. */
+  const void *heap_base;
+  uint64_t heap_len;
+} dmb_host_column;
+
+typedef struct dmb_host_batch {
+  int32_t ncols;
+  int32_t flags;           /* DMB_BATCH_* */
+  int64_t nchunks;
+  const uint32_t *counts;  /* [nchunks] */
+  const dmb_host_column *cols;
+} dmb_host_batch;
+
+#define DMB_BATCH_PINNED 1 /* all data/validity/heap pointers are in page-locked memory */
+
+/* Build a result from host chunks: stages them to the device (async, on the ctx streams).
+ * Conversion happens lazily per export call or eagerly with duckdb_mb_gpu_result_materialise.
+ * Stands where the reference keeps the duckdb_result (src/duckdb_native.c:2219-2268). */
+duckdb_mb_arrow_result *duckdb_mb_gpu_result_from_chunks(duckdb_mb_gpu_ctx *ctx,
+                                                         const dmb_host_batch *batch);
+
+/* Arrow C Data Interface structs (Arrow spec; 80 / 72 bytes) */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+struct ArrowSchema {
+  const char *format;
+  const char *name;
+  const char *metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema **children;
+  struct ArrowSchema *dictionary;
+  void (*release)(struct ArrowSchema *);
+  void *private_data;
+};
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void **buffers;
+  struct ArrowArray **children;
+  struct ArrowArray *dictionary;
+  void (*release)(struct ArrowArray *);
+  void *private_data;
+};
+#endif
+
+/* DataChunk -> Arrow for every column: H2D (if not yet staged), kernels, D2H into pinned
+ * buffers owned by the result.  Blocking.  Returns 1/0 (reference mutator convention). */
+int32_t duckdb_mb_gpu_result_materialise_arrow(duckdb_mb_arrow_result *r);
+/* Export column `col` (or the whole batch as a struct array with col = -1). */
+int32_t duckdb_mb_gpu_result_export_arrow(duckdb_mb_arrow_result *r, int32_t col,
+                                          struct ArrowArray *out_array,
+                                          struct ArrowSchema *out_schema);
+
+/* typed columns (columnar to_typed; replaces the string round trip
+ * src/duckdb_native.mbt:477-497 -> src/duckdb_typed_result.mbt:8-43) */
+enum dmb_value_tag { /* order of `Value` in src/duckdb.mbt:183-193 */
+  DMB_VALUE_INT = 0, DMB_VALUE_DOUBLE = 1, DMB_VALUE_BOOL = 2, DMB_VALUE_STRING = 3,
+  DMB_VALUE_DATE = 4, DMB_VALUE_TIMESTAMP = 5, DMB_VALUE_DECIMAL = 6, DMB_VALUE_BLOB = 7,
+  DMB_VALUE_NULL = 8
+};
+typedef struct dmb_typed_column {
+  int32_t tag;            /* enum dmb_value_tag of the non-null cells                      */
+  int32_t width;          /* bytes per value: Int 4, Double 8, Bool 1, Date 4, Timestamp 8 */
+  int64_t length;
+  int64_t null_count;
+  const void *values;     /* host, pinned, owned by the result                            */
+  const uint8_t *valid;   /* byte per row, 1 = non-null                                   */
+  const int32_t *offsets; /* String: utf8 offsets[n+1]                                    */
+  const uint8_t *data;    /* String: utf8 bytes                                           */
+} dmb_typed_column;
+int32_t duckdb_mb_gpu_result_typed_column(duckdb_mb_arrow_result *r, int32_t col,
+                                          dmb_typed_column *out);
+
+/* timings of the last materialise call, milliseconds: [0]=h2d [1]=kernels [2]=d2h [3]=total */
+int32_t duckdb_mb_gpu_result_timings(duckdb_mb_arrow_result *r, double *out4);
+/* bytes moved over the host link by the last materialise call: [0]=h2d [1]=d2h */
+int32_t duckdb_mb_gpu_result_link_bytes(duckdb_mb_arrow_result *r, uint64_t *out2);
+
+/* =====================================================================================
+ * L2 — the reference's own symbols (src/duckdb_arrow_native.mbt:9-104), byte-compatible
+ * results (src/duckdb_native.c:2357-2797), served by the GPU path.
+ * duckdb_mb_query_arrow itself needs libduckdb to run SQL; INTEGRATION.md shows the glue that
+ * turns its duckdb_result into a dmb_host_batch.
+ * ===================================================================================== */
+int32_t duckdb_mb_arrow_column_count(duckdb_mb_arrow_result *r); /* :2270-2275 */
+int32_t duckdb_mb_arrow_row_count(duckdb_mb_arrow_result *r);    /* :2277-2282 */
+moonbit_bytes_t duckdb_mb_arrow_schema(duckdb_mb_arrow_result *r); /* :2285-2355 */
+moonbit_bytes_t duckdb_mb_arrow_get_column_int32(duckdb_mb_arrow_result *r, int32_t col);  /* :2359 */
+moonbit_bytes_t duckdb_mb_arrow_get_column_int64(duckdb_mb_arrow_result *r, int32_t col);  /* :2392 */
+moonbit_bytes_t duckdb_mb_arrow_get_column_double(duckdb_mb_arrow_result *r, int32_t col); /* :2424 */
+moonbit_bytes_t duckdb_mb_arrow_get_column_string(duckdb_mb_arrow_result *r, int32_t col); /* :2456 */
+moonbit_bytes_t duckdb_mb_arrow_get_column_bool(duckdb_mb_arrow_result *r, int32_t col);   /* :2516 */
+moonbit_bytes_t duckdb_mb_arrow_get_column_int32_nullable(duckdb_mb_arrow_result *r, int32_t col);  /* :2572 */
+moonbit_bytes_t duckdb_mb_arrow_get_column_int64_nullable(duckdb_mb_arrow_result *r, int32_t col);  /* :2611 */
+moonbit_bytes_t duckdb_mb_arrow_get_column_double_nullable(duckdb_mb_arrow_result *r, int32_t col); /* :2649 */
+moonbit_bytes_t duckdb_mb_arrow_get_column_string_nullable(duckdb_mb_arrow_result *r, int32_t col); /* :2687 */
+moonbit_bytes_t duckdb_mb_arrow_get_column_bool_nullable(duckdb_mb_arrow_result *r, int32_t col);   /* :2761 */
+void duckdb_mb_arrow_destroy(duckdb_mb_arrow_result *r);              /* :2548-2554 */
+int32_t duckdb_mb_is_null_arrow_result(duckdb_mb_arrow_result *r);    /* :2556-2558 */
+double duckdb_mb_bytes_to_double(const char *bytes, int32_t offset);  /* :2561-2565 */
+
+/* =====================================================================================
+ * Reverse path: Arrow record batch -> DataChunk vectors for duckdb_append_data_chunk, gated by
+ * the appender protocol of src/duckdb_appender_state_machine.mbt:54-239.
+ * ===================================================================================== */
+typedef struct duckdb_mb_gpu_appender duckdb_mb_gpu_appender;
+
+/* sink called once per finished 2048-row chunk: `vec_data[c]` / `vec_validity[c]` are host
+ * pointers laid out exactly as duckdb_vector_get_data / _get_validity expect, so the glue
+ * memcpy's (or, with pinned vectors, hands) them to duckdb_append_data_chunk
+ * (src/duckdb_native.c:2109-2132).  Return 0 to abort. */
+typedef int32_t (*dmb_chunk_sink)(void *user, int32_t ncols, uint32_t count,
+                                  const void *const *vec_data,
+                                  const uint64_t *const *vec_validity);
+
+duckdb_mb_gpu_appender *duckdb_mb_gpu_appender_create(duckdb_mb_gpu_ctx *ctx, int32_t ncols,
+                                                      const int32_t *type_ids,
+                                                      dmb_chunk_sink sink, void *user);
+void duckdb_mb_gpu_appender_destroy(duckdb_mb_gpu_appender *a);
+moonbit_bytes_t duckdb_mb_gpu_appender_error(duckdb_mb_gpu_appender *a); /* cf. :1093-1098 */
+/* state: 0 NotCreated 1 Ready 2 RowInProgress 3 Flushed 4 Closed 5 Error
+ * (AppenderState, src/duckdb_appender_state_machine.mbt:7-14) */
+int32_t duckdb_mb_gpu_appender_state(duckdb_mb_gpu_appender *a);
+int64_t duckdb_mb_gpu_appender_row_count(duckdb_mb_gpu_appender *a);
+/* bulk append of one Arrow record batch (struct array, one child per column); legal in
+ * Ready / Flushed, like BeginRow; returns 1/0 with the per-handle error string set */
+int32_t duckdb_mb_gpu_append_arrow_batch(duckdb_mb_gpu_appender *a, const struct ArrowArray *batch,
+                                         const struct ArrowSchema *schema);
+int32_t duckdb_mb_gpu_appender_flush(duckdb_mb_gpu_appender *a); /* cf. duckdb_mb_flush :1237 */
+int32_t duckdb_mb_gpu_appender_close(duckdb_mb_gpu_appender *a);
+int32_t duckdb_mb_gpu_appender_timings(duckdb_mb_gpu_appender *a, double *out4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUCKDB_MB_GPU_H */
