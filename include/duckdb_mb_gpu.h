@@ -218,8 +218,10 @@ enum dmb_rev_op {
   DMB_REV_COUNT = 9
 };
 
-int32_t dmb_dev_rev_fixed_batch(const dmb_rev_fixed_job *jobs, int32_t njobs, int64_t nrows,
-                                void *stream);
+/* jobs_dev: device array, jobs_host: its host mirror.  Device copies of Arrow bitmaps / data
+ * buffers should carry >= 16 bytes of padding past their end. */
+int32_t dmb_dev_rev_fixed_batch(const dmb_rev_fixed_job *jobs_dev, const dmb_rev_fixed_job *jobs_host,
+                                int32_t njobs, int64_t nrows, void *stream);
 
 typedef struct dmb_rev_string_job {
   const void *in_offsets;       /* int32 (or int64 when large) offsets, at the slice start */
