@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""bench.py — DataChunk -> Arrow materialisation throughput (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows R]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1], the synthetic lineitem-shaped table
+(4 INTEGER, 4 DECIMAL(15,2), 3 DATE, 5 VARCHAR; 60 M rows per GPU, no NULLs) -> Arrow record batch.
+One step = one pass of the hot path over the whole table.  Row groups shard across GPUs with no
+data-path collective: every rank converts its own 60 M-row range, scaling "weak";
+torch.distributed (NCCL) is used for the barrier and the max-over-ranks timing only.
+
+  value      rows/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e        rows/s through the reference-facing C ABI (duckdb_mb_gpu_result_from_chunks +
+             _materialise_arrow) with page-locked HOST buffers, H2D + kernels + D2H in the timed region
+  roofline   the dominant kernel (string_batch_kernel): algorithmic bytes / its CUDA-event time
+  cpu_baseline  the oracle port of the reference's getters + decoders, 1 core, <= 1 M-row sample
+
+`--impl reference` times the reference's own CPU path (oracle port: the reference cannot be built
+here) on the host cores.  Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "datachunk_to_arrow_rows_per_s"
+UNIT = "rows/s"
+DEFAULT_ROWS = 60_000_000
+CPU_SAMPLE_ROWS = 1_000_000  # the reference's decoders return [] above this (src/duckdb_arrow_native.mbt:435)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- workload
+def build_c2_device(nrows: int, seed: int, device, host_heap_alloc=None):
+    """BASELINE.json configs[1] generated directly in HBM."""
+    import torch
+    from duckdb_mbt_b200 import chunks as ch
+    from duckdb_mbt_b200 import devgen
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    b = devgen.GeneratedBatch(nrows, device)
+    for nm in ("l_orderkey", "l_partkey", "l_suppkey", "l_linenumber"):
+        b.add_fixed(ch.T_INTEGER, 0, gen, 0.0, nm, lo=0, hi=2**31 - 1)
+    for nm in ("l_quantity", "l_extendedprice", "l_discount", "l_tax"):
+        b.add_fixed(ch.T_DECIMAL, 15, gen, 0.0, nm, lo=0, hi=10**7, dec_scale=2)
+    for nm in ("l_shipdate", "l_commitdate", "l_receiptdate"):
+        b.add_fixed(ch.T_DATE, 0, gen, 0.0, nm, lo=8035, hi=10592)
+    kw = dict(host_heap_alloc=host_heap_alloc)
+    b.add_string(gen, 0.0, 1, 1, name="l_returnflag", **kw)
+    b.add_string(gen, 0.0, 1, 1, name="l_linestatus", **kw)
+    b.add_string(gen, 0.0, 0, 0, name="l_shipinstruct", len_choices=[17, 11, 4, 16], **kw)
+    b.add_string(gen, 0.0, 0, 0, name="l_shipmode", len_choices=[7, 3, 4, 4, 5, 4, 3], **kw)
+    b.add_string(gen, 0.0, 10, 43, name="l_comment", **kw)
+    return b
+
+
+def arrow_dst(col):
+    from duckdb_mbt_b200 import chunks as ch
+    return ch.D_I128 if col.type_id == ch.T_DECIMAL else ch.D_SAME
+
+
+class DeviceStep:
+    """One pass of the hot path with inputs resident in HBM (device API, L0)."""
+
+    def __init__(self, db):
+        import torch
+        from duckdb_mbt_b200 import chunks as ch
+        self.torch = torch
+        self.db = db
+        cols = db.batch.columns
+        fixed = [j for j, c in enumerate(cols) if c.phys != ch.P_STRING]
+        strings = [j for j, c in enumerate(cols) if c.phys == ch.P_STRING]
+        specs = [(j, arrow_dst(cols[j])) for j in fixed] + [(j, ch.OP_VALIDITY_ONLY) for j in strings]
+        self.plan = db.plan_fixed(specs, bitmap=True)
+        self.strings = [db.plan_string(j, 0, data_capacity=db.meta[j]["total_len"]) for j in strings]
+        n = db.nrows
+        self.alg_fixed = db.alg_bytes_fixed(self.plan)
+        self.alg_string = sum(16 * n + db.meta[j]["ptr_len"] + 4 * (n + 1) + db.meta[j]["total_len"] for j in strings)
+        self.n_fixed_launches = len({o.op for o in self.plan[0]})
+        self.launches = self.n_fixed_launches + len(self.strings)
+        self.ev = None
+
+    def run(self, record=False):
+        torch = self.torch
+        if record:
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+        self.db.run_fixed(self.plan)
+        if record:
+            e1.record()
+        for so in self.strings:
+            self.db.run_string(so)
+        if record:
+            e2.record()
+            return e0, e1, e2
+        return None
+
+    def check(self):
+        for so in self.strings:
+            if self.db.string_error(so) != 0:
+                from duckdb_mbt_b200 import native as nat
+                raise RuntimeError("string kernel flagged an error: " + nat.last_error())
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_reference_pass(batch):
+    """The reference path on one result: duckdb_mb_arrow_get_column_* per column (the getter the
+    schema's type_id selects, src/duckdb_native.c:2314-2339) + the MoonBit decoder loops.
+    Returns seconds."""
+    import oracle
+    from duckdb_mbt_b200 import chunks as ch
+    t0 = time.perf_counter()
+    ora = oracle.OracleResult(batch)
+    for j, col in enumerate(batch.columns):
+        if col.type_id in (ch.T_TINYINT, ch.T_SMALLINT, ch.T_INTEGER):
+            oracle.decode_int32(ora.get_column("int32", j, True), True)
+        elif col.type_id == ch.T_BIGINT:
+            oracle.decode_int64_as_int(ora.get_column("int64", j, True), True)
+        elif col.type_id in (ch.T_FLOAT, ch.T_DOUBLE):
+            oracle.decode_double(ora.get_column("double", j, True), True)
+        elif col.type_id == ch.T_BOOLEAN:
+            oracle.decode_bool(ora.get_column("bool", j, True), True)
+        else:  # everything else is "string" in the reference's schema: duckdb_value_varchar per cell
+            blob = ora.get_column("string", j, True)
+            n = max(len(blob), 1)
+            import numpy as np
+            buf = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, np.uint8)
+            starts, ends, valid = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.uint8)
+            oracle.lib().ora_decode_string(buf.ctypes.data, len(blob), 1, starts.ctypes.data, ends.ctypes.data, valid.ctypes.data)
+    ora.close()
+    return time.perf_counter() - t0
+
+
+def _cpu_worker(args):
+    rows, seed, passes = args
+    from duckdb_mbt_b200 import chunks as ch
+    import oracle
+    oracle.lib()
+    batch = ch.config_c2(rows, seed=seed)
+    times = [cpu_reference_pass(batch) for _ in range(passes)]
+    return times
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    import concurrent.futures as cf
+    import oracle
+    oracle.build()
+    cores = max(1, min(os.cpu_count() or 1, env_int("DMB_REF_PROCS", 16)))
+    rows = min(args.rows, CPU_SAMPLE_ROWS)
+    passes = args.warmup + args.steps
+    with cf.ProcessPoolExecutor(max_workers=cores) as ex:
+        t0 = time.perf_counter()
+        results = list(ex.map(_cpu_worker, [(rows, 20260103 + i, passes) for i in range(cores)]))
+        wall = time.perf_counter() - t0
+    # every worker converts its own <= 1M-row result `steps` times; aggregate over the timed passes
+    per_worker = [sum(t[args.warmup:]) for t in results]
+    slowest = max(per_worker)
+    value = cores * rows * args.steps / slowest
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * slowest / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1]: lineitem-shaped table (4 INTEGER, 4 DECIMAL(15,2), 3 DATE, 5 VARCHAR) -> "
+                               "reference packed getters + MoonBit decoders", "rows_per_step": cores * rows,
+                   "note": "reference = CPU oracle port of src/duckdb_native.c:2357-2797 + src/duckdb_arrow_native.mbt:430-822 "
+                           "(MoonBit + libduckdb cannot be built in this image); one <=1M-row result per process (the decoders' cap), "
+                           f"{cores} processes"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} processes x {rows} rows x {args.steps} steps of the C2 table, generation untimed"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- ours
+def run_ours(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from duckdb_mbt_b200 import arrow_result as ar
+    from duckdb_mbt_b200 import native as nat
+    from duckdb_mbt_b200 import pinned
+
+    nat.lib()  # fails loudly when libduckdb_mb_gpu.so is missing: no fallback
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n = args.rows
+    e2e_rows = min(n, args.e2e_rows)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs, peak_src = (float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    # ---- inputs: generated in HBM; the e2e leg gets the same bytes in page-locked host slabs
+    pinned_arrays = []
+
+    def host_heap_alloc(nbytes):
+        a = pinned.pinned_empty(nbytes)
+        pinned_arrays.append(a)
+        return a
+
+    t_setup = time.perf_counter()
+    db = build_c2_device(n, 20260103 + rank, device, host_heap_alloc=host_heap_alloc if e2e_rows == n else None)
+    step = DeviceStep(db)
+    torch.cuda.synchronize(device)
+
+    # ---- value: device-resident, CUDA events on the launching (current) stream
+    for _ in range(args.warmup):
+        step.run()
+    step.check()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    spans = []
+    barrier()
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_a.record()
+    for _ in range(args.steps):
+        spans.append(step.run(record=True))
+    ev_b.record()
+    barrier()
+    dev_ms = ev_a.elapsed_time(ev_b)
+    clocks = sampler.stop() if rank == 0 else None
+    step.check()
+    fixed_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in spans) / args.steps
+    string_ms = sum(e1.elapsed_time(e2) for _, e1, e2 in spans) / args.steps
+    dev_ms_max = max_over_ranks(dev_ms)
+    value = world * n * args.steps / (dev_ms_max / 1e3)
+    step_alg_fixed, step_alg_string = step.alg_fixed, step.alg_string
+    alg_bytes = step_alg_fixed + step_alg_string
+    n_fixed_launches, n_string_launches = step.n_fixed_launches, len(step.strings)
+    n_launches = step.launches
+
+    # ---- e2e: host API, page-locked host buffers, H2D + kernels + D2H timed
+    if e2e_rows != n:
+        del step, db
+        torch.cuda.empty_cache()
+        db = build_c2_device(e2e_rows, 20260103 + rank, device, host_heap_alloc=host_heap_alloc)
+
+    def alloc(nb):
+        a = pinned.pinned_empty(nb)
+        pinned_arrays.append(a)
+        return a
+
+    host_batch = db.to_host_batch(alloc=alloc)
+    del db
+    if e2e_rows == n:
+        del step
+    torch.cuda.empty_cache()
+    setup_s = time.perf_counter() - t_setup
+    ctx = ar.GpuContext(local_rank)
+    hb = ar.HostBatch(host_batch, pinned=True)
+
+    def e2e_step():
+        h = ctx.lib.duckdb_mb_gpu_result_from_chunks(ctx.handle, C.byref(hb.struct))
+        if not h:
+            raise RuntimeError(nat.last_error())
+        res = ar.ArrowResult(ctx, h, hb)
+        res.materialise()
+        arr, sch = res.export_c(-1)  # the step's result: one record batch in page-locked host memory
+        rows_out = arr.length
+        t = res.timings()
+        ap_release(arr)
+        ap_release(sch)
+        res.close()
+        return rows_out, t
+
+    from duckdb_mbt_b200.appender import _release as ap_release
+    for _ in range(max(args.warmup, 1)):
+        rows_out, t_e2e = e2e_step()
+        assert rows_out == e2e_rows
+    barrier()
+    t0 = time.perf_counter()
+    kernels_ms = 0.0
+    for _ in range(args.steps):
+        rows_out, t_e2e = e2e_step()
+        kernels_ms += t_e2e["kernels_ms"]
+    ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s_max = max_over_ranks(e2e_s)
+    e2e_value = world * e2e_rows * args.steps / e2e_s_max
+    link_gbs = (t_e2e["h2d_bytes"] + t_e2e["d2h_bytes"]) * args.steps / e2e_s / 1e9
+    ctx.close()
+
+    # ---- cpu baseline (rank 0, N=1 only): oracle port, 1 core, <= 1M-row sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from duckdb_mbt_b200 import chunks as ch
+        import oracle
+        oracle.build()
+        sample = min(n, CPU_SAMPLE_ROWS)
+        cb = ch.config_c2(sample)
+        secs = cpu_reference_pass(cb)
+        cpu = {"value": sample / secs, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{sample} rows of the C2 table, one result (the reference decoders' 1M-row cap), "
+                         f"{secs:.2f} s: materialise + 16 packed getters + MoonBit decoder loops"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (string_batch_kernel: 5 launches per step)
+    dominant, dom_ms, dom_alg, dom_launches = "string_batch_kernel<utf8>", string_ms, step_alg_string, n_string_launches
+    if fixed_ms > string_ms:
+        dominant, dom_ms, dom_alg, dom_launches = "fixed_batch_kernel", fixed_ms, step_alg_fixed, n_fixed_launches
+    achieved = dom_alg / 1e6 / dom_ms  # GB/s: algorithmic bytes of the kernel's launches in a step / their device time
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("rows") == n and tj.get("kernel") == dominant:
+            traffic = tj.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1]: synthetic lineitem-shaped table (4 INTEGER, 4 DECIMAL(15,2)->decimal128, "
+                               "3 DATE, 5 VARCHAR: returnflag, linestatus, shipinstruct, shipmode, comment U[10,43]; no NULLs) "
+                               "-> Arrow record batch",
+                   "rows_per_gpu": n, "chunks_per_gpu": (n + 2047) // 2048, "parallelism": f"row-group shards x{world}, no collective",
+                   "l2": "inputs (~10.5 GB per GPU at 60M rows) far exceed the 126 MB L2: no flush between steps",
+                   "string_heap": "one contiguous heap per VARCHAR column, registered with the batch; pointers rebased in-kernel",
+                   "e2e_rows_per_gpu": e2e_rows},
+        "gb_per_s": world * alg_bytes * args.steps / (dev_ms_max / 1e3) / 1e9,
+        "algorithmic_bytes_per_step_per_gpu": alg_bytes,
+        "hbm_frac_whole_step": alg_bytes * args.steps / (dev_ms / 1e3) / 1e9 / peak_gbs,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(t_e2e["h2d_bytes"]),
+                "d2h_bytes_per_step": int(t_e2e["d2h_bytes"]), "ms_per_step": 1e3 * e2e_s_max / args.steps,
+                "link_gb_per_s_per_gpu": link_gbs, "kernels_ms_per_step": kernels_ms / args.steps,
+                "host_buffers": "page-locked (DMB_BATCH_PINNED), contiguous chunk slabs"},
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                     "launches_per_step": dom_launches, "algorithmic_bytes_per_launch": dom_alg / dom_launches,
+                     "avg_launch_ms": dom_ms / dom_launches},
+        "cpu_baseline": cpu,
+        "gpu_launches": n_launches * args.steps,
+        "clocks": clocks,
+        "kernel_ms_per_step": {"fixed_batch_kernel": fixed_ms, "string_batch_kernel": string_ms,
+                               "fixed_gb_per_s": step_alg_fixed / 1e6 / fixed_ms, "string_gb_per_s": step_alg_string / 1e6 / string_ms},
+        "setup_s": setup_s,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=env_int("DMB_BENCH_ROWS", DEFAULT_ROWS), help="rows per GPU")
+    ap.add_argument("--e2e-rows", type=int, default=env_int("DMB_BENCH_E2E_ROWS", DEFAULT_ROWS), help="rows per GPU for the host-buffer leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

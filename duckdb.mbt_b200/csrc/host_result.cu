@@ -1,0 +1,975 @@
+// L1 host API (duckdb_mb_gpu_result_*) and L2 drop-in symbols (duckdb_mb_arrow_*).
+//
+// A result holds what the reference keeps in `duckdb_mb_arrow_result` (src/duckdb_native.c:2211-2217:
+// the duckdb_result plus int32 column/row counts) in DataChunk form: per column, the pointers
+// duckdb_vector_get_data / duckdb_vector_get_validity return for each chunk.  Every export
+//   * stages the column to HBM (a few large cudaMemcpyAsync on the copy-in stream),
+//   * runs the conversion kernel of kernels_fixed.cu / kernels_string.cu on the compute stream,
+//   * copies the result into page-locked host memory on the copy-out stream,
+// column by column, so that copy-in of column j+1, the kernel of column j and copy-out of column
+// j-1 overlap (PCIe is full duplex; the kernels are ~100x faster than the link).
+//
+// There is no CPU fallback: without a CUDA device every entry point fails with an error string.
+
+#include <chrono>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "host_common.hpp"
+
+namespace dmb {
+namespace {
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// page-locked Arrow buffers of one column; exported ArrowArrays share ownership, so an exported
+// array stays valid after duckdb_mb_arrow_destroy / duckdb_mb_gpu_ctx_destroy
+struct ArrowColOut {
+  std::shared_ptr<CtxCore> core;
+  std::string name, format;
+  int64_t length = 0, null_count = 0;
+  void *validity = nullptr, *values = nullptr, *data = nullptr;  // values = offsets for utf8
+  size_t validity_bytes = 0, values_bytes = 0, data_bytes = 0;
+  ~ArrowColOut() {
+    if (!core) return;
+    core->pin.free(validity);
+    core->pin.free(values);
+    core->pin.free(data);
+  }
+};
+
+struct TypedOut {
+  bool ready = false;
+  int32_t tag = DMB_VALUE_NULL, width = 0;
+  int64_t null_count = 0;
+  void *values = nullptr, *valid = nullptr, *offsets = nullptr, *data = nullptr;  // pinned
+};
+
+struct Col {
+  std::string name;
+  int32_t type_id = 0, phys = 0, dec_width = 0, dec_scale = 0, width = 0;
+  std::vector<const void *> data;
+  std::vector<const void *> validity;  // entries may be NULL; empty = no masks at all
+  bool any_validity = false;
+  const uint8_t *heap_base = nullptr;
+  uint64_t heap_len = 0;
+  // device copy (lives as long as the result)
+  bool staged = false;
+  uint8_t *d_data = nullptr;
+  uint64_t *d_validity = nullptr;
+  dmb_vec_desc *d_vecs = nullptr;
+  uint8_t *d_heap = nullptr;
+  uint64_t heap_host_base = 0, d_heap_len = 0;
+  cudaEvent_t ev_staged = nullptr;
+  std::shared_ptr<ArrowColOut> arrow;
+  TypedOut typed;
+};
+
+}  // namespace
+}  // namespace dmb
+
+using namespace dmb;
+
+struct duckdb_mb_arrow_result {
+  std::shared_ptr<CtxCore> core;
+  int64_t nchunks = 0, nrows = 0;
+  int32_t column_count = 0, row_count = 0;  // (int32_t) casts like src/duckdb_native.c:2264-2265
+  bool pinned_input = false;
+  std::vector<uint32_t> counts;
+  std::vector<int64_t> row_off;
+  uint32_t *d_counts = nullptr;
+  int64_t *d_row_off = nullptr;
+  bool meta_staged = false;
+  std::vector<Col> cols;
+  std::vector<void *> dev_keep, pin_keep;  // staged inputs / typed outputs: freed when the result dies
+  std::vector<cudaEvent_t> events;
+  bool arrow_ready = false;
+  double t_h2d = 0, t_kernels = 0, t_d2h = 0, t_total = 0;
+  uint64_t bytes_h2d = 0, bytes_d2h = 0;
+};
+
+namespace dmb {
+namespace {
+
+typedef duckdb_mb_arrow_result Result;
+
+void *keep_dev(Result *r, size_t bytes) {
+  void *p = r->core->dev.alloc(bytes + 64);
+  if (p) r->dev_keep.push_back(p);
+  return p;
+}
+void *keep_pin(Result *r, size_t bytes) {
+  void *p = r->core->pin.alloc(bytes + 64);
+  if (p) r->pin_keep.push_back(p);
+  return p;
+}
+
+void free_result(Result *r) {
+  if (!r) return;
+  CtxCore &c = *r->core;
+  {
+    std::lock_guard<std::mutex> g(c.mu);
+    c.bind();
+    cudaStreamSynchronize(c.s_in);
+    cudaStreamSynchronize(c.s_compute);
+    cudaStreamSynchronize(c.s_out);
+    for (void *p : r->dev_keep) c.dev.free(p);
+    for (void *p : r->pin_keep) c.pin.free(p);
+    for (cudaEvent_t e : r->events) cudaEventDestroy(e);
+    r->cols.clear();  // ArrowColOut buffers go back to the pinned pool unless an export still holds them
+  }
+  delete r;
+}
+
+int32_t ensure_meta(Result *r) {
+  if (r->meta_staged) return 0;
+  CtxCore &c = *r->core;
+  const size_t nb_counts = sizeof(uint32_t) * (size_t)(r->nchunks > 0 ? r->nchunks : 1);
+  const size_t nb_off = sizeof(int64_t) * (size_t)(r->nchunks + 1);
+  r->d_counts = (uint32_t *)keep_dev(r, nb_counts);
+  r->d_row_off = (int64_t *)keep_dev(r, nb_off);
+  uint8_t *pin = (uint8_t *)keep_pin(r, nb_counts + nb_off);
+  if (!r->d_counts || !r->d_row_off || !pin) return -1;
+  if (r->nchunks) memcpy(pin, r->counts.data(), sizeof(uint32_t) * (size_t)r->nchunks);
+  memcpy(pin + nb_counts, r->row_off.data(), nb_off);
+  if (check_cuda(cudaMemcpyAsync(r->d_counts, pin, nb_counts, cudaMemcpyHostToDevice, c.s_in), "counts H2D")) return -1;
+  if (check_cuda(cudaMemcpyAsync(r->d_row_off, pin + nb_counts, nb_off, cudaMemcpyHostToDevice, c.s_in), "row_off H2D")) return -1;
+  r->bytes_h2d += nb_counts + nb_off;
+  r->meta_staged = true;
+  return 0;
+}
+
+struct CompactCtx {  // string columns whose heap is scattered: compact into a pinned arena
+  const Col *col;
+  const uint64_t *arena_start;  // [nchunks+1] byte offset of chunk k's strings in the arena
+  uint8_t *arena;
+  uint64_t fake_base;
+};
+
+inline bool host_row_valid(const void *mask, uint32_t row) {
+  if (!mask) return true;
+  return (reinterpret_cast<const uint64_t *>(mask)[row >> 6] >> (row & 63)) & 1ull;
+}
+
+void compact_fixup(void *user, int64_t k, uint8_t *staged, size_t bytes) {
+  CompactCtx *cc = reinterpret_cast<CompactCtx *>(user);
+  dmb_string_t *e = reinterpret_cast<dmb_string_t *>(staged);
+  const uint32_t n = (uint32_t)(bytes / sizeof(dmb_string_t));
+  const void *mask = cc->col->validity.empty() ? nullptr : cc->col->validity[(size_t)k];
+  uint64_t pos = cc->arena_start[k];
+  for (uint32_t i = 0; i < n; ++i) {
+    if (!host_row_valid(mask, i)) continue;  // payload under a NULL row is unspecified: never dereference it
+    const uint32_t len = e[i].length;
+    if (len <= 12) continue;
+    memcpy(cc->arena + pos, reinterpret_cast<const void *>((uintptr_t)e[i].value.ptr.ptr), len);
+    e[i].value.ptr.ptr = cc->fake_base + pos;
+    pos += len;
+  }
+}
+
+// copy one column's chunk vectors (payload, validity masks, descriptors, string heap) to HBM
+int32_t stage_column(Result *r, int j) {
+  Col &col = r->cols[(size_t)j];
+  if (col.staged) return 0;
+  if (ensure_meta(r)) return -1;
+  CtxCore &c = *r->core;
+  const int64_t nch = r->nchunks;
+  const size_t nslots = (size_t)(nch > 0 ? nch : 1);
+  const size_t slot = (size_t)DMB_VECTOR_SIZE * (size_t)col.width;
+  col.d_data = (uint8_t *)keep_dev(r, slot * nslots + 16);
+  if (!col.d_data) return -1;
+  if (col.any_validity) {
+    col.d_validity = (uint64_t *)keep_dev(r, 8 * (size_t)DMB_VALIDITY_WORDS * nslots + 16);
+    if (!col.d_validity) return -1;
+  }
+  dmb_vec_desc *pv = (dmb_vec_desc *)keep_pin(r, sizeof(dmb_vec_desc) * nslots);
+  col.d_vecs = (dmb_vec_desc *)keep_dev(r, sizeof(dmb_vec_desc) * nslots);
+  if (!pv || !col.d_vecs) return -1;
+  for (int64_t k = 0; k < nch; ++k) {
+    pv[k].data_off = (uint64_t)k * slot;
+    pv[k].val_off = (col.any_validity && col.validity[(size_t)k]) ? k * DMB_VALIDITY_WORDS : -1;
+  }
+  if (nch && check_cuda(cudaMemcpyAsync(col.d_vecs, pv, sizeof(dmb_vec_desc) * (size_t)nch, cudaMemcpyHostToDevice, c.s_in), "vec desc H2D")) return -1;
+  r->bytes_h2d += sizeof(dmb_vec_desc) * (size_t)nch;
+
+  stage_fixup_fn fixup = nullptr;
+  CompactCtx cc{};
+  std::vector<uint64_t> arena_start;
+  if (col.phys == DMB_PHYS_STRING) {
+    if (col.heap_len > 0 && col.heap_base) {
+      // contiguous heap registered by the caller: copy wholesale, rebase pointers in the kernel
+      col.d_heap = (uint8_t *)keep_dev(r, (size_t)col.heap_len + 32);
+      if (!col.d_heap) return -1;
+      if (stage_contiguous(c, c.s_in, col.d_heap, col.heap_base, (size_t)col.heap_len, r->pinned_input ? 1 : 0, &r->bytes_h2d)) return -1;
+      col.heap_host_base = (uint64_t)(uintptr_t)col.heap_base;
+      col.d_heap_len = col.heap_len;
+    } else {
+      // scattered heap: size pass, then gather into a pinned arena while the string_t are staged
+      arena_start.assign((size_t)nch + 1, 0);
+      parallel_for(nch, c.stage_threads, [&](int64_t k) {
+        const dmb_string_t *e = reinterpret_cast<const dmb_string_t *>(col.data[(size_t)k]);
+        const void *mask = col.validity.empty() ? nullptr : col.validity[(size_t)k];
+        uint64_t sum = 0;
+        for (uint32_t i = 0; e && i < r->counts[(size_t)k]; ++i)
+          if (host_row_valid(mask, i) && e[i].length > 12) sum += e[i].length;
+        arena_start[(size_t)k + 1] = sum;
+      });
+      for (int64_t k = 0; k < nch; ++k) arena_start[(size_t)k + 1] += arena_start[(size_t)k];
+      const uint64_t total = arena_start[(size_t)nch];
+      uint8_t *arena = (uint8_t *)keep_pin(r, (size_t)total + 32);
+      col.d_heap = (uint8_t *)keep_dev(r, (size_t)total + 32);
+      if (!arena || !col.d_heap) return -1;
+      col.heap_host_base = 1ull << 40;
+      col.d_heap_len = total;
+      cc.col = &col;
+      cc.arena_start = arena_start.data();
+      cc.arena = arena;
+      cc.fake_base = col.heap_host_base;
+      fixup = compact_fixup;
+    }
+  }
+  if (nch && stage_pieces(c, c.s_in, col.data.data(), r->counts.data(), (size_t)col.width, slot, nch, col.d_data,
+                          r->pinned_input, fixup, &cc, &r->bytes_h2d)) return -1;
+  if (fixup && arena_start[(size_t)nch]) {
+    // every piece was gathered (host side) before its ring copy was issued, so the arena is complete
+    if (check_cuda(cudaMemcpyAsync(col.d_heap, cc.arena, (size_t)arena_start[(size_t)nch], cudaMemcpyHostToDevice, c.s_in), "string arena H2D")) return -1;
+    r->bytes_h2d += arena_start[(size_t)nch];
+  }
+  if (col.any_validity && nch) {
+    if (stage_pieces(c, c.s_in, col.validity.data(), nullptr, 0, 8 * (size_t)DMB_VALIDITY_WORDS, nch,
+                     (uint8_t *)col.d_validity, r->pinned_input, nullptr, nullptr, &r->bytes_h2d)) return -1;
+  }
+  cudaEvent_t e = nullptr;
+  if (check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) return -1;
+  r->events.push_back(e);
+  col.ev_staged = e;
+  if (check_cuda(cudaEventRecord(col.ev_staged, c.s_in), "event record")) return -1;
+  col.staged = true;
+  return 0;
+}
+
+// upload one job struct; the device copy is consumed by the next launch on s_compute
+void *upload_job(Scope &sc, const void *job, size_t bytes) {
+  void *hp = sc.palloc(bytes), *dp = sc.dalloc(bytes);
+  if (!hp || !dp) return nullptr;
+  memcpy(hp, job, bytes);
+  if (check_cuda(cudaMemcpyAsync(dp, hp, bytes, cudaMemcpyHostToDevice, sc.c.s_compute), "job H2D")) return nullptr;
+  return dp;
+}
+
+struct FixedRun {
+  uint8_t *d_values = nullptr;
+  size_t values_bytes = 0;
+  uint64_t *d_bitmap = nullptr;
+  size_t bitmap_bytes = 0;
+  uint8_t *d_valid_bytes = nullptr;
+  unsigned long long *d_null_count = nullptr;
+  cudaEvent_t done = nullptr;
+};
+
+// launch one fixed-width conversion of column j on the compute stream (after its staging).
+// op == DMB_OP_VALIDITY_ONLY or an unsupported (phys,dst) pair with zero_width > 0: only the
+// validity outputs are produced and the values are `zero_width` zero bytes per row.
+int32_t run_fixed(Result *r, Scope &sc, int j, int32_t op, int zero_width, bool want_bitmap, bool want_valid_bytes,
+                  FixedRun *out) {
+  if (stage_column(r, j)) return -1;
+  CtxCore &c = *r->core;
+  Col &col = r->cols[(size_t)j];
+  const int64_t n = r->nrows;
+  int32_t w = -2;
+  if (op != DMB_OP_VALIDITY_ONLY) {
+    w = dmb_op_out_width(op);
+    if (w < 0 && zero_width <= 0) { set_error("unsupported conversion op 0x%x for column %d", op, j); return -1; }
+  }
+  if (w >= 0) {
+    out->values_bytes = w == 0 ? (size_t)((n + 7) / 8) : (size_t)n * (size_t)w;
+    out->d_values = (uint8_t *)sc.dalloc(out->values_bytes + 64);
+    if (!out->d_values) return -1;
+  } else if (zero_width > 0) {
+    out->values_bytes = (size_t)n * (size_t)zero_width;
+    out->d_values = (uint8_t *)sc.dalloc(out->values_bytes + 64);
+    if (!out->d_values) return -1;
+    if (check_cuda(cudaMemsetAsync(out->d_values, 0, out->values_bytes, c.s_compute), "zero values")) return -1;
+    op = DMB_OP_VALIDITY_ONLY;
+  }
+  if (want_bitmap) {
+    out->bitmap_bytes = (size_t)((n + 63) / 64) * 8;
+    out->d_bitmap = (uint64_t *)sc.dalloc(out->bitmap_bytes + 64);
+    if (!out->d_bitmap) return -1;
+  }
+  if (want_valid_bytes) {
+    out->d_valid_bytes = (uint8_t *)sc.dalloc((size_t)n + 64);
+    if (!out->d_valid_bytes) return -1;
+  }
+  out->d_null_count = (unsigned long long *)sc.dalloc(8);
+  if (!out->d_null_count) return -1;
+  if (check_cuda(cudaMemsetAsync(out->d_null_count, 0, 8, c.s_compute), "counter memset")) return -1;
+  dmb_fixed_job job;
+  memset(&job, 0, sizeof(job));
+  job.in_data = col.d_data;
+  job.in_validity = col.d_validity;
+  job.vecs = col.d_vecs;
+  job.out_values = op == DMB_OP_VALIDITY_ONLY ? nullptr : out->d_values;
+  job.out_validity = out->d_bitmap;
+  job.out_valid_bytes = out->d_valid_bytes;
+  job.null_count = out->d_null_count;
+  job.op = op;
+  if (check_cuda(cudaStreamWaitEvent(c.s_compute, col.ev_staged, 0), "wait staged")) return -1;
+  void *jd = upload_job(sc, &job, sizeof(job));
+  if (!jd) return -1;
+  cudaEvent_t k0 = sc.event(true), k1 = sc.event(true);
+  if (!k0 || !k1) return -1;
+  cudaEventRecord(k0, c.s_compute);
+  if (dmb_dev_fixed_batch((const dmb_fixed_job *)jd, &job, 1, r->d_counts, r->d_row_off, r->nchunks, n, c.s_compute)) return -1;
+  cudaEventRecord(k1, c.s_compute);
+  sc.kernel_spans.emplace_back(k0, k1);
+  out->done = k1;
+  return 0;
+}
+
+struct StringRun {
+  void *d_offsets = nullptr;
+  size_t offsets_bytes = 0;
+  uint8_t *d_data = nullptr;
+  size_t data_cap = 0;
+  FixedRun validity;  // bitmap / valid bytes / null count come from the fixed kernel's tile phase
+  void *d_scratch = nullptr;
+  unsigned long long *d_total = nullptr;
+  unsigned long long *h_ctr = nullptr;  // pinned: [0] total bytes [1] error flags [2] null count
+  int mode = 0;
+  cudaEvent_t done = nullptr;  // kernel + the small counter copies
+};
+
+int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool want_valid_bytes, StringRun *out) {
+  if (stage_column(r, j)) return -1;
+  CtxCore &c = *r->core;
+  Col &col = r->cols[(size_t)j];
+  const int64_t n = r->nrows;
+  out->mode = mode;
+  out->offsets_bytes = (size_t)(n + 1) * (mode == DMB_STR_ARROW_LARGE ? 8 : 4);
+  out->d_offsets = sc.dalloc(out->offsets_bytes + 64);
+  out->data_cap = (size_t)12 * (size_t)n + (size_t)col.d_heap_len + (mode == DMB_STR_REF_BLOB ? (size_t)n : 0);
+  out->d_data = (uint8_t *)sc.dalloc(out->data_cap + 64);
+  out->d_scratch = sc.dalloc(dmb_dev_string_scratch_bytes(r->nchunks));
+  out->d_total = (unsigned long long *)sc.dalloc(8);
+  out->h_ctr = (unsigned long long *)sc.palloc(32);
+  if (!out->d_offsets || !out->d_data || !out->d_scratch || !out->d_total || !out->h_ctr) return -1;
+  memset(out->h_ctr, 0, 32);
+  // validity outputs + null count (the count is always needed: the reference blob's length depends on it)
+  if (run_fixed(r, sc, j, DMB_OP_VALIDITY_ONLY, 0, want_bitmap, want_valid_bytes, &out->validity)) return -1;
+  if (check_cuda(cudaMemsetAsync(out->d_total, 0, 8, c.s_compute), "total memset")) return -1;
+  dmb_string_job job;
+  memset(&job, 0, sizeof(job));
+  job.in = (const dmb_string_t *)col.d_data;
+  job.in_validity = col.d_validity;
+  job.vecs = col.d_vecs;
+  job.heap_dev = col.d_heap;
+  job.heap_host_base = col.heap_host_base;
+  job.heap_len = col.d_heap_len;
+  job.out_offsets = out->d_offsets;
+  job.out_data = out->d_data;
+  job.total_bytes = out->d_total;
+  job.mode = mode;
+  cudaEvent_t k0 = sc.event(true), k1 = sc.event(true), done = sc.event(false);
+  if (!k0 || !k1 || !done) return -1;
+  cudaEventRecord(k0, c.s_compute);
+  if (dmb_dev_string_batch(&job, r->d_counts, r->d_row_off, r->nchunks, n, out->d_scratch, c.s_compute)) return -1;
+  cudaEventRecord(k1, c.s_compute);
+  sc.kernel_spans.emplace_back(k0, k1);
+  // the data length is needed on the host to size the device->host copy; flags travel with it
+  if (check_cuda(cudaMemcpyAsync(out->h_ctr + 0, out->d_total, 8, cudaMemcpyDeviceToHost, c.s_compute), "string total D2H")) return -1;
+  if (n > 0 && check_cuda(cudaMemcpyAsync(out->h_ctr + 1, (unsigned long long *)out->d_scratch + 1, 8, cudaMemcpyDeviceToHost, c.s_compute), "string flags D2H")) return -1;
+  if (check_cuda(cudaMemcpyAsync(out->h_ctr + 2, out->validity.d_null_count, 8, cudaMemcpyDeviceToHost, c.s_compute), "null count D2H")) return -1;
+  cudaEventRecord(done, c.s_compute);
+  out->done = done;
+  return 0;
+}
+
+int32_t string_flags_error(unsigned long long flags) {
+  if (!flags) return 0;
+  if (flags & 4) set_error("string_t pointer outside the registered heap");
+  else if (flags & 2) set_error("utf8 data exceeds int32 offsets");
+  else set_error("a 1024-row tile holds more than 4 GiB of string bytes");
+  return -1;
+}
+
+// ------------------------------------------------------------------ DuckDB type -> Arrow
+struct ArrowMap {
+  int32_t op = -1;      // fixed-width conversion, or -1 for strings
+  bool is_string = false;
+  std::string format;
+};
+
+bool arrow_map(const Col &col, ArrowMap *m) {
+  char buf[48];
+  auto same = [&](const char *fmt) { m->op = DMB_OP(col.phys, DMB_DST_SAME); m->format = fmt; return true; };
+  switch (col.type_id) {
+    case DMB_TYPE_BOOLEAN: m->op = DMB_OP(DMB_PHYS_BOOL, DMB_DST_BOOL_BITS); m->format = "b"; return true;
+    case DMB_TYPE_TINYINT: return same("c");
+    case DMB_TYPE_SMALLINT: return same("s");
+    case DMB_TYPE_INTEGER: return same("i");
+    case DMB_TYPE_BIGINT: return same("l");
+    case DMB_TYPE_UTINYINT: return same("C");
+    case DMB_TYPE_USMALLINT: return same("S");
+    case DMB_TYPE_UINTEGER: return same("I");
+    case DMB_TYPE_UBIGINT: return same("L");
+    case DMB_TYPE_FLOAT: return same("f");
+    case DMB_TYPE_DOUBLE: return same("g");
+    case DMB_TYPE_DATE: return same("tdD");
+    case DMB_TYPE_TIME: return same("ttu");
+    case DMB_TYPE_TIME_NS: return same("ttn");
+    case DMB_TYPE_TIME_TZ: return same("L");  // packed micros|offset bits, as stored
+    case DMB_TYPE_TIMESTAMP: return same("tsu:");
+    case DMB_TYPE_TIMESTAMP_TZ: return same("tsu:UTC");
+    case DMB_TYPE_TIMESTAMP_S: return same("tss:");
+    case DMB_TYPE_TIMESTAMP_MS: return same("tsm:");
+    case DMB_TYPE_TIMESTAMP_NS: return same("tsn:");
+    case DMB_TYPE_INTERVAL: m->op = DMB_OP(DMB_PHYS_INTERVAL, DMB_DST_MONTH_DAY_NANO); m->format = "tin"; return true;
+    case DMB_TYPE_HUGEINT: m->op = DMB_OP(DMB_PHYS_I128, DMB_DST_I128); m->format = "d:38,0"; return true;
+    case DMB_TYPE_UHUGEINT:
+    case DMB_TYPE_UUID: m->op = DMB_OP(DMB_PHYS_U128, DMB_DST_SAME); m->format = "w:16"; return true;
+    case DMB_TYPE_DECIMAL:
+      m->op = DMB_OP(col.phys, DMB_DST_I128);
+      snprintf(buf, sizeof(buf), "d:%d,%d", col.dec_width > 0 ? col.dec_width : 38, col.dec_scale);
+      m->format = buf;
+      return true;
+    case DMB_TYPE_VARCHAR: m->is_string = true; m->format = "u"; return true;
+    case DMB_TYPE_BLOB: m->is_string = true; m->format = "z"; return true;
+    default: set_error("column type %d has no Arrow mapping", col.type_id); return false;
+  }
+}
+
+struct Pending {  // one column between its kernel launch and its device->host copies
+  ArrowMap map;
+  FixedRun fr;
+  StringRun sr;
+  std::shared_ptr<ArrowColOut> out;
+  unsigned long long *h_null = nullptr;
+};
+
+int32_t launch_arrow_col(Result *r, Scope &sc, int j, int string_mode, Pending *p) {
+  Col &col = r->cols[(size_t)j];
+  if (!arrow_map(col, &p->map)) return -1;
+  p->out = std::make_shared<ArrowColOut>();
+  p->out->core = r->core;
+  p->out->name = col.name;
+  p->out->length = r->nrows;
+  if (p->map.is_string) {
+    p->sr = StringRun();
+    if (run_string(r, sc, j, string_mode, true, false, &p->sr)) return -1;
+    p->out->format = string_mode == DMB_STR_ARROW_LARGE ? (col.type_id == DMB_TYPE_BLOB ? "Z" : "U") : p->map.format;
+  } else {
+    p->fr = FixedRun();
+    if (run_fixed(r, sc, j, p->map.op, 0, true, false, &p->fr)) return -1;
+    p->out->format = p->map.format;
+  }
+  return 0;
+}
+
+// enqueue the device->host copies of a launched column on the copy-out stream.
+// Returns 1 when a utf8 column overflowed int32 offsets and must be relaunched with large offsets.
+int32_t drain_arrow_col(Result *r, Scope &sc, Pending *p) {
+  CtxCore &c = *r->core;
+  ArrowColOut &o = *p->out;
+  const int64_t n = r->nrows;
+  if (p->map.is_string) {
+    StringRun &s = p->sr;
+    if (check_cuda(cudaEventSynchronize(s.done), "string kernel wait")) return -1;
+    if (s.h_ctr[1] & 2ull) {
+      if (s.mode == DMB_STR_ARROW_UTF8) return 1;
+    }
+    if (string_flags_error(s.h_ctr[1])) return -1;
+    const size_t total = (size_t)s.h_ctr[0];
+    o.values_bytes = s.offsets_bytes;
+    o.validity_bytes = s.validity.bitmap_bytes;
+    o.data_bytes = total;
+    o.values = c.pin.alloc(o.values_bytes + 64);
+    o.validity = c.pin.alloc(o.validity_bytes + 64);
+    o.data = c.pin.alloc(total + 64);
+    if (!o.values || !o.validity || !o.data) return -1;
+    o.null_count = (int64_t)s.h_ctr[2];
+    if (n == 0) {
+      memset(o.values, 0, o.values_bytes);
+      return 0;
+    }
+    if (check_cuda(cudaStreamWaitEvent(c.s_out, s.done, 0), "wait kernel")) return -1;
+    if (check_cuda(cudaMemcpyAsync(o.values, s.d_offsets, o.values_bytes, cudaMemcpyDeviceToHost, c.s_out), "offsets D2H")) return -1;
+    if (total && check_cuda(cudaMemcpyAsync(o.data, s.d_data, total, cudaMemcpyDeviceToHost, c.s_out), "utf8 data D2H")) return -1;
+    if (o.validity_bytes && check_cuda(cudaMemcpyAsync(o.validity, s.validity.d_bitmap, o.validity_bytes, cudaMemcpyDeviceToHost, c.s_out), "bitmap D2H")) return -1;
+    r->bytes_d2h += o.values_bytes + total + o.validity_bytes;
+    return 0;
+  }
+  FixedRun &f = p->fr;
+  o.values_bytes = f.values_bytes;
+  o.validity_bytes = f.bitmap_bytes;
+  o.values = c.pin.alloc(o.values_bytes + 64);
+  o.validity = c.pin.alloc(o.validity_bytes + 64);
+  p->h_null = (unsigned long long *)sc.palloc(8);
+  if (!o.values || !o.validity || !p->h_null) return -1;
+  *p->h_null = 0;
+  if (n == 0) return 0;
+  if (check_cuda(cudaStreamWaitEvent(c.s_out, f.done, 0), "wait kernel")) return -1;
+  if (o.values_bytes && check_cuda(cudaMemcpyAsync(o.values, f.d_values, o.values_bytes, cudaMemcpyDeviceToHost, c.s_out), "values D2H")) return -1;
+  if (o.validity_bytes && check_cuda(cudaMemcpyAsync(o.validity, f.d_bitmap, o.validity_bytes, cudaMemcpyDeviceToHost, c.s_out), "bitmap D2H")) return -1;
+  if (check_cuda(cudaMemcpyAsync(p->h_null, f.d_null_count, 8, cudaMemcpyDeviceToHost, c.s_out), "null count D2H")) return -1;
+  r->bytes_d2h += o.values_bytes + o.validity_bytes + 8;
+  return 0;
+}
+
+int32_t materialise_arrow(Result *r) {
+  if (r->arrow_ready) return 0;
+  CtxCore &c = *r->core;
+  if (!c.bind()) return -1;
+  const double t0 = now_ms();
+  const int ncols = (int)r->cols.size();
+  {
+    std::vector<Pending> pend((size_t)ncols);  // declared first: the Scope drains the streams before these die
+    Scope sc(c);
+    cudaEvent_t in0 = sc.event(true), in1 = sc.event(true), out0 = sc.event(true), out1 = sc.event(true);
+    if (!in0 || !in1 || !out0 || !out1) return -1;
+    r->bytes_h2d = 0;
+    r->bytes_d2h = 0;
+    const bool restage = !r->meta_staged;
+    cudaEventRecord(in0, c.s_in);
+    cudaEventRecord(out0, c.s_out);
+    auto drain = [&](int j) -> int32_t {
+      int32_t rc = drain_arrow_col(r, sc, &pend[(size_t)j]);
+      if (rc == 1) {  // utf8 offsets overflowed: redo this column with 64-bit offsets
+        pend[(size_t)j] = Pending();
+        if (launch_arrow_col(r, sc, j, DMB_STR_ARROW_LARGE, &pend[(size_t)j])) return -1;
+        rc = drain_arrow_col(r, sc, &pend[(size_t)j]);
+      }
+      return rc;
+    };
+    for (int j = 0; j < ncols; ++j) {
+      const Col &col = r->cols[(size_t)j];
+      const bool surely_large = col.phys == DMB_PHYS_STRING && col.heap_len > 0x7fffffffull;
+      if (launch_arrow_col(r, sc, j, surely_large ? DMB_STR_ARROW_LARGE : DMB_STR_ARROW_UTF8, &pend[(size_t)j])) return -1;
+      if (j > 0 && drain(j - 1)) return -1;
+    }
+    cudaEventRecord(in1, c.s_in);
+    if (ncols > 0 && drain(ncols - 1)) return -1;
+    cudaEventRecord(out1, c.s_out);
+    if (check_cuda(cudaStreamSynchronize(c.s_in), "sync copy-in") || check_cuda(cudaStreamSynchronize(c.s_compute), "sync compute") ||
+        check_cuda(cudaStreamSynchronize(c.s_out), "sync copy-out"))
+      return -1;
+    for (int j = 0; j < ncols; ++j) {
+      Pending &p = pend[(size_t)j];
+      if (!p.map.is_string && p.h_null) p.out->null_count = (int64_t)*p.h_null;
+      r->cols[(size_t)j].arrow = p.out;
+    }
+    float f = 0;
+    r->t_h2d = (restage && cudaEventElapsedTime(&f, in0, in1) == cudaSuccess) ? f : 0;
+    r->t_d2h = cudaEventElapsedTime(&f, out0, out1) == cudaSuccess ? f : 0;
+    r->t_kernels = sc.kernel_ms();
+  }
+  r->t_total = now_ms() - t0;
+  r->arrow_ready = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------ Arrow C Data export
+struct ExportPriv {
+  std::vector<std::shared_ptr<ArrowColOut>> cols;
+  const void *buffers[3] = {nullptr, nullptr, nullptr};
+  std::vector<ArrowArray *> child_arrays;
+  std::vector<ArrowSchema *> child_schemas;
+  std::string format, name;
+};
+
+void release_array(ArrowArray *a) {
+  if (!a || !a->release) return;
+  ExportPriv *p = reinterpret_cast<ExportPriv *>(a->private_data);
+  for (ArrowArray *ch : p->child_arrays) {
+    if (ch->release) ch->release(ch);
+    free(ch);
+  }
+  delete p;
+  a->release = nullptr;
+}
+
+void release_schema(ArrowSchema *s) {
+  if (!s || !s->release) return;
+  ExportPriv *p = reinterpret_cast<ExportPriv *>(s->private_data);
+  for (ArrowSchema *ch : p->child_schemas) {
+    if (ch->release) ch->release(ch);
+    free(ch);
+  }
+  delete p;
+  s->release = nullptr;
+}
+
+void export_column(const std::shared_ptr<ArrowColOut> &o, ArrowArray *a, ArrowSchema *s) {
+  if (a) {
+    ExportPriv *p = new ExportPriv();
+    p->cols.push_back(o);
+    memset(a, 0, sizeof(*a));
+    a->length = o->length;
+    a->null_count = o->null_count;
+    a->offset = 0;
+    p->buffers[0] = o->validity;
+    p->buffers[1] = o->values;
+    p->buffers[2] = o->data;
+    a->n_buffers = o->data ? 3 : 2;
+    a->buffers = p->buffers;
+    a->release = release_array;
+    a->private_data = p;
+  }
+  if (s) {
+    ExportPriv *p = new ExportPriv();
+    p->format = o->format;
+    p->name = o->name;
+    memset(s, 0, sizeof(*s));
+    s->format = p->format.c_str();
+    s->name = p->name.c_str();
+    s->flags = 2;  // ARROW_FLAG_NULLABLE
+    s->release = release_schema;
+    s->private_data = p;
+  }
+}
+
+// ------------------------------------------------------------------ typed columns
+struct TypedMap {
+  int32_t tag, op, width;
+};
+
+bool typed_map(const Col &col, TypedMap *m) {
+  auto set = [&](int32_t tag, int32_t dst, int32_t width) { m->tag = tag; m->op = DMB_OP(col.phys, dst); m->width = width; return true; };
+  switch (col.type_id) {
+    case DMB_TYPE_BOOLEAN: return set(DMB_VALUE_BOOL, DMB_DST_BOOL_BYTE, 1);
+    case DMB_TYPE_TINYINT: case DMB_TYPE_SMALLINT: case DMB_TYPE_INTEGER: case DMB_TYPE_BIGINT:
+    case DMB_TYPE_UTINYINT: case DMB_TYPE_USMALLINT: case DMB_TYPE_UINTEGER: case DMB_TYPE_UBIGINT:
+      return set(DMB_VALUE_INT, DMB_DST_I32_SAT, 4);  // src/duckdb_parsing.mbt:88-99 -> parse_int :203-237
+    case DMB_TYPE_FLOAT: case DMB_TYPE_DOUBLE: return set(DMB_VALUE_DOUBLE, DMB_DST_F64, 8);
+    case DMB_TYPE_DATE: return set(DMB_VALUE_DATE, DMB_DST_DATE_REF, 4);
+    // parse_timestamp semantics (src/duckdb_parsing.mbt:375-398), including the day-number quirk
+    case DMB_TYPE_TIMESTAMP: case DMB_TYPE_TIMESTAMP_TZ: return set(DMB_VALUE_TIMESTAMP, DMB_DST_TS_REF, 8);
+    case DMB_TYPE_TIMESTAMP_S: return set(DMB_VALUE_TIMESTAMP, DMB_DST_TS_REF_FROM_S, 8);
+    case DMB_TYPE_TIMESTAMP_MS: return set(DMB_VALUE_TIMESTAMP, DMB_DST_TS_REF_FROM_MS, 8);
+    case DMB_TYPE_TIMESTAMP_NS: return set(DMB_VALUE_TIMESTAMP, DMB_DST_TS_REF_FROM_NS, 8);
+    case DMB_TYPE_VARCHAR: m->tag = DMB_VALUE_STRING; m->op = -1; m->width = 0; return true;
+    default:
+      // DECIMAL, HUGEINT, UHUGEINT, INTERVAL, TIME*, BLOB, UUID stay Value::String (libduckdb's
+      // text rendering) in the reference, src/duckdb_parsing.mbt:120-141
+      set_error("column type %d is a text-rendered Value::String in the reference; no typed column form", col.type_id);
+      return false;
+  }
+}
+
+int32_t typed_column(Result *r, int j, dmb_typed_column *out) {
+  Col &col = r->cols[(size_t)j];
+  CtxCore &c = *r->core;
+  if (!c.bind()) return -1;
+  const int64_t n = r->nrows;
+  if (!col.typed.ready) {
+    TypedMap m;
+    if (!typed_map(col, &m)) return -1;
+    Scope sc(c);
+    TypedOut &t = col.typed;
+    t.tag = m.tag;
+    t.width = m.width;
+    t.valid = keep_pin(r, (size_t)n);
+    if (!t.valid) return -1;
+    if (m.op < 0) {
+      StringRun s;
+      if (run_string(r, sc, j, DMB_STR_ARROW_UTF8, false, true, &s)) return -1;
+      if (check_cuda(cudaEventSynchronize(s.done), "string kernel wait")) return -1;
+      if (string_flags_error(s.h_ctr[1])) return -1;
+      const size_t total = (size_t)s.h_ctr[0];
+      t.offsets = keep_pin(r, s.offsets_bytes);
+      t.data = keep_pin(r, total);
+      if (!t.offsets || !t.data) return -1;
+      if (n == 0) memset(t.offsets, 0, s.offsets_bytes);
+      if (n && check_cuda(cudaMemcpyAsync(t.offsets, s.d_offsets, s.offsets_bytes, cudaMemcpyDeviceToHost, c.s_compute), "offsets D2H")) return -1;
+      if (total && check_cuda(cudaMemcpyAsync(t.data, s.d_data, total, cudaMemcpyDeviceToHost, c.s_compute), "data D2H")) return -1;
+      if (n && check_cuda(cudaMemcpyAsync(t.valid, s.validity.d_valid_bytes, (size_t)n, cudaMemcpyDeviceToHost, c.s_compute), "valid D2H")) return -1;
+      if (check_cuda(cudaStreamSynchronize(c.s_compute), "typed sync")) return -1;
+      t.null_count = (int64_t)s.h_ctr[2];
+    } else {
+      FixedRun f;
+      if (run_fixed(r, sc, j, m.op, 0, false, true, &f)) return -1;
+      t.values = keep_pin(r, f.values_bytes);
+      unsigned long long *h_null = (unsigned long long *)sc.palloc(8);
+      if (!t.values || !h_null) return -1;
+      *h_null = 0;
+      if (n && check_cuda(cudaMemcpyAsync(t.values, f.d_values, f.values_bytes, cudaMemcpyDeviceToHost, c.s_compute), "values D2H")) return -1;
+      if (n && check_cuda(cudaMemcpyAsync(t.valid, f.d_valid_bytes, (size_t)n, cudaMemcpyDeviceToHost, c.s_compute), "valid D2H")) return -1;
+      if (n && check_cuda(cudaMemcpyAsync(h_null, f.d_null_count, 8, cudaMemcpyDeviceToHost, c.s_compute), "null count D2H")) return -1;
+      if (check_cuda(cudaStreamSynchronize(c.s_compute), "typed sync")) return -1;
+      t.null_count = (int64_t)*h_null;
+    }
+    t.ready = true;
+  }
+  const TypedOut &t = col.typed;
+  out->tag = t.tag;
+  out->width = t.width;
+  out->length = n;
+  out->null_count = t.null_count;
+  out->values = t.values;
+  out->valid = (const uint8_t *)t.valid;
+  out->offsets = (const int32_t *)t.offsets;
+  out->data = (const uint8_t *)t.data;
+  return 0;
+}
+
+// ------------------------------------------------------------------ reference packed getters
+moonbit_bytes_t empty_bytes() { return moonbit_make_bytes_raw(0); }  // duckdb_mb_make_bytes("", 0)
+
+enum GetterKind { kGetInt32, kGetInt64, kGetDouble, kGetBool };
+
+// [n:i32][values][validity bytes]  (src/duckdb_native.c:2359-2454, 2516-2546, 2572-2685, 2761-2797)
+moonbit_bytes_t getter_fixed(Result *r, int32_t col_idx, GetterKind kind, bool nullable) {
+  if (!r) return empty_bytes();
+  const int32_t row_count = r->row_count;
+  if (col_idx < 0 || col_idx >= r->column_count || row_count <= 0) return empty_bytes();
+  CtxCore &c = *r->core;
+  std::lock_guard<std::mutex> g(c.mu);
+  if (!c.bind()) return empty_bytes();
+  static const int32_t kDst[] = {DMB_DST_I32_TRUNC, DMB_DST_I64, DMB_DST_F64, DMB_DST_BOOL_BYTE};
+  static const int kWidth[] = {4, 8, 8, 1};
+  const int w = kWidth[kind];
+  const int64_t total64 = 4 + (int64_t)row_count * w + (nullable ? row_count : 0);
+  if (total64 > 0x7fffffffll) {  // the reference's int32 total_size overflows here (:2371,2404)
+    set_error("result blob of %lld bytes exceeds the int32 length of MoonBit Bytes", (long long)total64);
+    return empty_bytes();
+  }
+  const Col &col = r->cols[(size_t)col_idx];
+  Scope sc(c);
+  FixedRun f;
+  // a (phys,dst) pair libduckdb cannot cast (or the oracle leaves at 0) yields zero values
+  if (run_fixed(r, sc, col_idx, col.phys == DMB_PHYS_STRING ? DMB_OP_VALIDITY_ONLY : DMB_OP(col.phys, kDst[kind]), w,
+                false, nullable, &f))
+    return empty_bytes();
+  moonbit_bytes_t blob = moonbit_make_bytes_raw((int32_t)total64);
+  if (!blob) { set_error("out of memory"); return empty_bytes(); }
+  memcpy(blob, &row_count, 4);
+  const size_t vbytes = (size_t)row_count * (size_t)w;
+  bool ok = check_cuda(cudaMemcpyAsync(blob + 4, f.d_values, vbytes, cudaMemcpyDeviceToHost, c.s_compute), "values D2H") == 0;
+  if (ok && nullable)
+    ok = check_cuda(cudaMemcpyAsync(blob + 4 + vbytes, f.d_valid_bytes, (size_t)row_count, cudaMemcpyDeviceToHost, c.s_compute), "validity D2H") == 0;
+  if (ok) ok = check_cuda(cudaStreamSynchronize(c.s_compute), "getter sync") == 0;
+  r->bytes_d2h += vbytes + (nullable ? (size_t)row_count : 0);
+  if (!ok) { memset(blob, 0, (size_t)total64); }
+  return blob;
+}
+
+// [n:i32][total:i32][s0\0 s1\0 ...][validity bytes]  (src/duckdb_native.c:2456-2514, 2687-2759).
+// The reference counts no terminator for a NULL row in `total` but still writes one, so the
+// stream it keeps is the first `total` bytes of the full NUL-terminated stream.
+moonbit_bytes_t getter_string(Result *r, int32_t col_idx, bool nullable) {
+  if (!r) return empty_bytes();
+  const int32_t row_count = r->row_count;
+  if (col_idx < 0 || col_idx >= r->column_count || row_count <= 0) return empty_bytes();
+  CtxCore &c = *r->core;
+  std::lock_guard<std::mutex> g(c.mu);
+  if (!c.bind()) return empty_bytes();
+  const Col &col = r->cols[(size_t)col_idx];
+  if (col.phys != DMB_PHYS_STRING) {
+    set_error("get_column_string on a non-VARCHAR column needs libduckdb's text rendering (duckdb_value_varchar); not on the GPU path");
+    return empty_bytes();
+  }
+  Scope sc(c);
+  StringRun s;
+  if (run_string(r, sc, col_idx, DMB_STR_REF_BLOB, false, nullable, &s)) return empty_bytes();
+  if (check_cuda(cudaEventSynchronize(s.done), "string kernel wait")) return empty_bytes();
+  if (string_flags_error(s.h_ctr[1])) return empty_bytes();
+  const uint64_t stream_total = s.h_ctr[0], nulls = s.h_ctr[2];
+  const uint64_t total_data_len = stream_total - nulls;
+  const int64_t total64 = 8 + (int64_t)total_data_len + (nullable ? row_count : 0);
+  if (total64 > 0x7fffffffll) {  // int32 total_size overflow in the reference (:2488)
+    set_error("result blob of %lld bytes exceeds the int32 length of MoonBit Bytes", (long long)total64);
+    return empty_bytes();
+  }
+  moonbit_bytes_t blob = moonbit_make_bytes_raw((int32_t)total64);
+  if (!blob) { set_error("out of memory"); return empty_bytes(); }
+  const int32_t tdl = (int32_t)total_data_len;
+  memcpy(blob, &row_count, 4);
+  memcpy(blob + 4, &tdl, 4);
+  bool ok = true;
+  if (total_data_len) ok = check_cuda(cudaMemcpyAsync(blob + 8, s.d_data, (size_t)total_data_len, cudaMemcpyDeviceToHost, c.s_compute), "string data D2H") == 0;
+  if (ok && nullable)
+    ok = check_cuda(cudaMemcpyAsync(blob + 8 + total_data_len, s.validity.d_valid_bytes, (size_t)row_count, cudaMemcpyDeviceToHost, c.s_compute), "validity D2H") == 0;
+  if (ok) ok = check_cuda(cudaStreamSynchronize(c.s_compute), "getter sync") == 0;
+  r->bytes_d2h += total_data_len + (nullable ? (size_t)row_count : 0);
+  if (!ok) memset(blob + 8, 0, (size_t)total64 - 8);
+  return blob;
+}
+
+}  // namespace
+}  // namespace dmb
+
+// =====================================================================================  L1
+extern "C" duckdb_mb_arrow_result *duckdb_mb_gpu_result_from_chunks(duckdb_mb_gpu_ctx *ctx, const dmb_host_batch *batch) {
+  if (!ctx || !ctx->core) { set_error("duckdb_mb_gpu_result_from_chunks: null context"); return nullptr; }
+  if (!batch || batch->ncols < 0 || batch->nchunks < 0 || (batch->ncols > 0 && !batch->cols) || (batch->nchunks > 0 && !batch->counts)) {
+    set_error("duckdb_mb_gpu_result_from_chunks: malformed batch");
+    return nullptr;
+  }
+  std::unique_ptr<Result> r(new Result());
+  r->core = ctx->core;
+  r->nchunks = batch->nchunks;
+  r->pinned_input = (batch->flags & DMB_BATCH_PINNED) != 0;
+  r->counts.assign(batch->counts, batch->counts + batch->nchunks);
+  r->row_off.assign((size_t)batch->nchunks + 1, 0);
+  for (int64_t k = 0; k < batch->nchunks; ++k) {
+    if (batch->counts[k] > DMB_VECTOR_SIZE) { set_error("chunk %lld has %u rows (> %d)", (long long)k, batch->counts[k], DMB_VECTOR_SIZE); return nullptr; }
+    r->row_off[(size_t)k + 1] = r->row_off[(size_t)k] + batch->counts[k];
+  }
+  r->nrows = r->row_off[(size_t)batch->nchunks];
+  r->column_count = batch->ncols;
+  r->row_count = (int32_t)r->nrows;  // idx_t -> int32_t, src/duckdb_native.c:2265
+  r->cols.resize((size_t)batch->ncols);
+  for (int32_t j = 0; j < batch->ncols; ++j) {
+    const dmb_host_column &hc = batch->cols[j];
+    Col &col = r->cols[(size_t)j];
+    col.name = hc.name ? hc.name : "";
+    col.type_id = hc.type_id;
+    col.phys = hc.phys;
+    col.dec_width = hc.dec_width;
+    col.dec_scale = hc.dec_scale;
+    col.width = dmb_phys_width(hc.phys);
+    if (col.width <= 0) { set_error("column %d: bad physical type %d", j, hc.phys); return nullptr; }
+    if (batch->nchunks > 0 && !hc.data) { set_error("column %d: no data pointers", j); return nullptr; }
+    col.data.assign(hc.data, hc.data + batch->nchunks);
+    for (int64_t k = 0; k < batch->nchunks; ++k)
+      if (batch->counts[k] && !col.data[(size_t)k]) { set_error("column %d: chunk %lld has rows but a null data pointer", j, (long long)k); return nullptr; }
+    if (hc.validity) {
+      col.validity.assign((const void *const *)hc.validity, (const void *const *)hc.validity + batch->nchunks);
+      for (const void *p : col.validity) col.any_validity |= p != nullptr;
+      if (!col.any_validity) col.validity.clear();
+    }
+    col.heap_base = (const uint8_t *)hc.heap_base;
+    col.heap_len = hc.heap_len;
+  }
+  return r.release();
+}
+
+extern "C" int32_t duckdb_mb_gpu_result_materialise_arrow(duckdb_mb_arrow_result *r) {
+  if (!r) { set_error("null result"); return 0; }
+  std::lock_guard<std::mutex> g(r->core->mu);
+  return materialise_arrow(r) == 0 ? 1 : 0;
+}
+
+extern "C" int32_t duckdb_mb_gpu_result_export_arrow(duckdb_mb_arrow_result *r, int32_t col, struct ArrowArray *out_array,
+                                                     struct ArrowSchema *out_schema) {
+  if (!r) { set_error("null result"); return 0; }
+  if (col < -1 || col >= r->column_count) { set_error("column %d out of range", col); return 0; }
+  std::lock_guard<std::mutex> g(r->core->mu);
+  if (materialise_arrow(r)) return 0;
+  if (col >= 0) {
+    export_column(r->cols[(size_t)col].arrow, out_array, out_schema);
+    return 1;
+  }
+  // whole batch: struct array, one child per column
+  const size_t nc = r->cols.size();
+  if (out_array) {
+    ExportPriv *p = new ExportPriv();
+    memset(out_array, 0, sizeof(*out_array));
+    for (size_t j = 0; j < nc; ++j) {
+      ArrowArray *ch = (ArrowArray *)calloc(1, sizeof(ArrowArray));
+      export_column(r->cols[j].arrow, ch, nullptr);
+      p->child_arrays.push_back(ch);
+    }
+    out_array->length = r->nrows;
+    out_array->null_count = 0;
+    out_array->n_buffers = 1;
+    out_array->buffers = p->buffers;  // validity = NULL
+    out_array->n_children = (int64_t)nc;
+    out_array->children = p->child_arrays.data();
+    out_array->release = release_array;
+    out_array->private_data = p;
+  }
+  if (out_schema) {
+    ExportPriv *p = new ExportPriv();
+    memset(out_schema, 0, sizeof(*out_schema));
+    for (size_t j = 0; j < nc; ++j) {
+      ArrowSchema *ch = (ArrowSchema *)calloc(1, sizeof(ArrowSchema));
+      export_column(r->cols[j].arrow, nullptr, ch);
+      p->child_schemas.push_back(ch);
+    }
+    p->format = "+s";
+    out_schema->format = p->format.c_str();
+    out_schema->name = p->name.c_str();
+    out_schema->n_children = (int64_t)nc;
+    out_schema->children = p->child_schemas.data();
+    out_schema->release = release_schema;
+    out_schema->private_data = p;
+  }
+  return 1;
+}
+
+extern "C" int32_t duckdb_mb_gpu_result_typed_column(duckdb_mb_arrow_result *r, int32_t col, dmb_typed_column *out) {
+  if (!r || !out) { set_error("null argument"); return 0; }
+  if (col < 0 || col >= r->column_count) { set_error("column %d out of range", col); return 0; }
+  std::lock_guard<std::mutex> g(r->core->mu);
+  return typed_column(r, col, out) == 0 ? 1 : 0;
+}
+
+extern "C" int32_t duckdb_mb_gpu_result_timings(duckdb_mb_arrow_result *r, double *out4) {
+  if (!r || !out4) return 0;
+  out4[0] = r->t_h2d;
+  out4[1] = r->t_kernels;
+  out4[2] = r->t_d2h;
+  out4[3] = r->t_total;
+  return 1;
+}
+
+extern "C" int32_t duckdb_mb_gpu_result_link_bytes(duckdb_mb_arrow_result *r, uint64_t *out2) {
+  if (!r || !out2) return 0;
+  out2[0] = r->bytes_h2d;
+  out2[1] = r->bytes_d2h;
+  return 1;
+}
+
+// =====================================================================================  L2
+extern "C" int32_t duckdb_mb_arrow_column_count(duckdb_mb_arrow_result *r) { return r ? r->column_count : 0; }
+extern "C" int32_t duckdb_mb_arrow_row_count(duckdb_mb_arrow_result *r) { return r ? r->row_count : 0; }
+
+// JSON [{"name":..,"nullable":true,"type_id":..}], type map of src/duckdb_native.c:2314-2339;
+// names are not escaped and nullable is always true, like the reference (:2342-2346)
+extern "C" moonbit_bytes_t duckdb_mb_arrow_schema(duckdb_mb_arrow_result *r) {
+  std::string json = "[";
+  if (r) {
+    for (int32_t i = 0; i < r->column_count; ++i) {
+      const Col &col = r->cols[(size_t)i];
+      const char *type_id = "string";
+      switch (col.type_id) {
+        case DMB_TYPE_BOOLEAN: type_id = "bool"; break;
+        case DMB_TYPE_TINYINT: case DMB_TYPE_SMALLINT: case DMB_TYPE_INTEGER: type_id = "int32"; break;
+        case DMB_TYPE_BIGINT: type_id = "int64"; break;
+        case DMB_TYPE_FLOAT: case DMB_TYPE_DOUBLE: type_id = "double"; break;
+        default: break;
+      }
+      if (i) json += ",";
+      json += "{\"name\":\"" + col.name + "\",\"nullable\":true,\"type_id\":\"" + type_id + "\"}";
+    }
+  }
+  json += "]";
+  moonbit_bytes_t b = moonbit_make_bytes_raw((int32_t)json.size());
+  if (b) memcpy(b, json.data(), json.size());
+  return b;
+}
+
+extern "C" moonbit_bytes_t duckdb_mb_arrow_get_column_int32(duckdb_mb_arrow_result *r, int32_t col) { return getter_fixed(r, col, kGetInt32, false); }
+extern "C" moonbit_bytes_t duckdb_mb_arrow_get_column_int64(duckdb_mb_arrow_result *r, int32_t col) { return getter_fixed(r, col, kGetInt64, false); }
+extern "C" moonbit_bytes_t duckdb_mb_arrow_get_column_double(duckdb_mb_arrow_result *r, int32_t col) { return getter_fixed(r, col, kGetDouble, false); }
+extern "C" moonbit_bytes_t duckdb_mb_arrow_get_column_bool(duckdb_mb_arrow_result *r, int32_t col) { return getter_fixed(r, col, kGetBool, false); }
+extern "C" moonbit_bytes_t duckdb_mb_arrow_get_column_string(duckdb_mb_arrow_result *r, int32_t col) { return getter_string(r, col, false); }
+extern "C" moonbit_bytes_t duckdb_mb_arrow_get_column_int32_nullable(duckdb_mb_arrow_result *r, int32_t col) { return getter_fixed(r, col, kGetInt32, true); }
+extern "C" moonbit_bytes_t duckdb_mb_arrow_get_column_int64_nullable(duckdb_mb_arrow_result *r, int32_t col) { return getter_fixed(r, col, kGetInt64, true); }
+extern "C" moonbit_bytes_t duckdb_mb_arrow_get_column_double_nullable(duckdb_mb_arrow_result *r, int32_t col) { return getter_fixed(r, col, kGetDouble, true); }
+extern "C" moonbit_bytes_t duckdb_mb_arrow_get_column_bool_nullable(duckdb_mb_arrow_result *r, int32_t col) { return getter_fixed(r, col, kGetBool, true); }
+extern "C" moonbit_bytes_t duckdb_mb_arrow_get_column_string_nullable(duckdb_mb_arrow_result *r, int32_t col) { return getter_string(r, col, true); }
+
+extern "C" void duckdb_mb_arrow_destroy(duckdb_mb_arrow_result *r) { free_result(r); }
+extern "C" int32_t duckdb_mb_is_null_arrow_result(duckdb_mb_arrow_result *r) { return r == nullptr ? 1 : 0; }
+
+extern "C" double duckdb_mb_bytes_to_double(const char *bytes, int32_t offset) {
+  double d;
+  memcpy(&d, bytes + offset, sizeof(d));
+  return d;
+}

@@ -103,6 +103,17 @@ struct CvMdn {
   }
 };
 struct CvDateRef { __device__ __forceinline__ int32_t operator()(int32_t v) const { return date_ref_quirk(v); } };
+// typed TIMESTAMP through the reference's parse_timestamp: quirky day number * 86400e6 + time of day
+__device__ __forceinline__ int64_t ts_ref_quirk(int64_t micros) {
+  const int64_t kDay = 86400000000ll;
+  const int64_t days = floor_div(micros, kDay);
+  if (days < -2147483648ll || days > 2147483647ll) return micros;
+  const int64_t tod = micros - days * kDay;
+  return (int64_t)date_ref_quirk((int32_t)days) * kDay + tod;
+}
+template <typename Pre>
+struct CvTsRef { __device__ __forceinline__ int64_t operator()(int64_t v) const { return ts_ref_quirk(Pre()(v)); } };
+struct CvId64 { __device__ __forceinline__ int64_t operator()(int64_t v) const { return v; } };
 
 template <typename D> __device__ __forceinline__ D zero_of() { D z; memset(&z, 0, sizeof(D)); return z; }
 
@@ -327,6 +338,10 @@ static fixed_kernel_fn select_kernel(int32_t op) {
     case DMB_OP(DMB_PHYS_I64, DMB_DST_TS_US_FROM_NS): return fixed_batch_kernel<int64_t, int64_t, CvTsNs, kKindConvert>;
     case DMB_OP(DMB_PHYS_INTERVAL, DMB_DST_MONTH_DAY_NANO): return fixed_batch_kernel<interval_t, month_day_nano_t, CvMdn, kKindConvert>;
     case DMB_OP(DMB_PHYS_I32, DMB_DST_DATE_REF): return fixed_batch_kernel<int32_t, int32_t, CvDateRef, kKindConvert>;
+    case DMB_OP(DMB_PHYS_I64, DMB_DST_TS_REF): return fixed_batch_kernel<int64_t, int64_t, CvTsRef<CvId64>, kKindConvert>;
+    case DMB_OP(DMB_PHYS_I64, DMB_DST_TS_REF_FROM_S): return fixed_batch_kernel<int64_t, int64_t, CvTsRef<CvTsS>, kKindConvert>;
+    case DMB_OP(DMB_PHYS_I64, DMB_DST_TS_REF_FROM_MS): return fixed_batch_kernel<int64_t, int64_t, CvTsRef<CvTsMs>, kKindConvert>;
+    case DMB_OP(DMB_PHYS_I64, DMB_DST_TS_REF_FROM_NS): return fixed_batch_kernel<int64_t, int64_t, CvTsRef<CvTsNs>, kKindConvert>;
     case DMB_OP_VALIDITY_ONLY: return fixed_batch_kernel<uint8_t, uint8_t, CvSame, kKindValidityOnly>;
     default: return nullptr;
   }
@@ -415,7 +430,11 @@ extern "C" int32_t dmb_op_out_width(int32_t op) {
     case DMB_DST_I32_SAT: return integer ? 4 : -1;
     case DMB_DST_TS_US_FROM_S:
     case DMB_DST_TS_US_FROM_MS:
-    case DMB_DST_TS_US_FROM_NS: return phys == DMB_PHYS_I64 ? 8 : -1;
+    case DMB_DST_TS_US_FROM_NS:
+    case DMB_DST_TS_REF:
+    case DMB_DST_TS_REF_FROM_S:
+    case DMB_DST_TS_REF_FROM_MS:
+    case DMB_DST_TS_REF_FROM_NS: return phys == DMB_PHYS_I64 ? 8 : -1;
     case DMB_DST_MONTH_DAY_NANO: return phys == DMB_PHYS_INTERVAL ? 16 : -1;
     case DMB_DST_DATE_REF: return phys == DMB_PHYS_I32 ? 4 : -1;
     default: return -1;

@@ -64,12 +64,17 @@ class GeneratedBatch(DeviceBatch):
         packed = (valid.view(-1, 8).to(torch.int32) * w).sum(dim=1).to(torch.uint8)
         return packed, valid[: self.nrows]
 
-    def add_fixed(self, type_id: int, dec_width: int, gen: torch.Generator, null_frac: float, name: str = "c"):
+    def add_fixed(self, type_id: int, dec_width: int, gen: torch.Generator, null_frac: float, name: str = "c",
+                  lo: Optional[int] = None, hi: Optional[int] = None, dec_scale: int = 0):
+        """lo/hi: uniform integer payload in [lo, hi) (valid rows and NULL slots alike); default: random bits."""
         phys = ch.phys_of_type(type_id, dec_width)
         width = ch.PHYS_WIDTH[phys]
         nbytes = self.capacity * width
         if phys == ch.P_BOOL:
             data = torch.randint(0, 2, (nbytes,), generator=gen, device=self.device, dtype=torch.uint8)
+        elif lo is not None and width in (4, 8):
+            dt = torch.int32 if width == 4 else torch.int64
+            data = torch.randint(lo, hi, (self.capacity,), generator=gen, device=self.device, dtype=dt).view(torch.uint8)
         else:
             # random payload everywhere, including under NULLs (garbage that must be zeroed on output)
             data = torch.randint(-2**63, 2**63 - 1, ((nbytes + 7) // 8,), generator=gen, device=self.device,
@@ -81,16 +86,24 @@ class GeneratedBatch(DeviceBatch):
         self.validity.append(packed)
         self.vecs.append(self._vecs(width, packed is not None))
         self.heap.append(None)
-        col = SimpleNamespace(name=name, type_id=type_id, phys=phys, dec_width=dec_width, dec_scale=0,
+        col = SimpleNamespace(name=name, type_id=type_id, phys=phys, dec_width=dec_width, dec_scale=dec_scale,
                               heap=None, heap_base=0, width=width)
         self.batch.columns.append(col)
         self.meta.append({"valid": valid})
         return len(self.data) - 1
 
     def add_string(self, gen: torch.Generator, null_frac: float, min_len: int, max_len: int,
-                   host_base: int = 0x7F0000000000, name: str = "s"):
+                   host_base: int = 0x7F0000000000, name: str = "s", len_choices: Optional[Sequence[int]] = None,
+                   host_heap_alloc=None):
+        """len_choices: lengths drawn uniformly from this list (dictionary-like columns) instead of
+        U[min_len, max_len].  host_heap_alloc(nbytes) -> uint8 numpy array: the string_t pointers then
+        are real addresses into that (page-locked) host array, which to_host_batch fills."""
         n = self.nrows
-        lens = torch.randint(min_len, max_len + 1, (n,), generator=gen, device=self.device, dtype=torch.int64)
+        if len_choices is not None:
+            table = torch.tensor(list(len_choices), dtype=torch.int64, device=self.device)
+            lens = table[torch.randint(0, len(len_choices), (n,), generator=gen, device=self.device)]
+        else:
+            lens = torch.randint(min_len, max_len + 1, (n,), generator=gen, device=self.device, dtype=torch.int64)
         packed, valid = (None, None)
         if null_frac > 0:
             packed, valid = self._validity(gen, null_frac)
@@ -99,6 +112,10 @@ class GeneratedBatch(DeviceBatch):
         heap_off = torch.cumsum(heap_lens, 0) - heap_lens
         heap_total = int(heap_lens.sum().item())
         heap = torch.randint(0x20, 0x7F, (heap_total + 64,), generator=gen, device=self.device, dtype=torch.uint8)
+        host_heap = None
+        if host_heap_alloc is not None:
+            host_heap = host_heap_alloc(heap_total + 64)
+            host_base = int(host_heap.ctypes.data)
         # inline rows take their bytes from an arbitrary heap position (they own no heap storage)
         idx = torch.arange(n, dtype=torch.int64, device=self.device)
         inline_src = (idx * 13) % max(heap_total, 1)
@@ -121,8 +138,37 @@ class GeneratedBatch(DeviceBatch):
         live = lens if valid is None else torch.where(valid, lens, torch.zeros_like(lens))
         live_ptr = torch.where(is_ptr, live, torch.zeros_like(live))
         self.meta.append({"valid": valid, "total_len": int(live.sum().item()), "ptr_len": int(live_ptr.sum().item()),
-                          "heap_total": heap_total, "lens": lens})
+                          "heap_total": heap_total, "host_heap": host_heap})
         return len(self.data) - 1
+
+    # ---- host copy (bench e2e leg, L1 tests): same bytes in (page-locked) host slabs
+    def to_host_batch(self, alloc=None) -> ch.ChunkBatch:
+        """alloc(nbytes) -> uint8 numpy array (e.g. pinned.pinned_empty); default: pageable numpy."""
+        alloc = alloc or (lambda nb: np.empty(max(int(nb), 1), dtype=np.uint8)[: int(nb)])
+
+        def to_host(t: torch.Tensor) -> np.ndarray:
+            out = alloc(t.numel())
+            torch.from_numpy(out).copy_(t.view(torch.uint8).reshape(-1))
+            return out
+
+        counts = self.counts.view(torch.int32).cpu().numpy().astype(np.uint32)
+        cols = []
+        for j, c in enumerate(self.batch.columns):
+            data = to_host(self.data[j])
+            validity = None if self.validity[j] is None else to_host(self.validity[j]).view(np.uint64)
+            vecs = self.vecs[j].view(torch.int64).reshape(-1, 2).cpu().numpy()
+            heap = None
+            if c.phys == ch.P_STRING:
+                host_heap = self.meta[j].get("host_heap")
+                if host_heap is None:
+                    raise ValueError("string column was generated without host_heap_alloc: its pointers are not host addresses")
+                nb = self.heap[j].numel()
+                torch.from_numpy(host_heap[:nb]).copy_(self.heap[j])
+                heap = host_heap[: self.meta[j]["heap_total"] + 16]
+            cols.append(ch.Column(c.name, c.type_id, c.phys, data, vecs[:, 0].astype(np.uint64).copy(), validity,
+                                  vecs[:, 1].copy(), c.dec_width, c.dec_scale, heap))
+        torch.cuda.synchronize(self.device)
+        return ch.ChunkBatch(counts, cols)
 
     # ---- algorithmic bytes (SURVEY.md §8d)
     def alg_bytes_fixed(self, plan) -> int:

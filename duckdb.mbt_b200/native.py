@@ -101,6 +101,10 @@ EXPORTED_SYMBOLS = [
     "duckdb_mb_gpu_appender_create", "duckdb_mb_gpu_appender_destroy", "duckdb_mb_gpu_appender_error",
     "duckdb_mb_gpu_appender_state", "duckdb_mb_gpu_appender_row_count", "duckdb_mb_gpu_append_arrow_batch",
     "duckdb_mb_gpu_appender_flush", "duckdb_mb_gpu_appender_close", "duckdb_mb_gpu_appender_timings",
+    "duckdb_mb_gpu_appender_flushed_row_count", "duckdb_mb_gpu_appender_link_bytes",
+    "duckdb_mb_gpu_begin_row", "duckdb_mb_gpu_append_int", "duckdb_mb_gpu_append_bigint", "duckdb_mb_gpu_append_double",
+    "duckdb_mb_gpu_append_varchar", "duckdb_mb_gpu_append_bool", "duckdb_mb_gpu_append_null", "duckdb_mb_gpu_append_date",
+    "duckdb_mb_gpu_append_timestamp", "duckdb_mb_gpu_end_row",
 ]
 
 _lib = None
@@ -208,6 +212,16 @@ def lib():
     L.duckdb_mb_gpu_appender_close.argtypes = [vp]
     L.duckdb_mb_gpu_appender_timings.restype = i32
     L.duckdb_mb_gpu_appender_timings.argtypes = [vp, C.POINTER(C.c_double)]
+    L.duckdb_mb_gpu_appender_flushed_row_count.restype = i64
+    L.duckdb_mb_gpu_appender_flushed_row_count.argtypes = [vp]
+    L.duckdb_mb_gpu_appender_link_bytes.restype = i32
+    L.duckdb_mb_gpu_appender_link_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
+    for name, extra in (("begin_row", []), ("append_int", [i32]), ("append_bigint", [i64]), ("append_double", [C.c_double]),
+                        ("append_varchar", [C.c_char_p, i32]), ("append_bool", [i32]), ("append_null", []),
+                        ("append_date", [i32]), ("append_timestamp", [i64]), ("end_row", [])):
+        f = getattr(L, "duckdb_mb_gpu_" + name)
+        f.restype = i32
+        f.argtypes = [vp] + extra
     _lib = real
     return real
 

@@ -100,7 +100,15 @@ enum dmb_dst {
   DMB_DST_MONTH_DAY_NANO = 11, /* INTERVAL -> Arrow month_day_nano_interval                   */
   DMB_DST_DATE_REF = 12,  /* typed Value::Date through the reference's date_to_days, incl. its
                              pre-1970 leap-day defect      src/duckdb_parsing.mbt:318-338      */
-  DMB_DST_COUNT = 13
+  /* typed Value::Timestamp exactly as the reference computes it: text -> parse_timestamp =
+     parse_date(date part) * 86400e6 + time of day (src/duckdb_parsing.mbt:375-398), so the
+     date_to_days pre-1970 behaviour carries over; the source unit is converted to micros first
+     (fraction truncated to 6 digits, :402-417) */
+  DMB_DST_TS_REF = 13,
+  DMB_DST_TS_REF_FROM_S = 14,
+  DMB_DST_TS_REF_FROM_MS = 15,
+  DMB_DST_TS_REF_FROM_NS = 16,
+  DMB_DST_COUNT = 17
 };
 
 #define DMB_OP(phys, dst) (((int32_t)(phys) << 8) | (int32_t)(dst))
@@ -418,7 +426,28 @@ int32_t duckdb_mb_gpu_append_arrow_batch(duckdb_mb_gpu_appender *a, const struct
                                          const struct ArrowSchema *schema);
 int32_t duckdb_mb_gpu_appender_flush(duckdb_mb_gpu_appender *a); /* cf. duckdb_mb_flush :1237 */
 int32_t duckdb_mb_gpu_appender_close(duckdb_mb_gpu_appender *a);
+int64_t duckdb_mb_gpu_appender_flushed_row_count(duckdb_mb_gpu_appender *a);
+/* timings of the last conversion, ms: [0]=h2d [1]=kernels [2]=d2h [3]=total; link bytes [0]=h2d [1]=d2h */
 int32_t duckdb_mb_gpu_appender_timings(duckdb_mb_gpu_appender *a, double *out4);
+int32_t duckdb_mb_gpu_appender_link_bytes(duckdb_mb_gpu_appender *a, uint64_t *out2);
+
+/* The reference's row-at-a-time protocol (duckdb_mb_begin_row / append_* / end_row,
+ * src/duckdb_native.c:1100-1235, MoonBit wrappers src/duckdb_native.mbt:974-1058) on the same
+ * handle: cells are buffered column-wise on the host and converted by the same kernels on
+ * flush / close / every 2^20 rows.  Same 1/0 + per-handle error convention; an over- or
+ * under-filled row, or a call outside a row, moves the handle to the Error state
+ * (src/duckdb_appender_state_machine.mbt:96-177,228-238). */
+int32_t duckdb_mb_gpu_begin_row(duckdb_mb_gpu_appender *a);                                   /* :1100 */
+int32_t duckdb_mb_gpu_append_int(duckdb_mb_gpu_appender *a, int32_t v);                       /* :1116 */
+int32_t duckdb_mb_gpu_append_bigint(duckdb_mb_gpu_appender *a, int64_t v);                    /* :1132 */
+int32_t duckdb_mb_gpu_append_double(duckdb_mb_gpu_appender *a, double v);                     /* :1148 */
+int32_t duckdb_mb_gpu_append_varchar(duckdb_mb_gpu_appender *a, const uint8_t *bytes, int32_t len); /* :1164 */
+int32_t duckdb_mb_gpu_append_bool(duckdb_mb_gpu_appender *a, int32_t v);                      /* :1189 */
+int32_t duckdb_mb_gpu_append_null(duckdb_mb_gpu_appender *a);                                 /* :1205 */
+int32_t duckdb_mb_gpu_append_date(duckdb_mb_gpu_appender *a, int32_t days);   /* exact days, not the
+                                      approximate string path of :1313-1331 */
+int32_t duckdb_mb_gpu_append_timestamp(duckdb_mb_gpu_appender *a, int64_t micros);            /* :1350 */
+int32_t duckdb_mb_gpu_end_row(duckdb_mb_gpu_appender *a);                                     /* :1221 */
 
 #ifdef __cplusplus
 }
