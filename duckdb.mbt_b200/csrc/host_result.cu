@@ -96,6 +96,7 @@ namespace dmb {
 namespace {
 
 typedef duckdb_mb_arrow_result Result;
+static_assert(sizeof(dmb_string_t) == 16, "duckdb_string_t is 16 bytes");
 
 void *keep_dev(Result *r, size_t bytes) {
   void *p = r->core->dev.alloc(bytes + 64);
@@ -165,8 +166,8 @@ void compact_fixup(void *user, int64_t k, uint8_t *staged, size_t bytes) {
     if (!host_row_valid(mask, i)) continue;  // payload under a NULL row is unspecified: never dereference it
     const uint32_t len = e[i].length;
     if (len <= 12) continue;
-    memcpy(cc->arena + pos, reinterpret_cast<const void *>((uintptr_t)e[i].value.ptr.ptr), len);
-    e[i].value.ptr.ptr = cc->fake_base + pos;
+    memcpy(cc->arena + pos, reinterpret_cast<const void *>((uintptr_t)e[i].tail.ptr), len);
+    e[i].tail.ptr = cc->fake_base + pos;
     pos += len;
   }
 }

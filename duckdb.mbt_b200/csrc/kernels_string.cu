@@ -3,13 +3,18 @@
 // Tile = 1024 consecutive rows of one chunk (two tiles per 2048-row vector).  A CTA
 //   1. takes a ticket (tiles are processed in ticket order => look-back always makes progress),
 //   2. loads the tile's string_t into shared memory with coalesced 128-bit loads (read once),
-//   3. block-scans the (validity-masked) lengths,
+//   3. block-scans the (validity-masked) lengths into tile-local offsets,
 //   4. publishes its aggregate and resolves its exclusive base by decoupled look-back over the
 //      predecessors' 64-bit status words (flag | value in one word, so no fences are needed),
-//   5. writes offsets, and
-//   6. gathers the bytes (inline bytes from the shared-memory copy of string_t, pointer strings
-//      from the device heap with the host pointer rebased) into a shared-memory stage laid out
-//      with the destination's 16-byte phase, which is then written with coalesced 128-bit stores.
+//   5. writes offsets (coalesced), and
+//   6. gathers the bytes OUTPUT-centrically: a thread owns one 16-byte aligned vector of the
+//      output stream, finds the row that covers its first byte by binary search over the
+//      tile-local offsets, assembles the 16 bytes from the rows it overlaps (inline bytes come
+//      from the shared-memory copy of string_t, pointer strings from the device heap with the
+//      host pointer rebased; aligned 32-bit loads + funnel shifts) and stores them with one
+//      128-bit streaming store.  Every load of a thread is independent of the others, consecutive
+//      threads read consecutive heap bytes and write consecutive vectors, and there is no
+//      shared-memory staging of the data bytes.
 //
 // Replaces the reference's per-cell string_t read src/duckdb_native.c:597-603 and the two-pass
 // malloc/strlen/memcpy getters :2474-2510 and :2699-2755.  DMB_STR_REF_BLOB reproduces the
@@ -21,7 +26,6 @@ namespace dmb {
 
 constexpr int kStrTileRows = 1024;
 constexpr int kStrPerThread = kStrTileRows / kThreads;  // 4 consecutive rows per thread
-constexpr int kStageBytes = 32768;
 
 constexpr uint64_t kFlagAggregate = 1ull << 62;
 constexpr uint64_t kFlagPrefix = 2ull << 62;
@@ -31,51 +35,39 @@ constexpr uint64_t kValueMask = (1ull << 62) - 1ull;
 enum { kErrTileTooBig = 1, kErrOffsetOverflow = 2, kErrHeapRange = 4 };
 
 struct StrSmem {
-  uint4 str[kStrTileRows + 1];       // string_t copies (+1 pad: the funnel copy may touch the next word)
-  uint32_t off[kStrTileRows + 1];    // tile-local exclusive offsets
+  uint4 str[kStrTileRows];           // string_t copies
+  uint32_t off[kStrTileRows + 1];    // tile-local exclusive offsets; off[nrows] = tile total
   uint64_t warp_sum[kThreads / 32];
   uint64_t base;
   int64_t tile;
-  alignas(16) uint8_t stage[kStageBytes + 16];
 };
 
 __device__ __forceinline__ uint64_t ld_status(const unsigned long long *p) {
   return *reinterpret_cast<const volatile unsigned long long *>(p);
 }
 
-// Copy len bytes, arbitrary alignments, dst in shared memory.  One aligned 32-bit source load
-// per destination word (funnel shift), bytes only at the ragged ends.
-__device__ __forceinline__ void copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t len) {
-  uint32_t i = 0;
-  uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
-  if (head > len) head = len;
-  for (; i < head; ++i) dst[i] = src[i];
-  uint32_t nwords = (len - i) >> 2;
-  if (nwords) {
-    const uint8_t *s = src + i;
-    uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3u) * 8u;
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
-    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + i);
-    if (sh == 0) {
-      for (uint32_t w = 0; w < nwords; ++w) dw[w] = sw[w];
-    } else {
-      uint32_t lo = sw[0];
-      for (uint32_t w = 0; w < nwords; ++w) {
-        uint32_t hi = sw[w + 1];
-        dw[w] = __funnelshift_r(lo, hi, sh);
-        lo = hi;
-      }
-    }
-    i += nwords * 4u;
-  }
-  for (; i < len; ++i) dst[i] = src[i];
+// 4 bytes starting at byte offset o (0..11) of the 12 inline bytes (y,z,w) of a string_t
+__device__ __forceinline__ uint32_t inline_bytes4(const uint4 &e, uint32_t o) {
+  const uint32_t wi = o >> 2, sh = (o & 3u) * 8u;
+  const uint32_t x = wi == 0 ? e.y : (wi == 1 ? e.z : e.w);
+  const uint32_t y = wi == 0 ? e.z : (wi == 1 ? e.w : 0u);
+  return __funnelshift_r(x, y, sh);
+}
+
+// 4 bytes starting at an arbitrary global address; only the low `nb` bytes are needed.  Reads
+// whole aligned words (the heap copy carries >= 16 bytes of padding past its end).
+__device__ __forceinline__ uint32_t global_bytes4(const uint8_t *p, uint32_t nb) {
+  const uint32_t *a = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+  const uint32_t x = __ldg(a);
+  const uint32_t y = (sh + 8u * nb > 32u) ? __ldg(a + 1) : 0u;
+  return __funnelshift_r(x, y, sh);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  StrSmem &sm = *reinterpret_cast<StrSmem *>(smem_raw);
+  __shared__ StrSmem sm;
   unsigned long long *status = scratch + 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -94,36 +86,32 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
 
   // 2. string_t tile -> shared memory
   for (int i = tid; i < nrows_tile; i += kThreads) sm.str[i] = ld_stream(in + i);
-  if (tid == 0) sm.str[kStrTileRows] = make_uint4(0, 0, 0, 0);
   __syncthreads();
 
   // 3. lengths (4 consecutive rows per thread) and block scan
   uint32_t len[kStrPerThread];
-  const uint8_t *src[kStrPerThread];
   uint64_t tsum = 0;
   bool bad_heap = false;
 #pragma unroll
   for (int k = 0; k < kStrPerThread; ++k) {
     const int i = tid * kStrPerThread + k;
     len[k] = 0;
-    src[k] = nullptr;
     if (i < nrows_tile) {
       const int row = r_begin + i;
       const bool valid = mask ? ((__ldg(mask + (row >> 6)) >> (row & 63)) & 1ull) : true;
       if (valid) {
         const uint4 e = sm.str[i];
         uint32_t l = e.x;
-        if (l <= 12u) {
-          src[k] = reinterpret_cast<const uint8_t *>(&sm.str[i]) + 4;
-        } else {
-          uint64_t p = ((uint64_t)e.w << 32) | (uint64_t)e.z;
-          uint64_t rel = p - job.heap_host_base;
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(&sm.str[i]) + 4;
+        if (l > 12u) {
+          const uint64_t p = ((uint64_t)e.w << 32) | (uint64_t)e.z;
+          const uint64_t rel = p - job.heap_host_base;
           if (p < job.heap_host_base || rel + l > job.heap_len) { bad_heap = true; l = 0; }
-          src[k] = job.heap_dev + rel;
+          src = job.heap_dev + rel;
         }
         if (MODE == DMB_STR_REF_BLOB) {  // strlen() of the malloc'ed copy: stop at an embedded NUL
           uint32_t n = 0;
-          while (n < l && src[k][n] != 0) ++n;
+          while (n < l && src[n] != 0) ++n;
           l = n;
         }
         len[k] = l;
@@ -147,19 +135,18 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     if (w < warp) warp_excl += s;
     tile_total += s;
   }
-  uint64_t excl = warp_excl + incl - tsum;
-  if (tile_total > 0xffffffffull) {
-    if (tid == 0) atomicOr(scratch + 1, (unsigned long long)kErrTileTooBig);
-  }
+  const uint64_t excl = warp_excl + incl - tsum;
+  const bool too_big = tile_total > 0xfffffff0ull;
+  if (too_big && tid == 0) atomicOr(scratch + 1, (unsigned long long)kErrTileTooBig);
   if (bad_heap) atomicOr(scratch + 1, (unsigned long long)kErrHeapRange);
   {
     uint32_t o = (uint32_t)excl;
 #pragma unroll
     for (int k = 0; k < kStrPerThread; ++k) {
-      const int i = tid * kStrPerThread + k;
-      if (i < kStrTileRows) sm.off[i] = o;
+      sm.off[tid * kStrPerThread + k] = o;
       o += len[k];
     }
+    if (tid == kThreads - 1) sm.off[kStrTileRows] = o;
   }
 
   // 4. decoupled look-back (warp 0)
@@ -207,46 +194,71 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     }
     if (tile == ntiles - 1 && tid == 0 && job.total_bytes) *job.total_bytes = base + tile_total;
   }
-  if (tile_total == 0 || tile_total > 0xffffffffull) return;
+  if (tile_total == 0 || too_big) return;
 
-  // 6. gather bytes through the shared-memory stage.  Stage position p <-> global byte
-  //    out_data[base - mis + p], so p % 16 == 0 is a 16-byte aligned global address.
+  // 6. output-centric gather.  Vector v covers global bytes [16v - mis, 16v - mis + 16) relative
+  //    to the tile's first output byte, so every vector is 16-byte aligned in out_data.
+  const uint32_t total = (uint32_t)tile_total;
   const uint32_t mis = (uint32_t)(base & 15ull);
   uint8_t *gbase = job.out_data + (base - mis);
-  const uint32_t end = mis + (uint32_t)tile_total;  // tile_total < 2^32 - 16 in practice
-  for (uint32_t w0 = 0; w0 < end; w0 += kStageBytes) {
-    const uint32_t w1 = w0 + kStageBytes;
-    uint32_t o = mis + (uint32_t)excl;
+  const uint32_t nvec = (mis + total + 15u) >> 4;
+  // rows >= nrows_tile have len 0, so off[] is non-decreasing over the whole [0, 1024] range
+  for (uint32_t v = tid; v < nvec; v += kThreads) {
+    const uint32_t vbeg = v << 4;                          // position + mis of the vector's first byte
+    const uint32_t lo = v ? vbeg - mis : 0u;               // tile-local byte range [lo, hi) owned by this vector
+    const uint32_t hi = (vbeg + 16u - mis) < total ? (vbeg + 16u - mis) : total;
+    int l = 0, h = kStrTileRows;                           // invariant: off[l] <= lo < off[h]
+#pragma unroll 1
+    while (h - l > 1) {
+      const int m = (l + h) >> 1;
+      if (sm.off[m] <= lo) l = m; else h = m;
+    }
+    int r = l;
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    uint32_t pos = lo;
+    uint32_t r_off = sm.off[r], r_end = sm.off[r + 1];
+#pragma unroll 1
+    while (pos < hi) {
+      if (r_end <= pos) {  // empty (or exhausted) row: next
+        ++r;
+        r_off = r_end;
+        r_end = sm.off[r + 1];
+        continue;
+      }
+      const uint32_t pay_end = MODE == DMB_STR_REF_BLOB ? r_end - 1u : r_end;  // the terminator byte stays 0
+      const uint32_t seg_end = pay_end < hi ? pay_end : hi;
+      if (seg_end > pos) {
+        const uint4 e = sm.str[r];
+        const uint32_t soff = pos - r_off;                 // offset inside the string
+        const uint32_t d = pos + mis - vbeg;               // destination byte inside the vector
+        const uint32_t k = seg_end - pos;                  // bytes to place (1..16)
+        const bool is_inline = e.x <= 12u;
+        const uint8_t *gsrc = job.heap_dev + ((((uint64_t)e.w << 32) | (uint64_t)e.z) - job.heap_host_base) + soff;
 #pragma unroll
-    for (int k = 0; k < kStrPerThread; ++k) {
-      const uint32_t l = len[k];
-      const uint32_t s0 = o, s1 = o + l;
-      o = s1;
-      if (l == 0 || s1 <= w0 || s0 >= w1) continue;
-      const uint32_t nbytes = MODE == DMB_STR_REF_BLOB ? l - 1 : l;  // payload bytes
-      const uint32_t lo = s0 > w0 ? s0 : w0;
-      const uint32_t hi_payload = (s0 + nbytes) < w1 ? (s0 + nbytes) : w1;
-      if (hi_payload > lo) copy_bytes(sm.stage + (lo - w0), src[k] + (lo - s0), hi_payload - lo);
-      if (MODE == DMB_STR_REF_BLOB) {
-        const uint32_t tpos = s0 + nbytes;
-        if (tpos >= w0 && tpos < w1) sm.stage[tpos - w0] = 0;
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t a = d > 4u * j ? d : 4u * j;
+          const uint32_t bb = (d + k) < (4u * j + 4u) ? (d + k) : (4u * j + 4u);
+          if (bb > a) {
+            const uint32_t nb = bb - a;
+            const uint32_t val = is_inline ? inline_bytes4(e, soff + (a - d)) : global_bytes4(gsrc + (a - d), nb);
+            const uint32_t m = nb == 4u ? 0xffffffffu : ((1u << (8u * nb)) - 1u);
+            const uint32_t piece = (val & m) << (8u * (a - 4u * j));
+            if (j == 0) w0 |= piece; else if (j == 1) w1 |= piece; else if (j == 2) w2 |= piece; else w3 |= piece;
+          }
+        }
+      }
+      pos = (MODE == DMB_STR_REF_BLOB && seg_end == pay_end && pay_end < hi) ? r_end : seg_end;
+    }
+    const bool full = (v > 0 || mis == 0) && (vbeg + 16u - mis <= total);
+    if (full) {
+      st_stream(reinterpret_cast<uint4 *>(gbase + vbeg), make_uint4(w0, w1, w2, w3));
+    } else {  // the neighbouring tiles own the other bytes of this vector
+      const uint32_t q0 = lo + mis - vbeg, q1 = hi + mis - vbeg;
+      for (uint32_t q = q0; q < q1; ++q) {
+        const uint32_t word = q < 4 ? w0 : (q < 8 ? w1 : (q < 12 ? w2 : w3));
+        gbase[vbeg + q] = (uint8_t)(word >> (8u * (q & 3u)));
       }
     }
-    __syncthreads();
-    const uint32_t lo = w0 > mis ? w0 : mis;
-    const uint32_t hi = w1 < end ? w1 : end;
-    for (uint32_t v = tid; v < kStageBytes / 16; v += kThreads) {
-      const uint32_t p = w0 + 16u * v;
-      if (p >= hi) break;
-      if (p + 16u <= lo) continue;
-      if (p >= lo && p + 16u <= hi) {
-        st_stream(reinterpret_cast<uint4 *>(gbase + p), *reinterpret_cast<const uint4 *>(sm.stage + 16u * v));
-      } else {
-        const uint32_t q0 = p > lo ? p : lo, q1 = (p + 16u) < hi ? (p + 16u) : hi;
-        for (uint32_t q = q0; q < q1; ++q) gbase[q] = sm.stage[q - w0];
-      }
-    }
-    __syncthreads();
   }
 }
 
@@ -289,20 +301,14 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
   const int64_t ntiles = 2 * nchunks;
   if (check_cuda(cudaMemsetAsync(scratch, 0, dmb_dev_string_scratch_bytes(nchunks), st), "string scratch memset")) return -1;
   BatchView b{counts, row_off, nchunks, nrows};
-  const size_t smem = sizeof(StrSmem);
-  static bool attr_set[3] = {false, false, false};
-  auto launch = [&](auto kernel, int mode) -> int32_t {
-    if (!attr_set[mode]) {
-      if (check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "string kernel smem attr")) return -1;
-      attr_set[mode] = true;
-    }
-    kernel<<<(unsigned)ntiles, kThreads, smem, st>>>(*job, b, (unsigned long long *)scratch, ntiles);
+  auto launch = [&](auto kernel) -> int32_t {
+    kernel<<<(unsigned)ntiles, kThreads, 0, st>>>(*job, b, (unsigned long long *)scratch, ntiles);
     return check_cuda(cudaGetLastError(), "string_batch_kernel launch");
   };
   switch (job->mode) {
-    case DMB_STR_ARROW_UTF8: return launch(string_batch_kernel<DMB_STR_ARROW_UTF8>, 0);
-    case DMB_STR_ARROW_LARGE: return launch(string_batch_kernel<DMB_STR_ARROW_LARGE>, 1);
-    case DMB_STR_REF_BLOB: return launch(string_batch_kernel<DMB_STR_REF_BLOB>, 2);
+    case DMB_STR_ARROW_UTF8: return launch(string_batch_kernel<DMB_STR_ARROW_UTF8>);
+    case DMB_STR_ARROW_LARGE: return launch(string_batch_kernel<DMB_STR_ARROW_LARGE>);
+    case DMB_STR_REF_BLOB: return launch(string_batch_kernel<DMB_STR_REF_BLOB>);
     default: set_error("dmb_dev_string_batch: bad mode %d", job->mode); return -1;
   }
 }

@@ -139,10 +139,11 @@ typedef struct dmb_fixed_job {
 /* duckdb_string_t, 16 bytes (reference reads it at src/duckdb_native.c:597-603) */
 typedef struct dmb_string_t {
   uint32_t length;
+  char prefix[4];          /* first 4 bytes of the string (both forms) */
   union {
-    struct { char inlined[12]; } inl;               /* length <= 12 */
-    struct { char prefix[4]; uint64_t ptr; } ptr;   /* length  > 12: host heap pointer */
-  } value;
+    char inlined_rest[8];  /* length <= 12: bytes 4..11, unused bytes zero */
+    uint64_t ptr;          /* length  > 12: host heap pointer to the whole string */
+  } tail;
 } dmb_string_t;
 
 enum dmb_string_mode {
