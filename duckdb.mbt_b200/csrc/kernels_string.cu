@@ -1,20 +1,18 @@
 // K5 string_unpack: duckdb_string_t[16 B] -> Arrow utf8 (offsets + data) in ONE pass.
 //
-// Tile = 1024 consecutive rows of one chunk (two tiles per 2048-row vector).  A CTA
+// Tile = 512 consecutive rows of one chunk (four tiles per 2048-row vector).  A CTA
 //   1. takes a ticket (tiles are processed in ticket order => look-back always makes progress),
 //   2. loads the tile's string_t into shared memory with coalesced 128-bit loads (read once),
 //   3. block-scans the (validity-masked) lengths into tile-local offsets,
 //   4. publishes its aggregate and resolves its exclusive base by decoupled look-back over the
 //      predecessors' 64-bit status words (flag | value in one word, so no fences are needed),
 //   5. writes offsets (coalesced), and
-//   6. gathers the bytes OUTPUT-centrically: a thread owns one 16-byte aligned vector of the
-//      output stream, finds the row that covers its first byte by binary search over the
-//      tile-local offsets, assembles the 16 bytes from the rows it overlaps (inline bytes come
-//      from the shared-memory copy of string_t, pointer strings from the device heap with the
-//      host pointer rebased; aligned 32-bit loads + funnel shifts) and stores them with one
-//      128-bit streaming store.  Every load of a thread is independent of the others, consecutive
-//      threads read consecutive heap bytes and write consecutive vectors, and there is no
-//      shared-memory staging of the data bytes.
+//   6. gathers the bytes row by row into a shared-memory stage laid out with the destination's
+//      16-byte phase (lane i of a warp takes row i, so a warp reads one contiguous stretch of the
+//      heap; inline bytes come from the shared-memory copy of string_t, pointer strings from the
+//      device heap with the host pointer rebased; aligned 32-bit loads, five in flight, funnel
+//      shifted to the stage's word alignment), then writes the stage with coalesced 128-bit
+//      streaming stores.
 //
 // Replaces the reference's per-cell string_t read src/duckdb_native.c:597-603 and the two-pass
 // malloc/strlen/memcpy getters :2474-2510 and :2699-2755.  DMB_STR_REF_BLOB reproduces the
@@ -24,8 +22,10 @@
 
 namespace dmb {
 
-constexpr int kStrTileRows = 1024;
-constexpr int kStrPerThread = kStrTileRows / kThreads;  // 4 consecutive rows per thread
+constexpr int kStrTileRows = 512;
+constexpr int kStrTilesPerChunk = kVec / kStrTileRows;
+constexpr int kStrPerThread = kStrTileRows / kThreads;  // 2 consecutive rows per thread in the scan
+constexpr int kStageBytes = 16384;
 
 constexpr uint64_t kFlagAggregate = 1ull << 62;
 constexpr uint64_t kFlagPrefix = 2ull << 62;
@@ -36,7 +36,8 @@ enum { kErrTileTooBig = 1, kErrOffsetOverflow = 2, kErrHeapRange = 4 };
 
 struct StrSmem {
   uint4 str[kStrTileRows];           // string_t copies
-  uint32_t off[kStrTileRows + 1];    // tile-local exclusive offsets; off[nrows] = tile total
+  uint32_t off[kStrTileRows + 4];    // tile-local exclusive offsets; off[kStrTileRows] = tile total
+  alignas(16) uint8_t stage[kStageBytes + 16];
   uint64_t warp_sum[kThreads / 32];
   uint64_t base;
   int64_t tile;
@@ -46,26 +47,42 @@ __device__ __forceinline__ uint64_t ld_status(const unsigned long long *p) {
   return *reinterpret_cast<const volatile unsigned long long *>(p);
 }
 
-// 4 bytes starting at byte offset o (0..11) of the 12 inline bytes (y,z,w) of a string_t
-__device__ __forceinline__ uint32_t inline_bytes4(const uint4 &e, uint32_t o) {
-  const uint32_t wi = o >> 2, sh = (o & 3u) * 8u;
-  const uint32_t x = wi == 0 ? e.y : (wi == 1 ? e.z : e.w);
-  const uint32_t y = wi == 0 ? e.z : (wi == 1 ? e.w : 0u);
-  return __funnelshift_r(x, y, sh);
-}
-
-// 4 bytes starting at an arbitrary global address; only the low `nb` bytes are needed.  Reads
-// whole aligned words (the heap copy carries >= 16 bytes of padding past its end).
-__device__ __forceinline__ uint32_t global_bytes4(const uint8_t *p, uint32_t nb) {
-  const uint32_t *a = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
-  const uint32_t x = __ldg(a);
-  const uint32_t y = (sh + 8u * nb > 32u) ? __ldg(a + 1) : 0u;
-  return __funnelshift_r(x, y, sh);
+// Copy len bytes from src (generic address: device heap or the shared-memory string_t copy, any
+// alignment) to dst in shared memory (any alignment).  Whole destination words are written with
+// one store each from two aligned source words (funnel shift), five source loads in flight; only
+// the ragged ends go byte by byte.  Source words are read whole: the heap copy carries >= 16
+// bytes of padding and the string_t copy is followed by other shared-memory fields.
+__device__ __forceinline__ void copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t len) {
+  uint32_t i = 0;
+  uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
+  if (head > len) head = len;
+  for (; i < head; ++i) dst[i] = src[i];
+  const uint32_t nwords = (len - i) >> 2;
+  if (nwords) {
+    const uint8_t *s = src + i;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3u) * 8u;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + i);
+    const uint32_t last = sh ? nwords : nwords - 1u;  // highest source word index that holds needed bytes
+#pragma unroll 1
+    for (uint32_t w = 0; w < nwords; w += 4) {
+      const uint32_t x0 = sw[w];
+      const uint32_t x1 = w + 1 <= last ? sw[w + 1] : 0u;
+      const uint32_t x2 = w + 2 <= last ? sw[w + 2] : 0u;
+      const uint32_t x3 = w + 3 <= last ? sw[w + 3] : 0u;
+      const uint32_t x4 = w + 4 <= last ? sw[w + 4] : 0u;
+      dw[w] = __funnelshift_r(x0, x1, sh);
+      if (w + 1 < nwords) dw[w + 1] = __funnelshift_r(x1, x2, sh);
+      if (w + 2 < nwords) dw[w + 2] = __funnelshift_r(x2, x3, sh);
+      if (w + 3 < nwords) dw[w + 3] = __funnelshift_r(x3, x4, sh);
+    }
+    i += nwords * 4u;
+  }
+  for (; i < len; ++i) dst[i] = src[i];
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 8)
 string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles) {
   __shared__ StrSmem sm;
   unsigned long long *status = scratch + 2;
@@ -75,8 +92,8 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   __syncthreads();
   const int64_t tile = sm.tile;
   if (tile >= ntiles) return;
-  const int64_t c = tile >> 1;
-  const int r_begin = (int)(tile & 1) * kStrTileRows;
+  const int64_t c = tile / kStrTilesPerChunk;
+  const int r_begin = (int)(tile % kStrTilesPerChunk) * kStrTileRows;
   const int count = (int)__ldg(b.counts + c);
   int nrows_tile = count - r_begin;
   nrows_tile = nrows_tile < 0 ? 0 : (nrows_tile > kStrTileRows ? kStrTileRows : nrows_tile);
@@ -88,7 +105,8 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   for (int i = tid; i < nrows_tile; i += kThreads) sm.str[i] = ld_stream(in + i);
   __syncthreads();
 
-  // 3. lengths (4 consecutive rows per thread) and block scan
+  // 3. lengths (consecutive rows per thread) and block scan.  A row that contributes no bytes
+  //    (NULL, empty, bad pointer) gets length 0 and is never touched again.
   uint32_t len[kStrPerThread];
   uint64_t tsum = 0;
   bool bad_heap = false;
@@ -196,69 +214,41 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   }
   if (tile_total == 0 || too_big) return;
 
-  // 6. output-centric gather.  Vector v covers global bytes [16v - mis, 16v - mis + 16) relative
-  //    to the tile's first output byte, so every vector is 16-byte aligned in out_data.
-  const uint32_t total = (uint32_t)tile_total;
+  // 6. gather bytes through the shared-memory stage.  Stage position p <-> global byte
+  //    out_data[base - mis + p], so p % 16 == 0 is a 16-byte aligned global address.
   const uint32_t mis = (uint32_t)(base & 15ull);
   uint8_t *gbase = job.out_data + (base - mis);
-  const uint32_t nvec = (mis + total + 15u) >> 4;
-  // rows >= nrows_tile have len 0, so off[] is non-decreasing over the whole [0, 1024] range
-  for (uint32_t v = tid; v < nvec; v += kThreads) {
-    const uint32_t vbeg = v << 4;                          // position + mis of the vector's first byte
-    const uint32_t lo = v ? vbeg - mis : 0u;               // tile-local byte range [lo, hi) owned by this vector
-    const uint32_t hi = (vbeg + 16u - mis) < total ? (vbeg + 16u - mis) : total;
-    int l = 0, h = kStrTileRows;                           // invariant: off[l] <= lo < off[h]
+  const uint32_t end = mis + (uint32_t)tile_total;
+  for (uint32_t w0 = 0; w0 < end; w0 += kStageBytes) {
+    const uint32_t w1 = w0 + kStageBytes;
 #pragma unroll 1
-    while (h - l > 1) {
-      const int m = (l + h) >> 1;
-      if (sm.off[m] <= lo) l = m; else h = m;
+    for (int i = tid; i < nrows_tile; i += kThreads) {  // lane -> consecutive rows
+      const uint32_t s0 = mis + sm.off[i], s1 = mis + sm.off[i + 1];
+      if (s1 == s0 || s1 <= w0 || s0 >= w1) continue;
+      const uint4 e = sm.str[i];
+      const uint8_t *src = e.x <= 12u ? reinterpret_cast<const uint8_t *>(&sm.str[i]) + 4
+                                      : job.heap_dev + ((((uint64_t)e.w << 32) | (uint64_t)e.z) - job.heap_host_base);
+      const uint32_t pay_end = MODE == DMB_STR_REF_BLOB ? s1 - 1u : s1;  // payload bytes [s0, pay_end)
+      const uint32_t lo = s0 > w0 ? s0 : w0;
+      const uint32_t hi = pay_end < w1 ? pay_end : w1;
+      if (hi > lo) copy_bytes(sm.stage + (lo - w0), src + (lo - s0), hi - lo);
+      if (MODE == DMB_STR_REF_BLOB && pay_end >= w0 && pay_end < w1) sm.stage[pay_end - w0] = 0;
     }
-    int r = l;
-    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-    uint32_t pos = lo;
-    uint32_t r_off = sm.off[r], r_end = sm.off[r + 1];
-#pragma unroll 1
-    while (pos < hi) {
-      if (r_end <= pos) {  // empty (or exhausted) row: next
-        ++r;
-        r_off = r_end;
-        r_end = sm.off[r + 1];
-        continue;
-      }
-      const uint32_t pay_end = MODE == DMB_STR_REF_BLOB ? r_end - 1u : r_end;  // the terminator byte stays 0
-      const uint32_t seg_end = pay_end < hi ? pay_end : hi;
-      if (seg_end > pos) {
-        const uint4 e = sm.str[r];
-        const uint32_t soff = pos - r_off;                 // offset inside the string
-        const uint32_t d = pos + mis - vbeg;               // destination byte inside the vector
-        const uint32_t k = seg_end - pos;                  // bytes to place (1..16)
-        const bool is_inline = e.x <= 12u;
-        const uint8_t *gsrc = job.heap_dev + ((((uint64_t)e.w << 32) | (uint64_t)e.z) - job.heap_host_base) + soff;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t a = d > 4u * j ? d : 4u * j;
-          const uint32_t bb = (d + k) < (4u * j + 4u) ? (d + k) : (4u * j + 4u);
-          if (bb > a) {
-            const uint32_t nb = bb - a;
-            const uint32_t val = is_inline ? inline_bytes4(e, soff + (a - d)) : global_bytes4(gsrc + (a - d), nb);
-            const uint32_t m = nb == 4u ? 0xffffffffu : ((1u << (8u * nb)) - 1u);
-            const uint32_t piece = (val & m) << (8u * (a - 4u * j));
-            if (j == 0) w0 |= piece; else if (j == 1) w1 |= piece; else if (j == 2) w2 |= piece; else w3 |= piece;
-          }
-        }
-      }
-      pos = (MODE == DMB_STR_REF_BLOB && seg_end == pay_end && pay_end < hi) ? r_end : seg_end;
-    }
-    const bool full = (v > 0 || mis == 0) && (vbeg + 16u - mis <= total);
-    if (full) {
-      st_stream(reinterpret_cast<uint4 *>(gbase + vbeg), make_uint4(w0, w1, w2, w3));
-    } else {  // the neighbouring tiles own the other bytes of this vector
-      const uint32_t q0 = lo + mis - vbeg, q1 = hi + mis - vbeg;
-      for (uint32_t q = q0; q < q1; ++q) {
-        const uint32_t word = q < 4 ? w0 : (q < 8 ? w1 : (q < 12 ? w2 : w3));
-        gbase[vbeg + q] = (uint8_t)(word >> (8u * (q & 3u)));
+    __syncthreads();
+    const uint32_t lo = w0 > mis ? w0 : mis;
+    const uint32_t hi = w1 < end ? w1 : end;
+    for (uint32_t v = tid; v < kStageBytes / 16; v += kThreads) {
+      const uint32_t p = w0 + 16u * v;
+      if (p >= hi) break;
+      if (p + 16u <= lo) continue;
+      if (p >= lo && p + 16u <= hi) {
+        st_stream(reinterpret_cast<uint4 *>(gbase + p), *reinterpret_cast<const uint4 *>(sm.stage + 16u * v));
+      } else {  // the neighbouring tiles own the other bytes of this vector
+        const uint32_t q0 = p > lo ? p : lo, q1 = (p + 16u) < hi ? (p + 16u) : hi;
+        for (uint32_t q = q0; q < q1; ++q) gbase[q] = sm.stage[q - w0];
       }
     }
+    if (w1 < end) __syncthreads();
   }
 }
 
@@ -289,7 +279,7 @@ make_string_t_kernel(const uint32_t *__restrict__ lengths, const uint64_t *__res
 using namespace dmb;
 
 extern "C" size_t dmb_dev_string_scratch_bytes(int64_t nchunks) {
-  return (size_t)(2 + 2 * (nchunks > 0 ? nchunks : 0)) * sizeof(unsigned long long);
+  return (size_t)(2 + kStrTilesPerChunk * (nchunks > 0 ? nchunks : 0)) * sizeof(unsigned long long);
 }
 
 extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_t *counts,
@@ -298,7 +288,7 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
   if (!job) { set_error("dmb_dev_string_batch: job is null"); return -1; }
   cudaStream_t st = (cudaStream_t)stream;
   if (nchunks <= 0 || nrows <= 0) return 0;
-  const int64_t ntiles = 2 * nchunks;
+  const int64_t ntiles = (int64_t)kStrTilesPerChunk * nchunks;
   if (check_cuda(cudaMemsetAsync(scratch, 0, dmb_dev_string_scratch_bytes(nchunks), st), "string scratch memset")) return -1;
   BatchView b{counts, row_off, nchunks, nrows};
   auto launch = [&](auto kernel) -> int32_t {

@@ -195,7 +195,7 @@ int32_t dmb_dev_fixed_batch(const dmb_fixed_job *jobs_dev, const dmb_fixed_job *
 int32_t dmb_op_out_width(int32_t op);
 int32_t dmb_phys_width(int32_t phys);
 
-/* K5: string_t -> utf8 offsets + data, single pass (block scan + decoupled look-back).
+/* K5: string_t -> utf8 offsets + data, single pass (block scan + decoupled look-back, 512-row tiles).
  *   scratch   device, >= dmb_dev_string_scratch_bytes(nchunks) bytes, zeroed by the call
  * Replaces src/duckdb_native.c:597-603 (string_t read) and :2474-2510 / :2699-2755. */
 size_t dmb_dev_string_scratch_bytes(int64_t nchunks);
