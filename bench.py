@@ -159,11 +159,15 @@ class DeviceStep:
         self.db.run_fixed(self.plan)
         if record:
             e1.record()
+        marks = []
         for so in self.strings:
             self.db.run_string(so)
+            if record:
+                m = torch.cuda.Event(enable_timing=True)
+                m.record()
+                marks.append(m)
         if record:
-            e2.record()
-            return e0, e1, e2
+            return e0, e1, marks[-1], marks
         return None
 
     def check(self):
@@ -325,8 +329,14 @@ def run_ours(args, rank, local_rank, world):
     dev_ms = ev_a.elapsed_time(ev_b)
     clocks = sampler.stop() if rank == 0 else None
     step.check()
-    fixed_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in spans) / args.steps
-    string_ms = sum(e1.elapsed_time(e2) for _, e1, e2 in spans) / args.steps
+    fixed_ms = sum(sp[0].elapsed_time(sp[1]) for sp in spans) / args.steps
+    string_ms = sum(sp[1].elapsed_time(sp[2]) for sp in spans) / args.steps
+    string_cols = [db.batch.columns[so.col].name for so in step.strings]
+    string_col_ms = {}
+    for ci, nm in enumerate(string_cols):
+        string_col_ms[nm] = sum((sp[1] if ci == 0 else sp[3][ci - 1]).elapsed_time(sp[3][ci]) for sp in spans) / args.steps
+    string_col_alg = {db.batch.columns[so.col].name: 16 * n_rows_dev + db.meta[so.col]["ptr_len"] + 4 * (n_rows_dev + 1) + db.meta[so.col]["total_len"]
+                      for so in step.strings} if (n_rows_dev := db.nrows) else {}
     dev_ms_max = max_over_ranks(dev_ms)
     value = world * n * args.steps / (dev_ms_max / 1e3)
     step_alg_fixed, step_alg_string = step.alg_fixed, step.alg_string
@@ -441,7 +451,9 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": n_launches * args.steps,
         "clocks": clocks,
         "kernel_ms_per_step": {"fixed_batch_kernel": fixed_ms, "string_batch_kernel": string_ms,
-                               "fixed_gb_per_s": step_alg_fixed / 1e6 / fixed_ms, "string_gb_per_s": step_alg_string / 1e6 / string_ms},
+                               "fixed_gb_per_s": step_alg_fixed / 1e6 / fixed_ms, "string_gb_per_s": step_alg_string / 1e6 / string_ms,
+                               "string_columns": {nm: {"ms": string_col_ms[nm], "gb_per_s": string_col_alg[nm] / 1e6 / string_col_ms[nm]}
+                                                  for nm in string_col_ms}},
         "setup_s": setup_s,
     }
     print(json.dumps(line), flush=True)

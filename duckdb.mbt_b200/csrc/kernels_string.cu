@@ -1,18 +1,24 @@
 // K5 string_unpack: duckdb_string_t[16 B] -> Arrow utf8 (offsets + data) in ONE pass.
 //
 // Tile = 512 consecutive rows of one chunk (four tiles per 2048-row vector).  A CTA
-//   1. takes a ticket (tiles are processed in ticket order => look-back always makes progress),
+//   1. takes tile blockIdx.x (CTAs are dispatched in blockIdx order => look-back always makes progress),
 //   2. loads the tile's string_t into shared memory with coalesced 128-bit loads (read once),
-//   3. block-scans the (validity-masked) lengths into tile-local offsets,
+//   3. block-scans the (validity-masked) lengths into tile-local offsets and, in the same scan, a
+//      running maximum that gives every row the first row of its RUN: a maximal sequence of rows
+//      whose source bytes follow one another in the heap (DuckDB fills its string heap in row
+//      order, so runs are long; an inlined string or a scattered pointer starts a new run),
 //   4. publishes its aggregate and resolves its exclusive base by decoupled look-back over the
 //      predecessors' 64-bit status words (flag | value in one word, so no fences are needed),
 //   5. writes offsets (coalesced), and
-//   6. gathers the bytes row by row into a shared-memory stage laid out with the destination's
-//      16-byte phase (lane i of a warp takes row i, so a warp reads one contiguous stretch of the
-//      heap; inline bytes come from the shared-memory copy of string_t, pointer strings from the
-//      device heap with the host pointer rebased; aligned 32-bit loads, five in flight, funnel
-//      shifted to the stage's word alignment), then writes the stage with coalesced 128-bit
-//      streaming stores.
+//   6. gathers the bytes OUTPUT-centrically: a thread owns one 16-byte aligned vector of the
+//      output stream.  Rows first publish, per vector, which row holds the vector's first byte
+//      (a 2-byte map entry: O(1) lookup, no search).  A vector that lies inside one run (the
+//      common case) is three aligned 64-bit loads, two funnel shifts and one 128-bit streaming
+//      store, with no branches on the data.  Vectors that straddle a run boundary are queued in
+//      a shared-memory list and finished afterwards by a dense loop that walks their rows and
+//      merges the pieces with byte masks, so the divergent work is paid per such vector and not
+//      per warp.  Consecutive threads read consecutive heap bytes and write consecutive
+//      vectors; the data bytes never touch shared memory.
 //
 // Replaces the reference's per-cell string_t read src/duckdb_native.c:597-603 and the two-pass
 // malloc/strlen/memcpy getters :2474-2510 and :2699-2755.  DMB_STR_REF_BLOB reproduces the
@@ -25,73 +31,113 @@ namespace dmb {
 constexpr int kStrTileRows = 512;
 constexpr int kStrTilesPerChunk = kVec / kStrTileRows;
 constexpr int kStrPerThread = kStrTileRows / kThreads;  // 2 consecutive rows per thread in the scan
-constexpr int kStageBytes = 16384;
+constexpr int kMapVecs = 2048;                          // output vectors per window (32 KiB of utf8 data)
+constexpr uint32_t kMaxRowBytes = 1u << 22;             // tile-local sums stay below 2^32 (512 rows * 4 MiB)
 
 constexpr uint64_t kFlagAggregate = 1ull << 62;
 constexpr uint64_t kFlagPrefix = 2ull << 62;
 constexpr uint64_t kValueMask = (1ull << 62) - 1ull;
 
-// scratch layout (uint64 words): [0] ticket  [1] error flags  [2..] tile status
+// scratch layout (uint64 words): [0] unused  [1] error flags  [2..] tile status
 enum { kErrTileTooBig = 1, kErrOffsetOverflow = 2, kErrHeapRange = 4 };
 
 struct StrSmem {
-  uint4 str[kStrTileRows];           // string_t copies
-  uint32_t off[kStrTileRows + 4];    // tile-local exclusive offsets; off[kStrTileRows] = tile total
-  alignas(16) uint8_t stage[kStageBytes + 16];
-  uint64_t warp_sum[kThreads / 32];
+  uint4 str[kStrTileRows];            // string_t copies
+  uint64_t src[kStrTileRows];         // device (generic) address of every row's first byte
+  uint32_t off[kStrTileRows + 4];     // tile-local exclusive offsets; off[kStrTileRows] = tile total
+  uint16_t run[kStrTileRows];         // first row of the run a row belongs to
+  union {
+    struct {
+      uint16_t first_row[kMapVecs + 2];  // per output vector of the window: the row that holds its first byte
+      uint16_t slow[kMapVecs];           // window-local ids of the vectors that straddle a run boundary
+    };
+    alignas(16) uint8_t stage[kStrTileRows * 13 + 32];  // all-inline tiles: the tile's whole output (<= 13 B per row)
+  };
+  uint4 low_mask[17];                 // low_mask[d]: bytes < d of a 16-byte vector are 0xff
+  uint32_t warp_sum[kThreads / 32];
+  uint32_t warp_run[kThreads / 32];
+  uint32_t nslow;
   uint64_t base;
-  int64_t tile;
 };
 
 __device__ __forceinline__ uint64_t ld_status(const unsigned long long *p) {
   return *reinterpret_cast<const volatile unsigned long long *>(p);
 }
 
-// Copy len bytes from src (generic address: device heap or the shared-memory string_t copy, any
-// alignment) to dst in shared memory (any alignment).  Whole destination words are written with
-// one store each from two aligned source words (funnel shift), five source loads in flight; only
-// the ragged ends go byte by byte.  Source words are read whole: the heap copy carries >= 16
-// bytes of padding and the string_t copy is followed by other shared-memory fields.
-__device__ __forceinline__ void copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t len) {
-  uint32_t i = 0;
-  uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
-  if (head > len) head = len;
-  for (; i < head; ++i) dst[i] = src[i];
-  const uint32_t nwords = (len - i) >> 2;
-  if (nwords) {
-    const uint8_t *s = src + i;
-    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3u) * 8u;
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
-    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + i);
-    const uint32_t last = sh ? nwords : nwords - 1u;  // highest source word index that holds needed bytes
-#pragma unroll 1
-    for (uint32_t w = 0; w < nwords; w += 4) {
-      const uint32_t x0 = sw[w];
-      const uint32_t x1 = w + 1 <= last ? sw[w + 1] : 0u;
-      const uint32_t x2 = w + 2 <= last ? sw[w + 2] : 0u;
-      const uint32_t x3 = w + 3 <= last ? sw[w + 3] : 0u;
-      const uint32_t x4 = w + 4 <= last ? sw[w + 4] : 0u;
-      dw[w] = __funnelshift_r(x0, x1, sh);
-      if (w + 1 < nwords) dw[w + 1] = __funnelshift_r(x1, x2, sh);
-      if (w + 2 < nwords) dw[w + 2] = __funnelshift_r(x2, x3, sh);
-      if (w + 3 < nwords) dw[w + 3] = __funnelshift_r(x3, x4, sh);
-    }
-    i += nwords * 4u;
-  }
-  for (; i < len; ++i) dst[i] = src[i];
+// (y:x) >> s bits, s in {0, 8, ..., 56}
+__device__ __forceinline__ uint64_t funnel64(uint64_t x, uint64_t y, uint32_t s) {
+  const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32), y0 = (uint32_t)y, y1 = (uint32_t)(y >> 32);
+  const bool up = s >= 32u;
+  const uint32_t a = up ? x1 : x0, b = up ? y0 : x1, c = up ? y1 : y0;
+  const uint32_t lo = __funnelshift_r(a, b, s), hi = __funnelshift_r(b, c, s);  // shift taken mod 32
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// 16 source bytes starting at sp (any alignment) as two 64-bit words.  Aligned loads only; the
+// word past the 16 bytes is read only when it holds needed bytes.
+__device__ __forceinline__ void load16(const uint8_t *sp, uint64_t &w0, uint64_t &w1) {
+  const uintptr_t vs = reinterpret_cast<uintptr_t>(sp);
+  const uint32_t t = (uint32_t)vs & 7u;
+  const uint64_t *ab = reinterpret_cast<const uint64_t *>(vs - t);
+  const uint64_t x0 = ab[0], x1 = ab[1], x2 = t ? ab[2] : 0ull;
+  w0 = funnel64(x0, x1, 8u * t);
+  w1 = funnel64(x1, x2, 8u * t);
+}
+
+// Merge source bytes [sp, sp + (d1 - d0)) into bytes [d0, d1) of the 16-byte vector (w0, w1).
+// Whole aligned 64-bit words are read, but only words that hold needed bytes, so nothing outside
+// the heap copy (+ its >= 16 bytes of padding) or the shared-memory string_t tile is touched.
+// low_mask is the shared-memory byte-mask table.
+__device__ __forceinline__ void emit(uint64_t &w0, uint64_t &w1, const uint8_t *sp, uint32_t d0, uint32_t d1,
+                                     const uint4 *low_mask) {
+  const uintptr_t vs = reinterpret_cast<uintptr_t>(sp) - d0;  // source address of vector byte 0
+  const uint32_t t = (uint32_t)vs & 7u;
+  const uint64_t *ab = reinterpret_cast<const uint64_t *>(vs - t);
+  const uint32_t f = d0 + t, l = d1 + t;  // needed source bytes, relative to ab: [f, l)
+  const uint64_t x0 = f < 8u ? ab[0] : 0ull;
+  const uint64_t x1 = (f < 16u && l > 8u) ? ab[1] : 0ull;
+  const uint64_t x2 = l > 16u ? ab[2] : 0ull;  // l > 16 implies t != 0
+  const uint64_t v0 = funnel64(x0, x1, 8u * t), v1 = funnel64(x1, x2, 8u * t);
+  const uint4 hi = low_mask[d1], lo = low_mask[d0];
+  const uint64_t m0 = (((uint64_t)hi.y << 32) | hi.x) & ~(((uint64_t)lo.y << 32) | lo.x);
+  const uint64_t m1 = (((uint64_t)hi.w << 32) | hi.z) & ~(((uint64_t)lo.w << 32) | lo.z);
+  w0 |= v0 & m0;
+  w1 |= v1 & m1;
+}
+
+// bytes [nb0, nb1) of a 32-bit word, 0 <= nb0 < nb1 <= 4
+__device__ __forceinline__ uint32_t byte_mask32(uint32_t nb0, uint32_t nb1) {
+  const uint32_t hi = nb1 >= 4u ? 0xffffffffu : ((1u << (8u * nb1)) - 1u);
+  return hi & ~((1u << (8u * nb0)) - 1u);
+}
+
+// place `val` (already positioned) into a 32-bit word of the zeroed inline stage: whole word ->
+// store, part -> OR (neighbouring rows own the other bytes)
+__device__ __forceinline__ void put32(uint32_t *w, uint32_t val, int nb0, int nb1) {
+  nb0 = nb0 < 0 ? 0 : nb0;
+  nb1 = nb1 > 4 ? 4 : nb1;
+  if (nb1 <= nb0) return;
+  if (nb1 - nb0 == 4) *w = val;
+  else atomicOr(w, val & byte_mask32((uint32_t)nb0, (uint32_t)nb1));
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __launch_bounds__(kThreads, 6)
 string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles) {
   __shared__ StrSmem sm;
   unsigned long long *status = scratch + 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  if (tid == 0) sm.tile = (int64_t)atomicAdd(scratch, 1ull);
-  __syncthreads();
-  const int64_t tile = sm.tile;
+  // Tiles are taken in blockIdx order: the hardware dispatches CTAs of a 1-D grid in increasing
+  // blockIdx, so every predecessor a look-back waits for is already resident (the assumption
+  // CUB's single-pass scan makes as well).
+  const int64_t tile = (int64_t)blockIdx.x;
   if (tile >= ntiles) return;
+  if (tid < 17) {
+    const uint32_t d = (uint32_t)tid;
+    auto m = [&](uint32_t w) { return d >= 4u * w + 4u ? 0xffffffffu : (d <= 4u * w ? 0u : ((1u << (8u * (d - 4u * w))) - 1u)); };
+    sm.low_mask[tid] = make_uint4(m(0), m(1), m(2), m(3));
+  }
   const int64_t c = tile / kStrTilesPerChunk;
   const int r_begin = (int)(tile % kStrTilesPerChunk) * kStrTileRows;
   const int count = (int)__ldg(b.counts + c);
@@ -101,75 +147,122 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   const uint4 *in = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(job.in) + vd.data_off) + r_begin;
   const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
 
-  // 2. string_t tile -> shared memory
-  for (int i = tid; i < nrows_tile; i += kThreads) sm.str[i] = ld_stream(in + i);
-  __syncthreads();
-
-  // 3. lengths (consecutive rows per thread) and block scan.  A row that contributes no bytes
-  //    (NULL, empty, bad pointer) gets length 0 and is never touched again.
+  // 2. + 3. every thread loads its own consecutive rows (and lane 0 the row before them) straight
+  //    into registers, together with the validity words, then derives length and source address;
+  //    a row that contributes no bytes (NULL, empty, bad pointer) gets length 0 and is never
+  //    touched again.  The shared-memory copy serves the inlined strings and the gather.
+  int flags = 0;  // 1: a pointer (non-inlined) row is present  2: bad heap pointer  4: oversized row
+  uint4 ent[kStrPerThread + 1];
+  bool ok[kStrPerThread + 1];
+#pragma unroll
+  for (int k = 0; k <= kStrPerThread; ++k) {
+    const int i = tid * kStrPerThread + k - 1;  // k = 0: the row before this thread's rows
+    ent[k] = make_uint4(0, 0, 0, 0);
+    ok[k] = false;
+    if (i >= 0 && i < nrows_tile && (k > 0 || lane == 0)) {
+      ent[k] = ld_stream(in + i);
+      const int row = r_begin + i;
+      ok[k] = mask ? ((__ldg(mask + (row >> 6)) >> (row & 63)) & 1ull) : true;
+    }
+  }
+#pragma unroll
+  for (int k = 1; k <= kStrPerThread; ++k) {
+    const int i = tid * kStrPerThread + k - 1;
+    if (i < nrows_tile) sm.str[i] = ent[k];
+  }
+  if (MODE == DMB_STR_REF_BLOB) __syncthreads();  // strlen below reads inlined bytes of other threads' rows
+  auto row_info = [&](int i, const uint4 &e, bool valid, uint32_t &l_out, uint64_t &src_out) {
+    l_out = 0;
+    src_out = 0;
+    if (i < 0 || i >= nrows_tile) return;
+    if (valid) {
+      uint32_t l = e.x;
+      const uint8_t *src = reinterpret_cast<const uint8_t *>(&sm.str[i]) + 4;
+      if (l > 12u) {
+        const uint64_t p = ((uint64_t)e.w << 32) | (uint64_t)e.z;
+        const uint64_t rel = p - job.heap_host_base;
+        if (l >= kMaxRowBytes) { flags |= 4; l = 0; }
+        else if (p < job.heap_host_base || rel + l > job.heap_len) { flags |= 2; l = 0; }
+        src = job.heap_dev + rel;
+        if (l) {  // pull the heap bytes towards L2 while the scan and the look-back run
+          flags |= 1;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + l - 1u));
+        }
+      }
+      if (MODE == DMB_STR_REF_BLOB) {  // strlen() of the malloc'ed copy: stop at an embedded NUL
+        uint32_t n = 0;
+        while (n < l && src[n] != 0) ++n;
+        l = n;
+      }
+      l_out = l;
+      src_out = reinterpret_cast<uint64_t>(src);
+    }
+    if (MODE == DMB_STR_REF_BLOB) l_out += 1;  // terminator; a NULL row is a lone '\0'
+  };
   uint32_t len[kStrPerThread];
-  uint64_t tsum = 0;
-  bool bad_heap = false;
+  uint64_t srcp[kStrPerThread];
+  uint32_t tsum = 0;
 #pragma unroll
   for (int k = 0; k < kStrPerThread; ++k) {
-    const int i = tid * kStrPerThread + k;
-    len[k] = 0;
-    if (i < nrows_tile) {
-      const int row = r_begin + i;
-      const bool valid = mask ? ((__ldg(mask + (row >> 6)) >> (row & 63)) & 1ull) : true;
-      if (valid) {
-        const uint4 e = sm.str[i];
-        uint32_t l = e.x;
-        const uint8_t *src = reinterpret_cast<const uint8_t *>(&sm.str[i]) + 4;
-        if (l > 12u) {
-          const uint64_t p = ((uint64_t)e.w << 32) | (uint64_t)e.z;
-          const uint64_t rel = p - job.heap_host_base;
-          if (p < job.heap_host_base || rel + l > job.heap_len) { bad_heap = true; l = 0; }
-          src = job.heap_dev + rel;
-        }
-        if (MODE == DMB_STR_REF_BLOB) {  // strlen() of the malloc'ed copy: stop at an embedded NUL
-          uint32_t n = 0;
-          while (n < l && src[n] != 0) ++n;
-          l = n;
-        }
-        len[k] = l;
-      }
-      if (MODE == DMB_STR_REF_BLOB) len[k] += 1;  // terminator; a NULL row is a lone '\0'
-    }
+    row_info(tid * kStrPerThread + k, ent[k + 1], ok[k + 1], len[k], srcp[k]);
+    sm.src[tid * kStrPerThread + k] = srcp[k];
     tsum += len[k];
   }
-  uint64_t incl = tsum;
+  // run starts: row i starts a run unless its bytes directly follow those of row i-1
+  uint32_t start_row[kStrPerThread];  // i + 1 when row i starts a run, else 0 (max-scanned below)
+  {
+    uint32_t pl = __shfl_up_sync(0xffffffffu, len[kStrPerThread - 1], 1);
+    uint64_t ps = __shfl_up_sync(0xffffffffu, srcp[kStrPerThread - 1], 1);
+    if (lane == 0) {  // the previous warp's last row: recompute from this lane's own copy of it
+      const int keep = flags;
+      row_info(tid * kStrPerThread - 1, ent[0], ok[0], pl, ps);
+      flags = keep;
+    }
+#pragma unroll
+    for (int k = 0; k < kStrPerThread; ++k) {
+      const bool follows = MODE != DMB_STR_REF_BLOB && pl != 0u && srcp[k] == ps + pl;
+      start_row[k] = (len[k] != 0u && !follows) ? (uint32_t)(tid * kStrPerThread + k) + 1u : 0u;
+      if (len[k] != 0u) { pl = len[k]; ps = srcp[k]; } else { pl = 0u; }
+    }
+  }
+  uint32_t incl = tsum;
+  uint32_t rmax = start_row[0] > start_row[kStrPerThread - 1] ? start_row[0] : start_row[kStrPerThread - 1];
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    uint64_t n = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += n;
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+    const uint32_t m = __shfl_up_sync(0xffffffffu, rmax, d);
+    if (lane >= d) { incl += n; rmax = rmax > m ? rmax : m; }
   }
-  if (lane == 31) sm.warp_sum[warp] = incl;
-  __syncthreads();
-  uint64_t warp_excl = 0, tile_total = 0;
+  if (lane == 31) { sm.warp_sum[warp] = incl; sm.warp_run[warp] = rmax; }
+  const uint32_t rmax_excl_lane = __shfl_up_sync(0xffffffffu, rmax, 1);
+  const int tile_flags = __syncthreads_or(flags);
+  uint32_t warp_excl = 0, tile_total = 0, run_excl = 0;
 #pragma unroll
   for (int w = 0; w < kThreads / 32; ++w) {
-    uint64_t s = sm.warp_sum[w];
-    if (w < warp) warp_excl += s;
+    const uint32_t s = sm.warp_sum[w];
+    const uint32_t m = sm.warp_run[w];
+    if (w < warp) { warp_excl += s; run_excl = run_excl > m ? run_excl : m; }
     tile_total += s;
   }
-  const uint64_t excl = warp_excl + incl - tsum;
-  const bool too_big = tile_total > 0xfffffff0ull;
-  if (too_big && tid == 0) atomicOr(scratch + 1, (unsigned long long)kErrTileTooBig);
-  if (bad_heap) atomicOr(scratch + 1, (unsigned long long)kErrHeapRange);
+  if (lane > 0) run_excl = run_excl > rmax_excl_lane ? run_excl : rmax_excl_lane;
+  if (tid == 0 && (tile_flags & 6))
+    atomicOr(scratch + 1, (unsigned long long)(((tile_flags & 2) ? kErrHeapRange : 0) | ((tile_flags & 4) ? kErrTileTooBig : 0)));
+  const uint32_t my_off = warp_excl + incl - tsum;
   {
-    uint32_t o = (uint32_t)excl;
+    uint32_t o = my_off, run = run_excl;
 #pragma unroll
     for (int k = 0; k < kStrPerThread; ++k) {
       sm.off[tid * kStrPerThread + k] = o;
       o += len[k];
+      run = run > start_row[k] ? run : start_row[k];
+      sm.run[tid * kStrPerThread + k] = (uint16_t)run;  // (first row of the run) + 1; only read for non-empty rows
     }
     if (tid == kThreads - 1) sm.off[kStrTileRows] = o;
   }
 
   // 4. decoupled look-back (warp 0)
   if (warp == 0) {
-    uint64_t agg = tile_total & kValueMask;
+    const uint64_t agg = (uint64_t)tile_total;
     if (lane == 0) atomicExch(status + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | agg);
     uint64_t prefix = 0;
     if (tile > 0) {
@@ -212,43 +305,141 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     }
     if (tile == ntiles - 1 && tid == 0 && job.total_bytes) *job.total_bytes = base + tile_total;
   }
-  if (tile_total == 0 || too_big) return;
+  if (tile_total == 0) return;
 
-  // 6. gather bytes through the shared-memory stage.  Stage position p <-> global byte
-  //    out_data[base - mis + p], so p % 16 == 0 is a 16-byte aligned global address.
+  // 6. output-centric gather.  Vector v covers tile-local bytes [16v - mis, 16v - mis + 16), i.e. a
+  //    16-byte aligned vector of out_data; L(v) = max(16v - mis, 0) is its first owned byte.
+  const uint32_t total = tile_total;
   const uint32_t mis = (uint32_t)(base & 15ull);
   uint8_t *gbase = job.out_data + (base - mis);
-  const uint32_t end = mis + (uint32_t)tile_total;
-  for (uint32_t w0 = 0; w0 < end; w0 += kStageBytes) {
-    const uint32_t w1 = w0 + kStageBytes;
+  const uint32_t nvec = (mis + total + 15u) >> 4;
+  if ((tile_flags & 1) == 0) {
+    // All rows are inlined (<= 12 payload bytes each, in registers): one lane per row shifts its
+    // bytes to the stage's word phase and ORs them into a zeroed shared-memory image of the tile's
+    // output, which then leaves with coalesced 128-bit stores.
+    const uint32_t end = mis + total;
+    const uint32_t nstage = (end + 15u) >> 4;
+    uint4 *sv = reinterpret_cast<uint4 *>(sm.stage);
+    for (uint32_t i = tid; i < nstage; i += kThreads) sv[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    uint32_t *sw = reinterpret_cast<uint32_t *>(sm.stage);
 #pragma unroll 1
-    for (int i = tid; i < nrows_tile; i += kThreads) {  // lane -> consecutive rows
+    for (int i = tid; i < nrows_tile; i += kThreads) {
       const uint32_t s0 = mis + sm.off[i], s1 = mis + sm.off[i + 1];
-      if (s1 == s0 || s1 <= w0 || s0 >= w1) continue;
+      const uint32_t pay_end = MODE == DMB_STR_REF_BLOB ? s1 - 1u : s1;  // the terminator stays 0
+      if (pay_end <= s0) continue;
       const uint4 e = sm.str[i];
-      const uint8_t *src = e.x <= 12u ? reinterpret_cast<const uint8_t *>(&sm.str[i]) + 4
-                                      : job.heap_dev + ((((uint64_t)e.w << 32) | (uint64_t)e.z) - job.heap_host_base);
-      const uint32_t pay_end = MODE == DMB_STR_REF_BLOB ? s1 - 1u : s1;  // payload bytes [s0, pay_end)
-      const uint32_t lo = s0 > w0 ? s0 : w0;
-      const uint32_t hi = pay_end < w1 ? pay_end : w1;
-      if (hi > lo) copy_bytes(sm.stage + (lo - w0), src + (lo - s0), hi - lo);
-      if (MODE == DMB_STR_REF_BLOB && pay_end >= w0 && pay_end < w1) sm.stage[pay_end - w0] = 0;
+      const uint32_t a = s0 & 3u, sh = 8u * a;
+      const int l = (int)(pay_end - s0);
+      uint32_t *w = sw + (s0 >> 2);
+      put32(w, e.y << sh, (int)a, (int)a + l);
+      put32(w + 1, __funnelshift_l(e.y, e.z, sh), (int)a - 4, (int)a + l - 4);
+      put32(w + 2, __funnelshift_l(e.z, e.w, sh), (int)a - 8, (int)a + l - 8);
+      put32(w + 3, __funnelshift_l(e.w, 0u, sh), (int)a - 12, (int)a + l - 12);
     }
     __syncthreads();
-    const uint32_t lo = w0 > mis ? w0 : mis;
-    const uint32_t hi = w1 < end ? w1 : end;
-    for (uint32_t v = tid; v < kStageBytes / 16; v += kThreads) {
-      const uint32_t p = w0 + 16u * v;
-      if (p >= hi) break;
-      if (p + 16u <= lo) continue;
-      if (p >= lo && p + 16u <= hi) {
-        st_stream(reinterpret_cast<uint4 *>(gbase + p), *reinterpret_cast<const uint4 *>(sm.stage + 16u * v));
+    for (uint32_t v = tid; v < nstage; v += kThreads) {
+      const uint32_t p = 16u * v;
+      if (p >= mis && p + 16u <= end) {
+        st_stream(reinterpret_cast<uint4 *>(gbase + p), sv[v]);
       } else {  // the neighbouring tiles own the other bytes of this vector
-        const uint32_t q0 = p > lo ? p : lo, q1 = (p + 16u) < hi ? (p + 16u) : hi;
-        for (uint32_t q = q0; q < q1; ++q) gbase[q] = sm.stage[q - w0];
+        const uint32_t b0 = p > mis ? p : mis, b1 = (p + 16u) < end ? (p + 16u) : end;
+        for (uint32_t q = b0; q < b1; ++q) gbase[q] = sm.stage[q];
       }
     }
-    if (w1 < end) __syncthreads();
+    return;
+  }
+  for (uint32_t q0 = 0; q0 < nvec; q0 += kMapVecs) {
+    const uint32_t q1 = q0 + kMapVecs < nvec ? q0 + kMapVecs : nvec;
+    const uint32_t qmap = q1 < nvec ? q1 + 1u : q1;  // one entry past the window: the fast-path test looks at v + 1
+    if (tid == 0) sm.nslow = 0;
+    // (a) every non-empty row publishes the vectors v with L(v) inside the row
+    {
+      uint32_t o = my_off;
+#pragma unroll
+      for (int k = 0; k < kStrPerThread; ++k) {
+        const uint32_t start = o, stop = o + len[k];
+        o = stop;
+        if (stop == start) continue;
+        uint32_t qa = start == 0u ? 0u : (start + mis + 15u) >> 4;  // first v with L(v) >= start
+        uint32_t qb = (stop + mis + 15u) >> 4;                      // first v with L(v) >= stop
+        qa = qa > q0 ? qa : q0;
+        qb = qb < qmap ? qb : qmap;
+        for (uint32_t q = qa; q < qb; ++q) sm.first_row[q - q0] = (uint16_t)(tid * kStrPerThread + k);
+      }
+    }
+    __syncthreads();
+    // (b) fast pass: vectors inside one run; the others are queued
+    for (uint32_t vb = q0; vb < q1; vb += kThreads) {
+      const uint32_t v = vb + tid;
+      bool slow = false;
+      if (v < q1) {
+        const uint32_t vbeg = v << 4;
+        const bool whole = (v > 0 || mis == 0) && (vbeg + 16u - mis <= total) && (v + 1u < nvec);
+        const int r = sm.first_row[v - q0];
+        slow = !whole || sm.run[r] != sm.run[sm.first_row[v + 1u - q0]];
+        if (!slow) {
+          uint64_t w0, w1;
+          load16(reinterpret_cast<const uint8_t *>(sm.src[r]) + (vbeg - mis - sm.off[r]), w0, w1);
+          st_stream(reinterpret_cast<uint4 *>(gbase + vbeg),
+                    make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32)));
+        }
+      }
+      const uint32_t ballot = __ballot_sync(0xffffffffu, slow);
+      if (ballot) {
+        uint32_t pos = 0;
+        if (lane == 0) pos = atomicAdd(&sm.nslow, (uint32_t)__popc(ballot));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (slow) sm.slow[pos + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)(v - q0);
+      }
+    }
+    __syncthreads();
+    // (c) dense pass over the queued vectors: walk the rows, merge the pieces
+    const uint32_t nslow = sm.nslow;
+#pragma unroll 1
+    for (uint32_t idx = tid; idx < nslow; idx += kThreads) {
+      const uint32_t v = q0 + sm.slow[idx];
+      const uint32_t vbeg = v << 4;                    // position + mis of the vector's first byte
+      const uint32_t lo = v ? vbeg - mis : 0u;         // tile-local bytes [lo, hi) owned by this vector
+      const uint32_t hi = (vbeg + 16u - mis) < total ? (vbeg + 16u - mis) : total;
+      int r = sm.first_row[v - q0];
+      uint64_t w0 = 0, w1 = 0;
+      uint32_t seg_pos = lo;                           // current source stream covers [seg_pos, seg_end)
+      const uint8_t *sp = reinterpret_cast<const uint8_t *>(sm.src[r]) + (lo - sm.off[r]);
+      uint32_t row_end = sm.off[r + 1];
+      uint32_t seg_end = MODE == DMB_STR_REF_BLOB ? row_end - 1u : row_end;  // payload end; the terminator stays 0
+#pragma unroll 1
+      while (row_end < hi) {
+        int r2 = r + 1;                                // next non-empty row (off[] is packed: it starts at row_end)
+        uint32_t o2 = sm.off[r2 + 1];
+        while (o2 == row_end) { ++r2; o2 = sm.off[r2 + 1]; }
+        const bool same_run = sm.run[r2] == sm.run[r];
+        r = r2;
+        if (same_run) {                                // heap bytes continue: same stream
+          row_end = o2;
+          seg_end = o2;
+          continue;
+        }
+        if (seg_end > seg_pos) emit(w0, w1, sp, seg_pos + mis - vbeg, seg_end + mis - vbeg, sm.low_mask);
+        seg_pos = row_end;
+        sp = reinterpret_cast<const uint8_t *>(sm.src[r2]);
+        row_end = o2;
+        seg_end = MODE == DMB_STR_REF_BLOB ? o2 - 1u : o2;
+      }
+      {
+        const uint32_t e = seg_end < hi ? seg_end : hi;
+        if (e > seg_pos) emit(w0, w1, sp, seg_pos + mis - vbeg, e + mis - vbeg, sm.low_mask);
+      }
+      const bool full = (v > 0 || mis == 0) && (vbeg + 16u - mis <= total);
+      if (full) {
+        st_stream(reinterpret_cast<uint4 *>(gbase + vbeg),
+                  make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32)));
+      } else {  // the neighbouring tiles own the other bytes of this vector
+        const uint32_t b0 = lo + mis - vbeg, b1 = hi + mis - vbeg;
+        for (uint32_t q = b0; q < b1; ++q) gbase[vbeg + q] = (uint8_t)((q < 8 ? w0 : w1) >> (8u * (q & 7u)));
+      }
+    }
+    if (q1 < nvec) __syncthreads();
   }
 }
 
