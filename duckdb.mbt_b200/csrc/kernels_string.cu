@@ -28,11 +28,17 @@
 
 namespace dmb {
 
-constexpr int kStrTileRows = 512;
+#ifndef DMB_STR_TILE_ROWS
+#define DMB_STR_TILE_ROWS 512
+#endif
+#ifndef DMB_STR_MIN_CTAS
+#define DMB_STR_MIN_CTAS 6
+#endif
+constexpr int kStrTileRows = DMB_STR_TILE_ROWS;
 constexpr int kStrTilesPerChunk = kVec / kStrTileRows;
 constexpr int kStrPerThread = kStrTileRows / kThreads;  // 2 consecutive rows per thread in the scan
 constexpr int kMapVecs = 2048;                          // output vectors per window (32 KiB of utf8 data)
-constexpr uint32_t kMaxRowBytes = 1u << 22;             // tile-local sums stay below 2^32 (512 rows * 4 MiB)
+constexpr uint32_t kMaxRowBytes = 1u << 21;             // tile-local sums stay below 2^32 (<= 2048 rows * 2 MiB)
 
 constexpr uint64_t kFlagAggregate = 1ull << 62;
 constexpr uint64_t kFlagPrefix = 2ull << 62;
@@ -122,7 +128,7 @@ __device__ __forceinline__ void put32(uint32_t *w, uint32_t val, int nb0, int nb
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 6)
+__global__ void __launch_bounds__(kThreads, DMB_STR_MIN_CTAS)
 string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles) {
   __shared__ StrSmem sm;
   unsigned long long *status = scratch + 2;
@@ -226,7 +232,9 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     }
   }
   uint32_t incl = tsum;
-  uint32_t rmax = start_row[0] > start_row[kStrPerThread - 1] ? start_row[0] : start_row[kStrPerThread - 1];
+  uint32_t rmax = 0;
+#pragma unroll
+  for (int k = 0; k < kStrPerThread; ++k) rmax = rmax > start_row[k] ? rmax : start_row[k];
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);

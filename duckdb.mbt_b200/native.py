@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libduckdb_mb_gpu.so")
+# DMB_LIB_PATH: development aid (kernel tuning variants built next to the default library)
+LIB_PATH = os.environ.get("DMB_LIB_PATH") or os.path.join(_HERE, "csrc", "libduckdb_mb_gpu.so")
 
 
 class VecDesc(C.Structure):
