@@ -100,6 +100,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index: int) -> None:
+    """Run this rank (and first-touch its page-locked buffers) on the CPUs next to its GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        if cpus & allowed:
+            os.sched_setaffinity(0, cpus & allowed)
+    except Exception:
+        pass
+
+
 # ----------------------------------------------------------------------------- workload
 def build_c2_device(nrows: int, seed: int, device, host_heap_alloc=None):
     """BASELINE.json configs[1] generated directly in HBM."""
@@ -262,6 +277,7 @@ def run_ours(args, rank, local_rank, world):
     from duckdb_mbt_b200 import pinned
 
     nat.lib()  # fails loudly when libduckdb_mb_gpu.so is missing: no fallback
+    bind_to_gpu_numa_node(local_rank)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
@@ -327,7 +343,6 @@ def run_ours(args, rank, local_rank, world):
     ev_b.record()
     barrier()
     dev_ms = ev_a.elapsed_time(ev_b)
-    clocks = sampler.stop() if rank == 0 else None
     step.check()
     fixed_ms = sum(sp[0].elapsed_time(sp[1]) for sp in spans) / args.steps
     string_ms = sum(sp[1].elapsed_time(sp[2]) for sp in spans) / args.steps
@@ -391,6 +406,7 @@ def run_ours(args, rank, local_rank, world):
     ctx.sync()
     e2e_s = time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop() if rank == 0 else None  # sampled from the start of the device-timed region to the end of the e2e region
     e2e_s_max = max_over_ranks(e2e_s)
     e2e_value = world * e2e_rows * args.steps / e2e_s_max
     link_gbs = (t_e2e["h2d_bytes"] + t_e2e["d2h_bytes"]) * args.steps / e2e_s / 1e9

@@ -11,6 +11,7 @@
 //
 // There is no CPU fallback: without a CUDA device every entry point fails with an error string.
 
+#include <algorithm>
 #include <chrono>
 #include <stdio.h>
 #include <stdlib.h>
@@ -546,14 +547,32 @@ int32_t materialise_arrow(Result *r) {
       }
       return rc;
     };
-    for (int j = 0; j < ncols; ++j) {
+    // Processing order: the copy-out stream trails the copy-in stream by one column, so the first
+    // column's copy-in and the last column's copy-out are the only transfers that do not overlap.
+    // Small columns go to both ends, the large ones to the middle ("pyramid").
+    std::vector<int> order((size_t)ncols), sorted((size_t)ncols);
+    {
+      std::vector<uint64_t> weight((size_t)ncols);
+      for (int j = 0; j < ncols; ++j) {
+        const Col &col = r->cols[(size_t)j];
+        weight[(size_t)j] = (uint64_t)col.width * (uint64_t)r->nrows + col.heap_len;
+        sorted[(size_t)j] = j;
+      }
+      std::stable_sort(sorted.begin(), sorted.end(), [&](int a, int b) { return weight[(size_t)a] < weight[(size_t)b]; });
+      int front = 0, back = ncols - 1;
+      for (int k = 0; k < ncols; ++k) {
+        if (k % 2 == 0) order[(size_t)front++] = sorted[(size_t)k]; else order[(size_t)back--] = sorted[(size_t)k];
+      }
+    }
+    for (int k = 0; k < ncols; ++k) {
+      const int j = order[(size_t)k];
       const Col &col = r->cols[(size_t)j];
       const bool surely_large = col.phys == DMB_PHYS_STRING && col.heap_len > 0x7fffffffull;
       if (launch_arrow_col(r, sc, j, surely_large ? DMB_STR_ARROW_LARGE : DMB_STR_ARROW_UTF8, &pend[(size_t)j])) return -1;
-      if (j > 0 && drain(j - 1)) return -1;
+      if (k > 0 && drain(order[(size_t)k - 1])) return -1;
     }
     cudaEventRecord(in1, c.s_in);
-    if (ncols > 0 && drain(ncols - 1)) return -1;
+    if (ncols > 0 && drain(order[(size_t)ncols - 1])) return -1;
     cudaEventRecord(out1, c.s_out);
     if (check_cuda(cudaStreamSynchronize(c.s_in), "sync copy-in") || check_cuda(cudaStreamSynchronize(c.s_compute), "sync compute") ||
         check_cuda(cudaStreamSynchronize(c.s_out), "sync copy-out"))

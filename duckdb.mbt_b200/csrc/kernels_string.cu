@@ -32,7 +32,7 @@ namespace dmb {
 #define DMB_STR_TILE_ROWS 512
 #endif
 #ifndef DMB_STR_MIN_CTAS
-#define DMB_STR_MIN_CTAS 6
+#define DMB_STR_MIN_CTAS 7
 #endif
 constexpr int kStrTileRows = DMB_STR_TILE_ROWS;
 constexpr int kStrTilesPerChunk = kVec / kStrTileRows;
@@ -47,9 +47,17 @@ constexpr uint64_t kValueMask = (1ull << 62) - 1ull;
 // scratch layout (uint64 words): [0] unused  [1] error flags  [2..] tile status
 enum { kErrTileTooBig = 1, kErrOffsetOverflow = 2, kErrHeapRange = 4 };
 
+#ifdef DMB_STR_TRACE
+__device__ unsigned long long g_str_trace[40000 * 8];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define DMB_TRACE(k) do { if (threadIdx.x == 0 && blockIdx.x < 40000) g_str_trace[blockIdx.x * 8 + (k)] = gtimer(); } while (0)
+#else
+#define DMB_TRACE(k) do { } while (0)
+#endif
+
 struct StrSmem {
   uint4 str[kStrTileRows];            // string_t copies
-  uint64_t src[kStrTileRows];         // device (generic) address of every row's first byte
+  uint64_t src[kStrTileRows];         // device (generic) address of every row's first byte, minus its tile-local offset
   uint32_t off[kStrTileRows + 4];     // tile-local exclusive offsets; off[kStrTileRows] = tile total
   uint16_t run[kStrTileRows];         // first row of the run a row belongs to
   union {
@@ -62,7 +70,6 @@ struct StrSmem {
   uint4 low_mask[17];                 // low_mask[d]: bytes < d of a 16-byte vector are 0xff
   uint32_t warp_sum[kThreads / 32];
   uint32_t warp_run[kThreads / 32];
-  uint32_t nslow;
   uint64_t base;
 };
 
@@ -139,6 +146,7 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   // CUB's single-pass scan makes as well).
   const int64_t tile = (int64_t)blockIdx.x;
   if (tile >= ntiles) return;
+  DMB_TRACE(0);
   if (tid < 17) {
     const uint32_t d = (uint32_t)tid;
     auto m = [&](uint32_t w) { return d >= 4u * w + 4u ? 0xffffffffu : (d <= 4u * w ? 0u : ((1u << (8u * (d - 4u * w))) - 1u)); };
@@ -158,22 +166,22 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   //    a row that contributes no bytes (NULL, empty, bad pointer) gets length 0 and is never
   //    touched again.  The shared-memory copy serves the inlined strings and the gather.
   int flags = 0;  // 1: a pointer (non-inlined) row is present  2: bad heap pointer  4: oversized row
-  uint4 ent[kStrPerThread + 1];
-  bool ok[kStrPerThread + 1];
+  uint4 ent[kStrPerThread];
+  bool ok[kStrPerThread];
 #pragma unroll
-  for (int k = 0; k <= kStrPerThread; ++k) {
-    const int i = tid * kStrPerThread + k - 1;  // k = 0: the row before this thread's rows
+  for (int k = 0; k < kStrPerThread; ++k) {
+    const int i = tid * kStrPerThread + k;
     ent[k] = make_uint4(0, 0, 0, 0);
     ok[k] = false;
-    if (i >= 0 && i < nrows_tile && (k > 0 || lane == 0)) {
+    if (i < nrows_tile) {
       ent[k] = ld_stream(in + i);
       const int row = r_begin + i;
       ok[k] = mask ? ((__ldg(mask + (row >> 6)) >> (row & 63)) & 1ull) : true;
     }
   }
 #pragma unroll
-  for (int k = 1; k <= kStrPerThread; ++k) {
-    const int i = tid * kStrPerThread + k - 1;
+  for (int k = 0; k < kStrPerThread; ++k) {
+    const int i = tid * kStrPerThread + k;
     if (i < nrows_tile) sm.str[i] = ent[k];
   }
   if (MODE == DMB_STR_REF_BLOB) __syncthreads();  // strlen below reads inlined bytes of other threads' rows
@@ -210,20 +218,17 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   uint32_t tsum = 0;
 #pragma unroll
   for (int k = 0; k < kStrPerThread; ++k) {
-    row_info(tid * kStrPerThread + k, ent[k + 1], ok[k + 1], len[k], srcp[k]);
-    sm.src[tid * kStrPerThread + k] = srcp[k];
+    row_info(tid * kStrPerThread + k, ent[k], ok[k], len[k], srcp[k]);
     tsum += len[k];
   }
   // run starts: row i starts a run unless its bytes directly follow those of row i-1
   uint32_t start_row[kStrPerThread];  // i + 1 when row i starts a run, else 0 (max-scanned below)
   {
+    // the row before this thread's rows belongs to the previous lane; the first row of a warp
+    // always starts a run (one extra boundary per 64 rows instead of a cross-warp dependency)
     uint32_t pl = __shfl_up_sync(0xffffffffu, len[kStrPerThread - 1], 1);
     uint64_t ps = __shfl_up_sync(0xffffffffu, srcp[kStrPerThread - 1], 1);
-    if (lane == 0) {  // the previous warp's last row: recompute from this lane's own copy of it
-      const int keep = flags;
-      row_info(tid * kStrPerThread - 1, ent[0], ok[0], pl, ps);
-      flags = keep;
-    }
+    if (lane == 0) pl = 0u;
 #pragma unroll
     for (int k = 0; k < kStrPerThread; ++k) {
       const bool follows = MODE != DMB_STR_REF_BLOB && pl != 0u && srcp[k] == ps + pl;
@@ -243,7 +248,9 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   }
   if (lane == 31) { sm.warp_sum[warp] = incl; sm.warp_run[warp] = rmax; }
   const uint32_t rmax_excl_lane = __shfl_up_sync(0xffffffffu, rmax, 1);
+  DMB_TRACE(1);
   const int tile_flags = __syncthreads_or(flags);
+  DMB_TRACE(2);
   uint32_t warp_excl = 0, tile_total = 0, run_excl = 0;
 #pragma unroll
   for (int w = 0; w < kThreads / 32; ++w) {
@@ -261,6 +268,7 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
 #pragma unroll
     for (int k = 0; k < kStrPerThread; ++k) {
       sm.off[tid * kStrPerThread + k] = o;
+      sm.src[tid * kStrPerThread + k] = srcp[k] - o;  // address of tile-local byte 0 if this row's stream started there
       o += len[k];
       run = run > start_row[k] ? run : start_row[k];
       sm.run[tid * kStrPerThread + k] = (uint16_t)run;  // (first row of the run) + 1; only read for non-empty rows
@@ -296,6 +304,7 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   }
   __syncthreads();
   const uint64_t base = sm.base;
+  DMB_TRACE(3);
 
   // 5. offsets
   {
@@ -360,7 +369,6 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   for (uint32_t q0 = 0; q0 < nvec; q0 += kMapVecs) {
     const uint32_t q1 = q0 + kMapVecs < nvec ? q0 + kMapVecs : nvec;
     const uint32_t qmap = q1 < nvec ? q1 + 1u : q1;  // one entry past the window: the fast-path test looks at v + 1
-    if (tid == 0) sm.nslow = 0;
     // (a) every non-empty row publishes the vectors v with L(v) inside the row
     {
       uint32_t o = my_off;
@@ -377,43 +385,45 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
       }
     }
     __syncthreads();
-    // (b) fast pass: vectors inside one run; the others are queued
-    for (uint32_t vb = q0; vb < q1; vb += kThreads) {
-      const uint32_t v = vb + tid;
+    DMB_TRACE(4);
+    // (b) fast pass: every warp owns an equal, contiguous share of the window's vectors; vectors
+    //     inside one run are finished here, the others go to the warp's own queue
+    uint16_t *my_slow = sm.slow + warp * (kMapVecs / (kThreads / 32));
+    uint32_t nslow = 0;
+    const uint32_t per_warp = ((q1 - q0 + (kThreads / 32) * 32u - 1u) / ((kThreads / 32) * 32u)) * 32u;  // <= 256, multiple of 32
+    const uint32_t wq0 = q0 + (uint32_t)warp * per_warp < q1 ? q0 + (uint32_t)warp * per_warp : q1;
+    const uint32_t wq1 = wq0 + per_warp < q1 ? wq0 + per_warp : q1;
+    for (uint32_t vb = wq0; vb < wq1; vb += 32) {
+      const uint32_t v = vb + lane;
       bool slow = false;
-      if (v < q1) {
+      if (v < wq1) {
         const uint32_t vbeg = v << 4;
         const bool whole = (v > 0 || mis == 0) && (vbeg + 16u - mis <= total) && (v + 1u < nvec);
         const int r = sm.first_row[v - q0];
         slow = !whole || sm.run[r] != sm.run[sm.first_row[v + 1u - q0]];
         if (!slow) {
           uint64_t w0, w1;
-          load16(reinterpret_cast<const uint8_t *>(sm.src[r]) + (vbeg - mis - sm.off[r]), w0, w1);
+          load16(reinterpret_cast<const uint8_t *>(sm.src[r] + (vbeg - mis)), w0, w1);
           st_stream(reinterpret_cast<uint4 *>(gbase + vbeg),
                     make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32)));
         }
       }
       const uint32_t ballot = __ballot_sync(0xffffffffu, slow);
-      if (ballot) {
-        uint32_t pos = 0;
-        if (lane == 0) pos = atomicAdd(&sm.nslow, (uint32_t)__popc(ballot));
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        if (slow) sm.slow[pos + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)(v - q0);
-      }
+      if (slow) my_slow[nslow + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)(v - q0);
+      nslow += __popc(ballot);
     }
-    __syncthreads();
-    // (c) dense pass over the queued vectors: walk the rows, merge the pieces
-    const uint32_t nslow = sm.nslow;
+    __syncwarp();
+    // (c) dense pass over the warp's queued vectors: walk the rows, merge the pieces
 #pragma unroll 1
-    for (uint32_t idx = tid; idx < nslow; idx += kThreads) {
-      const uint32_t v = q0 + sm.slow[idx];
+    for (uint32_t idx = lane; idx < nslow; idx += 32) {
+      const uint32_t v = q0 + my_slow[idx];
       const uint32_t vbeg = v << 4;                    // position + mis of the vector's first byte
       const uint32_t lo = v ? vbeg - mis : 0u;         // tile-local bytes [lo, hi) owned by this vector
       const uint32_t hi = (vbeg + 16u - mis) < total ? (vbeg + 16u - mis) : total;
       int r = sm.first_row[v - q0];
       uint64_t w0 = 0, w1 = 0;
       uint32_t seg_pos = lo;                           // current source stream covers [seg_pos, seg_end)
-      const uint8_t *sp = reinterpret_cast<const uint8_t *>(sm.src[r]) + (lo - sm.off[r]);
+      const uint8_t *sp = reinterpret_cast<const uint8_t *>(sm.src[r] + lo);
       uint32_t row_end = sm.off[r + 1];
       uint32_t seg_end = MODE == DMB_STR_REF_BLOB ? row_end - 1u : row_end;  // payload end; the terminator stays 0
 #pragma unroll 1
@@ -430,7 +440,7 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
         }
         if (seg_end > seg_pos) emit(w0, w1, sp, seg_pos + mis - vbeg, seg_end + mis - vbeg, sm.low_mask);
         seg_pos = row_end;
-        sp = reinterpret_cast<const uint8_t *>(sm.src[r2]);
+        sp = reinterpret_cast<const uint8_t *>(sm.src[r2] + row_end);
         row_end = o2;
         seg_end = MODE == DMB_STR_REF_BLOB ? o2 - 1u : o2;
       }
@@ -449,6 +459,10 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     }
     if (q1 < nvec) __syncthreads();
   }
+#ifdef DMB_STR_TRACE
+  __syncthreads();
+  DMB_TRACE(6);
+#endif
 }
 
 // bench/test helper: DuckDB-shaped string_t from lengths + heap offsets
@@ -476,6 +490,12 @@ make_string_t_kernel(const uint32_t *__restrict__ lengths, const uint64_t *__res
 }  // namespace dmb
 
 using namespace dmb;
+
+#ifdef DMB_STR_TRACE
+extern "C" int32_t dmb_dev_string_trace(unsigned long long *out, int64_t n) {
+  return (int32_t)cudaMemcpyFromSymbol(out, g_str_trace, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
 
 extern "C" size_t dmb_dev_string_scratch_bytes(int64_t nchunks) {
   return (size_t)(2 + kStrTilesPerChunk * (nchunks > 0 ? nchunks : 0)) * sizeof(unsigned long long);
