@@ -24,6 +24,8 @@
 // malloc/strlen/memcpy getters :2474-2510 and :2699-2755.  DMB_STR_REF_BLOB reproduces the
 // getter's NUL-terminated stream (strlen semantics) instead of Arrow offsets.
 
+#include <stdlib.h>
+
 #include "dmb_common.cuh"
 
 namespace dmb {
@@ -465,6 +467,171 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
 #endif
 }
 
+// ------------------------------------------------------------------ columns without a heap
+// A column whose batch registers no heap (heap_len == 0) can only hold inlined strings (<= 12
+// bytes; a pointer entry is reported as kErrHeapRange).  Rows then cost 16 bytes in and ~4 + len
+// bytes out, so the per-tile latency chain (load -> scan -> look-back) dominates: this kernel takes
+// a whole 2048-row vector per CTA, 8 rows per thread, loads them striped (lane-consecutive rows:
+// 512 contiguous bytes per request), scans the lengths with one warp scan per stripe, and builds
+// the tile's output in a zeroed shared-memory image straight from registers.
+constexpr int kInlRows = kVec;                       // rows per tile
+constexpr int kInlPerThread = kInlRows / kThreads;   // 8
+struct InlSmem {
+  alignas(16) uint8_t stage[kInlRows * 13 + 32];
+  uint32_t warp_sum[kThreads / 32];
+  uint64_t base;
+};
+
+// strlen of the <= l inline bytes (y, z, w), for the reference blob
+__device__ __forceinline__ uint32_t inline_strlen(const uint4 &e, uint32_t l) {
+  uint32_t n = 0;
+  const uint32_t w[3] = {e.y, e.z, e.w};
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    const bool z = ((w[k >> 2] >> (8 * (k & 3))) & 0xffu) == 0u;
+    if (n == (uint32_t)k && (uint32_t)k < l && !z) n = k + 1;
+  }
+  return n;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 4)
+string_inline_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles) {
+  __shared__ InlSmem sm;
+  unsigned long long *status = scratch + 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tile = (int64_t)blockIdx.x;  // = chunk index; CTAs are dispatched in blockIdx order
+  if (tile >= ntiles) return;
+  const int count = (int)__ldg(b.counts + tile);
+  const dmb_vec_desc vd = job.vecs[tile];
+  const uint4 *in = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(job.in) + vd.data_off);
+  const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
+
+  // stripe k of warp w holds rows w*256 + k*32 + lane
+  uint4 e[kInlPerThread];
+  uint32_t len[kInlPerThread];
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < kInlPerThread; ++k) {
+    const int row = warp * (32 * kInlPerThread) + k * 32 + lane;
+    e[k] = make_uint4(0, 0, 0, 0);
+    len[k] = 0;
+    if (row < count) {
+      e[k] = ld_stream(in + row);
+      const bool valid = mask ? ((__ldg(mask + (row >> 6)) >> (row & 63)) & 1ull) : true;
+      if (valid) {
+        uint32_t l = e[k].x;
+        if (l > 12u) { bad = 1; l = 0; }  // a pointer string, but the batch registered no heap
+        if (MODE == DMB_STR_REF_BLOB) l = inline_strlen(e[k], l);
+        len[k] = l;
+      }
+      if (MODE == DMB_STR_REF_BLOB) len[k] += 1;  // terminator; a NULL row is a lone '\0'
+    }
+  }
+  {  // zero the output image while the loads are in flight
+    uint4 *z = reinterpret_cast<uint4 *>(sm.stage);
+    for (int i = tid; i < (int)(sizeof(sm.stage) / 16); i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  // exclusive offsets: one warp scan per stripe, carried across the stripes of the warp
+  uint32_t off[kInlPerThread];
+  uint32_t carry = 0;
+#pragma unroll
+  for (int k = 0; k < kInlPerThread; ++k) {
+    uint32_t incl = len[k];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += n;
+    }
+    off[k] = carry + incl - len[k];
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) sm.warp_sum[warp] = carry;
+  const int any_bad = __syncthreads_or(bad);
+  uint32_t warp_excl = 0, tile_total = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const uint32_t s = sm.warp_sum[w];
+    if (w < warp) warp_excl += s;
+    tile_total += s;
+  }
+  if (tid == 0 && any_bad) atomicOr(scratch + 1, (unsigned long long)kErrHeapRange);
+
+  // decoupled look-back (warp 0)
+  if (warp == 0) {
+    const uint64_t agg = (uint64_t)tile_total;
+    if (lane == 0) atomicExch(status + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | agg);
+    uint64_t prefix = 0;
+    if (tile > 0) {
+      int64_t look = tile - 1;
+      while (true) {
+        const int64_t idx = look - lane;
+        uint64_t st = kFlagPrefix;
+        if (idx >= 0) {
+          do { st = ld_status(status + idx); } while ((st >> 62) == 0);
+        }
+        const uint32_t is_p = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+        const int first_p = is_p ? (__ffs(is_p) - 1) : 32;
+        uint64_t v = lane <= first_p ? (st & kValueMask) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        prefix += v;
+        if (is_p) break;
+        look -= 32;
+      }
+      if (lane == 0) atomicExch(status + tile, kFlagPrefix | ((prefix + agg) & kValueMask));
+    }
+    if (lane == 0) sm.base = prefix;
+  }
+  // the gather into the stage needs only (base & 15); do the part that does not need it first
+  __syncthreads();
+  const uint64_t base = sm.base;
+  const uint32_t mis = (uint32_t)(base & 15ull);
+  const int64_t out_row0 = __ldg(b.row_off + tile);
+  if (MODE != DMB_STR_ARROW_LARGE && base + tile_total > 0x7fffffffull && tid == 0)
+    atomicOr(scratch + 1, (unsigned long long)kErrOffsetOverflow);
+  uint32_t *sw = reinterpret_cast<uint32_t *>(sm.stage);
+#pragma unroll
+  for (int k = 0; k < kInlPerThread; ++k) {
+    const int row = warp * (32 * kInlPerThread) + k * 32 + lane;
+    if (row < count) {
+      const uint32_t o = warp_excl + off[k];
+      if (MODE == DMB_STR_ARROW_LARGE) __stcs(reinterpret_cast<long long *>(job.out_offsets) + out_row0 + row, (long long)(base + o));
+      else __stcs(reinterpret_cast<int32_t *>(job.out_offsets) + out_row0 + row, (int32_t)(base + o));
+      const int l = (int)len[k] - (MODE == DMB_STR_REF_BLOB ? 1 : 0);  // payload bytes; the terminator stays 0
+      if (l > 0) {
+        const uint32_t s0 = mis + o;
+        const uint32_t a = s0 & 3u, sh = 8u * a;
+        uint32_t *w = sw + (s0 >> 2);
+        put32(w, e[k].y << sh, (int)a, (int)a + l);
+        put32(w + 1, __funnelshift_l(e[k].y, e[k].z, sh), (int)a - 4, (int)a + l - 4);
+        put32(w + 2, __funnelshift_l(e[k].z, e[k].w, sh), (int)a - 8, (int)a + l - 8);
+        put32(w + 3, __funnelshift_l(e[k].w, 0u, sh), (int)a - 12, (int)a + l - 12);
+      }
+    }
+  }
+  if (tile == ntiles - 1 && tid == 0) {
+    if (MODE == DMB_STR_ARROW_LARGE) reinterpret_cast<int64_t *>(job.out_offsets)[b.nrows] = (int64_t)(base + tile_total);
+    else reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)(base + tile_total);
+    if (job.total_bytes) *job.total_bytes = base + tile_total;
+  }
+  if (tile_total == 0) return;
+  __syncthreads();
+  uint8_t *gbase = job.out_data + (base - mis);
+  const uint32_t end = mis + tile_total;
+  const uint32_t nstage = (end + 15u) >> 4;
+  const uint4 *sv = reinterpret_cast<const uint4 *>(sm.stage);
+  for (uint32_t v = tid; v < nstage; v += kThreads) {
+    const uint32_t p = 16u * v;
+    if (p >= mis && p + 16u <= end) {
+      st_stream(reinterpret_cast<uint4 *>(gbase + p), sv[v]);
+    } else {  // the neighbouring tiles own the other bytes of this vector
+      const uint32_t b0 = p > mis ? p : mis, b1 = (p + 16u) < end ? (p + 16u) : end;
+      for (uint32_t q = b0; q < b1; ++q) gbase[q] = sm.stage[q];
+    }
+  }
+}
+
 // bench/test helper: DuckDB-shaped string_t from lengths + heap offsets
 __global__ void __launch_bounds__(kThreads)
 make_string_t_kernel(const uint32_t *__restrict__ lengths, const uint64_t *__restrict__ heap_off,
@@ -514,6 +681,18 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
     kernel<<<(unsigned)ntiles, kThreads, 0, st>>>(*job, b, (unsigned long long *)scratch, ntiles);
     return check_cuda(cudaGetLastError(), "string_batch_kernel launch");
   };
+  if (job->heap_len == 0 && !getenv("DMB_STR_NO_INLINE_KERNEL")) {  // no heap: inlined strings only, whole-vector tiles
+    auto launch_inl = [&](auto kernel) -> int32_t {
+      kernel<<<(unsigned)nchunks, kThreads, 0, st>>>(*job, b, (unsigned long long *)scratch, nchunks);
+      return check_cuda(cudaGetLastError(), "string_inline_kernel launch");
+    };
+    switch (job->mode) {
+      case DMB_STR_ARROW_UTF8: return launch_inl(string_inline_kernel<DMB_STR_ARROW_UTF8>);
+      case DMB_STR_ARROW_LARGE: return launch_inl(string_inline_kernel<DMB_STR_ARROW_LARGE>);
+      case DMB_STR_REF_BLOB: return launch_inl(string_inline_kernel<DMB_STR_REF_BLOB>);
+      default: set_error("dmb_dev_string_batch: bad mode %d", job->mode); return -1;
+    }
+  }
   switch (job->mode) {
     case DMB_STR_ARROW_UTF8: return launch(string_batch_kernel<DMB_STR_ARROW_UTF8>);
     case DMB_STR_ARROW_LARGE: return launch(string_batch_kernel<DMB_STR_ARROW_LARGE>);

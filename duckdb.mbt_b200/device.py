@@ -144,9 +144,12 @@ class DeviceBatch:
         scratch = _empty(self.lib.dmb_dev_string_scratch_bytes(self.nchunks), self.device)
         v = self.validity[col_idx]
         heap = self.heap[col_idx]
+        # chunks.py pads every heap with 16 bytes: a heap of <= 16 bytes holds no string at all, and a
+        # column without a heap takes the whole-vector inline kernel
+        heap_len = 0 if (col.heap is None or col.heap.shape[0] <= 16) else col.heap.shape[0]
         job = nat.StringJob(self.data[col_idx].data_ptr(), v.data_ptr() if v is not None else None,
                             self.vecs[col_idx].data_ptr(), heap.data_ptr() if heap is not None else None,
-                            col.heap_base, 0 if col.heap is None else col.heap.shape[0],
+                            col.heap_base, heap_len,
                             offsets.data_ptr(), data.data_ptr(), None, None, None, total.data_ptr(), mode, 0)
         return StringOut(col_idx, mode, offsets, data, total, scratch, job)
 

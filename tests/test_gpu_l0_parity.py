@@ -147,3 +147,32 @@ def test_string_config_c2_columns():
     b = ch.config_c2(30_000)
     for col in range(11, 16):
         _check_string(dev, b, col=col, modes=(0,))
+
+
+@pytest.mark.parametrize("n,pattern,max_len", [(1, "full", 12), (2048, "full", 1), (2049, "full", 12), (50_000, "ragged", 12),
+                                               (70_001, "ragged", 3), (30_000, "full", 0)])
+def test_string_inline_only_columns_take_the_whole_vector_kernel(n, pattern, max_len):
+    """Columns without a heap (every string inlined): string_inline_kernel, all three modes."""
+    dev = _device_mod()
+    rng = np.random.default_rng(900 + n)
+    counts = ch.chunk_counts(n, pattern, rng)
+    lens = rng.integers(0, max_len + 1, n)
+    valid = rng.random(n) > 0.2
+    col = ch.string_column_bulk("s", lens, valid, counts, rng, utf8_fraction=0.1)
+    assert col.heap.shape[0] <= 16
+    _check_string(dev, ch.ChunkBatch(counts, [col]))
+    strings = [b"a", None, b"", b"exactly12byt", b"in\0l", b"\0", None, b"xyz"] * 300
+    counts = ch.chunk_counts(len(strings))
+    _check_string(dev, ch.ChunkBatch(counts, [ch.string_column("s", strings, counts)]))
+
+
+def test_string_pointer_row_without_a_heap_is_an_error():
+    dev = _device_mod()
+    strings = [b"short", b"this one is longer than twelve bytes", b"x"]
+    counts = ch.chunk_counts(len(strings))
+    col = ch.string_column("s", strings, counts)
+    col.heap = None  # the batch registers no heap
+    db = dev.DeviceBatch(ch.ChunkBatch(counts, [col]))
+    so = db.plan_string(0, 0, data_capacity=64)
+    db.run_string(so)
+    assert db.string_error(so) & 4  # kErrHeapRange
