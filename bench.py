@@ -115,6 +115,38 @@ def bind_to_gpu_numa_node(index: int) -> None:
         pass
 
 
+def measure_host_link(device, nbytes=1 << 30, iters=3):
+    """Pinned cudaMemcpyAsync bandwidth of this GPU's host link (GB/s): H2D alone, D2H alone, both at once.
+    The e2e leg is judged against these (BASELINE.json metric: % of host-link)."""
+    import torch
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+
+    def run(h2d, d2h):
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_a.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_b, non_blocking=True)
+        torch.cuda.synchronize(device)
+        return iters * nbytes / (time.perf_counter() - t0) / 1e9
+
+    run(True, True)
+    out = {"h2d_gbs": run(True, False), "d2h_gbs": run(False, True)}
+    both = run(True, True)
+    out["bidir_each_gbs"] = both
+    out["bidir_sum_gbs"] = 2 * both
+    del h_in, h_out, d_a, d_b
+    return out
+
+
 # ----------------------------------------------------------------------------- workload
 def build_c2_device(nrows: int, seed: int, device, host_heap_alloc=None):
     """BASELINE.json configs[1] generated directly in HBM."""
@@ -376,6 +408,7 @@ def run_ours(args, rank, local_rank, world):
         del step
     torch.cuda.empty_cache()
     setup_s = time.perf_counter() - t_setup
+    link = measure_host_link(device)
     ctx = ar.GpuContext(local_rank)
     hb = ar.HostBatch(host_batch, pinned=True)
 
@@ -457,7 +490,9 @@ def run_ours(args, rank, local_rank, world):
         "hbm_frac_whole_step": alg_bytes * args.steps / (dev_ms / 1e3) / 1e9 / peak_gbs,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(t_e2e["h2d_bytes"]),
                 "d2h_bytes_per_step": int(t_e2e["d2h_bytes"]), "ms_per_step": 1e3 * e2e_s_max / args.steps,
-                "link_gb_per_s_per_gpu": link_gbs, "kernels_ms_per_step": kernels_ms / args.steps,
+                "link_gb_per_s_per_gpu": link_gbs, "host_link_measured": link,
+                "link_frac": link_gbs / link["bidir_sum_gbs"] if link.get("bidir_sum_gbs") else None,
+                "kernels_ms_per_step": kernels_ms / args.steps,
                 "host_buffers": "page-locked (DMB_BATCH_PINNED), contiguous chunk slabs"},
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,

@@ -163,6 +163,66 @@ __device__ __forceinline__ void convert_chunk(const S *__restrict__ in, const ui
   }
 }
 
+// Narrow types (R >= 4 rows per 16-byte vector): one chunk is only 2048 / R vectors, fewer than the
+// 256 * 4 the CTA keeps in flight, so G = 1024 / (2048 / R) consecutive chunks are converted as one
+// index space: every thread still has four independent 16-byte loads outstanding.
+template <typename S, typename D, typename F>
+__device__ __forceinline__ void convert_group(const dmb_fixed_job &job, const BatchView &b, int64_t c0, int G, F f) {
+  constexpr int W = sizeof(S) > sizeof(D) ? sizeof(S) : sizeof(D);
+  constexpr int R = 16 / W;
+  constexpr int U = 4;
+  constexpr int VPC = kVec / R;  // vectors per full chunk
+  using PS = Pack<S, R>;
+  using PD = Pack<D, R>;
+  PS x[U];
+  int64_t cc[U];
+  int lv[U];
+  bool act[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int v = threadIdx.x + u * kThreads;
+    const int g = v / VPC;
+    lv[u] = v - g * VPC;
+    cc[u] = c0 + g;
+    act[u] = g < G && cc[u] < b.nchunks && (lv[u] + 1) * R <= (int)__ldg(b.counts + cc[u]);
+    if (act[u]) {
+      const S *in = reinterpret_cast<const S *>(reinterpret_cast<const uint8_t *>(job.in_data) + job.vecs[cc[u]].data_off);
+      x[u] = ld_stream(reinterpret_cast<const PS *>(in) + lv[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!act[u]) continue;
+    const int64_t vo = job.vecs[cc[u]].val_off;
+    const int row = lv[u] * R;
+    const uint32_t bits = vo >= 0 ? (uint32_t)(__ldg(job.in_validity + vo + (row >> 6)) >> (row & 63)) : 0xffffffffu;
+    D *out = reinterpret_cast<D *>(job.out_values) + __ldg(b.row_off + cc[u]);
+    PD y;
+#pragma unroll
+    for (int r = 0; r < R; ++r) y.v[r] = ((bits >> r) & 1u) ? (D)f(x[u].v[r]) : zero_of<D>();
+    if ((reinterpret_cast<uintptr_t>(out) % sizeof(PD)) == 0) {
+      st_stream(reinterpret_cast<PD *>(out) + lv[u], y);
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[row + r] = y.v[r];
+    }
+  }
+  // ragged ends: the < R rows after the last whole vector of each chunk
+  for (int t = threadIdx.x; t < G * R; t += kThreads) {
+    const int g = t / R;
+    const int64_t c = c0 + g;
+    if (c >= b.nchunks) break;
+    const int count = (int)__ldg(b.counts + c);
+    const int row = (count / R) * R + (t - g * R);
+    if (row >= count) continue;
+    const dmb_vec_desc vd = job.vecs[c];
+    const S *in = reinterpret_cast<const S *>(reinterpret_cast<const uint8_t *>(job.in_data) + vd.data_off);
+    const bool valid = vd.val_off >= 0 ? ((__ldg(job.in_validity + vd.val_off + (row >> 6)) >> (row & 63)) & 1ull) : true;
+    D *out = reinterpret_cast<D *>(job.out_values) + __ldg(b.row_off + c);
+    out[row] = valid ? (D)f(in[row]) : zero_of<D>();
+  }
+}
+
 // BOOLEAN bytes -> Arrow bit-packed values for output tile t (tile-centric: bit offsets of short
 // chunks are arbitrary).  Thread i owns output byte i of the tile = rows 8i..8i+7.
 __device__ __forceinline__ void bool_bits_tile(const BatchView &b, const dmb_fixed_job &job, int64_t t) {
@@ -246,17 +306,27 @@ __device__ __forceinline__ void validity_tile(const BatchView &b, const dmb_fixe
 // every job of a run of equal ops, so a batch costs one launch per DISTINCT conversion.
 enum { kKindConvert = 0, kKindBoolBits = 1, kKindValidityOnly = 2 };
 
+// chunks per work item: enough 16-byte vectors for the 256 x 4 loads a CTA keeps in flight
+template <typename S, typename D, int KIND>
+struct GroupOf {
+  static constexpr int W = sizeof(S) > sizeof(D) ? sizeof(S) : sizeof(D);
+  static constexpr int R = 16 / W;
+  static constexpr int value = (KIND == kKindConvert && R >= 4) ? (kThreads * 4) / (kVec / R) : 1;
+};
+
 template <typename S, typename D, typename F, int KIND>
 __global__ void __launch_bounds__(kThreads)
 fixed_batch_kernel(const dmb_fixed_job *__restrict__ jobs, int njobs, BatchView b) {
   __shared__ uint64_t s_words[DMB_VALIDITY_WORDS];
   __shared__ dmb_fixed_job s_job;
+  constexpr int G = GroupOf<S, D, KIND>::value;
   const int64_t ntiles = (b.nrows + kVec - 1) / kVec;
-  const int64_t items = (int64_t)njobs * b.nchunks;
+  const int64_t groups = (b.nchunks + G - 1) / G;
+  const int64_t items = (int64_t)njobs * groups;
   int cur_job = -1;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-    const int j = (int)(item / b.nchunks);
-    const int64_t i = item - (int64_t)j * b.nchunks;
+    const int j = (int)(item / groups);
+    const int64_t i0 = (item - (int64_t)j * groups) * G;
     if (j != cur_job) {  // CTA-uniform
       __syncthreads();
       if (threadIdx.x < sizeof(dmb_fixed_job) / 8)
@@ -265,20 +335,27 @@ fixed_batch_kernel(const dmb_fixed_job *__restrict__ jobs, int njobs, BatchView 
       cur_job = j;
     }
     const dmb_fixed_job &job = s_job;
-    if (KIND == kKindConvert) {
-      const int count = (int)__ldg(b.counts + i);
-      if (count > 0 && job.out_values) {
-        const dmb_vec_desc vd = job.vecs[i];
-        const S *in = reinterpret_cast<const S *>(reinterpret_cast<const uint8_t *>(job.in_data) + vd.data_off);
-        const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
-        D *out = reinterpret_cast<D *>(job.out_values) + __ldg(b.row_off + i);
-        convert_chunk<S, D, F>(in, mask, out, count, F());
+    if (KIND == kKindConvert && job.out_values) {
+      if (G > 1) {
+        convert_group<S, D, F>(job, b, i0, G, F());
+      } else {
+        const int count = (int)__ldg(b.counts + i0);
+        if (count > 0) {
+          const dmb_vec_desc vd = job.vecs[i0];
+          const S *in = reinterpret_cast<const S *>(reinterpret_cast<const uint8_t *>(job.in_data) + vd.data_off);
+          const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
+          D *out = reinterpret_cast<D *>(job.out_values) + __ldg(b.row_off + i0);
+          convert_chunk<S, D, F>(in, mask, out, count, F());
+        }
       }
-    } else if (KIND == kKindBoolBits) {
-      if (i < ntiles && job.out_values) bool_bits_tile(b, job, i);
     }
-    if (i < ntiles && (job.out_validity || job.out_valid_bytes || job.null_count))
-      validity_tile(b, job, i, s_words);
+    for (int64_t i = i0; i < i0 + G && i < b.nchunks; ++i) {
+      if (KIND == kKindBoolBits) {
+        if (i < ntiles && job.out_values) bool_bits_tile(b, job, i);
+      }
+      if (i < ntiles && (job.out_validity || job.out_valid_bytes || job.null_count))
+        validity_tile(b, job, i, s_words);
+    }
   }
 }
 
@@ -389,7 +466,13 @@ extern "C" int32_t dmb_dev_fixed_batch(const dmb_fixed_job *jobs_dev, const dmb_
     while (j1 < njobs && jobs_host[j1].op == jobs_host[j0].op) ++j1;
     fixed_kernel_fn fn = select_kernel(jobs_host[j0].op);
     if (!fn) { set_error("dmb_dev_fixed_batch: unsupported conversion op 0x%x (job %d)", jobs_host[j0].op, j0); return -1; }
-    const int64_t items = (int64_t)(j1 - j0) * nchunks;
+    int group = 1;  // must match GroupOf<>: narrow conversions take several chunks per item
+    if (jobs_host[j0].op != DMB_OP_VALIDITY_ONLY && (jobs_host[j0].op & 0xff) != DMB_DST_BOOL_BITS) {
+      const int wi = dmb_phys_width(jobs_host[j0].op >> 8), wo = dmb_op_out_width(jobs_host[j0].op);
+      const int w = wi > wo ? wi : wo;
+      if (w > 0 && w <= 4) group = (kThreads * 4) / (kVec / (16 / w));
+    }
+    const int64_t items = (int64_t)(j1 - j0) * ((nchunks + group - 1) / group);
     const int grid = (int)(items < max_grid ? items : max_grid);
     fn<<<grid, kThreads, 0, (cudaStream_t)stream>>>(jobs_dev + j0, j1 - j0, b);
     if (check_cuda(cudaGetLastError(), "fixed_batch_kernel launch")) return -1;

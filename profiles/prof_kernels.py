@@ -31,6 +31,11 @@ def main():
         db.add_string(gen, 0.1, 0, 64)
         so = db.plan_string(0, 0, data_capacity=db.total_len)
         fn = lambda: db.run_string(so)  # noqa: E731
+    elif args.which == "string_mixed":  # l_shipinstruct shape: lens {17,11,4,16}: half inline, half pointer
+        db = devgen.GeneratedBatch(n)
+        db.add_string(gen, 0.0, 0, 0, len_choices=[17, 11, 4, 16])
+        so = db.plan_string(0, 0, data_capacity=db.total_len)
+        fn = lambda: db.run_string(so)  # noqa: E731
     elif args.which == "string_short":  # l_returnflag shape: 1 byte inline
         db = devgen.GeneratedBatch(n)
         db.add_string(gen, 0.0, 1, 1)
