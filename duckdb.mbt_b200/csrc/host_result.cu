@@ -68,6 +68,7 @@ struct Col {
   cudaEvent_t ev_staged = nullptr;
   std::shared_ptr<ArrowColOut> arrow;
   TypedOut typed;
+  TypedOut text;  // VARCHAR rendering of the column (QueryResult's string form)
 };
 
 }  // namespace
@@ -346,15 +347,75 @@ struct StringRun {
   cudaEvent_t done = nullptr;  // kernel + the small counter copies
 };
 
-int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool want_valid_bytes, StringRun *out) {
+// where the string kernel reads a column from: the staged VARCHAR / BLOB column itself, or the text
+// rendering of a fixed-width column (kernels_render.cu) produced on the compute stream
+struct StringSource {
+  const dmb_string_t *in = nullptr;
+  const dmb_vec_desc *vecs = nullptr;
+  const uint8_t *heap = nullptr;
+  uint64_t heap_host_base = 0, heap_len = 0;
+};
+
+int32_t string_source(Result *r, Scope &sc, int j, StringSource *src) {
   if (stage_column(r, j)) return -1;
+  CtxCore &c = *r->core;
+  Col &col = r->cols[(size_t)j];
+  if (col.phys == DMB_PHYS_STRING) {
+    src->in = (const dmb_string_t *)col.d_data;
+    src->vecs = col.d_vecs;
+    src->heap = col.d_heap;
+    src->heap_host_base = col.heap_host_base;
+    src->heap_len = col.d_heap_len;
+    return 0;
+  }
+  if (!dmb_render_supported(col.type_id, col.phys)) {
+    set_error("column %d (type %d): libduckdb's text rendering of this type is not reproduced on the device", j, col.type_id);
+    return -1;
+  }
+  const int64_t nch = r->nchunks;
+  const size_t nslots = (size_t)(nch > 0 ? nch : 1) * DMB_VECTOR_SIZE;
+  dmb_string_t *d_str = (dmb_string_t *)sc.dalloc(nslots * sizeof(dmb_string_t));
+  uint8_t *d_heap = (uint8_t *)sc.dalloc(nslots * DMB_RENDER_SLOT_BYTES + 64);
+  std::vector<dmb_vec_desc> vecs((size_t)(nch > 0 ? nch : 1));
+  for (int64_t k = 0; k < nch; ++k) {
+    vecs[(size_t)k].data_off = (uint64_t)k * DMB_VECTOR_SIZE * sizeof(dmb_string_t);
+    vecs[(size_t)k].val_off = (col.any_validity && col.validity[(size_t)k]) ? k * DMB_VALIDITY_WORDS : -1;
+  }
+  if (!d_str || !d_heap) return -1;
+  if (check_cuda(cudaStreamWaitEvent(c.s_compute, col.ev_staged, 0), "wait staged")) return -1;
+  dmb_vec_desc *d_vecs2 = (dmb_vec_desc *)upload_job(sc, vecs.data(), sizeof(dmb_vec_desc) * vecs.size());
+  if (!d_vecs2) return -1;
+  dmb_render_job job;
+  memset(&job, 0, sizeof(job));
+  job.in_data = col.d_data;
+  job.in_validity = col.d_validity;
+  job.vecs = col.d_vecs;
+  job.out = d_str;
+  job.out_heap = d_heap;
+  job.heap_host_base = 1ull << 40;
+  job.type_id = col.type_id;
+  job.phys = col.phys;
+  job.dec_scale = col.dec_scale;
+  if (dmb_dev_render_text(&job, r->d_counts, nch, c.s_compute)) return -1;
+  src->in = d_str;
+  src->vecs = d_vecs2;
+  src->heap = d_heap;
+  src->heap_host_base = job.heap_host_base;
+  src->heap_len = (uint64_t)nslots * DMB_RENDER_SLOT_BYTES;
+  return 0;
+}
+
+int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool want_valid_bytes, StringRun *out) {
+  StringSource src;
+  if (string_source(r, sc, j, &src)) return -1;
   CtxCore &c = *r->core;
   Col &col = r->cols[(size_t)j];
   const int64_t n = r->nrows;
   out->mode = mode;
   out->offsets_bytes = (size_t)(n + 1) * (mode == DMB_STR_ARROW_LARGE ? 8 : 4);
   out->d_offsets = sc.dalloc(out->offsets_bytes + 64);
-  out->data_cap = (size_t)12 * (size_t)n + (size_t)col.d_heap_len + (mode == DMB_STR_REF_BLOB ? (size_t)n : 0);
+  const size_t per_row = col.phys == DMB_PHYS_STRING ? 12 : DMB_RENDER_SLOT_BYTES;  // rendered text: at most one slot per row
+  out->data_cap = per_row * (size_t)n + (col.phys == DMB_PHYS_STRING ? (size_t)col.d_heap_len : 0) + (mode == DMB_STR_REF_BLOB ? (size_t)n : 0);
   out->d_data = (uint8_t *)sc.dalloc(out->data_cap + 64);
   out->d_scratch = sc.dalloc(dmb_dev_string_scratch_bytes(r->nchunks));
   out->d_total = (unsigned long long *)sc.dalloc(8);
@@ -366,12 +427,12 @@ int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool
   if (check_cuda(cudaMemsetAsync(out->d_total, 0, 8, c.s_compute), "total memset")) return -1;
   dmb_string_job job;
   memset(&job, 0, sizeof(job));
-  job.in = (const dmb_string_t *)col.d_data;
+  job.in = src.in;
   job.in_validity = col.d_validity;
-  job.vecs = col.d_vecs;
-  job.heap_dev = col.d_heap;
-  job.heap_host_base = col.heap_host_base;
-  job.heap_len = col.d_heap_len;
+  job.vecs = src.vecs;
+  job.heap_dev = src.heap;
+  job.heap_host_base = src.heap_host_base;
+  job.heap_len = src.heap_len;
   job.out_offsets = out->d_offsets;
   job.out_data = out->d_data;
   job.total_bytes = out->d_total;
@@ -675,9 +736,32 @@ bool typed_map(const Col &col, TypedMap *m) {
     default:
       // DECIMAL, HUGEINT, UHUGEINT, INTERVAL, TIME*, BLOB, UUID stay Value::String (libduckdb's
       // text rendering) in the reference, src/duckdb_parsing.mbt:120-141
-      set_error("column type %d is a text-rendered Value::String in the reference; no typed column form", col.type_id);
+      if (dmb_render_supported(col.type_id, col.phys)) { m->tag = DMB_VALUE_STRING; m->op = -1; m->width = 0; return true; }
+      set_error("column type %d is a text-rendered Value::String in the reference; its rendering is not reproduced on the device", col.type_id);
       return false;
   }
+}
+
+// utf8 offsets + data + byte validity of column j's text form (the VARCHAR column itself, or the
+// device rendering of a fixed-width column), copied into pinned buffers owned by the result
+int32_t text_column_out(Result *r, Scope &sc, int j, TypedOut &t) {
+  CtxCore &c = *r->core;
+  const int64_t n = r->nrows;
+  StringRun s;
+  if (run_string(r, sc, j, DMB_STR_ARROW_UTF8, false, true, &s)) return -1;
+  if (check_cuda(cudaEventSynchronize(s.done), "string kernel wait")) return -1;
+  if (string_flags_error(s.h_ctr[1])) return -1;
+  const size_t total = (size_t)s.h_ctr[0];
+  t.offsets = keep_pin(r, s.offsets_bytes);
+  t.data = keep_pin(r, total);
+  if (!t.offsets || !t.data) return -1;
+  if (n == 0) memset(t.offsets, 0, s.offsets_bytes);
+  if (n && check_cuda(cudaMemcpyAsync(t.offsets, s.d_offsets, s.offsets_bytes, cudaMemcpyDeviceToHost, c.s_compute), "offsets D2H")) return -1;
+  if (total && check_cuda(cudaMemcpyAsync(t.data, s.d_data, total, cudaMemcpyDeviceToHost, c.s_compute), "data D2H")) return -1;
+  if (n && check_cuda(cudaMemcpyAsync(t.valid, s.validity.d_valid_bytes, (size_t)n, cudaMemcpyDeviceToHost, c.s_compute), "valid D2H")) return -1;
+  if (check_cuda(cudaStreamSynchronize(c.s_compute), "typed sync")) return -1;
+  t.null_count = (int64_t)s.h_ctr[2];
+  return 0;
 }
 
 int32_t typed_column(Result *r, int j, dmb_typed_column *out) {
@@ -695,20 +779,7 @@ int32_t typed_column(Result *r, int j, dmb_typed_column *out) {
     t.valid = keep_pin(r, (size_t)n);
     if (!t.valid) return -1;
     if (m.op < 0) {
-      StringRun s;
-      if (run_string(r, sc, j, DMB_STR_ARROW_UTF8, false, true, &s)) return -1;
-      if (check_cuda(cudaEventSynchronize(s.done), "string kernel wait")) return -1;
-      if (string_flags_error(s.h_ctr[1])) return -1;
-      const size_t total = (size_t)s.h_ctr[0];
-      t.offsets = keep_pin(r, s.offsets_bytes);
-      t.data = keep_pin(r, total);
-      if (!t.offsets || !t.data) return -1;
-      if (n == 0) memset(t.offsets, 0, s.offsets_bytes);
-      if (n && check_cuda(cudaMemcpyAsync(t.offsets, s.d_offsets, s.offsets_bytes, cudaMemcpyDeviceToHost, c.s_compute), "offsets D2H")) return -1;
-      if (total && check_cuda(cudaMemcpyAsync(t.data, s.d_data, total, cudaMemcpyDeviceToHost, c.s_compute), "data D2H")) return -1;
-      if (n && check_cuda(cudaMemcpyAsync(t.valid, s.validity.d_valid_bytes, (size_t)n, cudaMemcpyDeviceToHost, c.s_compute), "valid D2H")) return -1;
-      if (check_cuda(cudaStreamSynchronize(c.s_compute), "typed sync")) return -1;
-      t.null_count = (int64_t)s.h_ctr[2];
+      if (text_column_out(r, sc, j, t)) return -1;
     } else {
       FixedRun f;
       if (run_fixed(r, sc, j, m.op, 0, false, true, &f)) return -1;
@@ -730,6 +801,40 @@ int32_t typed_column(Result *r, int j, dmb_typed_column *out) {
   out->length = n;
   out->null_count = t.null_count;
   out->values = t.values;
+  out->valid = (const uint8_t *)t.valid;
+  out->offsets = (const int32_t *)t.offsets;
+  out->data = (const uint8_t *)t.data;
+  return 0;
+}
+
+// the string form of any column: what Connection::query collects cell by cell through
+// duckdb_mb_result_is_null / duckdb_mb_result_value (src/duckdb_native.c:215-238)
+int32_t text_column(Result *r, int j, dmb_typed_column *out) {
+  Col &col = r->cols[(size_t)j];
+  CtxCore &c = *r->core;
+  if (!c.bind()) return -1;
+  const int64_t n = r->nrows;
+  if (col.phys != DMB_PHYS_STRING && !dmb_render_supported(col.type_id, col.phys)) {
+    set_error("column %d (type %d): libduckdb's text rendering of this type is not reproduced on the device", j, col.type_id);
+    return -1;
+  }
+  if (col.typed.ready && col.typed.tag == DMB_VALUE_STRING && !col.text.ready) col.text = col.typed;
+  if (!col.text.ready) {
+    Scope sc(c);
+    TypedOut &t = col.text;
+    t.tag = DMB_VALUE_STRING;
+    t.width = 0;
+    t.valid = keep_pin(r, (size_t)n);
+    if (!t.valid) return -1;
+    if (text_column_out(r, sc, j, t)) return -1;
+    t.ready = true;
+  }
+  const TypedOut &t = col.text;
+  out->tag = t.tag;
+  out->width = 0;
+  out->length = n;
+  out->null_count = t.null_count;
+  out->values = nullptr;
   out->valid = (const uint8_t *)t.valid;
   out->offsets = (const int32_t *)t.offsets;
   out->data = (const uint8_t *)t.data;
@@ -788,8 +893,9 @@ moonbit_bytes_t getter_string(Result *r, int32_t col_idx, bool nullable) {
   std::lock_guard<std::mutex> g(c.mu);
   if (!c.bind()) return empty_bytes();
   const Col &col = r->cols[(size_t)col_idx];
-  if (col.phys != DMB_PHYS_STRING) {
-    set_error("get_column_string on a non-VARCHAR column needs libduckdb's text rendering (duckdb_value_varchar); not on the GPU path");
+  if (col.phys != DMB_PHYS_STRING && !dmb_render_supported(col.type_id, col.phys)) {
+    // duckdb_value_varchar of FLOAT/DOUBLE (shortest round-trip digits), HUGEINT, INTERVAL, TIME*, UUID, BLOB
+    set_error("get_column_string: libduckdb's text rendering of column type %d is not reproduced on the device", col.type_id);
     return empty_bytes();
   }
   Scope sc(c);
@@ -927,6 +1033,13 @@ extern "C" int32_t duckdb_mb_gpu_result_typed_column(duckdb_mb_arrow_result *r, 
   if (col < 0 || col >= r->column_count) { set_error("column %d out of range", col); return 0; }
   std::lock_guard<std::mutex> g(r->core->mu);
   return typed_column(r, col, out) == 0 ? 1 : 0;
+}
+
+extern "C" int32_t duckdb_mb_gpu_result_text_column(duckdb_mb_arrow_result *r, int32_t col, dmb_typed_column *out) {
+  if (!r || !out) { set_error("null argument"); return 0; }
+  if (col < 0 || col >= r->column_count) { set_error("column %d out of range", col); return 0; }
+  std::lock_guard<std::mutex> g(r->core->mu);
+  return text_column(r, col, out) == 0 ? 1 : 0;
 }
 
 extern "C" int32_t duckdb_mb_gpu_result_timings(duckdb_mb_arrow_result *r, double *out4) {

@@ -1,0 +1,190 @@
+// K7 render_text: fixed-width DuckDB cells -> their VARCHAR rendering, as duckdb_string_t.
+//
+// The reference hands every non-VARCHAR cell to libduckdb for text rendering:
+// duckdb_value_varchar in the result path (src/duckdb_native.c:224-238, and :2478 / :2715 for the
+// "string" getters that its schema JSON prescribes for DATE / DECIMAL / TIMESTAMP / ... columns,
+// :2314-2339) and duckdb_value_to_string in the chunk path (:305-318, :611-661).  Here one thread
+// renders one cell into a 48-byte slot and emits a 16-byte string_t (<= 12 bytes inlined, else
+// prefix + pointer to the slot), so the rendered column then flows through the same
+// string_batch_kernel (utf8 offsets + data, or the reference's NUL-terminated blob) as a VARCHAR
+// column.  Formats follow DuckDB 1.4's renderings pinned by src/duckdb_fixture_cases.mbt
+// (ints :27-32,83-102, DATE :41-46, TIMESTAMP :55-67, DECIMAL :69-81).
+
+#include "dmb_common.cuh"
+
+namespace dmb {
+
+constexpr int kRenderSlot = DMB_RENDER_SLOT_BYTES;
+
+struct TextBuf {
+  char s[kRenderSlot];
+  int n;
+  __device__ __forceinline__ void push(char c) { if (n < kRenderSlot) s[n++] = c; }
+  __device__ __forceinline__ void push_str(const char *p) { while (*p) push(*p++); }
+  // unsigned decimal, at least `min_digits` digits (zero padded)
+  __device__ __forceinline__ void push_u64(uint64_t v, int min_digits) {
+    char tmp[20];
+    int k = 0;
+    do { tmp[k++] = (char)('0' + (int)(v % 10ull)); v /= 10ull; } while (v != 0ull);
+    for (int i = k; i < min_digits; ++i) push('0');
+    while (k > 0) push(tmp[--k]);
+  }
+};
+
+__device__ __forceinline__ int64_t floor_div64(int64_t a, int64_t b) {
+  int64_t q = a / b;
+  return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+__device__ __forceinline__ void render_i64(TextBuf &t, int64_t v) {
+  if (v < 0) { t.push('-'); t.push_u64((uint64_t)0 - (uint64_t)v, 1); } else t.push_u64((uint64_t)v, 1);
+}
+
+// DECIMAL(w, scale) stored as an integer: sign, integer part, '.', exactly `scale` fraction digits
+__device__ __forceinline__ void render_decimal(TextBuf &t, int64_t v, int scale) {
+  const bool neg = v < 0;
+  uint64_t a = neg ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+  if (neg) t.push('-');
+  if (scale <= 0) { t.push_u64(a, 1); return; }
+  uint64_t p = 1;
+  for (int i = 0; i < scale; ++i) p *= 10ull;
+  t.push_u64(a / p, 1);
+  t.push('.');
+  t.push_u64(a % p, scale);
+}
+
+// proleptic Gregorian date: YYYY-MM-DD, more digits past year 9999, "(BC)" suffix before year 1
+__device__ __forceinline__ void render_date(TextBuf &t, int64_t days) {
+  int64_t z = days + 719468;
+  const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+  const int64_t doe = z - era * 146097;
+  const int64_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  const int64_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  const int64_t mp = (5 * doy + 2) / 153;
+  const int d = (int)(doy - (153 * mp + 2) / 5 + 1);
+  const int m = (int)(mp < 10 ? mp + 3 : mp - 9);
+  const int64_t y = yoe + era * 400 + (m <= 2 ? 1 : 0);
+  const bool bc = y < 1;
+  t.push_u64((uint64_t)(bc ? 1 - y : y), 4);
+  t.push('-');
+  t.push_u64((uint64_t)m, 2);
+  t.push('-');
+  t.push_u64((uint64_t)d, 2);
+  if (bc) t.push_str(" (BC)");
+}
+
+// v in units of 1/unit_per_sec seconds since the epoch; fraction digits trimmed of trailing zeros
+__device__ __forceinline__ void render_timestamp(TextBuf &t, int64_t v, int64_t unit_per_sec, bool tz) {
+  const int64_t secs = floor_div64(v, unit_per_sec);
+  const int64_t frac = v - secs * unit_per_sec;
+  const int64_t days = floor_div64(secs, 86400);
+  const int64_t sod = secs - days * 86400;
+  render_date(t, (int64_t)(int32_t)days);  // the oracle narrows the day number to int32 like DuckDB's date_t
+  t.push(' ');
+  t.push_u64((uint64_t)(sod / 3600), 2);
+  t.push(':');
+  t.push_u64((uint64_t)(sod / 60 % 60), 2);
+  t.push(':');
+  t.push_u64((uint64_t)(sod % 60), 2);
+  if (frac != 0) {
+    int digits = unit_per_sec == 1000 ? 3 : (unit_per_sec == 1000000 ? 6 : 9);
+    uint64_t f = (uint64_t)frac;
+    while (digits > 0 && f % 10ull == 0ull) { f /= 10ull; --digits; }
+    t.push('.');
+    t.push_u64(f, digits);
+  }
+  if (tz) t.push_str("+00");
+}
+
+__global__ void __launch_bounds__(kThreads)
+render_text_kernel(dmb_render_job job, const uint32_t *__restrict__ counts, int64_t nchunks) {
+  for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int count = (int)__ldg(counts + c);
+    const dmb_vec_desc vd = job.vecs[c];
+    const uint8_t *in = reinterpret_cast<const uint8_t *>(job.in_data) + vd.data_off;
+    const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
+    for (int i = threadIdx.x; i < count; i += kThreads) {
+      const int64_t slot = c * (int64_t)kVec + i;
+      uint4 e = make_uint4(0, 0, 0, 0);
+      const bool valid = mask ? ((__ldg(mask + (i >> 6)) >> (i & 63)) & 1ull) : true;
+      if (valid) {
+        TextBuf t;
+        t.n = 0;
+        int64_t v = 0;
+        uint64_t u = 0;
+        switch (job.phys) {
+          case DMB_PHYS_BOOL: case DMB_PHYS_U8: u = in[i]; v = (int64_t)u; break;
+          case DMB_PHYS_I8: v = reinterpret_cast<const int8_t *>(in)[i]; break;
+          case DMB_PHYS_I16: v = reinterpret_cast<const int16_t *>(in)[i]; break;
+          case DMB_PHYS_U16: u = reinterpret_cast<const uint16_t *>(in)[i]; v = (int64_t)u; break;
+          case DMB_PHYS_I32: v = reinterpret_cast<const int32_t *>(in)[i]; break;
+          case DMB_PHYS_U32: u = reinterpret_cast<const uint32_t *>(in)[i]; v = (int64_t)u; break;
+          case DMB_PHYS_I64: v = reinterpret_cast<const int64_t *>(in)[i]; break;
+          case DMB_PHYS_U64: u = reinterpret_cast<const uint64_t *>(in)[i]; v = (int64_t)u; break;
+          default: break;
+        }
+        switch (job.type_id) {
+          case DMB_TYPE_BOOLEAN: t.push_str(u ? "true" : "false"); break;
+          case DMB_TYPE_UBIGINT: t.push_u64(u, 1); break;
+          case DMB_TYPE_DATE: render_date(t, v); break;
+          case DMB_TYPE_TIMESTAMP: render_timestamp(t, v, 1000000, false); break;
+          case DMB_TYPE_TIMESTAMP_TZ: render_timestamp(t, v, 1000000, true); break;
+          case DMB_TYPE_TIMESTAMP_S: render_timestamp(t, v, 1, false); break;
+          case DMB_TYPE_TIMESTAMP_MS: render_timestamp(t, v, 1000, false); break;
+          case DMB_TYPE_TIMESTAMP_NS: render_timestamp(t, v, 1000000000, false); break;
+          case DMB_TYPE_DECIMAL: render_decimal(t, v, job.dec_scale); break;
+          default: render_i64(t, v); break;  // TINYINT .. BIGINT, UTINYINT .. UINTEGER
+        }
+        // string_t: length, then 12 inlined bytes or 4-byte prefix + pointer to the slot
+        uint32_t w[kRenderSlot / 4];
+#pragma unroll
+        for (int k = 0; k < kRenderSlot / 4; ++k) {
+          uint32_t x = 0;
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) x |= (4 * k + bb < t.n ? (uint32_t)(uint8_t)t.s[4 * k + bb] : 0u) << (8 * bb);
+          w[k] = x;
+        }
+        e.x = (uint32_t)t.n;
+        e.y = w[0];
+        if (t.n <= 12) {
+          e.z = w[1];
+          e.w = w[2];
+        } else {
+          const uint64_t p = job.heap_host_base + (uint64_t)slot * kRenderSlot;
+          e.z = (uint32_t)p;
+          e.w = (uint32_t)(p >> 32);
+          uint4 *dst = reinterpret_cast<uint4 *>(job.out_heap + (uint64_t)slot * kRenderSlot);
+#pragma unroll
+          for (int k = 0; k < kRenderSlot / 16; ++k) dst[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+        }
+      }
+      reinterpret_cast<uint4 *>(job.out)[slot] = e;
+    }
+  }
+}
+
+}  // namespace dmb
+
+using namespace dmb;
+
+extern "C" int32_t dmb_render_supported(int32_t type_id, int32_t phys) {
+  switch (type_id) {
+    case DMB_TYPE_BOOLEAN: case DMB_TYPE_TINYINT: case DMB_TYPE_SMALLINT: case DMB_TYPE_INTEGER: case DMB_TYPE_BIGINT:
+    case DMB_TYPE_UTINYINT: case DMB_TYPE_USMALLINT: case DMB_TYPE_UINTEGER: case DMB_TYPE_UBIGINT: case DMB_TYPE_DATE:
+    case DMB_TYPE_TIMESTAMP: case DMB_TYPE_TIMESTAMP_TZ: case DMB_TYPE_TIMESTAMP_S: case DMB_TYPE_TIMESTAMP_MS:
+    case DMB_TYPE_TIMESTAMP_NS:
+      return 1;
+    case DMB_TYPE_DECIMAL: return phys == DMB_PHYS_I16 || phys == DMB_PHYS_I32 || phys == DMB_PHYS_I64;
+    default: return 0;  // FLOAT/DOUBLE (shortest round-trip), HUGEINT, INTERVAL, TIME*, UUID, BLOB: not rendered on the device
+  }
+}
+
+extern "C" int32_t dmb_dev_render_text(const dmb_render_job *job, const uint32_t *counts, int64_t nchunks, void *stream) {
+  if (!job) { set_error("dmb_dev_render_text: job is null"); return -1; }
+  if (!dmb_render_supported(job->type_id, job->phys)) { set_error("dmb_dev_render_text: no device renderer for type %d", job->type_id); return -1; }
+  if (nchunks <= 0) return 0;
+  const int64_t max_grid = (int64_t)kNumSMs * 8;
+  const int grid = (int)(nchunks < max_grid ? nchunks : max_grid);
+  render_text_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(*job, counts, nchunks);
+  return check_cuda(cudaGetLastError(), "render_text_kernel launch");
+}

@@ -32,6 +32,12 @@ class StringJob(C.Structure):
                 ("mode", C.c_int32), ("reserved", C.c_int32)]
 
 
+class RenderJob(C.Structure):
+    _fields_ = [("in_data", C.c_void_p), ("in_validity", C.c_void_p), ("vecs", C.c_void_p), ("out", C.c_void_p),
+                ("out_heap", C.c_void_p), ("heap_host_base", C.c_uint64), ("type_id", C.c_int32), ("phys", C.c_int32),
+                ("dec_scale", C.c_int32), ("reserved", C.c_int32)]
+
+
 class RevFixedJob(C.Structure):
     _fields_ = [("in_values", C.c_void_p), ("in_validity", C.c_void_p), ("in_bit_offset", C.c_int64),
                 ("out_data", C.c_void_p), ("out_validity", C.c_void_p), ("null_count", C.c_void_p),
@@ -86,11 +92,11 @@ CHUNK_SINK = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_uint32, C.POINTER
 EXPORTED_SYMBOLS = [
     "dmb_dev_fixed_batch", "dmb_op_out_width", "dmb_phys_width", "dmb_dev_string_scratch_bytes",
     "dmb_dev_string_error", "dmb_dev_string_batch", "dmb_dev_rev_fixed_batch", "dmb_dev_rev_string_batch",
-    "dmb_dev_valid_bytes_to_masks", "dmb_dev_make_string_t",
+    "dmb_dev_valid_bytes_to_masks", "dmb_dev_make_string_t", "dmb_render_supported", "dmb_dev_render_text",
     "duckdb_mb_gpu_last_error", "duckdb_mb_gpu_device_count", "duckdb_mb_gpu_ctx_create",
     "duckdb_mb_gpu_ctx_destroy", "duckdb_mb_gpu_ctx_sync", "duckdb_mb_gpu_host_alloc", "duckdb_mb_gpu_host_free",
     "duckdb_mb_gpu_result_from_chunks", "duckdb_mb_gpu_result_materialise_arrow",
-    "duckdb_mb_gpu_result_export_arrow", "duckdb_mb_gpu_result_typed_column", "duckdb_mb_gpu_result_timings",
+    "duckdb_mb_gpu_result_export_arrow", "duckdb_mb_gpu_result_typed_column", "duckdb_mb_gpu_result_text_column", "duckdb_mb_gpu_result_timings",
     "duckdb_mb_gpu_result_link_bytes",
     "duckdb_mb_arrow_column_count", "duckdb_mb_arrow_row_count", "duckdb_mb_arrow_schema",
     "duckdb_mb_arrow_get_column_int32", "duckdb_mb_arrow_get_column_int64", "duckdb_mb_arrow_get_column_double",
@@ -153,6 +159,10 @@ def lib():
     L.dmb_dev_string_error.argtypes = [vp, vp]
     L.dmb_dev_make_string_t.restype = i32
     L.dmb_dev_make_string_t.argtypes = [vp, vp, vp, u64, vp, i64, vp]
+    L.dmb_render_supported.restype = i32
+    L.dmb_render_supported.argtypes = [i32, i32]
+    L.dmb_dev_render_text.restype = i32
+    L.dmb_dev_render_text.argtypes = [C.POINTER(RenderJob), vp, i64, vp]
     L.dmb_dev_valid_bytes_to_masks.restype = i32
     L.dmb_dev_valid_bytes_to_masks.argtypes = [vp, vp, vp, i64, vp]
     L.dmb_dev_rev_fixed_batch.restype = i32
@@ -176,6 +186,8 @@ def lib():
     L.duckdb_mb_gpu_result_export_arrow.argtypes = [vp, i32, vp, vp]
     L.duckdb_mb_gpu_result_typed_column.restype = i32
     L.duckdb_mb_gpu_result_typed_column.argtypes = [vp, i32, C.POINTER(TypedColumn)]
+    L.duckdb_mb_gpu_result_text_column.restype = i32
+    L.duckdb_mb_gpu_result_text_column.argtypes = [vp, i32, C.POINTER(TypedColumn)]
     L.duckdb_mb_gpu_result_timings.restype = i32
     L.duckdb_mb_gpu_result_timings.argtypes = [vp, C.POINTER(C.c_double)]
     L.duckdb_mb_gpu_result_link_bytes.restype = i32

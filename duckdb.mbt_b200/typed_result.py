@@ -179,10 +179,16 @@ _NUMPY_OF = {(INT, 4): np.dtype("<i4"), (DOUBLE, 8): np.dtype("<f8"), (BOOL, 1):
              (DATE, 4): np.dtype("<i4"), (TIMESTAMP, 8): np.dtype("<i8")}
 
 
-def typed_column(result: ArrowResult, col: int) -> TypedColumn:
+def text_column(result: ArrowResult, col: int) -> TypedColumn:
+    """The string form of one column (duckdb_mb_gpu_result_text_column): every cell's VARCHAR
+    rendering as utf8 offsets + data, what `Connection::query` collects per cell."""
+    return typed_column(result, col, _fn="duckdb_mb_gpu_result_text_column")
+
+
+def typed_column(result: ArrowResult, col: int, _fn: str = "duckdb_mb_gpu_result_typed_column") -> TypedColumn:
     """One typed column straight from the GPU (duckdb_mb_gpu_result_typed_column)."""
     tc = nat.TypedColumn()
-    if not result.lib.duckdb_mb_gpu_result_typed_column(result.handle, col, C.byref(tc)):
+    if not getattr(result.lib, _fn)(result.handle, col, C.byref(tc)):
         raise DuckDBError(nat.last_error())
     n = int(tc.length)
     valid = np.frombuffer(C.string_at(tc.valid, n), dtype=np.uint8) != 0 if n else np.zeros(0, dtype=bool)

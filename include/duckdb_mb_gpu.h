@@ -205,6 +205,29 @@ int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_t *counts,
                              const int64_t *row_off, int64_t nchunks, int64_t nrows,
                              void *scratch, void *stream);
 
+/* K7: fixed-width cells -> their DuckDB VARCHAR rendering as duckdb_string_t (<= 12 bytes inlined,
+ * else prefix + pointer into `out_heap`, one DMB_RENDER_SLOT_BYTES slot per row), so the rendered
+ * column can be fed to dmb_dev_string_batch like a VARCHAR column.  Replaces libduckdb's
+ * duckdb_value_varchar / duckdb_value_to_string at the reference's call sites
+ * src/duckdb_native.c:224-238, :2478, :2715 and :305-318.  Rendered: BOOLEAN, the eight integer
+ * types, DATE, TIMESTAMP / _TZ / _S / _MS / _NS, DECIMAL (int16/32/64 storage). */
+#define DMB_RENDER_SLOT_BYTES 48
+typedef struct dmb_render_job {
+  const void *in_data;         /* column slab */
+  const uint64_t *in_validity; /* validity slab or NULL */
+  const dmb_vec_desc *vecs;    /* [nchunks], of the source column */
+  dmb_string_t *out;           /* string_t slab: chunk k at k*2048 entries */
+  uint8_t *out_heap;           /* nchunks*2048*DMB_RENDER_SLOT_BYTES bytes */
+  uint64_t heap_host_base;     /* the "host address" written into pointer entries (any value; the
+                                  string kernel rebases against the same number) */
+  int32_t type_id;             /* enum dmb_type */
+  int32_t phys;                /* enum dmb_phys */
+  int32_t dec_scale;
+  int32_t reserved;
+} dmb_render_job;
+int32_t dmb_render_supported(int32_t type_id, int32_t phys);
+int32_t dmb_dev_render_text(const dmb_render_job *job, const uint32_t *counts, int64_t nchunks, void *stream);
+
 /* K6 reverse (Arrow -> DataChunk vectors), the bulk door behind the appender
  * (reference row-at-a-time path: src/duckdb_native.c:1100-1235; chunk door :2029-2132). */
 typedef struct dmb_rev_fixed_job {
@@ -369,6 +392,13 @@ typedef struct dmb_typed_column {
 } dmb_typed_column;
 int32_t duckdb_mb_gpu_result_typed_column(duckdb_mb_arrow_result *r, int32_t col,
                                           dmb_typed_column *out);
+/* the string form of a column (tag = DMB_VALUE_STRING: utf8 offsets + data + byte validity): the
+ * VARCHAR rendering of every cell, which the reference's Connection::query collects with two FFI
+ * calls per cell, duckdb_mb_result_is_null + duckdb_mb_result_value -> duckdb_value_varchar
+ * (src/duckdb_native.c:215-238, loop src/duckdb_native.mbt:477-497).  0 + last error for types
+ * whose libduckdb rendering is not reproduced on the device (dmb_render_supported). */
+int32_t duckdb_mb_gpu_result_text_column(duckdb_mb_arrow_result *r, int32_t col,
+                                         dmb_typed_column *out);
 
 /* timings of the last materialise call, milliseconds: [0]=h2d [1]=kernels [2]=d2h [3]=total */
 int32_t duckdb_mb_gpu_result_timings(duckdb_mb_arrow_result *r, double *out4);

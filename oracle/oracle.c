@@ -167,6 +167,7 @@ static void ora_materialise(ora_result *r) {
  * (libduckdb, un-vendored.  Call sites: src/duckdb_native.c:2380,2384,2414,2417,2446,2449,2475,
  * 2478,2538,2541.)  Same-family casts are pinned by src/duckdb_arrow_test.mbt; the rest UNPINNED. */
 typedef struct { uint64_t lo; int64_t hi; } ora_hugeint;
+int ora_render_cell(const ora_column *c, const uint8_t *p, char *out);
 
 __attribute__((noinline)) int ora_value_is_null(ora_result *r, int32_t col, int64_t row) {
   if (!r->materialised) ora_materialise(r);
@@ -243,10 +244,9 @@ __attribute__((noinline)) char *ora_value_varchar(ora_result *r, int32_t col, in
     memcpy(out, s, len + 1);
     return out;
   }
-  char buf[64];
-  if (c->phys == P_BOOL) snprintf(buf, sizeof buf, "%s", ora_value_boolean(r, col, row) ? "true" : "false");
-  else if (c->phys == P_U64) { uint64_t v; memcpy(&v, r->dep_data[col] + (size_t)row * 8, 8); snprintf(buf, sizeof buf, "%llu", (unsigned long long)v); }
-  else snprintf(buf, sizeof buf, "%lld", (long long)ora_value_int64(r, col, row)); /* integer family only */
+  char buf[96];
+  /* DuckDB's VARCHAR cast of the cell (ora_render_cell below; formats pinned by the fixture strings) */
+  if (ora_render_cell(c, r->dep_data[col] + (size_t)row * (size_t)PHYS_W[c->phys], buf) < 0) return NULL;
   size_t len = strlen(buf);
   char *out = (char *)malloc(len + 1);
   memcpy(out, buf, len + 1);

@@ -1,0 +1,137 @@
+"""GPU parity of the text-rendering path (K7 render_text + the string kernel) through the C ABI:
+`duckdb_mb_arrow_get_column_string[_nullable]` on non-VARCHAR columns (the getter the reference's
+schema JSON prescribes for DATE / DECIMAL / TIMESTAMP columns, src/duckdb_native.c:2314-2339,
+:2456-2514), the `Value::String` typed column form of DECIMAL (src/duckdb_parsing.mbt:120-141) and
+the string-form `QueryResult` (src/duckdb.mbt:49-62), bit-exact against the oracle and against the
+reference's fixture strings (src/duckdb_fixture_cases.mbt)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import oracle  # noqa: E402
+from duckdb_mbt_b200 import chunks as ch  # noqa: E402
+
+from test_gpu_l0_parity import _mixed_batch  # noqa: E402
+from test_oracle_golden import batch_of  # noqa: E402
+
+RENDERED = {"b", "i8", "i16", "i32", "i64", "u8", "u16", "u32", "u64", "dec4", "dec9", "dec18", "date", "ts_s", "ts_ms", "ts_ns"}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from duckdb_mbt_b200 import arrow_result as ar
+    c = ar.GpuContext(0)
+    yield c
+    c.close()
+
+
+def _result(ctx, batch, **kw):
+    from duckdb_mbt_b200 import arrow_result as ar
+    return ar.ArrowResult.from_chunks(ctx, batch, **kw)
+
+
+@pytest.mark.parametrize("n,pattern", [(1, "full"), (2049, "full"), (10_000, "ragged"), (40_001, "ragged")])
+def test_string_getter_on_fixed_width_columns(ctx, n, pattern):
+    batch = _mixed_batch(n, pattern, 900 + n)
+    ora = oracle.OracleResult(batch)
+    with _result(ctx, batch) as res:
+        seen = 0
+        for j, c in enumerate(batch.columns):
+            if c.name not in RENDERED:
+                continue
+            for nullable in (False, True):
+                got = res.raw_column("string", j, nullable)
+                exp = ora.get_column("string", j, nullable)
+                assert got == exp, f"col={c.name} nullable={nullable}"
+            seen += 1
+        assert seen == len(RENDERED)
+        # types whose libduckdb rendering is not reproduced on the device: empty Bytes + error, never a guess
+        from duckdb_mbt_b200 import native as nat
+        for name in ("f64", "huge", "iv", "uuid"):
+            j = [c.name for c in batch.columns].index(name)
+            assert res.raw_column("string", j) == b""
+            assert "not reproduced" in nat.last_error()
+
+
+def test_fixture_strings_through_gpu(ctx):
+    # src/duckdb_fixture_cases.mbt: integer extremes :27-32,83-102; BOOLEAN :20-25; DATE :41-46,62-67;
+    # TIMESTAMP :55-60; DECIMAL(10,3) :69-74, DECIMAL(9,2) :76-81
+    micros = (19877 * 86400 + 12 * 3600 + 34 * 60 + 56) * 1_000_000 + 789_000
+    batch = batch_of(
+        ("big", ch.T_BIGINT, [9223372036854775807, -9223372036854775808, 0, None]),
+        ("small", ch.T_SMALLINT, [32767, -32768, 0, None]),
+        ("tiny", ch.T_TINYINT, [127, -128, 0, None]),
+        ("int", ch.T_INTEGER, [2147483647, -2147483648, 0, None]),
+        ("b", ch.T_BOOLEAN, [1, 0, 1, None]),
+        ("d", ch.T_DATE, [19877, -1, 1, None]),
+        ("ts", ch.T_TIMESTAMP, [micros, 0, -1, None]),
+        ("dec", ch.T_DECIMAL, [123456, 5, -5, None], 10, 3),
+        ("dec2", ch.T_DECIMAL, [-99999999, 0, 100, None], 9, 2),
+        ("u64", ch.T_UBIGINT, [18446744073709551615, 0, 1, None]),
+    )
+    expect = [
+        ["9223372036854775807", "-9223372036854775808", "0"],
+        ["32767", "-32768", "0"],
+        ["127", "-128", "0"],
+        ["2147483647", "-2147483648", "0"],
+        ["true", "false", "true"],
+        ["2024-06-03", "1969-12-31", "1970-01-02"],
+        ["2024-06-03 12:34:56.789", "1970-01-01 00:00:00", "1969-12-31 23:59:59.999999"],
+        ["123.456", "0.005", "-0.005"],
+        ["-999999.99", "0.00", "1.00"],
+        ["18446744073709551615", "0", "1"],
+    ]
+    from duckdb_mbt_b200 import typed_result as tr
+    ora = oracle.OracleResult(batch)
+    with _result(ctx, batch) as res:
+        for j, exp in enumerate(expect):
+            t = tr.text_column(res, j)
+            assert [t.value(i).as_string() for i in range(3)] == exp, j
+            assert t.valid.tolist() == [True, True, True, False] and t.value(3).is_null()
+            assert int(t.offsets[4]) == int(t.offsets[3])  # NULL cell: zero-length
+            # the reference-format blob of the same column equals the oracle's (incl. its NULL-terminator defect)
+            for nullable in (False, True):
+                assert res.raw_column("string", j, nullable) == ora.get_column("string", j, nullable)
+
+
+def test_decimal_typed_column_is_value_string(ctx):
+    from duckdb_mbt_b200 import typed_result as tr
+    rng = np.random.default_rng(11)
+    n = 7000
+    counts = ch.chunk_counts(n, "ragged", rng)
+    valid = rng.random(n) > 0.2
+    vals = rng.integers(-10**17, 10**17, n, dtype=np.int64)
+    batch = ch.ChunkBatch(counts, [ch.fixed_column("dec", ch.T_DECIMAL, vals, counts, valid=valid, dec_width=18, dec_scale=3, garbage_rng=rng)])
+    with _result(ctx, batch) as res:
+        tc = tr.typed_column(res, 0)
+        assert tc.tag == tr.STRING
+        assert np.array_equal(tc.valid, valid)
+        for i in (0, 1, 17, n - 1):
+            v = tc.value(i)
+            if valid[i]:
+                assert v.as_string() == oracle.render_decimal64(int(vals[i]), 3)
+            else:
+                assert v.is_null()
+
+
+def test_query_result_string_form(ctx):
+    from duckdb_mbt_b200.query_result import QueryResult
+    batch = batch_of(("id", ch.T_INTEGER, [1, 2, None]),
+                     ("name", ch.T_VARCHAR, ["a", None, "ccc"]),
+                     ("d", ch.T_DATE, [19877, None, 0]),
+                     ("p", ch.T_DECIMAL, [1050, 99, None], 10, 2))
+    with _result(ctx, batch) as res:
+        q = QueryResult.from_result(res, [c.type_id for c in batch.columns])
+        assert q.row_count() == 3 and q.column_count() == 4
+        assert q.rows == [["1", "a", "2024-06-03", "10.50"], ["2", "", "", "0.99"], ["", "ccc", "1970-01-01", ""]]
+        assert q.nulls == [[False, False, False, False], [False, True, True, False], [True, False, False, True]]
+        assert q.cell(0, 3) == "10.50" and q.cell(1, 1) is None and q.cell(9, 0) is None
+        t = q.to_typed()
+        assert t.get_int(0, 0) == 1 and t.is_null(2, 0)
+        assert t.get_date(0, 2) == 19877
+        assert t.get_string(0, 3) == "10.50"
