@@ -136,6 +136,107 @@ __device__ __forceinline__ void put32(uint32_t *w, uint32_t val, int nb0, int nb
   else atomicOr(w, val & byte_mask32((uint32_t)nb0, (uint32_t)nb1));
 }
 
+// Step 6 of string_batch_kernel (see the header comment): output-centric gather of a tile whose
+// sm.str / sm.src / sm.off / sm.run / sm.low_mask are filled.  `len` / `my_off` are the calling
+// thread's own consecutive rows (tid * kStrPerThread + k) and its tile-local exclusive offset.
+template <int MODE>
+__device__ __forceinline__ void gather_runs(StrSmem &sm, int tid, int lane, int warp, const uint32_t (&len)[kStrPerThread],
+                                            uint32_t my_off, uint32_t total, uint32_t mis, uint8_t *gbase, uint32_t nvec) {
+  for (uint32_t q0 = 0; q0 < nvec; q0 += kMapVecs) {
+    const uint32_t q1 = q0 + kMapVecs < nvec ? q0 + kMapVecs : nvec;
+    const uint32_t qmap = q1 < nvec ? q1 + 1u : q1;  // one entry past the window: the fast-path test looks at v + 1
+    // (a) every non-empty row publishes the vectors v with L(v) inside the row
+    {
+      uint32_t o = my_off;
+#pragma unroll
+      for (int k = 0; k < kStrPerThread; ++k) {
+        const uint32_t start = o, stop = o + len[k];
+        o = stop;
+        if (stop == start) continue;
+        uint32_t qa = start == 0u ? 0u : (start + mis + 15u) >> 4;  // first v with L(v) >= start
+        uint32_t qb = (stop + mis + 15u) >> 4;                      // first v with L(v) >= stop
+        qa = qa > q0 ? qa : q0;
+        qb = qb < qmap ? qb : qmap;
+        for (uint32_t q = qa; q < qb; ++q) sm.first_row[q - q0] = (uint16_t)(tid * kStrPerThread + k);
+      }
+    }
+    __syncthreads();
+    DMB_TRACE(4);
+    // (b) fast pass: every warp owns an equal, contiguous share of the window's vectors; vectors
+    //     inside one run are finished here, the others go to the warp's own queue
+    uint16_t *my_slow = sm.slow + warp * (kMapVecs / (kThreads / 32));
+    uint32_t nslow = 0;
+    const uint32_t per_warp = ((q1 - q0 + (kThreads / 32) * 32u - 1u) / ((kThreads / 32) * 32u)) * 32u;  // <= 256, multiple of 32
+    const uint32_t wq0 = q0 + (uint32_t)warp * per_warp < q1 ? q0 + (uint32_t)warp * per_warp : q1;
+    const uint32_t wq1 = wq0 + per_warp < q1 ? wq0 + per_warp : q1;
+    for (uint32_t vb = wq0; vb < wq1; vb += 32) {
+      const uint32_t v = vb + lane;
+      bool slow = false;
+      if (v < wq1) {
+        const uint32_t vbeg = v << 4;
+        const bool whole = (v > 0 || mis == 0) && (vbeg + 16u - mis <= total) && (v + 1u < nvec);
+        const int r = sm.first_row[v - q0];
+        slow = !whole || sm.run[r] != sm.run[sm.first_row[v + 1u - q0]];
+        if (!slow) {
+          uint64_t w0, w1;
+          load16(reinterpret_cast<const uint8_t *>(sm.src[r] + (vbeg - mis)), w0, w1);
+          st_stream(reinterpret_cast<uint4 *>(gbase + vbeg),
+                    make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32)));
+        }
+      }
+      const uint32_t ballot = __ballot_sync(0xffffffffu, slow);
+      if (slow) my_slow[nslow + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)(v - q0);
+      nslow += __popc(ballot);
+    }
+    __syncwarp();
+    // (c) dense pass over the warp's queued vectors: walk the rows, merge the pieces
+#pragma unroll 1
+    for (uint32_t idx = lane; idx < nslow; idx += 32) {
+      const uint32_t v = q0 + my_slow[idx];
+      const uint32_t vbeg = v << 4;                    // position + mis of the vector's first byte
+      const uint32_t lo = v ? vbeg - mis : 0u;         // tile-local bytes [lo, hi) owned by this vector
+      const uint32_t hi = (vbeg + 16u - mis) < total ? (vbeg + 16u - mis) : total;
+      int r = sm.first_row[v - q0];
+      uint64_t w0 = 0, w1 = 0;
+      uint32_t seg_pos = lo;                           // current source stream covers [seg_pos, seg_end)
+      const uint8_t *sp = reinterpret_cast<const uint8_t *>(sm.src[r] + lo);
+      uint32_t row_end = sm.off[r + 1];
+      uint32_t seg_end = MODE == DMB_STR_REF_BLOB ? row_end - 1u : row_end;  // payload end; the terminator stays 0
+#pragma unroll 1
+      while (row_end < hi) {
+        int r2 = r + 1;                                // next non-empty row (off[] is packed: it starts at row_end)
+        uint32_t o2 = sm.off[r2 + 1];
+        while (o2 == row_end) { ++r2; o2 = sm.off[r2 + 1]; }
+        const bool same_run = sm.run[r2] == sm.run[r];
+        r = r2;
+        if (same_run) {                                // heap bytes continue: same stream
+          row_end = o2;
+          seg_end = o2;
+          continue;
+        }
+        if (seg_end > seg_pos) emit(w0, w1, sp, seg_pos + mis - vbeg, seg_end + mis - vbeg, sm.low_mask);
+        seg_pos = row_end;
+        sp = reinterpret_cast<const uint8_t *>(sm.src[r2] + row_end);
+        row_end = o2;
+        seg_end = MODE == DMB_STR_REF_BLOB ? o2 - 1u : o2;
+      }
+      {
+        const uint32_t e = seg_end < hi ? seg_end : hi;
+        if (e > seg_pos) emit(w0, w1, sp, seg_pos + mis - vbeg, e + mis - vbeg, sm.low_mask);
+      }
+      const bool full = (v > 0 || mis == 0) && (vbeg + 16u - mis <= total);
+      if (full) {
+        st_stream(reinterpret_cast<uint4 *>(gbase + vbeg),
+                  make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32)));
+      } else {  // the neighbouring tiles own the other bytes of this vector
+        const uint32_t b0 = lo + mis - vbeg, b1 = hi + mis - vbeg;
+        for (uint32_t q = b0; q < b1; ++q) gbase[vbeg + q] = (uint8_t)((q < 8 ? w0 : w1) >> (8u * (q & 7u)));
+      }
+    }
+    if (q1 < nvec) __syncthreads();
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, DMB_STR_MIN_CTAS)
 string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles) {
@@ -251,7 +352,10 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   if (lane == 31) { sm.warp_sum[warp] = incl; sm.warp_run[warp] = rmax; }
   const uint32_t rmax_excl_lane = __shfl_up_sync(0xffffffffu, rmax, 1);
   DMB_TRACE(1);
-  const int tile_flags = __syncthreads_or(flags);
+  // __syncthreads_or yields a predicate, not the OR of the values: it carries the "pointer row
+  // present" bit; the (rare) error bits are reported by the thread that saw them
+  if (flags & 6) atomicOr(scratch + 1, (unsigned long long)(((flags & 2) ? kErrHeapRange : 0) | ((flags & 4) ? kErrTileTooBig : 0)));
+  const int tile_flags = __syncthreads_or(flags & 1);
   DMB_TRACE(2);
   uint32_t warp_excl = 0, tile_total = 0, run_excl = 0;
 #pragma unroll
@@ -262,8 +366,6 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     tile_total += s;
   }
   if (lane > 0) run_excl = run_excl > rmax_excl_lane ? run_excl : rmax_excl_lane;
-  if (tid == 0 && (tile_flags & 6))
-    atomicOr(scratch + 1, (unsigned long long)(((tile_flags & 2) ? kErrHeapRange : 0) | ((tile_flags & 4) ? kErrTileTooBig : 0)));
   const uint32_t my_off = warp_excl + incl - tsum;
   {
     uint32_t o = my_off, run = run_excl;
@@ -368,103 +470,444 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     }
     return;
   }
-  for (uint32_t q0 = 0; q0 < nvec; q0 += kMapVecs) {
-    const uint32_t q1 = q0 + kMapVecs < nvec ? q0 + kMapVecs : nvec;
-    const uint32_t qmap = q1 < nvec ? q1 + 1u : q1;  // one entry past the window: the fast-path test looks at v + 1
-    // (a) every non-empty row publishes the vectors v with L(v) inside the row
-    {
-      uint32_t o = my_off;
-#pragma unroll
-      for (int k = 0; k < kStrPerThread; ++k) {
-        const uint32_t start = o, stop = o + len[k];
-        o = stop;
-        if (stop == start) continue;
-        uint32_t qa = start == 0u ? 0u : (start + mis + 15u) >> 4;  // first v with L(v) >= start
-        uint32_t qb = (stop + mis + 15u) >> 4;                      // first v with L(v) >= stop
-        qa = qa > q0 ? qa : q0;
-        qb = qb < qmap ? qb : qmap;
-        for (uint32_t q = qa; q < qb; ++q) sm.first_row[q - q0] = (uint16_t)(tid * kStrPerThread + k);
-      }
-    }
-    __syncthreads();
-    DMB_TRACE(4);
-    // (b) fast pass: every warp owns an equal, contiguous share of the window's vectors; vectors
-    //     inside one run are finished here, the others go to the warp's own queue
-    uint16_t *my_slow = sm.slow + warp * (kMapVecs / (kThreads / 32));
-    uint32_t nslow = 0;
-    const uint32_t per_warp = ((q1 - q0 + (kThreads / 32) * 32u - 1u) / ((kThreads / 32) * 32u)) * 32u;  // <= 256, multiple of 32
-    const uint32_t wq0 = q0 + (uint32_t)warp * per_warp < q1 ? q0 + (uint32_t)warp * per_warp : q1;
-    const uint32_t wq1 = wq0 + per_warp < q1 ? wq0 + per_warp : q1;
-    for (uint32_t vb = wq0; vb < wq1; vb += 32) {
-      const uint32_t v = vb + lane;
-      bool slow = false;
-      if (v < wq1) {
-        const uint32_t vbeg = v << 4;
-        const bool whole = (v > 0 || mis == 0) && (vbeg + 16u - mis <= total) && (v + 1u < nvec);
-        const int r = sm.first_row[v - q0];
-        slow = !whole || sm.run[r] != sm.run[sm.first_row[v + 1u - q0]];
-        if (!slow) {
-          uint64_t w0, w1;
-          load16(reinterpret_cast<const uint8_t *>(sm.src[r] + (vbeg - mis)), w0, w1);
-          st_stream(reinterpret_cast<uint4 *>(gbase + vbeg),
-                    make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32)));
-        }
-      }
-      const uint32_t ballot = __ballot_sync(0xffffffffu, slow);
-      if (slow) my_slow[nslow + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)(v - q0);
-      nslow += __popc(ballot);
-    }
-    __syncwarp();
-    // (c) dense pass over the warp's queued vectors: walk the rows, merge the pieces
-#pragma unroll 1
-    for (uint32_t idx = lane; idx < nslow; idx += 32) {
-      const uint32_t v = q0 + my_slow[idx];
-      const uint32_t vbeg = v << 4;                    // position + mis of the vector's first byte
-      const uint32_t lo = v ? vbeg - mis : 0u;         // tile-local bytes [lo, hi) owned by this vector
-      const uint32_t hi = (vbeg + 16u - mis) < total ? (vbeg + 16u - mis) : total;
-      int r = sm.first_row[v - q0];
-      uint64_t w0 = 0, w1 = 0;
-      uint32_t seg_pos = lo;                           // current source stream covers [seg_pos, seg_end)
-      const uint8_t *sp = reinterpret_cast<const uint8_t *>(sm.src[r] + lo);
-      uint32_t row_end = sm.off[r + 1];
-      uint32_t seg_end = MODE == DMB_STR_REF_BLOB ? row_end - 1u : row_end;  // payload end; the terminator stays 0
-#pragma unroll 1
-      while (row_end < hi) {
-        int r2 = r + 1;                                // next non-empty row (off[] is packed: it starts at row_end)
-        uint32_t o2 = sm.off[r2 + 1];
-        while (o2 == row_end) { ++r2; o2 = sm.off[r2 + 1]; }
-        const bool same_run = sm.run[r2] == sm.run[r];
-        r = r2;
-        if (same_run) {                                // heap bytes continue: same stream
-          row_end = o2;
-          seg_end = o2;
-          continue;
-        }
-        if (seg_end > seg_pos) emit(w0, w1, sp, seg_pos + mis - vbeg, seg_end + mis - vbeg, sm.low_mask);
-        seg_pos = row_end;
-        sp = reinterpret_cast<const uint8_t *>(sm.src[r2] + row_end);
-        row_end = o2;
-        seg_end = MODE == DMB_STR_REF_BLOB ? o2 - 1u : o2;
-      }
-      {
-        const uint32_t e = seg_end < hi ? seg_end : hi;
-        if (e > seg_pos) emit(w0, w1, sp, seg_pos + mis - vbeg, e + mis - vbeg, sm.low_mask);
-      }
-      const bool full = (v > 0 || mis == 0) && (vbeg + 16u - mis <= total);
-      if (full) {
-        st_stream(reinterpret_cast<uint4 *>(gbase + vbeg),
-                  make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32)));
-      } else {  // the neighbouring tiles own the other bytes of this vector
-        const uint32_t b0 = lo + mis - vbeg, b1 = hi + mis - vbeg;
-        for (uint32_t q = b0; q < b1; ++q) gbase[vbeg + q] = (uint8_t)((q < 8 ? w0 : w1) >> (8u * (q & 7u)));
-      }
-    }
-    if (q1 < nvec) __syncthreads();
-  }
+  gather_runs<MODE>(sm, tid, lane, warp, len, my_off, total, mis, gbase, nvec);
 #ifdef DMB_STR_TRACE
   __syncthreads();
   DMB_TRACE(6);
 #endif
+}
+
+// ------------------------------------------------------------------ TMA-staged pack kernel
+// string_pack_kernel<LARGE, R>: the Arrow utf8 path for columns of short strings (the common case:
+// names, flags, comments).  The run-gather above pays ~20 warp-instructions per row when runs are
+// short (every 16-byte output vector then straddles a run boundary) and is issue bound; this
+// kernel moves the byte work onto the copy engines and keeps the SIMT part row-centric and small:
+//
+//   1. tile = R*256 consecutive rows of one chunk; string_t loaded coalesced, transposed through
+//      (swizzled) shared memory so that every thread owns R CONSECUTIVE rows,
+//   2. lengths -> block scan; the tile's heap span [hmin, hmax) by redux.sync min/max,
+//   3. one elected thread fetches the whole span with ONE bulk copy (cp.async.bulk global ->
+//      shared, mbarrier complete_tx) while warp 0 resolves the tile's base by a 128-wide
+//      decoupled look-back (four status words in flight per lane: one L2 round trip per 128
+//      predecessors) and the other warps zero the output stage,
+//   4. offsets leave straight from registers (R consecutive values per thread: vector stores),
+//   5. every thread streams its rows' bytes (registers for inlined strings, the staged span for
+//      pointer strings) into the output stage with 32-bit funnel shifts: interior words are plain
+//      stores, the <= 2 words a thread shares with its neighbours are shared-memory atomicOr,
+//   6. the stage leaves with bulk copies shared -> global: one for the 16-byte aligned interior,
+//      and sm_100's byte-masked form (cp.async.bulk ... .cp_mask) for the ragged first / last
+//      vector, whose other bytes belong to the neighbouring tiles.
+//
+// Tiles whose span or output does not fit the stages (scattered pointers, long strings) fall back
+// to the run-gather in place (R == 2 only; same tiles, same status words).
+constexpr uint32_t kPackTail = 256;   // bytes of bookkeeping in front of the stages
+constexpr int kLookWide = 4;          // status words in flight per lane in the look-back
+
+struct PackTail {
+  unsigned long long mbar;
+  unsigned long long base;
+  uint32_t warp_sum[kThreads / 32];
+  uint32_t warp_hmin[kThreads / 32];
+  uint32_t warp_hmax[kThreads / 32];
+  uint32_t warp_run[kThreads / 32];
+};
+static_assert(sizeof(PackTail) <= kPackTail, "PackTail");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(__cvta_generic_to_global(dst)), "r"(src_smem), "r"(bytes) : "memory");
+}
+// byte i of every 16-byte chunk is copied iff bit i of `mask` is set (PTX ISA 8.6, sm_100)
+__device__ __forceinline__ void bulk_store_masked(void *dst, uint32_t src_smem, uint32_t bytes, uint32_t mask) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.cp_mask [%0], [%1], %2, %3;"
+               ::"l"(__cvta_generic_to_global(dst)), "r"(src_smem), "r"(bytes), "h"((unsigned short)mask) : "memory");
+}
+__device__ __forceinline__ void bulk_store_drain() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// low `n` bytes set, n in 0..4
+__device__ __forceinline__ uint32_t low_bytes(uint32_t n) { return n >= 4u ? 0xffffffffu : ((1u << (8u * n)) - 1u); }
+
+// slot of row i in the transposed string_t tile: a quarter-warp's 128-bit accesses stay conflict
+// free both for lane-consecutive rows (the coalesced store) and for rows R apart (the owner's load)
+__device__ __forceinline__ int swz(int i) { return i ^ ((i >> 3) & 7); }
+
+// exclusive prefix of tile `tile` by decoupled look-back, executed by one warp; kLookWide status
+// words are in flight per lane, so one L2 round trip inspects 32*kLookWide predecessors
+__device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, int64_t tile, uint64_t agg, int lane) {
+  if (lane == 0) atomicExch(status + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | agg);
+  uint64_t prefix = 0;
+  if (tile > 0) {
+    int64_t look = tile - 1;
+    while (true) {
+      uint64_t st[kLookWide];
+#pragma unroll
+      for (int j = 0; j < kLookWide; ++j) {
+        const int64_t idx = look - (int64_t)(32 * j + lane);
+        st[j] = idx >= 0 ? ld_status(status + idx) : kFlagPrefix;  // before tile 0: prefix 0
+      }
+      uint64_t v = 0;
+      int state = 0;  // 0: keep looking  1: a prefix closed the sum  2: a needed word is not published yet
+#pragma unroll
+      for (int j = 0; j < kLookWide; ++j) {
+        if (state == 0) {
+          const uint32_t ready = __ballot_sync(0xffffffffu, (st[j] >> 62) != 0);
+          const uint32_t is_p = __ballot_sync(0xffffffffu, (st[j] >> 62) == 2);
+          const int first_p = is_p ? (__ffs(is_p) - 1) : 31;
+          const uint32_t need = first_p >= 31 ? 0xffffffffu : ((2u << first_p) - 1u);
+          if ((ready & need) != need) state = 2;
+          else {
+            if (lane <= first_p) v += st[j] & kValueMask;
+            if (is_p) state = 1;
+          }
+        }
+      }
+      if (state == 2) continue;  // poll the window again (all its tiles are resident: they precede us)
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      prefix += v;
+      if (state == 1) break;
+      look -= 32 * kLookWide;
+    }
+    if (lane == 0) atomicExch(status + tile, kFlagPrefix | ((prefix + agg) & kValueMask));
+  }
+  return prefix;
+}
+
+template <bool LARGE, int R>
+__global__ void __launch_bounds__(kThreads, R == 2 ? 6 : 4)
+string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles,
+                   uint32_t ostage_bytes, uint32_t hstage_bytes) {
+  constexpr int kRows = kThreads * R;
+  constexpr int kTilesPerChunk = kVec / kRows;
+  constexpr int MODE = LARGE ? DMB_STR_ARROW_LARGE : DMB_STR_ARROW_UTF8;
+  static_assert(R == 2 || R == 8, "R");
+  static_assert(R != 2 || kRows == kStrTileRows, "the fallback shares the run-gather's tiles");
+  extern __shared__ __align__(128) uint8_t dsm[];
+  PackTail &pt = *reinterpret_cast<PackTail *>(dsm);
+  uint8_t *ostage = dsm + kPackTail;                 // output stage; first the transposed string_t tile
+  uint8_t *hstage = ostage + ostage_bytes;           // heap span of the tile
+  unsigned long long *status = scratch + 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tile = (int64_t)blockIdx.x;  // dispatch order = blockIdx order (see string_batch_kernel)
+  if (tile >= ntiles) return;
+  const uint32_t mbar = smem_u32(&pt.mbar);
+  if (tid == 0) mbar_init(mbar, 1);
+
+  const int64_t c = tile / kTilesPerChunk;
+  const int r_begin = (int)(tile % kTilesPerChunk) * kRows;
+  const int count = (int)__ldg(b.counts + c);
+  int nrows_tile = count - r_begin;
+  nrows_tile = nrows_tile < 0 ? 0 : (nrows_tile > kRows ? kRows : nrows_tile);
+  const dmb_vec_desc vd = job.vecs[c];
+  const uint4 *in = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(job.in) + vd.data_off) + r_begin;
+  const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
+
+  // 1. coalesced load, transpose: thread tid owns rows tid*R .. tid*R+R-1
+  uint4 ent[R];
+  {
+    uint4 *tr = reinterpret_cast<uint4 *>(ostage);
+    uint4 tmp[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int i = k * kThreads + tid;
+      tmp[k] = i < nrows_tile ? ld_stream(in + i) : make_uint4(0, 0, 0, 0);
+    }
+    uint64_t vword = ~0ull;
+    if (mask) vword = __ldg(mask + ((r_begin + tid * R) >> 6)) >> ((r_begin + tid * R) & 63);
+#pragma unroll
+    for (int k = 0; k < R; ++k) tr[swz(k * kThreads + tid)] = tmp[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      ent[k] = tr[swz(tid * R + k)];
+      if (!((vword >> k) & 1ull) || tid * R + k >= nrows_tile) ent[k].x = 0u;  // NULL / past the chunk: no bytes
+    }
+  }
+
+  // 2. lengths, heap span (16-byte units relative to the heap base), scan
+  int flags = 0;  // 2: bad heap pointer  4: oversized row
+  uint32_t len[R];
+  uint32_t hs[R];  // pointer rows: low 32 bits of the heap offset (rebased to the tile's span below)
+  uint32_t hmin = 0xffffffffu, hmax = 0u, tsum = 0u;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    uint32_t l = ent[k].x;
+    hs[k] = 0;
+    if (l > 12u) {
+      const uint64_t p = ((uint64_t)ent[k].w << 32) | (uint64_t)ent[k].z;
+      const uint64_t rel = p - job.heap_host_base;
+      if (l >= kMaxRowBytes) { flags |= 4; l = 0; }
+      else if (R == 8 || p < job.heap_host_base || rel + l > job.heap_len) { flags |= 2; l = 0; }  // R == 8: the column has no heap
+      else {
+        const uint32_t lo16 = (uint32_t)(rel >> 4), hi16 = (uint32_t)((rel + l + 15u) >> 4);
+        hmin = hmin < lo16 ? hmin : lo16;
+        hmax = hmax > hi16 ? hmax : hi16;
+        hs[k] = (uint32_t)rel;
+      }
+    }
+    len[k] = l;
+    tsum += l;
+  }
+  uint32_t incl = tsum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += n;
+  }
+  if (R == 2) {
+    hmin = __reduce_min_sync(0xffffffffu, hmin);
+    hmax = __reduce_max_sync(0xffffffffu, hmax);
+    if (lane == 0) { pt.warp_hmin[warp] = hmin; pt.warp_hmax[warp] = hmax; }
+  }
+  if (lane == 31) pt.warp_sum[warp] = incl;
+  if (flags) atomicOr(scratch + 1, (unsigned long long)(((flags & 2) ? kErrHeapRange : 0) | ((flags & 4) ? kErrTileTooBig : 0)));
+  __syncthreads();
+  uint32_t warp_excl = 0, tile_total = 0;
+  hmin = 0xffffffffu;
+  hmax = 0u;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const uint32_t s = pt.warp_sum[w];
+    if (w < warp) warp_excl += s;
+    tile_total += s;
+    if (R == 2) {
+      const uint32_t a = pt.warp_hmin[w], z = pt.warp_hmax[w];
+      hmin = hmin < a ? hmin : a;
+      hmax = hmax > z ? hmax : z;
+    }
+  }
+  const uint32_t my_off = warp_excl + incl - tsum;
+  const uint32_t hbytes = hmax > hmin ? (hmax - hmin) << 4 : 0u;
+  // block-uniform: does the tile fit the stages?  (R == 8: always; rows are <= 12 bytes)
+  const bool staged = R == 8 || (hbytes <= hstage_bytes && tile_total + 48u <= ostage_bytes &&
+                                 (hbytes == 0u || (reinterpret_cast<uintptr_t>(job.heap_dev) & 15u) == 0u));
+
+  // 3. span fetch || look-back || stage zeroing
+  uint32_t start_row[R == 2 ? R : 1];
+  if (staged) {
+    if (tid == 0 && hbytes) {
+      mbar_expect_tx(mbar, hbytes);
+      bulk_load(smem_u32(hstage), job.heap_dev + ((uint64_t)hmin << 4), hbytes, mbar);
+    }
+    // words shared between threads are ORed in: the stage starts zeroed.  Warp 0 is busy with the look-back.
+    uint4 *z = reinterpret_cast<uint4 *>(ostage);
+    const uint32_t nz = (tile_total + 47u) >> 4;
+    for (uint32_t i = tid; i < nz; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+  } else if (R == 2) {
+    // fallback: fill the run-gather's tile (the transposed tile is dead: barrier above)
+    StrSmem &sm = *reinterpret_cast<StrSmem *>(dsm + kPackTail);
+    if (tid < 17) {
+      const uint32_t d = (uint32_t)tid;
+      auto m = [&](uint32_t w) { return d >= 4u * w + 4u ? 0xffffffffu : (d <= 4u * w ? 0u : ((1u << (8u * (d - 4u * w))) - 1u)); };
+      sm.low_mask[tid] = make_uint4(m(0), m(1), m(2), m(3));
+    }
+    uint64_t srcp[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int i = tid * R + k;
+      sm.str[i] = ent[k];
+      const uint64_t p = ((uint64_t)ent[k].w << 32) | (uint64_t)ent[k].z;
+      srcp[k] = len[k] > 12u ? reinterpret_cast<uint64_t>(job.heap_dev + (p - job.heap_host_base))
+                             : reinterpret_cast<uint64_t>(reinterpret_cast<const uint8_t *>(&sm.str[i]) + 4);
+    }
+    uint32_t pl = __shfl_up_sync(0xffffffffu, len[R - 1], 1);
+    uint64_t ps = __shfl_up_sync(0xffffffffu, srcp[R - 1], 1);
+    if (lane == 0) pl = 0u;
+    uint32_t rmax = 0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const bool follows = pl != 0u && srcp[k] == ps + pl;
+      start_row[k] = (len[k] != 0u && !follows) ? (uint32_t)(tid * R + k) + 1u : 0u;
+      if (len[k] != 0u) { pl = len[k]; ps = srcp[k]; } else { pl = 0u; }
+      rmax = rmax > start_row[k] ? rmax : start_row[k];
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t m = __shfl_up_sync(0xffffffffu, rmax, d);
+      if (lane >= d) rmax = rmax > m ? rmax : m;
+    }
+    if (lane == 31) pt.warp_run[warp] = rmax;
+    uint32_t run = __shfl_up_sync(0xffffffffu, rmax, 1);
+    if (lane == 0) run = 0u;
+    uint32_t o = my_off;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int i = tid * R + k;
+      sm.off[i] = o;
+      sm.src[i] = srcp[k] - o;
+      o += len[k];
+      run = run > start_row[k] ? run : start_row[k];
+      start_row[k] = run;  // run id within the warp; the earlier warps' maximum is merged after the barrier
+    }
+    if (tid == kThreads - 1) sm.off[kRows] = o;
+  }
+  if (warp == 0) {
+    const uint64_t prefix = lookback_wide(status, tile, (uint64_t)tile_total, lane);
+    if (lane == 0) pt.base = prefix;
+  }
+  __syncthreads();
+  const uint64_t base = pt.base;
+
+  // 4. offsets: R consecutive values per thread
+  {
+    const int64_t out_row0 = __ldg(b.row_off + c) + r_begin;
+    if (!LARGE && base + tile_total > 0x7fffffffull && tid == 0) atomicOr(scratch + 1, (unsigned long long)kErrOffsetOverflow);
+    const int i0 = tid * R;
+    if (LARGE) {
+      long long *oo = reinterpret_cast<long long *>(job.out_offsets) + out_row0 + i0;
+      uint64_t o = base + my_off;
+      if (i0 + R <= nrows_tile && (reinterpret_cast<uintptr_t>(oo) & 15u) == 0u) {
+#pragma unroll
+        for (int k = 0; k < R; k += 2) {
+          const uint64_t o1 = o + len[k];
+          __stcs(reinterpret_cast<longlong2 *>(oo + k), make_longlong2((long long)o, (long long)o1));
+          o = o1 + len[k + 1];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          if (i0 + k < nrows_tile) __stcs(oo + k, (long long)o);
+          o += len[k];
+        }
+      }
+      if (tile == ntiles - 1 && tid == 0) reinterpret_cast<long long *>(job.out_offsets)[b.nrows] = (long long)(base + tile_total);
+    } else {
+      int32_t *oo = reinterpret_cast<int32_t *>(job.out_offsets) + out_row0 + i0;
+      uint32_t o = (uint32_t)base + my_off;
+      constexpr int kV = R == 2 ? 2 : 4;  // values per vector store
+      if (i0 + R <= nrows_tile && (reinterpret_cast<uintptr_t>(oo) & (4u * kV - 1u)) == 0u) {
+        if (R == 2) {
+          __stcs(reinterpret_cast<int2 *>(oo), make_int2((int)o, (int)(o + len[0])));
+        } else {
+#pragma unroll
+          for (int k = 0; k < R; k += 4) {
+            const uint32_t o1 = o + len[k], o2 = o1 + len[k + 1], o3 = o2 + len[k + 2];
+            __stcs(reinterpret_cast<int4 *>(oo + k), make_int4((int)o, (int)o1, (int)o2, (int)o3));
+            o = o3 + len[k + 3];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          if (i0 + k < nrows_tile) __stcs(oo + k, (int32_t)o);
+          o += len[k];
+        }
+      }
+      if (tile == ntiles - 1 && tid == 0) reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)(base + tile_total);
+    }
+    if (tile == ntiles - 1 && tid == 0 && job.total_bytes) *job.total_bytes = base + tile_total;
+  }
+  if (tile_total == 0) return;
+  const uint32_t mis = (uint32_t)(base & 15ull);
+  uint8_t *gbase = job.out_data + (base - mis);
+
+  if (R == 2 && !staged) {
+    StrSmem &sm = *reinterpret_cast<StrSmem *>(dsm + kPackTail);
+    uint32_t run_excl = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      const uint32_t m = pt.warp_run[w];
+      if (w < warp) run_excl = run_excl > m ? run_excl : m;
+    }
+#pragma unroll
+    for (int k = 0; k < (R == 2 ? R : 1); ++k) sm.run[tid * R + k] = (uint16_t)(start_row[k] > run_excl ? start_row[k] : run_excl);
+    __syncthreads();
+    uint32_t l2[kStrPerThread];
+#pragma unroll
+    for (int k = 0; k < kStrPerThread; ++k) l2[k] = len[k];
+    gather_runs<MODE>(sm, tid, lane, warp, l2, my_off, tile_total, mis, gbase, (mis + tile_total + 15u) >> 4);
+    return;
+  }
+
+  // 5. pack: this thread's rows as one byte stream starting at stage byte mis + my_off
+  if (hbytes) mbar_wait(mbar, 0);
+  {
+    uint32_t *ow = reinterpret_cast<uint32_t *>(ostage);
+    const uint32_t *hw = reinterpret_cast<const uint32_t *>(hstage);
+    const uint32_t hbase = hmin << 4;  // low 32 bits of the span's heap offset
+    const uint32_t pos = mis + my_off;
+    uint32_t wp = pos >> 2, fill = pos & 3u, cur = 0u;
+    const uint32_t shared_wp = fill ? wp : 0xffffffffu;  // a first word that earlier threads also write
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const uint32_t l = len[k];
+      if (l == 0u) continue;
+      const uint32_t n = fill + l, nw = n >> 2;
+      if (l <= 12u) {
+        // inlined: payload in registers, bytes past the length cleared
+        const uint32_t p0 = ent[k].y & low_bytes(l);
+        const uint32_t p1 = l > 4u ? ent[k].z & low_bytes(l - 4u) : 0u;
+        const uint32_t p2 = l > 8u ? ent[k].w & low_bytes(l - 8u) : 0u;
+        const uint32_t s = 8u * fill;
+        const uint32_t x0 = cur | (p0 << s);
+        const uint32_t x1 = __funnelshift_l(p0, p1, s);
+        const uint32_t x2 = __funnelshift_l(p1, p2, s);
+        const uint32_t x3 = __funnelshift_l(p2, 0u, s);
+        if (nw >= 1u) {
+          if (wp == shared_wp) atomicOr(ow + wp, x0); else ow[wp] = x0;
+        }
+        if (nw >= 2u) ow[wp + 1] = x1;
+        if (nw >= 3u) ow[wp + 2] = x2;
+        cur = nw == 0u ? x0 : (nw == 1u ? x1 : (nw == 2u ? x2 : x3));
+      } else if (R == 2) {
+        // pointer: the staged span.  Output word m of the row holds source bytes qp-4+4m .. +3
+        const uint32_t qp = (hs[k] - hbase) + 4u - fill;
+        const uint32_t sq = 8u * (qp & 3u);
+        const uint32_t *s = hw + (qp >> 2);
+        uint32_t prev = s[-1], nxt = s[0];
+        const uint32_t x0 = (__funnelshift_r(prev, nxt, sq) & ~low_bytes(fill)) | cur;
+        if (wp == shared_wp) atomicOr(ow + wp, x0); else ow[wp] = x0;  // l > 12: the word always completes
+        prev = nxt;
+        uint32_t *o = ow + wp;
+#pragma unroll 2
+        for (uint32_t m = 1; m < nw; ++m) {
+          nxt = s[m];
+          o[m] = __funnelshift_r(prev, nxt, sq);
+          prev = nxt;
+        }
+        cur = (n & 3u) ? (__funnelshift_r(prev, s[nw], sq) & low_bytes(n & 3u)) : 0u;
+      }
+      wp += nw;
+      fill = n & 3u;
+    }
+    if (fill) atomicOr(ow + wp, cur);  // last word: the next thread owns its other bytes
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  // 6. stage -> out_data: stage byte q is global byte gbase + q
+  if (tid == 0) {
+    const uint32_t end = mis + tile_total;
+    const uint32_t q0 = mis ? 16u : 0u, q1 = end & ~15u;
+    const uint32_t so = smem_u32(ostage);
+    if (mis) bulk_store_masked(gbase, so, 16u, (0xffffu << mis) & (end < 16u ? (1u << end) - 1u : 0xffffu));
+    if (q1 > q0) bulk_store(gbase + q0, so + q0, q1 - q0);
+    if ((end & 15u) && q1 >= q0) bulk_store_masked(gbase + q1, so + q1, 16u, (1u << (end & 15u)) - 1u);
+    bulk_store_drain();  // the stage must outlive the reads
+  }
 }
 
 // ------------------------------------------------------------------ columns without a heap
@@ -681,6 +1124,39 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
     kernel<<<(unsigned)ntiles, kThreads, 0, st>>>(*job, b, (unsigned long long *)scratch, ntiles);
     return check_cuda(cudaGetLastError(), "string_batch_kernel launch");
   };
+  // Arrow modes: the TMA-staged pack kernel, unless the strings are long (long runs: the run-gather is
+  // the better fit) or the heap is beyond 32-bit 16-byte units
+  static const bool no_pack = getenv("DMB_STR_NO_PACK") != nullptr;
+  if (!no_pack && (job->mode == DMB_STR_ARROW_UTF8 || job->mode == DMB_STR_ARROW_LARGE) && job->heap_len < (1ull << 35)) {
+    const bool large = job->mode == DMB_STR_ARROW_LARGE;
+    auto launch_pack = [&](auto kernel, int64_t nt, uint32_t ob, uint32_t hb) -> int32_t {
+      const size_t smem = (size_t)kPackTail + ob + hb + 128;
+      static thread_local const void *configured[8] = {nullptr};
+      bool seen = false;
+      for (const void *q : configured) seen = seen || q == (const void *)kernel;
+      if (!seen) {
+        if (check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024), "string_pack_kernel smem attribute")) return -1;
+        for (const void *&q : configured) if (!q) { q = (const void *)kernel; break; }
+      }
+      kernel<<<(unsigned)nt, kThreads, smem, st>>>(*job, b, (unsigned long long *)scratch, nt, ob, hb);
+      return check_cuda(cudaGetLastError(), "string_pack_kernel launch");
+    };
+    if (job->heap_len == 0) {  // inlined strings only: whole-vector tiles, 8 rows per thread
+      const uint32_t ob = (uint32_t)kVec * 16u;
+      return large ? launch_pack(string_pack_kernel<true, 8>, nchunks, ob, 0u) : launch_pack(string_pack_kernel<false, 8>, nchunks, ob, 0u);
+    }
+    const double heap_per_tile = (double)job->heap_len / (double)nrows * (double)kStrTileRows;
+    if (heap_per_tile <= 40.0 * 1024.0) {
+      static const double slack = getenv("DMB_STR_PACK_SLACK") ? atof(getenv("DMB_STR_PACK_SLACK")) : 1.15;
+      uint32_t hb = ((uint32_t)(heap_per_tile * slack) + 1024u + 127u) & ~127u;
+      if (hb < 2048u) hb = 2048u;
+      uint32_t ob = hb + 2048u;
+      if (ob < (uint32_t)kStrTileRows * 16u) ob = (uint32_t)kStrTileRows * 16u;
+      const uint32_t need = ((uint32_t)sizeof(StrSmem) + 127u) & ~127u;  // the in-place fallback's tile
+      if (ob + hb < need) ob = need - hb;
+      return large ? launch_pack(string_pack_kernel<true, 2>, ntiles, ob, hb) : launch_pack(string_pack_kernel<false, 2>, ntiles, ob, hb);
+    }
+  }
   if (job->heap_len == 0 && !getenv("DMB_STR_NO_INLINE_KERNEL")) {  // no heap: inlined strings only, whole-vector tiles
     auto launch_inl = [&](auto kernel) -> int32_t {
       kernel<<<(unsigned)nchunks, kThreads, 0, st>>>(*job, b, (unsigned long long *)scratch, nchunks);

@@ -176,3 +176,18 @@ def test_string_pointer_row_without_a_heap_is_an_error():
     so = db.plan_string(0, 0, data_capacity=64)
     db.run_string(so)
     assert db.string_error(so) & 4  # kErrHeapRange
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_string_pointer_outside_the_registered_heap_is_an_error(mode):
+    # a string_t whose pointer leaves the registered heap must raise kErrHeapRange (and contribute no bytes),
+    # in the Arrow kernels and in the reference-blob kernel
+    dev = _device_mod()
+    strings = [b"short", b"this one is longer than twelve bytes", b"x", b"another string beyond the inline limit"] * 200
+    counts = ch.chunk_counts(len(strings))
+    col = ch.string_column("s", strings, counts)
+    col.heap = col.heap[: col.heap.shape[0] // 2].copy()  # only the first half of the heap is registered
+    db = dev.DeviceBatch(ch.ChunkBatch(counts, [col]))
+    so = db.plan_string(0, mode, data_capacity=len(strings) * 64)
+    db.run_string(so)
+    assert db.string_error(so) & 4  # kErrHeapRange
