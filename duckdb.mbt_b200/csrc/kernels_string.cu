@@ -480,43 +480,63 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
 // ------------------------------------------------------------------ TMA-staged pack kernel
 // string_pack_kernel<LARGE, R>: the Arrow utf8 path for columns of short strings (the common case:
 // names, flags, comments).  The run-gather above pays ~20 warp-instructions per row when runs are
-// short (every 16-byte output vector then straddles a run boundary) and is issue bound; this
-// kernel moves the byte work onto the copy engines and keeps the SIMT part row-centric and small:
+// short and every tile stalls on its own dependent chain (metadata -> string_t -> scan ->
+// look-back -> gather).  This kernel is a persistent, warp-specialised pipeline: the byte movement
+// in and out of the SM is done by the copy engine (cp.async.bulk), every long-latency step of tile
+// t+1 is issued while tile t is being packed, and the SIMT part is row-centric and small.
 //
-//   1. tile = R*256 consecutive rows of one chunk; string_t loaded coalesced, transposed through
-//      (swizzled) shared memory so that every thread owns R CONSECUTIVE rows,
-//   2. lengths -> block scan; the tile's heap span [hmin, hmax) by redux.sync min/max,
-//   3. one elected thread fetches the whole span with ONE bulk copy (cp.async.bulk global ->
-//      shared, mbarrier complete_tx) while warp 0 resolves the tile's base by a 128-wide
-//      decoupled look-back (four status words in flight per lane: one L2 round trip per 128
-//      predecessors) and the other warps zero the output stage,
-//   4. offsets leave straight from registers (R consecutive values per thread: vector stores),
-//   5. every thread streams its rows' bytes (registers for inlined strings, the staged span for
-//      pointer strings) into the output stage with 32-bit funnel shifts: interior words are plain
-//      stores, the <= 2 words a thread shares with its neighbours are shared-memory atomicOr,
-//   6. the stage leaves with bulk copies shared -> global: one for the 16-byte aligned interior,
-//      and sm_100's byte-masked form (cp.async.bulk ... .cp_mask) for the ragged first / last
-//      vector, whose other bytes belong to the neighbouring tiles.
+//   CTA = 8 worker warps + producer warp P + look-back warp L; tiles (R*256 consecutive rows of a
+//   chunk) are claimed in order from a global ticket, so every predecessor of a claimed tile is
+//   owned by a running CTA (the look-back cannot starve).
 //
-// Tiles whose span or output does not fit the stages (scattered pointers, long strings) fall back
-// to the run-gather in place (R == 2 only; same tiles, same status words).
-constexpr uint32_t kPackTail = 256;   // bytes of bookkeeping in front of the stages
-constexpr int kLookWide = 4;          // status words in flight per lane in the look-back
+//   P  claims tile j+1 (ticket, chunk metadata), bulk-loads its string_t (and validity words) into
+//      the other S buffer; when the workers have scanned tile j it bulk-loads tile j's heap span
+//      [hmin, hmax) into H[j&1] (mbarrier complete_tx).
+//   W  front(j): own R consecutive rows from S -> lengths, block scan, span min/max (redux.sync).
+//      back(j-1): offsets straight from registers (vector stores), then every thread streams its
+//      rows' bytes (registers for inlined strings, the staged span for pointer strings) into the
+//      output stage O with 32-bit funnel shifts: interior words are plain stores, the <= 2 words
+//      a thread shares with its neighbours are shared-memory atomicOr into the zeroed stage.
+//   L  decoupled look-back of tile j-1 (256 status words in flight per round: one L2 round trip;
+//      the tile's aggregate was published by P a whole tile earlier, so the look-back rarely
+//      waits), publishes the inclusive prefix, zeroes O, and when the pack
+//      is done sends O to out_data with bulk stores: one for the 16-byte aligned interior and
+//      sm_100's byte-masked form (cp.async.bulk ... .cp_mask) for the ragged first / last vector,
+//      whose other bytes belong to the neighbouring tiles.
+//
+// A tile whose span or output does not fit the stages (scattered pointers, a long string) is copied
+// row by row, one warp per row and one byte per lane, straight from the heap to out_data.
+constexpr uint32_t kPackTail = 1024;  // bytes of bookkeeping in front of the stages
+constexpr int kLookWide = 8;          // status words in flight per lane in the look-back
+constexpr int kPackThreads = kThreads + 64;  // workers + P + L
+constexpr int kMetaRing = 4;
 
-struct PackTail {
-  unsigned long long mbar;
-  unsigned long long base;
+struct TileMeta {
+  long long tile;            // -1: no more tiles
+  long long out_row0;        // first output row of the tile
+  int32_t nrows;             // rows of the tile that exist (chunk count - r_begin, clamped)
+  int32_t has_mask;
+};
+
+struct PackPartials {
   uint32_t warp_sum[kThreads / 32];
   uint32_t warp_hmin[kThreads / 32];
   uint32_t warp_hmax[kThreads / 32];
-  uint32_t warp_run[kThreads / 32];
+};
+
+struct PackTail {
+  unsigned long long mbar_s[2];
+  unsigned long long mbar_h[2];
+  unsigned long long base[2];
+  TileMeta meta[kMetaRing];
+  PackPartials part[2];
+  unsigned long long vmask[2][kVec / 64];  // validity words of the tile in S[slot]
 };
 static_assert(sizeof(PackTail) <= kPackTail, "PackTail");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
@@ -541,23 +561,20 @@ __device__ __forceinline__ void bulk_store_masked(void *dst, uint32_t src_smem, 
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group.cp_mask [%0], [%1], %2, %3;"
                ::"l"(__cvta_generic_to_global(dst)), "r"(src_smem), "r"(bytes), "h"((unsigned short)mask) : "memory");
 }
-__device__ __forceinline__ void bulk_store_drain() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
+__device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_drain() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// named barriers: `sync` waits, `arrive` only signals; n = arriving + waiting threads
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+enum { kBarWorkers = 1, kBarScanP = 2, kBarBase = 3, kBarPacked = 4 };
 
-// low `n` bytes set, n in 0..4
-__device__ __forceinline__ uint32_t low_bytes(uint32_t n) { return n >= 4u ? 0xffffffffu : ((1u << (8u * n)) - 1u); }
-
-// slot of row i in the transposed string_t tile: a quarter-warp's 128-bit accesses stay conflict
-// free both for lane-consecutive rows (the coalesced store) and for rows R apart (the owner's load)
-__device__ __forceinline__ int swz(int i) { return i ^ ((i >> 3) & 7); }
+// low `n` bytes set, n in 0..3
+__device__ __forceinline__ uint32_t low_bytes3(uint32_t n) { return (1u << (8u * n)) - 1u; }
 
 // exclusive prefix of tile `tile` by decoupled look-back, executed by one warp; kLookWide status
 // words are in flight per lane, so one L2 round trip inspects 32*kLookWide predecessors
-__device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, int64_t tile, uint64_t agg, int lane) {
-  if (lane == 0) atomicExch(status + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | agg);
+__device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, int64_t tile, int lane) {
   uint64_t prefix = 0;
   if (tile > 0) {
     int64_t look = tile - 1;
@@ -584,329 +601,369 @@ __device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, in
           }
         }
       }
-      if (state == 2) continue;  // poll the window again (all its tiles are resident: they precede us)
+      if (state == 2) continue;  // poll the window again (its tiles are owned by running CTAs)
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
       prefix += v;
       if (state == 1) break;
       look -= 32 * kLookWide;
     }
-    if (lane == 0) atomicExch(status + tile, kFlagPrefix | ((prefix + agg) & kValueMask));
   }
   return prefix;
 }
 
+// per-tile state a worker thread carries from front() to back()
+template <int R>
+struct RowState {
+  uint32_t len[R];   // bytes the row contributes (0: NULL, empty, bad pointer, past the chunk)
+  uint32_t y[R], z[R], w[R];  // string_t words 1..3: inlined payload, or prefix + pointer
+  uint32_t my_off, total, hmin, hbytes;
+  bool staged;
+};
+
 template <bool LARGE, int R>
-__global__ void __launch_bounds__(kThreads, R == 2 ? 6 : 4)
+__global__ void __launch_bounds__(kPackThreads, 3)
 string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles,
                    uint32_t ostage_bytes, uint32_t hstage_bytes) {
   constexpr int kRows = kThreads * R;
   constexpr int kTilesPerChunk = kVec / kRows;
-  constexpr int MODE = LARGE ? DMB_STR_ARROW_LARGE : DMB_STR_ARROW_UTF8;
-  static_assert(R == 2 || R == 8, "R");
-  static_assert(R != 2 || kRows == kStrTileRows, "the fallback shares the run-gather's tiles");
+  constexpr uint32_t kSBytes = (uint32_t)kRows * 16u;
   extern __shared__ __align__(128) uint8_t dsm[];
   PackTail &pt = *reinterpret_cast<PackTail *>(dsm);
-  uint8_t *ostage = dsm + kPackTail;                 // output stage; first the transposed string_t tile
-  uint8_t *hstage = ostage + ostage_bytes;           // heap span of the tile
+  uint8_t *sbuf = dsm + kPackTail;                   // S[2]: string_t tiles
+  uint8_t *ostage = sbuf + 2u * kSBytes;             // O: output stage
+  uint8_t *hbuf = ostage + ostage_bytes;             // H[2]: heap spans (each hstage_bytes + 16)
+  const uint32_t hstride = hstage_bytes + 16u;
   unsigned long long *status = scratch + 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t tile = (int64_t)blockIdx.x;  // dispatch order = blockIdx order (see string_batch_kernel)
-  if (tile >= ntiles) return;
-  const uint32_t mbar = smem_u32(&pt.mbar);
-  if (tid == 0) mbar_init(mbar, 1);
 
-  const int64_t c = tile / kTilesPerChunk;
-  const int r_begin = (int)(tile % kTilesPerChunk) * kRows;
-  const int count = (int)__ldg(b.counts + c);
-  int nrows_tile = count - r_begin;
-  nrows_tile = nrows_tile < 0 ? 0 : (nrows_tile > kRows ? kRows : nrows_tile);
-  const dmb_vec_desc vd = job.vecs[c];
-  const uint4 *in = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(job.in) + vd.data_off) + r_begin;
-  const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
-
-  // 1. coalesced load, transpose: thread tid owns rows tid*R .. tid*R+R-1
-  uint4 ent[R];
-  {
-    uint4 *tr = reinterpret_cast<uint4 *>(ostage);
-    uint4 tmp[R];
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      const int i = k * kThreads + tid;
-      tmp[k] = i < nrows_tile ? ld_stream(in + i) : make_uint4(0, 0, 0, 0);
-    }
-    uint64_t vword = ~0ull;
-    if (mask) vword = __ldg(mask + ((r_begin + tid * R) >> 6)) >> ((r_begin + tid * R) & 63);
-#pragma unroll
-    for (int k = 0; k < R; ++k) tr[swz(k * kThreads + tid)] = tmp[k];
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      ent[k] = tr[swz(tid * R + k)];
-      if (!((vword >> k) & 1ull) || tid * R + k >= nrows_tile) ent[k].x = 0u;  // NULL / past the chunk: no bytes
-    }
-  }
-
-  // 2. lengths, heap span (16-byte units relative to the heap base), scan
-  int flags = 0;  // 2: bad heap pointer  4: oversized row
-  uint32_t len[R];
-  uint32_t hs[R];  // pointer rows: low 32 bits of the heap offset (rebased to the tile's span below)
-  uint32_t hmin = 0xffffffffu, hmax = 0u, tsum = 0u;
-#pragma unroll
-  for (int k = 0; k < R; ++k) {
-    uint32_t l = ent[k].x;
-    hs[k] = 0;
-    if (l > 12u) {
-      const uint64_t p = ((uint64_t)ent[k].w << 32) | (uint64_t)ent[k].z;
-      const uint64_t rel = p - job.heap_host_base;
-      if (l >= kMaxRowBytes) { flags |= 4; l = 0; }
-      else if (R == 8 || p < job.heap_host_base || rel + l > job.heap_len) { flags |= 2; l = 0; }  // R == 8: the column has no heap
-      else {
-        const uint32_t lo16 = (uint32_t)(rel >> 4), hi16 = (uint32_t)((rel + l + 15u) >> 4);
-        hmin = hmin < lo16 ? hmin : lo16;
-        hmax = hmax > hi16 ? hmax : hi16;
-        hs[k] = (uint32_t)rel;
-      }
-    }
-    len[k] = l;
-    tsum += l;
-  }
-  uint32_t incl = tsum;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += n;
-  }
-  if (R == 2) {
-    hmin = __reduce_min_sync(0xffffffffu, hmin);
-    hmax = __reduce_max_sync(0xffffffffu, hmax);
-    if (lane == 0) { pt.warp_hmin[warp] = hmin; pt.warp_hmax[warp] = hmax; }
-  }
-  if (lane == 31) pt.warp_sum[warp] = incl;
-  if (flags) atomicOr(scratch + 1, (unsigned long long)(((flags & 2) ? kErrHeapRange : 0) | ((flags & 4) ? kErrTileTooBig : 0)));
-  __syncthreads();
-  uint32_t warp_excl = 0, tile_total = 0;
-  hmin = 0xffffffffu;
-  hmax = 0u;
-#pragma unroll
-  for (int w = 0; w < kThreads / 32; ++w) {
-    const uint32_t s = pt.warp_sum[w];
-    if (w < warp) warp_excl += s;
-    tile_total += s;
-    if (R == 2) {
-      const uint32_t a = pt.warp_hmin[w], z = pt.warp_hmax[w];
-      hmin = hmin < a ? hmin : a;
-      hmax = hmax > z ? hmax : z;
-    }
-  }
-  const uint32_t my_off = warp_excl + incl - tsum;
-  const uint32_t hbytes = hmax > hmin ? (hmax - hmin) << 4 : 0u;
-  // block-uniform: does the tile fit the stages?  (R == 8: always; rows are <= 12 bytes)
-  const bool staged = R == 8 || (hbytes <= hstage_bytes && tile_total + 48u <= ostage_bytes &&
-                                 (hbytes == 0u || (reinterpret_cast<uintptr_t>(job.heap_dev) & 15u) == 0u));
-
-  // 3. span fetch || look-back || stage zeroing
-  uint32_t start_row[R == 2 ? R : 1];
-  if (staged) {
-    if (tid == 0 && hbytes) {
-      mbar_expect_tx(mbar, hbytes);
-      bulk_load(smem_u32(hstage), job.heap_dev + ((uint64_t)hmin << 4), hbytes, mbar);
-    }
-    // words shared between threads are ORed in: the stage starts zeroed.  Warp 0 is busy with the look-back.
-    uint4 *z = reinterpret_cast<uint4 *>(ostage);
-    const uint32_t nz = (tile_total + 47u) >> 4;
-    for (uint32_t i = tid; i < nz; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
-  } else if (R == 2) {
-    // fallback: fill the run-gather's tile (the transposed tile is dead: barrier above)
-    StrSmem &sm = *reinterpret_cast<StrSmem *>(dsm + kPackTail);
-    if (tid < 17) {
-      const uint32_t d = (uint32_t)tid;
-      auto m = [&](uint32_t w) { return d >= 4u * w + 4u ? 0xffffffffu : (d <= 4u * w ? 0u : ((1u << (8u * (d - 4u * w))) - 1u)); };
-      sm.low_mask[tid] = make_uint4(m(0), m(1), m(2), m(3));
-    }
-    uint64_t srcp[R];
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      const int i = tid * R + k;
-      sm.str[i] = ent[k];
-      const uint64_t p = ((uint64_t)ent[k].w << 32) | (uint64_t)ent[k].z;
-      srcp[k] = len[k] > 12u ? reinterpret_cast<uint64_t>(job.heap_dev + (p - job.heap_host_base))
-                             : reinterpret_cast<uint64_t>(reinterpret_cast<const uint8_t *>(&sm.str[i]) + 4);
-    }
-    uint32_t pl = __shfl_up_sync(0xffffffffu, len[R - 1], 1);
-    uint64_t ps = __shfl_up_sync(0xffffffffu, srcp[R - 1], 1);
-    if (lane == 0) pl = 0u;
-    uint32_t rmax = 0;
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      const bool follows = pl != 0u && srcp[k] == ps + pl;
-      start_row[k] = (len[k] != 0u && !follows) ? (uint32_t)(tid * R + k) + 1u : 0u;
-      if (len[k] != 0u) { pl = len[k]; ps = srcp[k]; } else { pl = 0u; }
-      rmax = rmax > start_row[k] ? rmax : start_row[k];
-    }
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t m = __shfl_up_sync(0xffffffffu, rmax, d);
-      if (lane >= d) rmax = rmax > m ? rmax : m;
-    }
-    if (lane == 31) pt.warp_run[warp] = rmax;
-    uint32_t run = __shfl_up_sync(0xffffffffu, rmax, 1);
-    if (lane == 0) run = 0u;
-    uint32_t o = my_off;
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      const int i = tid * R + k;
-      sm.off[i] = o;
-      sm.src[i] = srcp[k] - o;
-      o += len[k];
-      run = run > start_row[k] ? run : start_row[k];
-      start_row[k] = run;  // run id within the warp; the earlier warps' maximum is merged after the barrier
-    }
-    if (tid == kThreads - 1) sm.off[kRows] = o;
-  }
-  if (warp == 0) {
-    const uint64_t prefix = lookback_wide(status, tile, (uint64_t)tile_total, lane);
-    if (lane == 0) pt.base = prefix;
+  if (tid == 0) {
+    mbar_init(smem_u32(&pt.mbar_s[0]), 1);
+    mbar_init(smem_u32(&pt.mbar_s[1]), 1);
+    mbar_init(smem_u32(&pt.mbar_h[0]), 1);
+    mbar_init(smem_u32(&pt.mbar_h[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const uint64_t base = pt.base;
 
-  // 4. offsets: R consecutive values per thread
-  {
-    const int64_t out_row0 = __ldg(b.row_off + c) + r_begin;
-    if (!LARGE && base + tile_total > 0x7fffffffull && tid == 0) atomicOr(scratch + 1, (unsigned long long)kErrOffsetOverflow);
-    const int i0 = tid * R;
-    if (LARGE) {
-      long long *oo = reinterpret_cast<long long *>(job.out_offsets) + out_row0 + i0;
-      uint64_t o = base + my_off;
-      if (i0 + R <= nrows_tile && (reinterpret_cast<uintptr_t>(oo) & 15u) == 0u) {
-#pragma unroll
-        for (int k = 0; k < R; k += 2) {
-          const uint64_t o1 = o + len[k];
-          __stcs(reinterpret_cast<longlong2 *>(oo + k), make_longlong2((long long)o, (long long)o1));
-          o = o1 + len[k + 1];
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-          if (i0 + k < nrows_tile) __stcs(oo + k, (long long)o);
-          o += len[k];
-        }
-      }
-      if (tile == ntiles - 1 && tid == 0) reinterpret_cast<long long *>(job.out_offsets)[b.nrows] = (long long)(base + tile_total);
-    } else {
-      int32_t *oo = reinterpret_cast<int32_t *>(job.out_offsets) + out_row0 + i0;
-      uint32_t o = (uint32_t)base + my_off;
-      constexpr int kV = R == 2 ? 2 : 4;  // values per vector store
-      if (i0 + R <= nrows_tile && (reinterpret_cast<uintptr_t>(oo) & (4u * kV - 1u)) == 0u) {
-        if (R == 2) {
-          __stcs(reinterpret_cast<int2 *>(oo), make_int2((int)o, (int)(o + len[0])));
-        } else {
-#pragma unroll
-          for (int k = 0; k < R; k += 4) {
-            const uint32_t o1 = o + len[k], o2 = o1 + len[k + 1], o3 = o2 + len[k + 2];
-            __stcs(reinterpret_cast<int4 *>(oo + k), make_int4((int)o, (int)o1, (int)o2, (int)o3));
-            o = o3 + len[k + 3];
-          }
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-          if (i0 + k < nrows_tile) __stcs(oo + k, (int32_t)o);
-          o += len[k];
-        }
-      }
-      if (tile == ntiles - 1 && tid == 0) reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)(base + tile_total);
+  // claim the next tile and start the bulk load of its string_t (+ validity words) into S[slot]
+  auto claim = [&](int j) {  // one lane of P
+    TileMeta &m = pt.meta[j & (kMetaRing - 1)];
+    const long long t = (long long)atomicAdd(scratch, 1ull);
+    const int slot = j & 1;
+    const uint32_t mb = smem_u32(&pt.mbar_s[slot]);
+    if (t >= ntiles) {  // no tile: complete the phase all the same, the workers learn it from meta
+      m.tile = -1;
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
+      return;
     }
-    if (tile == ntiles - 1 && tid == 0 && job.total_bytes) *job.total_bytes = base + tile_total;
-  }
-  if (tile_total == 0) return;
-  const uint32_t mis = (uint32_t)(base & 15ull);
-  uint8_t *gbase = job.out_data + (base - mis);
-
-  if (R == 2 && !staged) {
-    StrSmem &sm = *reinterpret_cast<StrSmem *>(dsm + kPackTail);
-    uint32_t run_excl = 0;
+    const int64_t c = t / kTilesPerChunk;
+    const int r_begin = (int)(t % kTilesPerChunk) * kRows;
+    const int count = (int)__ldg(b.counts + c);
+    const dmb_vec_desc vd = job.vecs[c];
+    int nrows_tile = count - r_begin;
+    nrows_tile = nrows_tile < 0 ? 0 : (nrows_tile > kRows ? kRows : nrows_tile);
+    m.out_row0 = __ldg(b.row_off + c) + r_begin;
+    m.nrows = nrows_tile;
+    m.has_mask = vd.val_off >= 0;
+    m.tile = t;
+    // a DuckDB vector always has STANDARD_VECTOR_SIZE entries of storage: the whole tile is readable
+    mbar_expect_tx(mb, kSBytes + (vd.val_off >= 0 ? (uint32_t)kRows / 8u : 0u));
+    bulk_load(smem_u32(sbuf + (uint32_t)slot * kSBytes),
+              reinterpret_cast<const uint8_t *>(job.in) + vd.data_off + (uint64_t)r_begin * 16u, kSBytes, mb);
+    if (vd.val_off >= 0) bulk_load(smem_u32(&pt.vmask[slot][0]), job.in_validity + vd.val_off + (r_begin >> 6), (uint32_t)kRows / 8u, mb);
+  };
+  // block totals of the tile scanned into partials[slot]
+  auto totals = [&](int slot, int upto_warp, uint32_t &warp_excl, uint32_t &total, uint32_t &hmin, uint32_t &hmax) {
+    const PackPartials &pp = pt.part[slot];
+    warp_excl = 0; total = 0; hmin = 0xffffffffu; hmax = 0u;
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) {
-      const uint32_t m = pt.warp_run[w];
-      if (w < warp) run_excl = run_excl > m ? run_excl : m;
+      const uint32_t s = pp.warp_sum[w];
+      if (w < upto_warp) warp_excl += s;
+      total += s;
+      if (R == 2) {
+        const uint32_t a = pp.warp_hmin[w], z = pp.warp_hmax[w];
+        hmin = hmin < a ? hmin : a;
+        hmax = hmax > z ? hmax : z;
+      }
     }
-#pragma unroll
-    for (int k = 0; k < (R == 2 ? R : 1); ++k) sm.run[tid * R + k] = (uint16_t)(start_row[k] > run_excl ? start_row[k] : run_excl);
-    __syncthreads();
-    uint32_t l2[kStrPerThread];
-#pragma unroll
-    for (int k = 0; k < kStrPerThread; ++k) l2[k] = len[k];
-    gather_runs<MODE>(sm, tid, lane, warp, l2, my_off, tile_total, mis, gbase, (mis + tile_total + 15u) >> 4);
+  };
+  auto fits = [&](uint32_t total, uint32_t hbytes) {
+    return R != 2 || (hbytes <= hstage_bytes && total + 48u <= ostage_bytes &&
+                      (hbytes == 0u || (reinterpret_cast<uintptr_t>(job.heap_dev) & 15u) == 0u));
+  };
+
+  if (warp == kThreads / 32) {
+    // ------------------------------------------------------------ P: tickets, bulk loads
+    if (lane == 0) claim(0);
+    for (int j = 0;; ++j) {
+      bar_sync(kBarScanP, kThreads + 32);  // workers have scanned tile j (and are done with S[(j+1)&1], H[j&1])
+      const long long tile_j = pt.meta[j & (kMetaRing - 1)].tile;
+      if (tile_j < 0) break;
+      if (lane == 0) {
+        uint32_t we, total, hmin, hmax;
+        totals(j & 1, 0, we, total, hmin, hmax);
+        // the aggregate is published here, by the warp that never waits on other tiles
+        atomicExch(status + tile_j, (tile_j == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)total);
+        const uint32_t hbytes = hmax > hmin ? (hmax - hmin) << 4 : 0u;
+        if (R == 2 && hbytes && fits(total, hbytes)) {
+          const uint32_t mb = smem_u32(&pt.mbar_h[j & 1]);
+          mbar_expect_tx(mb, hbytes);
+          bulk_load(smem_u32(hbuf + (uint32_t)(j & 1) * hstride), job.heap_dev + ((uint64_t)hmin << 4), hbytes, mb);
+        }
+        claim(j + 1);
+      }
+      __syncwarp();
+    }
     return;
   }
 
-  // 5. pack: this thread's rows as one byte stream starting at stage byte mis + my_off
-  if (hbytes) mbar_wait(mbar, 0);
-  {
-    uint32_t *ow = reinterpret_cast<uint32_t *>(ostage);
-    const uint32_t *hw = reinterpret_cast<const uint32_t *>(hstage);
-    const uint32_t hbase = hmin << 4;  // low 32 bits of the span's heap offset
-    const uint32_t pos = mis + my_off;
-    uint32_t wp = pos >> 2, fill = pos & 3u, cur = 0u;
-    const uint32_t shared_wp = fill ? wp : 0xffffffffu;  // a first word that earlier threads also write
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      const uint32_t l = len[k];
-      if (l == 0u) continue;
-      const uint32_t n = fill + l, nw = n >> 2;
-      if (l <= 12u) {
-        // inlined: payload in registers, bytes past the length cleared
-        const uint32_t p0 = ent[k].y & low_bytes(l);
-        const uint32_t p1 = l > 4u ? ent[k].z & low_bytes(l - 4u) : 0u;
-        const uint32_t p2 = l > 8u ? ent[k].w & low_bytes(l - 8u) : 0u;
-        const uint32_t s = 8u * fill;
-        const uint32_t x0 = cur | (p0 << s);
-        const uint32_t x1 = __funnelshift_l(p0, p1, s);
-        const uint32_t x2 = __funnelshift_l(p1, p2, s);
-        const uint32_t x3 = __funnelshift_l(p2, 0u, s);
-        if (nw >= 1u) {
-          if (wp == shared_wp) atomicOr(ow + wp, x0); else ow[wp] = x0;
+  if (warp == kThreads / 32 + 1) {
+    // ------------------------------------------------------------ L: look-back, stage zeroing, bulk stores
+    for (int j = 0;; ++j) {
+      const long long tile_cur = j > 0 ? pt.meta[(j - 1) & (kMetaRing - 1)].tile : -1;
+      if (j > 0 && tile_cur < 0) break;
+      uint64_t base = 0;
+      uint32_t total_cur = 0;
+      bool staged_cur = false;
+      if (tile_cur >= 0) {
+        uint32_t we, hmin, hmax;
+        totals((j - 1) & 1, 0, we, total_cur, hmin, hmax);
+        staged_cur = fits(total_cur, hmax > hmin ? (hmax - hmin) << 4 : 0u);
+        base = lookback_wide(status, tile_cur, lane);
+        if (lane == 0) {
+          if (tile_cur > 0) atomicExch(status + tile_cur, kFlagPrefix | ((base + total_cur) & kValueMask));
+          pt.base[(j - 1) & 1] = base;
+          bulk_store_drain();  // the previous tile's bulk stores have read the stage
         }
-        if (nw >= 2u) ow[wp + 1] = x1;
-        if (nw >= 3u) ow[wp + 2] = x2;
-        cur = nw == 0u ? x0 : (nw == 1u ? x1 : (nw == 2u ? x2 : x3));
-      } else if (R == 2) {
-        // pointer: the staged span.  Output word m of the row holds source bytes qp-4+4m .. +3
-        const uint32_t qp = (hs[k] - hbase) + 4u - fill;
-        const uint32_t sq = 8u * (qp & 3u);
-        const uint32_t *s = hw + (qp >> 2);
-        uint32_t prev = s[-1], nxt = s[0];
-        const uint32_t x0 = (__funnelshift_r(prev, nxt, sq) & ~low_bytes(fill)) | cur;
-        if (wp == shared_wp) atomicOr(ow + wp, x0); else ow[wp] = x0;  // l > 12: the word always completes
-        prev = nxt;
-        uint32_t *o = ow + wp;
-#pragma unroll 2
-        for (uint32_t m = 1; m < nw; ++m) {
-          nxt = s[m];
-          o[m] = __funnelshift_r(prev, nxt, sq);
-          prev = nxt;
+        __syncwarp();
+        if (staged_cur && total_cur) {  // words shared between threads are ORed in: the stage starts zeroed
+          uint4 *z = reinterpret_cast<uint4 *>(ostage);
+          const uint32_t nz = (total_cur + 47u) >> 4;
+          for (uint32_t i = lane; i < nz; i += 32) z[i] = make_uint4(0, 0, 0, 0);
         }
-        cur = (n & 3u) ? (__funnelshift_r(prev, s[nw], sq) & low_bytes(n & 3u)) : 0u;
       }
-      wp += nw;
-      fill = n & 3u;
+      bar_arrive(kBarBase, kThreads + 32);  // base of tile j-1 published, stage zeroed
+      bar_sync(kBarPacked, kThreads + 32);  // tile j-1 packed
+      if (tile_cur >= 0 && lane == 0) {
+        if (!LARGE && base + total_cur > 0x7fffffffull) atomicOr(scratch + 1, (unsigned long long)kErrOffsetOverflow);
+        if (tile_cur == ntiles - 1) {
+          if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[b.nrows] = (long long)(base + total_cur);
+          else reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)(base + total_cur);
+          if (job.total_bytes) *job.total_bytes = base + total_cur;
+        }
+        if (total_cur && staged_cur) {
+          // stage byte q is global byte gbase + q
+          const uint32_t mis = (uint32_t)(base & 15ull);
+          uint8_t *gbase = job.out_data + (base - mis);
+          const uint32_t end = mis + total_cur;
+          const uint32_t q0 = mis ? 16u : 0u, q1 = end & ~15u;
+          const uint32_t so = smem_u32(ostage);
+          if (mis) bulk_store_masked(gbase, so, 16u, (0xffffu << mis) & (end < 16u ? (1u << end) - 1u : 0xffffu));
+          if (q1 > q0) bulk_store(gbase + q0, so + q0, q1 - q0);
+          if ((end & 15u) && q1 >= q0) bulk_store_masked(gbase + q1, so + q1, 16u, (1u << (end & 15u)) - 1u);
+          bulk_store_commit();
+        }
+      }
+      __syncwarp();
     }
-    if (fill) atomicOr(ow + wp, cur);  // last word: the next thread owns its other bytes
+    if (lane == 0) bulk_store_drain();  // the stage must outlive the reads
+    return;
   }
-  fence_proxy_async_smem();
-  __syncthreads();
 
-  // 6. stage -> out_data: stage byte q is global byte gbase + q
-  if (tid == 0) {
-    const uint32_t end = mis + tile_total;
-    const uint32_t q0 = mis ? 16u : 0u, q1 = end & ~15u;
-    const uint32_t so = smem_u32(ostage);
-    if (mis) bulk_store_masked(gbase, so, 16u, (0xffffu << mis) & (end < 16u ? (1u << end) - 1u : 0xffffu));
-    if (q1 > q0) bulk_store(gbase + q0, so + q0, q1 - q0);
-    if ((end & 15u) && q1 >= q0) bulk_store_masked(gbase + q1, so + q1, 16u, (1u << (end & 15u)) - 1u);
-    bulk_store_drain();  // the stage must outlive the reads
+  // -------------------------------------------------------------- W: scan (front) and pack (back)
+  RowState<R> cur, nxt;
+  bool cur_valid = false;
+  uint32_t phase_h0 = 0, phase_h1 = 0;
+  for (int j = 0;; ++j) {
+    if (j > 0 && !cur_valid) break;  // tickets are monotonic: no tile j-1, no tile j
+    // ---- front(tile j)
+    const int slot = j & 1;
+    mbar_wait(smem_u32(&pt.mbar_s[slot]), (uint32_t)(j >> 1) & 1u);  // P has claimed tile j (or found none)
+    const TileMeta mn = pt.meta[j & (kMetaRing - 1)];
+    const bool nxt_valid = mn.tile >= 0;
+    if (nxt_valid) {
+      const uint4 *s = reinterpret_cast<const uint4 *>(sbuf + (uint32_t)slot * kSBytes) + tid * R;
+      uint64_t vword = ~0ull;
+      if (mn.has_mask) vword = pt.vmask[slot][(tid * R) >> 6] >> ((tid * R) & 63);
+      int flags = 0;  // 2: bad heap pointer  4: oversized row
+      uint32_t hmin = 0xffffffffu, hmax = 0u, tsum = 0u;
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const uint4 e = s[k];
+        uint32_t l = (((vword >> k) & 1ull) && tid * R + k < mn.nrows) ? e.x : 0u;  // NULL / past the chunk: no bytes
+        if (l > 12u) {
+          const uint64_t p = ((uint64_t)e.w << 32) | (uint64_t)e.z;
+          const uint64_t rel = p - job.heap_host_base;
+          if (l >= kMaxRowBytes) { flags |= 4; l = 0; }
+          else if (R != 2 || p < job.heap_host_base || rel + l > job.heap_len) { flags |= 2; l = 0; }  // R != 2: the column has no heap
+          else {
+            const uint32_t lo16 = (uint32_t)(rel >> 4), hi16 = (uint32_t)((rel + l + 15u) >> 4);
+            hmin = hmin < lo16 ? hmin : lo16;
+            hmax = hmax > hi16 ? hmax : hi16;
+          }
+        }
+        nxt.len[k] = l; nxt.y[k] = e.y; nxt.z[k] = e.z; nxt.w[k] = e.w;
+        tsum += l;
+      }
+      if (flags) atomicOr(scratch + 1, (unsigned long long)(((flags & 2) ? kErrHeapRange : 0) | ((flags & 4) ? kErrTileTooBig : 0)));
+      uint32_t incl = tsum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+      }
+      PackPartials &pp = pt.part[slot];
+      if (R == 2) {
+        hmin = __reduce_min_sync(0xffffffffu, hmin);
+        hmax = __reduce_max_sync(0xffffffffu, hmax);
+        if (lane == 0) { pp.warp_hmin[warp] = hmin; pp.warp_hmax[warp] = hmax; }
+      }
+      if (lane == 31) pp.warp_sum[warp] = incl;
+      bar_sync(kBarWorkers, kThreads);
+      uint32_t warp_excl, hmx;
+      totals(slot, warp, warp_excl, nxt.total, nxt.hmin, hmx);
+      nxt.my_off = warp_excl + incl - tsum;
+      nxt.hbytes = hmx > nxt.hmin ? (hmx - nxt.hmin) << 4 : 0u;
+      nxt.staged = fits(nxt.total, nxt.hbytes);
+    }
+    bar_arrive(kBarScanP, kThreads + 32);
+
+    // ---- back(tile j-1)
+    bar_sync(kBarBase, kThreads + 32);
+    if (cur_valid) {
+      const TileMeta mc = pt.meta[(j - 1) & (kMetaRing - 1)];
+      const uint64_t base = pt.base[(j - 1) & 1];
+      // offsets: R consecutive values per thread
+      {
+        const int i0 = tid * R;
+        if (LARGE) {
+          long long *oo = reinterpret_cast<long long *>(job.out_offsets) + mc.out_row0 + i0;
+          uint64_t o = base + cur.my_off;
+          if (i0 + R <= mc.nrows && (reinterpret_cast<uintptr_t>(oo) & 15u) == 0u) {
+#pragma unroll
+            for (int k = 0; k < R; k += 2) {
+              const uint64_t o1 = o + cur.len[k];
+              __stcs(reinterpret_cast<longlong2 *>(oo + k), make_longlong2((long long)o, (long long)o1));
+              o = o1 + cur.len[k + 1];
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+              if (i0 + k < mc.nrows) __stcs(oo + k, (long long)o);
+              o += cur.len[k];
+            }
+          }
+        } else {
+          int32_t *oo = reinterpret_cast<int32_t *>(job.out_offsets) + mc.out_row0 + i0;
+          uint32_t o = (uint32_t)base + cur.my_off;
+          constexpr int kV = R == 2 ? 2 : 4;  // values per vector store
+          if (i0 + R <= mc.nrows && (reinterpret_cast<uintptr_t>(oo) & (4u * kV - 1u)) == 0u) {
+            if (R == 2) {
+              __stcs(reinterpret_cast<int2 *>(oo), make_int2((int)o, (int)(o + cur.len[0])));
+            } else {
+#pragma unroll
+              for (int k = 0; k < R; k += 4) {
+                const uint32_t o1 = o + cur.len[k], o2 = o1 + cur.len[k + 1], o3 = o2 + cur.len[k + 2];
+                __stcs(reinterpret_cast<int4 *>(oo + k), make_int4((int)o, (int)o1, (int)o2, (int)o3));
+                o = o3 + cur.len[k + 3];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+              if (i0 + k < mc.nrows) __stcs(oo + k, (int32_t)o);
+              o += cur.len[k];
+            }
+          }
+        }
+      }
+      const uint32_t mis = (uint32_t)(base & 15ull);
+      if (cur.total != 0u && cur.staged) {
+        // pack: this thread's rows as one byte stream starting at stage byte mis + my_off
+        const int hslot = (j - 1) & 1;
+        if (R == 2 && cur.hbytes) {
+          uint32_t &ph = hslot ? phase_h1 : phase_h0;
+          mbar_wait(smem_u32(&pt.mbar_h[hslot]), ph);
+          ph ^= 1u;
+        }
+        uint32_t *ow = reinterpret_cast<uint32_t *>(ostage);
+        const uint32_t *hw = reinterpret_cast<const uint32_t *>(hbuf + (uint32_t)hslot * hstride);
+        const uint32_t hbase = (cur.hmin << 4) + (uint32_t)job.heap_host_base;  // low 32 bits of the span's host address
+        const uint32_t pos = mis + cur.my_off;
+        uint32_t wp = pos >> 2, fill = pos & 3u, acc = 0u;
+        const uint32_t shared_wp = fill ? wp : 0xffffffffu;  // a first word that earlier threads also write
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const uint32_t l = cur.len[k];
+          if (l == 0u) continue;
+          const uint32_t n = fill + l, nw = n >> 2;
+          if (l <= 12u) {
+            // inlined: payload in registers; bytes past the length are dropped when the last word is kept
+            const uint32_t p0 = cur.y[k], p1 = cur.z[k], p2 = cur.w[k];
+            const uint32_t s = 8u * fill;
+            const uint32_t x0 = acc | (p0 << s);
+            const uint32_t x1 = __funnelshift_l(p0, p1, s);
+            const uint32_t x2 = __funnelshift_l(p1, p2, s);
+            const uint32_t x3 = __funnelshift_l(p2, 0u, s);
+            if (nw >= 1u) {
+              if (wp == shared_wp) atomicOr(ow + wp, x0); else ow[wp] = x0;
+            }
+            if (nw >= 2u) ow[wp + 1] = x1;
+            if (nw >= 3u) ow[wp + 2] = x2;
+            acc = (nw == 0u ? x0 : (nw == 1u ? x1 : (nw == 2u ? x2 : x3))) & low_bytes3(n & 3u);
+          } else if (R == 2) {
+            // pointer: the staged span.  Output word m of the row holds source bytes qp-4+4m .. +3
+            const uint32_t qp = (cur.z[k] - hbase) + 4u - fill;
+            const uint32_t sq = 8u * (qp & 3u);
+            const uint32_t *s = hw + (qp >> 2);
+            uint32_t prev = s[-1], nx = s[0];
+            const uint32_t x0 = (__funnelshift_r(prev, nx, sq) & ~low_bytes3(fill)) | acc;
+            if (wp == shared_wp) atomicOr(ow + wp, x0); else ow[wp] = x0;  // l > 12: the word always completes
+            prev = nx;
+            uint32_t *o = ow + wp;
+#pragma unroll 2
+            for (uint32_t m = 1; m < nw; ++m) {
+              nx = s[m];
+              o[m] = __funnelshift_r(prev, nx, sq);
+              prev = nx;
+            }
+            acc = (n & 3u) ? (__funnelshift_r(prev, s[nw], sq) & low_bytes3(n & 3u)) : 0u;
+          }
+          wp += nw;
+          fill = n & 3u;
+        }
+        if (fill) atomicOr(ow + wp, acc);  // last word: the next thread owns its other bytes
+        fence_proxy_async_smem();
+      } else if (R == 2 && cur.total != 0u) {
+        // not staged: one warp per row, one byte per lane, heap -> out_data
+        uint8_t *out = job.out_data + base;
+        uint32_t o0 = cur.my_off, o1 = cur.my_off + cur.len[0];
+#pragma unroll 1
+        for (int q = 0; q < 32 * R; ++q) {
+          const int owner = q / R, k = q % R;
+          const uint32_t l = __shfl_sync(0xffffffffu, k ? cur.len[R - 1] : cur.len[0], owner);
+          if (l == 0u) continue;
+          const uint32_t off = __shfl_sync(0xffffffffu, k ? o1 : o0, owner);
+          const uint32_t y = __shfl_sync(0xffffffffu, k ? cur.y[R - 1] : cur.y[0], owner);
+          const uint32_t z = __shfl_sync(0xffffffffu, k ? cur.z[R - 1] : cur.z[0], owner);
+          const uint32_t w = __shfl_sync(0xffffffffu, k ? cur.w[R - 1] : cur.w[0], owner);
+          if (l <= 12u) {
+            if ((uint32_t)lane < l) {
+              const uint32_t word = lane < 4 ? y : (lane < 8 ? z : w);
+              out[off + lane] = (uint8_t)(word >> (8 * (lane & 3)));
+            }
+          } else {
+            const uint8_t *src = job.heap_dev + ((((uint64_t)w << 32) | (uint64_t)z) - job.heap_host_base);
+            for (uint32_t i = lane; i < l; i += 32) out[off + i] = src[i];
+          }
+        }
+      }
+    }
+    bar_arrive(kBarPacked, kThreads + 32);
+    cur = nxt;
+    cur_valid = nxt_valid;
   }
 }
 
@@ -1129,32 +1186,34 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
   static const bool no_pack = getenv("DMB_STR_NO_PACK") != nullptr;
   if (!no_pack && (job->mode == DMB_STR_ARROW_UTF8 || job->mode == DMB_STR_ARROW_LARGE) && job->heap_len < (1ull << 35)) {
     const bool large = job->mode == DMB_STR_ARROW_LARGE;
-    auto launch_pack = [&](auto kernel, int64_t nt, uint32_t ob, uint32_t hb) -> int32_t {
-      const size_t smem = (size_t)kPackTail + ob + hb + 128;
-      static thread_local const void *configured[8] = {nullptr};
-      bool seen = false;
-      for (const void *q : configured) seen = seen || q == (const void *)kernel;
-      if (!seen) {
-        if (check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024), "string_pack_kernel smem attribute")) return -1;
-        for (const void *&q : configured) if (!q) { q = (const void *)kernel; break; }
-      }
-      kernel<<<(unsigned)nt, kThreads, smem, st>>>(*job, b, (unsigned long long *)scratch, nt, ob, hb);
+    // persistent grid: as many CTAs as are resident at once (tiles are claimed from a ticket)
+    auto launch_pack = [&](auto kernel, int rows_per_tile, uint32_t ob, uint32_t hb) -> int32_t {
+      const int64_t nt = (int64_t)(kVec / rows_per_tile) * nchunks;
+      const size_t smem = (size_t)kPackTail + 2u * (size_t)rows_per_tile * 16u + ob + 2u * ((size_t)hb + 16u) + 128u;
+      if (check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "string_pack_kernel smem attribute")) return -1;
+      int per_sm = 0;
+      if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPackThreads, smem), "string_pack_kernel occupancy")) return -1;
+      if (per_sm < 1) { set_error("string_pack_kernel does not fit an SM (%zu bytes of shared memory)", smem); return -1; }
+      static const int cap = getenv("DMB_STR_PACK_CTAS") ? atoi(getenv("DMB_STR_PACK_CTAS")) : 0;
+      if (cap > 0 && per_sm > cap) per_sm = cap;
+      int dev = 0, sms = kNumSMs;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      int64_t grid = (int64_t)per_sm * sms;
+      if (grid > nt) grid = nt;
+      kernel<<<(unsigned)grid, kPackThreads, smem, st>>>(*job, b, (unsigned long long *)scratch, nt, ob, hb);
       return check_cuda(cudaGetLastError(), "string_pack_kernel launch");
     };
-    if (job->heap_len == 0) {  // inlined strings only: whole-vector tiles, 8 rows per thread
-      const uint32_t ob = (uint32_t)kVec * 16u;
-      return large ? launch_pack(string_pack_kernel<true, 8>, nchunks, ob, 0u) : launch_pack(string_pack_kernel<false, 8>, nchunks, ob, 0u);
+    if (job->heap_len == 0) {  // inlined strings only: 4 rows per thread, 1024-row tiles
+      const uint32_t ob = ((1024u * 12u + 64u) + 127u) & ~127u;
+      return large ? launch_pack(string_pack_kernel<true, 4>, 1024, ob, 0u) : launch_pack(string_pack_kernel<false, 4>, 1024, ob, 0u);
     }
     const double heap_per_tile = (double)job->heap_len / (double)nrows * (double)kStrTileRows;
     if (heap_per_tile <= 40.0 * 1024.0) {
       static const double slack = getenv("DMB_STR_PACK_SLACK") ? atof(getenv("DMB_STR_PACK_SLACK")) : 1.15;
       uint32_t hb = ((uint32_t)(heap_per_tile * slack) + 1024u + 127u) & ~127u;
       if (hb < 2048u) hb = 2048u;
-      uint32_t ob = hb + 2048u;
-      if (ob < (uint32_t)kStrTileRows * 16u) ob = (uint32_t)kStrTileRows * 16u;
-      const uint32_t need = ((uint32_t)sizeof(StrSmem) + 127u) & ~127u;  // the in-place fallback's tile
-      if (ob + hb < need) ob = need - hb;
-      return large ? launch_pack(string_pack_kernel<true, 2>, ntiles, ob, hb) : launch_pack(string_pack_kernel<false, 2>, ntiles, ob, hb);
+      const uint32_t ob = hb + 2048u;  // inlined rows add at most 12 bytes each; a tile that exceeds the stage is copied row by row
+      return large ? launch_pack(string_pack_kernel<true, 2>, kStrTileRows, ob, hb) : launch_pack(string_pack_kernel<false, 2>, kStrTileRows, ob, hb);
     }
   }
   if (job->heap_len == 0 && !getenv("DMB_STR_NO_INLINE_KERNEL")) {  // no heap: inlined strings only, whole-vector tiles
