@@ -485,30 +485,40 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
 // in and out of the SM is done by the copy engine (cp.async.bulk), every long-latency step of tile
 // t+1 is issued while tile t is being packed, and the SIMT part is row-centric and small.
 //
-//   CTA = 8 worker warps + producer warp P + look-back warp L; tiles (R*256 consecutive rows of a
-//   chunk) are claimed in order from a global ticket, so every predecessor of a claimed tile is
-//   owned by a running CTA (the look-back cannot starve).
+//   CTA = 8 worker warps + three single-purpose warps; tiles (R*256 consecutive rows of a chunk) are
+//   claimed in order from a global ticket, so every predecessor of a claimed tile is owned by a
+//   running CTA (the look-back cannot starve).
 //
-//   P  claims tile j+1 (ticket, chunk metadata), bulk-loads its string_t (and validity words) into
-//      the other S buffer; when the workers have scanned tile j it bulk-loads tile j's heap span
-//      [hmin, hmax) into H[j&1] (mbarrier complete_tx).
-//   W  front(j): own R consecutive rows from S -> lengths, block scan, span min/max (redux.sync).
+//   P  claims tile j+1 (ticket, chunk metadata) and bulk-loads its string_t (and validity words)
+//      into the other S buffer as soon as the workers have left it.
+//   A  sums a tile's lengths the moment its string_t land and publishes the tile's aggregate (a
+//      short, uniform delay after the ticket: the look-backs behind it rarely wait), then
+//      bulk-loads the tile's heap span [hmin, hmax) into H[j&1] (mbarrier complete_tx).
+//   W  front(j): own R consecutive rows from S -> lengths, block scan.
 //      back(j-1): offsets straight from registers (vector stores), then every thread streams its
 //      rows' bytes (registers for inlined strings, the staged span for pointer strings) into the
 //      output stage O with 32-bit funnel shifts: interior words are plain stores, the <= 2 words
-//      a thread shares with its neighbours are shared-memory atomicOr into the zeroed stage.
-//   L  decoupled look-back of tile j-1 (256 status words in flight per round: one L2 round trip;
-//      the tile's aggregate was published by P a whole tile earlier, so the look-back rarely
-//      waits), publishes the inclusive prefix, zeroes O, and when the pack
+//      a thread shares with its neighbours are written byte by byte.
+//   L  decoupled look-back of tile j+1 while the workers scan it and pack tile j (256 status words
+//      in flight per round: one L2 round trip), publishes the inclusive prefix, and when a pack
 //      is done sends O to out_data with bulk stores: one for the 16-byte aligned interior and
 //      sm_100's byte-masked form (cp.async.bulk ... .cp_mask) for the ragged first / last vector,
 //      whose other bytes belong to the neighbouring tiles.
 //
 // A tile whose span or output does not fit the stages (scattered pointers, a long string) is copied
 // row by row, one warp per row and one byte per lane, straight from the heap to out_data.
-constexpr uint32_t kPackTail = 1024;  // bytes of bookkeeping in front of the stages
+#ifdef DMB_STR_TRACE
+#define DMB_PTRACE(j, ev) do { if (blockIdx.x < 32 && (j) < 64) g_str_trace[((blockIdx.x * 64 + (j)) << 4) + (ev)] = gtimer(); } while (0)
+#else
+#define DMB_PTRACE(j, ev) do { } while (0)
+#endif
+constexpr uint32_t kPackTail = 1280;  // bytes of bookkeeping in front of the stages
 constexpr int kLookWide = 8;          // status words in flight per lane in the look-back
-constexpr int kPackThreads = kThreads + 64;  // workers + P + L
+#ifndef DMB_LOOK_FIRST
+#define DMB_LOOK_FIRST 2
+#endif
+constexpr int kLookFirst = DMB_LOOK_FIRST;  // ... in its first round
+constexpr int kPackThreads = kThreads + 128;  // workers + P + L + A + T
 constexpr int kMetaRing = 4;
 
 struct TileMeta {
@@ -516,6 +526,11 @@ struct TileMeta {
   long long out_row0;        // first output row of the tile
   int32_t nrows;             // rows of the tile that exist (chunk count - r_begin, clamped)
   int32_t has_mask;
+  // written by P once the tile's string_t have landed and been summed
+  uint32_t total;            // bytes of the tile
+  uint32_t hmin;             // heap span start, 16-byte units from the heap base
+  uint32_t hbytes;           // heap span bytes (multiple of 16)
+  int32_t staged;            // the tile fits the stages
 };
 
 struct PackPartials {
@@ -527,10 +542,15 @@ struct PackPartials {
 struct PackTail {
   unsigned long long mbar_s[2];
   unsigned long long mbar_h[2];
-  unsigned long long base[2];
+  unsigned long long base[kMetaRing];
+  unsigned long long mbar_b[kMetaRing];  // L -> workers: base of tile k resolved
+  unsigned long long mbar_q[kMetaRing];  // workers -> L: tile k scanned (its look-back is due within an iteration)
+  unsigned long long mbar_f[kMetaRing];  // P -> L: tile k's aggregate is published (one phase per use)
+  unsigned long long mbar_w[2];  // workers -> P, A: iteration j finished (8 arrivals, alternating)
+  unsigned long long mbar_a[2];  // A -> P: the tile in S[slot] has been summed
   TileMeta meta[kMetaRing];
   PackPartials part[2];
-  unsigned long long vmask[2][kVec / 64];  // validity words of the tile in S[slot]
+  alignas(16) unsigned long long vmask[2][kVec / 64];  // validity words of the tile in S[slot] (bulk-copy destination)
 };
 static_assert(sizeof(PackTail) <= kPackTail, "PackTail");
 
@@ -541,13 +561,24 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// a protocol error must end as a launch failure, not as a hung GPU: waits give up after 4 s
+constexpr unsigned long long kWaitLimitNs = 4000000000ull;
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   uint32_t done;
-  do {
+  unsigned long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-  } while (!done);
+    if (done) return;
+    if ((spins & 255u) == 255u) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWaitLimitNs) __trap();
+    }
+  }
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); }
 __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t mbar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst_smem), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(mbar) : "memory");
@@ -567,58 +598,101 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // named barriers: `sync` waits, `arrive` only signals; n = arriving + waiting threads
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-enum { kBarWorkers = 1, kBarScanP = 2, kBarBase = 3, kBarPacked = 4 };
+enum { kBarWorkers = 1, kBarBase = 3, kBarPacked = 4 };
+
+// bytes [b0, b1) of `v` into the word at `w` (the other bytes belong to neighbouring threads)
+__device__ __forceinline__ void store_bytes(uint32_t *w, uint32_t v, uint32_t b0, uint32_t b1) {
+  uint8_t *p = reinterpret_cast<uint8_t *>(w);
+#pragma unroll
+  for (uint32_t k = 0; k < 4; ++k)
+    if (k >= b0 && k < b1) p[k] = (uint8_t)(v >> (8u * k));
+}
 
 // low `n` bytes set, n in 0..3
 __device__ __forceinline__ uint32_t low_bytes3(uint32_t n) { return (1u << (8u * n)) - 1u; }
 
 // exclusive prefix of tile `tile` by decoupled look-back, executed by one warp; kLookWide status
-// words are in flight per lane, so one L2 round trip inspects 32*kLookWide predecessors
-__device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, int64_t tile, int lane) {
+// words are in flight per lane, so one L2 round trip inspects 32*kLookWide predecessors; when a
+// needed word is not published yet only the unpublished ones are read again
+__device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, int64_t tile, int lane, unsigned *stats = nullptr) {
   uint64_t prefix = 0;
+  unsigned rounds = 0, retries = 0;
+  unsigned long long t0 = 0;
   if (tile > 0) {
     int64_t look = tile - 1;
+    int width = kLookFirst;  // the nearest predecessors usually hold a prefix: a narrow first round keeps the status lines cool
     while (true) {
       uint64_t st[kLookWide];
 #pragma unroll
-      for (int j = 0; j < kLookWide; ++j) {
-        const int64_t idx = look - (int64_t)(32 * j + lane);
-        st[j] = idx >= 0 ? ld_status(status + idx) : kFlagPrefix;  // before tile 0: prefix 0
-      }
-      uint64_t v = 0;
-      int state = 0;  // 0: keep looking  1: a prefix closed the sum  2: a needed word is not published yet
+      for (int j = 0; j < kLookWide; ++j) st[j] = 0;
+      uint64_t v;
+      int state;  // 0: keep looking  1: a prefix closed the sum  2: a needed word is not published yet
+      while (true) {
 #pragma unroll
-      for (int j = 0; j < kLookWide; ++j) {
-        if (state == 0) {
-          const uint32_t ready = __ballot_sync(0xffffffffu, (st[j] >> 62) != 0);
-          const uint32_t is_p = __ballot_sync(0xffffffffu, (st[j] >> 62) == 2);
-          const int first_p = is_p ? (__ffs(is_p) - 1) : 31;
-          const uint32_t need = first_p >= 31 ? 0xffffffffu : ((2u << first_p) - 1u);
-          if ((ready & need) != need) state = 2;
-          else {
-            if (lane <= first_p) v += st[j] & kValueMask;
-            if (is_p) state = 1;
+        for (int j = 0; j < kLookWide; ++j) {
+          const int64_t idx = look - (int64_t)(32 * j + lane);
+          if (j < width && (st[j] >> 62) == 0) st[j] = idx >= 0 ? ld_status(status + idx) : kFlagPrefix;  // before tile 0: prefix 0
+        }
+        v = 0;
+        state = 0;
+#pragma unroll
+        for (int j = 0; j < kLookWide; ++j) {
+          if (state == 0 && j < width) {
+            const uint32_t ready = __ballot_sync(0xffffffffu, (st[j] >> 62) != 0);
+            const uint32_t is_p = __ballot_sync(0xffffffffu, (st[j] >> 62) == 2);
+            const int first_p = is_p ? (__ffs(is_p) - 1) : 31;
+            const uint32_t need = first_p >= 31 ? 0xffffffffu : ((2u << first_p) - 1u);
+            if ((ready & need) != need) state = 2;
+            else {
+              if (lane <= first_p) v += st[j] & kValueMask;
+              if (is_p) state = 1;
+            }
           }
         }
+        if (state != 2) break;
+        ++retries;
+        __nanosleep(200);  // the unpublished tiles are owned by running CTAs
+        const unsigned long long now = global_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > kWaitLimitNs) __trap();
       }
-      if (state == 2) continue;  // poll the window again (its tiles are owned by running CTAs)
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
       prefix += v;
+      ++rounds;
       if (state == 1) break;
-      look -= 32 * kLookWide;
+      look -= 32 * width;
+      width = kLookWide;
     }
   }
+  if (stats) *stats = rounds * 1000u + retries;
   return prefix;
+}
+
+// bytes a row contributes: 0 for NULL / past the chunk / an unusable pointer (flagged); P and the
+// workers must agree on this, it defines the tile totals
+template <int R>
+__device__ __forceinline__ uint32_t row_bytes(const dmb_string_job &job, uint32_t x, uint32_t z, uint32_t w, bool live, int &flags,
+                                              uint32_t &lo16, uint32_t &hi16) {
+  uint32_t l = live ? x : 0u;
+  lo16 = 0xffffffffu;
+  hi16 = 0u;
+  if (l > 12u) {
+    const uint64_t p = ((uint64_t)w << 32) | (uint64_t)z;
+    const uint64_t rel = p - job.heap_host_base;
+    if (l >= kMaxRowBytes) { flags |= 4; l = 0; }
+    else if (R != 2 || p < job.heap_host_base || rel + l > job.heap_len) { flags |= 2; l = 0; }  // R != 2: the column has no heap
+    else { lo16 = (uint32_t)(rel >> 4); hi16 = (uint32_t)((rel + l + 15u) >> 4); }
+  }
+  return l;
 }
 
 // per-tile state a worker thread carries from front() to back()
 template <int R>
 struct RowState {
-  uint32_t len[R];   // bytes the row contributes (0: NULL, empty, bad pointer, past the chunk)
+  uint32_t len[R];            // row_bytes()
   uint32_t y[R], z[R], w[R];  // string_t words 1..3: inlined payload, or prefix + pointer
-  uint32_t my_off, total, hmin, hbytes;
-  bool staged;
+  uint32_t my_off;            // tile-local offset of the thread's first row
 };
 
 template <bool LARGE, int R>
@@ -628,6 +702,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
   constexpr int kRows = kThreads * R;
   constexpr int kTilesPerChunk = kVec / kRows;
   constexpr uint32_t kSBytes = (uint32_t)kRows * 16u;
+  constexpr int kWL = kThreads + 32;       // workers + T
   extern __shared__ __align__(128) uint8_t dsm[];
   PackTail &pt = *reinterpret_cast<PackTail *>(dsm);
   uint8_t *sbuf = dsm + kPackTail;                   // S[2]: string_t tiles
@@ -642,77 +717,94 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
     mbar_init(smem_u32(&pt.mbar_s[1]), 1);
     mbar_init(smem_u32(&pt.mbar_h[0]), 1);
     mbar_init(smem_u32(&pt.mbar_h[1]), 1);
+    for (int k = 0; k < kMetaRing; ++k) { mbar_init(smem_u32(&pt.mbar_f[k]), 1); mbar_init(smem_u32(&pt.mbar_b[k]), 1); mbar_init(smem_u32(&pt.mbar_q[k]), 1); }
+    mbar_init(smem_u32(&pt.mbar_w[0]), kThreads / 32);
+    mbar_init(smem_u32(&pt.mbar_w[1]), kThreads / 32);
+    mbar_init(smem_u32(&pt.mbar_a[0]), 1);
+    mbar_init(smem_u32(&pt.mbar_a[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // claim the next tile and start the bulk load of its string_t (+ validity words) into S[slot]
-  auto claim = [&](int j) {  // one lane of P
-    TileMeta &m = pt.meta[j & (kMetaRing - 1)];
-    const long long t = (long long)atomicAdd(scratch, 1ull);
-    const int slot = j & 1;
-    const uint32_t mb = smem_u32(&pt.mbar_s[slot]);
-    if (t >= ntiles) {  // no tile: complete the phase all the same, the workers learn it from meta
-      m.tile = -1;
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
-      return;
-    }
-    const int64_t c = t / kTilesPerChunk;
-    const int r_begin = (int)(t % kTilesPerChunk) * kRows;
-    const int count = (int)__ldg(b.counts + c);
-    const dmb_vec_desc vd = job.vecs[c];
-    int nrows_tile = count - r_begin;
-    nrows_tile = nrows_tile < 0 ? 0 : (nrows_tile > kRows ? kRows : nrows_tile);
-    m.out_row0 = __ldg(b.row_off + c) + r_begin;
-    m.nrows = nrows_tile;
-    m.has_mask = vd.val_off >= 0;
-    m.tile = t;
-    // a DuckDB vector always has STANDARD_VECTOR_SIZE entries of storage: the whole tile is readable
-    mbar_expect_tx(mb, kSBytes + (vd.val_off >= 0 ? (uint32_t)kRows / 8u : 0u));
-    bulk_load(smem_u32(sbuf + (uint32_t)slot * kSBytes),
-              reinterpret_cast<const uint8_t *>(job.in) + vd.data_off + (uint64_t)r_begin * 16u, kSBytes, mb);
-    if (vd.val_off >= 0) bulk_load(smem_u32(&pt.vmask[slot][0]), job.in_validity + vd.val_off + (r_begin >> 6), (uint32_t)kRows / 8u, mb);
-  };
-  // block totals of the tile scanned into partials[slot]
-  auto totals = [&](int slot, int upto_warp, uint32_t &warp_excl, uint32_t &total, uint32_t &hmin, uint32_t &hmax) {
-    const PackPartials &pp = pt.part[slot];
-    warp_excl = 0; total = 0; hmin = 0xffffffffu; hmax = 0u;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) {
-      const uint32_t s = pp.warp_sum[w];
-      if (w < upto_warp) warp_excl += s;
-      total += s;
-      if (R == 2) {
-        const uint32_t a = pp.warp_hmin[w], z = pp.warp_hmax[w];
-        hmin = hmin < a ? hmin : a;
-        hmax = hmax > z ? hmax : z;
+  if (warp == kThreads / 32) {
+    // ------------------------------------------------------------ P: tickets, string_t bulk loads
+    // claim tile k: ticket + chunk metadata, bulk load of its string_t (+ validity words) into S[k&1]
+    auto claim = [&](int k) -> long long {
+      TileMeta &m = pt.meta[k & (kMetaRing - 1)];
+      const int slot = k & 1;
+      const uint32_t mb = smem_u32(&pt.mbar_s[slot]);
+      DMB_PTRACE(k, 14);
+      long long tile = (long long)atomicAdd(scratch, 1ull);
+      if (tile >= ntiles) tile = -1;
+      m.tile = tile;
+      if (tile < 0) {  // no tile: complete the phase all the same, the others learn it from meta
+        mbar_arrive(mb);
+        return tile;
+      }
+      const int64_t c = tile / kTilesPerChunk;
+      const int r_begin = (int)(tile % kTilesPerChunk) * kRows;
+      const int count = (int)__ldg(b.counts + c);
+      const dmb_vec_desc vd = job.vecs[c];
+      int nrows_tile = count - r_begin;
+      nrows_tile = nrows_tile < 0 ? 0 : (nrows_tile > kRows ? kRows : nrows_tile);
+      m.out_row0 = __ldg(b.row_off + c) + r_begin;
+      m.nrows = nrows_tile;
+      m.has_mask = vd.val_off >= 0;
+      // a DuckDB vector always has STANDARD_VECTOR_SIZE entries of storage: the whole tile is readable
+      mbar_expect_tx(mb, kSBytes + (vd.val_off >= 0 ? (uint32_t)kRows / 8u : 0u));
+      bulk_load(smem_u32(sbuf + (uint32_t)slot * kSBytes),
+                reinterpret_cast<const uint8_t *>(job.in) + vd.data_off + (uint64_t)r_begin * 16u, kSBytes, mb);
+      if (vd.val_off >= 0) bulk_load(smem_u32(&pt.vmask[slot][0]), job.in_validity + vd.val_off + (r_begin >> 6), (uint32_t)kRows / 8u, mb);
+      DMB_PTRACE(k, 6);
+      return tile;
+    };
+    if (lane == 0) {
+      long long tile = claim(0);
+      for (int j = 0; tile >= 0; ++j) {
+        if (j >= 1) {  // S[(j+1)&1] held tile j-1: the workers have scanned it (iteration j-1 is over) and so has A
+          mbar_wait(smem_u32(&pt.mbar_w[(j - 1) & 1]), (uint32_t)((j - 1) >> 1) & 1u);
+          mbar_wait(smem_u32(&pt.mbar_a[(j - 1) & 1]), (uint32_t)((j - 1) >> 1) & 1u);
+        }
+        tile = claim(j + 1);
       }
     }
-  };
-  auto fits = [&](uint32_t total, uint32_t hbytes) {
-    return R != 2 || (hbytes <= hstage_bytes && total + 48u <= ostage_bytes &&
-                      (hbytes == 0u || (reinterpret_cast<uintptr_t>(job.heap_dev) & 15u) == 0u));
-  };
+    return;
+  }
 
-  if (warp == kThreads / 32) {
-    // ------------------------------------------------------------ P: tickets, bulk loads
-    if (lane == 0) claim(0);
-    for (int j = 0;; ++j) {
-      bar_sync(kBarScanP, kThreads + 32);  // workers have scanned tile j (and are done with S[(j+1)&1], H[j&1])
-      const long long tile_j = pt.meta[j & (kMetaRing - 1)].tile;
-      if (tile_j < 0) break;
+  if (warp == kThreads / 32 + 2) {
+    // ------------------------------------------------------------ A: tile totals, aggregates
+    // as soon as tile k's string_t have landed, sum its lengths and publish its aggregate, so that the
+    // delay between a ticket and its aggregate is short and the same for every CTA (the look-back of
+    // the tiles behind it then rarely has to wait)
+    for (int k = 0;; ++k) {
+      TileMeta &m = pt.meta[k & (kMetaRing - 1)];
+      const int slot = k & 1;
+      mbar_wait(smem_u32(&pt.mbar_s[slot]), (uint32_t)(k >> 1) & 1u);
+      const long long tile = m.tile;
+      if (tile < 0) {
+        if (lane == 0) mbar_arrive(smem_u32(&pt.mbar_f[k & (kMetaRing - 1)]));
+        break;
+      }
+      if (lane == 0) DMB_PTRACE(k, 7);
+      const int nrows = m.nrows;
+      const bool has_mask = m.has_mask != 0;
+      const uint4 *s = reinterpret_cast<const uint4 *>(sbuf + (uint32_t)slot * kSBytes);
+      uint32_t sum = 0;
+      int flags = 0;
+#pragma unroll 8
+      for (int i = lane; i < kRows; i += 32) {
+        const uint4 e = s[i];
+        const bool live = i < nrows && (!has_mask || ((pt.vmask[slot][i >> 6] >> (i & 63)) & 1ull));
+        uint32_t lo16, hi16;
+        sum += row_bytes<R>(job, e.x, e.z, e.w, live, flags, lo16, hi16);
+      }
+      sum = __reduce_add_sync(0xffffffffu, sum);
       if (lane == 0) {
-        uint32_t we, total, hmin, hmax;
-        totals(j & 1, 0, we, total, hmin, hmax);
-        // the aggregate is published here, by the warp that never waits on other tiles
-        atomicExch(status + tile_j, (tile_j == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)total);
-        const uint32_t hbytes = hmax > hmin ? (hmax - hmin) << 4 : 0u;
-        if (R == 2 && hbytes && fits(total, hbytes)) {
-          const uint32_t mb = smem_u32(&pt.mbar_h[j & 1]);
-          mbar_expect_tx(mb, hbytes);
-          bulk_load(smem_u32(hbuf + (uint32_t)(j & 1) * hstride), job.heap_dev + ((uint64_t)hmin << 4), hbytes, mb);
-        }
-        claim(j + 1);
+        m.total = sum;
+        atomicExch(status + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)sum);
+        DMB_PTRACE(k, 13);
+        mbar_arrive(smem_u32(&pt.mbar_f[k & (kMetaRing - 1)]));  // L may look at tile k
+        mbar_arrive(smem_u32(&pt.mbar_a[slot]));                 // P may reuse S[slot] once the workers are done with it
       }
       __syncwarp();
     }
@@ -720,55 +812,72 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
   }
 
   if (warp == kThreads / 32 + 1) {
-    // ------------------------------------------------------------ L: look-back, stage zeroing, bulk stores
-    for (int j = 0;; ++j) {
-      const long long tile_cur = j > 0 ? pt.meta[(j - 1) & (kMetaRing - 1)].tile : -1;
-      if (j > 0 && tile_cur < 0) break;
-      uint64_t base = 0;
-      uint32_t total_cur = 0;
-      bool staged_cur = false;
-      if (tile_cur >= 0) {
-        uint32_t we, hmin, hmax;
-        totals((j - 1) & 1, 0, we, total_cur, hmin, hmax);
-        staged_cur = fits(total_cur, hmax > hmin ? (hmax - hmin) << 4 : 0u);
-        base = lookback_wide(status, tile_cur, lane);
-        if (lane == 0) {
-          if (tile_cur > 0) atomicExch(status + tile_cur, kFlagPrefix | ((base + total_cur) & kValueMask));
-          pt.base[(j - 1) & 1] = base;
-          bulk_store_drain();  // the previous tile's bulk stores have read the stage
-        }
-        __syncwarp();
-        if (staged_cur && total_cur) {  // words shared between threads are ORed in: the stage starts zeroed
-          uint4 *z = reinterpret_cast<uint4 *>(ostage);
-          const uint32_t nz = (total_cur + 47u) >> 4;
-          for (uint32_t i = lane; i < nz; i += 32) z[i] = make_uint4(0, 0, 0, 0);
-        }
-      }
-      bar_arrive(kBarBase, kThreads + 32);  // base of tile j-1 published, stage zeroed
-      bar_sync(kBarPacked, kThreads + 32);  // tile j-1 packed
-      if (tile_cur >= 0 && lane == 0) {
-        if (!LARGE && base + total_cur > 0x7fffffffull) atomicOr(scratch + 1, (unsigned long long)kErrOffsetOverflow);
-        if (tile_cur == ntiles - 1) {
-          if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[b.nrows] = (long long)(base + total_cur);
-          else reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)(base + total_cur);
-          if (job.total_bytes) *job.total_bytes = base + total_cur;
-        }
-        if (total_cur && staged_cur) {
-          // stage byte q is global byte gbase + q
-          const uint32_t mis = (uint32_t)(base & 15ull);
-          uint8_t *gbase = job.out_data + (base - mis);
-          const uint32_t end = mis + total_cur;
-          const uint32_t q0 = mis ? 16u : 0u, q1 = end & ~15u;
-          const uint32_t so = smem_u32(ostage);
-          if (mis) bulk_store_masked(gbase, so, 16u, (0xffffu << mis) & (end < 16u ? (1u << end) - 1u : 0xffffu));
-          if (q1 > q0) bulk_store(gbase + q0, so + q0, q1 - q0);
-          if ((end & 15u) && q1 >= q0) bulk_store_masked(gbase + q1, so + q1, 16u, (1u << (end & 15u)) - 1u);
-          bulk_store_commit();
-        }
+    // ------------------------------------------------------------ L: look-back
+    for (int k = 0;; ++k) {
+      const TileMeta &m = pt.meta[k & (kMetaRing - 1)];
+      mbar_wait(smem_u32(&pt.mbar_f[k & (kMetaRing - 1)]), (uint32_t)(k / kMetaRing) & 1u);  // tile k's aggregate is out
+      const long long tile = m.tile;
+      if (tile < 0) break;
+      // a lazy look-back is a short one: by the time the workers have scanned tile k its predecessors'
+      // aggregates (often their prefixes) are out, and the result is not needed before tile k-1 is packed
+      mbar_wait(smem_u32(&pt.mbar_q[k & (kMetaRing - 1)]), (uint32_t)(k / kMetaRing) & 1u);
+      if (lane == 0) DMB_PTRACE(k, 8);
+#ifdef DMB_STR_TRACE
+      unsigned lb_stats = 0;
+      const uint64_t base = lookback_wide(status, tile, lane, &lb_stats);
+      if (lane == 0 && blockIdx.x < 32 && k < 64) g_str_trace[((blockIdx.x * 64 + k) << 4) + 9] = lb_stats;
+#else
+      const uint64_t base = lookback_wide(status, tile, lane);
+#endif
+      if (lane == 0) {
+        if (tile > 0) atomicExch(status + tile, kFlagPrefix | ((base + m.total) & kValueMask));
+        pt.base[k & (kMetaRing - 1)] = base;
+        DMB_PTRACE(k, 15);
+        mbar_arrive(smem_u32(&pt.mbar_b[k & (kMetaRing - 1)]));  // the workers may place tile k
       }
       __syncwarp();
     }
-    if (lane == 0) bulk_store_drain();  // the stage must outlive the reads
+    return;
+  }
+
+  if (warp == kThreads / 32 + 3) {
+    // ------------------------------------------------------------ T: bulk stores of the packed stage
+    bar_arrive(kBarBase, kWL);  // the stage is free
+    for (int j = 0;; ++j) {
+      bar_sync(kBarPacked, kWL);  // the workers have packed tile j-1 (and seen tile j's metadata)
+      if (lane == 0) {
+        DMB_PTRACE(j, 10);
+        if (j > 0) {
+          const TileMeta &mp = pt.meta[(j - 1) & (kMetaRing - 1)];
+          const uint64_t base = pt.base[(j - 1) & (kMetaRing - 1)];
+          const uint32_t total = mp.total;
+          if (!LARGE && base + total > 0x7fffffffull) atomicOr(scratch + 1, (unsigned long long)kErrOffsetOverflow);
+          if (mp.tile == ntiles - 1) {
+            if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[b.nrows] = (long long)(base + total);
+            else reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)(base + total);
+            if (job.total_bytes) *job.total_bytes = base + total;
+          }
+          if (total && mp.staged) {
+            // stage byte q is global byte gbase + q
+            const uint32_t mis = (uint32_t)(base & 15ull);
+            uint8_t *gbase = job.out_data + (base - mis);
+            const uint32_t end = mis + total;
+            const uint32_t q0 = mis ? 16u : 0u, q1 = end & ~15u;
+            const uint32_t so = smem_u32(ostage);
+            if (mis) bulk_store_masked(gbase, so, 16u, (0xffffu << mis) & (end < 16u ? (1u << end) - 1u : 0xffffu));
+            if (q1 > q0) bulk_store(gbase + q0, so + q0, q1 - q0);
+            if ((end & 15u) && q1 >= q0) bulk_store_masked(gbase + q1, so + q1, 16u, (1u << (end & 15u)) - 1u);
+            bulk_store_commit();
+            DMB_PTRACE(j, 11);
+            bulk_store_drain();  // the stage is free again once the copy engine has read it
+            DMB_PTRACE(j, 12);
+          }
+        }
+      }
+      __syncwarp();
+      if (pt.meta[j & (kMetaRing - 1)].tile < 0) break;
+      bar_arrive(kBarBase, kWL);  // the stage is free
+    }
     return;
   }
 
@@ -780,32 +889,26 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
     if (j > 0 && !cur_valid) break;  // tickets are monotonic: no tile j-1, no tile j
     // ---- front(tile j)
     const int slot = j & 1;
+    if (tid == 0) DMB_PTRACE(j, 0);
     mbar_wait(smem_u32(&pt.mbar_s[slot]), (uint32_t)(j >> 1) & 1u);  // P has claimed tile j (or found none)
-    const TileMeta mn = pt.meta[j & (kMetaRing - 1)];
-    const bool nxt_valid = mn.tile >= 0;
+    if (tid == 0) DMB_PTRACE(j, 1);
+    const bool nxt_valid = pt.meta[j & (kMetaRing - 1)].tile >= 0;
     if (nxt_valid) {
+      const int nrows = pt.meta[j & (kMetaRing - 1)].nrows;
       const uint4 *s = reinterpret_cast<const uint4 *>(sbuf + (uint32_t)slot * kSBytes) + tid * R;
       uint64_t vword = ~0ull;
-      if (mn.has_mask) vword = pt.vmask[slot][(tid * R) >> 6] >> ((tid * R) & 63);
+      if (pt.meta[j & (kMetaRing - 1)].has_mask) vword = pt.vmask[slot][(tid * R) >> 6] >> ((tid * R) & 63);
       int flags = 0;  // 2: bad heap pointer  4: oversized row
-      uint32_t hmin = 0xffffffffu, hmax = 0u, tsum = 0u;
+      uint32_t tsum = 0u, hmin = 0xffffffffu, hmax = 0u;
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         const uint4 e = s[k];
-        uint32_t l = (((vword >> k) & 1ull) && tid * R + k < mn.nrows) ? e.x : 0u;  // NULL / past the chunk: no bytes
-        if (l > 12u) {
-          const uint64_t p = ((uint64_t)e.w << 32) | (uint64_t)e.z;
-          const uint64_t rel = p - job.heap_host_base;
-          if (l >= kMaxRowBytes) { flags |= 4; l = 0; }
-          else if (R != 2 || p < job.heap_host_base || rel + l > job.heap_len) { flags |= 2; l = 0; }  // R != 2: the column has no heap
-          else {
-            const uint32_t lo16 = (uint32_t)(rel >> 4), hi16 = (uint32_t)((rel + l + 15u) >> 4);
-            hmin = hmin < lo16 ? hmin : lo16;
-            hmax = hmax > hi16 ? hmax : hi16;
-          }
-        }
+        uint32_t lo16, hi16;
+        const uint32_t l = row_bytes<R>(job, e.x, e.z, e.w, ((vword >> k) & 1ull) && tid * R + k < nrows, flags, lo16, hi16);
         nxt.len[k] = l; nxt.y[k] = e.y; nxt.z[k] = e.z; nxt.w[k] = e.w;
         tsum += l;
+        hmin = hmin < lo16 ? hmin : lo16;
+        hmax = hmax > hi16 ? hmax : hi16;
       }
       if (flags) atomicOr(scratch + 1, (unsigned long long)(((flags & 2) ? kErrHeapRange : 0) | ((flags & 4) ? kErrTileTooBig : 0)));
       uint32_t incl = tsum;
@@ -821,27 +924,58 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         if (lane == 0) { pp.warp_hmin[warp] = hmin; pp.warp_hmax[warp] = hmax; }
       }
       if (lane == 31) pp.warp_sum[warp] = incl;
-      bar_sync(kBarWorkers, kThreads);
-      uint32_t warp_excl, hmx;
-      totals(slot, warp, warp_excl, nxt.total, nxt.hmin, hmx);
+      bar_sync(kBarWorkers, kThreads);  // (every warp has also finished packing tile j-2: H[slot] is free)
+      uint32_t warp_excl = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) warp_excl += w < warp ? pp.warp_sum[w] : 0u;
       nxt.my_off = warp_excl + incl - tsum;
-      nxt.hbytes = hmx > nxt.hmin ? (hmx - nxt.hmin) << 4 : 0u;
-      nxt.staged = fits(nxt.total, nxt.hbytes);
+      if (tid == 0) {
+        // the tile's heap span [hmin, hmax) -> H[slot], one bulk copy
+        TileMeta &m = pt.meta[j & (kMetaRing - 1)];
+        uint32_t total = 0;
+        hmin = 0xffffffffu;
+        hmax = 0u;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) {
+          total += pp.warp_sum[w];
+          if (R == 2) {
+            hmin = hmin < pp.warp_hmin[w] ? hmin : pp.warp_hmin[w];
+            hmax = hmax > pp.warp_hmax[w] ? hmax : pp.warp_hmax[w];
+          }
+        }
+        const uint32_t hbytes = hmax > hmin ? (hmax - hmin) << 4 : 0u;
+        const bool staged = R != 2 || (hbytes <= hstage_bytes && total + 48u <= ostage_bytes &&
+                                       (hbytes == 0u || (reinterpret_cast<uintptr_t>(job.heap_dev) & 15u) == 0u));
+        m.hmin = hmin;
+        m.hbytes = hbytes;
+        m.staged = staged;
+        mbar_arrive(smem_u32(&pt.mbar_q[j & (kMetaRing - 1)]));  // L: tile j's look-back is due
+        if (R == 2 && staged && hbytes) {
+          const uint32_t mb = smem_u32(&pt.mbar_h[slot]);
+          mbar_expect_tx(mb, hbytes);
+          bulk_load(smem_u32(hbuf + (uint32_t)slot * hstride), job.heap_dev + ((uint64_t)hmin << 4), hbytes, mb);
+        }
+      }
     }
-    bar_arrive(kBarScanP, kThreads + 32);
+    if (tid == 0) DMB_PTRACE(j, 2);
 
     // ---- back(tile j-1)
-    bar_sync(kBarBase, kThreads + 32);
+    uint64_t base = 0;
     if (cur_valid) {
-      const TileMeta mc = pt.meta[(j - 1) & (kMetaRing - 1)];
-      const uint64_t base = pt.base[(j - 1) & 1];
+      mbar_wait(smem_u32(&pt.mbar_b[(j - 1) & (kMetaRing - 1)]), (uint32_t)((j - 1) / kMetaRing) & 1u);  // L has resolved tile j-1
+      base = pt.base[(j - 1) & (kMetaRing - 1)];
+    }
+    if (tid == 0) DMB_PTRACE(j, 3);
+    if (cur_valid) {
+      const TileMeta &mc = pt.meta[(j - 1) & (kMetaRing - 1)];
+      const int nrows = mc.nrows;
       // offsets: R consecutive values per thread
       {
         const int i0 = tid * R;
         if (LARGE) {
           long long *oo = reinterpret_cast<long long *>(job.out_offsets) + mc.out_row0 + i0;
           uint64_t o = base + cur.my_off;
-          if (i0 + R <= mc.nrows && (reinterpret_cast<uintptr_t>(oo) & 15u) == 0u) {
+          if (i0 + R <= nrows && (reinterpret_cast<uintptr_t>(oo) & 15u) == 0u) {
 #pragma unroll
             for (int k = 0; k < R; k += 2) {
               const uint64_t o1 = o + cur.len[k];
@@ -851,7 +985,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
           } else {
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-              if (i0 + k < mc.nrows) __stcs(oo + k, (long long)o);
+              if (i0 + k < nrows) __stcs(oo + k, (long long)o);
               o += cur.len[k];
             }
           }
@@ -859,7 +993,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
           int32_t *oo = reinterpret_cast<int32_t *>(job.out_offsets) + mc.out_row0 + i0;
           uint32_t o = (uint32_t)base + cur.my_off;
           constexpr int kV = R == 2 ? 2 : 4;  // values per vector store
-          if (i0 + R <= mc.nrows && (reinterpret_cast<uintptr_t>(oo) & (4u * kV - 1u)) == 0u) {
+          if (i0 + R <= nrows && (reinterpret_cast<uintptr_t>(oo) & (4u * kV - 1u)) == 0u) {
             if (R == 2) {
               __stcs(reinterpret_cast<int2 *>(oo), make_int2((int)o, (int)(o + cur.len[0])));
             } else {
@@ -873,26 +1007,33 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
           } else {
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-              if (i0 + k < mc.nrows) __stcs(oo + k, (int32_t)o);
+              if (i0 + k < nrows) __stcs(oo + k, (int32_t)o);
               o += cur.len[k];
             }
           }
         }
       }
+    }
+    bar_sync(kBarBase, kWL);  // the stage is free (T has sent tile j-2)
+    if (cur_valid) {
+      const TileMeta &mc = pt.meta[(j - 1) & (kMetaRing - 1)];
       const uint32_t mis = (uint32_t)(base & 15ull);
-      if (cur.total != 0u && cur.staged) {
+      const uint32_t total = mc.total;
+      if (total != 0u && mc.staged) {
         // pack: this thread's rows as one byte stream starting at stage byte mis + my_off
         const int hslot = (j - 1) & 1;
-        if (R == 2 && cur.hbytes) {
+        if (R == 2 && mc.hbytes) {
           uint32_t &ph = hslot ? phase_h1 : phase_h0;
           mbar_wait(smem_u32(&pt.mbar_h[hslot]), ph);
           ph ^= 1u;
         }
+        if (tid == 0) DMB_PTRACE(j, 4);
         uint32_t *ow = reinterpret_cast<uint32_t *>(ostage);
         const uint32_t *hw = reinterpret_cast<const uint32_t *>(hbuf + (uint32_t)hslot * hstride);
-        const uint32_t hbase = (cur.hmin << 4) + (uint32_t)job.heap_host_base;  // low 32 bits of the span's host address
+        const uint32_t hbase = (mc.hmin << 4) + (uint32_t)job.heap_host_base;  // low 32 bits of the span's host address
         const uint32_t pos = mis + cur.my_off;
         uint32_t wp = pos >> 2, fill = pos & 3u, acc = 0u;
+        const uint32_t head = fill;                          // bytes of the first word that belong to earlier threads
         const uint32_t shared_wp = fill ? wp : 0xffffffffu;  // a first word that earlier threads also write
 #pragma unroll
         for (int k = 0; k < R; ++k) {
@@ -908,7 +1049,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
             const uint32_t x2 = __funnelshift_l(p1, p2, s);
             const uint32_t x3 = __funnelshift_l(p2, 0u, s);
             if (nw >= 1u) {
-              if (wp == shared_wp) atomicOr(ow + wp, x0); else ow[wp] = x0;
+              if (wp == shared_wp) store_bytes(ow + wp, x0, head, 4u); else ow[wp] = x0;
             }
             if (nw >= 2u) ow[wp + 1] = x1;
             if (nw >= 3u) ow[wp + 2] = x2;
@@ -920,7 +1061,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
             const uint32_t *s = hw + (qp >> 2);
             uint32_t prev = s[-1], nx = s[0];
             const uint32_t x0 = (__funnelshift_r(prev, nx, sq) & ~low_bytes3(fill)) | acc;
-            if (wp == shared_wp) atomicOr(ow + wp, x0); else ow[wp] = x0;  // l > 12: the word always completes
+            if (wp == shared_wp) store_bytes(ow + wp, x0, head, 4u); else ow[wp] = x0;  // l > 12: the word always completes
             prev = nx;
             uint32_t *o = ow + wp;
 #pragma unroll 2
@@ -934,12 +1075,12 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
           wp += nw;
           fill = n & 3u;
         }
-        if (fill) atomicOr(ow + wp, acc);  // last word: the next thread owns its other bytes
+        if (fill) store_bytes(ow + wp, acc, wp == shared_wp ? head : 0u, fill);  // last word: the next thread owns its other bytes
         fence_proxy_async_smem();
-      } else if (R == 2 && cur.total != 0u) {
+      } else if (R == 2 && total != 0u) {
         // not staged: one warp per row, one byte per lane, heap -> out_data
         uint8_t *out = job.out_data + base;
-        uint32_t o0 = cur.my_off, o1 = cur.my_off + cur.len[0];
+        const uint32_t o0 = cur.my_off, o1 = cur.my_off + cur.len[0];
 #pragma unroll 1
         for (int q = 0; q < 32 * R; ++q) {
           const int owner = q / R, k = q % R;
@@ -961,7 +1102,10 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         }
       }
     }
-    bar_arrive(kBarPacked, kThreads + 32);
+    if (tid == 0) DMB_PTRACE(j, 5);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&pt.mbar_w[j & 1]));
+    bar_arrive(kBarPacked, kWL);
     cur = nxt;
     cur_valid = nxt_valid;
   }
