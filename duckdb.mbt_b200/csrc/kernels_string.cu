@@ -485,25 +485,27 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
 // in and out of the SM is done by the copy engine (cp.async.bulk), every long-latency step of tile
 // t+1 is issued while tile t is being packed, and the SIMT part is row-centric and small.
 //
-//   CTA = 8 worker warps + three single-purpose warps; tiles (R*256 consecutive rows of a chunk) are
+//   CTA = 8 (or 16) worker warps + four single-purpose warps; tiles (R*256 consecutive rows of a chunk) are
 //   claimed in order from a global ticket, so every predecessor of a claimed tile is owned by a
 //   running CTA (the look-back cannot starve).
 //
-//   P  claims tile j+1 (ticket, chunk metadata) and bulk-loads its string_t (and validity words)
-//      into the other S buffer as soon as the workers have left it.
-//   A  sums a tile's lengths the moment its string_t land and publishes the tile's aggregate (a
-//      short, uniform delay after the ticket: the look-backs behind it rarely wait), then
-//      bulk-loads the tile's heap span [hmin, hmax) into H[j&1] (mbarrier complete_tx).
-//   W  front(j): own R consecutive rows from S -> lengths, block scan.
+//   P  claims tile j+2 (ticket, chunk metadata) and bulk-loads its string_t (and validity words)
+//      into the S buffer the workers and A have just left; when the workers have packed a tile it
+//      sends the stage O to out_data with bulk stores: one for the 16-byte aligned interior and
+//      sm_100's byte-masked form (cp.async.bulk ... .cp_mask) for the ragged first / last vector,
+//      whose other bytes belong to the neighbouring tiles.
+//   A  (two warps, alternating tiles) sums a tile's lengths the moment its string_t land and
+//      publishes the tile's aggregate: a short, uniform delay after the ticket, so the look-backs
+//      behind it rarely wait.
+//   W  front(j): own R consecutive rows from S -> lengths, block scan, span min/max (redux.sync);
+//      one thread fetches the tile's heap span [hmin, hmax) into H[j&1] with ONE bulk copy.
 //      back(j-1): offsets straight from registers (vector stores), then every thread streams its
 //      rows' bytes (registers for inlined strings, the staged span for pointer strings) into the
 //      output stage O with 32-bit funnel shifts: interior words are plain stores, the <= 2 words
 //      a thread shares with its neighbours are written byte by byte.
-//   L  decoupled look-back of tile j+1 while the workers scan it and pack tile j (256 status words
-//      in flight per round: one L2 round trip), publishes the inclusive prefix, and when a pack
-//      is done sends O to out_data with bulk stores: one for the 16-byte aligned interior and
-//      sm_100's byte-masked form (cp.async.bulk ... .cp_mask) for the ragged first / last vector,
-//      whose other bytes belong to the neighbouring tiles.
+//   L  decoupled look-back of tile j, started lazily (when the workers have scanned it: by then
+//      its predecessors' aggregates, often their prefixes, are out) and due only when tile j-1
+//      has been packed; a narrow first round keeps the status lines cool.
 //
 // A tile whose span or output does not fit the stages (scattered pointers, a long string) is copied
 // row by row, one warp per row and one byte per lane, straight from the heap to out_data.
@@ -512,13 +514,12 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
 #else
 #define DMB_PTRACE(j, ev) do { } while (0)
 #endif
-constexpr uint32_t kPackTail = 1280;  // bytes of bookkeeping in front of the stages
+constexpr uint32_t kPackTail = 1792;  // bytes of bookkeeping in front of the stages
 constexpr int kLookWide = 8;          // status words in flight per lane in the look-back
 #ifndef DMB_LOOK_FIRST
 #define DMB_LOOK_FIRST 2
 #endif
 constexpr int kLookFirst = DMB_LOOK_FIRST;  // ... in its first round
-constexpr int kPackThreads = kThreads + 128;  // workers + P + L + A + T
 constexpr int kMetaRing = 4;
 
 struct TileMeta {
@@ -533,10 +534,13 @@ struct TileMeta {
   int32_t staged;            // the tile fits the stages
 };
 
+constexpr int kPackMaxWarps = 16;
 struct PackPartials {
-  uint32_t warp_sum[kThreads / 32];
-  uint32_t warp_hmin[kThreads / 32];
-  uint32_t warp_hmax[kThreads / 32];
+  uint32_t warp_sum[kPackMaxWarps];
+  uint32_t warp_hmin[kPackMaxWarps];
+  uint32_t warp_hmax[kPackMaxWarps];
+  uint32_t warp_cmin[kPackMaxWarps];  // min / max over the warp's pointer rows of (pointer - tile-local offset):
+  uint32_t warp_cmax[kPackMaxWarps];  // all equal <=> the tile's bytes are one contiguous piece of the heap
 };
 
 struct PackTail {
@@ -546,7 +550,6 @@ struct PackTail {
   unsigned long long mbar_b[kMetaRing];  // L -> workers: base of tile k resolved
   unsigned long long mbar_q[kMetaRing];  // workers -> L: tile k scanned (its look-back is due within an iteration)
   unsigned long long mbar_f[kMetaRing];  // P -> L: tile k's aggregate is published (one phase per use)
-  unsigned long long mbar_w[2];  // workers -> P, A: iteration j finished (8 arrivals, alternating)
   unsigned long long mbar_a[2];  // A -> P: the tile in S[slot] has been summed
   TileMeta meta[kMetaRing];
   PackPartials part[2];
@@ -565,13 +568,21 @@ __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t
 // a protocol error must end as a launch failure, not as a hung GPU: waits give up after 4 s
 constexpr unsigned long long kWaitLimitNs = 4000000000ull;
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  // try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs out:
+  // with the default (short) limit the retry loop alone took a third of the kernel's issue slots
   uint32_t done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(mbar), "r"(parity), "r"(20000u) : "memory");
+  if (done) return;
   unsigned long long t0 = 0;
-  for (uint32_t spins = 0;; ++spins) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+  for (uint32_t spins = 1;; ++spins) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(mbar), "r"(parity), "r"(20000u) : "memory");
     if (done) return;
-    if ((spins & 255u) == 255u) {
+#ifdef DMB_WAIT_SLEEP
+    __nanosleep(DMB_WAIT_SLEEP);
+#endif
+    if ((spins & 63u) == 0u) {
       const unsigned long long now = global_ns();
       if (t0 == 0) t0 = now;
       else if (now - t0 > kWaitLimitNs) __trap();
@@ -695,14 +706,15 @@ struct RowState {
   uint32_t my_off;            // tile-local offset of the thread's first row
 };
 
-template <bool LARGE, int R>
-__global__ void __launch_bounds__(kPackThreads, 3)
+template <bool LARGE, int R, int NW>
+__global__ void __launch_bounds__(NW * 32 + 128, NW == 8 ? 3 : 2)
 string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles,
                    uint32_t ostage_bytes, uint32_t hstage_bytes) {
-  constexpr int kRows = kThreads * R;
+  constexpr int kWT = NW * 32;             // worker threads
+  constexpr int kRows = kWT * R;
   constexpr int kTilesPerChunk = kVec / kRows;
   constexpr uint32_t kSBytes = (uint32_t)kRows * 16u;
-  constexpr int kWL = kThreads + 32;       // workers + T
+  constexpr int kWL = kWT + 32;            // workers + T
   extern __shared__ __align__(128) uint8_t dsm[];
   PackTail &pt = *reinterpret_cast<PackTail *>(dsm);
   uint8_t *sbuf = dsm + kPackTail;                   // S[2]: string_t tiles
@@ -718,16 +730,14 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
     mbar_init(smem_u32(&pt.mbar_h[0]), 1);
     mbar_init(smem_u32(&pt.mbar_h[1]), 1);
     for (int k = 0; k < kMetaRing; ++k) { mbar_init(smem_u32(&pt.mbar_f[k]), 1); mbar_init(smem_u32(&pt.mbar_b[k]), 1); mbar_init(smem_u32(&pt.mbar_q[k]), 1); }
-    mbar_init(smem_u32(&pt.mbar_w[0]), kThreads / 32);
-    mbar_init(smem_u32(&pt.mbar_w[1]), kThreads / 32);
     mbar_init(smem_u32(&pt.mbar_a[0]), 1);
     mbar_init(smem_u32(&pt.mbar_a[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  if (warp == kThreads / 32) {
-    // ------------------------------------------------------------ P: tickets, string_t bulk loads
+  if (warp == NW) {
+    // ------------------------------------------------------------ P: tickets, string_t bulk loads ...
     // claim tile k: ticket + chunk metadata, bulk load of its string_t (+ validity words) into S[k&1]
     auto claim = [&](int k) -> long long {
       TileMeta &m = pt.meta[k & (kMetaRing - 1)];
@@ -758,25 +768,65 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       DMB_PTRACE(k, 6);
       return tile;
     };
+    // ... and T: when the workers have packed a tile, send the stage to out_data with bulk stores and
+    // hand the stage back.  Both jobs are triggered by the end of a worker iteration.
     if (lane == 0) {
-      long long tile = claim(0);
-      for (int j = 0; tile >= 0; ++j) {
-        if (j >= 1) {  // S[(j+1)&1] held tile j-1: the workers have scanned it (iteration j-1 is over) and so has A
-          mbar_wait(smem_u32(&pt.mbar_w[(j - 1) & 1]), (uint32_t)((j - 1) >> 1) & 1u);
-          mbar_wait(smem_u32(&pt.mbar_a[(j - 1) & 1]), (uint32_t)((j - 1) >> 1) & 1u);
+      claim(0);
+      claim(1);  // claims run two tiles ahead, also past the end: each A warp must meet a tile that says so
+    }
+    bar_arrive(kBarBase, kWL);  // the stage is free
+    for (int j = 0;; ++j) {
+      bar_sync(kBarPacked, kWL);  // the workers have finished iteration j: tile j-1 packed, tile j scanned
+      bool more = false;
+      if (lane == 0) {
+        DMB_PTRACE(j, 10);
+        if (j > 0) {
+          const TileMeta &mp = pt.meta[(j - 1) & (kMetaRing - 1)];
+          const uint64_t base = pt.base[(j - 1) & (kMetaRing - 1)];
+          const uint32_t total = mp.total;
+          if (!LARGE && base + total > 0x7fffffffull) atomicOr(scratch + 1, (unsigned long long)kErrOffsetOverflow);
+          if (mp.tile == ntiles - 1) {
+            if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[b.nrows] = (long long)(base + total);
+            else reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)(base + total);
+            if (job.total_bytes) *job.total_bytes = base + total;
+          }
+          if (total && mp.staged) {
+            // stage byte q is global byte gbase + q
+            const uint32_t mis = (uint32_t)(base & 15ull);
+            uint8_t *gbase = job.out_data + (base - mis);
+            const uint32_t end = mis + total;
+            const uint32_t q0 = mis ? 16u : 0u, q1 = end & ~15u;
+            const uint32_t so = smem_u32(ostage);
+            if (mis) bulk_store_masked(gbase, so, 16u, (0xffffu << mis) & (end < 16u ? (1u << end) - 1u : 0xffffu));
+            if (q1 > q0) bulk_store(gbase + q0, so + q0, q1 - q0);
+            if ((end & 15u) && q1 >= q0) bulk_store_masked(gbase + q1, so + q1, 16u, (1u << (end & 15u)) - 1u);
+            bulk_store_commit();
+            DMB_PTRACE(j, 11);
+            bulk_store_drain();  // the stage is free again once the copy engine has read it
+            DMB_PTRACE(j, 12);
+          }
         }
-        tile = claim(j + 1);
+        more = pt.meta[j & (kMetaRing - 1)].tile >= 0;
       }
+      more = __shfl_sync(0xffffffffu, more, 0);
+      if (!more) break;
+      bar_arrive(kBarBase, kWL);  // the stage is free
+      if (lane == 0) {
+        // S[j&1] held tile j: the workers have scanned it (barrier above), and so has A
+        mbar_wait(smem_u32(&pt.mbar_a[j & 1]), (uint32_t)(j >> 1) & 1u);
+        claim(j + 2);
+      }
+      __syncwarp();
     }
     return;
   }
 
-  if (warp == kThreads / 32 + 2) {
-    // ------------------------------------------------------------ A: tile totals, aggregates
+  if (warp >= NW + 2) {
+    // ------------------------------------------------------------ A (two warps, alternating tiles): tile totals, aggregates
     // as soon as tile k's string_t have landed, sum its lengths and publish its aggregate, so that the
     // delay between a ticket and its aggregate is short and the same for every CTA (the look-back of
     // the tiles behind it then rarely has to wait)
-    for (int k = 0;; ++k) {
+    for (int k = warp - (NW + 2);; k += 2) {
       TileMeta &m = pt.meta[k & (kMetaRing - 1)];
       const int slot = k & 1;
       mbar_wait(smem_u32(&pt.mbar_s[slot]), (uint32_t)(k >> 1) & 1u);
@@ -811,7 +861,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
     return;
   }
 
-  if (warp == kThreads / 32 + 1) {
+  if (warp == NW + 1) {
     // ------------------------------------------------------------ L: look-back
     for (int k = 0;; ++k) {
       const TileMeta &m = pt.meta[k & (kMetaRing - 1)];
@@ -836,47 +886,6 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         mbar_arrive(smem_u32(&pt.mbar_b[k & (kMetaRing - 1)]));  // the workers may place tile k
       }
       __syncwarp();
-    }
-    return;
-  }
-
-  if (warp == kThreads / 32 + 3) {
-    // ------------------------------------------------------------ T: bulk stores of the packed stage
-    bar_arrive(kBarBase, kWL);  // the stage is free
-    for (int j = 0;; ++j) {
-      bar_sync(kBarPacked, kWL);  // the workers have packed tile j-1 (and seen tile j's metadata)
-      if (lane == 0) {
-        DMB_PTRACE(j, 10);
-        if (j > 0) {
-          const TileMeta &mp = pt.meta[(j - 1) & (kMetaRing - 1)];
-          const uint64_t base = pt.base[(j - 1) & (kMetaRing - 1)];
-          const uint32_t total = mp.total;
-          if (!LARGE && base + total > 0x7fffffffull) atomicOr(scratch + 1, (unsigned long long)kErrOffsetOverflow);
-          if (mp.tile == ntiles - 1) {
-            if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[b.nrows] = (long long)(base + total);
-            else reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)(base + total);
-            if (job.total_bytes) *job.total_bytes = base + total;
-          }
-          if (total && mp.staged) {
-            // stage byte q is global byte gbase + q
-            const uint32_t mis = (uint32_t)(base & 15ull);
-            uint8_t *gbase = job.out_data + (base - mis);
-            const uint32_t end = mis + total;
-            const uint32_t q0 = mis ? 16u : 0u, q1 = end & ~15u;
-            const uint32_t so = smem_u32(ostage);
-            if (mis) bulk_store_masked(gbase, so, 16u, (0xffffu << mis) & (end < 16u ? (1u << end) - 1u : 0xffffu));
-            if (q1 > q0) bulk_store(gbase + q0, so + q0, q1 - q0);
-            if ((end & 15u) && q1 >= q0) bulk_store_masked(gbase + q1, so + q1, 16u, (1u << (end & 15u)) - 1u);
-            bulk_store_commit();
-            DMB_PTRACE(j, 11);
-            bulk_store_drain();  // the stage is free again once the copy engine has read it
-            DMB_PTRACE(j, 12);
-          }
-        }
-      }
-      __syncwarp();
-      if (pt.meta[j & (kMetaRing - 1)].tile < 0) break;
-      bar_arrive(kBarBase, kWL);  // the stage is free
     }
     return;
   }
@@ -924,11 +933,28 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         if (lane == 0) { pp.warp_hmin[warp] = hmin; pp.warp_hmax[warp] = hmax; }
       }
       if (lane == 31) pp.warp_sum[warp] = incl;
-      bar_sync(kBarWorkers, kThreads);  // (every warp has also finished packing tile j-2: H[slot] is free)
+      bar_sync(kBarWorkers, kWT);  // (every warp has also finished packing tile j-2: H[slot] is free)
       uint32_t warp_excl = 0;
 #pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) warp_excl += w < warp ? pp.warp_sum[w] : 0u;
+      for (int w = 0; w < NW; ++w) warp_excl += w < warp ? pp.warp_sum[w] : 0u;
       nxt.my_off = warp_excl + incl - tsum;
+      if (R == 2) {
+        // is the tile one run?  (every non-empty row a pointer row whose bytes follow its predecessor's in the heap)
+        uint32_t cmin = 0xffffffffu, cmax = 0u, o = nxt.my_off;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const uint32_t l = nxt.len[k];
+          if (l != 0u) {
+            const uint32_t c = nxt.z[k] - o;
+            cmin = l > 12u ? (cmin < c ? cmin : c) : 0u;
+            cmax = l > 12u ? (cmax > c ? cmax : c) : 0xffffffffu;  // an inlined row: never one run
+          }
+          o += l;
+        }
+        cmin = __reduce_min_sync(0xffffffffu, cmin);
+        cmax = __reduce_max_sync(0xffffffffu, cmax);
+        if (lane == 0) { pp.warp_cmin[warp] = cmin; pp.warp_cmax[warp] = cmax; }  // read after the next barrier, in back()
+      }
       if (tid == 0) {
         // the tile's heap span [hmin, hmax) -> H[slot], one bulk copy
         TileMeta &m = pt.meta[j & (kMetaRing - 1)];
@@ -936,7 +962,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         hmin = 0xffffffffu;
         hmax = 0u;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) {
+        for (int w = 0; w < NW; ++w) {
           total += pp.warp_sum[w];
           if (R == 2) {
             hmin = hmin < pp.warp_hmin[w] ? hmin : pp.warp_hmin[w];
@@ -1031,6 +1057,31 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         uint32_t *ow = reinterpret_cast<uint32_t *>(ostage);
         const uint32_t *hw = reinterpret_cast<const uint32_t *>(hbuf + (uint32_t)hslot * hstride);
         const uint32_t hbase = (mc.hmin << 4) + (uint32_t)job.heap_host_base;  // low 32 bits of the span's host address
+        bool one_run = false;
+        uint32_t run_c = 0;
+        if (R == 2 && mc.hbytes) {
+          const PackPartials &pq = pt.part[hslot];
+          uint32_t cmin = 0xffffffffu, cmax = 0u;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) {
+            cmin = cmin < pq.warp_cmin[w] ? cmin : pq.warp_cmin[w];
+            cmax = cmax > pq.warp_cmax[w] ? cmax : pq.warp_cmax[w];
+          }
+          one_run = cmin == cmax;
+          run_c = cmin;
+        }
+        if (one_run) {
+          // the tile's output is one contiguous piece of the staged span, shifted: out word w = span bytes
+          // 4w + d .. 4w + d + 3.  Consecutive lanes, consecutive words: conflict free, no row logic;
+          // the bytes outside [mis, mis + total) of the first / last word are masked off by the bulk store
+          const uint32_t d = (run_c - hbase) + 64u - mis;  // > 0
+          const uint32_t sh = 8u * (d & 3u);
+          const uint32_t *s = hw + (d >> 2) - 16;
+          const uint32_t wend = (mis + total + 3u) >> 2;
+#pragma unroll 2
+          for (uint32_t w = (mis >> 2) + (uint32_t)tid; w < wend; w += (uint32_t)kWT) ow[w] = __funnelshift_r(s[w], s[w + 1], sh);
+          fence_proxy_async_smem();
+        } else {
         const uint32_t pos = mis + cur.my_off;
         uint32_t wp = pos >> 2, fill = pos & 3u, acc = 0u;
         const uint32_t head = fill;                          // bytes of the first word that belong to earlier threads
@@ -1077,6 +1128,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         }
         if (fill) store_bytes(ow + wp, acc, wp == shared_wp ? head : 0u, fill);  // last word: the next thread owns its other bytes
         fence_proxy_async_smem();
+        }
       } else if (R == 2 && total != 0u) {
         // not staged: one warp per row, one byte per lane, heap -> out_data
         uint8_t *out = job.out_data + base;
@@ -1103,8 +1155,6 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       }
     }
     if (tid == 0) DMB_PTRACE(j, 5);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&pt.mbar_w[j & 1]));
     bar_arrive(kBarPacked, kWL);
     cur = nxt;
     cur_valid = nxt_valid;
@@ -1331,12 +1381,12 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
   if (!no_pack && (job->mode == DMB_STR_ARROW_UTF8 || job->mode == DMB_STR_ARROW_LARGE) && job->heap_len < (1ull << 35)) {
     const bool large = job->mode == DMB_STR_ARROW_LARGE;
     // persistent grid: as many CTAs as are resident at once (tiles are claimed from a ticket)
-    auto launch_pack = [&](auto kernel, int rows_per_tile, uint32_t ob, uint32_t hb) -> int32_t {
+    auto launch_pack = [&](auto kernel, int rows_per_tile, int threads, uint32_t ob, uint32_t hb) -> int32_t {
       const int64_t nt = (int64_t)(kVec / rows_per_tile) * nchunks;
       const size_t smem = (size_t)kPackTail + 2u * (size_t)rows_per_tile * 16u + ob + 2u * ((size_t)hb + 16u) + 128u;
       if (check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "string_pack_kernel smem attribute")) return -1;
       int per_sm = 0;
-      if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPackThreads, smem), "string_pack_kernel occupancy")) return -1;
+      if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem), "string_pack_kernel occupancy")) return -1;
       if (per_sm < 1) { set_error("string_pack_kernel does not fit an SM (%zu bytes of shared memory)", smem); return -1; }
       static const int cap = getenv("DMB_STR_PACK_CTAS") ? atoi(getenv("DMB_STR_PACK_CTAS")) : 0;
       if (cap > 0 && per_sm > cap) per_sm = cap;
@@ -1344,20 +1394,29 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
       if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       int64_t grid = (int64_t)per_sm * sms;
       if (grid > nt) grid = nt;
-      kernel<<<(unsigned)grid, kPackThreads, smem, st>>>(*job, b, (unsigned long long *)scratch, nt, ob, hb);
+      kernel<<<(unsigned)grid, threads, smem, st>>>(*job, b, (unsigned long long *)scratch, nt, ob, hb);
       return check_cuda(cudaGetLastError(), "string_pack_kernel launch");
     };
-    if (job->heap_len == 0) {  // inlined strings only: 4 rows per thread, 1024-row tiles
-      const uint32_t ob = ((1024u * 12u + 64u) + 127u) & ~127u;
-      return large ? launch_pack(string_pack_kernel<true, 4>, 1024, ob, 0u) : launch_pack(string_pack_kernel<false, 4>, 1024, ob, 0u);
+    static const int force_nw = getenv("DMB_STR_PACK_NW") ? atoi(getenv("DMB_STR_PACK_NW")) : 0;
+    if (job->heap_len == 0) {  // inlined strings only: 4 rows per thread, 16 worker warps: whole-vector tiles
+      if (force_nw == 8) {
+        const uint32_t ob = ((1024u * 12u + 64u) + 127u) & ~127u;
+        return large ? launch_pack(string_pack_kernel<true, 4, 8>, 1024, 384, ob, 0u) : launch_pack(string_pack_kernel<false, 4, 8>, 1024, 384, ob, 0u);
+      }
+      const uint32_t ob = ((2048u * 12u + 64u) + 127u) & ~127u;
+      return large ? launch_pack(string_pack_kernel<true, 4, 16>, 2048, 640, ob, 0u) : launch_pack(string_pack_kernel<false, 4, 16>, 2048, 640, ob, 0u);
     }
-    const double heap_per_tile = (double)job->heap_len / (double)nrows * (double)kStrTileRows;
-    if (heap_per_tile <= 40.0 * 1024.0) {
+    const double heap_per_row = (double)job->heap_len / (double)nrows;
+    if (heap_per_row * 512.0 <= 40.0 * 1024.0) {
       static const double slack = getenv("DMB_STR_PACK_SLACK") ? atof(getenv("DMB_STR_PACK_SLACK")) : 1.15;
-      uint32_t hb = ((uint32_t)(heap_per_tile * slack) + 1024u + 127u) & ~127u;
+      // 1024-row tiles (16 worker warps) when two such CTAs fit an SM, else 512-row tiles (8 worker warps, 3 CTAs)
+      const bool wide = force_nw ? force_nw == 16 : heap_per_row <= 20.0;
+      const int rows = wide ? 1024 : 512;
+      uint32_t hb = ((uint32_t)(heap_per_row * rows * slack) + 1024u + 127u) & ~127u;
       if (hb < 2048u) hb = 2048u;
-      const uint32_t ob = hb + 2048u;  // inlined rows add at most 12 bytes each; a tile that exceeds the stage is copied row by row
-      return large ? launch_pack(string_pack_kernel<true, 2>, kStrTileRows, ob, hb) : launch_pack(string_pack_kernel<false, 2>, kStrTileRows, ob, hb);
+      const uint32_t ob = hb + (wide ? 4096u : 2048u);  // inlined rows add at most 12 bytes each; a tile that exceeds the stage is copied row by row
+      if (wide) return large ? launch_pack(string_pack_kernel<true, 2, 16>, 1024, 640, ob, hb) : launch_pack(string_pack_kernel<false, 2, 16>, 1024, 640, ob, hb);
+      return large ? launch_pack(string_pack_kernel<true, 2, 8>, 512, 384, ob, hb) : launch_pack(string_pack_kernel<false, 2, 8>, 512, 384, ob, hb);
     }
   }
   if (job->heap_len == 0 && !getenv("DMB_STR_NO_INLINE_KERNEL")) {  // no heap: inlined strings only, whole-vector tiles
