@@ -13,7 +13,7 @@ torch.distributed (NCCL) is used for the barrier and the max-over-ranks timing o
   value      rows/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
   e2e        rows/s through the reference-facing C ABI (duckdb_mb_gpu_result_from_chunks +
              _materialise_arrow) with page-locked HOST buffers, H2D + kernels + D2H in the timed region
-  roofline   the dominant kernel (string_batch_kernel): algorithmic bytes / its CUDA-event time
+  roofline   the dominant kernel (string_pack_kernel): algorithmic bytes / its CUDA-event time
   cpu_baseline  the oracle port of the reference's getters + decoders, 1 core, <= 1 M-row sample
 
 `--impl reference` times the reference's own CPU path (oracle port: the reference cannot be built
@@ -462,8 +462,8 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (string_batch_kernel: 5 launches per step)
-    dominant, dom_ms, dom_alg, dom_launches = "string_batch_kernel<utf8>", string_ms, step_alg_string, n_string_launches
+    # ---- roofline of the dominant kernel (string_pack_kernel: 5 launches per step, one per VARCHAR column)
+    dominant, dom_ms, dom_alg, dom_launches = "string_pack_kernel<utf8>", string_ms, step_alg_string, n_string_launches
     if fixed_ms > string_ms:
         dominant, dom_ms, dom_alg, dom_launches = "fixed_batch_kernel", fixed_ms, step_alg_fixed, n_fixed_launches
     achieved = dom_alg / 1e6 / dom_ms  # GB/s: algorithmic bytes of the kernel's launches in a step / their device time
@@ -501,7 +501,7 @@ def run_ours(args, rank, local_rank, world):
         "cpu_baseline": cpu,
         "gpu_launches": n_launches * args.steps,
         "clocks": clocks,
-        "kernel_ms_per_step": {"fixed_batch_kernel": fixed_ms, "string_batch_kernel": string_ms,
+        "kernel_ms_per_step": {"fixed_batch_kernel": fixed_ms, "string_pack_kernel": string_ms,
                                "fixed_gb_per_s": step_alg_fixed / 1e6 / fixed_ms, "string_gb_per_s": step_alg_string / 1e6 / string_ms,
                                "string_columns": {nm: {"ms": string_col_ms[nm], "gb_per_s": string_col_alg[nm] / 1e6 / string_col_ms[nm]}
                                                   for nm in string_col_ms}},

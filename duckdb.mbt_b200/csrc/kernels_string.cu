@@ -682,7 +682,7 @@ __device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, in
 
 // bytes a row contributes: 0 for NULL / past the chunk / an unusable pointer (flagged); P and the
 // workers must agree on this, it defines the tile totals
-template <int R>
+template <bool HEAP>
 __device__ __forceinline__ uint32_t row_bytes(const dmb_string_job &job, uint32_t x, uint32_t z, uint32_t w, bool live, int &flags,
                                               uint32_t &lo16, uint32_t &hi16) {
   uint32_t l = live ? x : 0u;
@@ -692,7 +692,7 @@ __device__ __forceinline__ uint32_t row_bytes(const dmb_string_job &job, uint32_
     const uint64_t p = ((uint64_t)w << 32) | (uint64_t)z;
     const uint64_t rel = p - job.heap_host_base;
     if (l >= kMaxRowBytes) { flags |= 4; l = 0; }
-    else if (R != 2 || p < job.heap_host_base || rel + l > job.heap_len) { flags |= 2; l = 0; }  // R != 2: the column has no heap
+    else if (!HEAP || p < job.heap_host_base || rel + l > job.heap_len) { flags |= 2; l = 0; }  // !HEAP: the column registered no heap
     else { lo16 = (uint32_t)(rel >> 4); hi16 = (uint32_t)((rel + l + 15u) >> 4); }
   }
   return l;
@@ -706,7 +706,7 @@ struct RowState {
   uint32_t my_off;            // tile-local offset of the thread's first row
 };
 
-template <bool LARGE, int R, int NW>
+template <bool LARGE, int R, int NW, bool HEAP>
 __global__ void __launch_bounds__(NW * 32 + 128, NW == 8 ? 3 : 2)
 string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles,
                    uint32_t ostage_bytes, uint32_t hstage_bytes) {
@@ -846,7 +846,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         const uint4 e = s[i];
         const bool live = i < nrows && (!has_mask || ((pt.vmask[slot][i >> 6] >> (i & 63)) & 1ull));
         uint32_t lo16, hi16;
-        sum += row_bytes<R>(job, e.x, e.z, e.w, live, flags, lo16, hi16);
+        sum += row_bytes<HEAP>(job, e.x, e.z, e.w, live, flags, lo16, hi16);
       }
       sum = __reduce_add_sync(0xffffffffu, sum);
       if (lane == 0) {
@@ -913,7 +913,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       for (int k = 0; k < R; ++k) {
         const uint4 e = s[k];
         uint32_t lo16, hi16;
-        const uint32_t l = row_bytes<R>(job, e.x, e.z, e.w, ((vword >> k) & 1ull) && tid * R + k < nrows, flags, lo16, hi16);
+        const uint32_t l = row_bytes<HEAP>(job, e.x, e.z, e.w, ((vword >> k) & 1ull) && tid * R + k < nrows, flags, lo16, hi16);
         nxt.len[k] = l; nxt.y[k] = e.y; nxt.z[k] = e.z; nxt.w[k] = e.w;
         tsum += l;
         hmin = hmin < lo16 ? hmin : lo16;
@@ -927,7 +927,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         if (lane >= d) incl += n;
       }
       PackPartials &pp = pt.part[slot];
-      if (R == 2) {
+      if (HEAP) {
         hmin = __reduce_min_sync(0xffffffffu, hmin);
         hmax = __reduce_max_sync(0xffffffffu, hmax);
         if (lane == 0) { pp.warp_hmin[warp] = hmin; pp.warp_hmax[warp] = hmax; }
@@ -938,7 +938,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
 #pragma unroll
       for (int w = 0; w < NW; ++w) warp_excl += w < warp ? pp.warp_sum[w] : 0u;
       nxt.my_off = warp_excl + incl - tsum;
-      if (R == 2) {
+      if (HEAP) {
         // is the tile one run?  (every non-empty row a pointer row whose bytes follow its predecessor's in the heap)
         uint32_t cmin = 0xffffffffu, cmax = 0u, o = nxt.my_off;
 #pragma unroll
@@ -964,19 +964,19 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
           total += pp.warp_sum[w];
-          if (R == 2) {
+          if (HEAP) {
             hmin = hmin < pp.warp_hmin[w] ? hmin : pp.warp_hmin[w];
             hmax = hmax > pp.warp_hmax[w] ? hmax : pp.warp_hmax[w];
           }
         }
         const uint32_t hbytes = hmax > hmin ? (hmax - hmin) << 4 : 0u;
-        const bool staged = R != 2 || (hbytes <= hstage_bytes && total + 48u <= ostage_bytes &&
+        const bool staged = !HEAP || (hbytes <= hstage_bytes && total + 48u <= ostage_bytes &&
                                        (hbytes == 0u || (reinterpret_cast<uintptr_t>(job.heap_dev) & 15u) == 0u));
         m.hmin = hmin;
         m.hbytes = hbytes;
         m.staged = staged;
         mbar_arrive(smem_u32(&pt.mbar_q[j & (kMetaRing - 1)]));  // L: tile j's look-back is due
-        if (R == 2 && staged && hbytes) {
+        if (HEAP && staged && hbytes) {
           const uint32_t mb = smem_u32(&pt.mbar_h[slot]);
           mbar_expect_tx(mb, hbytes);
           bulk_load(smem_u32(hbuf + (uint32_t)slot * hstride), job.heap_dev + ((uint64_t)hmin << 4), hbytes, mb);
@@ -1048,7 +1048,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       if (total != 0u && mc.staged) {
         // pack: this thread's rows as one byte stream starting at stage byte mis + my_off
         const int hslot = (j - 1) & 1;
-        if (R == 2 && mc.hbytes) {
+        if (HEAP && mc.hbytes) {
           uint32_t &ph = hslot ? phase_h1 : phase_h0;
           mbar_wait(smem_u32(&pt.mbar_h[hslot]), ph);
           ph ^= 1u;
@@ -1059,7 +1059,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         const uint32_t hbase = (mc.hmin << 4) + (uint32_t)job.heap_host_base;  // low 32 bits of the span's host address
         bool one_run = false;
         uint32_t run_c = 0;
-        if (R == 2 && mc.hbytes) {
+        if (HEAP && mc.hbytes) {
           const PackPartials &pq = pt.part[hslot];
           uint32_t cmin = 0xffffffffu, cmax = 0u;
 #pragma unroll
@@ -1105,7 +1105,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
             if (nw >= 2u) ow[wp + 1] = x1;
             if (nw >= 3u) ow[wp + 2] = x2;
             acc = (nw == 0u ? x0 : (nw == 1u ? x1 : (nw == 2u ? x2 : x3))) & low_bytes3(n & 3u);
-          } else if (R == 2) {
+          } else if (HEAP) {
             // pointer: the staged span.  Output word m of the row holds source bytes qp-4+4m .. +3
             const uint32_t qp = (cur.z[k] - hbase) + 4u - fill;
             const uint32_t sq = 8u * (qp & 3u);
@@ -1129,19 +1129,28 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         if (fill) store_bytes(ow + wp, acc, wp == shared_wp ? head : 0u, fill);  // last word: the next thread owns its other bytes
         fence_proxy_async_smem();
         }
-      } else if (R == 2 && total != 0u) {
+      } else if (HEAP && total != 0u) {
         // not staged: one warp per row, one byte per lane, heap -> out_data
         uint8_t *out = job.out_data + base;
-        const uint32_t o0 = cur.my_off, o1 = cur.my_off + cur.len[0];
+        uint32_t offk[R];
+        offk[0] = cur.my_off;
+#pragma unroll
+        for (int k = 1; k < R; ++k) offk[k] = offk[k - 1] + cur.len[k - 1];
+        auto pick = [&](const uint32_t (&a)[R], int k) {
+          uint32_t v = a[0];
+#pragma unroll
+          for (int i = 1; i < R; ++i) v = k == i ? a[i] : v;
+          return v;
+        };
 #pragma unroll 1
         for (int q = 0; q < 32 * R; ++q) {
           const int owner = q / R, k = q % R;
-          const uint32_t l = __shfl_sync(0xffffffffu, k ? cur.len[R - 1] : cur.len[0], owner);
+          const uint32_t l = __shfl_sync(0xffffffffu, pick(cur.len, k), owner);
           if (l == 0u) continue;
-          const uint32_t off = __shfl_sync(0xffffffffu, k ? o1 : o0, owner);
-          const uint32_t y = __shfl_sync(0xffffffffu, k ? cur.y[R - 1] : cur.y[0], owner);
-          const uint32_t z = __shfl_sync(0xffffffffu, k ? cur.z[R - 1] : cur.z[0], owner);
-          const uint32_t w = __shfl_sync(0xffffffffu, k ? cur.w[R - 1] : cur.w[0], owner);
+          const uint32_t off = __shfl_sync(0xffffffffu, pick(offk, k), owner);
+          const uint32_t y = __shfl_sync(0xffffffffu, pick(cur.y, k), owner);
+          const uint32_t z = __shfl_sync(0xffffffffu, pick(cur.z, k), owner);
+          const uint32_t w = __shfl_sync(0xffffffffu, pick(cur.w, k), owner);
           if (l <= 12u) {
             if ((uint32_t)lane < l) {
               const uint32_t word = lane < 4 ? y : (lane < 8 ? z : w);
@@ -1398,25 +1407,35 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
       return check_cuda(cudaGetLastError(), "string_pack_kernel launch");
     };
     static const int force_nw = getenv("DMB_STR_PACK_NW") ? atoi(getenv("DMB_STR_PACK_NW")) : 0;
-    if (job->heap_len == 0) {  // inlined strings only: 4 rows per thread, 16 worker warps: whole-vector tiles
-      if (force_nw == 8) {
+    if (job->heap_len == 0) {  // inlined strings only: 4 rows per thread (1024-row tiles with 8 worker warps, 2048 with 16)
+      if (force_nw != 16) {
         const uint32_t ob = ((1024u * 12u + 64u) + 127u) & ~127u;
-        return large ? launch_pack(string_pack_kernel<true, 4, 8>, 1024, 384, ob, 0u) : launch_pack(string_pack_kernel<false, 4, 8>, 1024, 384, ob, 0u);
+        return large ? launch_pack(string_pack_kernel<true, 4, 8, false>, 1024, 8 * 32 + 128, ob, 0u) : launch_pack(string_pack_kernel<false, 4, 8, false>, 1024, 8 * 32 + 128, ob, 0u);
       }
       const uint32_t ob = ((2048u * 12u + 64u) + 127u) & ~127u;
-      return large ? launch_pack(string_pack_kernel<true, 4, 16>, 2048, 640, ob, 0u) : launch_pack(string_pack_kernel<false, 4, 16>, 2048, 640, ob, 0u);
+      return large ? launch_pack(string_pack_kernel<true, 4, 16, false>, 2048, 16 * 32 + 128, ob, 0u) : launch_pack(string_pack_kernel<false, 4, 16, false>, 2048, 16 * 32 + 128, ob, 0u);
     }
     const double heap_per_row = (double)job->heap_len / (double)nrows;
     if (heap_per_row * 512.0 <= 40.0 * 1024.0) {
       static const double slack = getenv("DMB_STR_PACK_SLACK") ? atof(getenv("DMB_STR_PACK_SLACK")) : 1.15;
-      // 1024-row tiles (16 worker warps) when two such CTAs fit an SM, else 512-row tiles (8 worker warps, 3 CTAs)
-      const bool wide = force_nw ? force_nw == 16 : heap_per_row <= 20.0;
+      // 512-row tiles, 8 worker warps, 3 CTAs per SM
+      // (measured on the C2 columns: the 16-warp CTAs are no faster, so they stay an experiment: DMB_STR_PACK_NW=16)
+      const bool wide = force_nw == 16 && heap_per_row <= 20.0;
       const int rows = wide ? 1024 : 512;
       uint32_t hb = ((uint32_t)(heap_per_row * rows * slack) + 1024u + 127u) & ~127u;
       if (hb < 2048u) hb = 2048u;
       const uint32_t ob = hb + (wide ? 4096u : 2048u);  // inlined rows add at most 12 bytes each; a tile that exceeds the stage is copied row by row
-      if (wide) return large ? launch_pack(string_pack_kernel<true, 2, 16>, 1024, 640, ob, hb) : launch_pack(string_pack_kernel<false, 2, 16>, 1024, 640, ob, hb);
-      return large ? launch_pack(string_pack_kernel<true, 2, 8>, 512, 384, ob, hb) : launch_pack(string_pack_kernel<false, 2, 8>, 512, 384, ob, hb);
+      // few heap bytes per row (codes, short names): 1024-row tiles, 4 rows per thread, halve the per-tile costs
+      static const double r4_limit = getenv("DMB_STR_PACK_R4_LIMIT") ? atof(getenv("DMB_STR_PACK_R4_LIMIT")) : 9.5;
+      if (!wide && heap_per_row <= r4_limit) {
+        uint32_t hb4 = ((uint32_t)(heap_per_row * 1024.0 * slack) + 1024u + 127u) & ~127u;
+        if (hb4 < 2048u) hb4 = 2048u;
+        const uint32_t ob4 = hb4 + 4096u + 1024u * 4u;  // inlined rows add at most 12 bytes each: room for a third of the rows
+        return large ? launch_pack(string_pack_kernel<true, 4, 8, true>, 1024, 8 * 32 + 128, ob4, hb4)
+                     : launch_pack(string_pack_kernel<false, 4, 8, true>, 1024, 8 * 32 + 128, ob4, hb4);
+      }
+      if (wide) return large ? launch_pack(string_pack_kernel<true, 2, 16, true>, 1024, 16 * 32 + 128, ob, hb) : launch_pack(string_pack_kernel<false, 2, 16, true>, 1024, 16 * 32 + 128, ob, hb);
+      return large ? launch_pack(string_pack_kernel<true, 2, 8, true>, 512, 8 * 32 + 128, ob, hb) : launch_pack(string_pack_kernel<false, 2, 8, true>, 512, 8 * 32 + 128, ob, hb);
     }
   }
   if (job->heap_len == 0 && !getenv("DMB_STR_NO_INLINE_KERNEL")) {  // no heap: inlined strings only, whole-vector tiles

@@ -36,6 +36,11 @@ def main():
         db.add_string(gen, 0.0, 0, 0, len_choices=[17, 11, 4, 16])
         so = db.plan_string(0, 0, data_capacity=db.total_len)
         fn = lambda: db.run_string(so)  # noqa: E731
+    elif args.which == "string_run":  # every row a pointer string, heap in row order: each tile is one run
+        db = devgen.GeneratedBatch(n)
+        db.add_string(gen, 0.0, 13, 43)
+        so = db.plan_string(0, 0, data_capacity=db.total_len)
+        fn = lambda: db.run_string(so)  # noqa: E731
     elif args.which == "string_short":  # l_returnflag shape: 1 byte inline
         db = devgen.GeneratedBatch(n)
         db.add_string(gen, 0.0, 1, 1)
