@@ -541,6 +541,7 @@ struct PackPartials {
   uint32_t warp_hmax[kPackMaxWarps];
   uint32_t warp_cmin[kPackMaxWarps];  // min / max over the warp's pointer rows of (pointer - tile-local offset):
   uint32_t warp_cmax[kPackMaxWarps];  // all equal <=> the tile's bytes are one contiguous piece of the heap
+  uint32_t not_one_run;               // set by any warp that holds an inlined row or two runs
 };
 
 struct PackTail {
@@ -933,6 +934,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         if (lane == 0) { pp.warp_hmin[warp] = hmin; pp.warp_hmax[warp] = hmax; }
       }
       if (lane == 31) pp.warp_sum[warp] = incl;
+      if (tid == 0) pp.not_one_run = 0u;
       bar_sync(kBarWorkers, kWT);  // (every warp has also finished packing tile j-2: H[slot] is free)
       uint32_t warp_excl = 0;
 #pragma unroll
@@ -951,9 +953,14 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
           }
           o += l;
         }
-        cmin = __reduce_min_sync(0xffffffffu, cmin);
-        cmax = __reduce_max_sync(0xffffffffu, cmax);
-        if (lane == 0) { pp.warp_cmin[warp] = cmin; pp.warp_cmax[warp] = cmax; }  // read after the next barrier, in back()
+        // (read after the next barrier, in back(); most tiles of a mixed column are settled by the first test)
+        if (__any_sync(0xffffffffu, cmin == 0u && cmax == 0xffffffffu)) {
+          if (lane == 0) pp.not_one_run = 1u;
+        } else {
+          cmin = __reduce_min_sync(0xffffffffu, cmin);
+          cmax = __reduce_max_sync(0xffffffffu, cmax);
+          if (lane == 0) { pp.warp_cmin[warp] = cmin; pp.warp_cmax[warp] = cmax; }
+        }
       }
       if (tid == 0) {
         // the tile's heap span [hmin, hmax) -> H[slot], one bulk copy
@@ -1059,7 +1066,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         const uint32_t hbase = (mc.hmin << 4) + (uint32_t)job.heap_host_base;  // low 32 bits of the span's host address
         bool one_run = false;
         uint32_t run_c = 0;
-        if (HEAP && mc.hbytes) {
+        if (HEAP && mc.hbytes && pt.part[hslot].not_one_run == 0u) {
           const PackPartials &pq = pt.part[hslot];
           uint32_t cmin = 0xffffffffu, cmax = 0u;
 #pragma unroll
@@ -1416,7 +1423,9 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
       return large ? launch_pack(string_pack_kernel<true, 4, 16, false>, 2048, 16 * 32 + 128, ob, 0u) : launch_pack(string_pack_kernel<false, 4, 16, false>, 2048, 16 * 32 + 128, ob, 0u);
     }
     const double heap_per_row = (double)job->heap_len / (double)nrows;
-    if (heap_per_row * 512.0 <= 40.0 * 1024.0) {
+    // the pipeline needs three CTAs per SM to hide its latencies: S[2] + O + H[2] <= ~72 KiB, i.e. a heap span of
+    // <= 18 KiB per 512-row tile.  Longer strings come in long runs, which is what the run-gather is good at.
+    if (heap_per_row <= 29.5) {
       static const double slack = getenv("DMB_STR_PACK_SLACK") ? atof(getenv("DMB_STR_PACK_SLACK")) : 1.15;
       // 512-row tiles, 8 worker warps, 3 CTAs per SM
       // (measured on the C2 columns: the 16-warp CTAs are no faster, so they stay an experiment: DMB_STR_PACK_NW=16)

@@ -195,8 +195,15 @@ int32_t dmb_dev_fixed_batch(const dmb_fixed_job *jobs_dev, const dmb_fixed_job *
 int32_t dmb_op_out_width(int32_t op);
 int32_t dmb_phys_width(int32_t phys);
 
-/* K5: string_t -> utf8 offsets + data, single pass (block scan + decoupled look-back, 512-row tiles).
+/* K5: string_t -> utf8 offsets + data, single pass over the column (tile scan + decoupled look-back).
+ * Arrow modes run string_pack_kernel: a persistent, warp-specialised pipeline whose byte movement in
+ * and out of the SM is done by the copy engine (cp.async.bulk / mbarrier, sm_100 byte-masked bulk
+ * stores); columns of long strings (> 29 heap bytes per row on average) and DMB_STR_REF_BLOB run the
+ * run-gather string_batch_kernel.
  *   scratch   device, >= dmb_dev_string_scratch_bytes(nchunks) bytes, zeroed by the call
+ *   layout    every chunk's string_t vector must have DMB_VECTOR_SIZE entries of storage (a DuckDB
+ *             vector always has: rows past `count` are never interpreted, but whole tiles are fetched);
+ *             `in`, `out_data`, `heap_dev` 16-byte aligned; the heap copy followed by >= 16 readable bytes
  * Replaces src/duckdb_native.c:597-603 (string_t read) and :2474-2510 / :2699-2755. */
 size_t dmb_dev_string_scratch_bytes(int64_t nchunks);
 /* error flags raised by the last string launch on `scratch` (0 = none); synchronises `stream` */

@@ -191,3 +191,51 @@ def test_string_pointer_outside_the_registered_heap_is_an_error(mode):
     so = db.plan_string(0, mode, data_capacity=len(strings) * 64)
     db.run_string(so)
     assert db.string_error(so) & 4  # kErrHeapRange
+
+
+# ------------------------------------------------------------------ string_pack_kernel paths
+def _bulk(n, lens, valid_p, pattern, seed):
+    rng = np.random.default_rng(seed)
+    counts = ch.chunk_counts(n, pattern, rng)
+    valid = None if valid_p is None else rng.random(n) >= valid_p
+    return ch.ChunkBatch(counts, [ch.string_column_bulk("s", lens(rng, n), valid, counts, rng, utf8_fraction=0.05)])
+
+
+@pytest.mark.parametrize("n,pattern", [(513, "full"), (40_000, "full"), (40_000, "ragged")])
+def test_string_one_run_tiles(n, pattern):
+    # every row a pointer string laid out in row order: each tile is one shifted copy of its heap span;
+    # with NULLs (no heap bytes) in between the tiles are still one run
+    dev = _device_mod()
+    _check_string(dev, _bulk(n, lambda r, m: r.integers(13, 44, m), None, pattern, 11), modes=(0, 1))
+    _check_string(dev, _bulk(n, lambda r, m: r.integers(13, 44, m), 0.2, pattern, 12), modes=(0, 1))
+
+
+@pytest.mark.parametrize("n,pattern", [(3000, "full"), (50_000, "ragged")])
+def test_string_few_heap_bytes_per_row(n, pattern):
+    # l_shipinstruct shape: a few distinct values around the inline limit -> the 1024-row-tile variant
+    dev = _device_mod()
+    choices = np.asarray([17, 11, 4, 16, 0, 12, 13])
+    _check_string(dev, _bulk(n, lambda r, m: choices[r.integers(0, choices.shape[0], m)], 0.1, pattern, 13))
+
+
+def test_string_tiles_that_do_not_fit_the_stages():
+    # short strings on average (the pack kernel is chosen), but some tiles hold long strings or point all over
+    # the heap: those tiles take the row-by-row path inside the same launch
+    dev = _device_mod()
+    rng = np.random.default_rng(14)
+    n = 30_000
+    lens = rng.integers(0, 30, n)
+    lens[rng.integers(0, n, 12)] = rng.integers(20_000, 70_000, 12)   # a few very long rows
+    counts = ch.chunk_counts(n, "ragged", rng)
+    col = ch.string_column_bulk("s", lens, rng.random(n) > 0.1, counts, rng)
+    _check_string(dev, ch.ChunkBatch(counts, [col]))
+    # scattered pointers: reverse the heap order of the pointer strings (every tile's span becomes huge)
+    strings = [bytes(rng.integers(0x20, 0x7F, int(l), dtype=np.uint8)) for l in rng.integers(0, 40, 6000)]
+    counts = ch.chunk_counts(len(strings))
+    col = ch.string_column("s", strings, counts)
+    col2 = ch.string_column("s", strings[::-1], counts)   # same strings, heap filled in the opposite order
+    # rows in forward order, heap (and pointers) from the reversed column
+    data = col2.data.reshape(-1, 16)[: len(strings)][::-1].copy()
+    col.data.reshape(-1, 16)[: len(strings)] = data
+    col.heap = col2.heap
+    _check_string(dev, ch.ChunkBatch(counts, [col]), modes=(0, 1))
