@@ -505,7 +505,7 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
 //      a thread shares with its neighbours are written byte by byte.
 //   L  decoupled look-back of tile j, started lazily (when the workers have scanned it: by then
 //      its predecessors' aggregates, often their prefixes, are out) and due only when tile j-1
-//      has been packed; a narrow first round keeps the status lines cool.
+//      has been packed.
 //
 // A tile whose span or output does not fit the stages (scattered pointers, a long string) is copied
 // row by row, one warp per row and one byte per lane, straight from the heap to out_data.
@@ -517,10 +517,14 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
 constexpr uint32_t kPackTail = 1792;  // bytes of bookkeeping in front of the stages
 constexpr int kLookWide = 8;          // status words in flight per lane in the look-back
 #ifndef DMB_LOOK_FIRST
-#define DMB_LOOK_FIRST 2
+#define DMB_LOOK_FIRST 8
 #endif
 constexpr int kLookFirst = DMB_LOOK_FIRST;  // ... in its first round
 constexpr int kMetaRing = 4;
+#ifndef DMB_PACK_UNROLL
+#define DMB_PACK_UNROLL 2
+#endif
+constexpr int kPackUnroll = DMB_PACK_UNROLL;  // words in flight per thread in the pointer-row copy loop
 
 struct TileMeta {
   long long tile;            // -1: no more tiles
@@ -632,7 +636,7 @@ __device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, in
   unsigned long long t0 = 0;
   if (tile > 0) {
     int64_t look = tile - 1;
-    int width = kLookFirst;  // the nearest predecessors usually hold a prefix: a narrow first round keeps the status lines cool
+    int width = kLookFirst;  // (a narrow first round was tried: it costs a second L2 round trip more often than it saves traffic)
     while (true) {
       uint64_t st[kLookWide];
 #pragma unroll
@@ -1122,7 +1126,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
             if (wp == shared_wp) store_bytes(ow + wp, x0, head, 4u); else ow[wp] = x0;  // l > 12: the word always completes
             prev = nx;
             uint32_t *o = ow + wp;
-#pragma unroll 2
+#pragma unroll kPackUnroll
             for (uint32_t m = 1; m < nw; ++m) {
               nx = s[m];
               o[m] = __funnelshift_r(prev, nx, sq);
