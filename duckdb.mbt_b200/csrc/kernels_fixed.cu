@@ -257,11 +257,13 @@ __device__ __forceinline__ void bool_bits_tile(const BatchView &b, const dmb_fix
 }
 
 // ------------------------------------------------------------------ phase B: validity of tile t
+// One WARP per output tile (32 bitmap words of 64 rows): a tile is a chain of dependent loads
+// (geometry -> descriptor -> mask words), so a CTA runs eight tiles side by side.
 __device__ __forceinline__ void validity_tile(const BatchView &b, const dmb_fixed_job &job, int64_t t,
                                               uint64_t *s_words) {
   const int64_t nwords = (b.nrows + 63) >> 6;
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  {
     const int64_t w = t * DMB_VALIDITY_WORDS + lane;
     uint64_t word = 0;
     if (w < nwords) {
@@ -285,19 +287,22 @@ __device__ __forceinline__ void validity_tile(const BatchView &b, const dmb_fixe
     }
   }
   if (job.out_valid_bytes) {  // reference form: one byte per row, 1 = valid (duckdb_native.c:2594-2606)
-    __syncthreads();
-    const int64_t r0 = t * (int64_t)kVec + 8 * (int64_t)threadIdx.x;
-    if (r0 < b.nrows) {
-      uint32_t bits = reinterpret_cast<const uint8_t *>(s_words)[threadIdx.x];
-      uint64_t bytes = spread8(bits);
-      uint8_t *dst = job.out_valid_bytes + r0;
-      if (r0 + 8 <= b.nrows) {
-        __stcs(reinterpret_cast<unsigned long long *>(dst), bytes);
-      } else {
-        for (int k = 0; r0 + k < b.nrows; ++k) dst[k] = (uint8_t)(bytes >> (8 * k));
+    __syncwarp();
+#pragma unroll 2
+    for (int g = lane; g < kVec / 8; g += 32) {
+      const int64_t r0 = t * (int64_t)kVec + 8 * (int64_t)g;
+      if (r0 < b.nrows) {
+        uint32_t bits = reinterpret_cast<const uint8_t *>(s_words)[g];
+        uint64_t bytes = spread8(bits);
+        uint8_t *dst = job.out_valid_bytes + r0;
+        if (r0 + 8 <= b.nrows) {
+          __stcs(reinterpret_cast<unsigned long long *>(dst), bytes);
+        } else {
+          for (int k = 0; r0 + k < b.nrows; ++k) dst[k] = (uint8_t)(bytes >> (8 * k));
+        }
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -311,13 +316,14 @@ template <typename S, typename D, int KIND>
 struct GroupOf {
   static constexpr int W = sizeof(S) > sizeof(D) ? sizeof(S) : sizeof(D);
   static constexpr int R = 16 / W;
-  static constexpr int value = (KIND == kKindConvert && R >= 4) ? (kThreads * 4) / (kVec / R) : 1;
+  // validity only: one tile per warp
+  static constexpr int value = KIND == kKindValidityOnly ? kThreads / 32 : ((KIND == kKindConvert && R >= 4) ? (kThreads * 4) / (kVec / R) : 1);
 };
 
 template <typename S, typename D, typename F, int KIND>
 __global__ void __launch_bounds__(kThreads)
 fixed_batch_kernel(const dmb_fixed_job *__restrict__ jobs, int njobs, BatchView b) {
-  __shared__ uint64_t s_words[DMB_VALIDITY_WORDS];
+  __shared__ uint64_t s_words[kThreads / 32][DMB_VALIDITY_WORDS];
   __shared__ dmb_fixed_job s_job;
   constexpr int G = GroupOf<S, D, KIND>::value;
   const int64_t ntiles = (b.nrows + kVec - 1) / kVec;
@@ -349,12 +355,13 @@ fixed_batch_kernel(const dmb_fixed_job *__restrict__ jobs, int njobs, BatchView 
         }
       }
     }
-    for (int64_t i = i0; i < i0 + G && i < b.nchunks; ++i) {
-      if (KIND == kKindBoolBits) {
+    if (KIND == kKindBoolBits) {
+      for (int64_t i = i0; i < i0 + G && i < b.nchunks; ++i)
         if (i < ntiles && job.out_values) bool_bits_tile(b, job, i);
-      }
-      if (i < ntiles && (job.out_validity || job.out_valid_bytes || job.null_count))
-        validity_tile(b, job, i, s_words);
+    }
+    if (job.out_validity || job.out_valid_bytes || job.null_count) {
+      const int warp = threadIdx.x >> 5;
+      for (int64_t i = i0 + warp; i < i0 + G && i < b.nchunks && i < ntiles; i += kThreads / 32) validity_tile(b, job, i, s_words[warp]);
     }
   }
 }
@@ -467,7 +474,8 @@ extern "C" int32_t dmb_dev_fixed_batch(const dmb_fixed_job *jobs_dev, const dmb_
     fixed_kernel_fn fn = select_kernel(jobs_host[j0].op);
     if (!fn) { set_error("dmb_dev_fixed_batch: unsupported conversion op 0x%x (job %d)", jobs_host[j0].op, j0); return -1; }
     int group = 1;  // must match GroupOf<>: narrow conversions take several chunks per item
-    if (jobs_host[j0].op != DMB_OP_VALIDITY_ONLY && (jobs_host[j0].op & 0xff) != DMB_DST_BOOL_BITS) {
+    if (jobs_host[j0].op == DMB_OP_VALIDITY_ONLY) group = kThreads / 32;  // one tile per warp
+    else if ((jobs_host[j0].op & 0xff) != DMB_DST_BOOL_BITS) {
       const int wi = dmb_phys_width(jobs_host[j0].op >> 8), wo = dmb_op_out_width(jobs_host[j0].op);
       const int w = wi > wo ? wi : wo;
       if (w > 0 && w <= 4) group = (kThreads * 4) / (kVec / (16 / w));
