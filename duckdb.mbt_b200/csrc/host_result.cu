@@ -1101,6 +1101,148 @@ extern "C" moonbit_bytes_t duckdb_mb_arrow_get_column_string_nullable(duckdb_mb_
 extern "C" void duckdb_mb_arrow_destroy(duckdb_mb_arrow_result *r) { free_result(r); }
 extern "C" int32_t duckdb_mb_is_null_arrow_result(duckdb_mb_arrow_result *r) { return r == nullptr ? 1 : 0; }
 
+// ------------------------------------------------------------------ per-cell drop-ins
+// The reference's materialised-result and streaming-chunk accessors hand MoonBit one cell per FFI
+// call (Connection::query, src/duckdb_native.mbt:477-497; ResultStream::next, :557-577).  Here the
+// column's text form is produced once on the GPU (K7 + K5, cached in pinned memory by
+// text_column) and a cell is a slice of it.
+namespace dmb {
+namespace {
+
+// the VARCHAR rendering of cell (col, row) of the whole result, strlen-truncated like the
+// reference's `strlen(value)` copy; empty Bytes for NULL, bad indices and types with no renderer
+moonbit_bytes_t cell_text(Result *r, int32_t col, int64_t row) {
+  if (!r || col < 0 || col >= r->column_count || row < 0 || row >= r->nrows) return empty_bytes();
+  Col &c = r->cols[(size_t)col];
+  if (c.type_id == DMB_TYPE_BLOB) {  // duckdb_value_varchar escapes BLOB bytes (\xAA): not reproduced
+    set_error("column %d: libduckdb's text rendering of BLOB is not reproduced on the device", col);
+    return empty_bytes();
+  }
+  dmb_typed_column t;
+  {
+    std::lock_guard<std::mutex> g(r->core->mu);
+    if (text_column(r, col, &t)) return empty_bytes();
+  }
+  if (!t.valid[row]) return empty_bytes();
+  const uint8_t *s = t.data + t.offsets[row];
+  int32_t len = t.offsets[row + 1] - t.offsets[row];
+  const void *nul = len > 0 ? memchr(s, 0, (size_t)len) : nullptr;
+  if (nul) len = (int32_t)((const uint8_t *)nul - s);
+  moonbit_bytes_t b = moonbit_make_bytes_raw(len);
+  if (len > 0) memcpy(b, s, (size_t)len);
+  return b;
+}
+
+// duckdb_validity_row_is_valid on the chunk's own mask (src/duckdb_native.c:529-534)
+int32_t cell_is_null(Result *r, int32_t col, int64_t chunk, int32_t row) {
+  if (!r || col < 0 || col >= r->column_count || row < 0 || row >= DMB_VECTOR_SIZE || chunk < 0 || chunk >= r->nchunks) return 1;
+  const Col &c = r->cols[(size_t)col];
+  const uint64_t *mask = c.validity.empty() ? nullptr : (const uint64_t *)c.validity[(size_t)chunk];
+  if (!mask) return 0;
+  return ((mask[row >> 6] >> (row & 63)) & 1ull) ? 0 : 1;
+}
+
+}  // namespace
+}  // namespace dmb
+
+// ---- materialised result: src/duckdb_native.c:174-254 (the handle is the same result object)
+extern "C" void duckdb_mb_result_destroy(duckdb_mb_arrow_result *r) { free_result(r); }
+extern "C" int32_t duckdb_mb_is_null_result(duckdb_mb_arrow_result *r) { return r == nullptr ? 1 : 0; }
+extern "C" int32_t duckdb_mb_result_column_count(duckdb_mb_arrow_result *r) { return r ? r->column_count : 0; }
+extern "C" int32_t duckdb_mb_result_row_count(duckdb_mb_arrow_result *r) { return r ? r->row_count : 0; }
+extern "C" moonbit_bytes_t duckdb_mb_result_column_name(duckdb_mb_arrow_result *r, int32_t col) {
+  if (!r || col < 0 || col >= r->column_count) return empty_bytes();
+  const std::string &n = r->cols[(size_t)col].name;
+  moonbit_bytes_t b = moonbit_make_bytes_raw((int32_t)n.size());
+  memcpy(b, n.data(), n.size());
+  return b;
+}
+extern "C" int32_t duckdb_mb_result_column_type(duckdb_mb_arrow_result *r, int32_t col) {
+  if (!r || col < 0 || col >= r->column_count) return DMB_TYPE_INVALID;
+  return r->cols[(size_t)col].type_id;
+}
+extern "C" int32_t duckdb_mb_result_is_null(duckdb_mb_arrow_result *r, int32_t col, int32_t row) {
+  if (!r) return 1;
+  if (col < 0 || col >= r->column_count || row < 0 || row >= r->nrows) return 1;  // duckdb_value_is_null: out of range counts as NULL
+  // locate the chunk of the row: chunks are at most 2048 rows, so start from the regular guess
+  int64_t k = row / DMB_VECTOR_SIZE;
+  if (k >= r->nchunks) k = r->nchunks - 1;
+  while (k > 0 && r->row_off[(size_t)k] > row) --k;
+  while (k + 1 < r->nchunks && r->row_off[(size_t)k + 1] <= row) ++k;
+  return cell_is_null(r, col, k, (int32_t)(row - r->row_off[(size_t)k]));
+}
+extern "C" moonbit_bytes_t duckdb_mb_result_value(duckdb_mb_arrow_result *r, int32_t col, int32_t row) {
+  return cell_text(r, col, row);
+}
+
+// ---- streaming chunks: src/duckdb_native.c:260-667
+struct duckdb_mb_stream {
+  duckdb_mb_arrow_result *result;
+  int64_t next_chunk;
+};
+struct duckdb_mb_chunk {
+  duckdb_mb_stream *stream;
+  int64_t index;
+};
+
+static bool stream_supported_type(int32_t type_id) {  // whitelist of src/duckdb_native.c:271-303
+  switch (type_id) {
+    case DMB_TYPE_BOOLEAN: case DMB_TYPE_TINYINT: case DMB_TYPE_SMALLINT: case DMB_TYPE_INTEGER: case DMB_TYPE_BIGINT:
+    case DMB_TYPE_UTINYINT: case DMB_TYPE_USMALLINT: case DMB_TYPE_UINTEGER: case DMB_TYPE_UBIGINT: case DMB_TYPE_FLOAT:
+    case DMB_TYPE_DOUBLE: case DMB_TYPE_VARCHAR: case DMB_TYPE_BLOB: case DMB_TYPE_DATE: case DMB_TYPE_TIME:
+    case DMB_TYPE_TIME_NS: case DMB_TYPE_TIME_TZ: case DMB_TYPE_TIMESTAMP: case DMB_TYPE_TIMESTAMP_TZ:
+    case DMB_TYPE_TIMESTAMP_S: case DMB_TYPE_TIMESTAMP_MS: case DMB_TYPE_TIMESTAMP_NS: case DMB_TYPE_INTERVAL:
+    case DMB_TYPE_HUGEINT: case DMB_TYPE_UHUGEINT: case DMB_TYPE_UUID:
+      return true;
+    default: return false;
+  }
+}
+
+// what duckdb_mb_query_stream does after running the SQL (duckdb_mb_stream_from_result, :319-353);
+// the stream does not own the result
+extern "C" duckdb_mb_stream *duckdb_mb_gpu_stream_from_result(duckdb_mb_arrow_result *r) {
+  if (!r) { set_error("result is null"); return nullptr; }
+  for (int32_t c = 0; c < r->column_count; ++c)
+    if (!stream_supported_type(r->cols[(size_t)c].type_id)) { set_error("streaming query has unsupported column type"); return nullptr; }
+  duckdb_mb_stream *s = new duckdb_mb_stream();
+  s->result = r;
+  s->next_chunk = 0;
+  return s;
+}
+extern "C" void duckdb_mb_stream_destroy(duckdb_mb_stream *s) { delete s; }
+extern "C" int32_t duckdb_mb_is_null_stream(duckdb_mb_stream *s) { return s == nullptr ? 1 : 0; }
+extern "C" int32_t duckdb_mb_stream_column_count(duckdb_mb_stream *s) { return s ? s->result->column_count : 0; }
+extern "C" moonbit_bytes_t duckdb_mb_stream_column_name(duckdb_mb_stream *s, int32_t col) {
+  return s ? duckdb_mb_result_column_name(s->result, col) : empty_bytes();
+}
+// NULL with an empty last error at the end of the stream (:472-480)
+extern "C" duckdb_mb_chunk *duckdb_mb_stream_fetch_chunk(duckdb_mb_stream *s) {
+  if (!s || !s->result) { set_error("stream is null"); return nullptr; }
+  if (s->next_chunk >= s->result->nchunks) { set_error("%s", ""); return nullptr; }
+  duckdb_mb_chunk *c = new duckdb_mb_chunk();
+  c->stream = s;
+  c->index = s->next_chunk++;
+  return c;
+}
+extern "C" void duckdb_mb_chunk_destroy(duckdb_mb_chunk *c) { delete c; }
+extern "C" int32_t duckdb_mb_is_null_chunk(duckdb_mb_chunk *c) { return c == nullptr ? 1 : 0; }
+extern "C" int32_t duckdb_mb_chunk_row_count(duckdb_mb_chunk *c) {
+  return (c && c->stream) ? (int32_t)c->stream->result->counts[(size_t)c->index] : 0;
+}
+extern "C" int32_t duckdb_mb_chunk_column_count(duckdb_mb_chunk *c) { return (c && c->stream) ? c->stream->result->column_count : 0; }
+extern "C" int32_t duckdb_mb_chunk_is_null(duckdb_mb_chunk *c, int32_t col, int32_t row) {
+  if (!c || !c->stream) return 1;
+  return cell_is_null(c->stream->result, col, c->index, row);
+}
+// UNPINNED format: the reference renders the cell with duckdb_value_to_string (:305-318), which no
+// reference test looks at; this returns the VARCHAR cast of the cell like duckdb_mb_result_value
+extern "C" moonbit_bytes_t duckdb_mb_chunk_value(duckdb_mb_chunk *c, int32_t col, int32_t row) {
+  if (!c || !c->stream || row < 0) return empty_bytes();
+  duckdb_mb_arrow_result *r = c->stream->result;
+  if (row >= (int32_t)r->counts[(size_t)c->index]) return empty_bytes();
+  return cell_text(r, col, r->row_off[(size_t)c->index] + row);
+}
+
 extern "C" double duckdb_mb_bytes_to_double(const char *bytes, int32_t offset) {
   double d;
   memcpy(&d, bytes + offset, sizeof(d));

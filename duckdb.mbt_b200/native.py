@@ -104,6 +104,11 @@ EXPORTED_SYMBOLS = [
     "duckdb_mb_arrow_get_column_int32_nullable", "duckdb_mb_arrow_get_column_int64_nullable",
     "duckdb_mb_arrow_get_column_double_nullable", "duckdb_mb_arrow_get_column_string_nullable",
     "duckdb_mb_arrow_get_column_bool_nullable", "duckdb_mb_arrow_destroy", "duckdb_mb_is_null_arrow_result",
+    "duckdb_mb_result_destroy", "duckdb_mb_is_null_result", "duckdb_mb_result_column_count", "duckdb_mb_result_row_count",
+    "duckdb_mb_result_column_name", "duckdb_mb_result_column_type", "duckdb_mb_result_is_null", "duckdb_mb_result_value",
+    "duckdb_mb_gpu_stream_from_result", "duckdb_mb_stream_destroy", "duckdb_mb_is_null_stream", "duckdb_mb_stream_column_count",
+    "duckdb_mb_stream_column_name", "duckdb_mb_stream_fetch_chunk", "duckdb_mb_chunk_destroy", "duckdb_mb_is_null_chunk",
+    "duckdb_mb_chunk_row_count", "duckdb_mb_chunk_column_count", "duckdb_mb_chunk_is_null", "duckdb_mb_chunk_value",
     "duckdb_mb_bytes_to_double",
     "duckdb_mb_gpu_appender_create", "duckdb_mb_gpu_appender_destroy", "duckdb_mb_gpu_appender_error",
     "duckdb_mb_gpu_appender_state", "duckdb_mb_gpu_appender_row_count", "duckdb_mb_gpu_append_arrow_batch",
@@ -206,6 +211,29 @@ def lib():
     L.duckdb_mb_arrow_destroy.argtypes = [vp]
     L.duckdb_mb_is_null_arrow_result.restype = i32
     L.duckdb_mb_is_null_arrow_result.argtypes = [vp]
+    # per-cell drop-ins (materialised result, streaming chunks)
+    for name in ("duckdb_mb_result_destroy", "duckdb_mb_stream_destroy", "duckdb_mb_chunk_destroy"):
+        getattr(L, name).restype = None
+        getattr(L, name).argtypes = [vp]
+    for name in ("duckdb_mb_is_null_result", "duckdb_mb_result_column_count", "duckdb_mb_result_row_count", "duckdb_mb_is_null_stream",
+                 "duckdb_mb_stream_column_count", "duckdb_mb_is_null_chunk", "duckdb_mb_chunk_row_count", "duckdb_mb_chunk_column_count"):
+        getattr(L, name).restype = i32
+        getattr(L, name).argtypes = [vp]
+    for name in ("duckdb_mb_result_column_name", "duckdb_mb_stream_column_name"):
+        getattr(L, name).restype = vp
+        getattr(L, name).argtypes = [vp, i32]
+    L.duckdb_mb_result_column_type.restype = i32
+    L.duckdb_mb_result_column_type.argtypes = [vp, i32]
+    for name in ("duckdb_mb_result_is_null", "duckdb_mb_chunk_is_null"):
+        getattr(L, name).restype = i32
+        getattr(L, name).argtypes = [vp, i32, i32]
+    for name in ("duckdb_mb_result_value", "duckdb_mb_chunk_value"):
+        getattr(L, name).restype = vp
+        getattr(L, name).argtypes = [vp, i32, i32]
+    L.duckdb_mb_gpu_stream_from_result.restype = vp
+    L.duckdb_mb_gpu_stream_from_result.argtypes = [vp]
+    L.duckdb_mb_stream_fetch_chunk.restype = vp
+    L.duckdb_mb_stream_fetch_chunk.argtypes = [vp]
     L.duckdb_mb_bytes_to_double.restype = C.c_double
     L.duckdb_mb_bytes_to_double.argtypes = [vp, i32]
     L.duckdb_mb_gpu_appender_create.restype = vp

@@ -64,3 +64,84 @@ class QueryResult:
         if self._result is None:
             raise DuckDBError("to_typed needs the live result")
         return tr.to_typed(self._result)
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's own per-cell paths, call for call (the drop-in C symbols):
+#   Connection::query      src/duckdb_native.mbt:454-501  (duckdb_mb_result_is_null / _value per cell)
+#   Connection::query_stream / ResultStream::next  :504-582  (duckdb_mb_chunk_is_null / _value per cell)
+class DataChunk:
+    """`DataChunk` of src/duckdb.mbt:56-62: row-major strings + null mask of one fetched chunk."""
+
+    def __init__(self, rows: List[List[str]], nulls: List[List[bool]]):
+        self.rows = rows
+        self.nulls = nulls
+
+    def row_count(self) -> int:
+        return len(self.rows)
+
+
+class ResultStream:
+    def __init__(self, result: ArrowResult):
+        from . import native as nat
+        self._nat = nat
+        self.lib = result.lib
+        self._result = result
+        self.handle = self.lib.duckdb_mb_gpu_stream_from_result(result.handle)
+        if self.lib.duckdb_mb_is_null_stream(self.handle):
+            self.handle = None
+            raise DuckDBError(nat.last_error())
+
+    def columns(self) -> List[str]:  # src/duckdb_native.mbt:529-540
+        n = self.lib.duckdb_mb_stream_column_count(self.handle)
+        return [self._nat.moonbit_bytes(self.lib.duckdb_mb_stream_column_name(self.handle, j)).decode("utf-8", "replace") for j in range(n)]
+
+    def next(self) -> Optional[DataChunk]:  # :543-582: None at the end of the stream, DuckDBError on a fetch error
+        chunk = self.lib.duckdb_mb_stream_fetch_chunk(self.handle)
+        if self.lib.duckdb_mb_is_null_chunk(chunk):
+            err = self._nat.last_error()
+            if err:
+                raise DuckDBError(err)
+            return None
+        try:
+            nrows = self.lib.duckdb_mb_chunk_row_count(chunk)
+            ncols = self.lib.duckdb_mb_chunk_column_count(chunk)
+            rows, nulls = [], []
+            for r in range(nrows):
+                row, nrow = [], []
+                for c in range(ncols):
+                    if self.lib.duckdb_mb_chunk_is_null(chunk, c, r):
+                        row.append("")
+                        nrow.append(True)
+                    else:
+                        row.append(self._nat.moonbit_bytes(self.lib.duckdb_mb_chunk_value(chunk, c, r)).decode("utf-8", "replace"))
+                        nrow.append(False)
+                rows.append(row)
+                nulls.append(nrow)
+            return DataChunk(rows, nulls)
+        finally:
+            self.lib.duckdb_mb_chunk_destroy(chunk)
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.duckdb_mb_stream_destroy(self.handle)
+            self.handle = None
+
+
+def query_per_cell(result: ArrowResult) -> QueryResult:
+    """`Connection::query`'s cell loop over the drop-in symbols (two calls per cell, like the reference)."""
+    from . import native as nat
+    L = result.lib
+    ncols, nrows = L.duckdb_mb_result_column_count(result.handle), L.duckdb_mb_result_row_count(result.handle)
+    names = [nat.moonbit_bytes(L.duckdb_mb_result_column_name(result.handle, j)).decode("utf-8", "replace") for j in range(ncols)]
+    types = [L.duckdb_mb_result_column_type(result.handle, j) for j in range(ncols)]
+    strings = [[""] * nrows for _ in range(ncols)]
+    valid = [np.zeros(nrows, dtype=bool) for _ in range(ncols)]
+    for r in range(nrows):
+        for c in range(ncols):
+            if not L.duckdb_mb_result_is_null(result.handle, c, r):
+                valid[c][r] = True
+                strings[c][r] = nat.moonbit_bytes(L.duckdb_mb_result_value(result.handle, c, r)).decode("utf-8", "replace")
+    q = QueryResult(names, types, strings, valid)
+    q._result = result
+    return q

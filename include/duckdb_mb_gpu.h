@@ -407,6 +407,40 @@ int32_t duckdb_mb_gpu_result_typed_column(duckdb_mb_arrow_result *r, int32_t col
 int32_t duckdb_mb_gpu_result_text_column(duckdb_mb_arrow_result *r, int32_t col,
                                          dmb_typed_column *out);
 
+/* ---- L2 drop-in, per-cell accessors of the materialised result (src/duckdb_native.c:174-254;
+ * MoonBit externs src/duckdb_native.mbt:296-340).  The handle is the same result object: the
+ * glue's duckdb_mb_query returns what duckdb_mb_gpu_result_from_chunks built.  `value` is the
+ * cell's duckdb_value_varchar rendering (strlen-truncated, empty Bytes for NULL), produced for the
+ * whole column by one GPU pass on the first call and sliced afterwards. */
+void duckdb_mb_result_destroy(duckdb_mb_arrow_result *r);
+int32_t duckdb_mb_is_null_result(duckdb_mb_arrow_result *r);
+int32_t duckdb_mb_result_column_count(duckdb_mb_arrow_result *r);
+int32_t duckdb_mb_result_row_count(duckdb_mb_arrow_result *r);
+moonbit_bytes_t duckdb_mb_result_column_name(duckdb_mb_arrow_result *r, int32_t col);
+int32_t duckdb_mb_result_column_type(duckdb_mb_arrow_result *r, int32_t col);
+int32_t duckdb_mb_result_is_null(duckdb_mb_arrow_result *r, int32_t col, int32_t row);
+moonbit_bytes_t duckdb_mb_result_value(duckdb_mb_arrow_result *r, int32_t col, int32_t row);
+
+/* ---- L2 drop-in, streaming chunks (src/duckdb_native.c:260-667; externs src/duckdb_native.mbt:342-392).
+ * duckdb_mb_gpu_stream_from_result is what the glue's duckdb_mb_query_stream calls after running
+ * the SQL (reference: duckdb_mb_stream_from_result, :319-353, same type whitelist and error).
+ * chunk_is_null is the validity-bit test of :520-535; chunk_value returns the VARCHAR cast of the
+ * cell (the reference's duckdb_value_to_string format is pinned by no reference test: UNPINNED). */
+typedef struct duckdb_mb_stream duckdb_mb_stream;
+typedef struct duckdb_mb_chunk duckdb_mb_chunk;
+duckdb_mb_stream *duckdb_mb_gpu_stream_from_result(duckdb_mb_arrow_result *r);
+void duckdb_mb_stream_destroy(duckdb_mb_stream *s);
+int32_t duckdb_mb_is_null_stream(duckdb_mb_stream *s);
+int32_t duckdb_mb_stream_column_count(duckdb_mb_stream *s);
+moonbit_bytes_t duckdb_mb_stream_column_name(duckdb_mb_stream *s, int32_t col);
+duckdb_mb_chunk *duckdb_mb_stream_fetch_chunk(duckdb_mb_stream *s);
+void duckdb_mb_chunk_destroy(duckdb_mb_chunk *c);
+int32_t duckdb_mb_is_null_chunk(duckdb_mb_chunk *c);
+int32_t duckdb_mb_chunk_row_count(duckdb_mb_chunk *c);
+int32_t duckdb_mb_chunk_column_count(duckdb_mb_chunk *c);
+int32_t duckdb_mb_chunk_is_null(duckdb_mb_chunk *c, int32_t col, int32_t row);
+moonbit_bytes_t duckdb_mb_chunk_value(duckdb_mb_chunk *c, int32_t col, int32_t row);
+
 /* timings of the last materialise call, milliseconds: [0]=h2d [1]=kernels [2]=d2h [3]=total */
 int32_t duckdb_mb_gpu_result_timings(duckdb_mb_arrow_result *r, double *out4);
 /* bytes moved over the host link by the last materialise call: [0]=h2d [1]=d2h */

@@ -54,6 +54,10 @@ def lib():
         L.ora_arrow_schema.restype = C.c_void_p
         L.ora_arrow_schema.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.ora_free.argtypes = [C.c_void_p]
+        L.ora_value_is_null.restype = C.c_int
+        L.ora_value_is_null.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
+        L.ora_value_varchar.restype = C.c_void_p
+        L.ora_value_varchar.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
         L.ora_arrow_fixed.restype = C.c_int
         L.ora_arrow_fixed.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.ora_arrow_string.restype = C.c_int
@@ -139,6 +143,19 @@ class OracleResult:
 
     def get_column(self, kind: str, col: int, nullable: bool = False) -> bytes:
         return self._getter(f"ora_arrow_get_column_{kind}{'_nullable' if nullable else ''}", col)
+
+    def cell_is_null(self, col: int, row: int) -> bool:
+        """duckdb_mb_result_is_null (src/duckdb_native.c:215-222)"""
+        return bool(lib().ora_value_is_null(self.handle, col, row))
+
+    def cell_value(self, col: int, row: int) -> bytes:
+        """duckdb_mb_result_value (src/duckdb_native.c:224-238): duckdb_value_varchar, empty Bytes for NULL"""
+        p = lib().ora_value_varchar(self.handle, col, row)
+        if not p:
+            return b""
+        out = C.string_at(p)
+        lib().ora_free(p)
+        return out
 
     def schema(self) -> bytes:
         L = lib()
