@@ -8,7 +8,7 @@
 // prefix + pointer to the slot), so the rendered column then flows through the same
 // string_batch_kernel (utf8 offsets + data, or the reference's NUL-terminated blob) as a VARCHAR
 // column.  Formats follow DuckDB 1.4's renderings pinned by src/duckdb_fixture_cases.mbt
-// (ints :27-32,83-102, DATE :41-46, TIMESTAMP :55-67, DECIMAL :69-81).
+// (ints :27-32,83-102, HUGEINT sums :34-37,174-177, DATE :41-46, TIME :48-51, TIMESTAMP :55-67, DECIMAL :69-81).
 
 #include "dmb_common.cuh"
 
@@ -96,6 +96,52 @@ __device__ __forceinline__ void render_timestamp(TextBuf &t, int64_t v, int64_t 
   if (tz) t.push_str("+00");
 }
 
+// TIME: HH:MM:SS[.fraction], fraction digits trimmed of trailing zeros (fixture src/duckdb_fixture_cases.mbt:48-51)
+__device__ __forceinline__ void render_time(TextBuf &t, int64_t v, int64_t unit_per_sec) {
+  const int64_t secs = v / unit_per_sec, frac = v % unit_per_sec;
+  t.push_u64((uint64_t)(secs / 3600), 2);
+  t.push(':');
+  t.push_u64((uint64_t)(secs / 60 % 60), 2);
+  t.push(':');
+  t.push_u64((uint64_t)(secs % 60), 2);
+  if (frac != 0) {
+    int digits = unit_per_sec == 1000000 ? 6 : 9;
+    uint64_t f = (uint64_t)frac;
+    while (digits > 0 && f % 10ull == 0ull) { f /= 10ull; --digits; }
+    t.push('.');
+    t.push_u64(f, digits);
+  }
+}
+
+// 128-bit integers (HUGEINT: what SUM() of an integer column returns, fixtures :34-37; UHUGEINT;
+// DECIMAL(19..38, scale)): three base-10^19 limbs, '.' before the last `scale` digits
+__device__ __forceinline__ void render_i128(TextBuf &t, unsigned __int128 u, bool is_signed, int scale) {
+  const bool neg = is_signed && (__int128)u < 0;
+  unsigned __int128 a = neg ? (unsigned __int128)0 - u : u;
+  const unsigned __int128 kP19 = 10000000000000000000ull;
+  char d[40];  // least significant digit first
+  int n = 0;
+#pragma unroll 1
+  for (int limb = 0; limb < 3; ++limb) {
+    uint64_t r = (uint64_t)(a % kP19);
+    a /= kP19;
+    const bool last = a == 0;
+    for (int i = 0; i < 19 && n < 39; ++i) {
+      if (last && r == 0ull && i > 0) break;
+      d[n++] = (char)('0' + (int)(r % 10ull));
+      r /= 10ull;
+    }
+    if (last) break;
+  }
+  if (n == 0) d[n++] = '0';
+  while (n <= scale && n < 40) d[n++] = '0';  // at least one digit before the point
+  if (neg) t.push('-');
+  for (int i = n - 1; i >= 0; --i) {
+    t.push(d[i]);
+    if (scale > 0 && i == scale) t.push('.');
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 render_text_kernel(dmb_render_job job, const uint32_t *__restrict__ counts, int64_t nchunks) {
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -123,6 +169,11 @@ render_text_kernel(dmb_render_job job, const uint32_t *__restrict__ counts, int6
           case DMB_PHYS_U64: u = reinterpret_cast<const uint64_t *>(in)[i]; v = (int64_t)u; break;
           default: break;
         }
+        unsigned __int128 wide = 0;
+        if (job.phys == DMB_PHYS_I128 || job.phys == DMB_PHYS_U128) {
+          const uint4 q = reinterpret_cast<const uint4 *>(in)[i];
+          wide = ((unsigned __int128)(((uint64_t)q.w << 32) | q.z) << 64) | (((uint64_t)q.y << 32) | q.x);
+        }
         switch (job.type_id) {
           case DMB_TYPE_BOOLEAN: t.push_str(u ? "true" : "false"); break;
           case DMB_TYPE_UBIGINT: t.push_u64(u, 1); break;
@@ -132,7 +183,13 @@ render_text_kernel(dmb_render_job job, const uint32_t *__restrict__ counts, int6
           case DMB_TYPE_TIMESTAMP_S: render_timestamp(t, v, 1, false); break;
           case DMB_TYPE_TIMESTAMP_MS: render_timestamp(t, v, 1000, false); break;
           case DMB_TYPE_TIMESTAMP_NS: render_timestamp(t, v, 1000000000, false); break;
-          case DMB_TYPE_DECIMAL: render_decimal(t, v, job.dec_scale); break;
+          case DMB_TYPE_DECIMAL:
+            if (job.phys == DMB_PHYS_I128) render_i128(t, wide, true, job.dec_scale); else render_decimal(t, v, job.dec_scale);
+            break;
+          case DMB_TYPE_HUGEINT: render_i128(t, wide, true, 0); break;
+          case DMB_TYPE_UHUGEINT: render_i128(t, wide, false, 0); break;
+          case DMB_TYPE_TIME: render_time(t, v, 1000000); break;
+          case DMB_TYPE_TIME_NS: render_time(t, v, 1000000000); break;
           default: render_i64(t, v); break;  // TINYINT .. BIGINT, UTINYINT .. UINTEGER
         }
         // string_t: length, then 12 inlined bytes or 4-byte prefix + pointer to the slot
@@ -174,8 +231,12 @@ extern "C" int32_t dmb_render_supported(int32_t type_id, int32_t phys) {
     case DMB_TYPE_TIMESTAMP: case DMB_TYPE_TIMESTAMP_TZ: case DMB_TYPE_TIMESTAMP_S: case DMB_TYPE_TIMESTAMP_MS:
     case DMB_TYPE_TIMESTAMP_NS:
       return 1;
-    case DMB_TYPE_DECIMAL: return phys == DMB_PHYS_I16 || phys == DMB_PHYS_I32 || phys == DMB_PHYS_I64;
-    default: return 0;  // FLOAT/DOUBLE (shortest round-trip), HUGEINT, INTERVAL, TIME*, UUID, BLOB: not rendered on the device
+    case DMB_TYPE_TIME: case DMB_TYPE_TIME_NS:
+      return phys == DMB_PHYS_I64;
+    case DMB_TYPE_HUGEINT: return phys == DMB_PHYS_I128;
+    case DMB_TYPE_UHUGEINT: return phys == DMB_PHYS_U128;
+    case DMB_TYPE_DECIMAL: return phys == DMB_PHYS_I16 || phys == DMB_PHYS_I32 || phys == DMB_PHYS_I64 || phys == DMB_PHYS_I128;
+    default: return 0;  // FLOAT/DOUBLE (shortest round-trip), INTERVAL, TIME_TZ, UUID, BLOB: not rendered on the device
   }
 }
 

@@ -168,6 +168,8 @@ static void ora_materialise(ora_result *r) {
  * 2478,2538,2541.)  Same-family casts are pinned by src/duckdb_arrow_test.mbt; the rest UNPINNED. */
 typedef struct { uint64_t lo; int64_t hi; } ora_hugeint;
 int ora_render_cell(const ora_column *c, const uint8_t *p, char *out);
+int ora_render_time(int64_t v, int64_t unit_per_sec, char *out);
+int ora_render_decimal128(unsigned __int128 u, int is_signed, int scale, char *out);
 
 __attribute__((noinline)) int ora_value_is_null(ora_result *r, int32_t col, int64_t row) {
   if (!r->materialised) ora_materialise(r);
@@ -775,6 +777,38 @@ int ora_render_timestamp(int64_t v, int64_t unit_per_sec, int tz, char *out) {
   if (tz) n += sprintf(out + n, "+00");
   return n;
 }
+/* TIME: HH:MM:SS[.fraction], fraction digits trimmed like the time part of a TIMESTAMP */
+int ora_render_time(int64_t v, int64_t unit_per_sec, char *out) {
+  int64_t secs = v / unit_per_sec, frac = v % unit_per_sec;
+  int n = sprintf(out, "%02d:%02d:%02d", (int)(secs / 3600), (int)(secs / 60 % 60), (int)(secs % 60));
+  if (frac != 0) {
+    int digits = unit_per_sec == 1000000 ? 6 : 9;
+    char f[16];
+    sprintf(f, "%0*lld", digits, (long long)frac);
+    int L = digits;
+    while (L > 0 && f[L - 1] == '0') L--;
+    f[L] = 0;
+    n += sprintf(out + n, ".%s", f);
+  }
+  return n;
+}
+/* 128-bit integers (HUGEINT, UHUGEINT, DECIMAL(19..38, scale)): sign, digits, '.' before the last `scale` digits */
+int ora_render_decimal128(unsigned __int128 u, int is_signed, int scale, char *out) {
+  char digits[48];
+  int neg = is_signed && (__int128)u < 0;
+  unsigned __int128 a = neg ? (unsigned __int128)0 - u : u;
+  int n = 0;
+  do { digits[n++] = (char)('0' + (int)(a % 10)); a /= 10; } while (a != 0);
+  while (n <= scale) digits[n++] = '0';  /* at least one digit before the point */
+  int pos = 0;
+  if (neg) out[pos++] = '-';
+  for (int i = n - 1; i >= 0; i--) {
+    out[pos++] = digits[i];
+    if (scale > 0 && i == scale) out[pos++] = '.';
+  }
+  out[pos] = 0;
+  return pos;
+}
 int ora_render_decimal64(int64_t v, int scale, char *out) {
   char digits[32];
   int neg = v < 0;
@@ -853,8 +887,13 @@ int ora_render_cell(const ora_column *c, const uint8_t *p, char *out) {
     case T_TIMESTAMP_MS: { int64_t v; memcpy(&v, p, 8); return ora_render_timestamp(v, 1000, 0, out); }
     case T_TIMESTAMP_NS: { int64_t v; memcpy(&v, p, 8); return ora_render_timestamp(v, 1000000000, 0, out); }
     case T_DECIMAL:
-      if (c->phys == P_I128) return -1;
+      if (c->phys == P_I128) { unsigned __int128 u; memcpy(&u, p, 16); return ora_render_decimal128(u, 1, c->dec_scale, out); }
       return ora_render_decimal64(load_i64(c, p, &ok), c->dec_scale, out);
+    /* HUGEINT: what SUM() of an integer column returns (fixtures :34-37, :174-177) */
+    case T_HUGEINT: { unsigned __int128 u; memcpy(&u, p, 16); return ora_render_decimal128(u, 1, 0, out); }
+    case T_UHUGEINT: { unsigned __int128 u; memcpy(&u, p, 16); return ora_render_decimal128(u, 0, 0, out); }
+    case T_TIME: { int64_t v; memcpy(&v, p, 8); return ora_render_time(v, 1000000, out); }   /* fixture :48-51 */
+    case T_TIME_NS: { int64_t v; memcpy(&v, p, 8); return ora_render_time(v, 1000000000, out); }
     default: return -1;
   }
 }

@@ -17,7 +17,7 @@ from duckdb_mbt_b200 import chunks as ch  # noqa: E402
 from test_gpu_l0_parity import _mixed_batch  # noqa: E402
 from test_oracle_golden import batch_of  # noqa: E402
 
-RENDERED = {"b", "i8", "i16", "i32", "i64", "u8", "u16", "u32", "u64", "dec4", "dec9", "dec18", "date", "ts_s", "ts_ms", "ts_ns"}
+RENDERED = {"b", "i8", "i16", "i32", "i64", "u8", "u16", "u32", "u64", "huge", "dec4", "dec9", "dec18", "date", "ts_s", "ts_ms", "ts_ns"}
 
 
 @pytest.fixture(scope="module")

@@ -17,7 +17,7 @@ from duckdb_mbt_b200 import chunks as ch  # noqa: E402
 from test_gpu_l0_parity import _mixed_batch  # noqa: E402
 from test_oracle_golden import batch_of  # noqa: E402
 
-RENDERED = {"b", "i8", "i16", "i32", "i64", "u8", "u16", "u32", "u64", "dec4", "dec9", "dec18", "date", "ts_s", "ts_ms", "ts_ns"}
+RENDERED = {"b", "i8", "i16", "i32", "i64", "u8", "u16", "u32", "u64", "huge", "dec4", "dec9", "dec18", "date", "ts_s", "ts_ms", "ts_ns"}
 
 
 @pytest.fixture(scope="module")
@@ -52,7 +52,7 @@ def test_string_getter_on_fixed_width_columns(ctx, n, pattern):
         assert seen == len(RENDERED)
         # types whose libduckdb rendering is not reproduced on the device: empty Bytes + error, never a guess
         from duckdb_mbt_b200 import native as nat
-        for name in ("f64", "huge", "iv", "uuid"):
+        for name in ("f64", "iv", "uuid"):
             j = [c.name for c in batch.columns].index(name)
             assert res.raw_column("string", j) == b""
             assert "not reproduced" in nat.last_error()
@@ -135,3 +135,55 @@ def test_query_result_string_form(ctx):
         assert t.get_int(0, 0) == 1 and t.is_null(2, 0)
         assert t.get_date(0, 2) == 19877
         assert t.get_string(0, 3) == "10.50"
+
+
+def _wide(vals):
+    a = np.zeros((len(vals), 16), np.uint8)
+    for i, v in enumerate(vals):
+        a[i] = np.frombuffer((v & ((1 << 128) - 1)).to_bytes(16, "little"), np.uint8)
+    return a
+
+
+def test_hugeint_time_and_wide_decimal_renderings(ctx):
+    # HUGEINT is what SUM() over an integer column returns: src/duckdb_fixture_cases.mbt:34-37 ("6"), :174-177 ("15");
+    # TIME '12:34:56.789' :48-51
+    from duckdb_mbt_b200 import typed_result as tr
+    n = 4
+    counts = ch.chunk_counts(n)
+    cols = [ch.fixed_column("h", ch.T_HUGEINT, _wide([6, 15, 2**127 - 1, -2**127]), counts),
+            ch.fixed_column("u", ch.T_UHUGEINT, _wide([0, 2**128 - 1, 10**19, 10**38]), counts),
+            ch.fixed_column("t", ch.T_TIME, np.asarray([45296789000, 0, 86399999999, 1], np.int64), counts),
+            ch.fixed_column("tn", ch.T_TIME_NS, np.asarray([45296789000000, 0, 86399999999999, 1000], np.int64), counts),
+            ch.fixed_column("d", ch.T_DECIMAL, _wide([5, -5, 10**37, -123456789012345678901234567890]), counts, dec_width=38, dec_scale=3)]
+    expect = [["6", "15", "170141183460469231731687303715884105727", "-170141183460469231731687303715884105728"],
+              ["0", "340282366920938463463374607431768211455", "10000000000000000000", "100000000000000000000000000000000000000"],
+              ["12:34:56.789", "00:00:00", "23:59:59.999999", "00:00:00.000001"],
+              ["12:34:56.789", "00:00:00", "23:59:59.999999999", "00:00:00.000001"],
+              ["0.005", "-0.005", "10000000000000000000000000000000000.000", "-123456789012345678901234567.890"]]
+    batch = ch.ChunkBatch(counts, cols)
+    ora = oracle.OracleResult(batch)
+    with _result(ctx, batch) as res:
+        for j, exp in enumerate(expect):
+            t = tr.text_column(res, j)
+            assert [t.value(i).as_string() for i in range(n)] == exp, j
+            assert [ora.cell_value(j, i).decode() for i in range(n)] == exp, j
+        # HUGEINT / DECIMAL(38) / TIME stay Value::String in the reference's typed result (src/duckdb_parsing.mbt:120-141)
+        assert tr.typed_column(res, 0).tag == tr.STRING and tr.typed_column(res, 0).value(0).as_string() == "6"
+        assert tr.typed_column(res, 2).value(0).as_string() == "12:34:56.789"
+
+
+def test_random_hugeint_column_against_the_oracle(ctx):
+    rng = np.random.default_rng(21)
+    n = 9000
+    counts = ch.chunk_counts(n, "ragged", rng)
+    valid = rng.random(n) > 0.2
+    raw = rng.integers(0, 256, (n, 16), dtype=np.uint8)
+    raw[rng.random(n) < 0.3, 8:] = 0          # small positive values too
+    raw[rng.random(n) < 0.1, 1:] = 0
+    batch = ch.ChunkBatch(counts, [ch.fixed_column("h", ch.T_HUGEINT, raw, counts, valid=valid, garbage_rng=rng),
+                                   ch.fixed_column("d", ch.T_DECIMAL, raw.copy(), counts, valid=valid, dec_width=30, dec_scale=7, garbage_rng=rng)])
+    ora = oracle.OracleResult(batch)
+    with _result(ctx, batch) as res:
+        for j in range(2):
+            for nullable in (False, True):
+                assert res.raw_column("string", j, nullable) == ora.get_column("string", j, nullable), (j, nullable)

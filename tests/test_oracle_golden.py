@@ -175,6 +175,17 @@ def test_fixture_renderings(type_id, value, scale, text):
         assert tags[0] == 0 and iv[0] == oracle.parse_int(text)
 
 
+def test_fixture_time_and_hugeint_renderings():
+    # :48-51 TIME '12:34:56.789'; :34-37 / :174-177 sum() -> HUGEINT "6" / "15"
+    one = ch.chunk_counts(2)
+    wide = np.zeros((2, 16), np.uint8)
+    wide[0, 0], wide[1, 0] = 6, 15
+    r = oracle.OracleResult(ch.ChunkBatch(one, [ch.fixed_column("t", ch.T_TIME, np.asarray([45296789000, 0], np.int64), one),
+                                                ch.fixed_column("s", ch.T_HUGEINT, wide, one)]))
+    assert r.cell_value(0, 0) == b"12:34:56.789" and r.cell_value(0, 1) == b"00:00:00"
+    assert r.cell_value(1, 0) == b"6" and r.cell_value(1, 1) == b"15"
+
+
 def test_fixture_timestamp_and_decimal_renderings():
     micros = (19877 * 86400 + 12 * 3600 + 34 * 60 + 56) * 1_000_000 + 789_000
     assert oracle.render_timestamp(micros) == "2024-06-03 12:34:56.789"       # :55-60
