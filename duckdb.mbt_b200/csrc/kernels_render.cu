@@ -142,6 +142,147 @@ __device__ __forceinline__ void render_i128(TextBuf &t, unsigned __int128 u, boo
   }
 }
 
+// ---- DOUBLE / FLOAT: shortest decimal that reads back as the same double (what DuckDB's fmt-based
+// cast prints: "3.5", "5.333333333333333", src/duckdb_fixture_cases.mbt:20-25,167-172,216-221),
+// by Ryu (Ulf Adams, PLDI 2018): one 64x128-bit multiplication by a tabulated power of 5 gives the
+// decimal images of the value and of its two rounding-interval ends, then digits are dropped
+// while the ends still differ.  Tables: ryu_tables.inc (gen/make_ryu_tables.py).
+#include "ryu_tables.inc"
+
+__device__ __forceinline__ uint64_t ryu_mul_shift(uint64_t m, const unsigned long long *mul, int j) {
+  const unsigned __int128 b0 = (unsigned __int128)m * __ldg(mul);
+  const unsigned __int128 b2 = (unsigned __int128)m * __ldg(mul + 1);
+  return (uint64_t)(((b0 >> 64) + b2) >> (j - 64));
+}
+__device__ __forceinline__ bool ryu_multiple_of_pow5(uint64_t v, int p) {
+  int c = 0;
+  while (v != 0ull && v % 5ull == 0ull) { v /= 5ull; ++c; }
+  return c >= p;
+}
+// bits of a finite non-zero double -> (digits, exponent): value = digits * 10^exponent, digits shortest
+__device__ __forceinline__ uint64_t ryu_shortest(uint64_t bits, int &exp10) {
+  const uint64_t ieee_m = bits & ((1ull << 52) - 1ull);
+  const int ieee_e = (int)((bits >> 52) & 0x7ffu);
+  int e2;
+  uint64_t m2;
+  if (ieee_e == 0) { e2 = 1 - 1023 - 52 - 2; m2 = ieee_m; }
+  else { e2 = ieee_e - 1023 - 52 - 2; m2 = (1ull << 52) | ieee_m; }
+  const bool accept = (m2 & 1ull) == 0ull;  // round-to-even: the interval ends themselves read back
+  const uint64_t mv = 4ull * m2;
+  const uint32_t mm_shift = (ieee_m != 0ull || ieee_e <= 1) ? 1u : 0u;  // below a power of two the interval is half as wide
+  uint64_t vr, vp, vm;
+  int e10;
+  bool vm_tz = false, vr_tz = false;
+  if (e2 >= 0) {
+    const int q = ((e2 * 78913) >> 18) - (e2 > 3 ? 1 : 0);
+    e10 = q;
+    const int k = 125 + (((q * 1217359) >> 19) + 1) - 1;
+    const int i = -e2 + q + k;
+    const unsigned long long *mul = kRyuPow5InvSplit[q];
+    vr = ryu_mul_shift(mv, mul, i);
+    vp = ryu_mul_shift(mv + 2ull, mul, i);
+    vm = ryu_mul_shift(mv - 1ull - mm_shift, mul, i);
+    if (q <= 21) {
+      if (mv % 5ull == 0ull) vr_tz = ryu_multiple_of_pow5(mv, q);
+      else if (accept) vm_tz = ryu_multiple_of_pow5(mv - 1ull - mm_shift, q);
+      else vp -= ryu_multiple_of_pow5(mv + 2ull, q) ? 1ull : 0ull;
+    }
+  } else {
+    const int q = (((-e2) * 732923) >> 20) - (-e2 > 1 ? 1 : 0);
+    e10 = q + e2;
+    const int i = -e2 - q;
+    const int k = (((i * 1217359) >> 19) + 1) - 125;
+    const int j = q - k;
+    const unsigned long long *mul = kRyuPow5Split[i];
+    vr = ryu_mul_shift(mv, mul, j);
+    vp = ryu_mul_shift(mv + 2ull, mul, j);
+    vm = ryu_mul_shift(mv - 1ull - mm_shift, mul, j);
+    if (q <= 1) {
+      vr_tz = true;
+      if (accept) vm_tz = mm_shift == 1u;
+      else --vp;
+    } else if (q < 63) {
+      vr_tz = (mv & ((1ull << q) - 1ull)) == 0ull;
+    }
+  }
+  int removed = 0;
+  uint32_t last = 0;
+  uint64_t out;
+  if (vm_tz || vr_tz) {  // rare: exact decimal images, ties must be seen
+    while (vp / 10ull > vm / 10ull) {
+      vm_tz = vm_tz && vm % 10ull == 0ull;
+      vr_tz = vr_tz && last == 0u;
+      last = (uint32_t)(vr % 10ull);
+      vr /= 10ull; vp /= 10ull; vm /= 10ull;
+      ++removed;
+    }
+    if (vm_tz) {
+      while (vm % 10ull == 0ull) {
+        vr_tz = vr_tz && last == 0u;
+        last = (uint32_t)(vr % 10ull);
+        vr /= 10ull; vp /= 10ull; vm /= 10ull;
+        ++removed;
+      }
+    }
+    if (vr_tz && last == 5u && vr % 2ull == 0ull) last = 4u;  // exactly half: round to even
+    out = vr + (((vr == vm && (!accept || !vm_tz)) || last >= 5u) ? 1ull : 0ull);
+  } else {
+    bool round_up = false;
+    while (vp / 10ull > vm / 10ull) {
+      round_up = vr % 10ull >= 5ull;
+      vr /= 10ull; vp /= 10ull; vm /= 10ull;
+      ++removed;
+    }
+    out = vr + ((vr == vm || round_up) ? 1ull : 0ull);
+  }
+  exp10 = e10 + removed;
+  return out;
+}
+
+// fmt-style layout of the digits: fixed notation for 1e-5 <= |v| < 1e16 (always with a fraction:
+// "1.0"), else d.ddde+XX (at least two exponent digits)
+__device__ __forceinline__ void render_double(TextBuf &t, double v) {
+  const uint64_t bits = (uint64_t)__double_as_longlong(v);
+  if (((bits >> 52) & 0x7ffu) == 0x7ffu) {
+    if (bits & ((1ull << 52) - 1ull)) t.push_str("nan");
+    else t.push_str((bits >> 63) ? "-inf" : "inf");
+    return;
+  }
+  uint64_t digits = 0;
+  int e = 0;
+  if (bits & ~(1ull << 63)) digits = ryu_shortest(bits, e);
+  while (digits != 0ull && digits % 10ull == 0ull) { digits /= 10ull; ++e; }
+  char m[20];  // most significant digit first
+  int nd = 0;
+  {
+    char r[20];
+    uint64_t x = digits;
+    do { r[nd++] = (char)('0' + (int)(x % 10ull)); x /= 10ull; } while (x != 0ull);
+    for (int i = 0; i < nd; ++i) m[i] = r[nd - 1 - i];
+  }
+  const int x10 = e + nd - 1;  // scientific exponent
+  if (bits >> 63) t.push('-');
+  if (x10 >= -5 && x10 < 16) {
+    if (x10 >= 0) {
+      for (int i = 0; i <= x10; ++i) t.push(i < nd ? m[i] : '0');
+      t.push('.');
+      if (nd > x10 + 1) { for (int i = x10 + 1; i < nd; ++i) t.push(m[i]); }
+      else t.push('0');
+    } else {
+      t.push('0');
+      t.push('.');
+      for (int i = 0; i < -x10 - 1; ++i) t.push('0');
+      for (int i = 0; i < nd; ++i) t.push(m[i]);
+    }
+    return;
+  }
+  t.push(m[0]);
+  if (nd > 1) { t.push('.'); for (int i = 1; i < nd; ++i) t.push(m[i]); }
+  t.push('e');
+  t.push(x10 < 0 ? '-' : '+');
+  t.push_u64((uint64_t)(x10 < 0 ? -x10 : x10), 2);
+}
+
 __global__ void __launch_bounds__(kThreads)
 render_text_kernel(dmb_render_job job, const uint32_t *__restrict__ counts, int64_t nchunks) {
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -169,6 +310,9 @@ render_text_kernel(dmb_render_job job, const uint32_t *__restrict__ counts, int6
           case DMB_PHYS_U64: u = reinterpret_cast<const uint64_t *>(in)[i]; v = (int64_t)u; break;
           default: break;
         }
+        double fv = 0.0;
+        if (job.phys == DMB_PHYS_F64) fv = reinterpret_cast<const double *>(in)[i];
+        if (job.phys == DMB_PHYS_F32) fv = (double)reinterpret_cast<const float *>(in)[i];  // the oracle widens first (UNPINNED)
         unsigned __int128 wide = 0;
         if (job.phys == DMB_PHYS_I128 || job.phys == DMB_PHYS_U128) {
           const uint4 q = reinterpret_cast<const uint4 *>(in)[i];
@@ -186,6 +330,7 @@ render_text_kernel(dmb_render_job job, const uint32_t *__restrict__ counts, int6
           case DMB_TYPE_DECIMAL:
             if (job.phys == DMB_PHYS_I128) render_i128(t, wide, true, job.dec_scale); else render_decimal(t, v, job.dec_scale);
             break;
+          case DMB_TYPE_FLOAT: case DMB_TYPE_DOUBLE: render_double(t, fv); break;
           case DMB_TYPE_HUGEINT: render_i128(t, wide, true, 0); break;
           case DMB_TYPE_UHUGEINT: render_i128(t, wide, false, 0); break;
           case DMB_TYPE_TIME: render_time(t, v, 1000000); break;
@@ -233,10 +378,12 @@ extern "C" int32_t dmb_render_supported(int32_t type_id, int32_t phys) {
       return 1;
     case DMB_TYPE_TIME: case DMB_TYPE_TIME_NS:
       return phys == DMB_PHYS_I64;
+    case DMB_TYPE_FLOAT: return phys == DMB_PHYS_F32;
+    case DMB_TYPE_DOUBLE: return phys == DMB_PHYS_F64;
     case DMB_TYPE_HUGEINT: return phys == DMB_PHYS_I128;
     case DMB_TYPE_UHUGEINT: return phys == DMB_PHYS_U128;
     case DMB_TYPE_DECIMAL: return phys == DMB_PHYS_I16 || phys == DMB_PHYS_I32 || phys == DMB_PHYS_I64 || phys == DMB_PHYS_I128;
-    default: return 0;  // FLOAT/DOUBLE (shortest round-trip), INTERVAL, TIME_TZ, UUID, BLOB: not rendered on the device
+    default: return 0;  // INTERVAL, TIME_TZ, UUID, BLOB: not rendered on the device
   }
 }
 

@@ -217,7 +217,7 @@ int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_t *counts,
  * column can be fed to dmb_dev_string_batch like a VARCHAR column.  Replaces libduckdb's
  * duckdb_value_varchar / duckdb_value_to_string at the reference's call sites
  * src/duckdb_native.c:224-238, :2478, :2715 and :305-318.  Rendered: BOOLEAN, the eight integer
- * types, HUGEINT, UHUGEINT, DATE, TIME, TIME_NS, TIMESTAMP / _TZ / _S / _MS / _NS, DECIMAL (any storage). */
+ * types, HUGEINT, UHUGEINT, FLOAT, DOUBLE (shortest round trip), DATE, TIME, TIME_NS, TIMESTAMP / _TZ / _S / _MS / _NS, DECIMAL (any storage). */
 #define DMB_RENDER_SLOT_BYTES 48
 typedef struct dmb_render_job {
   const void *in_data;         /* column slab */

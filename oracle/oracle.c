@@ -838,6 +838,35 @@ int ora_render_double(double v, char *out) {
   for (prec = 1; prec <= 17; prec++) {
     snprintf(buf, sizeof buf, "%.*e", prec - 1, v);
     if (strtod(buf, NULL) == v) break;
+    /* the correctly rounded prec-digit decimal is the closest one, but below a power of two the
+     * rounding interval is half as wide as above it: the next prec-digit decimal up (or down) may
+     * still read back as v although the closest does not.  Shortest round trip takes it. */
+    {
+      char *ee = strchr(buf, 'e');
+      int x10 = atoi(ee + 1), ng = buf[0] == '-';
+      unsigned long long m = 0;
+      for (char *q = buf + ng; q < ee; q++) if (*q != '.') m = m * 10ull + (unsigned long long)(*q - '0');
+      int found = 0;
+      for (int step = 1; step >= -1 && !found; step -= 2) {
+        unsigned long long m2 = m + (unsigned long long)(long long)step;
+        char cand[48];
+        snprintf(cand, sizeof cand, "%s%llue%d", ng ? "-" : "", m2, x10 - (prec - 1));
+        if (m2 != 0 && strtod(cand, NULL) == v) {
+          /* renormalise: m2 may have gained a digit (99 -> 100) */
+          char digits[24];
+          int nd2 = snprintf(digits, sizeof digits, "%llu", m2);
+          int e2 = x10 + (nd2 - prec);
+          while (nd2 > 1 && digits[nd2 - 1] == '0') nd2--;
+          int pos2 = 0;
+          if (ng) buf[pos2++] = '-';
+          buf[pos2++] = digits[0];
+          if (nd2 > 1) { buf[pos2++] = '.'; memcpy(buf + pos2, digits + 1, (size_t)(nd2 - 1)); pos2 += nd2 - 1; }
+          snprintf(buf + pos2, sizeof buf - (size_t)pos2, "e%+03d", e2);
+          found = 1;
+        }
+      }
+      if (found) break;
+    }
   }
   /* buf = d.ddddde[+-]XX */
   char *e = strchr(buf, 'e');

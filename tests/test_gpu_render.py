@@ -17,7 +17,7 @@ from duckdb_mbt_b200 import chunks as ch  # noqa: E402
 from test_gpu_l0_parity import _mixed_batch  # noqa: E402
 from test_oracle_golden import batch_of  # noqa: E402
 
-RENDERED = {"b", "i8", "i16", "i32", "i64", "u8", "u16", "u32", "u64", "huge", "dec4", "dec9", "dec18", "date", "ts_s", "ts_ms", "ts_ns"}
+RENDERED = {"b", "i8", "i16", "i32", "i64", "u8", "u16", "u32", "u64", "f32", "f64", "huge", "dec4", "dec9", "dec18", "date", "ts_s", "ts_ms", "ts_ns"}
 
 
 @pytest.fixture(scope="module")
@@ -52,7 +52,7 @@ def test_string_getter_on_fixed_width_columns(ctx, n, pattern):
         assert seen == len(RENDERED)
         # types whose libduckdb rendering is not reproduced on the device: empty Bytes + error, never a guess
         from duckdb_mbt_b200 import native as nat
-        for name in ("f64", "iv", "uuid"):
+        for name in ("iv", "uuid"):
             j = [c.name for c in batch.columns].index(name)
             assert res.raw_column("string", j) == b""
             assert "not reproduced" in nat.last_error()
@@ -187,3 +187,43 @@ def test_random_hugeint_column_against_the_oracle(ctx):
         for j in range(2):
             for nullable in (False, True):
                 assert res.raw_column("string", j, nullable) == ora.get_column("string", j, nullable), (j, nullable)
+
+
+def test_double_shortest_round_trip_rendering(ctx):
+    # fixtures: "3.5" :20-25, "5.333333333333333" :167-172, nan / inf / -inf :209-214, "3.14159265359" ... :216-221;
+    # plus zeros, subnormals, extremes, powers of two (half-width rounding interval below them) and random bit patterns
+    import struct
+    from duckdb_mbt_b200 import typed_result as tr
+    fixed = [3.5, 16.0 / 3.0, float("nan"), float("inf"), float("-inf"), 3.14159265359, 2.71828182846, 1.41421356237,
+             0.0, -0.0, 1.0, -1.0, 0.1, 1e15, 1e16, 1e-5, 1e-6, 123456789012345678.0, 5e-324, 1.7976931348623157e308,
+             2.2250738585072014e-308, 9007199254740993.0, 1e22, 1e23, 7.120236347223045e-307, 999999.0, 0.3]
+    expect = ["3.5", "5.333333333333333", "nan", "inf", "-inf", "3.14159265359", "2.71828182846", "1.41421356237",
+              "0.0", "-0.0", "1.0", "-1.0", "0.1", "1000000000000000.0", "1e+16", "0.00001", "1e-06", "1.2345678901234568e+17",
+              "5e-324", "1.7976931348623157e+308", "2.2250738585072014e-308", "9007199254740992.0", "1e+22", "1e+23",
+              "7.120236347223045e-307", "999999.0", "0.3"]
+    rng = np.random.default_rng(33)
+    rnd = rng.integers(0, 2**64 - 1, 20000, dtype=np.uint64).view(np.float64)
+    pows = np.asarray([2.0 ** k for k in range(-1074, 1024)])
+    near = rng.standard_normal(10000) * 10.0 ** rng.integers(-12, 12, 10000)
+    ints = rng.integers(-10**9, 10**9, 5000).astype(np.float64)
+    vals = np.concatenate([np.asarray(fixed), rnd, pows, near, ints])
+    n = vals.shape[0]
+    counts = ch.chunk_counts(n)
+    f32 = (rng.standard_normal(n) * 1e3).astype(np.float32)
+    batch = ch.ChunkBatch(counts, [ch.fixed_column("d", ch.T_DOUBLE, vals, counts), ch.fixed_column("f", ch.T_FLOAT, f32, counts)])
+    ora = oracle.OracleResult(batch)
+    with _result(ctx, batch) as res:
+        t = tr.text_column(res, 0)
+        assert [t.value(i).as_string() for i in range(len(fixed))] == expect
+        for j in range(2):
+            t = tr.text_column(res, j)
+            got = [t.data[int(t.offsets[i]):int(t.offsets[i + 1])] for i in range(n)]
+            exp = [ora.cell_value(j, i) for i in range(n)]
+            bad = [i for i in range(n) if got[i] != exp[i]]
+            assert not bad, (j, bad[:5], [(got[i], exp[i]) for i in bad[:5]])
+        # every finite rendering reads back as the same double
+        t = tr.text_column(res, 0)
+        for i in rng.integers(0, n, 3000):
+            s_ = t.value(int(i)).as_string()
+            if s_ not in ("nan", "inf", "-inf"):
+                assert struct.pack("<d", float(s_)) == struct.pack("<d", float(vals[i])), (s_, vals[i])

@@ -175,6 +175,23 @@ def test_fixture_renderings(type_id, value, scale, text):
         assert tags[0] == 0 and iv[0] == oracle.parse_int(text)
 
 
+def test_double_rendering_is_the_shortest_round_trip():
+    # pins the oracle's digits to an independent implementation: Python's repr is the shortest decimal that reads
+    # back as the same double (the property DuckDB's fmt-based cast has); the layout (fixed / exponent) is the oracle's own
+    import struct
+    rng = np.random.default_rng(5)
+    vals = list(rng.integers(0, 2**64 - 1, 4000, dtype=np.uint64).view(np.float64)) + [2.0 ** k for k in range(-1074, 1024, 7)]
+    vals += list(rng.standard_normal(2000) * 10.0 ** rng.integers(-9, 9, 2000))
+    for v in vals:
+        v = float(v)
+        if v != v or v in (float("inf"), float("-inf")):
+            continue
+        text = oracle.render_double(v)
+        assert struct.pack("<d", float(text)) == struct.pack("<d", v), (v, text)
+        digits = lambda s_: s_.lower().split("e")[0].replace("-", "").replace(".", "").strip("0")
+        assert digits(text) == digits(repr(v)), (v, text, repr(v))
+
+
 def test_fixture_time_and_hugeint_renderings():
     # :48-51 TIME '12:34:56.789'; :34-37 / :174-177 sum() -> HUGEINT "6" / "15"
     one = ch.chunk_counts(2)
