@@ -145,3 +145,23 @@ def test_stream_chunks_nulls_and_whitelist(ctx):
     with _result(ctx, batch_of(("dec", ch.T_DECIMAL, [1], 10, 3))) as res:
         with pytest.raises(DuckDBError, match="unsupported column type"):
             ResultStream(res)
+
+
+def test_c1_string_form_and_typed(ctx):
+    # BASELINE.json configs[0]: SELECT i::INTEGER, i::DOUBLE, CASE WHEN i%7=0 THEN NULL [ELSE i] END FROM range(n):
+    # the string form Connection::query builds (every column rendered on the device) and the typed form
+    from duckdb_mbt_b200 import typed_result as tr
+    from duckdb_mbt_b200.query_result import QueryResult
+    n = 30_000
+    for variant_b in (False, True):
+        batch = ch.config_c1(n, variant_b=variant_b)
+        ora = oracle.OracleResult(batch)
+        with _result(ctx, batch) as res:
+            q = QueryResult.from_result(res, [c.type_id for c in batch.columns])
+            assert q.row_count() == n and q.column_count() == 3
+            for r in (0, 1, 6, 7, 14, 999, n - 1):
+                for c in range(3):
+                    assert q.cell(r, c) == (None if ora.cell_is_null(c, r) else ora.cell_value(c, r).decode()), (r, c)
+            assert q.cell(7, 0) == "7" and q.cell(7, 1) == "7.0" and q.cell(7, 2) is None
+            t = q.to_typed()
+            assert t.get_int(n - 1, 0) == n - 1 and t.get_double(n - 1, 1) == float(n - 1) and t.is_null(7, 2)
