@@ -521,6 +521,9 @@ constexpr int kLookWide = 8;          // status words in flight per lane in the 
 #endif
 constexpr int kLookFirst = DMB_LOOK_FIRST;  // ... in its first round
 constexpr int kMetaRing = 4;
+#ifndef DMB_NOHEAP_CTAS
+#define DMB_NOHEAP_CTAS 4
+#endif
 #ifndef DMB_PACK_UNROLL
 #define DMB_PACK_UNROLL 2
 #endif
@@ -712,7 +715,7 @@ struct RowState {
 };
 
 template <bool LARGE, int R, int NW, bool HEAP>
-__global__ void __launch_bounds__(NW * 32 + 128, NW == 8 ? 3 : 2)
+__global__ void __launch_bounds__(NW * 32 + 128, NW == 8 ? (HEAP ? 3 : DMB_NOHEAP_CTAS) : 2)
 string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles,
                    uint32_t ostage_bytes, uint32_t hstage_bytes) {
   constexpr int kWT = NW * 32;             // worker threads
@@ -875,7 +878,9 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       if (tile < 0) break;
       // a lazy look-back is a short one: by the time the workers have scanned tile k its predecessors'
       // aggregates (often their prefixes) are out, and the result is not needed before tile k-1 is packed
+#ifndef DMB_LOOK_EAGER
       mbar_wait(smem_u32(&pt.mbar_q[k & (kMetaRing - 1)]), (uint32_t)(k / kMetaRing) & 1u);
+#endif
       if (lane == 0) DMB_PTRACE(k, 8);
 #ifdef DMB_STR_TRACE
       unsigned lb_stats = 0;
