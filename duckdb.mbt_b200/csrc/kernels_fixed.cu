@@ -15,6 +15,10 @@
 
 #include "dmb_common.cuh"
 
+#ifndef DMB_GROUP_U
+#define DMB_GROUP_U 4  // 16-byte vectors in flight per thread in the narrow-type group path
+#endif
+
 namespace dmb {
 
 // ------------------------------------------------------------------ value conversions
@@ -170,7 +174,7 @@ template <typename S, typename D, typename F>
 __device__ __forceinline__ void convert_group(const dmb_fixed_job &job, const BatchView &b, int64_t c0, int G, F f) {
   constexpr int W = sizeof(S) > sizeof(D) ? sizeof(S) : sizeof(D);
   constexpr int R = 16 / W;
-  constexpr int U = 4;
+  constexpr int U = DMB_GROUP_U;
   constexpr int VPC = kVec / R;  // vectors per full chunk
   using PS = Pack<S, R>;
   using PD = Pack<D, R>;
@@ -317,7 +321,7 @@ struct GroupOf {
   static constexpr int W = sizeof(S) > sizeof(D) ? sizeof(S) : sizeof(D);
   static constexpr int R = 16 / W;
   // validity only: one tile per warp
-  static constexpr int value = KIND == kKindValidityOnly ? kThreads / 32 : ((KIND == kKindConvert && R >= 4) ? (kThreads * 4) / (kVec / R) : 1);
+  static constexpr int value = KIND == kKindValidityOnly ? kThreads / 32 : ((KIND == kKindConvert && R >= 4) ? (kThreads * DMB_GROUP_U) / (kVec / R) : 1);
 };
 
 template <typename S, typename D, typename F, int KIND>
@@ -478,7 +482,7 @@ extern "C" int32_t dmb_dev_fixed_batch(const dmb_fixed_job *jobs_dev, const dmb_
     else if ((jobs_host[j0].op & 0xff) != DMB_DST_BOOL_BITS) {
       const int wi = dmb_phys_width(jobs_host[j0].op >> 8), wo = dmb_op_out_width(jobs_host[j0].op);
       const int w = wi > wo ? wi : wo;
-      if (w > 0 && w <= 4) group = (kThreads * 4) / (kVec / (16 / w));
+      if (w > 0 && w <= 4) group = (kThreads * DMB_GROUP_U) / (kVec / (16 / w));
     }
     const int64_t items = (int64_t)(j1 - j0) * ((nchunks + group - 1) / group);
     const int grid = (int)(items < max_grid ? items : max_grid);
