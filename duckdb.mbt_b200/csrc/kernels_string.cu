@@ -1351,6 +1351,160 @@ string_inline_kernel(dmb_string_job job, BatchView b, unsigned long long *scratc
   }
 }
 
+// ------------------------------------------------------------------ columns without a heap, Arrow modes
+// string_short_kernel<LARGE, RPT>: flags, codes, short names (every string inlined in its string_t).
+// Rows cost 16 bytes in and 4 + len bytes out, so nothing but the per-tile dependent chain
+// (metadata -> string_t -> scan -> look-back -> stores) can keep the kernel from the HBM roofline.
+// One CTA per tile of RPT*256 rows, many CTAs per SM, no roles and no pipeline inside the CTA:
+//   * striped loads straight into registers (lane-consecutive rows: 512 contiguous bytes per request)
+//   * two stripes' lengths share one 32-bit scan (len <= 12, so a stripe sums to <= 384 < 2^16)
+//   * the tile's aggregate is published right after the block scan; warp 0 then resolves the prefix
+//     with the wide look-back (256 status words per L2 round trip) WHILE the other warps place their
+//     bytes in the stage at tile-local positions (byte stores: no zeroing, no read-modify-write)
+//   * the stage leaves as 16-byte vectors aligned to the destination; the shift between tile-local
+//     and destination alignment is a funnel shift on the way out
+template <bool LARGE, int RPT>
+__global__ void __launch_bounds__(kThreads, RPT >= 8 ? 4 : 5)
+string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles) {
+  constexpr int kRows = kThreads * RPT;
+  constexpr int kTilesPerChunk = kVec / kRows;
+  constexpr int kWarps = kThreads / 32;
+  __shared__ __align__(16) uint8_t stage[kRows * 12 + 32];
+  __shared__ uint32_t warp_sum[kWarps];
+  __shared__ uint64_t base_sh;
+  unsigned long long *status = scratch + 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tile = (int64_t)blockIdx.x;  // CTAs are dispatched in blockIdx order: every predecessor is running or done
+  if (tile >= ntiles) return;
+  const int64_t c = tile / kTilesPerChunk;
+  const int r_begin = (int)(tile % kTilesPerChunk) * kRows;
+  const int count = (int)__ldg(b.counts + c) - r_begin;  // rows of this tile that exist (may be <= 0)
+  const dmb_vec_desc vd = job.vecs[c];
+  const uint4 *in = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(job.in) + vd.data_off) + r_begin;
+  const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off + (r_begin >> 6);
+
+  // stripe k of warp w holds tile rows w*32*RPT + k*32 + lane
+  const int row0 = warp * (32 * RPT) + lane;
+  uint4 e[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int row = row0 + 32 * k;
+    e[k] = make_uint4(0, 0, 0, 0);
+    if (row < count) e[k] = ld_stream(in + row);
+  }
+  int bad = 0;
+  uint32_t lmax = 0;
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int row = row0 + 32 * k;
+    uint32_t l = 0;
+    if (row < count) {
+      const bool valid = mask ? ((__ldg(mask + (row >> 6)) >> (row & 63)) & 1ull) : true;
+      l = valid ? e[k].x : 0u;
+      if (l > 12u) { bad = 1; l = 0; }  // a pointer string, but the batch registered no heap
+    }
+    e[k].x = l;  // from here on: the bytes the row contributes
+    lmax = lmax > l ? lmax : l;
+  }
+  // exclusive offsets within the warp: stripes 2i and 2i+1 scanned together in 16-bit halves
+  uint32_t off[RPT];
+  uint32_t carry = 0;
+#pragma unroll
+  for (int k = 0; k < RPT; k += 2) {
+    const uint32_t both = e[k].x | (e[k + 1].x << 16);
+    uint32_t incl = both;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += n;
+    }
+    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t excl = incl - both;
+    off[k] = carry + (excl & 0xffffu);
+    carry += tot & 0xffffu;
+    off[k + 1] = carry + (excl >> 16);
+    carry += tot >> 16;
+  }
+  if (lane == 0) warp_sum[warp] = carry;
+  lmax = __reduce_max_sync(0xffffffffu, lmax);
+  const int any_bad = __syncthreads_or(bad);
+  uint32_t warp_excl = 0, tile_total = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    const uint32_t s = warp_sum[w];
+    warp_excl += w < warp ? s : 0u;
+    tile_total += s;
+  }
+  if (tid == 0) {
+    atomicExch(status + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)tile_total);
+    if (any_bad) atomicOr(scratch + 1, (unsigned long long)kErrHeapRange);
+  }
+  // place the bytes at their tile-local positions (stage byte q = byte q of the tile's output)
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) off[k] += warp_excl;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    if ((uint32_t)i < lmax) {  // warp-uniform
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const uint32_t wsel = i < 4 ? e[k].y : (i < 8 ? e[k].z : e[k].w);
+        if ((uint32_t)i < e[k].x) stage[off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
+      }
+    }
+  }
+  // decoupled look-back (warp 0)
+  if (warp == 0) {
+    const uint64_t prefix = lookback_wide(status, tile, lane);
+    if (lane == 0) {
+      if (tile > 0) atomicExch(status + tile, kFlagPrefix | ((prefix + tile_total) & kValueMask));
+      base_sh = prefix;
+    }
+  }
+  __syncthreads();
+  const uint64_t base = base_sh;
+  const int64_t out_row0 = __ldg(b.row_off + c) + r_begin;
+  if (tid == 0) {
+    if (!LARGE && base + tile_total > 0x7fffffffull) atomicOr(scratch + 1, (unsigned long long)kErrOffsetOverflow);
+    if (tile == ntiles - 1) {
+      if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[b.nrows] = (long long)(base + tile_total);
+      else reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)(base + tile_total);
+      if (job.total_bytes) *job.total_bytes = base + tile_total;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int row = row0 + 32 * k;
+    if (row < count) {
+      if (LARGE) __stcs(reinterpret_cast<long long *>(job.out_offsets) + out_row0 + row, (long long)(base + off[k]));
+      else __stcs(reinterpret_cast<int32_t *>(job.out_offsets) + out_row0 + row, (int32_t)((uint32_t)base + off[k]));
+    }
+  }
+  if (tile_total == 0) return;
+  // stage -> out_data: destination-aligned 16-byte vectors; vector v holds tile bytes [16v - mis, 16v - mis + 16)
+  uint8_t *gdst = job.out_data + base;
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
+  const uint32_t end = mis + tile_total;
+  const uint32_t nvec = (end + 15u) >> 4;
+  const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage);
+  for (uint32_t v = tid; v < nvec; v += kThreads) {
+    const uint32_t p = 16u * v;
+    if (p >= mis && p + 16u <= end) {
+      const uint32_t q = p - mis, sh = 8u * (q & 3u);
+      const uint32_t *s = sw + (q >> 2);
+      const uint32_t a0 = s[0], a1 = s[1], a2 = s[2], a3 = s[3], a4 = s[4];  // s[4]: inside the stage's 32 bytes of slack
+      uint4 o;
+      o.x = __funnelshift_r(a0, a1, sh);
+      o.y = __funnelshift_r(a1, a2, sh);
+      o.z = __funnelshift_r(a2, a3, sh);
+      o.w = __funnelshift_r(a3, a4, sh);
+      st_stream(reinterpret_cast<uint4 *>(gdst - mis + p), o);
+    } else {  // the neighbouring tiles own the other bytes of this vector
+      const uint32_t b0 = p > mis ? p : mis, b1 = (p + 16u) < end ? (p + 16u) : end;
+      for (uint32_t q = b0; q < b1; ++q) gdst[q - mis] = stage[q - mis];
+    }
+  }
+}
+
 // bench/test helper: DuckDB-shaped string_t from lengths + heap offsets
 __global__ void __launch_bounds__(kThreads)
 make_string_t_kernel(const uint32_t *__restrict__ lengths, const uint64_t *__restrict__ heap_off,
@@ -1423,7 +1577,17 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
       return check_cuda(cudaGetLastError(), "string_pack_kernel launch");
     };
     static const int force_nw = getenv("DMB_STR_PACK_NW") ? atoi(getenv("DMB_STR_PACK_NW")) : 0;
-    if (job->heap_len == 0) {  // inlined strings only: 4 rows per thread (1024-row tiles with 8 worker warps, 2048 with 16)
+    static const int short_rpt = getenv("DMB_STR_SHORT_RPT") ? atoi(getenv("DMB_STR_SHORT_RPT")) : 8;
+    if (job->heap_len == 0 && short_rpt > 0) {  // inlined strings only: one CTA per tile, prefix by look-back
+      auto launch_short = [&](auto kernel, int rows_per_tile) -> int32_t {
+        const int64_t nt = (int64_t)(kVec / rows_per_tile) * nchunks;
+        kernel<<<(unsigned)nt, kThreads, 0, st>>>(*job, b, (unsigned long long *)scratch, nt);
+        return check_cuda(cudaGetLastError(), "string_short_kernel launch");
+      };
+      if (short_rpt == 4) return large ? launch_short(string_short_kernel<true, 4>, 1024) : launch_short(string_short_kernel<false, 4>, 1024);
+      return large ? launch_short(string_short_kernel<true, 8>, 2048) : launch_short(string_short_kernel<false, 8>, 2048);
+    }
+    if (job->heap_len == 0) {  // (experiment: DMB_STR_SHORT_RPT=0) the pipeline below with 4 rows per thread
       if (force_nw != 16) {
         const uint32_t ob = ((1024u * 12u + 64u) + 127u) & ~127u;
         return large ? launch_pack(string_pack_kernel<true, 4, 8, false>, 1024, 8 * 32 + 128, ob, 0u) : launch_pack(string_pack_kernel<false, 4, 8, false>, 1024, 8 * 32 + 128, ob, 0u);
