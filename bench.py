@@ -13,7 +13,7 @@ torch.distributed (NCCL) is used for the barrier and the max-over-ranks timing o
   value      rows/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
   e2e        rows/s through the reference-facing C ABI (duckdb_mb_gpu_result_from_chunks +
              _materialise_arrow) with page-locked HOST buffers, H2D + kernels + D2H in the timed region
-  roofline   the dominant kernel (string_pack_kernel): algorithmic bytes / its CUDA-event time
+  roofline   the dominant kernel family (most device time in a step): algorithmic bytes / its CUDA-event time
   cpu_baseline  the oracle port of the reference's getters + decoders, 1 core, <= 1 M-row sample
 
 `--impl reference` times the reference's own CPU path (oracle port: the reference cannot be built
@@ -384,6 +384,9 @@ def run_ours(args, rank, local_rank, world):
         string_col_ms[nm] = sum((sp[1] if ci == 0 else sp[3][ci - 1]).elapsed_time(sp[3][ci]) for sp in spans) / args.steps
     string_col_alg = {db.batch.columns[so.col].name: 16 * n_rows_dev + db.meta[so.col]["ptr_len"] + 4 * (n_rows_dev + 1) + db.meta[so.col]["total_len"]
                       for so in step.strings} if (n_rows_dev := db.nrows) else {}
+    # which kernel a VARCHAR column goes to (kernels_string.cu, dmb_dev_string_batch): no heap -> string_short_kernel
+    string_col_kernel = {db.batch.columns[so.col].name: ("string_short_kernel" if db.meta[so.col]["ptr_len"] == 0 else "string_pack_kernel")
+                         for so in step.strings}
     dev_ms_max = max_over_ranks(dev_ms)
     value = world * n * args.steps / (dev_ms_max / 1e3)
     step_alg_fixed, step_alg_string = step.alg_fixed, step.alg_string
@@ -462,10 +465,15 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (string_pack_kernel: 5 launches per step, one per VARCHAR column)
-    dominant, dom_ms, dom_alg, dom_launches = "string_pack_kernel<utf8>", string_ms, step_alg_string, n_string_launches
-    if fixed_ms > string_ms:
-        dominant, dom_ms, dom_alg, dom_launches = "fixed_batch_kernel", fixed_ms, step_alg_fixed, n_fixed_launches
+    # ---- roofline of the dominant kernel: the family with the most device time in a step
+    families = {"fixed_batch_kernel": [fixed_ms, step_alg_fixed, n_fixed_launches]}
+    for nm, k in string_col_kernel.items():
+        f = families.setdefault(k, [0.0, 0, 0])
+        f[0] += string_col_ms[nm]
+        f[1] += string_col_alg[nm]
+        f[2] += 1
+    dominant = max(families, key=lambda k: families[k][0])
+    dom_ms, dom_alg, dom_launches = families[dominant]
     achieved = dom_alg / 1e6 / dom_ms  # GB/s: algorithmic bytes of the kernel's launches in a step / their device time
     traffic = None
     try:
@@ -501,9 +509,12 @@ def run_ours(args, rank, local_rank, world):
         "cpu_baseline": cpu,
         "gpu_launches": n_launches * args.steps,
         "clocks": clocks,
-        "kernel_ms_per_step": {"fixed_batch_kernel": fixed_ms, "string_pack_kernel": string_ms,
-                               "fixed_gb_per_s": step_alg_fixed / 1e6 / fixed_ms, "string_gb_per_s": step_alg_string / 1e6 / string_ms,
-                               "string_columns": {nm: {"ms": string_col_ms[nm], "gb_per_s": string_col_alg[nm] / 1e6 / string_col_ms[nm]}
+        "kernel_ms_per_step": {**{k: v[0] for k, v in families.items()},
+                               "families": {k: {"ms": v[0], "launches": v[2], "gb_per_s": v[1] / 1e6 / v[0], "frac": v[1] / 1e6 / v[0] / peak_gbs}
+                                            for k, v in families.items()},
+                               "string_ms": string_ms, "string_gb_per_s": step_alg_string / 1e6 / string_ms,
+                               "string_columns": {nm: {"kernel": string_col_kernel[nm], "ms": string_col_ms[nm],
+                                                       "gb_per_s": string_col_alg[nm] / 1e6 / string_col_ms[nm]}
                                                   for nm in string_col_ms}},
         "setup_s": setup_s,
     }

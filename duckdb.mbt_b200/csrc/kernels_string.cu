@@ -1363,8 +1363,11 @@ string_inline_kernel(dmb_string_job job, BatchView b, unsigned long long *scratc
 //     bytes in the stage at tile-local positions (byte stores: no zeroing, no read-modify-write)
 //   * the stage leaves as 16-byte vectors aligned to the destination; the shift between tile-local
 //     and destination alignment is a funnel shift on the way out
+#ifndef DMB_SHORT_CTAS8
+#define DMB_SHORT_CTAS8 4
+#endif
 template <bool LARGE, int RPT>
-__global__ void __launch_bounds__(kThreads, RPT >= 8 ? 4 : 5)
+__global__ void __launch_bounds__(kThreads, RPT >= 8 ? DMB_SHORT_CTAS8 : 5)
 string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles) {
   constexpr int kRows = kThreads * RPT;
   constexpr int kTilesPerChunk = kVec / kRows;
@@ -1439,6 +1442,29 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     atomicExch(status + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)tile_total);
     if (any_bad) atomicOr(scratch + 1, (unsigned long long)kErrHeapRange);
   }
+#ifdef DMB_SHORT_LB_FIRST
+  // decoupled look-back (warp 0)
+  if (warp == 0) {
+    const uint64_t prefix = lookback_wide(status, tile, lane);
+    if (lane == 0) {
+      if (tile > 0) atomicExch(status + tile, kFlagPrefix | ((prefix + tile_total) & kValueMask));
+      base_sh = prefix;
+    }
+  }
+  // place the bytes at their tile-local positions (stage byte q = byte q of the tile's output)
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) off[k] += warp_excl;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    if ((uint32_t)i < lmax) {  // warp-uniform
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const uint32_t wsel = i < 4 ? e[k].y : (i < 8 ? e[k].z : e[k].w);
+        if ((uint32_t)i < e[k].x) stage[off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
+      }
+    }
+  }
+#else
   // place the bytes at their tile-local positions (stage byte q = byte q of the tile's output)
 #pragma unroll
   for (int k = 0; k < RPT; ++k) off[k] += warp_excl;
@@ -1460,6 +1486,7 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
       base_sh = prefix;
     }
   }
+#endif
   __syncthreads();
   const uint64_t base = base_sh;
   const int64_t out_row0 = __ldg(b.row_off + c) + r_begin;

@@ -1,4 +1,4 @@
-"""profiles/traffic.json (read by bench.py: roofline.traffic) from the --set full capture of the five
+"""profiles/traffic.json (read by bench.py: roofline.traffic) from the --set full capture of the
 string_pack_kernel launches of one bench step.
 usage: python profiles/make_traffic.py gpurun_out/<tag>_bench_string_full.ncu-rep profiles/<tag>_bench_string_kernel_ncu_full.txt"""
 import csv, json, os, subprocess, sys
@@ -20,8 +20,8 @@ with open(txt, 'w') as f:
                 f.write(f"  {k:72s} {r[hdr.index(k)]:>16s} {units[hdr.index(k)]}\n")
         b = sum(float(r[hdr.index(k)]) * mult[units[hdr.index(k)]] for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
         tot.append(b)
-json.dump({"rows": 60000000, "kernel": "string_pack_kernel<utf8>", "dram_bytes_per_launch": int(sum(tot) / len(tot)),
-           "source": f"ncu --set full --clock-control none -k regex:string_pack -s 5 -c 5 python bench.py --steps 2 --warmup 1 --no-cpu "
-                     f"({os.path.basename(txt)}): dram__bytes_read.sum + dram__bytes_write.sum, mean over the five VARCHAR columns of one step",
+json.dump({"rows": 60000000, "kernel": "string_pack_kernel", "dram_bytes_per_launch": int(sum(tot) / len(tot)),
+           "source": f"ncu --set full --clock-control none -k regex:string_pack -s 2 -c 2 python bench.py --steps 2 --warmup 1 --no-cpu "
+                     f"({os.path.basename(txt)}): dram__bytes_read.sum + dram__bytes_write.sum, mean over the string_pack_kernel launches of one step (l_shipinstruct, l_comment)",
            "launches": len(tot)}, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'traffic.json'), 'w'), indent=1)
 print(open(txt).read())

@@ -41,6 +41,11 @@ def main():
         db.add_string(gen, 0.0, 13, 43)
         so = db.plan_string(0, 0, data_capacity=db.total_len)
         fn = lambda: db.run_string(so)  # noqa: E731
+    elif args.which == "string_mode":  # l_shipmode shape: 3..7 bytes inline
+        db = devgen.GeneratedBatch(n)
+        db.add_string(gen, 0.0, 0, 0, len_choices=[7, 3, 4, 4, 5, 4, 3])
+        so = db.plan_string(0, 0, data_capacity=db.total_len)
+        fn = lambda: db.run_string(so)  # noqa: E731
     elif args.which == "string_short":  # l_returnflag shape: 1 byte inline
         db = devgen.GeneratedBatch(n)
         db.add_string(gen, 0.0, 1, 1)
