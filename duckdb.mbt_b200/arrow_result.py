@@ -94,6 +94,8 @@ class HostBatch:
             heap_base, heap_len = None, 0
             if getattr(col, "heap", None) is not None and register_heap:
                 heap_base, heap_len = col.heap.ctypes.data, int(col.heap.shape[0])
+            elif getattr(col, "inline_only", False):
+                heap_base, heap_len = 1, 0  # DMB_HEAP_INLINE_ONLY
             self._keep.append((data_ptrs, val_ptrs, name))
             self._cols[j] = nat.HostColumn(name, col.type_id, col.phys, col.dec_width, col.dec_scale,
                                            C.cast(data_ptrs.ctypes.data, C.POINTER(C.c_void_p)),

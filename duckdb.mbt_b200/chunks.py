@@ -79,6 +79,7 @@ class Column:
     dec_width: int = 0
     dec_scale: int = 0
     heap: Optional[np.ndarray] = None  # uint8 string heap (VARCHAR/BLOB)
+    inline_only: bool = False          # VARCHAR/BLOB: every string is inlined (<= 12 bytes): DMB_HEAP_INLINE_ONLY
 
     @property
     def width(self) -> int:

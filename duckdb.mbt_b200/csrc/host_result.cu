@@ -203,7 +203,12 @@ int32_t stage_column(Result *r, int j) {
   CompactCtx cc{};
   std::vector<uint64_t> arena_start;
   if (col.phys == DMB_PHYS_STRING) {
-    if (col.heap_len > 0 && col.heap_base) {
+    if (col.heap_base == (const uint8_t *)DMB_HEAP_INLINE_ONLY && col.heap_len == 0) {
+      // the caller vouches for an all-inlined column: nothing to stage, the heap-less kernel checks every entry
+      col.d_heap = nullptr;
+      col.heap_host_base = 0;
+      col.d_heap_len = 0;
+    } else if (col.heap_len > 0 && col.heap_base) {
       // contiguous heap registered by the caller: copy wholesale, rebase pointers in the kernel
       col.d_heap = (uint8_t *)keep_dev(r, (size_t)col.heap_len + 32);
       if (!col.d_heap) return -1;

@@ -164,9 +164,11 @@ class GeneratedBatch(DeviceBatch):
                     raise ValueError("string column was generated without host_heap_alloc: its pointers are not host addresses")
                 nb = self.heap[j].numel()
                 torch.from_numpy(host_heap[:nb]).copy_(self.heap[j])
-                heap = host_heap[: self.meta[j]["heap_total"] + 16]
+                # a vector whose strings are all inlined owns no string heap (DuckDB allocates none): register none
+                heap = host_heap[: self.meta[j]["heap_total"] + 16] if self.meta[j]["heap_total"] > 0 else None
             cols.append(ch.Column(c.name, c.type_id, c.phys, data, vecs[:, 0].astype(np.uint64).copy(), validity,
-                                  vecs[:, 1].copy(), c.dec_width, c.dec_scale, heap))
+                                  vecs[:, 1].copy(), c.dec_width, c.dec_scale, heap,
+                                  inline_only=c.phys == ch.P_STRING and heap is None))
         torch.cuda.synchronize(self.device)
         return ch.ChunkBatch(counts, cols)
 

@@ -328,6 +328,12 @@ typedef struct dmb_host_column {
   uint64_t heap_len;
 } dmb_host_column;
 
+/* heap_base == DMB_HEAP_INLINE_ONLY (heap_len 0): the caller guarantees that every string of the
+ * column is inlined in its string_t (<= 12 bytes: flags, codes, CHAR(n <= 12)), so there is no heap
+ * to stage or compact and the heap-less kernel runs.  A pointer entry is then an error
+ * ("string_t pointer outside the registered heap"), never a wild read. */
+#define DMB_HEAP_INLINE_ONLY ((const void *)(uintptr_t)1)
+
 typedef struct dmb_host_batch {
   int32_t ncols;
   int32_t flags;           /* DMB_BATCH_* */

@@ -252,6 +252,44 @@ def test_scattered_heap_is_compacted_by_the_stager(ctx):
         assert res.raw_column("string", 0, True) == ora.get_column("string", 0, True)
 
 
+def test_inline_only_columns_skip_the_heap(ctx):
+    # DMB_HEAP_INLINE_ONLY: the caller vouches that every string is inlined; nothing is staged or compacted,
+    # the heap-less kernel runs (flags / codes: l_returnflag, l_shipmode shapes), NULLs and ragged chunks included
+    rng = np.random.default_rng(21)
+    n = 50_000
+    counts = ch.chunk_counts(n, "ragged", rng)
+    cols = [ch.string_column_bulk("flag", rng.integers(1, 2, n), None, counts, rng),
+            ch.string_column_bulk("mode", rng.integers(0, 13, n), rng.random(n) > 0.2, counts, rng, utf8_fraction=0.1)]
+    for c in cols:
+        c.heap = None
+        c.inline_only = True
+    batch = ch.ChunkBatch(counts, cols)
+    ora = oracle.OracleResult(batch)
+    with _result(ctx, batch) as res:
+        for j in range(2):
+            eo, ed = ora.arrow_string(j, 0)
+            arr = res.to_arrow(j)
+            assert np.array_equal(np.frombuffer(arr.buffers()[1], dtype=np.int32)[: n + 1], eo)
+            assert bytes(arr.buffers()[2])[: ed.shape[0]] == ed.tobytes()
+            arr.validate(full=True)
+            assert res.raw_column("string", j, True) == ora.get_column("string", j, True)
+
+
+def test_inline_only_contract_violation_is_an_error(ctx):
+    # a pointer string in a column declared inline-only must fail loudly, never read through the pointer
+    rng = np.random.default_rng(22)
+    n = 5000
+    counts = ch.chunk_counts(n, "full", rng)
+    lens = rng.integers(0, 13, n)
+    lens[1234] = 40
+    col = ch.string_column_bulk("s", lens, None, counts, rng)
+    col.heap = None
+    col.inline_only = True
+    with _result(ctx, ch.ChunkBatch(counts, [col])) as res:
+        with pytest.raises(Exception, match="heap"):
+            res.to_arrow(0)
+
+
 def test_pinned_inputs_take_the_direct_dma_path(ctx):
     from duckdb_mbt_b200 import pinned
     batch = ch.config_c2(40_000)
