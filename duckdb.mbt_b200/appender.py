@@ -136,6 +136,22 @@ class Appender:
     def append_timestamp(self, micros: int):
         self._check(self.lib.duckdb_mb_gpu_append_timestamp(self.handle, int(micros)), "append_timestamp")
 
+    def append_blob(self, data: bytes):  # src/duckdb_native.mbt:165-177 / src/duckdb_native.c:1397
+        self._check(self.lib.duckdb_mb_gpu_append_blob(self.handle, data, len(data)), "append_blob")
+
+    def set_decimal(self, col: int, width: int, scale: int):
+        """The table column's DECIMAL(width, scale) (what duckdb_appender_column_type reports)."""
+        self._check(self.lib.duckdb_mb_gpu_appender_set_decimal(self.handle, int(col), int(width), int(scale)), "set_decimal")
+
+    def append_decimal(self, width: int, scale: int, unscaled: int):  # src/duckdb_native.c:1447-1481 (hugeint parts)
+        lo = unscaled & 0xFFFFFFFFFFFFFFFF
+        hi = (unscaled >> 64) & 0xFFFFFFFFFFFFFFFF
+        as_i64 = lambda x: x - (1 << 64) if x >= (1 << 63) else x  # noqa: E731
+        self._check(self.lib.duckdb_mb_gpu_append_decimal(self.handle, int(width), int(scale), as_i64(lo), as_i64(hi)), "append_decimal")
+
+    def append_interval(self, months: int, days: int, micros: int):  # src/duckdb_native.c:1511-1533
+        self._check(self.lib.duckdb_mb_gpu_append_interval(self.handle, int(months), int(days), int(micros)), "append_interval")
+
     def end_row(self):  # :1052
         self._check(self.lib.duckdb_mb_gpu_end_row(self.handle), "end_row")
 

@@ -32,6 +32,7 @@ enum { kNotCreated = 0, kReady = 1, kRowInProgress = 2, kFlushed = 3, kClosed = 
 
 struct RowBuf {  // one column of buffered rows (row API)
   int width = 0;               // bytes per value; 0: string
+  int dec_prec = 0, dec_scale = 0;  // DECIMAL: the table column's precision / scale (0: not declared yet); values buffered as int128
   std::vector<uint8_t> values, valid;
   std::vector<int32_t> offsets;  // strings: n+1 entries
   std::vector<uint8_t> data;
@@ -104,6 +105,7 @@ int row_width(int32_t type_id) {
     case DMB_TYPE_TIMESTAMP_S: case DMB_TYPE_TIMESTAMP_MS: case DMB_TYPE_TIMESTAMP_NS: case DMB_TYPE_TIMESTAMP_TZ:
     case DMB_TYPE_TIME: case DMB_TYPE_TIME_NS: return 8;
     case DMB_TYPE_VARCHAR: case DMB_TYPE_BLOB: return 0;
+    case DMB_TYPE_INTERVAL: case DMB_TYPE_DECIMAL: return 16;  // DECIMAL: int128 in the buffer, narrowed on flush
     default: return -1;
   }
 }
@@ -388,6 +390,15 @@ int32_t flush_rows(App *a) {
       ci.rev_op = copy_op(rb.width);
       ci.w_in = ci.w_out = rb.width;
       ci.values = rb.values.data();
+      if (a->type_ids[(size_t)j] == DMB_TYPE_DECIMAL) {  // int128 -> the physical width DuckDB uses for the precision
+        if (rb.dec_prec <= 0) {
+          fail(a, "flush: DECIMAL column %d has no declared precision (duckdb_mb_gpu_appender_set_decimal)", j);
+          return 0;
+        }
+        if (rb.dec_prec <= 4) { ci.rev_op = DMB_REV_I128_TO_I16; ci.w_out = 2; }
+        else if (rb.dec_prec <= 9) { ci.rev_op = DMB_REV_I128_TO_I32; ci.w_out = 4; }
+        else if (rb.dec_prec <= 18) { ci.rev_op = DMB_REV_I128_TO_I64; ci.w_out = 8; }
+      }
     }
   }
   const int32_t ok = convert_rows(a, cols, a->buffered_rows);
@@ -562,6 +573,72 @@ extern "C" int32_t duckdb_mb_gpu_append_bigint(duckdb_mb_gpu_appender *a, int64_
 extern "C" int32_t duckdb_mb_gpu_append_double(duckdb_mb_gpu_appender *a, double v) { return a ? push_number(a, "append_double", 0, v, true) : 0; }
 extern "C" int32_t duckdb_mb_gpu_append_date(duckdb_mb_gpu_appender *a, int32_t days) { return a ? push_number(a, "append_date", days, 0, false) : 0; }
 extern "C" int32_t duckdb_mb_gpu_append_timestamp(duckdb_mb_gpu_appender *a, int64_t micros) { return a ? push_number(a, "append_timestamp", micros, 0, false) : 0; }
+
+// BLOB cell (src/duckdb_native.c:1397-1415): the bytes as they are, no UTF-8 requirement
+extern "C" int32_t duckdb_mb_gpu_append_blob(duckdb_mb_gpu_appender *a, const uint8_t *bytes, int32_t len) {
+  return duckdb_mb_gpu_append_varchar(a, bytes, len);
+}
+
+// INTERVAL cell (src/duckdb_native.c:1511-1533): duckdb_interval {months, days, micros}
+extern "C" int32_t duckdb_mb_gpu_append_interval(duckdb_mb_gpu_appender *a, int32_t months, int32_t days, int64_t micros) {
+  if (!a) return 0;
+  RowBuf *rb = cell(a, "append_interval");
+  if (!rb) return 0;
+  if (a->type_ids[(size_t)a->cur_col] != DMB_TYPE_INTERVAL) return type_mismatch(a, "append_interval");
+  interval_t v{months, days, micros};
+  const uint8_t *p = reinterpret_cast<const uint8_t *>(&v);
+  rb->values.insert(rb->values.end(), p, p + sizeof(v));
+  rb->valid.push_back(1);
+  a->cur_col++;
+  return 1;
+}
+
+// the table column's DECIMAL(width, scale) (duckdb_appender_column_type -> duckdb_decimal_width / _scale)
+extern "C" int32_t duckdb_mb_gpu_appender_set_decimal(duckdb_mb_gpu_appender *a, int32_t col, int32_t width, int32_t scale) {
+  if (!a) return 0;
+  if (col < 0 || col >= a->ncols || a->type_ids[(size_t)col] != DMB_TYPE_DECIMAL || width < 1 || width > 38 || scale < 0 || scale > width) {
+    fail(a, "appender_set_decimal: column %d is not a DECIMAL column or DECIMAL(%d,%d) is not a type", col, width, scale);
+    return 0;
+  }
+  RowBuf &rb = a->rows[(size_t)col];
+  if (rb.dec_prec && (rb.dec_prec != width || rb.dec_scale != scale)) {
+    fail(a, "appender_set_decimal: column %d is already DECIMAL(%d,%d)", col, rb.dec_prec, rb.dec_scale);
+    return 0;
+  }
+  rb.dec_prec = width;
+  rb.dec_scale = scale;
+  return 1;
+}
+
+// DECIMAL cell from hugeint parts (src/duckdb_native.c:1447-1481: duckdb_create_decimal + duckdb_append_value).
+// The value is brought to the column's scale like DuckDB's decimal -> decimal cast (exact when the scale grows,
+// round half away from zero when it shrinks) and must fit the column's precision.
+extern "C" int32_t duckdb_mb_gpu_append_decimal(duckdb_mb_gpu_appender *a, int32_t width, int32_t scale, int64_t lower, int64_t upper) {
+  if (!a) return 0;
+  RowBuf *rb = cell(a, "append_decimal");
+  if (!rb) return 0;
+  if (a->type_ids[(size_t)a->cur_col] != DMB_TYPE_DECIMAL) return type_mismatch(a, "append_decimal");
+  if (width < 1 || width > 38 || scale < 0 || scale > width) { fail(a, "append_decimal: DECIMAL(%d,%d) is not a type", width, scale); a->state = kError; return 0; }
+  if (rb->dec_prec == 0) { rb->dec_prec = width; rb->dec_scale = scale; }  // first value declares the column
+  __int128 v = (__int128)(((unsigned __int128)(uint64_t)upper << 64) | (unsigned __int128)(uint64_t)lower);
+  auto pow10 = [](int e) { __int128 p = 1; while (e-- > 0) p *= 10; return p; };
+  if (scale < rb->dec_scale) {
+    const int up = rb->dec_scale - scale;
+    const __int128 lim = pow10(38 - up);
+    if (v >= lim || v <= -lim) { fail(a, "append_decimal: value out of range for DECIMAL(%d,%d)", rb->dec_prec, rb->dec_scale); a->state = kError; return 0; }
+    v *= pow10(up);
+  } else if (scale > rb->dec_scale) {
+    const __int128 d = pow10(scale - rb->dec_scale), half = d / 2;
+    v = v >= 0 ? (v + half) / d : -((-v + half) / d);
+  }
+  const __int128 bound = pow10(rb->dec_prec);
+  if (v >= bound || v <= -bound) { fail(a, "append_decimal: value out of range for DECIMAL(%d,%d)", rb->dec_prec, rb->dec_scale); a->state = kError; return 0; }
+  const uint8_t *p = reinterpret_cast<const uint8_t *>(&v);
+  rb->values.insert(rb->values.end(), p, p + 16);
+  rb->valid.push_back(1);
+  a->cur_col++;
+  return 1;
+}
 
 extern "C" int32_t duckdb_mb_gpu_append_bool(duckdb_mb_gpu_appender *a, int32_t v) {
   if (!a) return 0;

@@ -116,7 +116,8 @@ EXPORTED_SYMBOLS = [
     "duckdb_mb_gpu_appender_flushed_row_count", "duckdb_mb_gpu_appender_link_bytes",
     "duckdb_mb_gpu_begin_row", "duckdb_mb_gpu_append_int", "duckdb_mb_gpu_append_bigint", "duckdb_mb_gpu_append_double",
     "duckdb_mb_gpu_append_varchar", "duckdb_mb_gpu_append_bool", "duckdb_mb_gpu_append_null", "duckdb_mb_gpu_append_date",
-    "duckdb_mb_gpu_append_timestamp", "duckdb_mb_gpu_end_row",
+    "duckdb_mb_gpu_append_timestamp", "duckdb_mb_gpu_end_row", "duckdb_mb_gpu_append_blob", "duckdb_mb_gpu_append_decimal",
+    "duckdb_mb_gpu_append_interval", "duckdb_mb_gpu_appender_set_decimal",
 ]
 
 _lib = None
@@ -259,7 +260,9 @@ def lib():
     L.duckdb_mb_gpu_appender_link_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
     for name, extra in (("begin_row", []), ("append_int", [i32]), ("append_bigint", [i64]), ("append_double", [C.c_double]),
                         ("append_varchar", [C.c_char_p, i32]), ("append_bool", [i32]), ("append_null", []),
-                        ("append_date", [i32]), ("append_timestamp", [i64]), ("end_row", [])):
+                        ("append_date", [i32]), ("append_timestamp", [i64]), ("end_row", []),
+                        ("append_blob", [C.c_char_p, i32]), ("append_decimal", [i32, i32, i64, i64]),
+                        ("append_interval", [i32, i32, i64]), ("appender_set_decimal", [i32, i32, i32])):
         f = getattr(L, "duckdb_mb_gpu_" + name)
         f.restype = i32
         f.argtypes = [vp] + extra

@@ -525,6 +525,13 @@ int32_t duckdb_mb_gpu_append_null(duckdb_mb_gpu_appender *a);                   
 int32_t duckdb_mb_gpu_append_date(duckdb_mb_gpu_appender *a, int32_t days);   /* exact days, not the
                                       approximate string path of :1313-1331 */
 int32_t duckdb_mb_gpu_append_timestamp(duckdb_mb_gpu_appender *a, int64_t micros);            /* :1350 */
+int32_t duckdb_mb_gpu_append_blob(duckdb_mb_gpu_appender *a, const uint8_t *bytes, int32_t len);    /* :1397 */
+/* DECIMAL from hugeint parts (:1447-1481).  The column's DECIMAL(width, scale) comes from
+ * duckdb_mb_gpu_appender_set_decimal (what duckdb_appender_column_type reports) or, failing that, from the
+ * first value; values of another scale are cast like DuckDB's decimal -> decimal cast, out-of-range is an error. */
+int32_t duckdb_mb_gpu_appender_set_decimal(duckdb_mb_gpu_appender *a, int32_t col, int32_t width, int32_t scale);
+int32_t duckdb_mb_gpu_append_decimal(duckdb_mb_gpu_appender *a, int32_t width, int32_t scale, int64_t lower, int64_t upper);
+int32_t duckdb_mb_gpu_append_interval(duckdb_mb_gpu_appender *a, int32_t months, int32_t days, int64_t micros); /* :1511 */
 int32_t duckdb_mb_gpu_end_row(duckdb_mb_gpu_appender *a);                                     /* :1221 */
 
 #ifdef __cplusplus

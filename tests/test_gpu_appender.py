@@ -214,6 +214,78 @@ def test_row_api_matches_bulk_path_and_reference_tests(ctx):
     a.close()
 
 
+def test_row_api_blob_decimal_interval(ctx):
+    """src/duckdb_native.c:1397-1415 (blob), :1447-1481 (decimal from hugeint parts), :1511-1533 (interval):
+    the cells land in the vectors as DuckDB stores them (DECIMAL narrowed to the precision's physical width)."""
+    from duckdb_mbt_b200 import appender as ap
+    from duckdb_mbt_b200.arrow_result import DuckDBError
+    types = [ch.T_BLOB, ch.T_DECIMAL, ch.T_DECIMAL, ch.T_DECIMAL, ch.T_INTERVAL]
+    sink = ap.CollectedChunks(types, [0, 15, 38, 4, 0])
+    a = ap.Appender(ctx, types, sink)
+    a.set_decimal(1, 15, 2)
+    a.set_decimal(2, 38, 0)
+    rng = np.random.default_rng(5)
+    rows = []
+    for i in range(3000):
+        blob = None if i % 11 == 0 else bytes(rng.integers(0, 256, int(rng.integers(0, 40)), dtype=np.uint8))
+        d15 = None if i % 7 == 0 else int(rng.integers(-10**15 + 1, 10**15))
+        d38 = None if i % 5 == 0 else (int.from_bytes(rng.bytes(16), "little") % 10**38) * (1 if i % 2 else -1)
+        d4 = int(rng.integers(-9999, 10000))
+        iv = None if i % 13 == 0 else (int(rng.integers(-100, 100)), int(rng.integers(-400, 400)), int(rng.integers(-2**50, 2**50)))
+        rows.append((blob, d15, d38, d4, iv))
+        a.begin_row()
+        a.append_blob(blob) if blob is not None else a.append_null()
+        a.append_decimal(15, 2, d15) if d15 is not None else a.append_null()
+        a.append_decimal(38, 0, d38) if d38 is not None else a.append_null()
+        a.append_decimal(4, 1, d4)  # the first value declares DECIMAL(4,1): physical int16
+        a.append_interval(*iv) if iv is not None else a.append_null()
+        a.end_row()
+    a.flush()
+    n = len(rows)
+    assert sink.nrows == n
+    ent = np.frombuffer(sink.column_bytes(0), dtype=np.uint8).reshape(-1, 16)
+    vb = sink.valid_bits(0)
+    for i in (1, 2, 3, 500, 2999):
+        blob = rows[i][0]
+        assert vb[i] == (blob is not None)
+        if blob is not None:
+            assert int(ent[i, 0:4].view(np.uint32)[0]) == len(blob)
+            assert bytes(ent[i, 4:4 + min(len(blob), 12 if len(blob) <= 12 else 4)]) == blob[: 12 if len(blob) <= 12 else 4]
+    d15 = np.frombuffer(sink.column_bytes(1), dtype=np.int64)
+    assert d15.tolist() == [0 if r[1] is None else r[1] for r in rows]
+    assert sink.valid_bits(1).tolist() == [r[1] is not None for r in rows]
+    d38 = np.frombuffer(sink.column_bytes(2), dtype=np.uint64).reshape(-1, 2)
+    got38 = [(int(lo) | (int(hi) << 64)) - ((1 << 128) if int(hi) >> 63 else 0) for lo, hi in d38]
+    assert got38 == [0 if r[2] is None else r[2] for r in rows]
+    assert np.frombuffer(sink.column_bytes(3), dtype=np.int16).tolist() == [r[3] for r in rows]
+    iv = np.frombuffer(sink.column_bytes(4), dtype=np.dtype([("m", "<i4"), ("d", "<i4"), ("us", "<i8")]))
+    assert [tuple(int(x) for x in v) for v in iv] == [(0, 0, 0) if r[4] is None else r[4] for r in rows]
+    # decimal -> decimal cast on the way in: scale up exactly, scale down rounding half away from zero, range checked
+    a.begin_row()
+    a.append_null()
+    a.append_decimal(5, 1, 123)       # 12.3 -> DECIMAL(15,2): 1230
+    a.append_decimal(10, 3, -12345)   # -12.345 -> DECIMAL(38,0): -12
+    a.append_decimal(6, 2, 1255)      # 12.55 -> DECIMAL(4,1): 126 (12.6)
+    a.append_null()
+    a.end_row()
+    a.flush()
+    assert np.frombuffer(sink.column_bytes(1), dtype=np.int64)[n] == 1230
+    assert np.frombuffer(sink.column_bytes(2), dtype=np.int64).reshape(-1, 2)[n].tolist() == [-12, -1]
+    assert np.frombuffer(sink.column_bytes(3), dtype=np.int16)[n] == 126
+    a.begin_row()
+    a.append_null()
+    with pytest.raises(DuckDBError, match="out of range"):
+        a.append_decimal(18, 2, 10**17)  # 10^15 does not fit DECIMAL(15,2)
+    assert a.state == ap.ERROR
+    a.close()
+    b = ap.Appender(ctx, [ch.T_INTEGER], discard=True)
+    b.begin_row()
+    with pytest.raises(DuckDBError):
+        b.append_interval(1, 2, 3)  # type mismatch: 0 + per-handle error, state Error
+    assert b.state == ap.ERROR
+    b.close()
+
+
 def test_protocol_follows_the_reference_model(ctx):
     from duckdb_mbt_b200 import appender as ap
     from duckdb_mbt_b200.arrow_result import DuckDBError
