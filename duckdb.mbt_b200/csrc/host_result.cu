@@ -380,7 +380,8 @@ int32_t string_source(Result *r, Scope &sc, int j, StringSource *src) {
   const int64_t nch = r->nchunks;
   const size_t nslots = (size_t)(nch > 0 ? nch : 1) * DMB_VECTOR_SIZE;
   dmb_string_t *d_str = (dmb_string_t *)sc.dalloc(nslots * sizeof(dmb_string_t));
-  uint8_t *d_heap = (uint8_t *)sc.dalloc(nslots * DMB_RENDER_SLOT_BYTES + 64);
+  const size_t slot_bytes = (size_t)dmb_render_slot_bytes(col.type_id);
+  uint8_t *d_heap = (uint8_t *)sc.dalloc(nslots * slot_bytes + 64);
   std::vector<dmb_vec_desc> vecs((size_t)(nch > 0 ? nch : 1));
   for (int64_t k = 0; k < nch; ++k) {
     vecs[(size_t)k].data_off = (uint64_t)k * DMB_VECTOR_SIZE * sizeof(dmb_string_t);
@@ -406,7 +407,7 @@ int32_t string_source(Result *r, Scope &sc, int j, StringSource *src) {
   src->vecs = d_vecs2;
   src->heap = d_heap;
   src->heap_host_base = job.heap_host_base;
-  src->heap_len = (uint64_t)nslots * DMB_RENDER_SLOT_BYTES;
+  src->heap_len = (uint64_t)nslots * slot_bytes;
   return 0;
 }
 

@@ -4,7 +4,7 @@
 // duckdb_value_varchar in the result path (src/duckdb_native.c:224-238, and :2478 / :2715 for the
 // "string" getters that its schema JSON prescribes for DATE / DECIMAL / TIMESTAMP / ... columns,
 // :2314-2339) and duckdb_value_to_string in the chunk path (:305-318, :611-661).  Here one thread
-// renders one cell into a 48-byte slot and emits a 16-byte string_t (<= 12 bytes inlined, else
+// renders one cell into a 48-byte slot (80 for INTERVAL) and emits a 16-byte string_t (<= 12 bytes inlined, else
 // prefix + pointer to the slot), so the rendered column then flows through the same
 // string_batch_kernel (utf8 offsets + data, or the reference's NUL-terminated blob) as a VARCHAR
 // column.  Formats follow DuckDB 1.4's renderings pinned by src/duckdb_fixture_cases.mbt
@@ -14,12 +14,11 @@
 
 namespace dmb {
 
-constexpr int kRenderSlot = DMB_RENDER_SLOT_BYTES;
-
+template <int SLOT>
 struct TextBuf {
-  char s[kRenderSlot];
+  char s[SLOT];
   int n;
-  __device__ __forceinline__ void push(char c) { if (n < kRenderSlot) s[n++] = c; }
+  __device__ __forceinline__ void push(char c) { if (n < SLOT) s[n++] = c; }
   __device__ __forceinline__ void push_str(const char *p) { while (*p) push(*p++); }
   // unsigned decimal, at least `min_digits` digits (zero padded)
   __device__ __forceinline__ void push_u64(uint64_t v, int min_digits) {
@@ -36,12 +35,14 @@ __device__ __forceinline__ int64_t floor_div64(int64_t a, int64_t b) {
   return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
 }
 
-__device__ __forceinline__ void render_i64(TextBuf &t, int64_t v) {
+template <class TB>
+__device__ __forceinline__ void render_i64(TB &t, int64_t v) {
   if (v < 0) { t.push('-'); t.push_u64((uint64_t)0 - (uint64_t)v, 1); } else t.push_u64((uint64_t)v, 1);
 }
 
 // DECIMAL(w, scale) stored as an integer: sign, integer part, '.', exactly `scale` fraction digits
-__device__ __forceinline__ void render_decimal(TextBuf &t, int64_t v, int scale) {
+template <class TB>
+__device__ __forceinline__ void render_decimal(TB &t, int64_t v, int scale) {
   const bool neg = v < 0;
   uint64_t a = neg ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
   if (neg) t.push('-');
@@ -54,7 +55,8 @@ __device__ __forceinline__ void render_decimal(TextBuf &t, int64_t v, int scale)
 }
 
 // proleptic Gregorian date: YYYY-MM-DD, more digits past year 9999, "(BC)" suffix before year 1
-__device__ __forceinline__ void render_date(TextBuf &t, int64_t days) {
+template <class TB>
+__device__ __forceinline__ void render_date(TB &t, int64_t days) {
   int64_t z = days + 719468;
   const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
   const int64_t doe = z - era * 146097;
@@ -74,7 +76,8 @@ __device__ __forceinline__ void render_date(TextBuf &t, int64_t days) {
 }
 
 // v in units of 1/unit_per_sec seconds since the epoch; fraction digits trimmed of trailing zeros
-__device__ __forceinline__ void render_timestamp(TextBuf &t, int64_t v, int64_t unit_per_sec, bool tz) {
+template <class TB>
+__device__ __forceinline__ void render_timestamp(TB &t, int64_t v, int64_t unit_per_sec, bool tz) {
   const int64_t secs = floor_div64(v, unit_per_sec);
   const int64_t frac = v - secs * unit_per_sec;
   const int64_t days = floor_div64(secs, 86400);
@@ -97,7 +100,8 @@ __device__ __forceinline__ void render_timestamp(TextBuf &t, int64_t v, int64_t 
 }
 
 // TIME: HH:MM:SS[.fraction], fraction digits trimmed of trailing zeros (fixture src/duckdb_fixture_cases.mbt:48-51)
-__device__ __forceinline__ void render_time(TextBuf &t, int64_t v, int64_t unit_per_sec) {
+template <class TB>
+__device__ __forceinline__ void render_time(TB &t, int64_t v, int64_t unit_per_sec) {
   const int64_t secs = v / unit_per_sec, frac = v % unit_per_sec;
   t.push_u64((uint64_t)(secs / 3600), 2);
   t.push(':');
@@ -115,7 +119,8 @@ __device__ __forceinline__ void render_time(TextBuf &t, int64_t v, int64_t unit_
 
 // 128-bit integers (HUGEINT: what SUM() of an integer column returns, fixtures :34-37; UHUGEINT;
 // DECIMAL(19..38, scale)): three base-10^19 limbs, '.' before the last `scale` digits
-__device__ __forceinline__ void render_i128(TextBuf &t, unsigned __int128 u, bool is_signed, int scale) {
+template <class TB>
+__device__ __forceinline__ void render_i128(TB &t, unsigned __int128 u, bool is_signed, int scale) {
   const bool neg = is_signed && (__int128)u < 0;
   unsigned __int128 a = neg ? (unsigned __int128)0 - u : u;
   const unsigned __int128 kP19 = 10000000000000000000ull;
@@ -241,7 +246,8 @@ __device__ __forceinline__ uint64_t ryu_shortest(uint64_t bits, int &exp10) {
 
 // fmt-style layout of the digits: fixed notation for 1e-5 <= |v| < 1e16 (always with a fraction:
 // "1.0"), else d.ddde+XX (at least two exponent digits)
-__device__ __forceinline__ void render_double(TextBuf &t, double v) {
+template <class TB>
+__device__ __forceinline__ void render_double(TB &t, double v) {
   const uint64_t bits = (uint64_t)__double_as_longlong(v);
   if (((bits >> 52) & 0x7ffu) == 0x7ffu) {
     if (bits & ((1ull << 52) - 1ull)) t.push_str("nan");
@@ -283,6 +289,78 @@ __device__ __forceinline__ void render_double(TextBuf &t, double v) {
   t.push_u64((uint64_t)(x10 < 0 ? -x10 : x10), 2);
 }
 
+// UUID: DuckDB keeps a UUID as a hugeint whose top bit is flipped (so that UUIDs order like signed hugeints);
+// text is lowercase hex 8-4-4-4-12.  UNPINNED (no reference fixture holds a UUID).
+template <class TB>
+__device__ __forceinline__ void render_uuid(TB &t, unsigned __int128 u) {
+  const uint64_t hi = (uint64_t)(u >> 64) ^ (1ull << 63), lo = (uint64_t)u;
+  auto hex = [&](uint64_t v, int digits) {
+    for (int i = digits - 1; i >= 0; --i) t.push("0123456789abcdef"[(v >> (4 * i)) & 15ull]);
+  };
+  hex(hi >> 32, 8); t.push('-');
+  hex(hi >> 16, 4); t.push('-');
+  hex(hi, 4); t.push('-');
+  hex(lo >> 48, 4); t.push('-');
+  hex(lo, 12);
+}
+
+// TIME WITH TIME ZONE: bits = micros << 24 | (57599 - offset seconds); text = TIME, then +HH / -HH, ":MM" and ":SS"
+// only when non-zero.  UNPINNED.
+template <class TB>
+__device__ __forceinline__ void render_time_tz(TB &t, uint64_t bits) {
+  render_time(t, (int64_t)(bits >> 24), 1000000);
+  int off = 57599 - (int)(bits & 0xffffffull);
+  t.push(off < 0 ? '-' : '+');
+  if (off < 0) off = -off;
+  t.push_u64((uint64_t)(off / 3600), 2);
+  const int mm = off % 3600 / 60, ss = off % 60;
+  if (mm) { t.push(':'); t.push_u64((uint64_t)mm, 2); }
+  if (ss) { t.push(':'); t.push_u64((uint64_t)ss, 2); }
+}
+
+// INTERVAL {months, days, micros}: "Y year[s] M month[s] D day[s] [-]HH:MM:SS[.ffffff]", zero parts left out,
+// "00:00:00" when everything is zero; unit names take an 's' unless the count is +-1.  UNPINNED.
+template <class TB>
+__device__ __forceinline__ void render_interval(TB &t, int32_t months, int32_t days, int64_t micros) {
+  auto part = [&](int64_t v, const char *name) {
+    if (v == 0) return;
+    if (t.n) t.push(' ');
+    render_i64(t, v);
+    t.push_str(name);
+    if (v != 1 && v != -1) t.push('s');
+  };
+  const int32_t years = months / 12;
+  part(years, " year");
+  part(months - years * 12, " month");
+  part(days, " day");
+  if (micros != 0) {
+    if (t.n) t.push(' ');
+    int64_t m = micros;  // kept non-positive: INT64_MIN has no positive twin
+    if (m < 0) t.push('-'); else m = -m;
+    const int64_t hour = -(m / 3600000000ll);
+    m += hour * 3600000000ll;
+    const int64_t min = -(m / 60000000ll);
+    m += min * 60000000ll;
+    const int64_t sec = -(m / 1000000ll);
+    m += sec * 1000000ll;
+    t.push_u64((uint64_t)hour, 2);
+    t.push(':');
+    t.push_u64((uint64_t)min, 2);
+    t.push(':');
+    t.push_u64((uint64_t)sec, 2);
+    uint64_t f = (uint64_t)(-m);
+    if (f) {
+      int digits = 6;
+      while (f % 10ull == 0ull) { f /= 10ull; --digits; }
+      t.push('.');
+      t.push_u64(f, digits);
+    }
+  } else if (t.n == 0) {
+    t.push_str("00:00:00");
+  }
+}
+
+template <int SLOT>
 __global__ void __launch_bounds__(kThreads)
 render_text_kernel(dmb_render_job job, const uint32_t *__restrict__ counts, int64_t nchunks) {
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -295,7 +373,7 @@ render_text_kernel(dmb_render_job job, const uint32_t *__restrict__ counts, int6
       uint4 e = make_uint4(0, 0, 0, 0);
       const bool valid = mask ? ((__ldg(mask + (i >> 6)) >> (i & 63)) & 1ull) : true;
       if (valid) {
-        TextBuf t;
+        TextBuf<SLOT> t;
         t.n = 0;
         int64_t v = 0;
         uint64_t u = 0;
@@ -314,7 +392,7 @@ render_text_kernel(dmb_render_job job, const uint32_t *__restrict__ counts, int6
         if (job.phys == DMB_PHYS_F64) fv = reinterpret_cast<const double *>(in)[i];
         if (job.phys == DMB_PHYS_F32) fv = (double)reinterpret_cast<const float *>(in)[i];  // the oracle widens first (UNPINNED)
         unsigned __int128 wide = 0;
-        if (job.phys == DMB_PHYS_I128 || job.phys == DMB_PHYS_U128) {
+        if (job.phys == DMB_PHYS_I128 || job.phys == DMB_PHYS_U128 || job.phys == DMB_PHYS_INTERVAL) {
           const uint4 q = reinterpret_cast<const uint4 *>(in)[i];
           wide = ((unsigned __int128)(((uint64_t)q.w << 32) | q.z) << 64) | (((uint64_t)q.y << 32) | q.x);
         }
@@ -335,12 +413,15 @@ render_text_kernel(dmb_render_job job, const uint32_t *__restrict__ counts, int6
           case DMB_TYPE_UHUGEINT: render_i128(t, wide, false, 0); break;
           case DMB_TYPE_TIME: render_time(t, v, 1000000); break;
           case DMB_TYPE_TIME_NS: render_time(t, v, 1000000000); break;
+          case DMB_TYPE_TIME_TZ: render_time_tz(t, u); break;
+          case DMB_TYPE_UUID: render_uuid(t, wide); break;
+          case DMB_TYPE_INTERVAL: render_interval(t, (int32_t)(uint32_t)wide, (int32_t)(uint32_t)(wide >> 32), (int64_t)(uint64_t)(wide >> 64)); break;
           default: render_i64(t, v); break;  // TINYINT .. BIGINT, UTINYINT .. UINTEGER
         }
         // string_t: length, then 12 inlined bytes or 4-byte prefix + pointer to the slot
-        uint32_t w[kRenderSlot / 4];
+        uint32_t w[SLOT / 4];
 #pragma unroll
-        for (int k = 0; k < kRenderSlot / 4; ++k) {
+        for (int k = 0; k < SLOT / 4; ++k) {
           uint32_t x = 0;
 #pragma unroll
           for (int bb = 0; bb < 4; ++bb) x |= (4 * k + bb < t.n ? (uint32_t)(uint8_t)t.s[4 * k + bb] : 0u) << (8 * bb);
@@ -352,12 +433,12 @@ render_text_kernel(dmb_render_job job, const uint32_t *__restrict__ counts, int6
           e.z = w[1];
           e.w = w[2];
         } else {
-          const uint64_t p = job.heap_host_base + (uint64_t)slot * kRenderSlot;
+          const uint64_t p = job.heap_host_base + (uint64_t)slot * SLOT;
           e.z = (uint32_t)p;
           e.w = (uint32_t)(p >> 32);
-          uint4 *dst = reinterpret_cast<uint4 *>(job.out_heap + (uint64_t)slot * kRenderSlot);
+          uint4 *dst = reinterpret_cast<uint4 *>(job.out_heap + (uint64_t)slot * SLOT);
 #pragma unroll
-          for (int k = 0; k < kRenderSlot / 16; ++k) dst[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+          for (int k = 0; k < SLOT / 16; ++k) dst[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
         }
       }
       reinterpret_cast<uint4 *>(job.out)[slot] = e;
@@ -368,6 +449,11 @@ render_text_kernel(dmb_render_job job, const uint32_t *__restrict__ counts, int6
 }  // namespace dmb
 
 using namespace dmb;
+
+// bytes of out_heap per row: the longest rendering of the type, rounded up to 16 (INTERVAL: up to 70 characters)
+extern "C" int32_t dmb_render_slot_bytes(int32_t type_id) {
+  return type_id == DMB_TYPE_INTERVAL ? DMB_RENDER_SLOT_BYTES_WIDE : DMB_RENDER_SLOT_BYTES;
+}
 
 extern "C" int32_t dmb_render_supported(int32_t type_id, int32_t phys) {
   switch (type_id) {
@@ -383,7 +469,10 @@ extern "C" int32_t dmb_render_supported(int32_t type_id, int32_t phys) {
     case DMB_TYPE_HUGEINT: return phys == DMB_PHYS_I128;
     case DMB_TYPE_UHUGEINT: return phys == DMB_PHYS_U128;
     case DMB_TYPE_DECIMAL: return phys == DMB_PHYS_I16 || phys == DMB_PHYS_I32 || phys == DMB_PHYS_I64 || phys == DMB_PHYS_I128;
-    default: return 0;  // INTERVAL, TIME_TZ, UUID, BLOB: not rendered on the device
+    case DMB_TYPE_TIME_TZ: return phys == DMB_PHYS_U64 || phys == DMB_PHYS_I64;
+    case DMB_TYPE_UUID: return phys == DMB_PHYS_U128 || phys == DMB_PHYS_I128;
+    case DMB_TYPE_INTERVAL: return phys == DMB_PHYS_INTERVAL;
+    default: return 0;  // BLOB and nested types: not rendered on the device
   }
 }
 
@@ -393,6 +482,7 @@ extern "C" int32_t dmb_dev_render_text(const dmb_render_job *job, const uint32_t
   if (nchunks <= 0) return 0;
   const int64_t max_grid = (int64_t)kNumSMs * 8;
   const int grid = (int)(nchunks < max_grid ? nchunks : max_grid);
-  render_text_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(*job, counts, nchunks);
+  if (dmb_render_slot_bytes(job->type_id) == DMB_RENDER_SLOT_BYTES_WIDE) render_text_kernel<DMB_RENDER_SLOT_BYTES_WIDE><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*job, counts, nchunks);
+  else render_text_kernel<DMB_RENDER_SLOT_BYTES><<<grid, kThreads, 0, (cudaStream_t)stream>>>(*job, counts, nchunks);
   return check_cuda(cudaGetLastError(), "render_text_kernel launch");
 }

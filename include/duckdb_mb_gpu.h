@@ -219,12 +219,13 @@ int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_t *counts,
  * src/duckdb_native.c:224-238, :2478, :2715 and :305-318.  Rendered: BOOLEAN, the eight integer
  * types, HUGEINT, UHUGEINT, FLOAT, DOUBLE (shortest round trip), DATE, TIME, TIME_NS, TIMESTAMP / _TZ / _S / _MS / _NS, DECIMAL (any storage). */
 #define DMB_RENDER_SLOT_BYTES 48
+#define DMB_RENDER_SLOT_BYTES_WIDE 80 /* INTERVAL: up to 70 characters */
 typedef struct dmb_render_job {
   const void *in_data;         /* column slab */
   const uint64_t *in_validity; /* validity slab or NULL */
   const dmb_vec_desc *vecs;    /* [nchunks], of the source column */
   dmb_string_t *out;           /* string_t slab: chunk k at k*2048 entries */
-  uint8_t *out_heap;           /* nchunks*2048*DMB_RENDER_SLOT_BYTES bytes */
+  uint8_t *out_heap;           /* nchunks*2048*dmb_render_slot_bytes(type_id) bytes */
   uint64_t heap_host_base;     /* the "host address" written into pointer entries (any value; the
                                   string kernel rebases against the same number) */
   int32_t type_id;             /* enum dmb_type */
@@ -233,6 +234,7 @@ typedef struct dmb_render_job {
   int32_t reserved;
 } dmb_render_job;
 int32_t dmb_render_supported(int32_t type_id, int32_t phys);
+int32_t dmb_render_slot_bytes(int32_t type_id); /* out_heap bytes per row for this type (48, INTERVAL: 80) */
 int32_t dmb_dev_render_text(const dmb_render_job *job, const uint32_t *counts, int64_t nchunks, void *stream);
 
 /* K6 reverse (Arrow -> DataChunk vectors), the bulk door behind the appender

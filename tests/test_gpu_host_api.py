@@ -388,9 +388,9 @@ def test_typed_reference_vectors(ctx):
     # DECIMAL stays a text-rendered Value::String in the reference (src/duckdb_parsing.mbt:124-127)
     with _result(ctx, batch_of(("dec", ch.T_DECIMAL, [1], 10, 3))) as res:
         assert tr.typed_column(res, 0).value(0).as_string() == "0.001"
-    # UUID's libduckdb rendering is not reproduced on the device: an error, never a guess
+    # UUID stays a text-rendered Value::String too (src/duckdb_parsing.mbt:122)
     one = ch.chunk_counts(1)
-    with _result(ctx, ch.ChunkBatch(one, [ch.fixed_column("h", ch.T_UUID, np.zeros((1, 16), np.uint8), one)])) as res:
-        from duckdb_mbt_b200.arrow_result import DuckDBError
-        with pytest.raises(DuckDBError):
-            tr.typed_column(res, 0)
+    zero = np.zeros((1, 16), np.uint8)
+    zero[0, 15] = 0x80  # stored with the top bit flipped
+    with _result(ctx, ch.ChunkBatch(one, [ch.fixed_column("h", ch.T_UUID, zero, one)])) as res:
+        assert tr.typed_column(res, 0).value(0).as_string() == "00000000-0000-0000-0000-000000000000"

@@ -17,7 +17,7 @@ from duckdb_mbt_b200 import chunks as ch  # noqa: E402
 from test_gpu_l0_parity import _mixed_batch  # noqa: E402
 from test_oracle_golden import batch_of  # noqa: E402
 
-RENDERED = {"b", "i8", "i16", "i32", "i64", "u8", "u16", "u32", "u64", "f32", "f64", "huge", "dec4", "dec9", "dec18", "date", "ts_s", "ts_ms", "ts_ns"}
+RENDERED = {"b", "i8", "i16", "i32", "i64", "u8", "u16", "u32", "u64", "f32", "f64", "huge", "dec4", "dec9", "dec18", "date", "ts_s", "ts_ms", "ts_ns", "iv", "uuid"}
 
 
 @pytest.fixture(scope="module")
@@ -50,12 +50,6 @@ def test_string_getter_on_fixed_width_columns(ctx, n, pattern):
                 assert got == exp, f"col={c.name} nullable={nullable}"
             seen += 1
         assert seen == len(RENDERED)
-        # types whose libduckdb rendering is not reproduced on the device: empty Bytes + error, never a guess
-        from duckdb_mbt_b200 import native as nat
-        for name in ("iv", "uuid"):
-            j = [c.name for c in batch.columns].index(name)
-            assert res.raw_column("string", j) == b""
-            assert "not reproduced" in nat.last_error()
 
 
 def test_fixture_strings_through_gpu(ctx):
@@ -170,6 +164,43 @@ def test_hugeint_time_and_wide_decimal_renderings(ctx):
         # HUGEINT / DECIMAL(38) / TIME stay Value::String in the reference's typed result (src/duckdb_parsing.mbt:120-141)
         assert tr.typed_column(res, 0).tag == tr.STRING and tr.typed_column(res, 0).value(0).as_string() == "6"
         assert tr.typed_column(res, 2).value(0).as_string() == "12:34:56.789"
+
+
+def test_uuid_timetz_interval_renderings(ctx):
+    # the remaining scalar types of the reference's stream whitelist (src/duckdb_native.c:287-299): device text == oracle text,
+    # known answers first, then random cells (NULLs, garbage under NULLs, ragged chunks)
+    from duckdb_mbt_b200 import typed_result as tr
+    from test_oracle_golden import INTERVAL_CASES, TIMETZ_CASES, UUID_CASES, _interval_rows, _uuid_bytes
+    n = len(UUID_CASES)
+    one = ch.chunk_counts(n)
+    batch = ch.ChunkBatch(one, [ch.fixed_column("u", ch.T_UUID, np.stack([_uuid_bytes(t) for t in UUID_CASES]), one),
+                                ch.fixed_column("z", ch.T_TIME_TZ, np.asarray([c[0] for c in TIMETZ_CASES], np.uint64), one)])
+    with _result(ctx, batch) as res:
+        assert [tr.text_column(res, 0).value(i).as_string() for i in range(n)] == UUID_CASES
+        assert [tr.text_column(res, 1).value(i).as_string() for i in range(n)] == [c[1] for c in TIMETZ_CASES]
+    m = len(INTERVAL_CASES)
+    cm = ch.chunk_counts(m)
+    with _result(ctx, ch.ChunkBatch(cm, [ch.fixed_column("i", ch.T_INTERVAL, _interval_rows([c[0] for c in INTERVAL_CASES]), cm)])) as res:
+        assert [tr.text_column(res, 0).value(i).as_string() for i in range(m)] == [c[1] for c in INTERVAL_CASES]
+    rng = np.random.default_rng(33)
+    n = 7000
+    counts = ch.chunk_counts(n, "ragged", rng)
+    valid = rng.random(n) > 0.2
+    iv = np.zeros(n, dtype=np.dtype([("m", "<i4"), ("d", "<i4"), ("us", "<i8")]))
+    iv["m"] = rng.integers(-400, 400, n) * (rng.random(n) < 0.7)
+    iv["d"] = rng.integers(-5000, 5000, n) * (rng.random(n) < 0.7)
+    iv["us"] = rng.integers(-2**46, 2**46, n) * (rng.random(n) < 0.7) * np.where(rng.random(n) < 0.3, 1000, 1)
+    iv[:4] = [(-(2**31), -(2**31), -(2**63)), (2**31 - 1, 2**31 - 1, 2**63 - 1), (0, 0, 0), (1, 1, 1)]
+    tz = (rng.integers(0, 86400 * 10**6, n).astype(np.uint64) << np.uint64(24)) | rng.integers(0, 2 * 57599 + 1, n).astype(np.uint64)
+    tz[rng.random(n) < 0.5] &= ~np.uint64(0xFFFFFF) | np.uint64(57599 - 3600 * 2)
+    batch = ch.ChunkBatch(counts, [ch.fixed_column("u", ch.T_UUID, rng.integers(0, 256, (n, 16), dtype=np.uint8), counts, valid=valid, garbage_rng=rng),
+                                   ch.fixed_column("z", ch.T_TIME_TZ, tz, counts, valid=valid, garbage_rng=rng),
+                                   ch.fixed_column("i", ch.T_INTERVAL, iv.view(np.uint8).reshape(n, 16), counts, valid=valid, garbage_rng=rng)])
+    ora = oracle.OracleResult(batch)
+    with _result(ctx, batch) as res:
+        for j in range(3):
+            for nullable in (False, True):
+                assert res.raw_column("string", j, nullable) == ora.get_column("string", j, nullable), (j, nullable)
 
 
 def test_random_hugeint_column_against_the_oracle(ctx):

@@ -203,6 +203,46 @@ def test_fixture_time_and_hugeint_renderings():
     assert r.cell_value(1, 0) == b"6" and r.cell_value(1, 1) == b"15"
 
 
+def _uuid_bytes(text):
+    v = int(text.replace("-", ""), 16) ^ (1 << 127)  # DuckDB stores a UUID as a hugeint with the top bit flipped
+    return np.frombuffer(v.to_bytes(16, "little"), np.uint8)
+
+
+def _interval_rows(vals):
+    a = np.zeros(len(vals), dtype=np.dtype([("m", "<i4"), ("d", "<i4"), ("us", "<i8")]))
+    for i, v in enumerate(vals):
+        a[i] = v
+    return a.view(np.uint8).reshape(len(vals), 16)
+
+
+UUID_CASES = ["550e8400-e29b-41d4-a716-446655440000", "00000000-0000-0000-0000-000000000000",
+              "ffffffff-ffff-ffff-ffff-ffffffffffff", "80000000-0000-0000-0000-000000000001"]
+TIMETZ_CASES = [((45296 * 10**6 + 789000) << 24 | (57599 - 19800), "12:34:56.789+05:30"),
+                ((45296 * 10**6) << 24 | (57599 + 8 * 3600), "12:34:56-08"),
+                (0 << 24 | 57599, "00:00:00+00"),
+                ((86399 * 10**6 + 999999) << 24 | (57599 - 57599), "23:59:59.999999+15:59:59")]
+INTERVAL_CASES = [((14, 3, (4 * 3600 + 5 * 60 + 6) * 10**6 + 789000), "1 year 2 months 3 days 04:05:06.789"),
+                  ((0, 0, 0), "00:00:00"), ((12, 0, 0), "1 year"), ((-12, 0, 0), "-1 year"), ((1, 1, 0), "1 month 1 day"),
+                  ((25, -2, 0), "2 years 1 month -2 days"), ((0, 0, -1), "-00:00:00.000001"), ((0, 7, 90 * 10**6), "7 days 00:01:30"),
+                  ((-13, 0, 100 * 3600 * 10**6), "-1 year -1 month 100:00:00"),
+                  ((-(2**31), -(2**31), -(2**63)), "-178956970 years -8 months -2147483648 days -2562047788:00:54.775808")]
+
+
+def test_uuid_timetz_interval_renderings():
+    """UNPINNED by the reference (no fixture holds these types): known answers of DuckDB's documented VARCHAR casts
+    for the cells the stream whitelist lets through (src/duckdb_native.c:287-299, loaded at :615-662)."""
+    n = len(UUID_CASES)
+    one = ch.chunk_counts(n)
+    r = oracle.OracleResult(ch.ChunkBatch(one, [ch.fixed_column("u", ch.T_UUID, np.stack([_uuid_bytes(t) for t in UUID_CASES]), one),
+                                                ch.fixed_column("z", ch.T_TIME_TZ, np.asarray([c[0] for c in TIMETZ_CASES], np.uint64), one)]))
+    assert [r.cell_value(0, i).decode() for i in range(n)] == UUID_CASES
+    assert [r.cell_value(1, i).decode() for i in range(n)] == [c[1] for c in TIMETZ_CASES]
+    m = len(INTERVAL_CASES)
+    cm = ch.chunk_counts(m)
+    ri = oracle.OracleResult(ch.ChunkBatch(cm, [ch.fixed_column("i", ch.T_INTERVAL, _interval_rows([c[0] for c in INTERVAL_CASES]), cm)]))
+    assert [ri.cell_value(0, i).decode() for i in range(m)] == [c[1] for c in INTERVAL_CASES]
+
+
 def test_fixture_timestamp_and_decimal_renderings():
     micros = (19877 * 86400 + 12 * 3600 + 34 * 60 + 56) * 1_000_000 + 789_000
     assert oracle.render_timestamp(micros) == "2024-06-03 12:34:56.789"       # :55-60
