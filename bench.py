@@ -478,8 +478,8 @@ def run_ours(args, rank, local_rank, world):
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if tj.get("rows") == n and tj.get("kernel") == dominant:
-            traffic = tj.get("dram_bytes_per_launch")
+        if tj.get("rows") == n and dominant in tj.get("kernels", {}):
+            traffic = tj["kernels"][dominant].get("dram_bytes_per_launch")
     except Exception:
         pass
     line = {

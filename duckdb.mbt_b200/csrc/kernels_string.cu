@@ -485,20 +485,17 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
 // in and out of the SM is done by the copy engine (cp.async.bulk), every long-latency step of tile
 // t+1 is issued while tile t is being packed, and the SIMT part is row-centric and small.
 //
-//   CTA = 8 (or 16) worker warps + four single-purpose warps; tiles (R*256 consecutive rows of a chunk) are
+//   CTA = 8 (or 16) worker warps + two single-purpose warps; tiles (R*256 consecutive rows of a chunk) are
 //   claimed in order from a global ticket, so every predecessor of a claimed tile is owned by a
 //   running CTA (the look-back cannot starve).
 //
 //   P  claims tile j+2 (ticket, chunk metadata) and bulk-loads its string_t (and validity words)
-//      into the S buffer the workers and A have just left; when the workers have packed a tile it
+//      into the S buffer the workers have just left; when the workers have packed a tile it
 //      sends the stage O to out_data with bulk stores: one for the 16-byte aligned interior and
 //      sm_100's byte-masked form (cp.async.bulk ... .cp_mask) for the ragged first / last vector,
 //      whose other bytes belong to the neighbouring tiles.
-//   A  (two warps, alternating tiles) sums a tile's lengths the moment its string_t land and
-//      publishes the tile's aggregate: a short, uniform delay after the ticket, so the look-backs
-//      behind it rarely wait.
 //   W  front(j): own R consecutive rows from S -> lengths, block scan, span min/max (redux.sync);
-//      one thread fetches the tile's heap span [hmin, hmax) into H[j&1] with ONE bulk copy.
+//      one thread publishes the tile's aggregate and fetches the tile's heap span [hmin, hmax) into H[j&1] with ONE bulk copy.
 //      back(j-1): offsets straight from registers (vector stores), then every thread streams its
 //      rows' bytes (registers for inlined strings, the staged span for pointer strings) into the
 //      output stage O with 32-bit funnel shifts: interior words are plain stores, the <= 2 words
@@ -558,7 +555,6 @@ struct PackTail {
   unsigned long long mbar_b[kMetaRing];  // L -> workers: base of tile k resolved
   unsigned long long mbar_q[kMetaRing];  // workers -> L: tile k scanned (its look-back is due within an iteration)
   unsigned long long mbar_f[kMetaRing];  // P -> L: tile k's aggregate is published (one phase per use)
-  unsigned long long mbar_a[2];  // A -> P: the tile in S[slot] has been summed
   TileMeta meta[kMetaRing];
   PackPartials part[2];
   alignas(16) unsigned long long vmask[2][kVec / 64];  // validity words of the tile in S[slot] (bulk-copy destination)
@@ -715,7 +711,7 @@ struct RowState {
 };
 
 template <bool LARGE, int R, int NW, bool HEAP>
-__global__ void __launch_bounds__(NW * 32 + 128, NW == 8 ? (HEAP ? 3 : DMB_NOHEAP_CTAS) : 2)
+__global__ void __launch_bounds__(NW * 32 + 64, NW == 8 ? (HEAP ? 3 : DMB_NOHEAP_CTAS) : 2)
 string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles,
                    uint32_t ostage_bytes, uint32_t hstage_bytes) {
   constexpr int kWT = NW * 32;             // worker threads
@@ -738,8 +734,6 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
     mbar_init(smem_u32(&pt.mbar_h[0]), 1);
     mbar_init(smem_u32(&pt.mbar_h[1]), 1);
     for (int k = 0; k < kMetaRing; ++k) { mbar_init(smem_u32(&pt.mbar_f[k]), 1); mbar_init(smem_u32(&pt.mbar_b[k]), 1); mbar_init(smem_u32(&pt.mbar_q[k]), 1); }
-    mbar_init(smem_u32(&pt.mbar_a[0]), 1);
-    mbar_init(smem_u32(&pt.mbar_a[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -780,7 +774,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
     // hand the stage back.  Both jobs are triggered by the end of a worker iteration.
     if (lane == 0) {
       claim(0);
-      claim(1);  // claims run two tiles ahead, also past the end: each A warp must meet a tile that says so
+      claim(1);  // claims run two tiles ahead, also past the end: the workers must meet a tile that says so
     }
     bar_arrive(kBarBase, kWL);  // the stage is free
     for (int j = 0;; ++j) {
@@ -821,48 +815,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       bar_arrive(kBarBase, kWL);  // the stage is free
       if (lane == 0) {
         // S[j&1] held tile j: the workers have scanned it (barrier above), and so has A
-        mbar_wait(smem_u32(&pt.mbar_a[j & 1]), (uint32_t)(j >> 1) & 1u);
         claim(j + 2);
-      }
-      __syncwarp();
-    }
-    return;
-  }
-
-  if (warp >= NW + 2) {
-    // ------------------------------------------------------------ A (two warps, alternating tiles): tile totals, aggregates
-    // as soon as tile k's string_t have landed, sum its lengths and publish its aggregate, so that the
-    // delay between a ticket and its aggregate is short and the same for every CTA (the look-back of
-    // the tiles behind it then rarely has to wait)
-    for (int k = warp - (NW + 2);; k += 2) {
-      TileMeta &m = pt.meta[k & (kMetaRing - 1)];
-      const int slot = k & 1;
-      mbar_wait(smem_u32(&pt.mbar_s[slot]), (uint32_t)(k >> 1) & 1u);
-      const long long tile = m.tile;
-      if (tile < 0) {
-        if (lane == 0) mbar_arrive(smem_u32(&pt.mbar_f[k & (kMetaRing - 1)]));
-        break;
-      }
-      if (lane == 0) DMB_PTRACE(k, 7);
-      const int nrows = m.nrows;
-      const bool has_mask = m.has_mask != 0;
-      const uint4 *s = reinterpret_cast<const uint4 *>(sbuf + (uint32_t)slot * kSBytes);
-      uint32_t sum = 0;
-      int flags = 0;
-#pragma unroll 8
-      for (int i = lane; i < kRows; i += 32) {
-        const uint4 e = s[i];
-        const bool live = i < nrows && (!has_mask || ((pt.vmask[slot][i >> 6] >> (i & 63)) & 1ull));
-        uint32_t lo16, hi16;
-        sum += row_bytes<HEAP>(job, e.x, e.z, e.w, live, flags, lo16, hi16);
-      }
-      sum = __reduce_add_sync(0xffffffffu, sum);
-      if (lane == 0) {
-        m.total = sum;
-        atomicExch(status + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)sum);
-        DMB_PTRACE(k, 13);
-        mbar_arrive(smem_u32(&pt.mbar_f[k & (kMetaRing - 1)]));  // L may look at tile k
-        mbar_arrive(smem_u32(&pt.mbar_a[slot]));                 // P may reuse S[slot] once the workers are done with it
       }
       __syncwarp();
     }
@@ -991,6 +944,11 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         m.hmin = hmin;
         m.hbytes = hbytes;
         m.staged = staged;
+        // the tile's aggregate goes out here (a separate warp that summed the lengths as soon as the string_t landed, one
+        // iteration earlier, made the look-backs behind it a little shorter but cost 3 % of the kernel: every row was read twice)
+        m.total = total;
+        atomicExch(status + m.tile, (m.tile == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)total);
+        mbar_arrive(smem_u32(&pt.mbar_f[j & (kMetaRing - 1)]));
         mbar_arrive(smem_u32(&pt.mbar_q[j & (kMetaRing - 1)]));  // L: tile j's look-back is due
         if (HEAP && staged && hbytes) {
           const uint32_t mb = smem_u32(&pt.mbar_h[slot]);
@@ -999,6 +957,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         }
       }
     }
+    if (!nxt_valid && tid == 0) mbar_arrive(smem_u32(&pt.mbar_f[j & (kMetaRing - 1)]));  // L: no tile j
     if (tid == 0) DMB_PTRACE(j, 2);
 
     // ---- back(tile j-1)
@@ -1617,10 +1576,10 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
     if (job->heap_len == 0) {  // (experiment: DMB_STR_SHORT_RPT=0) the pipeline below with 4 rows per thread
       if (force_nw != 16) {
         const uint32_t ob = ((1024u * 12u + 64u) + 127u) & ~127u;
-        return large ? launch_pack(string_pack_kernel<true, 4, 8, false>, 1024, 8 * 32 + 128, ob, 0u) : launch_pack(string_pack_kernel<false, 4, 8, false>, 1024, 8 * 32 + 128, ob, 0u);
+        return large ? launch_pack(string_pack_kernel<true, 4, 8, false>, 1024, 8 * 32 + 64, ob, 0u) : launch_pack(string_pack_kernel<false, 4, 8, false>, 1024, 8 * 32 + 64, ob, 0u);
       }
       const uint32_t ob = ((2048u * 12u + 64u) + 127u) & ~127u;
-      return large ? launch_pack(string_pack_kernel<true, 4, 16, false>, 2048, 16 * 32 + 128, ob, 0u) : launch_pack(string_pack_kernel<false, 4, 16, false>, 2048, 16 * 32 + 128, ob, 0u);
+      return large ? launch_pack(string_pack_kernel<true, 4, 16, false>, 2048, 16 * 32 + 64, ob, 0u) : launch_pack(string_pack_kernel<false, 4, 16, false>, 2048, 16 * 32 + 64, ob, 0u);
     }
     const double heap_per_row = (double)job->heap_len / (double)nrows;
     // the pipeline needs three CTAs per SM to hide its latencies: S[2] + O + H[2] <= ~72 KiB, i.e. a heap span of
@@ -1640,11 +1599,11 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
         uint32_t hb4 = ((uint32_t)(heap_per_row * 1024.0 * slack) + 1024u + 127u) & ~127u;
         if (hb4 < 2048u) hb4 = 2048u;
         const uint32_t ob4 = hb4 + 4096u + 1024u * 4u;  // inlined rows add at most 12 bytes each: room for a third of the rows
-        return large ? launch_pack(string_pack_kernel<true, 4, 8, true>, 1024, 8 * 32 + 128, ob4, hb4)
-                     : launch_pack(string_pack_kernel<false, 4, 8, true>, 1024, 8 * 32 + 128, ob4, hb4);
+        return large ? launch_pack(string_pack_kernel<true, 4, 8, true>, 1024, 8 * 32 + 64, ob4, hb4)
+                     : launch_pack(string_pack_kernel<false, 4, 8, true>, 1024, 8 * 32 + 64, ob4, hb4);
       }
-      if (wide) return large ? launch_pack(string_pack_kernel<true, 2, 16, true>, 1024, 16 * 32 + 128, ob, hb) : launch_pack(string_pack_kernel<false, 2, 16, true>, 1024, 16 * 32 + 128, ob, hb);
-      return large ? launch_pack(string_pack_kernel<true, 2, 8, true>, 512, 8 * 32 + 128, ob, hb) : launch_pack(string_pack_kernel<false, 2, 8, true>, 512, 8 * 32 + 128, ob, hb);
+      if (wide) return large ? launch_pack(string_pack_kernel<true, 2, 16, true>, 1024, 16 * 32 + 64, ob, hb) : launch_pack(string_pack_kernel<false, 2, 16, true>, 1024, 16 * 32 + 64, ob, hb);
+      return large ? launch_pack(string_pack_kernel<true, 2, 8, true>, 512, 8 * 32 + 64, ob, hb) : launch_pack(string_pack_kernel<false, 2, 8, true>, 512, 8 * 32 + 64, ob, hb);
     }
   }
   if (job->heap_len == 0 && !getenv("DMB_STR_NO_INLINE_KERNEL")) {  // no heap: inlined strings only, whole-vector tiles
