@@ -12,37 +12,44 @@
 // Replaces the reference's row-at-a-time appends src/duckdb_native.c:1116-1235 (one FFI call and
 // one duckdb_append_* per cell); the vectors are what duckdb_append_data_chunk (:2109-2132) takes.
 
+#include <type_traits>
+
 #include "dmb_common.cuh"
 
 namespace dmb {
 
-// `take` (<= 57) bits starting at bit position p of an LSB bitmap of nbytes bytes
-__device__ __forceinline__ uint64_t load_bits(const uint8_t *bm, int64_t nbytes, int64_t p, int take) {
-  int64_t b0 = p >> 3;
-  uint64_t acc = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    int64_t b = b0 + k;
-    uint64_t byte = b < nbytes ? (uint64_t)__ldg(bm + b) : 0ull;
-    acc |= byte << (8 * k);
-  }
-  acc >>= (p & 7);
-  return take >= 64 ? acc : (acc & ((1ull << take) - 1ull));
+// An LSB bitmap read as aligned 32-bit words: `w` is the bitmap address rounded down to 4 bytes and
+// `base` the bit position of row 0 counted from there (Arrow array offset + the rounded-off bytes).
+struct BitSrc {
+  const uint32_t *w;
+  int64_t base;
+};
+__device__ __forceinline__ BitSrc bit_src(const uint8_t *bm, int64_t bit_offset) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(bm);
+  return BitSrc{reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3), bit_offset + (int64_t)(a & 3u) * 8};
+}
+
+// `take` (1..32) bits from bit position p; only the words that hold a requested bit are touched
+__device__ __forceinline__ uint32_t load_bits32(const uint32_t *w, int64_t p, int take) {
+  const int64_t wi = p >> 5;
+  const int s = (int)(p & 31);
+  const uint32_t lo = __ldg(w + wi);
+  const uint32_t hi = (s + take > 32) ? __ldg(w + wi + 1) : 0u;
+  const uint32_t r = __funnelshift_r(lo, hi, (uint32_t)s);
+  return take >= 32 ? r : (r & ((1u << take) - 1u));
 }
 
 // 64 validity bits for output word w (rows 64w..64w+63), rows >= nrows are 0
-__device__ __forceinline__ uint64_t rev_valid_word(const uint8_t *bm, int64_t bit_offset, int64_t nrows, int64_t w) {
-  int64_t r0 = w << 6;
+__device__ __forceinline__ uint64_t rev_valid_word(const BitSrc &bs, bool has_bm, int64_t nrows, int64_t w) {
+  const int64_t r0 = w << 6;
   if (r0 >= nrows) return 0ull;
-  int64_t left = nrows - r0;
-  int live = left < 64 ? (int)left : 64;
-  if (!bm) return live == 64 ? ~0ull : ((1ull << live) - 1ull);
-  int64_t nbytes = (bit_offset + nrows + 7) >> 3;
-  int64_t p = bit_offset + r0;
-  uint64_t lo = load_bits(bm, nbytes, p, 32);
-  uint64_t hi = load_bits(bm, nbytes, p + 32, 32);
-  uint64_t word = lo | (hi << 32);
-  return live == 64 ? word : (word & ((1ull << live) - 1ull));
+  const int64_t left = nrows - r0;
+  const int live = left < 64 ? (int)left : 64;
+  if (!has_bm) return live == 64 ? ~0ull : ((1ull << live) - 1ull);
+  const int64_t p = bs.base + r0;
+  const uint64_t lo = load_bits32(bs.w, p, live < 32 ? live : 32);
+  const uint64_t hi = live > 32 ? load_bits32(bs.w, p + 32, live - 32) : 0u;
+  return lo | (hi << 32);
 }
 
 template <typename S, typename D>
@@ -52,62 +59,131 @@ __device__ __forceinline__ D narrow(const S &v) {
   return d;
 }
 
-template <typename S, typename D>
-__device__ __forceinline__ void rev_convert(const dmb_rev_fixed_job &job, int64_t nrows) {
-  constexpr int W = sizeof(S) > sizeof(D) ? sizeof(S) : sizeof(D);
-  constexpr int R = 16 / W;
-  using PS = Pack<S, R>;
-  using PD = Pack<D, R>;
-  const S *in = reinterpret_cast<const S *>(job.in_values);
-  D *out = reinterpret_cast<D *>(job.out_data);
-  const uint8_t *bm = job.in_validity;
-  const int64_t nbytes = (job.in_bit_offset + nrows + 7) >> 3;
-  const int64_t nvec = nrows / R;
-  const bool in_vec_ok = (reinterpret_cast<uintptr_t>(in) % sizeof(PS)) == 0;
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += stride) {
-    PS x;
-    if (in_vec_ok) {
-      x = ld_stream(reinterpret_cast<const PS *>(in) + v);
-    } else {
-#pragma unroll
-      for (int r = 0; r < R; ++r) x.v[r] = in[v * R + r];
-    }
-    uint32_t bits = bm ? (uint32_t)load_bits(bm, nbytes, job.in_bit_offset + v * R, R) : 0xffffffffu;
-    PD y;
-#pragma unroll
-    for (int r = 0; r < R; ++r) y.v[r] = ((bits >> r) & 1u) ? narrow<S, D>(x.v[r]) : narrow<S, D>(S{});
-    st_stream(reinterpret_cast<PD *>(out) + v, y);
+// words [ws, ws+4] of the 8 words (a, b), shifted right by sh bits: the 16 bytes that start m = 4*ws + sh/8
+// bytes into a
+__device__ __forceinline__ uint4 shift_words(const uint4 &a, const uint4 &b, int ws, uint32_t sh) {
+  uint32_t w0, w1, w2, w3, w4;
+  switch (ws) {
+    case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
+    case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
+    case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
+    default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
   }
-  for (int64_t row = nvec * R + (int64_t)blockIdx.x * kThreads + threadIdx.x; row < nrows; row += stride) {
-    bool valid = bm ? (load_bits(bm, nbytes, job.in_bit_offset + row, 1) != 0) : true;
-    out[row] = valid ? narrow<S, D>(in[row]) : narrow<S, D>(S{});
+  return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+
+// keep-mask of 32-bit word i of a 16-byte vector of 16/W elements, bit r of `bits` = element r valid
+template <int W>
+__device__ __forceinline__ uint32_t word_keep(uint32_t bits, int i) {
+  if (W >= 4) return ((bits >> (i * 4 / W)) & 1u) ? 0xffffffffu : 0u;
+  if (W == 2) {
+    const uint32_t b = bits >> (2 * i);
+    return ((b & 1u) ? 0x0000ffffu : 0u) | ((b & 2u) ? 0xffff0000u : 0u);
+  }
+  const uint32_t b = bits >> (4 * i);
+  return ((b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21)) * 0xffu;
+}
+
+// Same-width copy with NULL payloads zeroed.  The Arrow slice start is only element-aligned, so the input is
+// read as the aligned 16-byte vectors around it (4 per thread in flight); a lane takes the vector that follows
+// its own from its neighbour by shuffle and the byte shift is a funnel shift.
+template <int W>
+__device__ __forceinline__ void rev_copy(const dmb_rev_fixed_job &job, int64_t nrows) {
+  constexpr int R = 16 / W;
+  constexpr int U = 4;
+  const uint8_t *in = reinterpret_cast<const uint8_t *>(job.in_values);
+  uint8_t *out = reinterpret_cast<uint8_t *>(job.out_data);
+  const int m = (int)(reinterpret_cast<uintptr_t>(in) & 15u);
+  const uint4 *al = reinterpret_cast<const uint4 *>(in - m);
+  const int ws = m >> 2;
+  const uint32_t sh = (uint32_t)(m & 3) * 8u;
+  const bool has_bm = job.in_validity != nullptr;
+  const BitSrc bs = bit_src(job.in_validity, job.in_bit_offset);
+  const int64_t nvec = nrows / R;
+  const int lane = threadIdx.x & 31;
+  for (int64_t base = (int64_t)blockIdx.x * (U * kThreads); base < nvec; base += (int64_t)gridDim.x * (U * kThreads)) {
+    uint4 a[U], b[U];
+    uint32_t bits[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + u * kThreads + threadIdx.x;
+      a[u] = v < nvec ? ld_stream(al + v) : make_uint4(0, 0, 0, 0);
+    }
+    if (m) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = base + u * kThreads + threadIdx.x;
+        b[u].x = __shfl_down_sync(0xffffffffu, a[u].x, 1);
+        b[u].y = __shfl_down_sync(0xffffffffu, a[u].y, 1);
+        b[u].z = __shfl_down_sync(0xffffffffu, a[u].z, 1);
+        b[u].w = __shfl_down_sync(0xffffffffu, a[u].w, 1);
+        if (v < nvec && (lane == 31 || v + 1 >= nvec)) b[u] = ld_stream(al + v + 1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + u * kThreads + threadIdx.x;
+      bits[u] = (has_bm && v < nvec) ? load_bits32(bs.w, bs.base + v * R, R) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + u * kThreads + threadIdx.x;
+      if (v >= nvec) continue;
+      uint4 o = m ? shift_words(a[u], b[u], ws, sh) : a[u];
+      o.x &= word_keep<W>(bits[u], 0);
+      o.y &= word_keep<W>(bits[u], 1);
+      o.z &= word_keep<W>(bits[u], 2);
+      o.w &= word_keep<W>(bits[u], 3);
+      st_stream(reinterpret_cast<uint4 *>(out) + v, o);
+    }
+  }
+  // the last nrows % R rows
+  if (blockIdx.x == 0) {
+    for (int64_t row = nvec * R + threadIdx.x; row < nrows; row += kThreads) {
+      const bool valid = has_bm ? (load_bits32(bs.w, bs.base + row, 1) != 0u) : true;
+      for (int k = 0; k < W; ++k) out[row * W + k] = valid ? in[row * W + k] : (uint8_t)0;
+    }
   }
 }
 
-// Arrow bool bits -> bool bytes: thread handles 8 rows -> one 8-byte store
+// decimal128 -> narrower DECIMAL: low bytes, NULL payloads zeroed
+template <typename D>
+__device__ __forceinline__ void rev_narrow(const dmb_rev_fixed_job &job, int64_t nrows) {
+  const uint64_t *in = reinterpret_cast<const uint64_t *>(job.in_values);  // Arrow buffers are 8-byte aligned
+  D *out = reinterpret_cast<D *>(job.out_data);
+  const bool has_bm = job.in_validity != nullptr;
+  const BitSrc bs = bit_src(job.in_validity, job.in_bit_offset);
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t row = (int64_t)blockIdx.x * kThreads + threadIdx.x; row < nrows; row += stride) {
+    const uint64_t lo = __ldcs(in + 2 * row);
+    const bool valid = has_bm ? (load_bits32(bs.w, bs.base + row, 1) != 0u) : true;
+    out[row] = valid ? narrow<uint64_t, D>(lo) : D{};
+  }
+}
+
+// Arrow bool bits -> bool bytes: a thread handles 16 rows -> one 16-byte store
 __device__ __forceinline__ void rev_bits_to_bool(const dmb_rev_fixed_job &job, int64_t nrows) {
-  const uint8_t *vals = reinterpret_cast<const uint8_t *>(job.in_values);
-  const uint8_t *bm = job.in_validity;
   uint8_t *out = reinterpret_cast<uint8_t *>(job.out_data);
-  const int64_t nbytes = (job.in_bit_offset + nrows + 7) >> 3;
-  const int64_t ngroups = (nrows + 7) >> 3;
+  const bool has_bm = job.in_validity != nullptr;
+  const BitSrc vs = bit_src(reinterpret_cast<const uint8_t *>(job.in_values), job.in_bit_offset);
+  const BitSrc bs = bit_src(job.in_validity, job.in_bit_offset);
+  const int64_t ngroups = (nrows + 15) >> 4;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += stride) {
-    int64_t r0 = g << 3;
-    int live = nrows - r0 < 8 ? (int)(nrows - r0) : 8;
-    uint32_t bits = (uint32_t)load_bits(vals, nbytes, job.in_bit_offset + r0, live);
-    if (bm) bits &= (uint32_t)load_bits(bm, nbytes, job.in_bit_offset + r0, live);
-    uint64_t bytes = spread8(bits);
-    if (live == 8) {
-      __stcs(reinterpret_cast<unsigned long long *>(out + r0), bytes);
+    const int64_t r0 = g << 4;
+    const int live = nrows - r0 < 16 ? (int)(nrows - r0) : 16;
+    uint32_t bits = load_bits32(vs.w, vs.base + r0, live);
+    if (has_bm) bits &= load_bits32(bs.w, bs.base + r0, live);
+    const uint64_t lo = spread8(bits), hi = spread8(bits >> 8);
+    if (live == 16) {
+      st_stream(reinterpret_cast<uint4 *>(out + r0), make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)));
     } else {
-      for (int k = 0; k < live; ++k) out[r0 + k] = (uint8_t)(bytes >> (8 * k));
+      for (int k = 0; k < live; ++k) out[r0 + k] = (uint8_t)((k < 8 ? lo >> (8 * k) : hi >> (8 * (k - 8))) & 0xff);
     }
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 rev_fixed_kernel(const dmb_rev_fixed_job *__restrict__ jobs, int64_t nrows) {
   __shared__ dmb_rev_fixed_job s_job;
   if (threadIdx.x < sizeof(dmb_rev_fixed_job) / 8)
@@ -116,15 +192,15 @@ rev_fixed_kernel(const dmb_rev_fixed_job *__restrict__ jobs, int64_t nrows) {
   const dmb_rev_fixed_job &job = s_job;
   if (job.out_data) {
     switch (job.op) {
-      case DMB_REV_COPY1: rev_convert<uint8_t, uint8_t>(job, nrows); break;
-      case DMB_REV_COPY2: rev_convert<uint16_t, uint16_t>(job, nrows); break;
-      case DMB_REV_COPY4: rev_convert<uint32_t, uint32_t>(job, nrows); break;
-      case DMB_REV_COPY8: rev_convert<uint64_t, uint64_t>(job, nrows); break;
-      case DMB_REV_COPY16: rev_convert<u128, u128>(job, nrows); break;
+      case DMB_REV_COPY1: rev_copy<1>(job, nrows); break;
+      case DMB_REV_COPY2: rev_copy<2>(job, nrows); break;
+      case DMB_REV_COPY4: rev_copy<4>(job, nrows); break;
+      case DMB_REV_COPY8: rev_copy<8>(job, nrows); break;
+      case DMB_REV_COPY16: rev_copy<16>(job, nrows); break;
       case DMB_REV_BITS_TO_BOOL: rev_bits_to_bool(job, nrows); break;
-      case DMB_REV_I128_TO_I64: rev_convert<u128, uint64_t>(job, nrows); break;
-      case DMB_REV_I128_TO_I32: rev_convert<u128, uint32_t>(job, nrows); break;
-      case DMB_REV_I128_TO_I16: rev_convert<u128, uint16_t>(job, nrows); break;
+      case DMB_REV_I128_TO_I64: rev_narrow<uint64_t>(job, nrows); break;
+      case DMB_REV_I128_TO_I32: rev_narrow<uint32_t>(job, nrows); break;
+      case DMB_REV_I128_TO_I16: rev_narrow<uint16_t>(job, nrows); break;
       default: break;
     }
   }
@@ -132,9 +208,11 @@ rev_fixed_kernel(const dmb_rev_fixed_job *__restrict__ jobs, int64_t nrows) {
   if (job.out_validity) {
     const int64_t nwords = ((nrows + kVec - 1) / kVec) * DMB_VALIDITY_WORDS;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
+    const bool has_bm = job.in_validity != nullptr;
+    const BitSrc bs = bit_src(job.in_validity, job.in_bit_offset);
     int nulls = 0;
     for (int64_t w = (int64_t)blockIdx.x * kThreads + threadIdx.x; w < nwords; w += stride) {
-      uint64_t word = rev_valid_word(job.in_validity, job.in_bit_offset, nrows, w);
+      uint64_t word = rev_valid_word(bs, has_bm, nrows, w);
       __stcs(reinterpret_cast<unsigned long long *>(job.out_validity + w), word);
       int64_t left = nrows - (w << 6);
       int live = left <= 0 ? 0 : (left < 64 ? (int)left : 64);
@@ -147,63 +225,85 @@ rev_fixed_kernel(const dmb_rev_fixed_job *__restrict__ jobs, int64_t nrows) {
   }
 }
 
+// utf8 -> duckdb_string_t, two rows per thread in flight.  A warp's 32 rows share one validity word (which is also
+// the word the mask slab takes) and read 33 offsets: one per lane plus one for lane 31.
 template <bool LARGE>
 __global__ void __launch_bounds__(kThreads)
 rev_string_kernel(dmb_rev_string_job job, int64_t nrows) {
+  constexpr int U = 2;
+  using off_t = typename std::conditional<LARGE, long long, int>::type;
+  const off_t *off = reinterpret_cast<const off_t *>(job.in_offsets);
   const int lane = threadIdx.x & 31;
-  const int64_t capacity = ((nrows + kVec - 1) / kVec) * (int64_t)kVec;
-  const int64_t nbytes = (job.in_bit_offset + nrows + 7) >> 3;
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  const int64_t capacity = ((nrows + kVec - 1) / kVec) * (int64_t)kVec;  // a multiple of U * kThreads
+  const bool has_bm = job.in_validity != nullptr;
+  const BitSrc bs = bit_src(job.in_validity, job.in_bit_offset);
   uint4 *out = reinterpret_cast<uint4 *>(job.out);
   uint32_t *out_val32 = reinterpret_cast<uint32_t *>(job.out_validity);
   int nulls = 0;
-  // capacity is a multiple of 2048, so every warp iteration is full: ballots are warp-wide
-  for (int64_t row = (int64_t)blockIdx.x * kThreads + threadIdx.x; row < capacity; row += stride) {
-    const bool live = row < nrows;
-    bool valid = live;
-    if (live && job.in_validity) valid = load_bits(job.in_validity, nbytes, job.in_bit_offset + row, 1) != 0;
-    uint4 e = make_uint4(0, 0, 0, 0);
-    if (valid) {
-      int64_t o0, o1;
-      if (LARGE) {
-        const int64_t *off = reinterpret_cast<const int64_t *>(job.in_offsets);
-        o0 = __ldg(off + row); o1 = __ldg(off + row + 1);
-      } else {
-        const int32_t *off = reinterpret_cast<const int32_t *>(job.in_offsets);
-        o0 = __ldg(off + row); o1 = __ldg(off + row + 1);
-      }
-      const uint32_t len = (uint32_t)(o1 - o0);
-      // first 12 bytes of the string with 4 aligned 32-bit loads + funnel shifts
-      const uint8_t *q = job.in_data + o0;
-      const uint32_t *base = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)3);
-      const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3u) * 8u;
-      const uint32_t need = len < 12u ? len : 12u;
-      const uint32_t nw = need ? ((need + (sh >> 3) + 3u) >> 2) : 0u;  // aligned words that hold needed bytes
-      uint32_t w0 = nw > 0 ? __ldg(base) : 0u, w1 = nw > 1 ? __ldg(base + 1) : 0u;
-      uint32_t w2 = nw > 2 ? __ldg(base + 2) : 0u, w3 = nw > 3 ? __ldg(base + 3) : 0u;
-      uint32_t r0 = __funnelshift_r(w0, w1, sh), r1 = __funnelshift_r(w1, w2, sh), r2 = __funnelshift_r(w2, w3, sh);
-      e.x = len;
-      if (len <= 12u) {
-        auto keep = [](uint32_t word, int nb) { return nb >= 4 ? word : (nb <= 0 ? 0u : (word & ((1u << (8 * nb)) - 1u))); };
-        e.y = keep(r0, (int)len);
-        e.z = keep(r1, (int)len - 4);
-        e.w = keep(r2, (int)len - 8);
-      } else {
-        e.y = r0;  // prefix
-        uint64_t p = job.data_host_base + (uint64_t)o0;
-        e.z = (uint32_t)p;
-        e.w = (uint32_t)(p >> 32);
-      }
+  for (int64_t base = (int64_t)blockIdx.x * (U * kThreads); base < capacity; base += (int64_t)gridDim.x * (U * kThreads)) {
+    off_t o0[U], o1[U];
+    uint32_t vb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = base + u * kThreads + threadIdx.x;
+      o0[u] = __ldg(off + (row < nrows ? row : nrows));
     }
-    st_stream(out + row, e);
-    const uint32_t word = __ballot_sync(0xffffffffu, valid);
-    if (lane == 0 && out_val32) out_val32[row >> 5] = word;
-    nulls += (live && !valid) ? 1 : 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = base + u * kThreads + threadIdx.x;
+      const int64_t row0 = row - lane;
+      const int64_t left = nrows - row0;
+      const int live = left <= 0 ? 0 : (left < 32 ? (int)left : 32);
+      vb[u] = live == 0 ? 0u : (has_bm ? load_bits32(bs.w, bs.base + row0, live) : (live == 32 ? 0xffffffffu : ((1u << live) - 1u)));
+      if (lane == 0) {
+        if (out_val32) out_val32[row >> 5] = vb[u];
+        nulls += live - __popc(vb[u]);
+      }
+      o1[u] = __shfl_down_sync(0xffffffffu, o0[u], 1);
+      if (lane == 31) o1[u] = __ldg(off + (row + 1 < nrows ? row + 1 : nrows));
+    }
+    uint32_t w[U][4], sh[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool valid = (vb[u] >> lane) & 1u;
+      const uint32_t len = (uint32_t)(o1[u] - o0[u]);
+      // first 12 bytes of the string with 4 aligned 32-bit loads + funnel shifts
+      const uint8_t *q = job.in_data + o0[u];
+      const uint32_t *b32 = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)3);
+      sh[u] = (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3u) * 8u;
+      const uint32_t need = !valid ? 0u : (len < 12u ? len : 12u);
+      const uint32_t nw = need ? ((need + (sh[u] >> 3) + 3u) >> 2) : 0u;  // aligned words that hold needed bytes
+      w[u][0] = nw > 0 ? __ldg(b32) : 0u;
+      w[u][1] = nw > 1 ? __ldg(b32 + 1) : 0u;
+      w[u][2] = nw > 2 ? __ldg(b32 + 2) : 0u;
+      w[u][3] = nw > 3 ? __ldg(b32 + 3) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = base + u * kThreads + threadIdx.x;
+      const bool valid = (vb[u] >> lane) & 1u;
+      uint4 e = make_uint4(0, 0, 0, 0);
+      if (valid) {
+        const uint32_t len = (uint32_t)(o1[u] - o0[u]);
+        const uint32_t r0 = __funnelshift_r(w[u][0], w[u][1], sh[u]), r1 = __funnelshift_r(w[u][1], w[u][2], sh[u]),
+                       r2 = __funnelshift_r(w[u][2], w[u][3], sh[u]);
+        e.x = len;
+        if (len <= 12u) {
+          auto keep = [](uint32_t word, int nb) { return nb >= 4 ? word : (nb <= 0 ? 0u : (word & ((1u << (8 * nb)) - 1u))); };
+          e.y = keep(r0, (int)len);
+          e.z = keep(r1, (int)len - 4);
+          e.w = keep(r2, (int)len - 8);
+        } else {
+          e.y = r0;  // prefix
+          const uint64_t p = job.data_host_base + (uint64_t)o0[u];
+          e.z = (uint32_t)p;
+          e.w = (uint32_t)(p >> 32);
+        }
+      }
+      st_stream(out + row, e);
+    }
   }
-  if (job.null_count) {
-    nulls = __reduce_add_sync(0xffffffffu, nulls);
-    if (lane == 0 && nulls) atomicAdd(job.null_count, (unsigned long long)nulls);
-  }
+  if (job.null_count && lane == 0 && nulls) atomicAdd(job.null_count, (unsigned long long)nulls);
 }
 
 }  // namespace dmb
@@ -216,8 +316,8 @@ extern "C" int32_t dmb_dev_rev_fixed_batch(const dmb_rev_fixed_job *jobs_dev, co
   if (!jobs_dev || !jobs_host) { set_error("dmb_dev_rev_fixed_batch: jobs is null"); return -1; }
   for (int32_t j = 0; j < njobs; ++j)
     if (jobs_host[j].op < 0 || jobs_host[j].op >= DMB_REV_COUNT) { set_error("dmb_dev_rev_fixed_batch: bad op %d", jobs_host[j].op); return -1; }
-  int64_t blocks = (nrows / 2 + kThreads - 1) / kThreads;  // >= 2 rows per thread at 8 B
-  int64_t max_grid = (int64_t)kNumSMs * 8;
+  int64_t blocks = (nrows / 2 + 4 * kThreads - 1) / (4 * kThreads);  // a CTA iteration moves 4 * 256 vectors of >= 2 rows
+  int64_t max_grid = (int64_t)kNumSMs * 4;
   int gx = (int)(blocks < 1 ? 1 : (blocks < max_grid ? blocks : max_grid));
   rev_fixed_kernel<<<dim3(gx, njobs), kThreads, 0, (cudaStream_t)stream>>>(jobs_dev, nrows);
   return check_cuda(cudaGetLastError(), "rev_fixed_kernel launch");
@@ -227,7 +327,7 @@ extern "C" int32_t dmb_dev_rev_string_batch(const dmb_rev_string_job *job, int64
   if (!job) { set_error("dmb_dev_rev_string_batch: job is null"); return -1; }
   if (nrows <= 0) return 0;
   int64_t capacity = ((nrows + kVec - 1) / kVec) * (int64_t)kVec;
-  int64_t blocks = capacity / kThreads;
+  int64_t blocks = capacity / (2 * kThreads);
   int64_t max_grid = (int64_t)kNumSMs * 8;
   int gx = (int)(blocks < max_grid ? blocks : max_grid);
   if (job->large_offsets) rev_string_kernel<true><<<gx, kThreads, 0, (cudaStream_t)stream>>>(*job, nrows);
