@@ -96,11 +96,18 @@ class HostBatch:
                 heap_base, heap_len = col.heap.ctypes.data, int(col.heap.shape[0])
             elif getattr(col, "inline_only", False):
                 heap_base, heap_len = 1, 0  # DMB_HEAP_INLINE_ONLY
+            dict_ptr = None
+            if getattr(col, "dictionary", None) is not None:  # ENUM: dmb_enum_dict
+                from . import chunks as _ch
+                d_offs, d_data = _ch.enum_dict_arrays(col.dictionary)
+                ed = nat.EnumDict(len(col.dictionary), 0, d_offs.ctypes.data, d_data.ctypes.data)
+                self._keep.append((d_offs, d_data, ed))
+                dict_ptr = C.pointer(ed)
             self._keep.append((data_ptrs, val_ptrs, name))
             self._cols[j] = nat.HostColumn(name, col.type_id, col.phys, col.dec_width, col.dec_scale,
                                            C.cast(data_ptrs.ctypes.data, C.POINTER(C.c_void_p)),
                                            C.cast(val_ptrs.ctypes.data, C.POINTER(C.c_void_p)) if val_ptrs is not None else None,
-                                           heap_base, heap_len)
+                                           heap_base, heap_len, dict_ptr)
         self.struct = nat.HostBatch(ncols, nat_flags(pinned), nchunks, self.counts.ctypes.data, self._cols)
 
 

@@ -29,6 +29,7 @@ T_INVALID, T_BOOLEAN, T_TINYINT, T_SMALLINT, T_INTEGER, T_BIGINT = 0, 1, 2, 3, 4
 T_UTINYINT, T_USMALLINT, T_UINTEGER, T_UBIGINT, T_FLOAT, T_DOUBLE = 6, 7, 8, 9, 10, 11
 T_TIMESTAMP, T_DATE, T_TIME, T_INTERVAL, T_HUGEINT, T_VARCHAR, T_BLOB, T_DECIMAL = 12, 13, 14, 15, 16, 17, 18, 19
 T_TIMESTAMP_S, T_TIMESTAMP_MS, T_TIMESTAMP_NS = 20, 21, 22
+T_ENUM = 23
 T_UUID, T_TIME_TZ, T_TIMESTAMP_TZ, T_UHUGEINT, T_TIME_NS = 27, 30, 31, 32, 39
 
 # enum dmb_phys
@@ -80,6 +81,7 @@ class Column:
     dec_scale: int = 0
     heap: Optional[np.ndarray] = None  # uint8 string heap (VARCHAR/BLOB)
     inline_only: bool = False          # VARCHAR/BLOB: every string is inlined (<= 12 bytes): DMB_HEAP_INLINE_ONLY
+    dictionary: Optional[List[bytes]] = None  # ENUM: the type's labels (duckdb_enum_dictionary_value), indices in `data`
 
     @property
     def width(self) -> int:
@@ -195,6 +197,28 @@ def fixed_column(name: str, type_id: int, values: np.ndarray, counts: np.ndarray
     vslab, val_off = make_validity(valid, counts, null_ptr_when_all_valid)
     return Column(name, type_id, phys, slab, _slab_offsets(counts.shape[0], width), vslab, val_off,
                   dec_width, dec_scale)
+
+
+def enum_column(name: str, labels: Sequence[bytes], indices: np.ndarray, counts: np.ndarray,
+                valid: Optional[np.ndarray] = None, garbage_rng: Optional[np.random.Generator] = None,
+                null_ptr_when_all_valid: bool = True) -> Column:
+    """ENUM column: indices in the width duckdb_enum_internal_type picks (uint8 up to 256 labels, uint16 up to
+    65536, else uint32) + the type's dictionary."""
+    n = len(labels)
+    dt, type_phys = (np.uint8, T_UTINYINT) if n <= 256 else (np.uint16, T_USMALLINT) if n <= 65536 else (np.uint32, T_UINTEGER)
+    col = fixed_column(name, type_phys, np.asarray(indices).astype(dt), counts, valid, garbage_rng=garbage_rng,
+                       null_ptr_when_all_valid=null_ptr_when_all_valid)
+    col.type_id = T_ENUM
+    col.dictionary = [bytes(x) for x in labels]
+    return col
+
+
+def enum_dict_arrays(labels: Sequence[bytes]):
+    """(uint32 offsets [n+1], uint8 data) of a dictionary: the dmb_enum_dict layout"""
+    offs = np.zeros(len(labels) + 1, dtype=np.uint32)
+    np.cumsum([len(x) for x in labels], out=offs[1:])
+    data = np.frombuffer(b"".join(labels) + b"\0", dtype=np.uint8).copy()
+    return offs, data
 
 
 def string_column(name: str, strings: Sequence[Optional[bytes]], counts: np.ndarray,

@@ -29,8 +29,19 @@ double now_ms() {
 
 // page-locked Arrow buffers of one column; exported ArrowArrays share ownership, so an exported
 // array stays valid after duckdb_mb_arrow_destroy / duckdb_mb_gpu_ctx_destroy
+// an ENUM type's dictionary (dmb_enum_dict copied at result_from_chunks); shared with exported Arrow dictionaries
+struct EnumDict {
+  std::vector<uint32_t> offsets;  // size + 1
+  std::vector<char> data;
+  uint32_t max_len = 0;
+  uint32_t *d_offsets = nullptr;  // device copies, staged on first use, owned by the result
+  uint8_t *d_data = nullptr;
+  uint32_t size() const { return (uint32_t)(offsets.size() - 1); }
+};
+
 struct ArrowColOut {
   std::shared_ptr<CtxCore> core;
+  std::shared_ptr<EnumDict> dict;  // dictionary-encoded export (ENUM)
   std::string name, format;
   int64_t length = 0, null_count = 0;
   void *validity = nullptr, *values = nullptr, *data = nullptr;  // values = offsets for utf8
@@ -58,6 +69,7 @@ struct Col {
   bool any_validity = false;
   const uint8_t *heap_base = nullptr;
   uint64_t heap_len = 0;
+  std::shared_ptr<EnumDict> dict;  // ENUM
   // device copy (lives as long as the result)
   bool staged = false;
   uint8_t *d_data = nullptr;
@@ -347,7 +359,7 @@ struct StringRun {
   FixedRun validity;  // bitmap / valid bytes / null count come from the fixed kernel's tile phase
   void *d_scratch = nullptr;
   unsigned long long *d_total = nullptr;
-  unsigned long long *h_ctr = nullptr;  // pinned: [0] total bytes [1] error flags [2] null count
+  unsigned long long *h_ctr = nullptr;  // pinned: [0] total bytes [1] error flags [2] null count [3] ENUM indices past the dictionary
   int mode = 0;
   cudaEvent_t done = nullptr;  // kernel + the small counter copies
 };
@@ -359,7 +371,16 @@ struct StringSource {
   const dmb_vec_desc *vecs = nullptr;
   const uint8_t *heap = nullptr;
   uint64_t heap_host_base = 0, heap_len = 0;
+  const unsigned long long *d_bad = nullptr;  // ENUM: device count of indices past the dictionary
+  size_t max_row_bytes = 0;                   // ENUM: longest label
 };
+
+// a column whose VARCHAR form the device produces: strings, the rendered scalar types, ENUM with its dictionary
+bool text_supported(const Col &col) {
+  if (col.phys == DMB_PHYS_STRING) return true;
+  if (col.type_id == DMB_TYPE_ENUM) return col.dict != nullptr;
+  return dmb_render_supported(col.type_id, col.phys) != 0;
+}
 
 int32_t string_source(Result *r, Scope &sc, int j, StringSource *src) {
   if (stage_column(r, j)) return -1;
@@ -371,6 +392,54 @@ int32_t string_source(Result *r, Scope &sc, int j, StringSource *src) {
     src->heap = col.d_heap;
     src->heap_host_base = col.heap_host_base;
     src->heap_len = col.d_heap_len;
+    return 0;
+  }
+  if (col.type_id == DMB_TYPE_ENUM && col.dict) {
+    // indices -> string_t into the dictionary (kernels_enum.cu); the dictionary bytes are the string heap
+    EnumDict &d = *col.dict;
+    const int64_t nch = r->nchunks;
+    const size_t nslots = (size_t)(nch > 0 ? nch : 1) * DMB_VECTOR_SIZE;
+    if (!d.d_offsets) {
+      d.d_offsets = (uint32_t *)keep_dev(r, d.offsets.size() * sizeof(uint32_t));
+      d.d_data = (uint8_t *)keep_dev(r, d.data.size() + 64);
+      if (!d.d_offsets || !d.d_data) return -1;
+      // small and pageable: synchronous copies, once per result
+      if (check_cuda(cudaMemcpy(d.d_offsets, d.offsets.data(), d.offsets.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "enum dictionary offsets H2D")) return -1;
+      if (!d.data.empty() && check_cuda(cudaMemcpy(d.d_data, d.data.data(), d.data.size(), cudaMemcpyHostToDevice), "enum dictionary data H2D")) return -1;
+      r->bytes_h2d += d.offsets.size() * sizeof(uint32_t) + d.data.size();
+    }
+    dmb_string_t *d_str = (dmb_string_t *)sc.dalloc(nslots * sizeof(dmb_string_t));
+    unsigned long long *d_bad = (unsigned long long *)sc.dalloc(8);
+    std::vector<dmb_vec_desc> vecs((size_t)(nch > 0 ? nch : 1));
+    for (int64_t k = 0; k < nch; ++k) {
+      vecs[(size_t)k].data_off = (uint64_t)k * DMB_VECTOR_SIZE * sizeof(dmb_string_t);
+      vecs[(size_t)k].val_off = (col.any_validity && col.validity[(size_t)k]) ? k * DMB_VALIDITY_WORDS : -1;
+    }
+    if (!d_str || !d_bad) return -1;
+    if (check_cuda(cudaStreamWaitEvent(c.s_compute, col.ev_staged, 0), "wait staged")) return -1;
+    dmb_vec_desc *d_vecs2 = (dmb_vec_desc *)upload_job(sc, vecs.data(), sizeof(dmb_vec_desc) * vecs.size());
+    if (!d_vecs2) return -1;
+    if (check_cuda(cudaMemsetAsync(d_bad, 0, 8, c.s_compute), "enum counter memset")) return -1;
+    dmb_enum_job job;
+    memset(&job, 0, sizeof(job));
+    job.in_data = col.d_data;
+    job.in_validity = col.d_validity;
+    job.vecs = col.d_vecs;
+    job.out = d_str;
+    job.dict_offsets = d.d_offsets;
+    job.dict_data = d.d_data;
+    job.dict_host_base = 1ull << 41;
+    job.bad_index = d_bad;
+    job.dict_size = d.size();
+    job.phys = col.phys;
+    if (dmb_dev_enum_to_string_t(&job, r->d_counts, nch, c.s_compute)) return -1;
+    src->in = d_str;
+    src->vecs = d_vecs2;
+    src->heap = d.d_data;
+    src->heap_host_base = job.dict_host_base;
+    src->heap_len = d.max_len > 12 ? (uint64_t)d.data.size() : 0;  // labels of <= 12 bytes are all inlined: the heap-less kernel
+    src->d_bad = d_bad;
+    src->max_row_bytes = d.max_len;
     return 0;
   }
   if (!dmb_render_supported(col.type_id, col.phys)) {
@@ -420,7 +489,8 @@ int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool
   out->mode = mode;
   out->offsets_bytes = (size_t)(n + 1) * (mode == DMB_STR_ARROW_LARGE ? 8 : 4);
   out->d_offsets = sc.dalloc(out->offsets_bytes + 64);
-  const size_t per_row = col.phys == DMB_PHYS_STRING ? 12 : DMB_RENDER_SLOT_BYTES;  // rendered text: at most one slot per row
+  // rendered text: at most one slot per row; ENUM: at most the longest label per row
+  const size_t per_row = col.phys == DMB_PHYS_STRING ? 12 : (col.type_id == DMB_TYPE_ENUM ? (src.max_row_bytes > 12 ? src.max_row_bytes : 12) : (size_t)dmb_render_slot_bytes(col.type_id));
   out->data_cap = per_row * (size_t)n + (col.phys == DMB_PHYS_STRING ? (size_t)col.d_heap_len : 0) + (mode == DMB_STR_REF_BLOB ? (size_t)n : 0);
   out->d_data = (uint8_t *)sc.dalloc(out->data_cap + 64);
   out->d_scratch = sc.dalloc(dmb_dev_string_scratch_bytes(r->nchunks));
@@ -453,6 +523,7 @@ int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool
   if (check_cuda(cudaMemcpyAsync(out->h_ctr + 0, out->d_total, 8, cudaMemcpyDeviceToHost, c.s_compute), "string total D2H")) return -1;
   if (n > 0 && check_cuda(cudaMemcpyAsync(out->h_ctr + 1, (unsigned long long *)out->d_scratch + 1, 8, cudaMemcpyDeviceToHost, c.s_compute), "string flags D2H")) return -1;
   if (check_cuda(cudaMemcpyAsync(out->h_ctr + 2, out->validity.d_null_count, 8, cudaMemcpyDeviceToHost, c.s_compute), "null count D2H")) return -1;
+  if (src.d_bad && check_cuda(cudaMemcpyAsync(out->h_ctr + 3, src.d_bad, 8, cudaMemcpyDeviceToHost, c.s_compute), "enum counter D2H")) return -1;
   cudaEventRecord(done, c.s_compute);
   out->done = done;
   return 0;
@@ -460,6 +531,7 @@ int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool
 
 int32_t string_flags_error(unsigned long long flags) {
   if (!flags) return 0;
+  if (flags & (1ull << 63)) { set_error("ENUM index outside the type's dictionary"); return -1; }
   if (flags & 4) set_error("string_t pointer outside the registered heap");
   else if (flags & 2) set_error("utf8 data exceeds int32 offsets");
   else set_error("a 1024-row tile holds more than 4 GiB of string bytes");
@@ -506,6 +578,9 @@ bool arrow_map(const Col &col, ArrowMap *m) {
       snprintf(buf, sizeof(buf), "d:%d,%d", col.dec_width > 0 ? col.dec_width : 38, col.dec_scale);
       m->format = buf;
       return true;
+    case DMB_TYPE_ENUM:  // dictionary-encoded: the indices as stored, the labels as the dictionary (export_column)
+      if (!col.dict) { set_error("ENUM column without a dictionary"); return false; }
+      return same(col.phys == DMB_PHYS_U8 ? "C" : col.phys == DMB_PHYS_U16 ? "S" : "I");
     case DMB_TYPE_VARCHAR: m->is_string = true; m->format = "u"; return true;
     case DMB_TYPE_BLOB: m->is_string = true; m->format = "z"; return true;
     default: set_error("column type %d has no Arrow mapping", col.type_id); return false;
@@ -527,6 +602,7 @@ int32_t launch_arrow_col(Result *r, Scope &sc, int j, int string_mode, Pending *
   p->out->core = r->core;
   p->out->name = col.name;
   p->out->length = r->nrows;
+  if (col.type_id == DMB_TYPE_ENUM) p->out->dict = col.dict;
   if (p->map.is_string) {
     p->sr = StringRun();
     if (run_string(r, sc, j, string_mode, true, false, &p->sr)) return -1;
@@ -551,7 +627,7 @@ int32_t drain_arrow_col(Result *r, Scope &sc, Pending *p) {
     if (s.h_ctr[1] & 2ull) {
       if (s.mode == DMB_STR_ARROW_UTF8) return 1;
     }
-    if (string_flags_error(s.h_ctr[1])) return -1;
+    if (string_flags_error(s.h_ctr[1] | (s.h_ctr[3] ? (1ull << 63) : 0ull))) return -1;
     const size_t total = (size_t)s.h_ctr[0];
     o.values_bytes = s.offsets_bytes;
     o.validity_bytes = s.validity.bitmap_bytes;
@@ -665,6 +741,7 @@ struct ExportPriv {
   const void *buffers[3] = {nullptr, nullptr, nullptr};
   std::vector<ArrowArray *> child_arrays;
   std::vector<ArrowSchema *> child_schemas;
+  std::shared_ptr<EnumDict> dict;  // a dictionary array's buffers
   std::string format, name;
 };
 
@@ -674,6 +751,11 @@ void release_array(ArrowArray *a) {
   for (ArrowArray *ch : p->child_arrays) {
     if (ch->release) ch->release(ch);
     free(ch);
+  }
+  if (a->dictionary) {
+    if (a->dictionary->release) a->dictionary->release(a->dictionary);
+    free(a->dictionary);
+    a->dictionary = nullptr;
   }
   delete p;
   a->release = nullptr;
@@ -685,6 +767,11 @@ void release_schema(ArrowSchema *s) {
   for (ArrowSchema *ch : p->child_schemas) {
     if (ch->release) ch->release(ch);
     free(ch);
+  }
+  if (s->dictionary) {
+    if (s->dictionary->release) s->dictionary->release(s->dictionary);
+    free(s->dictionary);
+    s->dictionary = nullptr;
   }
   delete p;
   s->release = nullptr;
@@ -705,6 +792,21 @@ void export_column(const std::shared_ptr<ArrowColOut> &o, ArrowArray *a, ArrowSc
     a->buffers = p->buffers;
     a->release = release_array;
     a->private_data = p;
+    if (o->dict) {  // ENUM: the labels as a utf8 dictionary array (no nulls), buffers shared with the result
+      static const char kNoBytes[1] = {0};
+      ArrowArray *da = (ArrowArray *)calloc(1, sizeof(ArrowArray));
+      ExportPriv *dp = new ExportPriv();
+      dp->dict = o->dict;
+      da->length = (int64_t)o->dict->size();
+      dp->buffers[0] = nullptr;
+      dp->buffers[1] = o->dict->offsets.data();
+      dp->buffers[2] = o->dict->data.empty() ? kNoBytes : o->dict->data.data();
+      da->n_buffers = 3;
+      da->buffers = dp->buffers;
+      da->release = release_array;
+      da->private_data = dp;
+      a->dictionary = da;
+    }
   }
   if (s) {
     ExportPriv *p = new ExportPriv();
@@ -716,6 +818,16 @@ void export_column(const std::shared_ptr<ArrowColOut> &o, ArrowArray *a, ArrowSc
     s->flags = 2;  // ARROW_FLAG_NULLABLE
     s->release = release_schema;
     s->private_data = p;
+    if (o->dict) {
+      ArrowSchema *ds = (ArrowSchema *)calloc(1, sizeof(ArrowSchema));
+      ExportPriv *dp = new ExportPriv();
+      dp->format = "u";
+      ds->format = dp->format.c_str();
+      ds->name = dp->name.c_str();
+      ds->release = release_schema;
+      ds->private_data = dp;
+      s->dictionary = ds;
+    }
   }
 }
 
@@ -742,7 +854,7 @@ bool typed_map(const Col &col, TypedMap *m) {
     default:
       // DECIMAL, HUGEINT, UHUGEINT, INTERVAL, TIME*, BLOB, UUID stay Value::String (libduckdb's
       // text rendering) in the reference, src/duckdb_parsing.mbt:120-141
-      if (dmb_render_supported(col.type_id, col.phys)) { m->tag = DMB_VALUE_STRING; m->op = -1; m->width = 0; return true; }
+      if (text_supported(col)) { m->tag = DMB_VALUE_STRING; m->op = -1; m->width = 0; return true; }
       set_error("column type %d is a text-rendered Value::String in the reference; its rendering is not reproduced on the device", col.type_id);
       return false;
   }
@@ -756,7 +868,7 @@ int32_t text_column_out(Result *r, Scope &sc, int j, TypedOut &t) {
   StringRun s;
   if (run_string(r, sc, j, DMB_STR_ARROW_UTF8, false, true, &s)) return -1;
   if (check_cuda(cudaEventSynchronize(s.done), "string kernel wait")) return -1;
-  if (string_flags_error(s.h_ctr[1])) return -1;
+  if (string_flags_error(s.h_ctr[1] | (s.h_ctr[3] ? (1ull << 63) : 0ull))) return -1;
   const size_t total = (size_t)s.h_ctr[0];
   t.offsets = keep_pin(r, s.offsets_bytes);
   t.data = keep_pin(r, total);
@@ -820,7 +932,7 @@ int32_t text_column(Result *r, int j, dmb_typed_column *out) {
   CtxCore &c = *r->core;
   if (!c.bind()) return -1;
   const int64_t n = r->nrows;
-  if (col.phys != DMB_PHYS_STRING && !dmb_render_supported(col.type_id, col.phys)) {
+  if (!text_supported(col)) {
     set_error("column %d (type %d): libduckdb's text rendering of this type is not reproduced on the device", j, col.type_id);
     return -1;
   }
@@ -899,7 +1011,7 @@ moonbit_bytes_t getter_string(Result *r, int32_t col_idx, bool nullable) {
   std::lock_guard<std::mutex> g(c.mu);
   if (!c.bind()) return empty_bytes();
   const Col &col = r->cols[(size_t)col_idx];
-  if (col.phys != DMB_PHYS_STRING && !dmb_render_supported(col.type_id, col.phys)) {
+  if (!text_supported(col)) {
     // duckdb_value_varchar of FLOAT/DOUBLE (shortest round-trip digits), HUGEINT, INTERVAL, TIME*, UUID, BLOB
     set_error("get_column_string: libduckdb's text rendering of column type %d is not reproduced on the device", col.type_id);
     return empty_bytes();
@@ -908,7 +1020,7 @@ moonbit_bytes_t getter_string(Result *r, int32_t col_idx, bool nullable) {
   StringRun s;
   if (run_string(r, sc, col_idx, DMB_STR_REF_BLOB, false, nullable, &s)) return empty_bytes();
   if (check_cuda(cudaEventSynchronize(s.done), "string kernel wait")) return empty_bytes();
-  if (string_flags_error(s.h_ctr[1])) return empty_bytes();
+  if (string_flags_error(s.h_ctr[1] | (s.h_ctr[3] ? (1ull << 63) : 0ull))) return empty_bytes();
   const uint64_t stream_total = s.h_ctr[0], nulls = s.h_ctr[2];
   const uint64_t total_data_len = stream_total - nulls;
   const int64_t total64 = 8 + (int64_t)total_data_len + (nullable ? row_count : 0);
@@ -976,6 +1088,21 @@ extern "C" duckdb_mb_arrow_result *duckdb_mb_gpu_result_from_chunks(duckdb_mb_gp
     }
     col.heap_base = (const uint8_t *)hc.heap_base;
     col.heap_len = hc.heap_len;
+    if (hc.type_id == DMB_TYPE_ENUM) {
+      if (hc.phys != DMB_PHYS_U8 && hc.phys != DMB_PHYS_U16 && hc.phys != DMB_PHYS_U32) { set_error("column %d: ENUM indices are uint8/uint16/uint32", j); return nullptr; }
+      const dmb_enum_dict *d = hc.dict;
+      if (!d || !d->offsets || (d->size && d->offsets[d->size] && !d->data)) { set_error("column %d: ENUM column without a dictionary", j); return nullptr; }
+      auto dict = std::make_shared<EnumDict>();
+      dict->offsets.assign(d->offsets, d->offsets + (size_t)d->size + 1);
+      if (dict->offsets[0] != 0 || dict->offsets[d->size] > 0x7fffffffu) { set_error("column %d: ENUM dictionary offsets must start at 0 and stay below 2 GiB", j); return nullptr; }
+      for (uint32_t i = 0; i < d->size; ++i) {
+        if (dict->offsets[i + 1] < dict->offsets[i]) { set_error("column %d: ENUM dictionary offsets are not monotonic", j); return nullptr; }
+        const uint32_t len = dict->offsets[i + 1] - dict->offsets[i];
+        if (len > dict->max_len) dict->max_len = len;
+      }
+      if (d->offsets[d->size]) dict->data.assign(d->data, d->data + d->offsets[d->size]);
+      col.dict = dict;
+    }
   }
   return r.release();
 }

@@ -1584,7 +1584,13 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
     const double heap_per_row = (double)job->heap_len / (double)nrows;
     // the pipeline needs three CTAs per SM to hide its latencies: S[2] + O + H[2] <= ~72 KiB, i.e. a heap span of
     // <= 18 KiB per 512-row tile.  Longer strings come in long runs, which is what the run-gather is good at.
-    if (heap_per_row <= 29.5) {
+    // Largest heap stage of a 512-row tile that still leaves three CTAs per SM (228 KiB of shared memory, 1 KiB
+    // reserved per CTA; smem = tail + S[2] + O (= hb + 2048) + H[2]).  Measured on the C3 shape (30.8 heap bytes per
+    // row): three CTAs 0.98 ms, two CTAs 1.21 ms, the run-gather kernel 1.17 ms per 50 M rows.
+    constexpr uint32_t kHb3 = ((233472u / 3u - 1024u - kPackTail - 2u * 512u * 16u - 2048u - 32u - 128u) / 3u) & ~127u;
+    static const double min_slack = getenv("DMB_STR_PACK_MIN_SLACK") ? atof(getenv("DMB_STR_PACK_MIN_SLACK")) : 1.04;
+    static const double hpr_limit = getenv("DMB_STR_PACK_HPR_LIMIT") ? atof(getenv("DMB_STR_PACK_HPR_LIMIT")) : ((double)kHb3 - 1024.0 - 128.0) / (512.0 * min_slack);
+    if (heap_per_row <= hpr_limit) {
       static const double slack = getenv("DMB_STR_PACK_SLACK") ? atof(getenv("DMB_STR_PACK_SLACK")) : 1.15;
       // 512-row tiles, 8 worker warps, 3 CTAs per SM
       // (measured on the C2 columns: the 16-warp CTAs are no faster, so they stay an experiment: DMB_STR_PACK_NW=16)
@@ -1592,6 +1598,9 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
       const int rows = wide ? 1024 : 512;
       uint32_t hb = ((uint32_t)(heap_per_row * rows * slack) + 1024u + 127u) & ~127u;
       if (hb < 2048u) hb = 2048u;
+      // a stage a little tighter than `slack` asks for rather than a third CTA lost (tiles that overflow the stage
+      // are copied row by row: min_slack keeps them rare)
+      if (!wide && hb > kHb3 && (double)kHb3 >= heap_per_row * rows * min_slack + 1024.0) hb = kHb3;
       const uint32_t ob = hb + (wide ? 4096u : 2048u);  // inlined rows add at most 12 bytes each; a tile that exceeds the stage is copied row by row
       // few heap bytes per row (codes, short names): 1024-row tiles, 4 rows per thread, halve the per-tile costs
       static const double r4_limit = getenv("DMB_STR_PACK_R4_LIMIT") ? atof(getenv("DMB_STR_PACK_R4_LIMIT")) : 9.5;

@@ -51,10 +51,20 @@ class RevStringJob(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class EnumDict(C.Structure):
+    _fields_ = [("size", C.c_uint32), ("reserved", C.c_uint32), ("offsets", C.c_void_p), ("data", C.c_void_p)]
+
+
+class EnumJob(C.Structure):
+    _fields_ = [("in_data", C.c_void_p), ("in_validity", C.c_void_p), ("vecs", C.c_void_p), ("out", C.c_void_p),
+                ("dict_offsets", C.c_void_p), ("dict_data", C.c_void_p), ("dict_host_base", C.c_uint64),
+                ("bad_index", C.c_void_p), ("dict_size", C.c_uint32), ("phys", C.c_int32)]
+
+
 class HostColumn(C.Structure):
     _fields_ = [("name", C.c_char_p), ("type_id", C.c_int32), ("phys", C.c_int32), ("dec_width", C.c_int32),
                 ("dec_scale", C.c_int32), ("data", C.POINTER(C.c_void_p)), ("validity", C.POINTER(C.c_void_p)),
-                ("heap_base", C.c_void_p), ("heap_len", C.c_uint64)]
+                ("heap_base", C.c_void_p), ("heap_len", C.c_uint64), ("dict", C.POINTER(EnumDict))]
 
 
 class HostBatch(C.Structure):
@@ -92,7 +102,7 @@ CHUNK_SINK = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_uint32, C.POINTER
 EXPORTED_SYMBOLS = [
     "dmb_dev_fixed_batch", "dmb_op_out_width", "dmb_phys_width", "dmb_dev_string_scratch_bytes",
     "dmb_dev_string_error", "dmb_dev_string_batch", "dmb_dev_rev_fixed_batch", "dmb_dev_rev_string_batch",
-    "dmb_dev_valid_bytes_to_masks", "dmb_dev_make_string_t", "dmb_render_supported", "dmb_render_slot_bytes", "dmb_dev_render_text",
+    "dmb_dev_valid_bytes_to_masks", "dmb_dev_make_string_t", "dmb_render_supported", "dmb_render_slot_bytes", "dmb_dev_render_text", "dmb_dev_enum_to_string_t",
     "duckdb_mb_gpu_last_error", "duckdb_mb_gpu_device_count", "duckdb_mb_gpu_ctx_create",
     "duckdb_mb_gpu_ctx_destroy", "duckdb_mb_gpu_ctx_sync", "duckdb_mb_gpu_host_alloc", "duckdb_mb_gpu_host_free",
     "duckdb_mb_gpu_result_from_chunks", "duckdb_mb_gpu_result_materialise_arrow",
@@ -171,6 +181,8 @@ def lib():
     L.dmb_dev_render_text.argtypes = [C.POINTER(RenderJob), vp, i64, vp]
     L.dmb_dev_valid_bytes_to_masks.restype = i32
     L.dmb_dev_valid_bytes_to_masks.argtypes = [vp, vp, vp, i64, vp]
+    L.dmb_dev_enum_to_string_t.restype = i32
+    L.dmb_dev_enum_to_string_t.argtypes = [C.POINTER(EnumJob), vp, i64, vp]
     L.dmb_dev_rev_fixed_batch.restype = i32
     L.dmb_dev_rev_fixed_batch.argtypes = [vp, vp, i32, i64, vp]
     L.dmb_dev_rev_string_batch.restype = i32

@@ -56,6 +56,7 @@ enum dmb_type {
   DMB_TYPE_TIMESTAMP_S = 20,
   DMB_TYPE_TIMESTAMP_MS = 21,
   DMB_TYPE_TIMESTAMP_NS = 22,
+  DMB_TYPE_ENUM = 23,     /* uint8/16/32 indices into the type's dictionary (dmb_enum_dict) */
   DMB_TYPE_UUID = 27,
   DMB_TYPE_TIME_TZ = 30,
   DMB_TYPE_TIMESTAMP_TZ = 31,
@@ -237,6 +238,25 @@ int32_t dmb_render_supported(int32_t type_id, int32_t phys);
 int32_t dmb_render_slot_bytes(int32_t type_id); /* out_heap bytes per row for this type (48, INTERVAL: 80) */
 int32_t dmb_dev_render_text(const dmb_render_job *job, const uint32_t *counts, int64_t nchunks, void *stream);
 
+/* K8: ENUM index vectors -> string_t that refer to the dictionary's labels (<= 12 bytes inlined, else
+ * prefix + dict_host_base + offset), one 2048-entry slot per chunk; feed the result to
+ * dmb_dev_string_batch with the dictionary bytes as the heap.  Rows whose validity bit is clear get a
+ * zero string_t; a valid row whose index is >= dict_size is counted in *bad_index and left empty. */
+typedef struct dmb_enum_job {
+  const void *in_data;            /* index slab                                     */
+  const uint64_t *in_validity;    /* validity slab                                  */
+  const dmb_vec_desc *vecs;       /* [nchunks]                                      */
+  dmb_string_t *out;              /* chunk k at k*2048 entries                      */
+  const uint32_t *dict_offsets;   /* device, [dict_size + 1]                        */
+  const uint8_t *dict_data;       /* device                                         */
+  uint64_t dict_host_base;        /* address the emitted pointers are relative to   */
+  unsigned long long *bad_index;  /* device counter or NULL                         */
+  uint32_t dict_size;
+  int32_t phys;                   /* DMB_PHYS_U8 / U16 / U32                        */
+} dmb_enum_job;
+
+int32_t dmb_dev_enum_to_string_t(const dmb_enum_job *job, const uint32_t *counts, int64_t nchunks, void *stream);
+
 /* K6 reverse (Arrow -> DataChunk vectors), the bulk door behind the appender
  * (reference row-at-a-time path: src/duckdb_native.c:1100-1235; chunk door :2029-2132). */
 typedef struct dmb_rev_fixed_job {
@@ -313,6 +333,18 @@ int32_t duckdb_mb_gpu_ctx_sync(duckdb_mb_gpu_ctx *ctx);
 void *duckdb_mb_gpu_host_alloc(size_t bytes);
 void duckdb_mb_gpu_host_free(void *p);
 
+/* ENUM: the type's dictionary, what duckdb_enum_dictionary_size / duckdb_enum_dictionary_value return,
+ * packed: label i = data[offsets[i] .. offsets[i+1]).  The column's vectors hold the indices in the
+ * width duckdb_enum_internal_type names (phys DMB_PHYS_U8 / U16 / U32).  The reference keeps an ENUM
+ * cell as Value::String of its label (src/duckdb_parsing.mbt:119-122) and maps the column to "string"
+ * in the Arrow schema (src/duckdb_native.c:2314-2339); the Arrow C Data export is dictionary-encoded. */
+typedef struct dmb_enum_dict {
+  uint32_t size;
+  uint32_t reserved;
+  const uint32_t *offsets; /* [size + 1], offsets[0] == 0 */
+  const char *data;
+} dmb_enum_dict;
+
 /* One column of a host chunk batch: the pointers duckdb_vector_get_data /
  * duckdb_vector_get_validity return for each chunk (src/duckdb_native.c:529-530,547). */
 typedef struct dmb_host_column {
@@ -328,6 +360,7 @@ typedef struct dmb_host_column {
    * the pointed-to bytes into pinned memory itself. */
   const void *heap_base;
   uint64_t heap_len;
+  const dmb_enum_dict *dict;        /* ENUM columns: the dictionary (copied by result_from_chunks); else NULL */
 } dmb_host_column;
 
 /* heap_base == DMB_HEAP_INLINE_ONLY (heap_len 0): the caller guarantees that every string of the

@@ -26,7 +26,7 @@ def build(force: bool = False) -> str:
 class OraColumn(C.Structure):
     _fields_ = [("type_id", C.c_int32), ("phys", C.c_int32), ("dec_width", C.c_int32), ("dec_scale", C.c_int32),
                 ("data", C.c_void_p), ("data_off", C.c_void_p), ("validity", C.c_void_p), ("val_off", C.c_void_p),
-                ("name", C.c_char_p)]
+                ("name", C.c_char_p), ("dict_offsets", C.c_void_p), ("dict_data", C.c_void_p), ("dict_size", C.c_uint32)]
 
 
 class OraBatch(C.Structure):
@@ -117,8 +117,16 @@ class OracleResult:
         for i, c in enumerate(batch.columns):
             nm = c.name.encode()
             self._names.append(nm)
+            d_offs = d_data = None
+            labels = getattr(c, "dictionary", None)
+            if labels is not None:  # ENUM
+                d_offs = np.zeros(len(labels) + 1, dtype=np.uint32)
+                np.cumsum([len(x) for x in labels], out=d_offs[1:])
+                d_data = np.frombuffer(b"".join(labels) + b"\0", dtype=np.uint8).copy()
+                self._names.append((d_offs, d_data))
             self._cols[i] = OraColumn(c.type_id, c.phys, c.dec_width, c.dec_scale, _ptr(c.data), _ptr(c.data_off),
-                                      _ptr(c.validity), _ptr(c.val_off), nm)
+                                      _ptr(c.validity), _ptr(c.val_off), nm, _ptr(d_offs), _ptr(d_data),
+                                      0 if labels is None else len(labels))
         self._b = OraBatch(self._counts.shape[0], _ptr(self._counts), n, self._cols)
         self.handle = L.ora_result_create(C.byref(self._b))
         self.nrows = int(L.ora_result_rows(self.handle))

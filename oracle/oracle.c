@@ -41,6 +41,11 @@ typedef struct {
   const uint64_t *validity; /* slab or NULL */
   const int64_t *val_off;   /* [nchunks], -1 = NULL pointer */
   const char *name;
+  /* ENUM (type 23): the type's dictionary as duckdb_enum_dictionary_value returns it, packed:
+   * label i = dict_data[dict_offsets[i] .. dict_offsets[i+1]); vectors hold uint8/16/32 indices */
+  const uint32_t *dict_offsets;
+  const char *dict_data;
+  uint32_t dict_size;
 } ora_column;
 
 typedef struct {
@@ -247,6 +252,19 @@ __attribute__((noinline)) char *ora_value_varchar(ora_result *r, int32_t col, in
     size_t len = strlen(s);
     char *out = (char *)malloc(len + 1);
     memcpy(out, s, len + 1);
+    return out;
+  }
+  if (c->type_id == 23) {
+    /* ENUM: the cell's VARCHAR cast is its dictionary label; the reference keeps it as Value::String
+     * (src/duckdb_parsing.mbt:119-122).  UNPINNED: no reference test or fixture holds an ENUM column. */
+    const uint8_t *p = r->dep_data[col] + (size_t)row * (size_t)PHYS_W[c->phys];
+    uint32_t idx = 0;
+    memcpy(&idx, p, (size_t)PHYS_W[c->phys]); /* little endian: uint8 / uint16 / uint32 */
+    if (!c->dict_offsets || idx >= c->dict_size) return NULL;
+    size_t len = c->dict_offsets[idx + 1] - c->dict_offsets[idx];
+    char *out = (char *)malloc(len + 1);
+    memcpy(out, c->dict_data + c->dict_offsets[idx], len);
+    out[len] = 0;
     return out;
   }
   char buf[96];

@@ -141,12 +141,17 @@ def c5(scale, flush):
         nat.check(L.dmb_dev_rev_fixed_batch(jobs_dev.data_ptr(), C.cast(jobs, C.c_void_p), 4, n, stream), "rev_fixed")
         nat.check(L.dmb_dev_rev_string_batch(C.byref(sjob), n, stream), "rev_string")
     ms = timeit(run)
+    ms_fixed = timeit(lambda: nat.check(L.dmb_dev_rev_fixed_batch(jobs_dev.data_ptr(), C.cast(jobs, C.c_void_p), 4, n, stream), "rev_fixed"))
+    ms_string = timeit(lambda: nat.check(L.dmb_dev_rev_string_batch(C.byref(sjob), n, stream), "rev_string"))
     live = int((offs64[n + off] - offs64[off]).item())
     # SURVEY.md §8d reverse accounting: Arrow buffers read once, vectors + masks written; string bytes are read
     # for the prefix / inline fill only (pointer strings refer to the Arrow data buffer in place)
-    alg = n * (4 + 4) + n * (8 + 8) * 2 + (n // 8 + n) + 4 * (n // 8) * 2 + n // 8 + (4 * (n + 1) + live + 16 * n + 2 * (n // 8))
+    alg_s = 4 * (n + 1) + live + 16 * n + 2 * (n // 8)
+    alg = n * (4 + 4) + n * (8 + 8) * 2 + (n // 8 + n) + 4 * (n // 8) * 2 + n // 8 + alg_s
     report("C5 appender reverse: Arrow (int32,int64,float64,bool,utf8 U[0,24]) -> DataChunk vectors, 10% NULL, bit offset 3",
-           n, alg, ms, {"batch": "50M-row device-resident batch (a 500M-row table is 10 such batches per GPU)"})
+           n, alg, ms, {"batch": "50M-row device-resident batch (a 500M-row table is 10 such batches per GPU)",
+                        "rev_fixed_kernel": {"ms": ms_fixed, "gb_per_s": (alg - alg_s) / 1e6 / ms_fixed},
+                        "rev_string_kernel": {"ms": ms_string, "gb_per_s": alg_s / 1e6 / ms_string}})
 
 
 def main():

@@ -356,3 +356,30 @@ def test_arrow_layout_oracle_against_pyarrow():
             assert got[i] == decimal.Decimal(int(vals[i])).scaleb(-3)
         else:
             assert got[i] is None and bytes(v[16 * i:16 * i + 16]) == bytes(16)
+
+
+def test_oracle_enum_cells_are_their_labels():
+    """ENUM (SURVEY.md §8f item 3): the VARCHAR form of a cell is its dictionary label, kept as Value::String by
+    the reference (src/duckdb_parsing.mbt:119-122).  UNPINNED in the reference; this pins the restatement itself."""
+    import oracle
+    rng = np.random.default_rng(3)
+    n = 5000
+    counts = ch.chunk_counts(n, "ragged", rng)
+    labels = [b"sad", b"ok", b"happy", b"a-label-longer-than-twelve-bytes"]
+    idx = rng.integers(0, len(labels), n)
+    valid = rng.random(n) > 0.25
+    col = ch.enum_column("mood", labels, idx, counts, valid=valid, garbage_rng=rng)
+    assert col.type_id == ch.T_ENUM and col.phys == ch.P_U8
+    ora = oracle.OracleResult(ch.ChunkBatch(counts, [col]))
+    for i in range(0, n, 7):  # per cell (the packed string blob of a column with NULLs loses its tail: DESIGN.md §1)
+        assert ora.cell_is_null(0, i) == (not valid[i])
+        if valid[i]:
+            assert ora.cell_value(0, i) == labels[idx[i]]
+    allv = ch.enum_column("mood", labels, idx, counts)
+    strs, _ = oracle.decode_string(oracle.OracleResult(ch.ChunkBatch(counts, [allv])).get_column("string", 0, False), False)
+    assert strs == [labels[i] for i in idx]
+    wide = ch.enum_column("w", [b"%d" % i for i in range(70_000)], np.array([0, 255, 256, 65_535, 65_536, 69_999]), ch.chunk_counts(6, "full"))
+    assert wide.phys == ch.P_U32
+    ora2 = oracle.OracleResult(ch.ChunkBatch(ch.chunk_counts(6, "full"), [wide]))
+    strs2, _ = oracle.decode_string(ora2.get_column("string", 0, False), False)
+    assert strs2 == [b"0", b"255", b"256", b"65535", b"65536", b"69999"]
