@@ -104,26 +104,27 @@ __device__ __forceinline__ void rev_copy(const dmb_rev_fixed_job &job, int64_t n
   for (int64_t base = (int64_t)blockIdx.x * (U * kThreads); base < nvec; base += (int64_t)gridDim.x * (U * kThreads)) {
     uint4 a[U], b[U];
     uint32_t bits[U];
+    // every load of the iteration is issued before anything waits: the vectors, lane 31's extra vector, the bitmap words
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t v = base + u * kThreads + threadIdx.x;
       a[u] = v < nvec ? ld_stream(al + v) : make_uint4(0, 0, 0, 0);
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + u * kThreads + threadIdx.x;
+      b[u] = make_uint4(0, 0, 0, 0);
+      if (m && v < nvec && (lane == 31 || v + 1 >= nvec)) b[u] = ld_stream(al + v + 1);
+      bits[u] = (has_bm && v < nvec) ? load_bits32(bs.w, bs.base + v * R, R) : 0xffffffffu;
+    }
     if (m) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t v = base + u * kThreads + threadIdx.x;
-        b[u].x = __shfl_down_sync(0xffffffffu, a[u].x, 1);
-        b[u].y = __shfl_down_sync(0xffffffffu, a[u].y, 1);
-        b[u].z = __shfl_down_sync(0xffffffffu, a[u].z, 1);
-        b[u].w = __shfl_down_sync(0xffffffffu, a[u].w, 1);
-        if (v < nvec && (lane == 31 || v + 1 >= nvec)) b[u] = ld_stream(al + v + 1);
+        const uint32_t nx = __shfl_down_sync(0xffffffffu, a[u].x, 1), ny = __shfl_down_sync(0xffffffffu, a[u].y, 1);
+        const uint32_t nz = __shfl_down_sync(0xffffffffu, a[u].z, 1), nw = __shfl_down_sync(0xffffffffu, a[u].w, 1);
+        if (!(lane == 31 || v + 1 >= nvec)) b[u] = make_uint4(nx, ny, nz, nw);
       }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t v = base + u * kThreads + threadIdx.x;
-      bits[u] = (has_bm && v < nvec) ? load_bits32(bs.w, bs.base + v * R, R) : 0xffffffffu;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {

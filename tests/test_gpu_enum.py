@@ -124,3 +124,27 @@ def test_enum_column_without_dictionary_is_rejected(ctx):
     with pytest.raises(Exception, match="dictionary"):
         ar.ArrowResult.from_chunks(ctx, ch.ChunkBatch(counts, [col]))
     assert "dictionary" in nat.last_error()
+
+
+def test_enum_cells_through_connection_query_symbols(ctx):
+    """Connection::query's per-cell loop (duckdb_mb_result_is_null / _value, src/duckdb_native.mbt:477-497) and the
+    columnar string form give the labels; to_typed keeps them as Value::String (src/duckdb_parsing.mbt:119-122)."""
+    from duckdb_mbt_b200 import native as nat
+    from duckdb_mbt_b200.query_result import QueryResult, query_per_cell
+    batch, labels, idx, valid = _enum_batch(5000, 6, 30, "ragged", 123)
+    ora = oracle.OracleResult(batch)
+    with _result(ctx, batch) as res:
+        L, h = res.lib, res.handle
+        assert L.duckdb_mb_result_column_type(h, 0) == ch.T_ENUM
+        for r in range(0, 5000, 61):
+            assert bool(L.duckdb_mb_result_is_null(h, 0, r)) == ora.cell_is_null(0, r) == (not valid[r])
+            assert nat.moonbit_bytes(L.duckdb_mb_result_value(h, 0, r)) == ora.cell_value(0, r)
+            if valid[r]:
+                assert ora.cell_value(0, r) == labels[idx[r]]
+        q = query_per_cell(res)
+        c = QueryResult.from_result(res, q.column_types)
+        assert c.rows == q.rows and c.nulls == q.nulls
+        assert [row[0] for row in q.rows[:50]] == [labels[idx[i]].decode() if valid[i] else "" for i in range(50)]
+        t = c.to_typed()
+        first = int(np.argmax(valid))
+        assert t.get_string(first, 0) == labels[idx[first]].decode()

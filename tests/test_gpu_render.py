@@ -258,3 +258,20 @@ def test_double_shortest_round_trip_rendering(ctx):
             s_ = t.value(int(i)).as_string()
             if s_ not in ("nan", "inf", "-inf"):
                 assert struct.pack("<d", float(s_)) == struct.pack("<d", float(vals[i])), (s_, vals[i])
+
+
+def test_all_reference_fixture_cases_replayed_on_the_gpu(ctx):
+    """Every case of src/duckdb_fixture_cases.mbt (tests/golden/reference_fixture_cases.json) through the device:
+    the columnar string form (K7 render + K5) and Connection::query's per-cell symbols must give the fixture's
+    rows and null masks -- the assertion of src/duckdb_test.mbt:88."""
+    import golden_cases as gc
+    from duckdb_mbt_b200.query_result import QueryResult, query_per_cell
+    for case in gc.CASES:
+        batch = gc.batch_for(case)
+        with _result(ctx, batch) as res:
+            q = QueryResult.from_result(res, [c.type_id for c in batch.columns])
+            assert q.columns == case["columns"], case["name"]
+            assert q.rows == case["rows"], case["name"]
+            assert q.nulls == case["nulls"], case["name"]
+            p = query_per_cell(res)
+            assert p.rows == case["rows"] and p.nulls == case["nulls"], case["name"]

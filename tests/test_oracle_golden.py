@@ -383,3 +383,18 @@ def test_oracle_enum_cells_are_their_labels():
     ora2 = oracle.OracleResult(ch.ChunkBatch(ch.chunk_counts(6, "full"), [wide]))
     strs2, _ = oracle.decode_string(ora2.get_column("string", 0, False), False)
     assert strs2 == [b"0", b"255", b"256", b"65535", b"65536", b"69999"]
+
+
+def test_all_reference_fixture_cases_replayed_on_the_oracle():
+    """Every case of src/duckdb_fixture_cases.mbt (tests/golden/reference_fixture_cases.json): Connection::query's
+    per-cell loop over the oracle (ora_value_is_null / ora_value_varchar, the restatement of
+    src/duckdb_native.c:215-238) must give the fixture's cell strings and null mask."""
+    import golden_cases as gc
+    import oracle
+    assert len(gc.CASES) == 35 and set(gc.INPUTS) == {c["name"] for c in gc.CASES}
+    for case in gc.CASES:
+        r = oracle.OracleResult(gc.batch_for(case))
+        for i, (row, nulls) in enumerate(zip(case["rows"], case["nulls"])):
+            for j, (text, is_null) in enumerate(zip(row, nulls)):
+                assert r.cell_is_null(j, i) == is_null, (case["name"], i, j)
+                assert r.cell_value(j, i).decode() == text, (case["name"], i, j)
