@@ -237,6 +237,7 @@ rev_string_kernel(dmb_rev_string_job job, int64_t nrows) {
   const int lane = threadIdx.x & 31;
   const int64_t capacity = ((nrows + kVec - 1) / kVec) * (int64_t)kVec;  // a multiple of U * kThreads
   const bool has_bm = job.in_validity != nullptr;
+  const bool has_data = job.in_data != nullptr;
   const BitSrc bs = bit_src(job.in_validity, job.in_bit_offset);
   uint4 *out = reinterpret_cast<uint4 *>(job.out);
   uint32_t *out_val32 = reinterpret_cast<uint32_t *>(job.out_validity);
@@ -266,18 +267,20 @@ rev_string_kernel(dmb_rev_string_job job, int64_t nrows) {
     uint32_t w[U][4], sh[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const bool valid = (vb[u] >> lane) & 1u;
-      const uint32_t len = (uint32_t)(o1[u] - o0[u]);
       // first 12 bytes of the string with 4 aligned 32-bit loads + funnel shifts
       const uint8_t *q = job.in_data + o0[u];
       const uint32_t *b32 = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)3);
       sh[u] = (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3u) * 8u;
-      const uint32_t need = !valid ? 0u : (len < 12u ? len : 12u);
-      const uint32_t nw = need ? ((need + (sh[u] >> 3) + 3u) >> 2) : 0u;  // aligned words that hold needed bytes
-      w[u][0] = nw > 0 ? __ldg(b32) : 0u;
-      w[u][1] = nw > 1 ? __ldg(b32 + 1) : 0u;
-      w[u][2] = nw > 2 ? __ldg(b32 + 2) : 0u;
-      w[u][3] = nw > 3 ? __ldg(b32 + 3) : 0u;
+      // all four words, unpredicated: the bytes past the string are the next rows' (or the buffer's 16 bytes of
+      // padding, see the header) and are masked off below
+      if (has_data) {
+        w[u][0] = __ldg(b32);
+        w[u][1] = __ldg(b32 + 1);
+        w[u][2] = __ldg(b32 + 2);
+        w[u][3] = __ldg(b32 + 3);
+      } else {
+        w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u;
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
