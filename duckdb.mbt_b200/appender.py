@@ -152,6 +152,36 @@ class Appender:
     def append_interval(self, months: int, days: int, micros: int):  # src/duckdb_native.c:1511-1533
         self._check(self.lib.duckdb_mb_gpu_append_interval(self.handle, int(months), int(days), int(micros)), "append_interval")
 
+    @staticmethod
+    def _bytes_array(items):
+        """Array[Bytes] of the reference (moonbit_bytes_t* + lengths) as (pointer array, int32 lengths, keep-alive)"""
+        enc = [x.encode("utf-8") if isinstance(x, str) else bytes(x) for x in items]
+        bufs = [C.create_string_buffer(b, len(b) + 1) for b in enc]
+        ptrs = (C.c_void_p * max(len(enc), 1))(*[C.addressof(b) for b in bufs])
+        lens = (C.c_int32 * max(len(enc), 1))(*[len(b) for b in enc])
+        return ptrs, lens, bufs
+
+    def append_list_varchar(self, values):  # src/duckdb_native.mbt:1703-1715 / src/duckdb_native.c:1735-1790
+        p, l, keep = self._bytes_array(values)
+        self._check(self.lib.duckdb_mb_gpu_append_list_varchar(self.handle, p, l, len(values)), "append_list_varchar")
+
+    def append_struct(self, fields, values):  # src/duckdb_native.mbt:1719-1735 / src/duckdb_native.c:1792-1858
+        if len(fields) != len(values):
+            raise ValueError("append_struct: fields and values differ in length")
+        pn, ln, k1 = self._bytes_array(fields)
+        pv, lv, k2 = self._bytes_array(values)
+        self._check(self.lib.duckdb_mb_gpu_append_struct_varchar(self.handle, pn, ln, pv, lv, len(fields)), "append_struct")
+
+    def append_map(self, keys, values):  # src/duckdb_native.mbt:1739-1755 / src/duckdb_native.c:1860-1926
+        if len(keys) != len(values):
+            raise ValueError("append_map: keys and values differ in length")
+        pk, lk, k1 = self._bytes_array(keys)
+        pv, lv, k2 = self._bytes_array(values)
+        self._check(self.lib.duckdb_mb_gpu_append_map_varchar_varchar(self.handle, pk, lk, pv, lv, len(keys)), "append_map")
+
+    def append_list_varchar_value(self, values):  # src/duckdb_native.mbt:1764-1795: a list literal, quotes doubled
+        self.append_varchar("[" + ", ".join("'" + v.replace("'", "''") + "'" for v in values) + "]")
+
     def end_row(self):  # :1052
         self._check(self.lib.duckdb_mb_gpu_end_row(self.handle), "end_row")
 

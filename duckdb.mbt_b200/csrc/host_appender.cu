@@ -579,6 +579,62 @@ extern "C" int32_t duckdb_mb_gpu_append_blob(duckdb_mb_gpu_appender *a, const ui
   return duckdb_mb_gpu_append_varchar(a, bytes, len);
 }
 
+// LIST / STRUCT / MAP cells of the reference's row protocol: the reference serialises them as text and appends that as
+// a VARCHAR cell (src/duckdb_native.c:1735-1790 `["a", "b"]`, :1792-1858 and :1860-1926 `{"k": "v", ...}`; no escaping).
+// The text reaches libduckdb through duckdb_append_varchar, a C string: it ends at the first NUL byte of any item.
+namespace {
+void put_quoted(std::vector<uint8_t> &t, const uint8_t *p, int32_t len) {
+  t.push_back('"');
+  if (p && len > 0) t.insert(t.end(), p, p + len);
+  t.push_back('"');
+}
+int32_t append_text_cell(duckdb_mb_gpu_appender *a, std::vector<uint8_t> &t) {
+  size_t n = 0;
+  while (n < t.size() && t[n] != 0) ++n;  // strlen of the reference's buffer
+  return duckdb_mb_gpu_append_varchar(a, t.data(), (int32_t)n);
+}
+}  // namespace
+
+extern "C" int32_t duckdb_mb_gpu_append_list_varchar(duckdb_mb_gpu_appender *a, const uint8_t *const *values, const int32_t *lens, int32_t count) {
+  if (!a) return 0;
+  if (count < 0 || (count > 0 && (!values || !lens))) { fail(a, "append_list_varchar: bad arguments"); a->state = kError; return 0; }
+  std::vector<uint8_t> t;
+  t.push_back('[');
+  for (int32_t i = 0; i < count; ++i) {
+    if (i > 0) { t.push_back(','); t.push_back(' '); }
+    put_quoted(t, values[i], lens[i]);
+  }
+  t.push_back(']');
+  return append_text_cell(a, t);
+}
+
+static int32_t append_pairs(duckdb_mb_gpu_appender *a, const char *what, const uint8_t *const *keys, const int32_t *key_lens,
+                            const uint8_t *const *values, const int32_t *value_lens, int32_t count) {
+  if (!a) return 0;
+  if (count < 0 || (count > 0 && (!keys || !key_lens || !values || !value_lens))) { fail(a, "%s: bad arguments", what); a->state = kError; return 0; }
+  std::vector<uint8_t> t;
+  t.push_back('{');
+  for (int32_t i = 0; i < count; ++i) {
+    if (i > 0) { t.push_back(','); t.push_back(' '); }
+    put_quoted(t, keys[i], key_lens[i]);
+    t.push_back(':');
+    t.push_back(' ');
+    put_quoted(t, values[i], value_lens[i]);
+  }
+  t.push_back('}');
+  return append_text_cell(a, t);
+}
+
+extern "C" int32_t duckdb_mb_gpu_append_struct_varchar(duckdb_mb_gpu_appender *a, const uint8_t *const *names, const int32_t *name_lens,
+                                                      const uint8_t *const *values, const int32_t *value_lens, int32_t count) {
+  return append_pairs(a, "append_struct_varchar", names, name_lens, values, value_lens, count);
+}
+
+extern "C" int32_t duckdb_mb_gpu_append_map_varchar_varchar(duckdb_mb_gpu_appender *a, const uint8_t *const *keys, const int32_t *key_lens,
+                                                           const uint8_t *const *values, const int32_t *value_lens, int32_t count) {
+  return append_pairs(a, "append_map_varchar_varchar", keys, key_lens, values, value_lens, count);
+}
+
 // INTERVAL cell (src/duckdb_native.c:1511-1533): duckdb_interval {months, days, micros}
 extern "C" int32_t duckdb_mb_gpu_append_interval(duckdb_mb_gpu_appender *a, int32_t months, int32_t days, int64_t micros) {
   if (!a) return 0;

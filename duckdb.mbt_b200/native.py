@@ -127,6 +127,7 @@ EXPORTED_SYMBOLS = [
     "duckdb_mb_gpu_begin_row", "duckdb_mb_gpu_append_int", "duckdb_mb_gpu_append_bigint", "duckdb_mb_gpu_append_double",
     "duckdb_mb_gpu_append_varchar", "duckdb_mb_gpu_append_bool", "duckdb_mb_gpu_append_null", "duckdb_mb_gpu_append_date",
     "duckdb_mb_gpu_append_timestamp", "duckdb_mb_gpu_end_row", "duckdb_mb_gpu_append_blob", "duckdb_mb_gpu_append_decimal",
+    "duckdb_mb_gpu_append_list_varchar", "duckdb_mb_gpu_append_struct_varchar", "duckdb_mb_gpu_append_map_varchar_varchar",
     "duckdb_mb_gpu_append_interval", "duckdb_mb_gpu_appender_set_decimal",
 ]
 
@@ -274,7 +275,9 @@ def lib():
                         ("append_varchar", [C.c_char_p, i32]), ("append_bool", [i32]), ("append_null", []),
                         ("append_date", [i32]), ("append_timestamp", [i64]), ("end_row", []),
                         ("append_blob", [C.c_char_p, i32]), ("append_decimal", [i32, i32, i64, i64]),
-                        ("append_interval", [i32, i32, i64]), ("appender_set_decimal", [i32, i32, i32])):
+                        ("append_interval", [i32, i32, i64]), ("appender_set_decimal", [i32, i32, i32]),
+                        ("append_list_varchar", [vp, vp, i32]), ("append_struct_varchar", [vp, vp, vp, vp, i32]),
+                        ("append_map_varchar_varchar", [vp, vp, vp, vp, i32])):
         f = getattr(L, "duckdb_mb_gpu_" + name)
         f.restype = i32
         f.argtypes = [vp] + extra

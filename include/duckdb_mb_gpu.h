@@ -567,6 +567,15 @@ int32_t duckdb_mb_gpu_append_blob(duckdb_mb_gpu_appender *a, const uint8_t *byte
 int32_t duckdb_mb_gpu_appender_set_decimal(duckdb_mb_gpu_appender *a, int32_t col, int32_t width, int32_t scale);
 int32_t duckdb_mb_gpu_append_decimal(duckdb_mb_gpu_appender *a, int32_t width, int32_t scale, int64_t lower, int64_t upper);
 int32_t duckdb_mb_gpu_append_interval(duckdb_mb_gpu_appender *a, int32_t months, int32_t days, int64_t micros); /* :1511 */
+/* LIST / STRUCT / MAP cells: the reference serialises them as text -- `["a", "b"]` (:1735-1790), `{"k": "v", ...}`
+ * (:1792-1858 struct, :1860-1926 map), items copied without escaping -- and appends the text as one VARCHAR cell
+ * through duckdb_append_varchar, so the text ends at the first NUL byte.  values[i] / lens[i] stand for the
+ * reference's Array[Bytes] (moonbit_bytes_t* + Moonbit_array_length). */
+int32_t duckdb_mb_gpu_append_list_varchar(duckdb_mb_gpu_appender *a, const uint8_t *const *values, const int32_t *lens, int32_t count);
+int32_t duckdb_mb_gpu_append_struct_varchar(duckdb_mb_gpu_appender *a, const uint8_t *const *names, const int32_t *name_lens,
+                                            const uint8_t *const *values, const int32_t *value_lens, int32_t count);
+int32_t duckdb_mb_gpu_append_map_varchar_varchar(duckdb_mb_gpu_appender *a, const uint8_t *const *keys, const int32_t *key_lens,
+                                                 const uint8_t *const *values, const int32_t *value_lens, int32_t count);
 int32_t duckdb_mb_gpu_end_row(duckdb_mb_gpu_appender *a);                                     /* :1221 */
 
 #ifdef __cplusplus

@@ -339,3 +339,32 @@ def rev_string(offsets: np.ndarray, data: np.ndarray, data_host_base: int, bitma
     lib().ora_rev_string(_ptr(offsets), large, _ptr(data), data_host_base, _ptr(bitmap), bit_offset, nrows,
                          _ptr(out), _ptr(val), C.byref(nc))
     return out, val, nc.value
+
+
+def _bytes_array(items):
+    enc = [x.encode("utf-8") if isinstance(x, str) else bytes(x) for x in items]
+    bufs = [C.create_string_buffer(b, len(b) + 1) for b in enc]
+    ptrs = (C.c_void_p * max(len(enc), 1))(*[C.addressof(b) for b in bufs])
+    lens = (C.c_int32 * max(len(enc), 1))(*[len(b) for b in enc])
+    return ptrs, lens, bufs, sum(len(b) for b in enc)
+
+
+def list_varchar_text(values) -> bytes:
+    """the VARCHAR cell duckdb_mb_append_list_varchar appends (src/duckdb_native.c:1735-1790)"""
+    p, l, keep, total = _bytes_array(values)
+    out = C.create_string_buffer(total + 4 * len(values) + 8)
+    f = lib().ora_list_varchar_text
+    f.restype = C.c_int64
+    n = f(p, l, C.c_int32(len(values)), out)
+    return out.raw[:n]
+
+
+def pairs_varchar_text(keys, values) -> bytes:
+    """the VARCHAR cell duckdb_mb_append_struct_varchar / _map_varchar_varchar append (:1792-1926)"""
+    pk, lk, k1, t1 = _bytes_array(keys)
+    pv, lv, k2, t2 = _bytes_array(values)
+    out = C.create_string_buffer(t1 + t2 + 8 * len(keys) + 8)
+    f = lib().ora_pairs_varchar_text
+    f.restype = C.c_int64
+    n = f(pk, lk, pv, lv, C.c_int32(len(keys)), out)
+    return out.raw[:n]

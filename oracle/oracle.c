@@ -1237,3 +1237,44 @@ int ora_rev_string(const void *offsets, int large, const uint8_t *data, uint64_t
   if (null_count) *null_count = nulls;
   return 0;
 }
+
+/* ------------------------------------------------------------------ LIST / STRUCT / MAP cells of the row appender
+ * The reference serialises them as text and appends the text as one VARCHAR cell (src/duckdb_native.c:1735-1790
+ * list, :1792-1858 struct, :1860-1926 map): items between double quotes, no escaping, ", " between entries, ": "
+ * between a key and its value.  duckdb_append_varchar takes a C string, so the cell ends at the first NUL byte.
+ * Returns the cell's length (strlen of the buffer); out needs room for the full serialisation + 1. */
+static size_t ora_put_quoted(char *out, size_t pos, const uint8_t *p, int32_t len) {
+  out[pos++] = '"';
+  for (int32_t j = 0; j < len; j++) out[pos++] = (char)p[j];
+  out[pos++] = '"';
+  return pos;
+}
+
+int64_t ora_list_varchar_text(const uint8_t *const *values, const int32_t *lens, int32_t count, char *out) {
+  size_t pos = 0;
+  out[pos++] = '[';
+  for (int32_t i = 0; i < count; i++) {
+    if (i > 0) { out[pos++] = ','; out[pos++] = ' '; }
+    pos = ora_put_quoted(out, pos, values[i], values[i] ? lens[i] : 0);
+  }
+  out[pos++] = ']';
+  out[pos] = '\0';
+  return (int64_t)strlen(out);
+}
+
+/* struct (field names / values) and map (keys / values) share the form */
+int64_t ora_pairs_varchar_text(const uint8_t *const *keys, const int32_t *key_lens, const uint8_t *const *values,
+                               const int32_t *value_lens, int32_t count, char *out) {
+  size_t pos = 0;
+  out[pos++] = '{';
+  for (int32_t i = 0; i < count; i++) {
+    if (i > 0) { out[pos++] = ','; out[pos++] = ' '; }
+    pos = ora_put_quoted(out, pos, keys[i], keys[i] ? key_lens[i] : 0);
+    out[pos++] = ':';
+    out[pos++] = ' ';
+    pos = ora_put_quoted(out, pos, values[i], values[i] ? value_lens[i] : 0);
+  }
+  out[pos++] = '}';
+  out[pos] = '\0';
+  return (int64_t)strlen(out);
+}

@@ -338,3 +338,77 @@ def test_append_arrow_errors_keep_the_reference_convention(ctx):
         c.append_arrow(pa.record_batch([pa.array([1], type=pa.int32())], names=["a"]))
     assert c.state == ap.ERROR
     c.close()
+
+
+class _StringSink:
+    """sink that resolves every VARCHAR cell while the chunk is handed over (pointer string_t refer to the appender's
+    own row buffer, valid during the call -- DuckDB copies them inside duckdb_append_data_chunk)"""
+
+    def __init__(self, ncols):
+        self.cells = [[] for _ in range(ncols)]
+
+    def __call__(self, count, vec_data, vec_validity):
+        import ctypes as C
+        for c in range(len(self.cells)):
+            ent = np.frombuffer(C.string_at(vec_data[c], count * 16), dtype=np.uint8).reshape(-1, 16)
+            mask = np.frombuffer(C.string_at(vec_validity[c], 8 * ch.VALIDITY_WORDS), dtype=np.uint64)
+            for i in range(count):
+                if not (int(mask[i >> 6]) >> (i & 63)) & 1:
+                    self.cells[c].append(None)
+                    continue
+                ln = int(ent[i, 0:4].view(np.uint32)[0])
+                if ln <= 12:
+                    self.cells[c].append(bytes(ent[i, 4:4 + ln]))
+                else:
+                    self.cells[c].append(C.string_at(int(ent[i, 8:16].view(np.uint64)[0]), ln))
+        return True
+
+
+def test_list_struct_map_cells_are_the_reference_text_forms(ctx):
+    """Appender::append_list_varchar / append_struct / append_map (src/duckdb_native.mbt:1703-1755 over
+    src/duckdb_native.c:1735-1926) and append_list_varchar_value (:1764-1795, the reference's own test
+    src/duckdb_test.mbt:1391-1425): one VARCHAR cell holding the serialised text, against the oracle's restatement."""
+    from duckdb_mbt_b200 import appender as ap
+    rng = np.random.default_rng(21)
+    sink = _StringSink(3)
+    a = ap.Appender(ctx, [ch.T_VARCHAR, ch.T_VARCHAR, ch.T_VARCHAR], sink)
+    word = lambda: bytes(rng.integers(0x20, 0x7F, int(rng.integers(0, 9)), dtype=np.uint8)).decode()  # noqa: E731
+    rows = []
+    for i in range(2500):
+        items = [word() for _ in range(int(rng.integers(0, 5)))]
+        keys = [word() for _ in range(int(rng.integers(0, 4)))]
+        vals = [word() for _ in keys]
+        rows.append((items, keys, vals))
+        a.begin_row()
+        a.append_list_varchar(items)
+        a.append_struct(keys, vals) if i % 2 else a.append_map(keys, vals)
+        a.append_list_varchar_value(items)
+        a.end_row()
+    # known answers + the C-string cut at an embedded NUL
+    a.begin_row()
+    a.append_list_varchar(["a", "b", "c"])
+    a.append_struct(["name", "age"], ["duck", "3"])
+    a.append_list_varchar_value(["a", "it's", "c"])
+    a.end_row()
+    a.begin_row()
+    a.append_list_varchar([b"ab\0cd", b"x"])
+    a.append_map([], [])
+    a.append_list_varchar_value([])
+    a.end_row()
+    assert a.state == ap.READY
+    a.flush()
+    n = len(rows)
+    assert len(sink.cells[0]) == n + 2
+    for i, (items, keys, vals) in enumerate(rows):
+        assert sink.cells[0][i] == oracle.list_varchar_text(items), i
+        assert sink.cells[1][i] == oracle.pairs_varchar_text(keys, vals), i
+        assert sink.cells[2][i] == ("[" + ", ".join("'" + v.replace("'", "''") + "'" for v in items) + "]").encode(), i
+    assert [c[n] for c in sink.cells] == [b'["a", "b", "c"]', b'{"name": "duck", "age": "3"}', b"['a', 'it''s', 'c']"]
+    assert [c[n + 1] for c in sink.cells] == [b'["ab', b"{}", b"[]"]
+    # wrong column type: the reference's mutator convention (0 + per-handle error), state -> Error
+    b = ap.Appender(ctx, [ch.T_INTEGER], _StringSink(1))
+    b.begin_row()
+    with pytest.raises(Exception):
+        b.append_list_varchar(["x"])
+    b.close()
+    a.close()

@@ -398,3 +398,17 @@ def test_all_reference_fixture_cases_replayed_on_the_oracle():
             for j, (text, is_null) in enumerate(zip(row, nulls)):
                 assert r.cell_is_null(j, i) == is_null, (case["name"], i, j)
                 assert r.cell_value(j, i).decode() == text, (case["name"], i, j)
+
+
+def test_oracle_list_struct_map_cells_known_answers():
+    """src/duckdb_native.c:1735-1926: the text the reference appends for LIST / STRUCT / MAP cells (the form its own
+    test expects, src/duckdb_test.mbt:1410-1413: "DuckDB returns list as string like '["a", "b", "c"]'")."""
+    import oracle
+    assert oracle.list_varchar_text(["a", "b", "c"]) == b'["a", "b", "c"]'
+    assert oracle.list_varchar_text([]) == b"[]"
+    assert oracle.list_varchar_text([""]) == b'[""]'
+    assert oracle.list_varchar_text(['q"uote', "né"]) == '["q"uote", "né"]'.encode()     # no escaping
+    assert oracle.list_varchar_text([b"ab\0cd", b"x"]) == b'["ab'                            # C string: ends at the first NUL
+    assert oracle.pairs_varchar_text(["name", "age"], ["duck", "3"]) == b'{"name": "duck", "age": "3"}'
+    assert oracle.pairs_varchar_text([], []) == b"{}"
+    assert oracle.pairs_varchar_text(["k"], [""]) == b'{"k": ""}'
