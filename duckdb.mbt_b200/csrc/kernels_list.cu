@@ -1,0 +1,269 @@
+// K9 list_to_arrow: DuckDB LIST vectors -> Arrow list<child> ("nested offsets kernels").
+//
+// DuckDB side, per chunk: a vector of duckdb_list_entry {uint64 offset, uint64 length} (what
+// duckdb_vector_get_data returns for a LIST vector) + its validity mask, and ONE child vector per chunk
+// (duckdb_list_vector_get_child / _get_size) that the entries index.  Entries need not be in row order or
+// contiguous (slices, selections), and the entry of a NULL row is unspecified.
+// Arrow side: offsets[n+1] (int32, or int64 for large_list) = running sum of the valid rows' lengths, the
+// child values gathered in row order, the child validity bitmap gathered with them (payload under a NULL
+// child element zeroed, like every other export of this library).
+//
+// The reference rejects LIST on its chunk path (src/duckdb_native.c:271-303) and its README lists
+// List/Struct/Map as "not yet supported" for Arrow: there is no reference output to match; the contract is
+// the Arrow format (validated with pyarrow) and the oracle's restatement of the loops above.
+//
+// Three launches, all HBM-bound streams over the entries / the child elements:
+//   list_sum_kernel    one CTA per chunk (grid-stride): sum of the valid rows' lengths -> chunk_sum[k]
+//   list_scan_kernel   one CTA: exclusive scan of chunk_sum -> chunk_base[k], total
+//   list_emit_kernel   one CTA per chunk: block scan of the lengths -> offsets; then output-centric gather of
+//                      the chunk's child elements (row of an output element by binary search over the
+//                      chunk's 2048 row starts in shared memory; a chunk whose entries are contiguous and in row
+//                      order -- the common case -- skips the search), child validity by warp ballot over
+//                      32-aligned groups of OUTPUT elements (whole words stored, the ragged first / last word of
+//                      a chunk merged with atomicOr into the pre-zeroed bitmap).
+
+#include "dmb_common.cuh"
+
+namespace dmb {
+
+constexpr int kListRpt = kVec / kThreads;  // rows per thread: 8
+
+struct ListEntry {
+  uint64_t offset, length;
+};
+
+__device__ __forceinline__ bool list_row_valid(const uint64_t *mask, int i) {
+  return mask ? ((__ldg(mask + (i >> 6)) >> (i & 63)) & 1ull) : true;
+}
+
+// block-wide exclusive scan of one value per thread (kThreads threads); returns the exclusive prefix, *total = sum
+__device__ __forceinline__ uint64_t block_exscan(uint64_t v, uint64_t *total, uint64_t *s_warp /* [kThreads / 32 + 1] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t w = lane < kThreads / 32 ? s_warp[lane] : 0ull;
+    uint64_t winc = w;
+#pragma unroll
+    for (int d = 1; d < kThreads / 32; d <<= 1) {
+      const uint64_t t = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += t;
+    }
+    if (lane < kThreads / 32) s_warp[lane] = winc - w;
+    if (lane == kThreads / 32 - 1) s_warp[kThreads / 32] = winc;
+  }
+  __syncthreads();
+  const uint64_t out = s_warp[warp] + inc - v;
+  *total = s_warp[kThreads / 32];
+  __syncthreads();
+  return out;
+}
+
+__global__ void __launch_bounds__(kThreads)
+list_sum_kernel(dmb_list_job job, const uint32_t *__restrict__ counts, int64_t nchunks, unsigned long long *chunk_sum) {
+  __shared__ uint64_t s_warp[kThreads / 32 + 1];
+  for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int count = (int)__ldg(counts + c);
+    const dmb_vec_desc vd = job.vecs[c];
+    const ListEntry *ent = reinterpret_cast<const ListEntry *>(reinterpret_cast<const uint8_t *>(job.in_entries) + vd.data_off);
+    const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
+    uint64_t sum = 0;
+    for (int i = threadIdx.x; i < count; i += kThreads)
+      if (list_row_valid(mask, i)) sum += ent[i].length;
+    uint64_t total;
+    block_exscan(sum, &total, s_warp);
+    if (threadIdx.x == 0) chunk_sum[c] = total;
+  }
+}
+
+// chunk_sum -> chunk_base (exclusive), in place is not allowed; one CTA
+__global__ void __launch_bounds__(kThreads)
+list_scan_kernel(const unsigned long long *chunk_sum, unsigned long long *chunk_base, int64_t nchunks, unsigned long long *total_out,
+                 unsigned long long *flags, int large) {
+  __shared__ uint64_t s_warp[kThreads / 32 + 1];
+  uint64_t carry = 0;
+  for (int64_t c0 = 0; c0 < nchunks; c0 += kThreads) {
+    const int64_t c = c0 + threadIdx.x;
+    const uint64_t v = c < nchunks ? chunk_sum[c] : 0ull;
+    uint64_t total;
+    const uint64_t ex = block_exscan(v, &total, s_warp);
+    if (c < nchunks) chunk_base[c] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) {
+    if (total_out) *total_out = carry;
+    if (!large && carry > 0x7fffffffull && flags) atomicOr(flags, 1ull);  // int32 offsets overflow: use large_list
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void copy_elem(uint8_t *dst, const uint8_t *src, bool valid) {
+  using T = typename RawVec<W>::type;
+  T v;
+  if (valid) v = *reinterpret_cast<const T *>(src); else memset(&v, 0, sizeof(T));
+  *reinterpret_cast<T *>(dst) = v;
+}
+
+template <int W, bool LARGE>
+__global__ void __launch_bounds__(kThreads)
+list_emit_kernel(dmb_list_job job, BatchView b, const unsigned long long *__restrict__ chunk_sum,
+                 const unsigned long long *__restrict__ chunk_base, unsigned long long *flags) {
+  __shared__ uint64_t s_warp[kThreads / 32 + 1];
+  __shared__ uint32_t s_start[kVec + 1];  // row -> first output element of the row, relative to the chunk
+  __shared__ uint64_t s_src[kVec];        // row -> entry.offset
+  __shared__ unsigned long long s_dmin, s_dmax;
+  const int lane = threadIdx.x & 31;
+  for (int64_t c = blockIdx.x; c < b.nchunks; c += gridDim.x) {
+    const int count = (int)__ldg(b.counts + c);
+    const int64_t row0 = __ldg(b.row_off + c);
+    const dmb_vec_desc vd = job.vecs[c];
+    const ListEntry *ent = reinterpret_cast<const ListEntry *>(reinterpret_cast<const uint8_t *>(job.in_entries) + vd.data_off);
+    const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
+    const uint64_t cbase = chunk_base[c], csum = chunk_sum[c];
+    if (threadIdx.x == 0) { s_dmin = ~0ull; s_dmax = 0ull; }
+    // ---- this thread's kListRpt consecutive rows: lengths (0 for NULL rows), block scan, offsets
+    uint64_t len[kListRpt], off[kListRpt], mine = 0;
+    const int i0 = threadIdx.x * kListRpt;
+#pragma unroll
+    for (int k = 0; k < kListRpt; ++k) {
+      const int i = i0 + k;
+      len[k] = 0;
+      off[k] = 0;
+      if (i < count && list_row_valid(mask, i)) {
+        const ListEntry e = ent[i];
+        len[k] = e.length;
+        off[k] = e.offset;
+      }
+      mine += len[k];
+    }
+    uint64_t total;
+    uint64_t ex = block_exscan(mine, &total, s_warp);  // its barriers also order the s_dmin / s_dmax reset
+    if (csum > 0xffffffffull) {  // one chunk with more than 4 G child elements (uniform branch)
+      if (threadIdx.x == 0) atomicOr(flags, 2ull);
+      continue;
+    }
+    // contiguity: the chunk's entries are one run in row order iff entry.offset - start is the same for every non-empty row
+    unsigned long long dmin = ~0ull, dmax = 0ull;
+#pragma unroll
+    for (int k = 0; k < kListRpt; ++k) {
+      const int i = i0 + k;
+      if (i < count) {
+        const uint64_t o = cbase + ex;
+        if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[row0 + i] = (long long)o;
+        else reinterpret_cast<int32_t *>(job.out_offsets)[row0 + i] = (int32_t)o;
+        s_start[i] = (uint32_t)ex;
+        s_src[i] = off[k];
+        if (len[k]) {
+          const unsigned long long d = off[k] - ex;
+          dmin = d < dmin ? d : dmin;
+          dmax = d > dmax ? d : dmax;
+        }
+      }
+      ex += len[k];
+    }
+    if (dmin <= dmax) {  // this thread has a non-empty row
+      atomicMin(&s_dmin, dmin);
+      atomicMax(&s_dmax, dmax);
+    }
+    if (threadIdx.x == 0) {
+      s_start[count] = (uint32_t)csum;
+      if (row0 + count == b.nrows) {  // the last chunk writes offsets[nrows]
+        const uint64_t o = cbase + csum;
+        if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[b.nrows] = (long long)o;
+        else reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)o;
+      }
+    }
+    __syncthreads();
+    const bool contiguous = s_dmin == s_dmax;
+    const uint64_t run_d = s_dmin;  // source element of output element e of a contiguous chunk: run_d + e
+    // ---- gather the chunk's child elements, output-centric, in 32-aligned groups of OUTPUT elements
+    const uint64_t child0 = __ldg(job.child_base + c);  // element index of the chunk's child vector in the staged slab
+    const int64_t cvo = job.child_val_off ? __ldg(job.child_val_off + c) : -1;
+    const uint64_t *cmask = (job.child_validity && cvo >= 0) ? job.child_validity + cvo : nullptr;
+    const uint64_t first = cbase & ~31ull, end = cbase + csum, stop = (end + 31ull) & ~31ull;
+    uint32_t *bm32 = reinterpret_cast<uint32_t *>(job.out_child_validity);
+    unsigned nulls = 0;
+    for (uint64_t E = first + threadIdx.x; E < stop; E += kThreads) {  // a warp's 32 elements share one bitmap word
+      const bool in = E >= cbase && E < end;
+      bool valid = false;
+      if (in) {
+        const uint32_t e = (uint32_t)(E - cbase);
+        uint64_t src;
+        if (contiguous) {
+          src = run_d + e;
+        } else {
+          int lo = 0, hi = count;  // the last row whose start is <= e: rows after it start later, empty rows before it are skipped
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_start[mid] <= e) lo = mid; else hi = mid;
+          }
+          src = s_src[lo] + (e - s_start[lo]);
+        }
+        valid = cmask ? ((__ldg(cmask + (src >> 6)) >> (src & 63)) & 1ull) : true;
+        copy_elem<W>(reinterpret_cast<uint8_t *>(job.out_child) + E * W,
+                     reinterpret_cast<const uint8_t *>(job.child_data) + (child0 + src) * W, valid);
+        nulls += valid ? 0u : 1u;
+      }
+      const uint32_t word = __ballot_sync(0xffffffffu, valid);
+      if (lane == 0 && bm32) {
+        if (E >= cbase && E + 32 <= end) bm32[E >> 5] = word;   // lane 0's E is 32-aligned
+        else if (word) atomicOr(bm32 + (E >> 5), word);         // ragged first / last word: shared with the neighbouring chunks
+      }
+    }
+    if (job.child_null_count) {
+      nulls = __reduce_add_sync(0xffffffffu, nulls);
+      if (lane == 0 && nulls) atomicAdd(job.child_null_count, (unsigned long long)nulls);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace dmb
+
+using namespace dmb;
+
+extern "C" size_t dmb_dev_list_scratch_bytes(int64_t nchunks) {
+  return (size_t)(2 * (nchunks > 0 ? nchunks : 0) + 2) * sizeof(unsigned long long);
+}
+
+// scratch: [0] error flags (1: int32 offsets overflow, 2: a chunk with > 4 G child elements), [1] unused,
+// then chunk_sum[nchunks], chunk_base[nchunks].  out_child_validity must hold ceil(total / 64) + 1 words.
+extern "C" int32_t dmb_dev_list_batch(const dmb_list_job *job, const uint32_t *counts, const int64_t *row_off, int64_t nchunks,
+                                      int64_t nrows, int64_t child_capacity, void *scratch, void *stream) {
+  if (!job) { set_error("dmb_dev_list_batch: job is null"); return -1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nchunks <= 0 || nrows <= 0) return 0;
+  const int w = job->child_width;
+  if (w != 1 && w != 2 && w != 4 && w != 8 && w != 16) { set_error("dmb_dev_list_batch: child width %d (fixed-width children of 1/2/4/8/16 bytes)", w); return -1; }
+  unsigned long long *flags = (unsigned long long *)scratch;
+  unsigned long long *chunk_sum = flags + 2, *chunk_base = chunk_sum + nchunks;
+  if (check_cuda(cudaMemsetAsync(scratch, 0, 16, st), "list scratch memset")) return -1;
+  if (job->out_child_validity && child_capacity > 0 &&
+      check_cuda(cudaMemsetAsync(job->out_child_validity, 0, (size_t)((child_capacity + 63) / 64 + 1) * 8, st), "list child bitmap memset")) return -1;
+  if (job->child_null_count && check_cuda(cudaMemsetAsync(job->child_null_count, 0, 8, st), "list null count memset")) return -1;
+  const int64_t max_grid = (int64_t)kNumSMs * 8;
+  const int grid = (int)(nchunks < max_grid ? nchunks : max_grid);
+  BatchView b{counts, row_off, nchunks, nrows};
+  list_sum_kernel<<<grid, kThreads, 0, st>>>(*job, counts, nchunks, chunk_sum);
+  list_scan_kernel<<<1, kThreads, 0, st>>>(chunk_sum, chunk_base, nchunks, job->total, flags, job->large);
+#define DMB_LIST_LAUNCH(W)                                                                                          \
+  do {                                                                                                              \
+    if (job->large) list_emit_kernel<W, true><<<grid, kThreads, 0, st>>>(*job, b, chunk_sum, chunk_base, flags);     \
+    else list_emit_kernel<W, false><<<grid, kThreads, 0, st>>>(*job, b, chunk_sum, chunk_base, flags);               \
+  } while (0)
+  switch (w) {
+    case 1: DMB_LIST_LAUNCH(1); break;
+    case 2: DMB_LIST_LAUNCH(2); break;
+    case 4: DMB_LIST_LAUNCH(4); break;
+    case 8: DMB_LIST_LAUNCH(8); break;
+    default: DMB_LIST_LAUNCH(16); break;
+  }
+#undef DMB_LIST_LAUNCH
+  return check_cuda(cudaGetLastError(), "list kernels launch");
+}

@@ -61,6 +61,13 @@ class EnumJob(C.Structure):
                 ("bad_index", C.c_void_p), ("dict_size", C.c_uint32), ("phys", C.c_int32)]
 
 
+class ListJob(C.Structure):
+    _fields_ = [("in_entries", C.c_void_p), ("in_validity", C.c_void_p), ("vecs", C.c_void_p), ("child_base", C.c_void_p),
+                ("child_data", C.c_void_p), ("child_validity", C.c_void_p), ("child_val_off", C.c_void_p),
+                ("out_offsets", C.c_void_p), ("out_child", C.c_void_p), ("out_child_validity", C.c_void_p),
+                ("total", C.c_void_p), ("child_null_count", C.c_void_p), ("child_width", C.c_int32), ("large", C.c_int32)]
+
+
 class HostColumn(C.Structure):
     _fields_ = [("name", C.c_char_p), ("type_id", C.c_int32), ("phys", C.c_int32), ("dec_width", C.c_int32),
                 ("dec_scale", C.c_int32), ("data", C.POINTER(C.c_void_p)), ("validity", C.POINTER(C.c_void_p)),
@@ -102,7 +109,7 @@ CHUNK_SINK = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_uint32, C.POINTER
 EXPORTED_SYMBOLS = [
     "dmb_dev_fixed_batch", "dmb_op_out_width", "dmb_phys_width", "dmb_dev_string_scratch_bytes",
     "dmb_dev_string_error", "dmb_dev_string_batch", "dmb_dev_rev_fixed_batch", "dmb_dev_rev_string_batch",
-    "dmb_dev_valid_bytes_to_masks", "dmb_dev_make_string_t", "dmb_render_supported", "dmb_render_slot_bytes", "dmb_dev_render_text", "dmb_dev_enum_to_string_t",
+    "dmb_dev_valid_bytes_to_masks", "dmb_dev_make_string_t", "dmb_render_supported", "dmb_render_slot_bytes", "dmb_dev_render_text", "dmb_dev_enum_to_string_t", "dmb_dev_list_scratch_bytes", "dmb_dev_list_batch",
     "duckdb_mb_gpu_last_error", "duckdb_mb_gpu_device_count", "duckdb_mb_gpu_ctx_create",
     "duckdb_mb_gpu_ctx_destroy", "duckdb_mb_gpu_ctx_sync", "duckdb_mb_gpu_host_alloc", "duckdb_mb_gpu_host_free",
     "duckdb_mb_gpu_result_from_chunks", "duckdb_mb_gpu_result_materialise_arrow",
@@ -184,6 +191,10 @@ def lib():
     L.dmb_dev_valid_bytes_to_masks.argtypes = [vp, vp, vp, i64, vp]
     L.dmb_dev_enum_to_string_t.restype = i32
     L.dmb_dev_enum_to_string_t.argtypes = [C.POINTER(EnumJob), vp, i64, vp]
+    L.dmb_dev_list_scratch_bytes.restype = C.c_size_t
+    L.dmb_dev_list_scratch_bytes.argtypes = [i64]
+    L.dmb_dev_list_batch.restype = i32
+    L.dmb_dev_list_batch.argtypes = [C.POINTER(ListJob), vp, vp, i64, i64, i64, vp, vp]
     L.dmb_dev_rev_fixed_batch.restype = i32
     L.dmb_dev_rev_fixed_batch.argtypes = [vp, vp, i32, i64, vp]
     L.dmb_dev_rev_string_batch.restype = i32

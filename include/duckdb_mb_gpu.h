@@ -257,6 +257,35 @@ typedef struct dmb_enum_job {
 
 int32_t dmb_dev_enum_to_string_t(const dmb_enum_job *job, const uint32_t *counts, int64_t nchunks, void *stream);
 
+/* K9: LIST vectors -> Arrow list<child> (fixed-width child).  The reference rejects
+ * LIST on its chunk path (src/duckdb_native.c:271-303): the contract is the Arrow format.  Per chunk: a vector of
+ * duckdb_list_entry {uint64 offset, uint64 length} (+ validity) indexing that chunk's child vector
+ * (duckdb_list_vector_get_child / _get_size).  The child vectors of all chunks are staged back to back:
+ * chunk k's elements start at element child_base[k], its validity mask (ceil(size/64) words) at word
+ * child_val_off[k] of child_validity (-1: all valid).  Output: offsets[nrows+1] (running sum of the valid rows'
+ * lengths), child values gathered in row order (payload under a NULL element zeroed), child bitmap. */
+typedef struct dmb_list_job {
+  const void *in_entries;           /* list_entry slab, chunk k at vecs[k].data_off             */
+  const uint64_t *in_validity;      /* validity slab of the LIST column                         */
+  const dmb_vec_desc *vecs;         /* [nchunks]                                                */
+  const uint64_t *child_base;       /* [nchunks]                                                */
+  const void *child_data;           /* staged child payload, child_width bytes per element      */
+  const uint64_t *child_validity;   /* staged child masks or NULL                               */
+  const int64_t *child_val_off;     /* [nchunks] or NULL                                        */
+  void *out_offsets;                /* int32 (int64 when large) [nrows + 1]                     */
+  void *out_child;                  /* child_width bytes per element, dense                     */
+  uint64_t *out_child_validity;     /* LSB bitmap, ceil(capacity/64)+1 words, or NULL           */
+  unsigned long long *total;        /* number of child elements written                         */
+  unsigned long long *child_null_count;
+  int32_t child_width;              /* 1 / 2 / 4 / 8 / 16                                       */
+  int32_t large;                    /* int64 offsets (large_list)                               */
+} dmb_list_job;
+
+size_t dmb_dev_list_scratch_bytes(int64_t nchunks);
+/* scratch[0] after the call: error flags (1: total exceeds int32 offsets, 2: a chunk with > 4 G child elements) */
+int32_t dmb_dev_list_batch(const dmb_list_job *job, const uint32_t *counts, const int64_t *row_off, int64_t nchunks,
+                           int64_t nrows, int64_t child_capacity, void *scratch, void *stream);
+
 /* K6 reverse (Arrow -> DataChunk vectors), the bulk door behind the appender
  * (reference row-at-a-time path: src/duckdb_native.c:1100-1235; chunk door :2029-2132). */
 typedef struct dmb_rev_fixed_job {

@@ -368,3 +368,21 @@ def pairs_varchar_text(keys, values) -> bytes:
     f.restype = C.c_int64
     n = f(pk, lk, pv, lv, C.c_int32(len(keys)), out)
     return out.raw[:n]
+
+
+def list_arrow(entries: np.ndarray, data_off: np.ndarray, validity: Optional[np.ndarray], val_off: np.ndarray,
+               counts: np.ndarray, child_base: np.ndarray, child_data: np.ndarray, child_validity: Optional[np.ndarray],
+               child_val_off: Optional[np.ndarray], child_width: int, large: bool, capacity: int):
+    """LIST vectors -> Arrow list<child>: (offsets, child bytes, child bitmap bytes, total, child null count)"""
+    nrows = int(np.asarray(counts, dtype=np.int64).sum())
+    offsets = np.zeros(nrows + 1, dtype=np.int64 if large else np.int32)
+    child = np.zeros(max(capacity, 1) * child_width, dtype=np.uint8)
+    bitmap = np.zeros((max(capacity, 1) + 63) // 64 * 8 + 8, dtype=np.uint8)
+    total, nulls = C.c_int64(0), C.c_int64(0)
+    f = lib().ora_list_arrow
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p] * 5 + [C.c_int64] + [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.POINTER(C.c_int64)] * 2
+    f(_ptr(entries), _ptr(data_off), _ptr(validity), _ptr(val_off), _ptr(np.ascontiguousarray(counts, dtype=np.uint32)),
+      int(len(counts)), _ptr(child_base), _ptr(child_data), _ptr(child_validity), _ptr(child_val_off), child_width,
+      1 if large else 0, _ptr(offsets), _ptr(child), _ptr(bitmap), C.byref(total), C.byref(nulls))
+    return offsets, child[: total.value * child_width], bitmap, total.value, nulls.value

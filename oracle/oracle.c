@@ -1278,3 +1278,40 @@ int64_t ora_pairs_varchar_text(const uint8_t *const *keys, const int32_t *key_le
   out[pos] = '\0';
   return (int64_t)strlen(out);
 }
+
+/* ------------------------------------------------------------------ LIST vectors -> Arrow list<child>
+ * (the reference rejects LIST on its chunk path, src/duckdb_native.c:271-303, so this restates
+ * the Arrow-format contract: what DuckDB's own Arrow appender produces for a LIST column of flat chunks.)
+ * Per chunk k: entries {uint64 offset, uint64 length} at entries + data_off[k], the LIST validity mask, and the
+ * chunk's child vector staged at element child_base[k] (mask words at child_val_off[k], -1 = all valid).
+ * Rows in order: a valid row appends its child elements [offset, offset + length); a NULL row appends nothing. */
+int ora_list_arrow(const uint8_t *entries, const uint64_t *data_off, const uint64_t *validity, const int64_t *val_off,
+                   const uint32_t *counts, int64_t nchunks, const uint64_t *child_base, const uint8_t *child_data,
+                   const uint64_t *child_validity, const int64_t *child_val_off, int child_width, int large,
+                   void *out_offsets, uint8_t *out_child, uint8_t *out_child_bitmap, int64_t *total, int64_t *child_nulls) {
+  int64_t row = 0, pos = 0, nulls = 0;
+  for (int64_t k = 0; k < nchunks; k++) {
+    const uint64_t *ent = (const uint64_t *)(entries + data_off[k]);
+    const uint64_t *mask = val_off[k] < 0 ? NULL : validity + val_off[k];
+    const uint64_t *cmask = (child_validity && child_val_off && child_val_off[k] >= 0) ? child_validity + child_val_off[k] : NULL;
+    for (uint32_t i = 0; i < counts[k]; i++, row++) {
+      if (large) ((int64_t *)out_offsets)[row] = pos; else ((int32_t *)out_offsets)[row] = (int32_t)pos;
+      if (mask && !((mask[i / 64] >> (i % 64)) & 1ull)) continue;
+      uint64_t off = ent[2 * i], len = ent[2 * i + 1];
+      for (uint64_t e = off; e < off + len; e++, pos++) {
+        int valid = cmask ? (int)((cmask[e / 64] >> (e % 64)) & 1ull) : 1;
+        if (valid) {
+          memcpy(out_child + (size_t)pos * (size_t)child_width, child_data + (size_t)(child_base[k] + e) * (size_t)child_width, (size_t)child_width);
+          out_child_bitmap[pos / 8] |= (uint8_t)(1u << (pos % 8));
+        } else {
+          memset(out_child + (size_t)pos * (size_t)child_width, 0, (size_t)child_width);
+          nulls++;
+        }
+      }
+    }
+  }
+  if (large) ((int64_t *)out_offsets)[row] = pos; else ((int32_t *)out_offsets)[row] = (int32_t)pos;
+  if (total) *total = pos;
+  if (child_nulls) *child_nulls = nulls;
+  return 0;
+}

@@ -1,0 +1,96 @@
+"""L0 parity of K9 (LIST vectors -> Arrow list<child>, kernels_list.cu) against the oracle's restatement
+(oracle.c ora_list_arrow, itself pinned on pyarrow in tests/test_oracle_golden.py): offsets, gathered child values
+(NULL elements zeroed), child bitmap, totals -- bit for bit, for contiguous, shuffled and shared entry layouts."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import oracle  # noqa: E402
+from duckdb_mbt_b200 import chunks as ch  # noqa: E402
+from duckdb_mbt_b200 import native as nat  # noqa: E402
+
+import list_cases  # noqa: E402
+
+
+def _dev(a: np.ndarray, pad: int = 64):
+    t = torch.zeros(a.nbytes + pad, dtype=torch.uint8, device="cuda:0")
+    if a.nbytes:
+        t[: a.nbytes] = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to("cuda:0")
+    return t
+
+
+def _run(lc, large):
+    L = nat.lib()
+    n = int(lc.counts.sum())
+    nch = lc.counts.shape[0]
+    vecs = np.zeros(nch, dtype=[("data_off", "<u8"), ("val_off", "<i8")])
+    vecs["data_off"], vecs["val_off"] = lc.data_off, lc.val_off
+    row_off = np.zeros(nch + 1, dtype=np.int64)
+    np.cumsum(lc.counts, out=row_off[1:])
+    d = {k: _dev(v) for k, v in dict(entries=lc.entries, validity=lc.validity if lc.validity is not None else np.zeros(1, np.uint64),
+                                     vecs=vecs, child_base=lc.child_base, child_data=lc.child_data, child_validity=lc.child_validity,
+                                     child_val_off=lc.child_val_off, counts=lc.counts.astype(np.uint32), row_off=row_off).items()}
+    cap = lc.capacity
+    ow = 8 if large else 4
+    out_off = torch.full(((n + 1) * ow + 64,), 0xAB, dtype=torch.uint8, device="cuda:0")
+    out_child = torch.full((max(cap, 1) * lc.width + 64,), 0xAB, dtype=torch.uint8, device="cuda:0")
+    out_bm = torch.full((((cap + 63) // 64 + 1) * 8,), 0xAB, dtype=torch.uint8, device="cuda:0")
+    ctr = torch.zeros(2, dtype=torch.int64, device="cuda:0")
+    scratch = torch.zeros(L.dmb_dev_list_scratch_bytes(nch) + 64, dtype=torch.uint8, device="cuda:0")
+    job = nat.ListJob(d["entries"].data_ptr(), d["validity"].data_ptr(), d["vecs"].data_ptr(), d["child_base"].data_ptr(),
+                      d["child_data"].data_ptr(), d["child_validity"].data_ptr(), d["child_val_off"].data_ptr(),
+                      out_off.data_ptr(), out_child.data_ptr(), out_bm.data_ptr(), ctr.data_ptr(), ctr.data_ptr() + 8,
+                      lc.width, 1 if large else 0)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    nat.check(L.dmb_dev_list_batch(C.byref(job), d["counts"].data_ptr(), d["row_off"].data_ptr(), nch, n, cap, scratch.data_ptr(), st), "list")
+    torch.cuda.synchronize()
+    flags = int(scratch[:8].cpu().numpy().view(np.uint64)[0])
+    offs = out_off.cpu().numpy()[: (n + 1) * ow].view(np.int64 if large else np.int32)
+    total, nulls = [int(x) for x in ctr.cpu().numpy()]
+    return offs, out_child.cpu().numpy()[: total * lc.width], out_bm.cpu().numpy(), total, nulls, flags
+
+
+@pytest.mark.parametrize("layout", ["contiguous", "shuffled", "shared"])
+@pytest.mark.parametrize("n,width,pattern,large", [(1, 4, "full", False), (2048, 1, "full", False), (2049, 8, "full", True),
+                                                   (10_000, 4, "ragged", False), (60_001, 2, "ragged", False), (150_000, 16, "full", True)])
+def test_list_to_arrow_matches_the_oracle(layout, n, width, pattern, large):
+    lc = list_cases.make_list_column(n, width, pattern, 500 + n + width, layout)
+    exp_off, exp_child, exp_bm, exp_total, exp_nulls = oracle.list_arrow(
+        lc.entries, lc.data_off, lc.validity, lc.val_off, lc.counts, lc.child_base, lc.child_data, lc.child_validity, lc.child_val_off,
+        width, large, lc.capacity)
+    offs, child, bm, total, nulls, flags = _run(lc, large)
+    assert flags == 0
+    assert total == exp_total == lc.capacity and nulls == exp_nulls
+    assert np.array_equal(offs, exp_off)
+    assert child.tobytes() == exp_child.tobytes()
+    nb = (total + 7) // 8
+    assert bm[:nb].tobytes() == exp_bm[:nb].tobytes()
+
+
+def test_list_without_nulls_and_empty_lists_only():
+    lc = list_cases.make_list_column(30_000, 4, "ragged", 9, "contiguous", null_frac=0.0, child_null_frac=0.0)
+    exp = oracle.list_arrow(lc.entries, lc.data_off, lc.validity, lc.val_off, lc.counts, lc.child_base, lc.child_data, lc.child_validity,
+                            lc.child_val_off, 4, False, lc.capacity)
+    offs, child, bm, total, nulls, flags = _run(lc, False)
+    assert flags == 0 and nulls == 0 and total == exp[3]
+    assert np.array_equal(offs, exp[0]) and child.tobytes() == exp[1].tobytes()
+    assert bm[: (total + 7) // 8].tobytes() == exp[2][: (total + 7) // 8].tobytes()
+    lc0 = list_cases.make_list_column(5000, 8, "full", 10, "contiguous", max_len=0)
+    offs, child, bm, total, nulls, flags = _run(lc0, False)
+    assert flags == 0 and total == 0 and not offs.any()
+
+
+def test_list_arrow_array_reads_back_in_pyarrow():
+    pa = pytest.importorskip("pyarrow")
+    lc = list_cases.make_list_column(7000, 4, "ragged", 77, "shuffled")
+    offs, child, bm, total, nulls, flags = _run(lc, False)
+    values = pa.Array.from_buffers(pa.binary(4), total, [pa.py_buffer(bm.tobytes()), pa.py_buffer(child.tobytes() + b"\0")], null_count=nulls)
+    pbits = np.packbits(lc.valid.astype(np.uint8), bitorder="little").tobytes() + b"\0"
+    arr = pa.Array.from_buffers(pa.list_(pa.binary(4)), len(lc.valid), [pa.py_buffer(pbits), pa.py_buffer(offs.tobytes())], children=[values])
+    arr.validate(full=True)
+    assert arr.to_pylist() == lc.expected
