@@ -74,40 +74,65 @@ list_sum_kernel(dmb_list_job job, const uint32_t *__restrict__ counts, int64_t n
     const ListEntry *ent = reinterpret_cast<const ListEntry *>(reinterpret_cast<const uint8_t *>(job.in_entries) + vd.data_off);
     const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
     uint64_t sum = 0;
-    for (int i = threadIdx.x; i < count; i += kThreads)
-      if (list_row_valid(mask, i)) sum += ent[i].length;
+    for (int i = threadIdx.x; i < count; i += kThreads) {
+      const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2 *>(ent) + i);  // consecutive lanes, consecutive 16-byte entries
+      if (list_row_valid(mask, i)) sum += e.y;
+    }
     uint64_t total;
     block_exscan(sum, &total, s_warp);
     if (threadIdx.x == 0) chunk_sum[c] = total;
   }
 }
 
-// chunk_sum -> chunk_base (exclusive), in place is not allowed; one CTA
-__global__ void __launch_bounds__(kThreads)
+// chunk_sum -> chunk_base (exclusive); one CTA of 1024 threads, thread t owns the consecutive chunks [t*m, t*m + m)
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads)
 list_scan_kernel(const unsigned long long *chunk_sum, unsigned long long *chunk_base, int64_t nchunks, unsigned long long *total_out,
                  unsigned long long *flags, int large) {
-  __shared__ uint64_t s_warp[kThreads / 32 + 1];
-  uint64_t carry = 0;
-  for (int64_t c0 = 0; c0 < nchunks; c0 += kThreads) {
-    const int64_t c = c0 + threadIdx.x;
-    const uint64_t v = c < nchunks ? chunk_sum[c] : 0ull;
-    uint64_t total;
-    const uint64_t ex = block_exscan(v, &total, s_warp);
-    if (c < nchunks) chunk_base[c] = carry + ex;
-    carry += total;
+  __shared__ uint64_t s_warp[kScanThreads / 32 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t m = (nchunks + kScanThreads - 1) / kScanThreads;
+  const int64_t c0 = (int64_t)threadIdx.x * m, c1 = c0 + m < nchunks ? c0 + m : nchunks;
+  uint64_t mine = 0;
+  for (int64_t c = c0; c < c1; ++c) mine += chunk_sum[c];
+  uint64_t inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const uint64_t w = s_warp[lane];
+    uint64_t winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint64_t t = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += t;
+    }
+    s_warp[lane] = winc - w;
+    if (lane == 31) s_warp[32] = winc;
+  }
+  __syncthreads();
+  uint64_t run = s_warp[warp] + inc - mine;
+  for (int64_t c = c0; c < c1; ++c) {
+    chunk_base[c] = run;
+    run += chunk_sum[c];
   }
   if (threadIdx.x == 0) {
-    if (total_out) *total_out = carry;
-    if (!large && carry > 0x7fffffffull && flags) atomicOr(flags, 1ull);  // int32 offsets overflow: use large_list
+    const uint64_t total = s_warp[32];
+    if (total_out) *total_out = total;
+    if (!large && total > 0x7fffffffull && flags) atomicOr(flags, 1ull);  // int32 offsets overflow: use large_list
   }
 }
 
 template <int W>
-__device__ __forceinline__ void copy_elem(uint8_t *dst, const uint8_t *src, bool valid) {
+__device__ __forceinline__ typename RawVec<W>::type load_elem(const uint8_t *src, bool valid) {
   using T = typename RawVec<W>::type;
   T v;
   if (valid) v = *reinterpret_cast<const T *>(src); else memset(&v, 0, sizeof(T));
-  *reinterpret_cast<T *>(dst) = v;
+  return v;
 }
 
 template <int W, bool LARGE>
@@ -117,7 +142,8 @@ list_emit_kernel(dmb_list_job job, BatchView b, const unsigned long long *__rest
   __shared__ uint64_t s_warp[kThreads / 32 + 1];
   __shared__ uint32_t s_start[kVec + 1];  // row -> first output element of the row, relative to the chunk
   __shared__ uint64_t s_src[kVec];        // row -> entry.offset
-  __shared__ unsigned long long s_dmin, s_dmax;
+  __shared__ unsigned long long s_wmin[kThreads / 32], s_wmax[kThreads / 32];
+  __shared__ unsigned s_nulls;
   const int lane = threadIdx.x & 31;
   for (int64_t c = blockIdx.x; c < b.nchunks; c += gridDim.x) {
     const int count = (int)__ldg(b.counts + c);
@@ -126,51 +152,64 @@ list_emit_kernel(dmb_list_job job, BatchView b, const unsigned long long *__rest
     const ListEntry *ent = reinterpret_cast<const ListEntry *>(reinterpret_cast<const uint8_t *>(job.in_entries) + vd.data_off);
     const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
     const uint64_t cbase = chunk_base[c], csum = chunk_sum[c];
-    if (threadIdx.x == 0) { s_dmin = ~0ull; s_dmax = 0ull; }
-    // ---- this thread's kListRpt consecutive rows: lengths (0 for NULL rows), block scan, offsets
-    uint64_t len[kListRpt], off[kListRpt], mine = 0;
-    const int i0 = threadIdx.x * kListRpt;
-#pragma unroll
-    for (int k = 0; k < kListRpt; ++k) {
-      const int i = i0 + k;
-      len[k] = 0;
-      off[k] = 0;
-      if (i < count && list_row_valid(mask, i)) {
-        const ListEntry e = ent[i];
-        len[k] = e.length;
-        off[k] = e.offset;
-      }
-      mine += len[k];
-    }
-    uint64_t total;
-    uint64_t ex = block_exscan(mine, &total, s_warp);  // its barriers also order the s_dmin / s_dmax reset
+    if (threadIdx.x == 0) s_nulls = 0u;
     if (csum > 0xffffffffull) {  // one chunk with more than 4 G child elements (uniform branch)
       if (threadIdx.x == 0) atomicOr(flags, 2ull);
       continue;
     }
+    // ---- entries into shared memory, striped (consecutive lanes, consecutive 16-byte entries); NULL rows: length 0
+    {
+      // all of a thread's loads are issued before any is used: the mask words and the entries do not depend on each other
+      // (the entry of a NULL row is read and dropped: it is storage of the vector, only its content is unspecified)
+      ulonglong2 e[kListRpt];
+      uint64_t mw[kListRpt];
+#pragma unroll
+      for (int k = 0; k < kListRpt; ++k) {
+        const int i = threadIdx.x + k * kThreads;
+        mw[k] = (mask && i < count) ? __ldg(mask + (i >> 6)) : ~0ull;
+        e[k] = i < count ? __ldg(reinterpret_cast<const ulonglong2 *>(ent) + i) : make_ulonglong2(0ull, 0ull);
+      }
+#pragma unroll
+      for (int k = 0; k < kListRpt; ++k) {
+        const int i = threadIdx.x + k * kThreads;
+        const bool valid = i < count && ((mw[k] >> (i & 63)) & 1ull);
+        s_src[i] = valid ? e[k].x : 0ull;
+        s_start[i] = valid ? (uint32_t)e[k].y : 0u;  // csum <= 4 G: every length fits
+      }
+    }
+    __syncthreads();
+    // ---- this thread's kListRpt consecutive rows: block scan of the lengths, starts written back in place
+    const int i0 = threadIdx.x * kListRpt;
+    uint32_t len[kListRpt];
+    uint64_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < kListRpt; ++k) {
+      len[k] = s_start[i0 + k];
+      mine += len[k];
+    }
+    uint64_t total;
+    uint64_t ex = block_exscan(mine, &total, s_warp);
+    (void)total;
     // contiguity: the chunk's entries are one run in row order iff entry.offset - start is the same for every non-empty row
     unsigned long long dmin = ~0ull, dmax = 0ull;
 #pragma unroll
     for (int k = 0; k < kListRpt; ++k) {
-      const int i = i0 + k;
-      if (i < count) {
-        const uint64_t o = cbase + ex;
-        if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[row0 + i] = (long long)o;
-        else reinterpret_cast<int32_t *>(job.out_offsets)[row0 + i] = (int32_t)o;
-        s_start[i] = (uint32_t)ex;
-        s_src[i] = off[k];
-        if (len[k]) {
-          const unsigned long long d = off[k] - ex;
-          dmin = d < dmin ? d : dmin;
-          dmax = d > dmax ? d : dmax;
-        }
+      s_start[i0 + k] = (uint32_t)ex;
+      if (len[k]) {
+        const unsigned long long d = s_src[i0 + k] - ex;
+        dmin = d < dmin ? d : dmin;
+        dmax = d > dmax ? d : dmax;
       }
       ex += len[k];
     }
-    if (dmin <= dmax) {  // this thread has a non-empty row
-      atomicMin(&s_dmin, dmin);
-      atomicMax(&s_dmax, dmax);
+    // warp reduction, one slot per warp (64-bit shared atomics are CAS loops: 256 of them on one word cost 30 us per chunk)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long omin = __shfl_xor_sync(0xffffffffu, dmin, d), omax = __shfl_xor_sync(0xffffffffu, dmax, d);
+      dmin = omin < dmin ? omin : dmin;
+      dmax = omax > dmax ? omax : dmax;
     }
+    if (lane == 0) { s_wmin[threadIdx.x >> 5] = dmin; s_wmax[threadIdx.x >> 5] = dmax; }
     if (threadIdx.x == 0) {
       s_start[count] = (uint32_t)csum;
       if (row0 + count == b.nrows) {  // the last chunk writes offsets[nrows]
@@ -180,8 +219,19 @@ list_emit_kernel(dmb_list_job job, BatchView b, const unsigned long long *__rest
       }
     }
     __syncthreads();
-    const bool contiguous = s_dmin == s_dmax;
-    const uint64_t run_d = s_dmin;  // source element of output element e of a contiguous chunk: run_d + e
+    for (int i = threadIdx.x; i < count; i += kThreads) {  // offsets: coalesced
+      const uint64_t o = cbase + s_start[i];
+      if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[row0 + i] = (long long)o;
+      else reinterpret_cast<int32_t *>(job.out_offsets)[row0 + i] = (int32_t)o;
+    }
+    unsigned long long cmin = ~0ull, cmax = 0ull;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      cmin = s_wmin[w] < cmin ? s_wmin[w] : cmin;
+      cmax = s_wmax[w] > cmax ? s_wmax[w] : cmax;
+    }
+    const bool contiguous = cmin == cmax;
+    const uint64_t run_d = cmin;  // source element of output element e of a contiguous chunk: run_d + e
     // ---- gather the chunk's child elements, output-centric, in 32-aligned groups of OUTPUT elements
     const uint64_t child0 = __ldg(job.child_base + c);  // element index of the chunk's child vector in the staged slab
     const int64_t cvo = job.child_val_off ? __ldg(job.child_val_off + c) : -1;
@@ -189,38 +239,60 @@ list_emit_kernel(dmb_list_job job, BatchView b, const unsigned long long *__rest
     const uint64_t first = cbase & ~31ull, end = cbase + csum, stop = (end + 31ull) & ~31ull;
     uint32_t *bm32 = reinterpret_cast<uint32_t *>(job.out_child_validity);
     unsigned nulls = 0;
-    for (uint64_t E = first + threadIdx.x; E < stop; E += kThreads) {  // a warp's 32 elements share one bitmap word
-      const bool in = E >= cbase && E < end;
-      bool valid = false;
-      if (in) {
-        const uint32_t e = (uint32_t)(E - cbase);
-        uint64_t src;
-        if (contiguous) {
-          src = run_d + e;
-        } else {
-          int lo = 0, hi = count;  // the last row whose start is <= e: rows after it start later, empty rows before it are skipped
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_start[mid] <= e) lo = mid; else hi = mid;
+    constexpr int U = 4;  // output elements per thread in flight
+    using T = typename RawVec<W>::type;
+    for (uint64_t E0 = first + threadIdx.x; E0 < stop; E0 += (uint64_t)U * kThreads) {  // a warp's 32 elements share one bitmap word
+      T v[U];
+      bool valid[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint64_t E = E0 + (uint64_t)u * kThreads;
+        valid[u] = false;
+        memset(&v[u], 0, sizeof(T));
+        if (E >= cbase && E < end) {
+          const uint32_t e = (uint32_t)(E - cbase);
+          uint64_t src;
+          if (contiguous) {
+            src = run_d + e;
+          } else {
+            int lo = 0, hi = count;  // the last row whose start is <= e: rows after it start later, empty rows before it are skipped
+            while (hi - lo > 1) {
+              const int mid = (lo + hi) >> 1;
+              if (s_start[mid] <= e) lo = mid; else hi = mid;
+            }
+            src = s_src[lo] + (e - s_start[lo]);
           }
-          src = s_src[lo] + (e - s_start[lo]);
+          // the element is read whether or not it is NULL (it is storage of the child vector): mask word and element in flight together
+          const uint64_t cw = cmask ? __ldg(cmask + (src >> 6)) : ~0ull;
+          v[u] = *reinterpret_cast<const T *>(reinterpret_cast<const uint8_t *>(job.child_data) + (child0 + src) * W);
+          valid[u] = (cw >> (src & 63)) & 1ull;
         }
-        valid = cmask ? ((__ldg(cmask + (src >> 6)) >> (src & 63)) & 1ull) : true;
-        copy_elem<W>(reinterpret_cast<uint8_t *>(job.out_child) + E * W,
-                     reinterpret_cast<const uint8_t *>(job.child_data) + (child0 + src) * W, valid);
-        nulls += valid ? 0u : 1u;
       }
-      const uint32_t word = __ballot_sync(0xffffffffu, valid);
-      if (lane == 0 && bm32) {
-        if (E >= cbase && E + 32 <= end) bm32[E >> 5] = word;   // lane 0's E is 32-aligned
-        else if (word) atomicOr(bm32 + (E >> 5), word);         // ragged first / last word: shared with the neighbouring chunks
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint64_t E = E0 + (uint64_t)u * kThreads;
+        if (E >= cbase && E < end && !valid[u]) {
+          memset(&v[u], 0, sizeof(T));
+          ++nulls;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint64_t E = E0 + (uint64_t)u * kThreads;
+        if (E >= cbase && E < end) *reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(job.out_child) + E * W) = v[u];
+        const uint32_t word = __ballot_sync(0xffffffffu, valid[u]);
+        if (lane == 0 && bm32 && E < stop) {
+          if (E >= cbase && E + 32 <= end) bm32[E >> 5] = word;   // lane 0's E is 32-aligned
+          else if (word) atomicOr(bm32 + (E >> 5), word);         // ragged first / last word: shared with the neighbouring chunks
+        }
       }
     }
-    if (job.child_null_count) {
+    if (job.child_null_count) {  // one global atomic per chunk
       nulls = __reduce_add_sync(0xffffffffu, nulls);
-      if (lane == 0 && nulls) atomicAdd(job.child_null_count, (unsigned long long)nulls);
+      if (lane == 0 && nulls) atomicAdd(&s_nulls, nulls);
     }
     __syncthreads();
+    if (threadIdx.x == 0 && job.child_null_count && s_nulls) atomicAdd(job.child_null_count, (unsigned long long)s_nulls);
   }
 }
 
@@ -251,7 +323,7 @@ extern "C" int32_t dmb_dev_list_batch(const dmb_list_job *job, const uint32_t *c
   const int grid = (int)(nchunks < max_grid ? nchunks : max_grid);
   BatchView b{counts, row_off, nchunks, nrows};
   list_sum_kernel<<<grid, kThreads, 0, st>>>(*job, counts, nchunks, chunk_sum);
-  list_scan_kernel<<<1, kThreads, 0, st>>>(chunk_sum, chunk_base, nchunks, job->total, flags, job->large);
+  list_scan_kernel<<<1, kScanThreads, 0, st>>>(chunk_sum, chunk_base, nchunks, job->total, flags, job->large);
 #define DMB_LIST_LAUNCH(W)                                                                                          \
   do {                                                                                                              \
     if (job->large) list_emit_kernel<W, true><<<grid, kThreads, 0, st>>>(*job, b, chunk_sum, chunk_base, flags);     \
