@@ -141,4 +141,51 @@ __device__ __forceinline__ uint64_t spread8(uint32_t bits) {
   return (x >> 7) & 0x0101010101010101ull;
 }
 
+// ---- bitmaps as aligned 32-bit words, misaligned 16-byte vectors (reverse kernels, LIST child copy) -----------------
+// An LSB bitmap read as aligned 32-bit words: `w` is the bitmap address rounded down to 4 bytes and
+// `base` the bit position of row 0 counted from there (Arrow array offset + the rounded-off bytes).
+struct BitSrc {
+  const uint32_t *w;
+  int64_t base;
+};
+__device__ __forceinline__ BitSrc bit_src(const uint8_t *bm, int64_t bit_offset) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(bm);
+  return BitSrc{reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3), bit_offset + (int64_t)(a & 3u) * 8};
+}
+
+// `take` (1..32) bits from bit position p; only the words that hold a requested bit are touched
+__device__ __forceinline__ uint32_t load_bits32(const uint32_t *w, int64_t p, int take) {
+  const int64_t wi = p >> 5;
+  const int s = (int)(p & 31);
+  const uint32_t lo = __ldg(w + wi);
+  const uint32_t hi = (s + take > 32) ? __ldg(w + wi + 1) : 0u;
+  const uint32_t r = __funnelshift_r(lo, hi, (uint32_t)s);
+  return take >= 32 ? r : (r & ((1u << take) - 1u));
+}
+
+// words [ws, ws+4] of the 8 words (a, b), shifted right by sh bits: the 16 bytes that start m = 4*ws + sh/8
+// bytes into a
+__device__ __forceinline__ uint4 shift_words(const uint4 &a, const uint4 &b, int ws, uint32_t sh) {
+  uint32_t w0, w1, w2, w3, w4;
+  switch (ws) {
+    case 0: w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; break;
+    case 1: w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; break;
+    case 2: w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; break;
+    default: w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; break;
+  }
+  return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+
+// keep-mask of 32-bit word i of a 16-byte vector of 16/W elements, bit r of `bits` = element r valid
+template <int W>
+__device__ __forceinline__ uint32_t word_keep(uint32_t bits, int i) {
+  if (W >= 4) return ((bits >> (i * 4 / W)) & 1u) ? 0xffffffffu : 0u;
+  if (W == 2) {
+    const uint32_t b = bits >> (2 * i);
+    return ((b & 1u) ? 0x0000ffffu : 0u) | ((b & 2u) ? 0xffff0000u : 0u);
+  }
+  const uint32_t b = bits >> (4 * i);
+  return ((b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21)) * 0xffu;
+}
+
 }  // namespace dmb

@@ -239,6 +239,89 @@ list_emit_kernel(dmb_list_job job, BatchView b, const unsigned long long *__rest
     const uint64_t first = cbase & ~31ull, end = cbase + csum, stop = (end + 31ull) & ~31ull;
     uint32_t *bm32 = reinterpret_cast<uint32_t *>(job.out_child_validity);
     unsigned nulls = 0;
+    if (contiguous) {
+      // ---- the chunk's output is one run of its child vector: out[cbase + e] = child[run_d + e].  Aligned 16-byte output
+      // vectors (source misaligned by whole elements: two aligned loads + funnel shift), NULL elements zeroed from the mask
+      // bits read as aligned 32-bit words; the bitmap is a shifted word copy, one output word per thread.
+      constexpr int R = 16 / W;
+      const uint8_t *srcb = reinterpret_cast<const uint8_t *>(job.child_data) + (child0 + run_d) * W;
+      uint8_t *dstb = reinterpret_cast<uint8_t *>(job.out_child) + cbase * W;
+      const uintptr_t d0 = reinterpret_cast<uintptr_t>(dstb);
+      const uintptr_t dA = (d0 + 15u) & ~(uintptr_t)15, dE = (d0 + csum * W) & ~(uintptr_t)15;
+      const uint32_t *cm32 = reinterpret_cast<const uint32_t *>(cmask);
+      uint32_t head = (uint32_t)csum, tail0 = (uint32_t)csum;  // elements [0, head) and [tail0, csum) are copied one by one
+      if (dE > dA) {
+        head = (uint32_t)((dA - d0) / W);
+        tail0 = (uint32_t)((dE - d0) / W);
+        const uint32_t nvec = (uint32_t)((dE - dA) >> 4);
+        const uint8_t *s0 = srcb + (dA - d0);
+        const int m = (int)(reinterpret_cast<uintptr_t>(s0) & 15u);
+        const uint4 *sal = reinterpret_cast<const uint4 *>(s0 - m);
+        const int ws = m >> 2;
+        const uint32_t sh = (uint32_t)(m & 3) * 8u;
+        const uint64_t sbit0 = run_d + head;  // mask bit of the first element of vector 0
+        uint4 *dal = reinterpret_cast<uint4 *>(dA);
+#pragma unroll 2
+        for (uint32_t v = threadIdx.x; v < nvec; v += kThreads) {
+          const uint4 a = ld_stream(sal + v);
+          uint4 o = a;
+          if (m) o = shift_words(a, __ldg(sal + v + 1), ws, sh);
+          if (cm32) {
+            const uint32_t bits = load_bits32(cm32, (int64_t)(sbit0 + (uint64_t)v * R), R);
+            o.x &= word_keep<W>(bits, 0);
+            o.y &= word_keep<W>(bits, 1);
+            o.z &= word_keep<W>(bits, 2);
+            o.w &= word_keep<W>(bits, 3);
+          }
+          st_stream(dal + v, o);
+        }
+      }
+      // the elements in front of / behind the aligned vectors (fewer than 16 / W each; a tiny chunk: all of them)
+      {
+        using T = typename RawVec<W>::type;
+        const uint32_t ntail = (uint32_t)csum - tail0;
+        uint32_t e = 0xffffffffu;
+        if (threadIdx.x < head) e = threadIdx.x;
+        else if (threadIdx.x >= 32 && threadIdx.x - 32 < ntail && tail0 >= head) e = tail0 + (threadIdx.x - 32);
+        if (head == (uint32_t)csum) {  // no aligned vector at all: csum < 2 * R elements... or more when dE <= dA: walk them
+          for (uint32_t q = threadIdx.x; q < (uint32_t)csum; q += kThreads) {
+            const uint64_t src = run_d + q;
+            const bool valid = cm32 ? (load_bits32(cm32, (int64_t)src, 1) != 0u) : true;
+            T v;
+            memset(&v, 0, sizeof(T));
+            if (valid) v = *reinterpret_cast<const T *>(srcb + (uint64_t)q * W);
+            *reinterpret_cast<T *>(dstb + (uint64_t)q * W) = v;
+          }
+        } else if (e != 0xffffffffu) {
+          const uint64_t src = run_d + e;
+          const bool valid = cm32 ? (load_bits32(cm32, (int64_t)src, 1) != 0u) : true;
+          T v;
+          memset(&v, 0, sizeof(T));
+          if (valid) v = *reinterpret_cast<const T *>(srcb + (uint64_t)e * W);
+          *reinterpret_cast<T *>(dstb + (uint64_t)e * W) = v;
+        }
+      }
+      // bitmap: output word Ew holds the mask bits of elements [Ew, Ew + 32) of the run
+      unsigned nulls = 0;
+      for (uint64_t Ew = first + 32ull * threadIdx.x; Ew < stop; Ew += 32ull * kThreads) {
+        const uint64_t lo = Ew > cbase ? Ew : cbase, hi = Ew + 32 < end ? Ew + 32 : end;
+        if (hi <= lo) continue;
+        const int nb = (int)(hi - lo);
+        const uint32_t bits = cm32 ? load_bits32(cm32, (int64_t)(run_d + (lo - cbase)), nb) : (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
+        nulls += (unsigned)(nb - __popc(bits));
+        if (bm32) {
+          if (nb == 32) bm32[Ew >> 5] = bits;
+          else if (bits) atomicOr(bm32 + (Ew >> 5), bits << (unsigned)(lo - Ew));  // ragged first / last word: shared with the neighbouring chunks
+        }
+      }
+      if (job.child_null_count) {
+        nulls = __reduce_add_sync(0xffffffffu, nulls);
+        if (lane == 0 && nulls) atomicAdd(&s_nulls, nulls);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0 && job.child_null_count && s_nulls) atomicAdd(job.child_null_count, (unsigned long long)s_nulls);
+      continue;
+    }
     constexpr int U = 4;  // output elements per thread in flight
     using T = typename RawVec<W>::type;
     for (uint64_t E0 = first + threadIdx.x; E0 < stop; E0 += (uint64_t)U * kThreads) {  // a warp's 32 elements share one bitmap word
