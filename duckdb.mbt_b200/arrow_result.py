@@ -103,11 +103,27 @@ class HostBatch:
                 ed = nat.EnumDict(len(col.dictionary), 0, d_offs.ctypes.data, d_data.ctypes.data)
                 self._keep.append((d_offs, d_data, ed))
                 dict_ptr = C.pointer(ed)
+            list_ptr = None
+            if getattr(col, "list_child_data", None) is not None:  # LIST: dmb_host_list
+                from . import chunks as _ch
+                cphys = _ch.phys_of_type(col.list_child_type)
+                cw = _ch.PHYS_WIDTH[cphys]
+                cbase = col.list_child_data.ctypes.data
+                c_ptrs = (np.asarray(col.list_child_base, dtype=np.uint64) * np.uint64(cw) + np.uint64(cbase)).astype(np.uint64)
+                cv_ptrs = None
+                if col.list_child_validity is not None and np.any(np.asarray(col.list_child_val_off) >= 0):
+                    vo = np.asarray(col.list_child_val_off, dtype=np.int64)
+                    cv_ptrs = np.where(vo >= 0, col.list_child_validity.ctypes.data + 8 * vo, 0).astype(np.uint64)
+                sizes = np.ascontiguousarray(col.list_child_sizes, dtype=np.uint64)
+                hl = nat.HostList(col.list_child_type, cphys, 0, 0, c_ptrs.ctypes.data,
+                                  cv_ptrs.ctypes.data if cv_ptrs is not None else None, sizes.ctypes.data)
+                self._keep.append((c_ptrs, cv_ptrs, sizes, hl))
+                list_ptr = C.pointer(hl)
             self._keep.append((data_ptrs, val_ptrs, name))
             self._cols[j] = nat.HostColumn(name, col.type_id, col.phys, col.dec_width, col.dec_scale,
                                            C.cast(data_ptrs.ctypes.data, C.POINTER(C.c_void_p)),
                                            C.cast(val_ptrs.ctypes.data, C.POINTER(C.c_void_p)) if val_ptrs is not None else None,
-                                           heap_base, heap_len, dict_ptr)
+                                           heap_base, heap_len, dict_ptr, list_ptr)
         self.struct = nat.HostBatch(ncols, nat_flags(pinned), nchunks, self.counts.ctypes.data, self._cols)
 
 

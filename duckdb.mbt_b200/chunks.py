@@ -30,6 +30,7 @@ T_UTINYINT, T_USMALLINT, T_UINTEGER, T_UBIGINT, T_FLOAT, T_DOUBLE = 6, 7, 8, 9, 
 T_TIMESTAMP, T_DATE, T_TIME, T_INTERVAL, T_HUGEINT, T_VARCHAR, T_BLOB, T_DECIMAL = 12, 13, 14, 15, 16, 17, 18, 19
 T_TIMESTAMP_S, T_TIMESTAMP_MS, T_TIMESTAMP_NS = 20, 21, 22
 T_ENUM = 23
+T_LIST = 24
 T_UUID, T_TIME_TZ, T_TIMESTAMP_TZ, T_UHUGEINT, T_TIME_NS = 27, 30, 31, 32, 39
 
 # enum dmb_phys
@@ -82,6 +83,13 @@ class Column:
     heap: Optional[np.ndarray] = None  # uint8 string heap (VARCHAR/BLOB)
     inline_only: bool = False          # VARCHAR/BLOB: every string is inlined (<= 12 bytes): DMB_HEAP_INLINE_ONLY
     dictionary: Optional[List[bytes]] = None  # ENUM: the type's labels (duckdb_enum_dictionary_value), indices in `data`
+    # LIST: `data` holds duckdb_list_entry {uint64 offset, uint64 length}; per chunk the child vector the entries index
+    list_child_type: int = 0
+    list_child_data: Optional[np.ndarray] = None      # uint8: the child vectors of all chunks back to back
+    list_child_base: Optional[np.ndarray] = None      # uint64 [nchunks]: first element of chunk k's child vector
+    list_child_sizes: Optional[np.ndarray] = None     # uint64 [nchunks]: duckdb_list_vector_get_size
+    list_child_validity: Optional[np.ndarray] = None  # uint64 words
+    list_child_val_off: Optional[np.ndarray] = None   # int64 [nchunks], -1 = NULL mask pointer
 
     @property
     def width(self) -> int:

@@ -42,6 +42,7 @@ struct EnumDict {
 struct ArrowColOut {
   std::shared_ptr<CtxCore> core;
   std::shared_ptr<EnumDict> dict;  // dictionary-encoded export (ENUM)
+  std::shared_ptr<ArrowColOut> child;  // list<child> export (LIST)
   std::string name, format;
   int64_t length = 0, null_count = 0;
   void *validity = nullptr, *values = nullptr, *data = nullptr;  // values = offsets for utf8
@@ -70,6 +71,17 @@ struct Col {
   const uint8_t *heap_base = nullptr;
   uint64_t heap_len = 0;
   std::shared_ptr<EnumDict> dict;  // ENUM
+  // LIST: per-chunk child vectors
+  bool is_list = false;
+  int32_t child_type_id = 0, child_phys = 0, child_dec_width = 0, child_dec_scale = 0, child_width = 0;
+  std::vector<const void *> child_data;
+  std::vector<const void *> child_validity;  // empty = no masks at all
+  std::vector<uint64_t> child_sizes, child_base;  // child_base: element index of chunk k's child vector in the staged slab (nchunks + 1)
+  std::vector<int64_t> child_val_off;
+  uint8_t *d_child = nullptr;
+  uint64_t *d_child_validity = nullptr, *d_child_base = nullptr;
+  int64_t *d_child_val_off = nullptr;
+  bool child_staged = false;
   // device copy (lives as long as the result)
   bool staged = false;
   uint8_t *d_data = nullptr;
@@ -538,11 +550,131 @@ int32_t string_flags_error(unsigned long long flags) {
   return -1;
 }
 
+// ------------------------------------------------------------------ LIST columns (kernels_list.cu)
+struct ListRun {
+  void *d_offsets = nullptr;
+  size_t offsets_bytes = 0;
+  uint8_t *d_child = nullptr;
+  uint64_t *d_child_bitmap = nullptr;
+  FixedRun validity;  // the LIST column's own bitmap / null count
+  unsigned long long *h_ctr = nullptr;  // pinned: [0] child elements [1] child nulls [2] error flags [3] parent null count
+  uint64_t capacity = 0;
+  cudaEvent_t done = nullptr;
+};
+
+// the child vectors of all chunks back to back on the device (gathered through a pinned arena: the vectors have different sizes)
+int32_t stage_list_child(Result *r, int j) {
+  Col &col = r->cols[(size_t)j];
+  if (col.child_staged) return 0;
+  CtxCore &c = *r->core;
+  const int64_t nch = r->nchunks;
+  const uint64_t total = col.child_base[(size_t)nch];
+  const size_t W = (size_t)col.child_width;
+  uint64_t words = 0;
+  for (int64_t k = 0; k < nch; ++k)
+    if (col.child_val_off[(size_t)k] >= 0) words += (col.child_sizes[(size_t)k] + 63) / 64 + 1;
+  uint8_t *arena = (uint8_t *)keep_pin(r, (size_t)total * W + 64);
+  uint64_t *warena = (uint64_t *)keep_pin(r, (size_t)(words + 2) * 8);
+  uint64_t *h_base = (uint64_t *)keep_pin(r, (size_t)(nch + 1) * 8);
+  int64_t *h_voff = (int64_t *)keep_pin(r, (size_t)(nch + 1) * 8);
+  col.d_child = (uint8_t *)keep_dev(r, (size_t)total * W + 64);
+  col.d_child_validity = (uint64_t *)keep_dev(r, (size_t)(words + 2) * 8);
+  col.d_child_base = (uint64_t *)keep_dev(r, (size_t)(nch + 1) * 8);
+  col.d_child_val_off = (int64_t *)keep_dev(r, (size_t)(nch + 1) * 8);
+  if (!arena || !warena || !h_base || !h_voff || !col.d_child || !col.d_child_validity || !col.d_child_base || !col.d_child_val_off) return -1;
+  memset(warena, 0, (size_t)(words + 2) * 8);
+  parallel_for(nch, c.stage_threads, [&](int64_t k) {
+    const uint64_t sz = col.child_sizes[(size_t)k];
+    if (sz) memcpy(arena + (size_t)col.child_base[(size_t)k] * W, col.child_data[(size_t)k], (size_t)sz * W);
+    if (col.child_val_off[(size_t)k] >= 0) memcpy(warena + col.child_val_off[(size_t)k], col.child_validity[(size_t)k], (size_t)((sz + 63) / 64) * 8);
+  });
+  memcpy(h_base, col.child_base.data(), (size_t)(nch + 1) * 8);
+  memcpy(h_voff, col.child_val_off.data(), (size_t)nch * 8);
+  if (total && check_cuda(cudaMemcpyAsync(col.d_child, arena, (size_t)total * W, cudaMemcpyHostToDevice, c.s_in), "list child H2D")) return -1;
+  if (words && check_cuda(cudaMemcpyAsync(col.d_child_validity, warena, (size_t)words * 8, cudaMemcpyHostToDevice, c.s_in), "list child masks H2D")) return -1;
+  if (check_cuda(cudaMemcpyAsync(col.d_child_base, h_base, (size_t)(nch + 1) * 8, cudaMemcpyHostToDevice, c.s_in), "list child base H2D")) return -1;
+  if (nch && check_cuda(cudaMemcpyAsync(col.d_child_val_off, h_voff, (size_t)nch * 8, cudaMemcpyHostToDevice, c.s_in), "list child mask offsets H2D")) return -1;
+  r->bytes_h2d += total * W + words * 8 + (uint64_t)(2 * nch + 1) * 8;
+  col.child_staged = true;
+  return 0;
+}
+
+int32_t run_list(Result *r, Scope &sc, int j, ListRun *out) {
+  Col &col = r->cols[(size_t)j];
+  CtxCore &c = *r->core;
+  const int64_t n = r->nrows, nch = r->nchunks;
+  if (stage_list_child(r, j)) return -1;  // before stage_column: its event then covers these copies too (same stream)
+  if (col.staged) {  // the entries were staged earlier: order the compute stream behind the child copies as well
+    cudaEvent_t e = sc.event(false);
+    if (!e) return -1;
+    cudaEventRecord(e, c.s_in);
+    if (check_cuda(cudaStreamWaitEvent(c.s_compute, e, 0), "wait list child")) return -1;
+  }
+  // the column's own validity bitmap + null count (also stages the entries)
+  if (run_fixed(r, sc, j, DMB_OP_VALIDITY_ONLY, 0, true, false, &out->validity)) return -1;
+  // upper bound of the child elements the export can hold: every element of every child vector, or (shared spans) more:
+  // sized exactly by a host pass over the entries
+  uint64_t cap = 0;
+  {
+    std::vector<uint64_t> part((size_t)(nch > 0 ? nch : 1), 0);
+    parallel_for(nch, c.stage_threads, [&](int64_t k) {
+      const uint64_t *e = reinterpret_cast<const uint64_t *>(col.data[(size_t)k]);
+      const void *mask = col.validity.empty() ? nullptr : col.validity[(size_t)k];
+      uint64_t sum = 0;
+      for (uint32_t i = 0; e && i < r->counts[(size_t)k]; ++i)
+        if (host_row_valid(mask, i)) sum += e[2 * i + 1];
+      part[(size_t)k] = sum;
+    });
+    for (uint64_t v : part) cap += v;
+  }
+  if (cap > 0x7fffffffull) { set_error("LIST column %d: %llu child elements exceed int32 offsets; use smaller batches", j, (unsigned long long)cap); return -1; }
+  out->capacity = cap;
+  out->offsets_bytes = (size_t)(n + 1) * 4;
+  out->d_offsets = sc.dalloc(out->offsets_bytes + 64);
+  out->d_child = (uint8_t *)sc.dalloc((size_t)cap * (size_t)col.child_width + 64);
+  out->d_child_bitmap = (uint64_t *)sc.dalloc((size_t)((cap + 63) / 64 + 2) * 8);
+  unsigned long long *d_ctr = (unsigned long long *)sc.dalloc(16);
+  void *d_scratch = sc.dalloc(dmb_dev_list_scratch_bytes(nch) + 16);
+  out->h_ctr = (unsigned long long *)sc.palloc(32);
+  if (!out->d_offsets || !out->d_child || !out->d_child_bitmap || !d_ctr || !d_scratch || !out->h_ctr) return -1;
+  memset(out->h_ctr, 0, 32);
+  if (n == 0) return 0;
+  if (check_cuda(cudaMemsetAsync(d_ctr, 0, 16, c.s_compute), "list counters memset")) return -1;
+  dmb_list_job job;
+  memset(&job, 0, sizeof(job));
+  job.in_entries = col.d_data;
+  job.in_validity = col.d_validity;
+  job.vecs = col.d_vecs;
+  job.child_base = col.d_child_base;
+  job.child_data = col.d_child;
+  job.child_validity = col.child_validity.empty() ? nullptr : col.d_child_validity;
+  job.child_val_off = col.d_child_val_off;
+  job.out_offsets = out->d_offsets;
+  job.out_child = out->d_child;
+  job.out_child_validity = out->d_child_bitmap;
+  job.total = d_ctr;
+  job.child_null_count = d_ctr + 1;
+  job.child_width = col.child_width;
+  job.large = 0;
+  cudaEvent_t k0 = sc.event(true), k1 = sc.event(true), done = sc.event(false);
+  if (!k0 || !k1 || !done) return -1;
+  cudaEventRecord(k0, c.s_compute);
+  if (dmb_dev_list_batch(&job, r->d_counts, r->d_row_off, nch, n, (int64_t)cap, d_scratch, c.s_compute)) return -1;
+  cudaEventRecord(k1, c.s_compute);
+  sc.kernel_spans.emplace_back(k0, k1);
+  if (check_cuda(cudaMemcpyAsync(out->h_ctr, d_ctr, 16, cudaMemcpyDeviceToHost, c.s_compute), "list counters D2H")) return -1;
+  if (check_cuda(cudaMemcpyAsync(out->h_ctr + 2, d_scratch, 8, cudaMemcpyDeviceToHost, c.s_compute), "list flags D2H")) return -1;
+  if (check_cuda(cudaMemcpyAsync(out->h_ctr + 3, out->validity.d_null_count, 8, cudaMemcpyDeviceToHost, c.s_compute), "null count D2H")) return -1;
+  cudaEventRecord(done, c.s_compute);
+  out->done = done;
+  return 0;
+}
+
 // ------------------------------------------------------------------ DuckDB type -> Arrow
 struct ArrowMap {
   int32_t op = -1;      // fixed-width conversion, or -1 for strings
-  bool is_string = false;
-  std::string format;
+  bool is_string = false, is_list = false;
+  std::string format, child_format;
 };
 
 bool arrow_map(const Col &col, ArrowMap *m) {
@@ -581,6 +713,22 @@ bool arrow_map(const Col &col, ArrowMap *m) {
     case DMB_TYPE_ENUM:  // dictionary-encoded: the indices as stored, the labels as the dictionary (export_column)
       if (!col.dict) { set_error("ENUM column without a dictionary"); return false; }
       return same(col.phys == DMB_PHYS_U8 ? "C" : col.phys == DMB_PHYS_U16 ? "S" : "I");
+    case DMB_TYPE_LIST: {  // list<child>, child copied as stored
+      if (!col.is_list) { set_error("LIST column without child vectors"); return false; }
+      Col child;
+      child.type_id = col.child_type_id;
+      child.phys = col.child_phys;
+      child.dec_width = col.child_dec_width;
+      child.dec_scale = col.child_dec_scale;
+      ArrowMap cm;
+      if (child.type_id == DMB_TYPE_LIST || child.type_id == DMB_TYPE_ENUM || !arrow_map(child, &cm)) { set_error("LIST child type %d has no Arrow mapping here", child.type_id); return false; }
+      const bool as_stored = !cm.is_string && (cm.op == DMB_OP(child.phys, DMB_DST_SAME) || child.type_id == DMB_TYPE_HUGEINT);
+      if (!as_stored) { set_error("LIST child type %d needs a conversion (only children exported as stored are supported)", child.type_id); return false; }
+      m->is_list = true;
+      m->format = "+l";
+      m->child_format = cm.format;
+      return true;
+    }
     case DMB_TYPE_VARCHAR: m->is_string = true; m->format = "u"; return true;
     case DMB_TYPE_BLOB: m->is_string = true; m->format = "z"; return true;
     default: set_error("column type %d has no Arrow mapping", col.type_id); return false;
@@ -591,6 +739,8 @@ struct Pending {  // one column between its kernel launch and its device->host c
   ArrowMap map;
   FixedRun fr;
   StringRun sr;
+  ListRun lr;
+  int32_t list_child_width = 0;
   std::shared_ptr<ArrowColOut> out;
   unsigned long long *h_null = nullptr;
 };
@@ -603,6 +753,13 @@ int32_t launch_arrow_col(Result *r, Scope &sc, int j, int string_mode, Pending *
   p->out->name = col.name;
   p->out->length = r->nrows;
   if (col.type_id == DMB_TYPE_ENUM) p->out->dict = col.dict;
+  if (p->map.is_list) {
+    p->lr = ListRun();
+    if (run_list(r, sc, j, &p->lr)) return -1;
+    p->list_child_width = col.child_width;
+    p->out->format = p->map.format;
+    return 0;
+  }
   if (p->map.is_string) {
     p->sr = StringRun();
     if (run_string(r, sc, j, string_mode, true, false, &p->sr)) return -1;
@@ -621,6 +778,45 @@ int32_t drain_arrow_col(Result *r, Scope &sc, Pending *p) {
   CtxCore &c = *r->core;
   ArrowColOut &o = *p->out;
   const int64_t n = r->nrows;
+  if (p->map.is_list) {
+    ListRun &l = p->lr;
+    o.values_bytes = l.offsets_bytes;
+    o.validity_bytes = l.validity.bitmap_bytes;
+    o.values = c.pin.alloc(o.values_bytes + 64);
+    o.validity = c.pin.alloc(o.validity_bytes + 64);
+    auto ch = std::make_shared<ArrowColOut>();
+    ch->core = r->core;
+    ch->name = "item";
+    ch->format = p->map.child_format;
+    o.child = ch;
+    if (!o.values || !o.validity) return -1;
+    if (n == 0) {
+      memset(o.values, 0, o.values_bytes);
+      ch->values = c.pin.alloc(64);
+      ch->validity = c.pin.alloc(64);
+      return (ch->values && ch->validity) ? 0 : -1;
+    }
+    if (check_cuda(cudaEventSynchronize(l.done), "list kernel wait")) return -1;
+    if (l.h_ctr[2] & 1ull) { set_error("LIST child elements exceed int32 offsets; use smaller batches"); return -1; }
+    if (l.h_ctr[2]) { set_error("a LIST chunk holds more than 4 G child elements"); return -1; }
+    const size_t total = (size_t)l.h_ctr[0];
+    const size_t cw = (size_t)p->list_child_width;
+    ch->length = (int64_t)total;
+    ch->null_count = (int64_t)l.h_ctr[1];
+    ch->values_bytes = total * cw;
+    ch->validity_bytes = (total + 7) / 8;
+    ch->values = c.pin.alloc(ch->values_bytes + 64);
+    ch->validity = c.pin.alloc(ch->validity_bytes + 64);
+    if (!ch->values || !ch->validity) return -1;
+    o.null_count = (int64_t)l.h_ctr[3];
+    if (check_cuda(cudaStreamWaitEvent(c.s_out, l.done, 0), "wait kernel")) return -1;
+    if (check_cuda(cudaMemcpyAsync(o.values, l.d_offsets, o.values_bytes, cudaMemcpyDeviceToHost, c.s_out), "list offsets D2H")) return -1;
+    if (o.validity_bytes && check_cuda(cudaMemcpyAsync(o.validity, l.validity.d_bitmap, o.validity_bytes, cudaMemcpyDeviceToHost, c.s_out), "bitmap D2H")) return -1;
+    if (ch->values_bytes && check_cuda(cudaMemcpyAsync(ch->values, l.d_child, ch->values_bytes, cudaMemcpyDeviceToHost, c.s_out), "list child D2H")) return -1;
+    if (ch->validity_bytes && check_cuda(cudaMemcpyAsync(ch->validity, l.d_child_bitmap, ch->validity_bytes, cudaMemcpyDeviceToHost, c.s_out), "list child bitmap D2H")) return -1;
+    r->bytes_d2h += o.values_bytes + o.validity_bytes + ch->values_bytes + ch->validity_bytes;
+    return 0;
+  }
   if (p->map.is_string) {
     StringRun &s = p->sr;
     if (check_cuda(cudaEventSynchronize(s.done), "string kernel wait")) return -1;
@@ -698,7 +894,7 @@ int32_t materialise_arrow(Result *r) {
       std::vector<uint64_t> weight((size_t)ncols);
       for (int j = 0; j < ncols; ++j) {
         const Col &col = r->cols[(size_t)j];
-        weight[(size_t)j] = (uint64_t)col.width * (uint64_t)r->nrows + col.heap_len;
+        weight[(size_t)j] = (uint64_t)col.width * (uint64_t)r->nrows + col.heap_len + (col.is_list ? col.child_base.back() * (uint64_t)col.child_width : 0);
         sorted[(size_t)j] = j;
       }
       std::stable_sort(sorted.begin(), sorted.end(), [&](int a, int b) { return weight[(size_t)a] < weight[(size_t)b]; });
@@ -722,7 +918,7 @@ int32_t materialise_arrow(Result *r) {
       return -1;
     for (int j = 0; j < ncols; ++j) {
       Pending &p = pend[(size_t)j];
-      if (!p.map.is_string && p.h_null) p.out->null_count = (int64_t)*p.h_null;
+      if (!p.map.is_string && !p.map.is_list && p.h_null) p.out->null_count = (int64_t)*p.h_null;
       r->cols[(size_t)j].arrow = p.out;
     }
     float f = 0;
@@ -792,6 +988,14 @@ void export_column(const std::shared_ptr<ArrowColOut> &o, ArrowArray *a, ArrowSc
     a->buffers = p->buffers;
     a->release = release_array;
     a->private_data = p;
+    if (o->child) {  // LIST: one child array
+      a->n_buffers = 2;
+      ArrowArray *ca = (ArrowArray *)calloc(1, sizeof(ArrowArray));
+      export_column(o->child, ca, nullptr);
+      p->child_arrays.push_back(ca);
+      a->n_children = 1;
+      a->children = p->child_arrays.data();
+    }
     if (o->dict) {  // ENUM: the labels as a utf8 dictionary array (no nulls), buffers shared with the result
       static const char kNoBytes[1] = {0};
       ArrowArray *da = (ArrowArray *)calloc(1, sizeof(ArrowArray));
@@ -818,6 +1022,13 @@ void export_column(const std::shared_ptr<ArrowColOut> &o, ArrowArray *a, ArrowSc
     s->flags = 2;  // ARROW_FLAG_NULLABLE
     s->release = release_schema;
     s->private_data = p;
+    if (o->child) {
+      ArrowSchema *cs = (ArrowSchema *)calloc(1, sizeof(ArrowSchema));
+      export_column(o->child, nullptr, cs);
+      p->child_schemas.push_back(cs);
+      s->n_children = 1;
+      s->children = p->child_schemas.data();
+    }
     if (o->dict) {
       ArrowSchema *ds = (ArrowSchema *)calloc(1, sizeof(ArrowSchema));
       ExportPriv *dp = new ExportPriv();
@@ -1102,6 +1313,37 @@ extern "C" duckdb_mb_arrow_result *duckdb_mb_gpu_result_from_chunks(duckdb_mb_gp
       }
       if (d->offsets[d->size]) dict->data.assign(d->data, d->data + d->offsets[d->size]);
       col.dict = dict;
+    }
+    if (hc.type_id == DMB_TYPE_LIST) {
+      const dmb_host_list *l = hc.list;
+      if (col.width != 16) { set_error("column %d: LIST vectors hold 16-byte list entries (phys DMB_PHYS_U128)", j); return nullptr; }
+      if (!l || (batch->nchunks > 0 && (!l->child_data || !l->child_sizes))) { set_error("column %d: LIST column without child vectors", j); return nullptr; }
+      col.is_list = true;
+      col.child_type_id = l->child_type_id;
+      col.child_phys = l->child_phys;
+      col.child_dec_width = l->child_dec_width;
+      col.child_dec_scale = l->child_dec_scale;
+      col.child_width = dmb_phys_width(l->child_phys);
+      if (col.child_width <= 0 || l->child_phys == DMB_PHYS_STRING) { set_error("column %d: LIST child must be a fixed-width type (physical type %d)", j, l->child_phys); return nullptr; }
+      col.child_data.assign(l->child_data, l->child_data + batch->nchunks);
+      col.child_sizes.assign(l->child_sizes, l->child_sizes + batch->nchunks);
+      if (l->child_validity) {
+        col.child_validity.assign((const void *const *)l->child_validity, (const void *const *)l->child_validity + batch->nchunks);
+        bool any = false;
+        for (const void *p : col.child_validity) any |= p != nullptr;
+        if (!any) col.child_validity.clear();
+      }
+      col.child_base.assign((size_t)batch->nchunks + 1, 0);
+      col.child_val_off.assign((size_t)(batch->nchunks > 0 ? batch->nchunks : 1), -1);
+      uint64_t words = 0;
+      for (int64_t k = 0; k < batch->nchunks; ++k) {
+        if (col.child_sizes[(size_t)k] && !col.child_data[(size_t)k]) { set_error("column %d: chunk %lld has child elements but a null child pointer", j, (long long)k); return nullptr; }
+        col.child_base[(size_t)k + 1] = col.child_base[(size_t)k] + col.child_sizes[(size_t)k];
+        if (!col.child_validity.empty() && col.child_validity[(size_t)k]) {
+          col.child_val_off[(size_t)k] = (int64_t)words;
+          words += (col.child_sizes[(size_t)k] + 63) / 64 + 1;
+        }
+      }
     }
   }
   return r.release();

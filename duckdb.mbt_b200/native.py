@@ -68,10 +68,15 @@ class ListJob(C.Structure):
                 ("total", C.c_void_p), ("child_null_count", C.c_void_p), ("child_width", C.c_int32), ("large", C.c_int32)]
 
 
+class HostList(C.Structure):
+    _fields_ = [("child_type_id", C.c_int32), ("child_phys", C.c_int32), ("child_dec_width", C.c_int32), ("child_dec_scale", C.c_int32),
+                ("child_data", C.c_void_p), ("child_validity", C.c_void_p), ("child_sizes", C.c_void_p)]
+
+
 class HostColumn(C.Structure):
     _fields_ = [("name", C.c_char_p), ("type_id", C.c_int32), ("phys", C.c_int32), ("dec_width", C.c_int32),
                 ("dec_scale", C.c_int32), ("data", C.POINTER(C.c_void_p)), ("validity", C.POINTER(C.c_void_p)),
-                ("heap_base", C.c_void_p), ("heap_len", C.c_uint64), ("dict", C.POINTER(EnumDict))]
+                ("heap_base", C.c_void_p), ("heap_len", C.c_uint64), ("dict", C.POINTER(EnumDict)), ("list", C.POINTER(HostList))]
 
 
 class HostBatch(C.Structure):

@@ -57,6 +57,7 @@ enum dmb_type {
   DMB_TYPE_TIMESTAMP_MS = 21,
   DMB_TYPE_TIMESTAMP_NS = 22,
   DMB_TYPE_ENUM = 23,     /* uint8/16/32 indices into the type's dictionary (dmb_enum_dict) */
+  DMB_TYPE_LIST = 24,     /* duckdb_list_entry vectors + one child vector per chunk (dmb_host_list) */
   DMB_TYPE_UUID = 27,
   DMB_TYPE_TIME_TZ = 30,
   DMB_TYPE_TIMESTAMP_TZ = 31,
@@ -374,6 +375,20 @@ typedef struct dmb_enum_dict {
   const char *data;
 } dmb_enum_dict;
 
+/* LIST of a fixed-width child: the column's vectors hold duckdb_list_entry {uint64 offset, uint64 length} (phys
+ * DMB_PHYS_U128: 16 bytes per row); per chunk, the child vector the entries index: duckdb_list_vector_get_child(v)
+ * -> duckdb_vector_get_data / _get_validity, and duckdb_list_vector_get_size(v) elements of it.  Arrow export only
+ * (list<child>, child copied as stored: integer / float / DATE / TIME / TIMESTAMP* / HUGEINT / UUID children); the
+ * reference rejects LIST on its chunk path (src/duckdb_native.c:271-303) and has no Arrow mapping for it. */
+typedef struct dmb_host_list {
+  int32_t child_type_id;                  /* enum dmb_type */
+  int32_t child_phys;                     /* enum dmb_phys */
+  int32_t child_dec_width, child_dec_scale;
+  const void *const *child_data;          /* [nchunks] */
+  const uint64_t *const *child_validity;  /* [nchunks], entries may be NULL; the array may be NULL */
+  const uint64_t *child_sizes;            /* [nchunks] elements in each chunk's child vector */
+} dmb_host_list;
+
 /* One column of a host chunk batch: the pointers duckdb_vector_get_data /
  * duckdb_vector_get_validity return for each chunk (src/duckdb_native.c:529-530,547). */
 typedef struct dmb_host_column {
@@ -390,6 +405,7 @@ typedef struct dmb_host_column {
   const void *heap_base;
   uint64_t heap_len;
   const dmb_enum_dict *dict;        /* ENUM columns: the dictionary (copied by result_from_chunks); else NULL */
+  const dmb_host_list *list;        /* LIST columns: the per-chunk child vectors (pointer tables copied); else NULL */
 } dmb_host_column;
 
 /* heap_base == DMB_HEAP_INLINE_ONLY (heap_len 0): the caller guarantees that every string of the

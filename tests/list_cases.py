@@ -21,7 +21,7 @@ def make_list_column(n, width, pattern, seed, layout="contiguous", null_frac=0.2
     lc.valid = rng.random(n) >= null_frac if null_frac else np.ones(n, bool)
     lc.lens = rng.integers(0, max_len + 1, n).astype(np.uint64)
     entries = np.zeros((nch, ch.VECTOR_SIZE, 2), dtype=np.uint64)
-    child_chunks, cmask_chunks, child_base, child_val_off = [], [], [], []
+    child_chunks, cmask_chunks, child_base, child_val_off, child_sizes = [], [], [], [], []
     lc.expected = []  # python lists (None = NULL row; None elements = NULL child)
     row, base_el, base_w = 0, 0, 0
     for k in range(nch):
@@ -60,6 +60,7 @@ def make_list_column(n, width, pattern, seed, layout="contiguous", null_frac=0.2
         all_valid = bool(cvalid.all()) and k % 2 == 1  # some chunks hand out a NULL mask pointer
         child_chunks.append(vals.reshape(-1))
         child_base.append(base_el)
+        child_sizes.append(size)
         child_val_off.append(-1 if all_valid else base_w)
         cmask_chunks.append(words)
         base_el += size
@@ -72,5 +73,18 @@ def make_list_column(n, width, pattern, seed, layout="contiguous", null_frac=0.2
     lc.child_validity = np.concatenate(cmask_chunks) if cmask_chunks else np.zeros(1, np.uint64)
     lc.child_base = np.asarray(child_base, dtype=np.uint64)
     lc.child_val_off = np.asarray(child_val_off, dtype=np.int64)
+    lc.child_sizes = np.asarray(child_sizes, dtype=np.uint64)
     lc.capacity = int(np.where(lc.valid, lc.lens, 0).sum())
     return lc
+
+
+def as_column(lc, name, child_type):
+    """the LIST column as a chunks.Column for the host API (dmb_host_column + dmb_host_list)"""
+    col = ch.Column(name, ch.T_LIST, ch.P_U128, lc.entries, lc.data_off, lc.validity, lc.val_off)
+    col.list_child_type = child_type
+    col.list_child_data = lc.child_data
+    col.list_child_base = lc.child_base
+    col.list_child_sizes = lc.child_sizes
+    col.list_child_validity = lc.child_validity
+    col.list_child_val_off = lc.child_val_off
+    return col
