@@ -132,3 +132,40 @@ def test_list_column_of_an_unsupported_child_is_an_error():
     with ar.GpuContext(0) as ctx, ar.ArrowResult.from_chunks(ctx, batch) as res:
         with pytest.raises(Exception, match="LIST child"):
             res.to_arrow(0)
+
+
+def test_list_and_enum_edge_cases_through_the_host_api():
+    """no chunks at all, all-NULL lists, only empty lists, an empty ENUM dictionary behind all-NULL rows"""
+    pa = pytest.importorskip("pyarrow")
+    from duckdb_mbt_b200 import arrow_result as ar
+    with ar.GpuContext(0) as ctx:
+        # all rows NULL: no child element is ever read (the entries are garbage)
+        lc = list_cases.make_list_column(3000, 4, "ragged", 5, "contiguous", null_frac=1.0)
+        with ar.ArrowResult.from_chunks(ctx, ch.ChunkBatch(lc.counts, [list_cases.as_column(lc, "l", ch.T_INTEGER)])) as res:
+            arr = res.to_arrow(0)
+            arr.validate(full=True)
+            assert arr.null_count == 3000 and len(arr.values) == 0
+        # only empty lists
+        lc = list_cases.make_list_column(2500, 8, "full", 6, "contiguous", null_frac=0.0, max_len=0)
+        with ar.ArrowResult.from_chunks(ctx, ch.ChunkBatch(lc.counts, [list_cases.as_column(lc, "l", ch.T_BIGINT)])) as res:
+            arr = res.to_arrow(0)
+            arr.validate(full=True)
+            assert arr.to_pylist() == [[]] * 2500
+        # a result without chunks
+        lc = list_cases.make_list_column(0, 4, "full", 7, "contiguous")
+        en = ch.enum_column("e", [b"a", b"bb"], np.zeros(0, np.int64), lc.counts)
+        with ar.ArrowResult.from_chunks(ctx, ch.ChunkBatch(lc.counts, [list_cases.as_column(lc, "l", ch.T_INTEGER), en])) as res:
+            assert res.row_count() == 0
+            rb = res.to_record_batch()
+            rb.validate(full=True)
+            assert rb.num_rows == 0 and pa.types.is_list(rb.column(0).type) and pa.types.is_dictionary(rb.column(1).type)
+            assert res.get_column_string(1) == []
+        # ENUM: all rows NULL over an empty dictionary
+        counts = ch.chunk_counts(100, "full")
+        en = ch.enum_column("e", [], np.zeros(100, np.int64), counts, valid=np.zeros(100, bool))
+        with ar.ArrowResult.from_chunks(ctx, ch.ChunkBatch(counts, [en])) as res:
+            arr = res.to_arrow(0)
+            arr.validate(full=True)
+            assert arr.null_count == 100 and len(arr.dictionary) == 0
+            strs, valid = res.get_column_string_nullable(0)
+            assert not any(valid)
