@@ -106,7 +106,7 @@ class HostBatch:
             list_ptr = None
             if getattr(col, "list_child_data", None) is not None:  # LIST: dmb_host_list
                 from . import chunks as _ch
-                cphys = _ch.phys_of_type(col.list_child_type)
+                cphys = _ch.phys_of_type(col.list_child_type, col.list_child_dec_width)
                 cw = _ch.PHYS_WIDTH[cphys]
                 cbase = col.list_child_data.ctypes.data
                 c_ptrs = (np.asarray(col.list_child_base, dtype=np.uint64) * np.uint64(cw) + np.uint64(cbase)).astype(np.uint64)
@@ -115,7 +115,7 @@ class HostBatch:
                     vo = np.asarray(col.list_child_val_off, dtype=np.int64)
                     cv_ptrs = np.where(vo >= 0, col.list_child_validity.ctypes.data + 8 * vo, 0).astype(np.uint64)
                 sizes = np.ascontiguousarray(col.list_child_sizes, dtype=np.uint64)
-                hl = nat.HostList(col.list_child_type, cphys, 0, 0, c_ptrs.ctypes.data,
+                hl = nat.HostList(col.list_child_type, cphys, col.list_child_dec_width, col.list_child_dec_scale, c_ptrs.ctypes.data,
                                   cv_ptrs.ctypes.data if cv_ptrs is not None else None, sizes.ctypes.data)
                 self._keep.append((c_ptrs, cv_ptrs, sizes, hl))
                 list_ptr = C.pointer(hl)

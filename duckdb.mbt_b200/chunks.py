@@ -85,6 +85,8 @@ class Column:
     dictionary: Optional[List[bytes]] = None  # ENUM: the type's labels (duckdb_enum_dictionary_value), indices in `data`
     # LIST: `data` holds duckdb_list_entry {uint64 offset, uint64 length}; per chunk the child vector the entries index
     list_child_type: int = 0
+    list_child_dec_width: int = 0
+    list_child_dec_scale: int = 0
     list_child_data: Optional[np.ndarray] = None      # uint8: the child vectors of all chunks back to back
     list_child_base: Optional[np.ndarray] = None      # uint64 [nchunks]: first element of chunk k's child vector
     list_child_sizes: Optional[np.ndarray] = None     # uint64 [nchunks]: duckdb_list_vector_get_size

@@ -559,6 +559,8 @@ struct ListRun {
   FixedRun validity;  // the LIST column's own bitmap / null count
   unsigned long long *h_ctr = nullptr;  // pinned: [0] child elements [1] child nulls [2] error flags [3] parent null count
   uint64_t capacity = 0;
+  uint8_t *d_child_out = nullptr;  // the child in its Arrow form (== d_child when it is exported as stored)
+  size_t child_out_bytes = 0;
   cudaEvent_t done = nullptr;
 };
 
@@ -599,7 +601,9 @@ int32_t stage_list_child(Result *r, int j) {
   return 0;
 }
 
-int32_t run_list(Result *r, Scope &sc, int j, ListRun *out) {
+// child_op: the child's fixed-width conversion (DMB_OP(child phys, dst)); children that are not exported as stored
+// (BOOLEAN -> bits, DECIMAL -> decimal128, INTERVAL -> month_day_nano) take a second pass over the gathered, dense child
+int32_t run_list(Result *r, Scope &sc, int j, int32_t child_op, bool child_as_stored, ListRun *out) {
   Col &col = r->cols[(size_t)j];
   CtxCore &c = *r->core;
   const int64_t n = r->nrows, nch = r->nchunks;
@@ -632,7 +636,7 @@ int32_t run_list(Result *r, Scope &sc, int j, ListRun *out) {
   out->offsets_bytes = (size_t)(n + 1) * 4;
   out->d_offsets = sc.dalloc(out->offsets_bytes + 64);
   out->d_child = (uint8_t *)sc.dalloc((size_t)cap * (size_t)col.child_width + 64);
-  out->d_child_bitmap = (uint64_t *)sc.dalloc((size_t)((cap + 63) / 64 + 2) * 8);
+  out->d_child_bitmap = (uint64_t *)sc.dalloc((size_t)((cap + DMB_VECTOR_SIZE - 1) / DMB_VECTOR_SIZE * DMB_VALIDITY_WORDS + 2) * 8);  // whole 32-word masks: the conversion pass reads it as chunk masks
   unsigned long long *d_ctr = (unsigned long long *)sc.dalloc(16);
   void *d_scratch = sc.dalloc(dmb_dev_list_scratch_bytes(nch) + 16);
   out->h_ctr = (unsigned long long *)sc.palloc(32);
@@ -662,6 +666,41 @@ int32_t run_list(Result *r, Scope &sc, int j, ListRun *out) {
   if (dmb_dev_list_batch(&job, r->d_counts, r->d_row_off, nch, n, (int64_t)cap, d_scratch, c.s_compute)) return -1;
   cudaEventRecord(k1, c.s_compute);
   sc.kernel_spans.emplace_back(k0, k1);
+  out->d_child_out = out->d_child;
+  out->child_out_bytes = (size_t)cap * (size_t)col.child_width;
+  if (!child_as_stored && cap > 0) {
+    // the gathered child is a dense column: 2048-element "chunks", its bitmap = their 32-word masks back to back
+    const int32_t ow = dmb_op_out_width(child_op);
+    if (ow < 0) { set_error("LIST column %d: unsupported child conversion 0x%x", j, child_op); return -1; }
+    const int64_t nck = (int64_t)((cap + DMB_VECTOR_SIZE - 1) / DMB_VECTOR_SIZE);
+    std::vector<uint32_t> cc((size_t)nck, DMB_VECTOR_SIZE);
+    std::vector<int64_t> ro((size_t)nck + 1);
+    std::vector<dmb_vec_desc> vd((size_t)nck);
+    cc[(size_t)nck - 1] = (uint32_t)(cap - (uint64_t)(nck - 1) * DMB_VECTOR_SIZE);
+    for (int64_t k = 0; k < nck; ++k) {
+      ro[(size_t)k] = k * (int64_t)DMB_VECTOR_SIZE;
+      vd[(size_t)k].data_off = (uint64_t)k * DMB_VECTOR_SIZE * (uint64_t)col.child_width;
+      vd[(size_t)k].val_off = k * DMB_VALIDITY_WORDS;
+    }
+    ro[(size_t)nck] = (int64_t)cap;
+    uint32_t *d_cc = (uint32_t *)upload_job(sc, cc.data(), cc.size() * sizeof(uint32_t));
+    int64_t *d_ro = (int64_t *)upload_job(sc, ro.data(), ro.size() * sizeof(int64_t));
+    dmb_vec_desc *d_vd = (dmb_vec_desc *)upload_job(sc, vd.data(), vd.size() * sizeof(dmb_vec_desc));
+    out->child_out_bytes = ow == 0 ? (size_t)((cap + 7) / 8) : (size_t)cap * (size_t)ow;
+    out->d_child_out = (uint8_t *)sc.dalloc(out->child_out_bytes + 64);
+    if (!d_cc || !d_ro || !d_vd || !out->d_child_out) return -1;
+    dmb_fixed_job fj;
+    memset(&fj, 0, sizeof(fj));
+    fj.in_data = out->d_child;
+    fj.in_validity = out->d_child_bitmap;
+    fj.vecs = d_vd;
+    fj.out_values = out->d_child_out;
+    fj.op = child_op;
+    void *fjd = upload_job(sc, &fj, sizeof(fj));
+    if (!fjd) return -1;
+    if (dmb_dev_fixed_batch((const dmb_fixed_job *)fjd, &fj, 1, d_cc, d_ro, nck, (int64_t)cap, c.s_compute)) return -1;
+    cudaEventRecord(k1, c.s_compute);  // the span now covers the conversion pass
+  }
   if (check_cuda(cudaMemcpyAsync(out->h_ctr, d_ctr, 16, cudaMemcpyDeviceToHost, c.s_compute), "list counters D2H")) return -1;
   if (check_cuda(cudaMemcpyAsync(out->h_ctr + 2, d_scratch, 8, cudaMemcpyDeviceToHost, c.s_compute), "list flags D2H")) return -1;
   if (check_cuda(cudaMemcpyAsync(out->h_ctr + 3, out->validity.d_null_count, 8, cudaMemcpyDeviceToHost, c.s_compute), "null count D2H")) return -1;
@@ -675,6 +714,8 @@ struct ArrowMap {
   int32_t op = -1;      // fixed-width conversion, or -1 for strings
   bool is_string = false, is_list = false;
   std::string format, child_format;
+  int32_t child_op = -1;
+  bool child_as_stored = true;
 };
 
 bool arrow_map(const Col &col, ArrowMap *m) {
@@ -722,8 +763,9 @@ bool arrow_map(const Col &col, ArrowMap *m) {
       child.dec_scale = col.child_dec_scale;
       ArrowMap cm;
       if (child.type_id == DMB_TYPE_LIST || child.type_id == DMB_TYPE_ENUM || !arrow_map(child, &cm)) { set_error("LIST child type %d has no Arrow mapping here", child.type_id); return false; }
-      const bool as_stored = !cm.is_string && (cm.op == DMB_OP(child.phys, DMB_DST_SAME) || child.type_id == DMB_TYPE_HUGEINT);
-      if (!as_stored) { set_error("LIST child type %d needs a conversion (only children exported as stored are supported)", child.type_id); return false; }
+      if (cm.is_string) { set_error("LIST child type %d: VARCHAR / BLOB children are not exported yet", child.type_id); return false; }
+      m->child_as_stored = cm.op == DMB_OP(child.phys, DMB_DST_SAME) || child.type_id == DMB_TYPE_HUGEINT;
+      m->child_op = cm.op;
       m->is_list = true;
       m->format = "+l";
       m->child_format = cm.format;
@@ -755,7 +797,7 @@ int32_t launch_arrow_col(Result *r, Scope &sc, int j, int string_mode, Pending *
   if (col.type_id == DMB_TYPE_ENUM) p->out->dict = col.dict;
   if (p->map.is_list) {
     p->lr = ListRun();
-    if (run_list(r, sc, j, &p->lr)) return -1;
+    if (run_list(r, sc, j, p->map.child_op, p->map.child_as_stored, &p->lr)) return -1;
     p->list_child_width = col.child_width;
     p->out->format = p->map.format;
     return 0;
@@ -800,10 +842,10 @@ int32_t drain_arrow_col(Result *r, Scope &sc, Pending *p) {
     if (l.h_ctr[2] & 1ull) { set_error("LIST child elements exceed int32 offsets; use smaller batches"); return -1; }
     if (l.h_ctr[2]) { set_error("a LIST chunk holds more than 4 G child elements"); return -1; }
     const size_t total = (size_t)l.h_ctr[0];
-    const size_t cw = (size_t)p->list_child_width;
     ch->length = (int64_t)total;
     ch->null_count = (int64_t)l.h_ctr[1];
-    ch->values_bytes = total * cw;
+    ch->values_bytes = l.child_out_bytes;
+    if (total != l.capacity) { set_error("LIST column: the device gathered %zu child elements, the host counted %llu", total, (unsigned long long)l.capacity); return -1; }
     ch->validity_bytes = (total + 7) / 8;
     ch->values = c.pin.alloc(ch->values_bytes + 64);
     ch->validity = c.pin.alloc(ch->validity_bytes + 64);
@@ -812,7 +854,7 @@ int32_t drain_arrow_col(Result *r, Scope &sc, Pending *p) {
     if (check_cuda(cudaStreamWaitEvent(c.s_out, l.done, 0), "wait kernel")) return -1;
     if (check_cuda(cudaMemcpyAsync(o.values, l.d_offsets, o.values_bytes, cudaMemcpyDeviceToHost, c.s_out), "list offsets D2H")) return -1;
     if (o.validity_bytes && check_cuda(cudaMemcpyAsync(o.validity, l.validity.d_bitmap, o.validity_bytes, cudaMemcpyDeviceToHost, c.s_out), "bitmap D2H")) return -1;
-    if (ch->values_bytes && check_cuda(cudaMemcpyAsync(ch->values, l.d_child, ch->values_bytes, cudaMemcpyDeviceToHost, c.s_out), "list child D2H")) return -1;
+    if (ch->values_bytes && check_cuda(cudaMemcpyAsync(ch->values, l.d_child_out, ch->values_bytes, cudaMemcpyDeviceToHost, c.s_out), "list child D2H")) return -1;
     if (ch->validity_bytes && check_cuda(cudaMemcpyAsync(ch->validity, l.d_child_bitmap, ch->validity_bytes, cudaMemcpyDeviceToHost, c.s_out), "list child bitmap D2H")) return -1;
     r->bytes_d2h += o.values_bytes + o.validity_bytes + ch->values_bytes + ch->validity_bytes;
     return 0;

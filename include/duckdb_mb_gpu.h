@@ -378,7 +378,8 @@ typedef struct dmb_enum_dict {
 /* LIST of a fixed-width child: the column's vectors hold duckdb_list_entry {uint64 offset, uint64 length} (phys
  * DMB_PHYS_U128: 16 bytes per row); per chunk, the child vector the entries index: duckdb_list_vector_get_child(v)
  * -> duckdb_vector_get_data / _get_validity, and duckdb_list_vector_get_size(v) elements of it.  Arrow export only
- * (list<child>, child copied as stored: integer / float / DATE / TIME / TIMESTAMP* / HUGEINT / UUID children); the
+ * (list<child>; the child in the Arrow form of its type, as for a top-level column: BOOLEAN bit-packed, DECIMAL as
+ * decimal128, INTERVAL as month_day_nano, the other fixed-width types as stored); the
  * reference rejects LIST on its chunk path (src/duckdb_native.c:271-303) and has no Arrow mapping for it. */
 typedef struct dmb_host_list {
   int32_t child_type_id;                  /* enum dmb_type */

@@ -78,10 +78,11 @@ def make_list_column(n, width, pattern, seed, layout="contiguous", null_frac=0.2
     return lc
 
 
-def as_column(lc, name, child_type):
+def as_column(lc, name, child_type, dec_width=0, dec_scale=0):
     """the LIST column as a chunks.Column for the host API (dmb_host_column + dmb_host_list)"""
     col = ch.Column(name, ch.T_LIST, ch.P_U128, lc.entries, lc.data_off, lc.validity, lc.val_off)
     col.list_child_type = child_type
+    col.list_child_dec_width, col.list_child_dec_scale = dec_width, dec_scale
     col.list_child_data = lc.child_data
     col.list_child_base = lc.child_base
     col.list_child_sizes = lc.child_sizes

@@ -125,13 +125,42 @@ def test_list_column_through_the_host_api(layout, n, child_type, pattern):
     del arr, rb
 
 
-def test_list_column_of_an_unsupported_child_is_an_error():
+def test_list_children_that_need_a_conversion():
+    """BOOLEAN children (Arrow bit-packed) and DECIMAL children (decimal128): the gathered dense child takes a second pass
+    through the fixed-width conversion kernel"""
+    import decimal
+    pa = pytest.importorskip("pyarrow")
     from duckdb_mbt_b200 import arrow_result as ar
-    lc = list_cases.make_list_column(100, 1, "full", 3, "contiguous")
-    batch = ch.ChunkBatch(lc.counts, [list_cases.as_column(lc, "l", ch.T_BOOLEAN)])   # bool children are bit-packed in Arrow: a conversion
-    with ar.GpuContext(0) as ctx, ar.ArrowResult.from_chunks(ctx, batch) as res:
-        with pytest.raises(Exception, match="LIST child"):
-            res.to_arrow(0)
+    with ar.GpuContext(0) as ctx:
+        lc = list_cases.make_list_column(20_000, 4, "ragged", 41, "shuffled")
+        batch = ch.ChunkBatch(lc.counts, [list_cases.as_column(lc, "l", ch.T_DECIMAL, 9, 2)])
+        with ar.ArrowResult.from_chunks(ctx, batch) as res:
+            arr = res.to_arrow(0)
+            assert arr.type == pa.list_(pa.field("item", pa.decimal128(9, 2)))
+            # validate(full=True) would reject random 32-bit payloads beyond 9 digits: the values are checked directly
+            arr.validate()
+            exp = [None if row is None else [None if v is None else decimal.Decimal(int.from_bytes(v, "little", signed=True)).scaleb(-2) for v in row] for row in lc.expected]
+            assert arr.to_pylist() == exp
+        lc = list_cases.make_list_column(30_001, 1, "ragged", 42, "contiguous")
+        lc.child_data &= 1  # DuckDB bool vectors hold 0 / 1
+        lc.expected = [None if row is None else [None if v is None else bool(v[0] & 1) for v in row] for row in lc.expected]
+        batch = ch.ChunkBatch(lc.counts, [list_cases.as_column(lc, "l", ch.T_BOOLEAN)])
+        with ar.ArrowResult.from_chunks(ctx, batch) as res:
+            arr = res.to_arrow(0)
+            arr.validate(full=True)
+            assert arr.type == pa.list_(pa.field("item", pa.bool_()))
+            assert arr.to_pylist() == lc.expected
+
+
+def test_list_of_varchar_is_not_exported_yet():
+    from duckdb_mbt_b200 import arrow_result as ar
+    from duckdb_mbt_b200 import native as nat
+    lc = list_cases.make_list_column(100, 16, "full", 3, "contiguous")
+    col = list_cases.as_column(lc, "l", ch.T_VARCHAR)
+    with ar.GpuContext(0) as ctx:
+        with pytest.raises(Exception, match="fixed-width"):
+            ar.ArrowResult.from_chunks(ctx, ch.ChunkBatch(lc.counts, [col]))
+        assert "LIST child" in nat.last_error()
 
 
 def test_list_and_enum_edge_cases_through_the_host_api():
