@@ -782,7 +782,6 @@ struct Pending {  // one column between its kernel launch and its device->host c
   FixedRun fr;
   StringRun sr;
   ListRun lr;
-  int32_t list_child_width = 0;
   std::shared_ptr<ArrowColOut> out;
   unsigned long long *h_null = nullptr;
 };
@@ -798,7 +797,6 @@ int32_t launch_arrow_col(Result *r, Scope &sc, int j, int string_mode, Pending *
   if (p->map.is_list) {
     p->lr = ListRun();
     if (run_list(r, sc, j, p->map.child_op, p->map.child_as_stored, &p->lr)) return -1;
-    p->list_child_width = col.child_width;
     p->out->format = p->map.format;
     return 0;
   }

@@ -15,12 +15,15 @@
 // Three launches, all HBM-bound streams over the entries / the child elements:
 //   list_sum_kernel    one CTA per chunk (grid-stride): sum of the valid rows' lengths -> chunk_sum[k]
 //   list_scan_kernel   one CTA: exclusive scan of chunk_sum -> chunk_base[k], total
-//   list_emit_kernel   one CTA per chunk: block scan of the lengths -> offsets; then output-centric gather of
-//                      the chunk's child elements (row of an output element by binary search over the
-//                      chunk's 2048 row starts in shared memory; a chunk whose entries are contiguous and in row
-//                      order -- the common case -- skips the search), child validity by warp ballot over
-//                      32-aligned groups of OUTPUT elements (whole words stored, the ragged first / last word of
-//                      a chunk merged with atomicOr into the pre-zeroed bitmap).
+//   list_emit_kernel   one CTA per chunk: entries striped into shared memory, block scan of the lengths -> offsets; then the
+//                      chunk's child elements.  A chunk whose entries are one run in row order (what a scan produces;
+//                      detected from entry.offset - start being the same for every non-empty row) is copied as aligned
+//                      16-byte output vectors (source misaligned by whole elements: two aligned loads + funnel shift),
+//                      NULL elements zeroed from the mask bits, the child bitmap as a shifted word copy.  Any other chunk
+//                      is gathered output-centric, one element per lane: row of an output element by binary search over
+//                      the chunk's 2048 row starts in shared memory, child validity by warp ballot over 32-aligned groups
+//                      of OUTPUT elements.  Whole bitmap words are stored; the ragged first / last word of a chunk is
+//                      merged with atomicOr into the pre-zeroed bitmap.
 
 #include "dmb_common.cuh"
 
