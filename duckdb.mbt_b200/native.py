@@ -115,7 +115,7 @@ EXPORTED_SYMBOLS = [
     "dmb_dev_fixed_batch", "dmb_op_out_width", "dmb_phys_width", "dmb_dev_string_scratch_bytes",
     "dmb_dev_string_error", "dmb_dev_string_batch", "dmb_dev_rev_fixed_batch", "dmb_dev_rev_string_batch",
     "dmb_dev_valid_bytes_to_masks", "dmb_dev_make_string_t", "dmb_render_supported", "dmb_render_slot_bytes", "dmb_dev_render_text", "dmb_dev_enum_to_string_t", "dmb_dev_list_scratch_bytes", "dmb_dev_list_batch",
-    "duckdb_mb_gpu_last_error", "duckdb_mb_gpu_device_count", "duckdb_mb_gpu_ctx_create",
+    "duckdb_mb_gpu_last_error", "duckdb_mb_gpu_device_count", "duckdb_mb_gpu_bind_numa", "duckdb_mb_gpu_ctx_create",
     "duckdb_mb_gpu_ctx_destroy", "duckdb_mb_gpu_ctx_sync", "duckdb_mb_gpu_host_alloc", "duckdb_mb_gpu_host_free",
     "duckdb_mb_gpu_result_from_chunks", "duckdb_mb_gpu_result_materialise_arrow",
     "duckdb_mb_gpu_result_export_arrow", "duckdb_mb_gpu_result_typed_column", "duckdb_mb_gpu_result_text_column", "duckdb_mb_gpu_result_timings",

@@ -358,6 +358,11 @@ duckdb_mb_gpu_ctx *duckdb_mb_gpu_ctx_create(int32_t device);
 void duckdb_mb_gpu_ctx_destroy(duckdb_mb_gpu_ctx *ctx);
 int32_t duckdb_mb_gpu_ctx_sync(duckdb_mb_gpu_ctx *ctx);
 
+/* Bind the calling thread (and the threads / page-locked allocations it makes afterwards) to the CPUs of the GPU's NUMA
+ * node: call once per process before creating the context and allocating host buffers when one process drives one GPU
+ * (SURVEY.md 8e).  Returns the node, or -1 when there is nothing to bind to; never fails. */
+int32_t duckdb_mb_gpu_bind_numa(int32_t device);
+
 /* pinned host memory for callers that can place chunk vectors / Arrow buffers in it
  * (staging then needs no bounce copy) */
 void *duckdb_mb_gpu_host_alloc(size_t bytes);
