@@ -12,7 +12,8 @@
 // List/Struct/Map as "not yet supported" for Arrow: there is no reference output to match; the contract is
 // the Arrow format (validated with pyarrow) and the oracle's restatement of the loops above.
 //
-// Three launches, all HBM-bound streams over the entries / the child elements:
+// One launch (list_emit_kernel, ONEPASS: the chunk base by a decoupled look-back over per-chunk status words); the three-launch
+// form below (sum, scan, emit with precomputed bases) stays behind DMB_LIST_THREE_PASS for A/B measurements:
 //   list_sum_kernel    one CTA per chunk (grid-stride): sum of the valid rows' lengths -> chunk_sum[k]
 //   list_scan_kernel   one CTA: exclusive scan of chunk_sum -> chunk_base[k], total
 //   list_emit_kernel   one CTA per chunk: entries striped into shared memory, block scan of the lengths -> offsets; then the
@@ -24,6 +25,8 @@
 //                      the chunk's 2048 row starts in shared memory, child validity by warp ballot over 32-aligned groups
 //                      of OUTPUT elements.  Whole bitmap words are stored; the ragged first / last word of a chunk is
 //                      merged with atomicOr into the pre-zeroed bitmap.
+
+#include <stdlib.h>
 
 #include "dmb_common.cuh"
 
@@ -138,10 +141,49 @@ __device__ __forceinline__ typename RawVec<W>::type load_elem(const uint8_t *src
   return v;
 }
 
-template <int W, bool LARGE>
+// ---- one-pass variant: the chunk bases come from a decoupled look-back over per-chunk status words instead of the
+// sum + scan launches (the entries are then read once).  status[c]: bits 63..62 = 1 (aggregate) / 2 (inclusive prefix),
+// low 62 bits the value.  The grid is persistent and no larger than what is resident at once, CTA b takes chunks b,
+// b + grid, ...: every predecessor a look-back waits for belongs to a resident CTA that waits only on earlier chunks.
+constexpr unsigned long long kStatusMask = (1ull << 62) - 1ull;
+__device__ __forceinline__ unsigned long long list_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+// exclusive prefix of chunk c, executed by one warp (lane 0 looks at c-1, lane 1 at c-2, ...)
+__device__ __forceinline__ uint64_t list_lookback(const unsigned long long *status, int64_t c, int lane, unsigned long long *flags) {
+  uint64_t prefix = 0;
+  int64_t pos = c - 1;
+  const unsigned long long t0 = list_now_ns();
+  while (pos >= 0) {
+    const int64_t idx = pos - lane;
+    const unsigned long long w = idx >= 0 ? *reinterpret_cast<const volatile unsigned long long *>(status + idx) : (2ull << 62);  // before chunk 0: prefix 0
+    const uint32_t flag = (uint32_t)(w >> 62);
+    const uint32_t is_prefix = __ballot_sync(0xffffffffu, flag == 2u), is_empty = __ballot_sync(0xffffffffu, flag == 0u);
+    const int first_empty = is_empty ? __ffs((int)is_empty) - 1 : 32;
+    const int first_prefix = is_prefix ? __ffs((int)is_prefix) - 1 : 32;
+    const bool done = first_prefix < first_empty;
+    const int upto = done ? first_prefix + 1 : first_empty;  // lanes [0, upto) hold published words
+    uint64_t v = lane < upto ? (w & kStatusMask) : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    prefix += v;
+    if (done) break;
+    pos -= upto;
+    if (upto == 0) {
+      if (list_now_ns() - t0 > 2000000000ull) {  // never hang the GPU: report and leave
+        if (lane == 0) atomicOr(flags, 4ull);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  return prefix;
+}
+
+template <int W, bool LARGE, bool ONEPASS>
 __global__ void __launch_bounds__(kThreads)
-list_emit_kernel(dmb_list_job job, BatchView b, const unsigned long long *__restrict__ chunk_sum,
+list_emit_kernel(dmb_list_job job, BatchView b, unsigned long long *chunk_sum /* ONEPASS: the status words */,
                  const unsigned long long *__restrict__ chunk_base, unsigned long long *flags) {
+  __shared__ unsigned long long s_cbase;
   __shared__ uint64_t s_warp[kThreads / 32 + 1];
   __shared__ uint32_t s_start[kVec + 1];  // row -> first output element of the row, relative to the chunk
   __shared__ uint64_t s_src[kVec];        // row -> entry.offset
@@ -154,9 +196,13 @@ list_emit_kernel(dmb_list_job job, BatchView b, const unsigned long long *__rest
     const dmb_vec_desc vd = job.vecs[c];
     const ListEntry *ent = reinterpret_cast<const ListEntry *>(reinterpret_cast<const uint8_t *>(job.in_entries) + vd.data_off);
     const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
-    const uint64_t cbase = chunk_base[c], csum = chunk_sum[c];
+    uint64_t cbase = 0, csum = 0;
+    if (!ONEPASS) {
+      cbase = chunk_base[c];
+      csum = chunk_sum[c];
+    }
     if (threadIdx.x == 0) s_nulls = 0u;
-    if (csum > 0xffffffffull) {  // one chunk with more than 4 G child elements (uniform branch)
+    if (!ONEPASS && csum > 0xffffffffull) {  // one chunk with more than 4 G child elements (uniform branch)
       if (threadIdx.x == 0) atomicOr(flags, 2ull);
       continue;
     }
@@ -166,6 +212,7 @@ list_emit_kernel(dmb_list_job job, BatchView b, const unsigned long long *__rest
       // (the entry of a NULL row is read and dropped: it is storage of the vector, only its content is unspecified)
       ulonglong2 e[kListRpt];
       uint64_t mw[kListRpt];
+      bool big = false;
 #pragma unroll
       for (int k = 0; k < kListRpt; ++k) {
         const int i = threadIdx.x + k * kThreads;
@@ -178,7 +225,9 @@ list_emit_kernel(dmb_list_job job, BatchView b, const unsigned long long *__rest
         const bool valid = i < count && ((mw[k] >> (i & 63)) & 1ull);
         s_src[i] = valid ? e[k].x : 0ull;
         s_start[i] = valid ? (uint32_t)e[k].y : 0u;  // csum <= 4 G: every length fits
+        big |= valid && (e[k].y >> 32) != 0ull;
       }
+      if (ONEPASS && big) atomicOr(flags, 2ull);  // a list of more than 4 G elements: reported, the output is not usable
     }
     __syncthreads();
     // ---- this thread's kListRpt consecutive rows: block scan of the lengths, starts written back in place
@@ -192,7 +241,21 @@ list_emit_kernel(dmb_list_job job, BatchView b, const unsigned long long *__rest
     }
     uint64_t total;
     uint64_t ex = block_exscan(mine, &total, s_warp);
-    (void)total;
+    if (ONEPASS) {
+      csum = total;
+      if (threadIdx.x < 32) {  // warp 0: publish the aggregate, resolve the base, publish the inclusive prefix
+        if (lane == 0 && c > 0) atomicExch(chunk_sum + c, (1ull << 62) | (csum & kStatusMask));
+        const uint64_t base = c > 0 ? list_lookback(chunk_sum, c, lane, flags) : 0ull;
+        if (lane == 0) {
+          atomicExch(chunk_sum + c, (2ull << 62) | ((base + csum) & kStatusMask));
+          s_cbase = base;
+          if (c == b.nchunks - 1) {
+            if (job.total) *job.total = base + csum;
+            if (!LARGE && base + csum > 0x7fffffffull) atomicOr(flags, 1ull);  // int32 offsets overflow: use large_list
+          }
+        }
+      }
+    }
     // contiguity: the chunk's entries are one run in row order iff entry.offset - start is the same for every non-empty row
     unsigned long long dmin = ~0ull, dmax = 0ull;
 #pragma unroll
@@ -213,15 +276,14 @@ list_emit_kernel(dmb_list_job job, BatchView b, const unsigned long long *__rest
       dmax = omax > dmax ? omax : dmax;
     }
     if (lane == 0) { s_wmin[threadIdx.x >> 5] = dmin; s_wmax[threadIdx.x >> 5] = dmax; }
-    if (threadIdx.x == 0) {
-      s_start[count] = (uint32_t)csum;
-      if (row0 + count == b.nrows) {  // the last chunk writes offsets[nrows]
-        const uint64_t o = cbase + csum;
-        if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[b.nrows] = (long long)o;
-        else reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)o;
-      }
-    }
+    if (threadIdx.x == 0) s_start[count] = (uint32_t)csum;
     __syncthreads();
+    if (ONEPASS) cbase = s_cbase;
+    if (threadIdx.x == 0 && row0 + count == b.nrows) {  // the last chunk writes offsets[nrows]
+      const uint64_t o = cbase + csum;
+      if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[b.nrows] = (long long)o;
+      else reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)o;
+    }
     for (int i = threadIdx.x; i < count; i += kThreads) {  // offsets: coalesced
       const uint64_t o = cbase + s_start[i];
       if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[row0 + i] = (long long)o;
@@ -408,12 +470,32 @@ extern "C" int32_t dmb_dev_list_batch(const dmb_list_job *job, const uint32_t *c
   const int64_t max_grid = (int64_t)kNumSMs * 8;
   const int grid = (int)(nchunks < max_grid ? nchunks : max_grid);
   BatchView b{counts, row_off, nchunks, nrows};
-  list_sum_kernel<<<grid, kThreads, 0, st>>>(*job, counts, nchunks, chunk_sum);
-  list_scan_kernel<<<1, kScanThreads, 0, st>>>(chunk_sum, chunk_base, nchunks, job->total, flags, job->large);
+  static const bool three_pass = getenv("DMB_LIST_THREE_PASS") != nullptr;  // A/B knob: the sum + scan + emit launches
+  if (three_pass) {
+    list_sum_kernel<<<grid, kThreads, 0, st>>>(*job, counts, nchunks, chunk_sum);
+    list_scan_kernel<<<1, kScanThreads, 0, st>>>(chunk_sum, chunk_base, nchunks, job->total, flags, job->large);
+  } else if (check_cuda(cudaMemsetAsync(chunk_sum, 0, (size_t)nchunks * 8, st), "list status memset")) {
+    return -1;
+  }
+  auto launch = [&](auto kernel3, auto kernel1) -> int32_t {
+    if (three_pass) {
+      kernel3<<<grid, kThreads, 0, st>>>(*job, b, chunk_sum, chunk_base, flags);
+      return 0;
+    }
+    // persistent grid, no larger than what is resident at once (the look-back relies on it)
+    int per_sm = 0, dev = 0, sms = kNumSMs;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel1, kThreads, 0), "list_emit_kernel occupancy")) return -1;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (per_sm < 1) { set_error("list_emit_kernel does not fit an SM"); return -1; }
+    const int64_t resident = (int64_t)per_sm * sms;
+    const int g1 = (int)(nchunks < resident ? nchunks : resident);
+    kernel1<<<g1, kThreads, 0, st>>>(*job, b, chunk_sum, chunk_base, flags);
+    return 0;
+  };
 #define DMB_LIST_LAUNCH(W)                                                                                          \
   do {                                                                                                              \
-    if (job->large) list_emit_kernel<W, true><<<grid, kThreads, 0, st>>>(*job, b, chunk_sum, chunk_base, flags);     \
-    else list_emit_kernel<W, false><<<grid, kThreads, 0, st>>>(*job, b, chunk_sum, chunk_base, flags);               \
+    if (job->large) { if (launch(list_emit_kernel<W, true, false>, list_emit_kernel<W, true, true>)) return -1; }   \
+    else { if (launch(list_emit_kernel<W, false, false>, list_emit_kernel<W, false, true>)) return -1; }            \
   } while (0)
   switch (w) {
     case 1: DMB_LIST_LAUNCH(1); break;
