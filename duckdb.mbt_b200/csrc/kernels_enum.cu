@@ -11,9 +11,36 @@
 
 namespace dmb {
 
+// the string_t of dictionary entry idx (<= 12 bytes inlined, else prefix + pointer relative to dict_host_base)
+__device__ __forceinline__ uint4 enum_entry(const dmb_enum_job &job, uint32_t idx) {
+  const uint32_t o0 = __ldg(job.dict_offsets + idx), o1 = __ldg(job.dict_offsets + idx + 1);
+  const uint32_t len = o1 - o0;
+  const uint8_t *q = job.dict_data + o0;
+  uint4 e = make_uint4(len, 0, 0, 0);
+  if (len <= 12u) {
+    uint32_t w[3] = {0u, 0u, 0u};
+    for (uint32_t k = 0; k < len; ++k) w[k >> 2] |= (uint32_t)__ldg(q + k) << (8u * (k & 3u));
+    e.y = w[0]; e.z = w[1]; e.w = w[2];
+  } else {
+    e.y = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16) | ((uint32_t)__ldg(q + 3) << 24);
+    const uint64_t p = job.dict_host_base + o0;
+    e.z = (uint32_t)p;
+    e.w = (uint32_t)(p >> 32);
+  }
+  return e;
+}
+
+constexpr uint32_t kEnumTable = 1024;  // dictionaries up to this size are turned into a string_t table in shared memory once per CTA
+
 template <typename I>
 __global__ void __launch_bounds__(kThreads)
 enum_to_string_t_kernel(dmb_enum_job job, const uint32_t *__restrict__ counts, int64_t nchunks) {
+  __shared__ uint4 s_tab[kEnumTable];
+  const bool table = job.dict_size <= kEnumTable;  // (every uint8 ENUM, most uint16 ones)
+  if (table) {
+    for (uint32_t t = threadIdx.x; t < job.dict_size; t += kThreads) s_tab[t] = enum_entry(job, t);
+    __syncthreads();
+  }
   unsigned long long bad = 0;
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const int count = (int)__ldg(counts + c);
@@ -21,29 +48,23 @@ enum_to_string_t_kernel(dmb_enum_job job, const uint32_t *__restrict__ counts, i
     const I *in = reinterpret_cast<const I *>(reinterpret_cast<const uint8_t *>(job.in_data) + vd.data_off);
     const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
     uint4 *out = reinterpret_cast<uint4 *>(job.out) + c * (int64_t)kVec;
-    for (int i = threadIdx.x; i < count; i += kThreads) {
+    constexpr int kRows = kVec / kThreads;  // 8 rows per thread, all loads issued before the first use
+    uint32_t idx[kRows];
+    uint64_t mw[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const int i = threadIdx.x + k * kThreads;
+      idx[k] = i < count ? (uint32_t)in[i] : 0u;   // the index of a NULL row is read and dropped (storage of the vector)
+      mw[k] = (mask && i < count) ? __ldg(mask + (i >> 6)) : ~0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const int i = threadIdx.x + k * kThreads;
+      if (i >= count) continue;
       uint4 e = make_uint4(0, 0, 0, 0);
-      const bool valid = mask ? ((__ldg(mask + (i >> 6)) >> (i & 63)) & 1ull) : true;
-      if (valid) {
-        const uint32_t idx = (uint32_t)in[i];
-        if (idx < job.dict_size) {
-          const uint32_t o0 = __ldg(job.dict_offsets + idx), o1 = __ldg(job.dict_offsets + idx + 1);
-          const uint32_t len = o1 - o0;
-          const uint8_t *q = job.dict_data + o0;
-          e.x = len;
-          if (len <= 12u) {
-            uint32_t w[3] = {0u, 0u, 0u};
-            for (uint32_t k = 0; k < len; ++k) w[k >> 2] |= (uint32_t)__ldg(q + k) << (8u * (k & 3u));
-            e.y = w[0]; e.z = w[1]; e.w = w[2];
-          } else {
-            e.y = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16) | ((uint32_t)__ldg(q + 3) << 24);
-            const uint64_t p = job.dict_host_base + o0;
-            e.z = (uint32_t)p;
-            e.w = (uint32_t)(p >> 32);
-          }
-        } else {
-          ++bad;  // an index past the dictionary: reported, rendered as the empty string
-        }
+      if ((mw[k] >> (i & 63)) & 1ull) {
+        if (idx[k] < job.dict_size) e = table ? s_tab[idx[k]] : enum_entry(job, idx[k]);
+        else ++bad;  // an index past the dictionary: reported, rendered as the empty string
       }
       st_stream(out + i, e);
     }
