@@ -385,6 +385,8 @@ struct StringSource {
   uint64_t heap_host_base = 0, heap_len = 0;
   const unsigned long long *d_bad = nullptr;  // ENUM: device count of indices past the dictionary
   size_t max_row_bytes = 0;                   // ENUM: longest label
+  bool fused_enum = false;                    // ENUM with a small dictionary of short labels: indices -> utf8 in one launch (dmb_dev_enum_utf8)
+  dmb_enum_job ejob{};
 };
 
 // a column whose VARCHAR form the device produces: strings, the rendered scalar types, ENUM with its dictionary
@@ -394,7 +396,7 @@ bool text_supported(const Col &col) {
   return dmb_render_supported(col.type_id, col.phys) != 0;
 }
 
-int32_t string_source(Result *r, Scope &sc, int j, StringSource *src) {
+int32_t string_source(Result *r, Scope &sc, int j, bool arrow_mode, StringSource *src) {
   if (stage_column(r, j)) return -1;
   CtxCore &c = *r->core;
   Col &col = r->cols[(size_t)j];
@@ -420,17 +422,19 @@ int32_t string_source(Result *r, Scope &sc, int j, StringSource *src) {
       if (!d.data.empty() && check_cuda(cudaMemcpy(d.d_data, d.data.data(), d.data.size(), cudaMemcpyHostToDevice), "enum dictionary data H2D")) return -1;
       r->bytes_h2d += d.offsets.size() * sizeof(uint32_t) + d.data.size();
     }
-    dmb_string_t *d_str = (dmb_string_t *)sc.dalloc(nslots * sizeof(dmb_string_t));
+    static const bool no_fused = getenv("DMB_ENUM_TWO_STEP") != nullptr;  // A/B: keep the string_t intermediate
+    const bool fused = arrow_mode && !no_fused && d.size() <= DMB_ENUM_FUSED_MAX_LABELS && d.max_len <= 12;
+    dmb_string_t *d_str = fused ? nullptr : (dmb_string_t *)sc.dalloc(nslots * sizeof(dmb_string_t));
     unsigned long long *d_bad = (unsigned long long *)sc.dalloc(8);
     std::vector<dmb_vec_desc> vecs((size_t)(nch > 0 ? nch : 1));
     for (int64_t k = 0; k < nch; ++k) {
       vecs[(size_t)k].data_off = (uint64_t)k * DMB_VECTOR_SIZE * sizeof(dmb_string_t);
       vecs[(size_t)k].val_off = (col.any_validity && col.validity[(size_t)k]) ? k * DMB_VALIDITY_WORDS : -1;
     }
-    if (!d_str || !d_bad) return -1;
+    if ((!fused && !d_str) || !d_bad) return -1;
     if (check_cuda(cudaStreamWaitEvent(c.s_compute, col.ev_staged, 0), "wait staged")) return -1;
-    dmb_vec_desc *d_vecs2 = (dmb_vec_desc *)upload_job(sc, vecs.data(), sizeof(dmb_vec_desc) * vecs.size());
-    if (!d_vecs2) return -1;
+    dmb_vec_desc *d_vecs2 = fused ? nullptr : (dmb_vec_desc *)upload_job(sc, vecs.data(), sizeof(dmb_vec_desc) * vecs.size());
+    if (!fused && !d_vecs2) return -1;
     if (check_cuda(cudaMemsetAsync(d_bad, 0, 8, c.s_compute), "enum counter memset")) return -1;
     dmb_enum_job job;
     memset(&job, 0, sizeof(job));
@@ -444,7 +448,9 @@ int32_t string_source(Result *r, Scope &sc, int j, StringSource *src) {
     job.bad_index = d_bad;
     job.dict_size = d.size();
     job.phys = col.phys;
-    if (dmb_dev_enum_to_string_t(&job, r->d_counts, nch, c.s_compute)) return -1;
+    src->fused_enum = fused;
+    src->ejob = job;
+    if (!fused && dmb_dev_enum_to_string_t(&job, r->d_counts, nch, c.s_compute)) return -1;
     src->in = d_str;
     src->vecs = d_vecs2;
     src->heap = d.d_data;
@@ -494,7 +500,7 @@ int32_t string_source(Result *r, Scope &sc, int j, StringSource *src) {
 
 int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool want_valid_bytes, StringRun *out) {
   StringSource src;
-  if (string_source(r, sc, j, &src)) return -1;
+  if (string_source(r, sc, j, mode != DMB_STR_REF_BLOB, &src)) return -1;
   CtxCore &c = *r->core;
   Col &col = r->cols[(size_t)j];
   const int64_t n = r->nrows;
@@ -528,7 +534,8 @@ int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool
   cudaEvent_t k0 = sc.event(true), k1 = sc.event(true), done = sc.event(false);
   if (!k0 || !k1 || !done) return -1;
   cudaEventRecord(k0, c.s_compute);
-  if (dmb_dev_string_batch(&job, r->d_counts, r->d_row_off, r->nchunks, n, out->d_scratch, c.s_compute)) return -1;
+  if (src.fused_enum ? dmb_dev_enum_utf8(&src.ejob, &job, r->d_counts, r->d_row_off, r->nchunks, n, out->d_scratch, c.s_compute)
+                     : dmb_dev_string_batch(&job, r->d_counts, r->d_row_off, r->nchunks, n, out->d_scratch, c.s_compute)) return -1;
   cudaEventRecord(k1, c.s_compute);
   sc.kernel_spans.emplace_back(k0, k1);
   // the data length is needed on the host to size the device->host copy; flags travel with it

@@ -11,25 +11,6 @@
 
 namespace dmb {
 
-// the string_t of dictionary entry idx (<= 12 bytes inlined, else prefix + pointer relative to dict_host_base)
-__device__ __forceinline__ uint4 enum_entry(const dmb_enum_job &job, uint32_t idx) {
-  const uint32_t o0 = __ldg(job.dict_offsets + idx), o1 = __ldg(job.dict_offsets + idx + 1);
-  const uint32_t len = o1 - o0;
-  const uint8_t *q = job.dict_data + o0;
-  uint4 e = make_uint4(len, 0, 0, 0);
-  if (len <= 12u) {
-    uint32_t w[3] = {0u, 0u, 0u};
-    for (uint32_t k = 0; k < len; ++k) w[k >> 2] |= (uint32_t)__ldg(q + k) << (8u * (k & 3u));
-    e.y = w[0]; e.z = w[1]; e.w = w[2];
-  } else {
-    e.y = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16) | ((uint32_t)__ldg(q + 3) << 24);
-    const uint64_t p = job.dict_host_base + o0;
-    e.z = (uint32_t)p;
-    e.w = (uint32_t)(p >> 32);
-  }
-  return e;
-}
-
 constexpr uint32_t kEnumTable = 1024;  // dictionaries up to this size are turned into a string_t table in shared memory once per CTA
 
 template <typename I>

@@ -1325,9 +1325,16 @@ string_inline_kernel(dmb_string_job job, BatchView b, unsigned long long *scratc
 #ifndef DMB_SHORT_CTAS8
 #define DMB_SHORT_CTAS8 4
 #endif
-template <bool LARGE, int RPT>
+// EW = 0: rows are string_t.  EW = 1 / 2 / 4 (dmb_dev_enum_utf8): rows are ENUM indices of that many bytes and a row's string_t is
+// looked up in a table of the dictionary's labels built in shared memory (<= DMB_ENUM_FUSED_MAX_LABELS labels of <= 12 bytes), so the
+// 16-byte-per-row string_t intermediate of enum_to_string_t_kernel is never written or read.
+template <int EW> struct EnumIndex { typedef uint8_t type; };
+template <> struct EnumIndex<2> { typedef uint16_t type; };
+template <> struct EnumIndex<4> { typedef uint32_t type; };
+
+template <bool LARGE, int RPT, int EW>
 __global__ void __launch_bounds__(kThreads, RPT >= 8 ? DMB_SHORT_CTAS8 : 5)
-string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles) {
+string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles, dmb_enum_job ej) {
   constexpr int kRows = kThreads * RPT;
   constexpr int kTilesPerChunk = kVec / kRows;
   constexpr int kWarps = kThreads / 32;
@@ -1341,20 +1348,30 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   const int64_t c = tile / kTilesPerChunk;
   const int r_begin = (int)(tile % kTilesPerChunk) * kRows;
   const int count = (int)__ldg(b.counts + c) - r_begin;  // rows of this tile that exist (may be <= 0)
-  const dmb_vec_desc vd = job.vecs[c];
-  const uint4 *in = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(job.in) + vd.data_off) + r_begin;
-  const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off + (r_begin >> 6);
+  const dmb_vec_desc vd = EW ? ej.vecs[c] : job.vecs[c];
+  const uint4 *in = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(job.in) + (EW ? 0 : vd.data_off)) + r_begin;
+  const uint64_t *mask = vd.val_off < 0 ? nullptr : (EW ? ej.in_validity : job.in_validity) + vd.val_off + (r_begin >> 6);
+  typedef typename EnumIndex<EW>::type I;
+  const I *in_idx = reinterpret_cast<const I *>(reinterpret_cast<const uint8_t *>(ej.in_data) + (EW ? vd.data_off : 0)) + r_begin;
+  __shared__ uint4 s_tab[EW ? DMB_ENUM_FUSED_MAX_LABELS : 1];
 
   // stripe k of warp w holds tile rows w*32*RPT + k*32 + lane
   const int row0 = warp * (32 * RPT) + lane;
   uint4 e[RPT];
+  uint32_t idx[EW ? RPT : 1];
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     const int row = row0 + 32 * k;
     e[k] = make_uint4(0, 0, 0, 0);
-    if (row < count) e[k] = ld_stream(in + row);
+    if (EW) idx[k] = row < count ? (uint32_t)in_idx[row] : 0u;  // (the index under a NULL row is read and dropped)
+    else if (row < count) e[k] = ld_stream(in + row);
+  }
+  if (EW) {  // the labels as string_t, once per CTA (the index loads above are in flight meanwhile)
+    for (uint32_t t = tid; t < ej.dict_size; t += kThreads) s_tab[t] = enum_entry(ej, t);
+    __syncthreads();
   }
   int bad = 0;
+  unsigned long long bad_idx = 0;
   uint32_t lmax = 0;
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
@@ -1362,8 +1379,12 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     uint32_t l = 0;
     if (row < count) {
       const bool valid = mask ? ((__ldg(mask + (row >> 6)) >> (row & 63)) & 1ull) : true;
+      if (EW && valid) {
+        if (idx[k] < ej.dict_size) e[k] = s_tab[idx[k]];
+        else ++bad_idx;  // an index past the dictionary: reported, rendered as the empty string
+      }
       l = valid ? e[k].x : 0u;
-      if (l > 12u) { bad = 1; l = 0; }  // a pointer string, but the batch registered no heap
+      if (l > 12u) { bad = 1; l = 0; }  // a pointer string, but the batch registered no heap (ENUM: a label too long for this kernel)
     }
     e[k].x = l;  // from here on: the bytes the row contributes
     lmax = lmax > l ? lmax : l;
@@ -1388,6 +1409,7 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     carry += tot >> 16;
   }
   if (lane == 0) warp_sum[warp] = carry;
+  if (EW && bad_idx && ej.bad_index) atomicAdd(ej.bad_index, bad_idx);
   lmax = __reduce_max_sync(0xffffffffu, lmax);
   const int any_bad = __syncthreads_or(bad);
   uint32_t warp_excl = 0, tile_total = 0;
@@ -1527,6 +1549,33 @@ extern "C" size_t dmb_dev_string_scratch_bytes(int64_t nchunks) {
   return (size_t)(2 + kStrTilesPerChunk * (nchunks > 0 ? nchunks : 0)) * sizeof(unsigned long long);
 }
 
+extern "C" int32_t dmb_dev_enum_utf8(const dmb_enum_job *ejob, const dmb_string_job *job, const uint32_t *counts,
+                                     const int64_t *row_off, int64_t nchunks, int64_t nrows,
+                                     void *scratch, void *stream) {
+  if (!ejob || !job) { set_error("dmb_dev_enum_utf8: job is null"); return -1; }
+  if (job->mode != DMB_STR_ARROW_UTF8 && job->mode != DMB_STR_ARROW_LARGE) { set_error("dmb_dev_enum_utf8: Arrow modes only (mode %d)", job->mode); return -1; }
+  if (ejob->dict_size > DMB_ENUM_FUSED_MAX_LABELS) {
+    set_error("dmb_dev_enum_utf8: %u labels, the fused kernel takes up to %d (use dmb_dev_enum_to_string_t + dmb_dev_string_batch)", ejob->dict_size, DMB_ENUM_FUSED_MAX_LABELS);
+    return -1;
+  }
+  if (ejob->dict_size && (!ejob->dict_offsets || !ejob->dict_data)) { set_error("dmb_dev_enum_utf8: dictionary is null"); return -1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nchunks <= 0 || nrows <= 0) return 0;
+  if (check_cuda(cudaMemsetAsync(scratch, 0, dmb_dev_string_scratch_bytes(nchunks), st), "string scratch memset")) return -1;
+  BatchView b{counts, row_off, nchunks, nrows};
+  const bool large = job->mode == DMB_STR_ARROW_LARGE;
+  auto launch = [&](auto kernel) -> int32_t {
+    kernel<<<(unsigned)nchunks, kThreads, 0, st>>>(*job, b, (unsigned long long *)scratch, nchunks, *ejob);
+    return check_cuda(cudaGetLastError(), "string_short_kernel (ENUM) launch");
+  };
+  switch (ejob->phys) {
+    case DMB_PHYS_U8: return large ? launch(string_short_kernel<true, 8, 1>) : launch(string_short_kernel<false, 8, 1>);
+    case DMB_PHYS_U16: return large ? launch(string_short_kernel<true, 8, 2>) : launch(string_short_kernel<false, 8, 2>);
+    case DMB_PHYS_U32: return large ? launch(string_short_kernel<true, 8, 4>) : launch(string_short_kernel<false, 8, 4>);
+    default: set_error("dmb_dev_enum_utf8: ENUM indices are uint8/uint16/uint32, not physical type %d", ejob->phys); return -1;
+  }
+}
+
 extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_t *counts,
                                         const int64_t *row_off, int64_t nchunks, int64_t nrows,
                                         void *scratch, void *stream) {
@@ -1567,11 +1616,11 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
     if (job->heap_len == 0 && short_rpt > 0) {  // inlined strings only: one CTA per tile, prefix by look-back
       auto launch_short = [&](auto kernel, int rows_per_tile) -> int32_t {
         const int64_t nt = (int64_t)(kVec / rows_per_tile) * nchunks;
-        kernel<<<(unsigned)nt, kThreads, 0, st>>>(*job, b, (unsigned long long *)scratch, nt);
+        kernel<<<(unsigned)nt, kThreads, 0, st>>>(*job, b, (unsigned long long *)scratch, nt, dmb_enum_job{});
         return check_cuda(cudaGetLastError(), "string_short_kernel launch");
       };
-      if (short_rpt == 4) return large ? launch_short(string_short_kernel<true, 4>, 1024) : launch_short(string_short_kernel<false, 4>, 1024);
-      return large ? launch_short(string_short_kernel<true, 8>, 2048) : launch_short(string_short_kernel<false, 8>, 2048);
+      if (short_rpt == 4) return large ? launch_short(string_short_kernel<true, 4, 0>, 1024) : launch_short(string_short_kernel<false, 4, 0>, 1024);
+      return large ? launch_short(string_short_kernel<true, 8, 0>, 2048) : launch_short(string_short_kernel<false, 8, 0>, 2048);
     }
     if (job->heap_len == 0) {  // (experiment: DMB_STR_SHORT_RPT=0) the pipeline below with 4 rows per thread
       if (force_nw != 16) {

@@ -258,6 +258,17 @@ typedef struct dmb_enum_job {
 
 int32_t dmb_dev_enum_to_string_t(const dmb_enum_job *job, const uint32_t *counts, int64_t nchunks, void *stream);
 
+/* K8 fused with K5 (Arrow modes): ENUM indices -> utf8 offsets + data in ONE launch, for dictionaries of up to
+ * DMB_ENUM_FUSED_MAX_LABELS labels of <= 12 bytes each (every uint8 ENUM with short labels: flags, modes, codes).  The
+ * labels become a string_t table in shared memory, so the string_t intermediate (16 B per row written and read back) of
+ * the two-step form does not exist.  `ejob->out` and `sjob->in / vecs / in_validity / heap_*` are ignored: rows and validity come from
+ * `ejob`, outputs from `sjob`.  A label longer than 12 bytes raises the heap-range flag (dmb_dev_string_error); a valid row whose
+ * index is >= dict_size is counted in *bad_index and left empty.  `scratch` as for dmb_dev_string_batch.
+ * Replaces, like the two-step form, libduckdb's duckdb_value_varchar on an ENUM cell at src/duckdb_native.c:224-238, :2478, :2715. */
+#define DMB_ENUM_FUSED_MAX_LABELS 256
+int32_t dmb_dev_enum_utf8(const dmb_enum_job *ejob, const dmb_string_job *sjob, const uint32_t *counts,
+                          const int64_t *row_off, int64_t nchunks, int64_t nrows, void *scratch, void *stream);
+
 /* K9: LIST vectors -> Arrow list<child> (fixed-width child).  The reference rejects
  * LIST on its chunk path (src/duckdb_native.c:271-303): the contract is the Arrow format.  Per chunk: a vector of
  * duckdb_list_entry {uint64 offset, uint64 length} (+ validity) indexing that chunk's child vector

@@ -257,13 +257,23 @@ def cenum(scale, flush):
     def run():
         lookup()
         pack()
-    ms = timeit(run)
+    ms2 = timeit(run)
     ms_lookup, ms_pack = timeit(lookup), timeit(pack)
     assert int(bad.item()) == 0 and int(total.view(torch.int64)[0].item()) == total_len
+    two_step = (offsets[:4 * (n + 1)].clone(), data[:total_len].clone())
+    offsets.zero_()
+    data.zero_()
+
+    def fused():
+        total.zero_()
+        nat.check(L.dmb_dev_enum_utf8(C.byref(ejob), C.byref(sjob), counts.data_ptr(), row_off.data_ptr(), nch, n, scratch.data_ptr(), stream), "enum_utf8")
+    ms = timeit(fused)
+    assert int(bad.item()) == 0 and int(total.view(torch.int64)[0].item()) == total_len
+    assert torch.equal(offsets[:4 * (n + 1)], two_step[0]) and torch.equal(data[:total_len], two_step[1])  # bit-identical to the two-step form
     alg = n * 1 + 4 * (n + 1) + total_len  # indices in, offsets + label bytes out (no validity: all valid)
-    report("ENUM(7 labels) uint8 indices, no NULLs -> utf8 (lookup kernel + heap-less string kernel)", n, alg, ms,
-           {"enum_to_string_t_kernel_ms": ms_lookup, "string_short_kernel_ms": ms_pack,
-            "note": "the 16-byte string_t intermediate (32 B/row written + read) is not algorithmic: a fused lookup+pack kernel is the next step"})
+    report("ENUM(7 labels) uint8 indices, no NULLs -> utf8, one launch (dmb_dev_enum_utf8: string_short_kernel with the label table in shared memory)", n, alg, ms,
+           {"two_step_ms": ms2, "enum_to_string_t_kernel_ms": ms_lookup, "string_short_kernel_ms": ms_pack,
+            "note": "two_step = lookup kernel + heap-less string kernel through a 16-byte string_t per row (32 B/row of traffic that is not algorithmic)"})
 
 
 def main():

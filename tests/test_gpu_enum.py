@@ -148,3 +148,87 @@ def test_enum_cells_through_connection_query_symbols(ctx):
         t = c.to_typed()
         first = int(np.argmax(valid))
         assert t.get_string(first, 0) == labels[idx[first]].decode()
+
+
+def _expected_utf8(labels, idx, valid):
+    """numpy restatement of what the Arrow utf8 form of an ENUM column holds: a valid row contributes its label, a NULL row nothing."""
+    lens = np.array([len(x) for x in labels], dtype=np.int64)[idx]
+    if valid is not None:
+        lens = np.where(valid, lens, 0)
+    offsets = np.zeros(len(idx) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    data = b"".join(labels[i] for i, v in zip(idx, valid if valid is not None else np.ones(len(idx), bool)) if v)
+    return offsets, data
+
+
+@pytest.mark.parametrize("n,k,max_len,pattern,null_frac", [
+    (1, 1, 12, "full", 0.0), (2048, 2, 1, "full", 0.5), (2049, 256, 12, "ragged", 0.2),   # 256 labels: the largest fused dictionary
+    (300_001, 7, 8, "ragged", 0.1), (1_000_000, 7, 7, "full", 0.0), (50_000, 3, 12, "ragged", 1.0)])
+def test_enum_fused_lookup_and_pack_every_offset_and_byte(ctx, n, k, max_len, pattern, null_frac):
+    """uint8 ENUM with labels of <= 12 bytes: indices -> utf8 in ONE launch (dmb_dev_enum_utf8: string_short_kernel<.., EW>),
+    no string_t intermediate.  Every offset and every data byte against the numpy restatement and the oracle's cells."""
+    from duckdb_mbt_b200 import typed_result as tr
+    batch, labels, idx, valid = _enum_batch(n, k, max_len, pattern, 900 + n + k, null_frac=null_frac)
+    if null_frac >= 1.0:
+        assert not valid.any()
+    exp_off, exp_data = _expected_utf8(labels, idx, valid)
+    ora = oracle.OracleResult(batch)
+    with _result(ctx, batch) as res:
+        tc = tr.text_column(res, 0)
+        assert np.array_equal(tc.offsets.astype(np.int64), exp_off)
+        assert tc.data == exp_data
+        assert np.array_equal(tc.valid, np.ones(n, bool) if valid is None else valid)
+        for r in range(0, n, max(1, n // 53)):
+            a, b = int(tc.offsets[r]), int(tc.offsets[r + 1])
+            assert tc.data[a:b] == (b"" if ora.cell_is_null(0, r) else ora.cell_value(0, r))
+
+
+def test_enum_fused_device_api_flags_long_labels_and_bad_indices(ctx):
+    """dmb_dev_enum_utf8 at the device API: a label of > 12 bytes raises the heap-range flag, an index past the dictionary is counted
+    and rendered empty, more than DMB_ENUM_FUSED_MAX_LABELS labels are refused before any launch."""
+    import ctypes as C
+    from duckdb_mbt_b200 import native as nat
+    L = nat.lib()
+    dev = torch.device("cuda")
+    n, nch = 5000, 3
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run(labels, idx_np, dict_size=None):
+        d_offs, d_data = ch.enum_dict_arrays(labels)
+        t_offs = torch.from_numpy(d_offs.view(np.uint8).copy()).to(dev)
+        t_data = torch.from_numpy(np.concatenate([d_data, np.zeros(64, np.uint8)])).to(dev)
+        slab = np.zeros(nch * 2048, np.uint8)
+        slab[:n] = idx_np
+        idx = torch.from_numpy(slab).to(dev)
+        counts = torch.tensor([2048, 2048, n - 4096], dtype=torch.int32, device=dev)
+        row_off = torch.tensor([0, 2048, 4096, n], dtype=torch.int64, device=dev)
+        vecs = torch.tensor([[0, -1], [2048, -1], [4096, -1]], dtype=torch.int64, device=dev)
+        bad = torch.zeros(1, dtype=torch.int64, device=dev)
+        offsets = torch.zeros(4 * (n + 1) + 64, dtype=torch.uint8, device=dev)
+        data = torch.zeros(12 * n + 64, dtype=torch.uint8, device=dev)
+        total = torch.zeros(1, dtype=torch.int64, device=dev)
+        scratch = torch.empty(L.dmb_dev_string_scratch_bytes(nch), dtype=torch.uint8, device=dev)
+        ejob = nat.EnumJob(idx.data_ptr(), None, vecs.data_ptr(), None, t_offs.data_ptr(), t_data.data_ptr(), 1 << 41, bad.data_ptr(),
+                           len(labels) if dict_size is None else dict_size, ch.P_U8)
+        sjob = nat.StringJob(None, None, None, None, 0, 0, offsets.data_ptr(), data.data_ptr(), None, None, None, total.data_ptr(), 0, 0)
+        rc = L.dmb_dev_enum_utf8(C.byref(ejob), C.byref(sjob), counts.data_ptr(), row_off.data_ptr(), nch, n, scratch.data_ptr(), stream)
+        flags = L.dmb_dev_string_error(scratch.data_ptr(), stream) if rc == 0 else None
+        tot = int(total.item())
+        return rc, flags, int(bad.item()), offsets[:4 * (n + 1)].cpu().numpy().view("<i4"), bytes(data[:tot].cpu().numpy())
+
+    rng = np.random.default_rng(4)
+    labels = [b"a", b"", b"twelve bytes", b"xyz"]
+    idx_np = rng.integers(0, 4, n).astype(np.uint8)
+    rc, flags, nbad, off, dat = run(labels, idx_np)
+    exp_off, exp_data = _expected_utf8(labels, idx_np, None)
+    assert (rc, flags, nbad) == (0, 0, 0) and np.array_equal(off, exp_off) and dat == exp_data
+    idx_bad = idx_np.copy()
+    idx_bad[[7, 4999]] = 200
+    rc, flags, nbad, off, dat = run(labels, idx_bad)
+    assert (rc, flags, nbad) == (0, 0, 2)
+    exp_off, exp_data = _expected_utf8(labels + [b""] * 252, idx_bad, None)   # rendered empty
+    assert np.array_equal(off, exp_off) and dat == exp_data
+    rc, flags, nbad, off, dat = run([b"a", b"thirteen byte"], (idx_np & 1))
+    assert rc == 0 and flags != 0                                             # heap-range flag: a label the kernel cannot inline
+    rc = run([b"a"], np.zeros(n, np.uint8), dict_size=257)[0]
+    assert rc != 0 and "labels" in nat.last_error()
