@@ -1332,8 +1332,10 @@ template <int EW> struct EnumIndex { typedef uint8_t type; };
 template <> struct EnumIndex<2> { typedef uint16_t type; };
 template <> struct EnumIndex<4> { typedef uint32_t type; };
 
-template <bool LARGE, int RPT, int EW>
-__global__ void __launch_bounds__(kThreads, RPT >= 8 ? DMB_SHORT_CTAS8 : 5)
+// ECTAS: CTAs per SM of the ENUM form, whose rows keep an index + a length in registers instead of a string_t
+// (6: 40 registers + 56 bytes of spills; 5: 48 registers; runtime choice DMB_ENUM_CTAS for A/B)
+template <bool LARGE, int RPT, int EW, int ECTAS = 6>
+__global__ void __launch_bounds__(kThreads, EW ? ECTAS : (RPT >= 8 ? DMB_SHORT_CTAS8 : 5))
 string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles, dmb_enum_job ej) {
   constexpr int kRows = kThreads * RPT;
   constexpr int kTilesPerChunk = kVec / kRows;
@@ -1357,14 +1359,17 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
 
   // stripe k of warp w holds tile rows w*32*RPT + k*32 + lane
   const int row0 = warp * (32 * RPT) + lane;
-  uint4 e[RPT];
-  uint32_t idx[EW ? RPT : 1];
+  uint4 e[EW ? 1 : RPT];
+  uint32_t idx[EW ? RPT : 1];  // ENUM: the row's index, from the scan on: index | bytes the row contributes << 16
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     const int row = row0 + 32 * k;
-    e[k] = make_uint4(0, 0, 0, 0);
-    if (EW) idx[k] = row < count ? (uint32_t)in_idx[row] : 0u;  // (the index under a NULL row is read and dropped)
-    else if (row < count) e[k] = ld_stream(in + row);
+    if (EW) {
+      idx[k] = row < count ? (uint32_t)in_idx[row] : 0u;  // (the index under a NULL row is read and dropped)
+    } else {
+      e[EW ? 0 : k] = make_uint4(0, 0, 0, 0);
+      if (row < count) e[EW ? 0 : k] = ld_stream(in + row);
+    }
   }
   if (EW) {  // the labels as string_t, once per CTA (the index loads above are in flight meanwhile)
     for (uint32_t t = tid; t < ej.dict_size; t += kThreads) s_tab[t] = enum_entry(ej, t);
@@ -1379,14 +1384,19 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     uint32_t l = 0;
     if (row < count) {
       const bool valid = mask ? ((__ldg(mask + (row >> 6)) >> (row & 63)) & 1ull) : true;
-      if (EW && valid) {
-        if (idx[k] < ej.dict_size) e[k] = s_tab[idx[k]];
-        else ++bad_idx;  // an index past the dictionary: reported, rendered as the empty string
+      if (EW) {
+        if (valid) {
+          if (idx[k] < ej.dict_size) l = s_tab[idx[k]].x;
+          else ++bad_idx;  // an index past the dictionary: reported, rendered as the empty string
+        }
+      } else {
+        l = valid ? e[EW ? 0 : k].x : 0u;
       }
-      l = valid ? e[k].x : 0u;
       if (l > 12u) { bad = 1; l = 0; }  // a pointer string, but the batch registered no heap (ENUM: a label too long for this kernel)
     }
-    e[k].x = l;  // from here on: the bytes the row contributes
+    // from here on: the bytes the row contributes
+    if (EW) idx[k] = (l ? idx[k] : 0u) | (l << 16);
+    else e[EW ? 0 : k].x = l;
     lmax = lmax > l ? lmax : l;
   }
   // exclusive offsets within the warp: stripes 2i and 2i+1 scanned together in 16-bit halves
@@ -1394,7 +1404,7 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   uint32_t carry = 0;
 #pragma unroll
   for (int k = 0; k < RPT; k += 2) {
-    const uint32_t both = e[k].x | (e[k + 1].x << 16);
+    const uint32_t both = EW ? ((idx[k] >> 16) | (idx[k + 1] & 0xffff0000u)) : (e[EW ? 0 : k].x | (e[EW ? 0 : k + 1].x << 16));
     uint32_t incl = both;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -1435,13 +1445,26 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   // place the bytes at their tile-local positions (stage byte q = byte q of the tile's output)
 #pragma unroll
   for (int k = 0; k < RPT; ++k) off[k] += warp_excl;
+  if (EW) {  // the label again from the table, one row at a time: only index + length stay live across the scan
 #pragma unroll
-  for (int i = 0; i < 12; ++i) {
-    if ((uint32_t)i < lmax) {  // warp-uniform
+    for (int k = 0; k < RPT; ++k) {
+      const uint32_t l = idx[k] >> 16;
+      const uint4 ent = s_tab[idx[k] & 0xffffu];
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) {
-        const uint32_t wsel = i < 4 ? e[k].y : (i < 8 ? e[k].z : e[k].w);
-        if ((uint32_t)i < e[k].x) stage[off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
+      for (int i = 0; i < 12; ++i) {
+        const uint32_t wsel = i < 4 ? ent.y : (i < 8 ? ent.z : ent.w);
+        if ((uint32_t)i < lmax && (uint32_t)i < l) stage[off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      if ((uint32_t)i < lmax) {  // warp-uniform
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const uint32_t wsel = i < 4 ? e[EW ? 0 : k].y : (i < 8 ? e[EW ? 0 : k].z : e[EW ? 0 : k].w);
+          if ((uint32_t)i < e[EW ? 0 : k].x) stage[off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
+        }
       }
     }
   }
@@ -1449,13 +1472,26 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   // place the bytes at their tile-local positions (stage byte q = byte q of the tile's output)
 #pragma unroll
   for (int k = 0; k < RPT; ++k) off[k] += warp_excl;
+  if (EW) {  // the label again from the table, one row at a time: only index + length stay live across the scan
 #pragma unroll
-  for (int i = 0; i < 12; ++i) {
-    if ((uint32_t)i < lmax) {  // warp-uniform
+    for (int k = 0; k < RPT; ++k) {
+      const uint32_t l = idx[k] >> 16;
+      const uint4 ent = s_tab[idx[k] & 0xffffu];
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) {
-        const uint32_t wsel = i < 4 ? e[k].y : (i < 8 ? e[k].z : e[k].w);
-        if ((uint32_t)i < e[k].x) stage[off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
+      for (int i = 0; i < 12; ++i) {
+        const uint32_t wsel = i < 4 ? ent.y : (i < 8 ? ent.z : ent.w);
+        if ((uint32_t)i < lmax && (uint32_t)i < l) stage[off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      if ((uint32_t)i < lmax) {  // warp-uniform
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const uint32_t wsel = i < 4 ? e[EW ? 0 : k].y : (i < 8 ? e[EW ? 0 : k].z : e[EW ? 0 : k].w);
+          if ((uint32_t)i < e[EW ? 0 : k].x) stage[off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
+        }
       }
     }
   }
@@ -1568,6 +1604,15 @@ extern "C" int32_t dmb_dev_enum_utf8(const dmb_enum_job *ejob, const dmb_string_
     kernel<<<(unsigned)nchunks, kThreads, 0, st>>>(*job, b, (unsigned long long *)scratch, nchunks, *ejob);
     return check_cuda(cudaGetLastError(), "string_short_kernel (ENUM) launch");
   };
+  static const int ctas = getenv("DMB_ENUM_CTAS") ? atoi(getenv("DMB_ENUM_CTAS")) : 6;
+  if (ctas == 5) {
+    switch (ejob->phys) {
+      case DMB_PHYS_U8: return large ? launch(string_short_kernel<true, 8, 1, 5>) : launch(string_short_kernel<false, 8, 1, 5>);
+      case DMB_PHYS_U16: return large ? launch(string_short_kernel<true, 8, 2, 5>) : launch(string_short_kernel<false, 8, 2, 5>);
+      case DMB_PHYS_U32: return large ? launch(string_short_kernel<true, 8, 4, 5>) : launch(string_short_kernel<false, 8, 4, 5>);
+      default: break;
+    }
+  }
   switch (ejob->phys) {
     case DMB_PHYS_U8: return large ? launch(string_short_kernel<true, 8, 1>) : launch(string_short_kernel<false, 8, 1>);
     case DMB_PHYS_U16: return large ? launch(string_short_kernel<true, 8, 2>) : launch(string_short_kernel<false, 8, 2>);
