@@ -1452,8 +1452,9 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
       const uint4 ent = s_tab[idx[k] & 0xffffu];
 #pragma unroll
       for (int i = 0; i < 12; ++i) {
+        if ((uint32_t)i >= lmax) break;  // warp-uniform: no issue slots for bytes past the longest label of the warp's rows
         const uint32_t wsel = i < 4 ? ent.y : (i < 8 ? ent.z : ent.w);
-        if ((uint32_t)i < lmax && (uint32_t)i < l) stage[off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
+        if ((uint32_t)i < l) stage[off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
       }
     }
   } else {
@@ -1479,8 +1480,9 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
       const uint4 ent = s_tab[idx[k] & 0xffffu];
 #pragma unroll
       for (int i = 0; i < 12; ++i) {
+        if ((uint32_t)i >= lmax) break;  // warp-uniform: no issue slots for bytes past the longest label of the warp's rows
         const uint32_t wsel = i < 4 ? ent.y : (i < 8 ? ent.z : ent.w);
-        if ((uint32_t)i < lmax && (uint32_t)i < l) stage[off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
+        if ((uint32_t)i < l) stage[off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
       }
     }
   } else {
