@@ -46,7 +46,8 @@ PHYS_NUMPY = {
 # enum dmb_dst
 (D_SAME, D_I32_TRUNC, D_I64, D_F64, D_BOOL_BYTE, D_BOOL_BITS, D_I128, D_I32_SAT,
  D_TS_US_FROM_S, D_TS_US_FROM_MS, D_TS_US_FROM_NS, D_MONTH_DAY_NANO, D_DATE_REF,
- D_TS_REF, D_TS_REF_FROM_S, D_TS_REF_FROM_MS, D_TS_REF_FROM_NS) = range(17)
+ D_TS_REF, D_TS_REF_FROM_S, D_TS_REF_FROM_MS, D_TS_REF_FROM_NS,
+ D_DEC_I64, D_DEC_I32_TRUNC, D_DEC_F64, D_DEC_BOOL_BYTE) = range(21)
 OP_VALIDITY_ONLY = 0x7F00
 
 

@@ -79,7 +79,7 @@ struct Col {
   std::vector<uint64_t> child_sizes, child_base;  // child_base: element index of chunk k's child vector in the staged slab (nchunks + 1)
   std::vector<int64_t> child_val_off;
   uint8_t *d_child = nullptr;
-  uint64_t *d_child_validity = nullptr, *d_child_base = nullptr;
+  uint64_t *d_child_validity = nullptr, *d_child_base = nullptr, *d_child_sizes = nullptr;
   int64_t *d_child_val_off = nullptr;
   bool child_staged = false;
   // device copy (lives as long as the result)
@@ -307,7 +307,7 @@ struct FixedRun {
 // op == DMB_OP_VALIDITY_ONLY or an unsupported (phys,dst) pair with zero_width > 0: only the
 // validity outputs are produced and the values are `zero_width` zero bytes per row.
 int32_t run_fixed(Result *r, Scope &sc, int j, int32_t op, int zero_width, bool want_bitmap, bool want_valid_bytes,
-                  FixedRun *out) {
+                  FixedRun *out, int32_t param = 0) {
   if (stage_column(r, j)) return -1;
   CtxCore &c = *r->core;
   Col &col = r->cols[(size_t)j];
@@ -350,6 +350,7 @@ int32_t run_fixed(Result *r, Scope &sc, int j, int32_t op, int zero_width, bool 
   job.out_valid_bytes = out->d_valid_bytes;
   job.null_count = out->d_null_count;
   job.op = op;
+  job.param = param;
   if (check_cuda(cudaStreamWaitEvent(c.s_compute, col.ev_staged, 0), "wait staged")) return -1;
   void *jd = upload_job(sc, &job, sizeof(job));
   if (!jd) return -1;
@@ -373,6 +374,7 @@ struct StringRun {
   unsigned long long *d_total = nullptr;
   unsigned long long *h_ctr = nullptr;  // pinned: [0] total bytes [1] error flags [2] null count [3] ENUM indices past the dictionary
   int mode = 0;
+  bool exact = false;          // data_cap was sized from a first launch's total
   cudaEvent_t done = nullptr;  // kernel + the small counter copies
 };
 
@@ -417,9 +419,15 @@ int32_t string_source(Result *r, Scope &sc, int j, bool arrow_mode, StringSource
       d.d_offsets = (uint32_t *)keep_dev(r, d.offsets.size() * sizeof(uint32_t));
       d.d_data = (uint8_t *)keep_dev(r, d.data.size() + 64);
       if (!d.d_offsets || !d.d_data) return -1;
-      // small and pageable: synchronous copies, once per result
-      if (check_cuda(cudaMemcpy(d.d_offsets, d.offsets.data(), d.offsets.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "enum dictionary offsets H2D")) return -1;
-      if (!d.data.empty() && check_cuda(cudaMemcpy(d.d_data, d.data.data(), d.data.size(), cudaMemcpyHostToDevice), "enum dictionary data H2D")) return -1;
+      // once per result, through a pinned copy on the stream of the kernels that read it (a pageable cudaMemcpy on the
+      // legacy stream is not ordered with the non-blocking compute stream)
+      const size_t ob = d.offsets.size() * sizeof(uint32_t);
+      uint8_t *hp = (uint8_t *)keep_pin(r, ob + d.data.size());
+      if (!hp) return -1;
+      memcpy(hp, d.offsets.data(), ob);
+      if (!d.data.empty()) memcpy(hp + ob, d.data.data(), d.data.size());
+      if (check_cuda(cudaMemcpyAsync(d.d_offsets, hp, ob, cudaMemcpyHostToDevice, c.s_compute), "enum dictionary offsets H2D")) return -1;
+      if (!d.data.empty() && check_cuda(cudaMemcpyAsync(d.d_data, hp + ob, d.data.size(), cudaMemcpyHostToDevice, c.s_compute), "enum dictionary data H2D")) return -1;
       r->bytes_h2d += d.offsets.size() * sizeof(uint32_t) + d.data.size();
     }
     static const bool no_fused = getenv("DMB_ENUM_TWO_STEP") != nullptr;  // A/B: keep the string_t intermediate
@@ -498,7 +506,8 @@ int32_t string_source(Result *r, Scope &sc, int j, bool arrow_mode, StringSource
   return 0;
 }
 
-int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool want_valid_bytes, StringRun *out) {
+// exact_cap != 0: the data bytes the column is known to need (a first launch reported them, see kStrFlagDataCap)
+int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool want_valid_bytes, StringRun *out, size_t exact_cap = 0) {
   StringSource src;
   if (string_source(r, sc, j, mode != DMB_STR_REF_BLOB, &src)) return -1;
   CtxCore &c = *r->core;
@@ -509,7 +518,10 @@ int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool
   out->d_offsets = sc.dalloc(out->offsets_bytes + 64);
   // rendered text: at most one slot per row; ENUM: at most the longest label per row
   const size_t per_row = col.phys == DMB_PHYS_STRING ? 12 : (col.type_id == DMB_TYPE_ENUM ? (src.max_row_bytes > 12 ? src.max_row_bytes : 12) : (size_t)dmb_render_slot_bytes(col.type_id));
+  // (string_t entries may alias heap bytes -- a flattened dictionary vector does -- so this is a first guess, not a bound:
+  // the kernels check it and report the exact total, and the caller launches again with exact_cap)
   out->data_cap = per_row * (size_t)n + (col.phys == DMB_PHYS_STRING ? (size_t)col.d_heap_len : 0) + (mode == DMB_STR_REF_BLOB ? (size_t)n : 0);
+  if (exact_cap) { out->data_cap = exact_cap; out->exact = true; }
   out->d_data = (uint8_t *)sc.dalloc(out->data_cap + 64);
   out->d_scratch = sc.dalloc(dmb_dev_string_scratch_bytes(r->nchunks));
   out->d_total = (unsigned long long *)sc.dalloc(8);
@@ -531,6 +543,7 @@ int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool
   job.out_data = out->d_data;
   job.total_bytes = out->d_total;
   job.mode = mode;
+  job.out_data_cap = out->data_cap;
   cudaEvent_t k0 = sc.event(true), k1 = sc.event(true), done = sc.event(false);
   if (!k0 || !k1 || !done) return -1;
   cudaEventRecord(k0, c.s_compute);
@@ -548,12 +561,32 @@ int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool
   return 0;
 }
 
+constexpr unsigned long long kStrFlagOverflow = 2, kStrFlagDataCap = 8;  // kernels_string.cu kErr*
 int32_t string_flags_error(unsigned long long flags) {
   if (!flags) return 0;
   if (flags & (1ull << 63)) { set_error("ENUM index outside the type's dictionary"); return -1; }
-  if (flags & 4) set_error("string_t pointer outside the registered heap");
-  else if (flags & 2) set_error("utf8 data exceeds int32 offsets");
+  if (flags & 16) set_error("a string tile's look-back gave up waiting for its predecessors (GPU preempted or oversubscribed?); run the call again");
+  else if (flags & 4) set_error("string_t pointer outside the registered heap");
+  else if (flags & kStrFlagDataCap) set_error("string bytes exceed the sized output buffer");
+  else if (flags & kStrFlagOverflow) set_error("utf8 data exceeds int32 offsets");
   else set_error("a 1024-row tile holds more than 4 GiB of string bytes");
+  return -1;
+}
+
+// run_string + wait; a column whose strings alias heap bytes overflows the first-guess buffer and is run again, sized exactly
+int32_t run_string_sync(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool want_valid_bytes, StringRun *out) {
+  size_t exact = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    *out = StringRun();
+    if (run_string(r, sc, j, mode, want_bitmap, want_valid_bytes, out, exact)) return -1;
+    if (check_cuda(cudaEventSynchronize(out->done), "string kernel wait")) return -1;
+    const unsigned long long flags = out->h_ctr[1];
+    if ((flags & kStrFlagDataCap) && !(flags & ~(kStrFlagDataCap | kStrFlagOverflow)) && attempt == 0) {
+      exact = (size_t)out->h_ctr[0];
+      continue;
+    }
+    return string_flags_error(flags | (out->h_ctr[3] ? (1ull << 63) : 0ull));
+  }
   return -1;
 }
 
@@ -585,12 +618,14 @@ int32_t stage_list_child(Result *r, int j) {
   uint8_t *arena = (uint8_t *)keep_pin(r, (size_t)total * W + 64);
   uint64_t *warena = (uint64_t *)keep_pin(r, (size_t)(words + 2) * 8);
   uint64_t *h_base = (uint64_t *)keep_pin(r, (size_t)(nch + 1) * 8);
+  uint64_t *h_sizes = (uint64_t *)keep_pin(r, (size_t)(nch + 1) * 8);
+  col.d_child_sizes = (uint64_t *)keep_dev(r, (size_t)(nch + 1) * 8);
   int64_t *h_voff = (int64_t *)keep_pin(r, (size_t)(nch + 1) * 8);
   col.d_child = (uint8_t *)keep_dev(r, (size_t)total * W + 64);
   col.d_child_validity = (uint64_t *)keep_dev(r, (size_t)(words + 2) * 8);
   col.d_child_base = (uint64_t *)keep_dev(r, (size_t)(nch + 1) * 8);
   col.d_child_val_off = (int64_t *)keep_dev(r, (size_t)(nch + 1) * 8);
-  if (!arena || !warena || !h_base || !h_voff || !col.d_child || !col.d_child_validity || !col.d_child_base || !col.d_child_val_off) return -1;
+  if (!arena || !warena || !h_base || !h_voff || !h_sizes || !col.d_child_sizes || !col.d_child || !col.d_child_validity || !col.d_child_base || !col.d_child_val_off) return -1;
   memset(warena, 0, (size_t)(words + 2) * 8);
   parallel_for(nch, c.stage_threads, [&](int64_t k) {
     const uint64_t sz = col.child_sizes[(size_t)k];
@@ -599,6 +634,8 @@ int32_t stage_list_child(Result *r, int j) {
   });
   memcpy(h_base, col.child_base.data(), (size_t)(nch + 1) * 8);
   memcpy(h_voff, col.child_val_off.data(), (size_t)nch * 8);
+  if (nch) memcpy(h_sizes, col.child_sizes.data(), (size_t)nch * 8);
+  if (nch && check_cuda(cudaMemcpyAsync(col.d_child_sizes, h_sizes, (size_t)nch * 8, cudaMemcpyHostToDevice, c.s_in), "list child sizes H2D")) return -1;
   if (total && check_cuda(cudaMemcpyAsync(col.d_child, arena, (size_t)total * W, cudaMemcpyHostToDevice, c.s_in), "list child H2D")) return -1;
   if (words && check_cuda(cudaMemcpyAsync(col.d_child_validity, warena, (size_t)words * 8, cudaMemcpyHostToDevice, c.s_in), "list child masks H2D")) return -1;
   if (check_cuda(cudaMemcpyAsync(col.d_child_base, h_base, (size_t)(nch + 1) * 8, cudaMemcpyHostToDevice, c.s_in), "list child base H2D")) return -1;
@@ -626,18 +663,24 @@ int32_t run_list(Result *r, Scope &sc, int j, int32_t child_op, bool child_as_st
   // upper bound of the child elements the export can hold: every element of every child vector, or (shared spans) more:
   // sized exactly by a host pass over the entries
   uint64_t cap = 0;
+  std::atomic<bool> outside{false};
   {
     std::vector<uint64_t> part((size_t)(nch > 0 ? nch : 1), 0);
     parallel_for(nch, c.stage_threads, [&](int64_t k) {
       const uint64_t *e = reinterpret_cast<const uint64_t *>(col.data[(size_t)k]);
       const void *mask = col.validity.empty() ? nullptr : col.validity[(size_t)k];
       uint64_t sum = 0;
-      for (uint32_t i = 0; e && i < r->counts[(size_t)k]; ++i)
-        if (host_row_valid(mask, i)) sum += e[2 * i + 1];
+      const uint64_t csize = col.child_sizes[(size_t)k];
+      for (uint32_t i = 0; e && i < r->counts[(size_t)k]; ++i) {
+        if (!host_row_valid(mask, i)) continue;
+        if (e[2 * i] > csize || e[2 * i + 1] > csize - e[2 * i]) { outside.store(true); continue; }
+        sum += e[2 * i + 1];
+      }
       part[(size_t)k] = sum;
     });
     for (uint64_t v : part) cap += v;
   }
+  if (outside.load()) { set_error("LIST column %d: an entry reaches outside its chunk's child vector (offset + length > duckdb_list_vector_get_size)", j); return -1; }
   if (cap > 0x7fffffffull) { set_error("LIST column %d: %llu child elements exceed int32 offsets; use smaller batches", j, (unsigned long long)cap); return -1; }
   out->capacity = cap;
   out->offsets_bytes = (size_t)(n + 1) * 4;
@@ -667,6 +710,7 @@ int32_t run_list(Result *r, Scope &sc, int j, int32_t child_op, bool child_as_st
   job.child_null_count = d_ctr + 1;
   job.child_width = col.child_width;
   job.large = 0;
+  job.child_sizes = col.d_child_sizes;
   cudaEvent_t k0 = sc.event(true), k1 = sc.event(true), done = sc.event(false);
   if (!k0 || !k1 || !done) return -1;
   cudaEventRecord(k0, c.s_compute);
@@ -793,7 +837,7 @@ struct Pending {  // one column between its kernel launch and its device->host c
   unsigned long long *h_null = nullptr;
 };
 
-int32_t launch_arrow_col(Result *r, Scope &sc, int j, int string_mode, Pending *p) {
+int32_t launch_arrow_col(Result *r, Scope &sc, int j, int string_mode, Pending *p, size_t exact_cap = 0) {
   Col &col = r->cols[(size_t)j];
   if (!arrow_map(col, &p->map)) return -1;
   p->out = std::make_shared<ArrowColOut>();
@@ -809,7 +853,7 @@ int32_t launch_arrow_col(Result *r, Scope &sc, int j, int string_mode, Pending *
   }
   if (p->map.is_string) {
     p->sr = StringRun();
-    if (run_string(r, sc, j, string_mode, true, false, &p->sr)) return -1;
+    if (run_string(r, sc, j, string_mode, true, false, &p->sr, exact_cap)) return -1;
     p->out->format = string_mode == DMB_STR_ARROW_LARGE ? (col.type_id == DMB_TYPE_BLOB ? "Z" : "U") : p->map.format;
   } else {
     p->fr = FixedRun();
@@ -844,8 +888,10 @@ int32_t drain_arrow_col(Result *r, Scope &sc, Pending *p) {
       return (ch->values && ch->validity) ? 0 : -1;
     }
     if (check_cuda(cudaEventSynchronize(l.done), "list kernel wait")) return -1;
+    if (l.h_ctr[2] & 8ull) { set_error("a LIST entry reaches outside its chunk's child vector (offset + length > duckdb_list_vector_get_size)"); return -1; }
+    if (l.h_ctr[2] & 4ull) { set_error("a LIST chunk's look-back gave up waiting for its predecessors (GPU preempted or oversubscribed?); run the call again"); return -1; }
+    if (l.h_ctr[2] & 2ull) { set_error("a LIST chunk holds more than 4 G child elements"); return -1; }
     if (l.h_ctr[2] & 1ull) { set_error("LIST child elements exceed int32 offsets; use smaller batches"); return -1; }
-    if (l.h_ctr[2]) { set_error("a LIST chunk holds more than 4 G child elements"); return -1; }
     const size_t total = (size_t)l.h_ctr[0];
     ch->length = (int64_t)total;
     ch->null_count = (int64_t)l.h_ctr[1];
@@ -867,8 +913,9 @@ int32_t drain_arrow_col(Result *r, Scope &sc, Pending *p) {
   if (p->map.is_string) {
     StringRun &s = p->sr;
     if (check_cuda(cudaEventSynchronize(s.done), "string kernel wait")) return -1;
-    if (s.h_ctr[1] & 2ull) {
-      if (s.mode == DMB_STR_ARROW_UTF8) return 1;
+    if (!(s.h_ctr[1] & ~(kStrFlagDataCap | kStrFlagOverflow)) && !s.h_ctr[3]) {
+      if ((s.h_ctr[1] & kStrFlagOverflow) && s.mode == DMB_STR_ARROW_UTF8) return 1;  // redo with 64-bit offsets
+      if ((s.h_ctr[1] & kStrFlagDataCap) && !s.exact) return 2;                        // redo, sized exactly
     }
     if (string_flags_error(s.h_ctr[1] | (s.h_ctr[3] ? (1ull << 63) : 0ull))) return -1;
     const size_t total = (size_t)s.h_ctr[0];
@@ -926,12 +973,16 @@ int32_t materialise_arrow(Result *r) {
     cudaEventRecord(out0, c.s_out);
     auto drain = [&](int j) -> int32_t {
       int32_t rc = drain_arrow_col(r, sc, &pend[(size_t)j]);
-      if (rc == 1) {  // utf8 offsets overflowed: redo this column with 64-bit offsets
+      for (int redo = 0; redo < 2 && (rc == 1 || rc == 2); ++redo) {
+        // 1: utf8 offsets overflowed -> 64-bit offsets; 2: aliased string_t pointers overflowed the first-guess data
+        // buffer -> sized exactly from the total the first launch reported (both can happen to one column)
+        const int mode = rc == 1 ? DMB_STR_ARROW_LARGE : pend[(size_t)j].sr.mode;
+        const size_t exact = (size_t)pend[(size_t)j].sr.h_ctr[0];
         pend[(size_t)j] = Pending();
-        if (launch_arrow_col(r, sc, j, DMB_STR_ARROW_LARGE, &pend[(size_t)j])) return -1;
+        if (launch_arrow_col(r, sc, j, mode, &pend[(size_t)j], exact)) return -1;
         rc = drain_arrow_col(r, sc, &pend[(size_t)j]);
       }
-      return rc;
+      return rc > 0 ? -1 : rc;
     };
     // Processing order: the copy-out stream trails the copy-in stream by one column, so the first
     // column's copy-in and the last column's copy-out are the only transfers that do not overlap.
@@ -1124,9 +1175,7 @@ int32_t text_column_out(Result *r, Scope &sc, int j, TypedOut &t) {
   CtxCore &c = *r->core;
   const int64_t n = r->nrows;
   StringRun s;
-  if (run_string(r, sc, j, DMB_STR_ARROW_UTF8, false, true, &s)) return -1;
-  if (check_cuda(cudaEventSynchronize(s.done), "string kernel wait")) return -1;
-  if (string_flags_error(s.h_ctr[1] | (s.h_ctr[3] ? (1ull << 63) : 0ull))) return -1;
+  if (run_string_sync(r, sc, j, DMB_STR_ARROW_UTF8, false, true, &s)) return -1;
   const size_t total = (size_t)s.h_ctr[0];
   t.offsets = keep_pin(r, s.offsets_bytes);
   t.data = keep_pin(r, total);
@@ -1222,6 +1271,29 @@ moonbit_bytes_t empty_bytes() { return moonbit_make_bytes_raw(0); }  // duckdb_m
 
 enum GetterKind { kGetInt32, kGetInt64, kGetDouble, kGetBool };
 
+// The reference reads a cell with duckdb_value_int64 / _double / _boolean (src/duckdb_native.c:2384,2417,2449,2541),
+// and libduckdb casts by the column's LOGICAL type: integers, floats, HUGEINT and UHUGEINT by TryCast (failure -> 0),
+// DECIMAL by its scale (TryCastFromDecimal), and DATE / TIME* / TIMESTAMP* / INTERVAL / UUID / ENUM have no cast to a
+// number, so the cell reads as 0.  VARCHAR -> number (libduckdb parses the text) is not reproduced: 0 as well.
+// Only the same-family casts are pinned by reference tests; the rest is UNPINNED.
+struct GetterOp {
+  int32_t op, param;
+};
+GetterOp getter_op(const Col &col, GetterKind kind) {
+  static const int32_t kDst[] = {DMB_DST_I32_TRUNC, DMB_DST_I64, DMB_DST_F64, DMB_DST_BOOL_BYTE};
+  static const int32_t kDecDst[] = {DMB_DST_DEC_I32_TRUNC, DMB_DST_DEC_I64, DMB_DST_DEC_F64, DMB_DST_DEC_BOOL_BYTE};
+  switch (col.type_id) {
+    case DMB_TYPE_BOOLEAN: case DMB_TYPE_TINYINT: case DMB_TYPE_SMALLINT: case DMB_TYPE_INTEGER: case DMB_TYPE_BIGINT:
+    case DMB_TYPE_UTINYINT: case DMB_TYPE_USMALLINT: case DMB_TYPE_UINTEGER: case DMB_TYPE_UBIGINT:
+    case DMB_TYPE_FLOAT: case DMB_TYPE_DOUBLE: case DMB_TYPE_HUGEINT: case DMB_TYPE_UHUGEINT:
+      return GetterOp{DMB_OP(col.phys, kDst[kind]), 0};
+    case DMB_TYPE_DECIMAL:
+      return GetterOp{DMB_OP(col.phys, kDecDst[kind]), col.dec_scale};
+    default:
+      return GetterOp{DMB_OP_VALIDITY_ONLY, 0};
+  }
+}
+
 // [n:i32][values][validity bytes]  (src/duckdb_native.c:2359-2454, 2516-2546, 2572-2685, 2761-2797)
 moonbit_bytes_t getter_fixed(Result *r, int32_t col_idx, GetterKind kind, bool nullable) {
   if (!r) return empty_bytes();
@@ -1230,7 +1302,6 @@ moonbit_bytes_t getter_fixed(Result *r, int32_t col_idx, GetterKind kind, bool n
   CtxCore &c = *r->core;
   std::lock_guard<std::mutex> g(c.mu);
   if (!c.bind()) return empty_bytes();
-  static const int32_t kDst[] = {DMB_DST_I32_TRUNC, DMB_DST_I64, DMB_DST_F64, DMB_DST_BOOL_BYTE};
   static const int kWidth[] = {4, 8, 8, 1};
   const int w = kWidth[kind];
   const int64_t total64 = 4 + (int64_t)row_count * w + (nullable ? row_count : 0);
@@ -1241,10 +1312,9 @@ moonbit_bytes_t getter_fixed(Result *r, int32_t col_idx, GetterKind kind, bool n
   const Col &col = r->cols[(size_t)col_idx];
   Scope sc(c);
   FixedRun f;
-  // a (phys,dst) pair libduckdb cannot cast (or the oracle leaves at 0) yields zero values
-  if (run_fixed(r, sc, col_idx, col.phys == DMB_PHYS_STRING ? DMB_OP_VALIDITY_ONLY : DMB_OP(col.phys, kDst[kind]), w,
-                false, nullable, &f))
-    return empty_bytes();
+  // a type libduckdb cannot cast to a number yields zero values (getter_op)
+  const GetterOp gop = getter_op(col, kind);
+  if (run_fixed(r, sc, col_idx, gop.op, w, false, nullable, &f, gop.param)) return empty_bytes();
   moonbit_bytes_t blob = moonbit_make_bytes_raw((int32_t)total64);
   if (!blob) { set_error("out of memory"); return empty_bytes(); }
   memcpy(blob, &row_count, 4);
@@ -1270,15 +1340,13 @@ moonbit_bytes_t getter_string(Result *r, int32_t col_idx, bool nullable) {
   if (!c.bind()) return empty_bytes();
   const Col &col = r->cols[(size_t)col_idx];
   if (!text_supported(col)) {
-    // duckdb_value_varchar of FLOAT/DOUBLE (shortest round-trip digits), HUGEINT, INTERVAL, TIME*, UUID, BLOB
+    // (every scalar type of the reference's stream whitelist is rendered by K7; what is left is LIST and friends)
     set_error("get_column_string: libduckdb's text rendering of column type %d is not reproduced on the device", col.type_id);
     return empty_bytes();
   }
   Scope sc(c);
   StringRun s;
-  if (run_string(r, sc, col_idx, DMB_STR_REF_BLOB, false, nullable, &s)) return empty_bytes();
-  if (check_cuda(cudaEventSynchronize(s.done), "string kernel wait")) return empty_bytes();
-  if (string_flags_error(s.h_ctr[1] | (s.h_ctr[3] ? (1ull << 63) : 0ull))) return empty_bytes();
+  if (run_string_sync(r, sc, col_idx, DMB_STR_REF_BLOB, false, nullable, &s)) return empty_bytes();
   const uint64_t stream_total = s.h_ctr[0], nulls = s.h_ctr[2];
   const uint64_t total_data_len = stream_total - nulls;
   const int64_t total64 = 8 + (int64_t)total_data_len + (nullable ? row_count : 0);

@@ -47,8 +47,87 @@ __device__ __forceinline__ int64_t to_i64<i128>(i128 v) {
   return fits ? (int64_t)v.lo : 0;
 }
 
+template <>
+__device__ __forceinline__ int64_t to_i64<u128>(u128 v) {  // UHUGEINT: fits iff upper == 0 and lower <= INT64_MAX
+  return (v.hi == 0 && v.lo <= 0x7fffffffffffffffull) ? (int64_t)v.lo : 0;
+}
+
 template <typename S>
 __device__ __forceinline__ double to_f64(S v) { return (double)v; }
+// DuckDB Hugeint::TryCast<double> (CastBigintToFloating): lower + upper * 2^64 in double arithmetic, with the
+// special case for upper == -1 that keeps small negative numbers exact.  UNPINNED (SUM() results read through
+// duckdb_value_double, src/duckdb_native.c:2449).
+template <>
+__device__ __forceinline__ double to_f64<i128>(i128 v) {
+  if (v.hi == -1) return -(double)(0xffffffffffffffffull - v.lo) - 1.0;
+  return (double)v.lo + (double)v.hi * 18446744073709551616.0;
+}
+template <>
+__device__ __forceinline__ double to_f64<u128>(u128 v) { return (double)v.lo + (double)v.hi * 18446744073709551616.0; }
+
+template <typename S>
+__device__ __forceinline__ bool nonzero(S v) { return v != (S)0; }
+template <>
+__device__ __forceinline__ bool nonzero<i128>(i128 v) { return (v.lo | (uint64_t)v.hi) != 0; }
+template <>
+__device__ __forceinline__ bool nonzero<u128>(u128 v) { return (v.lo | v.hi) != 0; }
+
+// ---- DECIMAL through duckdb_value_int64 / _double / _boolean (libduckdb casts by logical type).  Restated from
+// DuckDB's TryCastFromDecimal: integers round half away from zero, (input + sign * 10^scale / 2) / 10^scale with
+// truncating division; double is input / 10^scale when the stored integer is exact in a double (|input| <= 2^53) or
+// scale == 0, else (input / 10^scale) + (input % 10^scale) / 10^scale.  UNPINNED.
+__device__ const double kDoublePow10[39] = {
+    1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19,
+    1e20, 1e21, 1e22, 1e23, 1e24, 1e25, 1e26, 1e27, 1e28, 1e29, 1e30, 1e31, 1e32, 1e33, 1e34, 1e35, 1e36, 1e37, 1e38};
+__device__ __forceinline__ int64_t pow10_i64(int scale) {
+  int64_t p = 1;
+  for (int k = 0; k < scale && k < 18; ++k) p *= 10;
+  return p;
+}
+__device__ __forceinline__ __int128 pow10_i128(int scale) {
+  __int128 p = 1;
+  for (int k = 0; k < scale && k < 38; ++k) p *= 10;
+  return p;
+}
+__device__ __forceinline__ __int128 as_int128(i128 v) { return ((__int128)v.hi << 64) | (__int128)(unsigned __int128)v.lo; }
+__device__ __forceinline__ double int128_to_f64(__int128 x) {
+  i128 v;
+  v.lo = (uint64_t)x;
+  v.hi = (int64_t)(x >> 64);
+  return to_f64<i128>(v);
+}
+
+template <typename S>
+__device__ __forceinline__ int64_t dec_to_i64(S v, int scale) {
+  const int64_t power = pow10_i64(scale);
+  const int64_t x = (int64_t)v;
+  const int64_t rounding = (x < 0 ? -power : power) / 2;
+  return (x + rounding) / power;
+}
+template <>
+__device__ __forceinline__ int64_t dec_to_i64<i128>(i128 v, int scale) {
+  const __int128 power = pow10_i128(scale);
+  const __int128 x = as_int128(v);
+  const __int128 rounding = (x < 0 ? -power : power) / 2;
+  const __int128 q = (x + rounding) / power;
+  return (q >= -(__int128)9223372036854775807ll - 1 && q <= (__int128)9223372036854775807ll) ? (int64_t)q : 0;  // out of range: the cast fails -> 0
+}
+template <typename S>
+__device__ __forceinline__ double dec_to_f64(S v, int scale) {
+  const int64_t x = (int64_t)v;
+  const double dp = kDoublePow10[scale < 0 ? 0 : (scale > 38 ? 38 : scale)];
+  if (scale == 0 || (x <= 9007199254740992ll && x >= -9007199254740992ll)) return (double)x / dp;
+  const int64_t power = pow10_i64(scale);
+  return (double)(x / power) + (double)(x % power) / dp;
+}
+template <>
+__device__ __forceinline__ double dec_to_f64<i128>(i128 v, int scale) {
+  const __int128 x = as_int128(v);
+  const double dp = kDoublePow10[scale < 0 ? 0 : (scale > 38 ? 38 : scale)];
+  if (scale == 0 || (x <= (__int128)9007199254740992ll && x >= -(__int128)9007199254740992ll)) return int128_to_f64(x) / dp;
+  const __int128 power = pow10_i128(scale);
+  return int128_to_f64(x / power) + int128_to_f64(x % power) / dp;
+}
 
 template <typename S>
 __device__ __forceinline__ int32_t to_i32_sat(S v) {  // src/duckdb_parsing.mbt:203-237
@@ -87,26 +166,35 @@ __device__ __forceinline__ int32_t date_ref_quirk(int32_t days) {
   return (int32_t)((int64_t)days + missing);
 }
 
-struct CvSame { template <typename S> __device__ __forceinline__ S operator()(S v) const { return v; } };
-struct CvI64 { template <typename S> __device__ __forceinline__ int64_t operator()(S v) const { return to_i64<S>(v); } };
-struct CvI32Trunc { template <typename S> __device__ __forceinline__ int32_t operator()(S v) const { return (int32_t)to_i64<S>(v); } };
-struct CvF64 { template <typename S> __device__ __forceinline__ double operator()(S v) const { return to_f64<S>(v); } };
-struct CvBoolByte { template <typename S> __device__ __forceinline__ uint8_t operator()(S v) const { return v != (S)0 ? 1 : 0; } };
-struct CvI32Sat { template <typename S> __device__ __forceinline__ int32_t operator()(S v) const { return to_i32_sat<S>(v); } };
-struct CvI128 {
+// every functor is built from dmb_fixed_job.param (only the DECIMAL casts use it: the scale)
+struct CvNoParam { __device__ __forceinline__ CvNoParam(int32_t = 0) {} };
+struct CvSame : CvNoParam { using CvNoParam::CvNoParam; template <typename S> __device__ __forceinline__ S operator()(S v) const { return v; } };
+struct CvI64 : CvNoParam { using CvNoParam::CvNoParam; template <typename S> __device__ __forceinline__ int64_t operator()(S v) const { return to_i64<S>(v); } };
+struct CvI32Trunc : CvNoParam { using CvNoParam::CvNoParam; template <typename S> __device__ __forceinline__ int32_t operator()(S v) const { return (int32_t)to_i64<S>(v); } };
+struct CvF64 : CvNoParam { using CvNoParam::CvNoParam; template <typename S> __device__ __forceinline__ double operator()(S v) const { return to_f64<S>(v); } };
+struct CvBoolByte : CvNoParam { using CvNoParam::CvNoParam; template <typename S> __device__ __forceinline__ uint8_t operator()(S v) const { return nonzero<S>(v) ? 1 : 0; } };
+struct CvI32Sat : CvNoParam { using CvNoParam::CvNoParam; template <typename S> __device__ __forceinline__ int32_t operator()(S v) const { return to_i32_sat<S>(v); } };
+struct CvDecBase { int scale; __device__ __forceinline__ CvDecBase(int32_t p = 0) : scale(p) {} };
+struct CvDecI64 : CvDecBase { using CvDecBase::CvDecBase; template <typename S> __device__ __forceinline__ int64_t operator()(S v) const { return dec_to_i64<S>(v, scale); } };
+struct CvDecI32Trunc : CvDecBase { using CvDecBase::CvDecBase; template <typename S> __device__ __forceinline__ int32_t operator()(S v) const { return (int32_t)dec_to_i64<S>(v, scale); } };
+struct CvDecF64 : CvDecBase { using CvDecBase::CvDecBase; template <typename S> __device__ __forceinline__ double operator()(S v) const { return dec_to_f64<S>(v, scale); } };
+struct CvDecBoolByte : CvDecBase { using CvDecBase::CvDecBase; template <typename S> __device__ __forceinline__ uint8_t operator()(S v) const { return dec_to_i64<S>(v, scale) != 0 ? 1 : 0; } };
+struct CvI128 : CvNoParam {
+  using CvNoParam::CvNoParam;
   template <typename S> __device__ __forceinline__ i128 operator()(S v) const {
     i128 r; r.lo = (uint64_t)(int64_t)v; r.hi = (int64_t)v < 0 ? -1 : 0; return r;
   }
 };
-struct CvTsS { __device__ __forceinline__ int64_t operator()(int64_t v) const { return (int64_t)((uint64_t)v * 1000000ull); } };
-struct CvTsMs { __device__ __forceinline__ int64_t operator()(int64_t v) const { return (int64_t)((uint64_t)v * 1000ull); } };
-struct CvTsNs { __device__ __forceinline__ int64_t operator()(int64_t v) const { return floor_div(v, 1000); } };
-struct CvMdn {
+struct CvTsS : CvNoParam { using CvNoParam::CvNoParam; __device__ __forceinline__ int64_t operator()(int64_t v) const { return (int64_t)((uint64_t)v * 1000000ull); } };
+struct CvTsMs : CvNoParam { using CvNoParam::CvNoParam; __device__ __forceinline__ int64_t operator()(int64_t v) const { return (int64_t)((uint64_t)v * 1000ull); } };
+struct CvTsNs : CvNoParam { using CvNoParam::CvNoParam; __device__ __forceinline__ int64_t operator()(int64_t v) const { return floor_div(v, 1000); } };
+struct CvMdn : CvNoParam {
+  using CvNoParam::CvNoParam;
   __device__ __forceinline__ month_day_nano_t operator()(interval_t v) const {
     month_day_nano_t r; r.months = v.months; r.days = v.days; r.nanos = (int64_t)((uint64_t)v.micros * 1000ull); return r;
   }
 };
-struct CvDateRef { __device__ __forceinline__ int32_t operator()(int32_t v) const { return date_ref_quirk(v); } };
+struct CvDateRef : CvNoParam { using CvNoParam::CvNoParam; __device__ __forceinline__ int32_t operator()(int32_t v) const { return date_ref_quirk(v); } };
 // typed TIMESTAMP through the reference's parse_timestamp: quirky day number * 86400e6 + time of day
 __device__ __forceinline__ int64_t ts_ref_quirk(int64_t micros) {
   const int64_t kDay = 86400000000ll;
@@ -116,8 +204,8 @@ __device__ __forceinline__ int64_t ts_ref_quirk(int64_t micros) {
   return (int64_t)date_ref_quirk((int32_t)days) * kDay + tod;
 }
 template <typename Pre>
-struct CvTsRef { __device__ __forceinline__ int64_t operator()(int64_t v) const { return ts_ref_quirk(Pre()(v)); } };
-struct CvId64 { __device__ __forceinline__ int64_t operator()(int64_t v) const { return v; } };
+struct CvTsRef : CvNoParam { using CvNoParam::CvNoParam; __device__ __forceinline__ int64_t operator()(int64_t v) const { return ts_ref_quirk(Pre()(v)); } };
+struct CvId64 : CvNoParam { using CvNoParam::CvNoParam; __device__ __forceinline__ int64_t operator()(int64_t v) const { return v; } };
 
 template <typename D> __device__ __forceinline__ D zero_of() { D z; memset(&z, 0, sizeof(D)); return z; }
 
@@ -347,7 +435,7 @@ fixed_batch_kernel(const dmb_fixed_job *__restrict__ jobs, int njobs, BatchView 
     const dmb_fixed_job &job = s_job;
     if (KIND == kKindConvert && job.out_values) {
       if (G > 1) {
-        convert_group<S, D, F>(job, b, i0, G, F());
+        convert_group<S, D, F>(job, b, i0, G, F(job.param));
       } else {
         const int count = (int)__ldg(b.counts + i0);
         if (count > 0) {
@@ -355,7 +443,7 @@ fixed_batch_kernel(const dmb_fixed_job *__restrict__ jobs, int njobs, BatchView 
           const S *in = reinterpret_cast<const S *>(reinterpret_cast<const uint8_t *>(job.in_data) + vd.data_off);
           const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
           D *out = reinterpret_cast<D *>(job.out_values) + __ldg(b.row_off + i0);
-          convert_chunk<S, D, F>(in, mask, out, count, F());
+          convert_chunk<S, D, F>(in, mask, out, count, F(job.param));
         }
       }
     }
@@ -388,6 +476,12 @@ typedef void (*fixed_kernel_fn)(const dmb_fixed_job *, int, BatchView);
   case DMB_OP(DMB_PHYS_U32, DST): return fixed_batch_kernel<uint32_t, DT, CV, kKindConvert>;      \
   case DMB_OP(DMB_PHYS_U64, DST): return fixed_batch_kernel<uint64_t, DT, CV, kKindConvert>;
 
+#define DMB_FOR_DECIMAL(DST, DT, CV)                                                              \
+  case DMB_OP(DMB_PHYS_I16, DST): return fixed_batch_kernel<int16_t, DT, CV, kKindConvert>;       \
+  case DMB_OP(DMB_PHYS_I32, DST): return fixed_batch_kernel<int32_t, DT, CV, kKindConvert>;       \
+  case DMB_OP(DMB_PHYS_I64, DST): return fixed_batch_kernel<int64_t, DT, CV, kKindConvert>;       \
+  case DMB_OP(DMB_PHYS_I128, DST): return fixed_batch_kernel<i128, DT, CV, kKindConvert>;
+
 static fixed_kernel_fn select_kernel(int32_t op) {
   switch (op) {
     // raw copies, NULL slots zeroed
@@ -411,8 +505,19 @@ static fixed_kernel_fn select_kernel(int32_t op) {
     case DMB_OP(DMB_PHYS_I128, DMB_DST_I64): return fixed_batch_kernel<i128, int64_t, CvI64, kKindConvert>;
     DMB_FOR_NUMERIC(DMB_DST_I32_TRUNC, int32_t, CvI32Trunc)
     case DMB_OP(DMB_PHYS_I128, DMB_DST_I32_TRUNC): return fixed_batch_kernel<i128, int32_t, CvI32Trunc, kKindConvert>;
+    case DMB_OP(DMB_PHYS_U128, DMB_DST_I64): return fixed_batch_kernel<u128, int64_t, CvI64, kKindConvert>;
+    case DMB_OP(DMB_PHYS_U128, DMB_DST_I32_TRUNC): return fixed_batch_kernel<u128, int32_t, CvI32Trunc, kKindConvert>;
     DMB_FOR_NUMERIC(DMB_DST_F64, double, CvF64)
+    case DMB_OP(DMB_PHYS_I128, DMB_DST_F64): return fixed_batch_kernel<i128, double, CvF64, kKindConvert>;
+    case DMB_OP(DMB_PHYS_U128, DMB_DST_F64): return fixed_batch_kernel<u128, double, CvF64, kKindConvert>;
     DMB_FOR_NUMERIC(DMB_DST_BOOL_BYTE, uint8_t, CvBoolByte)
+    case DMB_OP(DMB_PHYS_I128, DMB_DST_BOOL_BYTE): return fixed_batch_kernel<i128, uint8_t, CvBoolByte, kKindConvert>;
+    case DMB_OP(DMB_PHYS_U128, DMB_DST_BOOL_BYTE): return fixed_batch_kernel<u128, uint8_t, CvBoolByte, kKindConvert>;
+    // DECIMAL through the reference getters: cast by logical type (scale in job.param)
+    DMB_FOR_DECIMAL(DMB_DST_DEC_I64, int64_t, CvDecI64)
+    DMB_FOR_DECIMAL(DMB_DST_DEC_I32_TRUNC, int32_t, CvDecI32Trunc)
+    DMB_FOR_DECIMAL(DMB_DST_DEC_F64, double, CvDecF64)
+    DMB_FOR_DECIMAL(DMB_DST_DEC_BOOL_BYTE, uint8_t, CvDecBoolByte)
     case DMB_OP(DMB_PHYS_BOOL, DMB_DST_BOOL_BITS): return fixed_batch_kernel<uint8_t, uint8_t, CvSame, kKindBoolBits>;
     // Arrow decimal128 widen
     case DMB_OP(DMB_PHYS_I16, DMB_DST_I128): return fixed_batch_kernel<int16_t, i128, CvI128, kKindConvert>;
@@ -513,12 +618,18 @@ extern "C" int32_t dmb_op_out_width(int32_t op) {
   if (phys < 0 || phys >= DMB_PHYS_STRING) return -1;
   bool numeric = phys <= DMB_PHYS_F64;
   bool integer = phys >= DMB_PHYS_I8 && phys <= DMB_PHYS_U64;
+  bool huge = phys == DMB_PHYS_I128 || phys == DMB_PHYS_U128;  // HUGEINT / UHUGEINT
+  bool decimal = phys == DMB_PHYS_I16 || phys == DMB_PHYS_I32 || phys == DMB_PHYS_I64 || phys == DMB_PHYS_I128;
   switch (dst) {
     case DMB_DST_SAME: return phys_w[phys];
-    case DMB_DST_I32_TRUNC: return (numeric || phys == DMB_PHYS_I128) ? 4 : -1;
-    case DMB_DST_I64: return (numeric || phys == DMB_PHYS_I128) ? 8 : -1;
-    case DMB_DST_F64: return numeric ? 8 : -1;
-    case DMB_DST_BOOL_BYTE: return numeric ? 1 : -1;
+    case DMB_DST_I32_TRUNC: return (numeric || huge) ? 4 : -1;
+    case DMB_DST_I64: return (numeric || huge) ? 8 : -1;
+    case DMB_DST_F64: return (numeric || huge) ? 8 : -1;
+    case DMB_DST_BOOL_BYTE: return (numeric || huge) ? 1 : -1;
+    case DMB_DST_DEC_I32_TRUNC: return decimal ? 4 : -1;
+    case DMB_DST_DEC_I64: return decimal ? 8 : -1;
+    case DMB_DST_DEC_F64: return decimal ? 8 : -1;
+    case DMB_DST_DEC_BOOL_BYTE: return decimal ? 1 : -1;
     case DMB_DST_BOOL_BITS: return phys == DMB_PHYS_BOOL ? 0 : -1;
     case DMB_DST_I128:
       return (phys == DMB_PHYS_I16 || phys == DMB_PHYS_I32 || phys == DMB_PHYS_I64 || phys == DMB_PHYS_I128) ? 16 : -1;

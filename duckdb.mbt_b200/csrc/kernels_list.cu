@@ -80,9 +80,10 @@ list_sum_kernel(dmb_list_job job, const uint32_t *__restrict__ counts, int64_t n
     const ListEntry *ent = reinterpret_cast<const ListEntry *>(reinterpret_cast<const uint8_t *>(job.in_entries) + vd.data_off);
     const uint64_t *mask = vd.val_off < 0 ? nullptr : job.in_validity + vd.val_off;
     uint64_t sum = 0;
+    const uint64_t csize = job.child_sizes ? __ldg(job.child_sizes + c) : ~0ull;
     for (int i = threadIdx.x; i < count; i += kThreads) {
       const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2 *>(ent) + i);  // consecutive lanes, consecutive 16-byte entries
-      if (list_row_valid(mask, i)) sum += e.y;
+      if (list_row_valid(mask, i) && e.x <= csize && e.y <= csize - e.x) sum += e.y;  // (an entry outside the child vector counts as empty, see list_emit_kernel)
     }
     uint64_t total;
     block_exscan(sum, &total, s_warp);
@@ -212,7 +213,8 @@ list_emit_kernel(dmb_list_job job, BatchView b, unsigned long long *chunk_sum /*
       // (the entry of a NULL row is read and dropped: it is storage of the vector, only its content is unspecified)
       ulonglong2 e[kListRpt];
       uint64_t mw[kListRpt];
-      bool big = false;
+      bool big = false, outside = false;
+      const uint64_t csize = job.child_sizes ? __ldg(job.child_sizes + c) : ~0ull;  // elements in this chunk's child vector
 #pragma unroll
       for (int k = 0; k < kListRpt; ++k) {
         const int i = threadIdx.x + k * kThreads;
@@ -222,12 +224,17 @@ list_emit_kernel(dmb_list_job job, BatchView b, unsigned long long *chunk_sum /*
 #pragma unroll
       for (int k = 0; k < kListRpt; ++k) {
         const int i = threadIdx.x + k * kThreads;
-        const bool valid = i < count && ((mw[k] >> (i & 63)) & 1ull);
+        bool valid = i < count && ((mw[k] >> (i & 63)) & 1ull);
+        if (valid && (e[k].x > csize || e[k].y > csize - e[k].x)) {  // a malformed / stale entry: never read outside the child vector
+          outside = true;
+          valid = false;  // contributes no elements; the error flag makes the host discard the output
+        }
         s_src[i] = valid ? e[k].x : 0ull;
         s_start[i] = valid ? (uint32_t)e[k].y : 0u;  // csum <= 4 G: every length fits
         big |= valid && (e[k].y >> 32) != 0ull;
       }
       if (ONEPASS && big) atomicOr(flags, 2ull);  // a list of more than 4 G elements: reported, the output is not usable
+      if (outside) atomicOr(flags, 8ull);
     }
     __syncthreads();
     // ---- this thread's kListRpt consecutive rows: block scan of the lengths, starts written back in place
@@ -452,7 +459,8 @@ extern "C" size_t dmb_dev_list_scratch_bytes(int64_t nchunks) {
   return (size_t)(2 * (nchunks > 0 ? nchunks : 0) + 2) * sizeof(unsigned long long);
 }
 
-// scratch: [0] error flags (1: int32 offsets overflow, 2: a chunk with > 4 G child elements), [1] unused,
+// scratch: [0] error flags (1: int32 offsets overflow, 2: a chunk with > 4 G child elements, 4: a look-back gave up
+// waiting, 8: a list entry reaches outside its chunk's child vector), [1] unused,
 // then chunk_sum[nchunks], chunk_base[nchunks].  out_child_validity must hold ceil(total / 64) + 1 words.
 extern "C" int32_t dmb_dev_list_batch(const dmb_list_job *job, const uint32_t *counts, const int64_t *row_off, int64_t nchunks,
                                       int64_t nrows, int64_t child_capacity, void *scratch, void *stream) {

@@ -1,7 +1,7 @@
 // K5 string_unpack: duckdb_string_t[16 B] -> Arrow utf8 (offsets + data) in ONE pass.
 //
 // Tile = 512 consecutive rows of one chunk (four tiles per 2048-row vector).  A CTA
-//   1. takes tile blockIdx.x (CTAs are dispatched in blockIdx order => look-back always makes progress),
+//   1. claims the next tile from a global ticket (so every predecessor belongs to a running CTA: the look-back always makes progress),
 //   2. loads the tile's string_t into shared memory with coalesced 128-bit loads (read once),
 //   3. block-scans the (validity-masked) lengths into tile-local offsets and, in the same scan, a
 //      running maximum that gives every row the first row of its RUN: a maximal sequence of rows
@@ -46,8 +46,16 @@ constexpr uint64_t kFlagAggregate = 1ull << 62;
 constexpr uint64_t kFlagPrefix = 2ull << 62;
 constexpr uint64_t kValueMask = (1ull << 62) - 1ull;
 
-// scratch layout (uint64 words): [0] unused  [1] error flags  [2..] tile status
-enum { kErrTileTooBig = 1, kErrOffsetOverflow = 2, kErrHeapRange = 4 };
+// scratch layout (uint64 words): [0] tile ticket  [1] error flags  [2..] tile status
+enum { kErrTileTooBig = 1, kErrOffsetOverflow = 2, kErrHeapRange = 4, kErrDataCap = 8, kErrTimeout = 16 };
+
+// Tiles are claimed from a global ticket (scratch[0], zeroed by the launch wrapper), never from blockIdx: CUDA does
+// not promise to dispatch CTAs in blockIdx order, and a look-back may only wait for tiles that RUNNING CTAs own.
+__device__ __forceinline__ int64_t claim_tile(unsigned long long *scratch, long long *slot) {
+  if (threadIdx.x == 0) *slot = (long long)atomicAdd(scratch, 1ull);
+  __syncthreads();
+  return (int64_t)*slot;
+}
 
 #ifdef DMB_STR_TRACE
 __device__ unsigned long long g_str_trace[40000 * 8];
@@ -73,6 +81,7 @@ struct StrSmem {
   uint32_t warp_sum[kThreads / 32];
   uint32_t warp_run[kThreads / 32];
   uint64_t base;
+  long long ticket;
 };
 
 __device__ __forceinline__ uint64_t ld_status(const unsigned long long *p) {
@@ -244,10 +253,7 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   unsigned long long *status = scratch + 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // Tiles are taken in blockIdx order: the hardware dispatches CTAs of a 1-D grid in increasing
-  // blockIdx, so every predecessor a look-back waits for is already resident (the assumption
-  // CUB's single-pass scan makes as well).
-  const int64_t tile = (int64_t)blockIdx.x;
+  const int64_t tile = claim_tile(scratch, &sm.ticket);
   if (tile >= ntiles) return;
   DMB_TRACE(0);
   if (tid < 17) {
@@ -427,6 +433,10 @@ string_batch_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     if (tile == ntiles - 1 && tid == 0 && job.total_bytes) *job.total_bytes = base + tile_total;
   }
   if (tile_total == 0) return;
+  if (job.out_data_cap && base + tile_total > job.out_data_cap) {  // aliased pointers: more bytes than the caller sized for
+    if (tid == 0) atomicOr(scratch + 1, (unsigned long long)kErrDataCap);
+    return;
+  }
 
   // 6. output-centric gather.  Vector v covers tile-local bytes [16v - mis, 16v - mis + 16), i.e. a
   //    16-byte aligned vector of out_data; L(v) = max(16v - mis, 0) is its first owned byte.
@@ -569,7 +579,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-// a protocol error must end as a launch failure, not as a hung GPU: waits give up after 4 s
+// A wait that cannot end must not hang the GPU.  Look-backs (the only waits on OTHER CTAs) give up after 4 s with an
+// error flag and let the launch finish; the mbarrier waits inside a CTA depend only on that CTA's own warps and copy
+// engine transactions, so one that is still pending after 3x that long is a protocol bug: it traps.
 constexpr unsigned long long kWaitLimitNs = 4000000000ull;
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   // try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs out:
@@ -589,7 +601,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     if ((spins & 63u) == 0u) {
       const unsigned long long now = global_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > kWaitLimitNs) __trap();
+      else if (now - t0 > 3ull * kWaitLimitNs) __trap();
     }
   }
 }
@@ -630,6 +642,7 @@ __device__ __forceinline__ uint32_t low_bytes3(uint32_t n) { return (1u << (8u *
 // words are in flight per lane, so one L2 round trip inspects 32*kLookWide predecessors; when a
 // needed word is not published yet only the unpublished ones are read again
 __device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, int64_t tile, int lane, unsigned *stats = nullptr) {
+  unsigned long long *err_flags = status - 1;  // scratch[1]
   uint64_t prefix = 0;
   unsigned rounds = 0, retries = 0;
   unsigned long long t0 = 0;
@@ -669,7 +682,13 @@ __device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, in
         __nanosleep(200);  // the unpublished tiles are owned by running CTAs
         const unsigned long long now = global_ns();
         if (t0 == 0) t0 = now;
-        else if (now - t0 > kWaitLimitNs) __trap();
+        // gave up (warp-uniform): flag it and go on with what has been summed -- the launch ends, the host reports the
+        // flag and discards the outputs; the context stays usable (a trap would poison it for every other result)
+        if (__any_sync(0xffffffffu, now - t0 > kWaitLimitNs)) {
+          if (lane == 0) atomicOr(err_flags, (unsigned long long)kErrTimeout);
+          state = 1;
+          break;
+        }
       }
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -792,7 +811,9 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
             else reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)(base + total);
             if (job.total_bytes) *job.total_bytes = base + total;
           }
-          if (total && mp.staged) {
+          const bool over_cap = job.out_data_cap && base + total > job.out_data_cap;
+          if (over_cap) atomicOr(scratch + 1, (unsigned long long)kErrDataCap);
+          if (total && mp.staged && !over_cap) {
             // stage byte q is global byte gbase + q
             const uint32_t mis = (uint32_t)(base & 15ull);
             uint8_t *gbase = job.out_data + (base - mis);
@@ -1104,7 +1125,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         if (fill) store_bytes(ow + wp, acc, wp == shared_wp ? head : 0u, fill);  // last word: the next thread owns its other bytes
         fence_proxy_async_smem();
         }
-      } else if (HEAP && total != 0u) {
+      } else if (HEAP && total != 0u && !(job.out_data_cap && base + total > job.out_data_cap)) {
         // not staged: one warp per row, one byte per lane, heap -> out_data
         uint8_t *out = job.out_data + base;
         uint32_t offk[R];
@@ -1158,6 +1179,7 @@ struct InlSmem {
   alignas(16) uint8_t stage[kInlRows * 13 + 32];
   uint32_t warp_sum[kThreads / 32];
   uint64_t base;
+  long long ticket;
 };
 
 // strlen of the <= l inline bytes (y, z, w), for the reference blob
@@ -1178,7 +1200,7 @@ string_inline_kernel(dmb_string_job job, BatchView b, unsigned long long *scratc
   __shared__ InlSmem sm;
   unsigned long long *status = scratch + 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t tile = (int64_t)blockIdx.x;  // = chunk index; CTAs are dispatched in blockIdx order
+  const int64_t tile = claim_tile(scratch, &sm.ticket);  // = chunk index
   if (tile >= ntiles) return;
   const int count = (int)__ldg(b.counts + tile);
   const dmb_vec_desc vd = job.vecs[tile];
@@ -1294,6 +1316,10 @@ string_inline_kernel(dmb_string_job job, BatchView b, unsigned long long *scratc
     if (job.total_bytes) *job.total_bytes = base + tile_total;
   }
   if (tile_total == 0) return;
+  if (job.out_data_cap && base + tile_total > job.out_data_cap) {
+    if (tid == 0) atomicOr(scratch + 1, (unsigned long long)kErrDataCap);
+    return;
+  }
   __syncthreads();
   uint8_t *gbase = job.out_data + (base - mis);
   const uint32_t end = mis + tile_total;
@@ -1343,9 +1369,10 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   __shared__ __align__(16) uint8_t stage[kRows * 12 + 32];
   __shared__ uint32_t warp_sum[kWarps];
   __shared__ uint64_t base_sh;
+  __shared__ long long ticket_sh;
   unsigned long long *status = scratch + 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t tile = (int64_t)blockIdx.x;  // CTAs are dispatched in blockIdx order: every predecessor is running or done
+  const int64_t tile = claim_tile(scratch, &ticket_sh);  // every predecessor is owned by a CTA that is running or done
   if (tile >= ntiles) return;
   const int64_t c = tile / kTilesPerChunk;
   const int r_begin = (int)(tile % kTilesPerChunk) * kRows;
@@ -1526,6 +1553,10 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     }
   }
   if (tile_total == 0) return;
+  if (job.out_data_cap && base + tile_total > job.out_data_cap) {
+    if (tid == 0) atomicOr(scratch + 1, (unsigned long long)kErrDataCap);
+    return;
+  }
   // stage -> out_data: destination-aligned 16-byte vectors; vector v holds tile bytes [16v - mis, 16v - mis + 16)
   uint8_t *gdst = job.out_data + base;
   const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
@@ -1736,7 +1767,9 @@ extern "C" int32_t dmb_dev_string_error(const void *scratch, void *stream) {
   unsigned long long flags = 0;
   if (check_cuda(cudaMemcpyAsync(&flags, (const unsigned long long *)scratch + 1, sizeof(flags), cudaMemcpyDeviceToHost, (cudaStream_t)stream), "string error copy")) return -1;
   if (check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "string error sync")) return -1;
-  if (flags & kErrHeapRange) set_error("string_t pointer outside the registered heap");
+  if (flags & kErrTimeout) set_error("a string tile's look-back gave up waiting for its predecessors; the outputs are not valid");
+  else if (flags & kErrHeapRange) set_error("string_t pointer outside the registered heap");
+  else if (flags & kErrDataCap) set_error("the column's strings total more bytes than out_data_cap (aliased string_t pointers?)");
   else if (flags & kErrOffsetOverflow) set_error("utf8 data exceeds int32 offsets; use large offsets or smaller batches");
   else if (flags & kErrTileTooBig) set_error("a 1024-row tile holds more than 4 GiB of string bytes");
   return (int32_t)flags;

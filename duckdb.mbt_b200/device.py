@@ -115,7 +115,8 @@ class DeviceBatch:
                                    o.values.data_ptr() if o.values is not None else None,
                                    o.bitmap.data_ptr() if o.bitmap is not None else None,
                                    o.valid_bytes.data_ptr() if o.valid_bytes is not None else None,
-                                   o.null_count.data_ptr(), o.op, 0)
+                                   o.null_count.data_ptr(), o.op,
+                                   self.batch.columns[o.col].dec_scale if (o.op & 0xFF) >= ch.D_DEC_I64 and o.op != ch.OP_VALIDITY_ONLY else 0)
         jobs_np = np.frombuffer(bytes(jobs), dtype=np.uint8)
         jobs_dev = _dev(jobs_np, self.device)
         return outs, jobs, jobs_dev

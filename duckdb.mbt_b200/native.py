@@ -21,7 +21,7 @@ class VecDesc(C.Structure):
 class FixedJob(C.Structure):
     _fields_ = [("in_data", C.c_void_p), ("in_validity", C.c_void_p), ("vecs", C.c_void_p),
                 ("out_values", C.c_void_p), ("out_validity", C.c_void_p), ("out_valid_bytes", C.c_void_p),
-                ("null_count", C.c_void_p), ("op", C.c_int32), ("reserved", C.c_int32)]
+                ("null_count", C.c_void_p), ("op", C.c_int32), ("param", C.c_int32)]
 
 
 class StringJob(C.Structure):
@@ -29,7 +29,7 @@ class StringJob(C.Structure):
                 ("heap_dev", C.c_void_p), ("heap_host_base", C.c_uint64), ("heap_len", C.c_uint64),
                 ("out_offsets", C.c_void_p), ("out_data", C.c_void_p), ("out_validity", C.c_void_p),
                 ("out_valid_bytes", C.c_void_p), ("null_count", C.c_void_p), ("total_bytes", C.c_void_p),
-                ("mode", C.c_int32), ("reserved", C.c_int32)]
+                ("mode", C.c_int32), ("reserved", C.c_int32), ("out_data_cap", C.c_uint64)]
 
 
 class RenderJob(C.Structure):
@@ -65,7 +65,8 @@ class ListJob(C.Structure):
     _fields_ = [("in_entries", C.c_void_p), ("in_validity", C.c_void_p), ("vecs", C.c_void_p), ("child_base", C.c_void_p),
                 ("child_data", C.c_void_p), ("child_validity", C.c_void_p), ("child_val_off", C.c_void_p),
                 ("out_offsets", C.c_void_p), ("out_child", C.c_void_p), ("out_child_validity", C.c_void_p),
-                ("total", C.c_void_p), ("child_null_count", C.c_void_p), ("child_width", C.c_int32), ("large", C.c_int32)]
+                ("total", C.c_void_p), ("child_null_count", C.c_void_p), ("child_width", C.c_int32), ("large", C.c_int32),
+                ("child_sizes", C.c_void_p)]
 
 
 class HostList(C.Structure):

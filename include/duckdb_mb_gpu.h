@@ -110,7 +110,15 @@ enum dmb_dst {
   DMB_DST_TS_REF_FROM_S = 14,
   DMB_DST_TS_REF_FROM_MS = 15,
   DMB_DST_TS_REF_FROM_NS = 16,
-  DMB_DST_COUNT = 17
+  /* DECIMAL columns through the reference getters: libduckdb's duckdb_value_int64 / _double / _boolean cast by the
+     LOGICAL type (call sites src/duckdb_native.c:2384,2417,2449,2541), i.e. the stored integer is divided by
+     10^scale -- round half away from zero for the integer targets (DuckDB TryCastFromDecimal), value / 10^scale for
+     double.  dmb_fixed_job.param carries the scale.  UNPINNED: no reference test reads a DECIMAL through these getters. */
+  DMB_DST_DEC_I64 = 17,
+  DMB_DST_DEC_I32_TRUNC = 18, /* (int32_t) of the int64 cast, :2384-2385 */
+  DMB_DST_DEC_F64 = 19,
+  DMB_DST_DEC_BOOL_BYTE = 20, /* rounded integer != 0 */
+  DMB_DST_COUNT = 21
 };
 
 #define DMB_OP(phys, dst) (((int32_t)(phys) << 8) | (int32_t)(dst))
@@ -135,7 +143,7 @@ typedef struct dmb_fixed_job {
                                   (src/duckdb_native.c:2594-2606)                        */
   unsigned long long *null_count; /* device counter, incremented; or NULL               */
   int32_t op;                  /* DMB_OP(phys, dst) */
-  int32_t reserved;
+  int32_t param;               /* DMB_DST_DEC_*: the DECIMAL's scale; otherwise 0 */
 } dmb_fixed_job;
 
 /* duckdb_string_t, 16 bytes (reference reads it at src/duckdb_native.c:597-603) */
@@ -173,6 +181,11 @@ typedef struct dmb_string_job {
   unsigned long long *total_bytes; /* device: final data length                            */
   int32_t mode;
   int32_t reserved;
+  uint64_t out_data_cap;       /* bytes `out_data` can hold, or 0: not checked.  string_t entries may ALIAS the same
+                                  heap bytes (a flattened dictionary / constant vector does), so the summed lengths are
+                                  not bounded by 12 n + heap_len: when the column's total exceeds the capacity no data
+                                  byte is written past it, flag 8 is raised (dmb_dev_string_error) and *total_bytes still
+                                  holds the exact total, so the caller can allocate and run again */
 } dmb_string_job;
 
 /* =====================================================================================
@@ -208,7 +221,9 @@ int32_t dmb_phys_width(int32_t phys);
  *             `in`, `out_data`, `heap_dev` 16-byte aligned; the heap copy followed by >= 16 readable bytes
  * Replaces src/duckdb_native.c:597-603 (string_t read) and :2474-2510 / :2699-2755. */
 size_t dmb_dev_string_scratch_bytes(int64_t nchunks);
-/* error flags raised by the last string launch on `scratch` (0 = none); synchronises `stream` */
+/* error flags raised by the last string launch on `scratch` (0 = none); synchronises `stream`.
+ * 1: a tile holds > 4 GiB  2: total exceeds int32 offsets  4: string_t pointer outside the heap
+ * 8: total exceeds out_data_cap  16: a look-back gave up waiting (the outputs are not valid) */
 int32_t dmb_dev_string_error(const void *scratch, void *stream);
 int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_t *counts,
                              const int64_t *row_off, int64_t nchunks, int64_t nrows,
@@ -291,10 +306,14 @@ typedef struct dmb_list_job {
   unsigned long long *child_null_count;
   int32_t child_width;              /* 1 / 2 / 4 / 8 / 16                                       */
   int32_t large;                    /* int64 offsets (large_list)                               */
+  const uint64_t *child_sizes;      /* [nchunks] elements in each chunk's child vector, or NULL: entries are not
+                                       range-checked.  A valid row whose offset + length reaches past its child
+                                       vector raises flag 8 and contributes no elements (never read)            */
 } dmb_list_job;
 
 size_t dmb_dev_list_scratch_bytes(int64_t nchunks);
-/* scratch[0] after the call: error flags (1: total exceeds int32 offsets, 2: a chunk with > 4 G child elements) */
+/* scratch[0] after the call: error flags (1: total exceeds int32 offsets, 2: a chunk with > 4 G child elements,
+ * 4: a look-back gave up waiting, 8: a list entry outside its child vector) */
 int32_t dmb_dev_list_batch(const dmb_list_job *job, const uint32_t *counts, const int64_t *row_off, int64_t nchunks,
                            int64_t nrows, int64_t child_capacity, void *scratch, void *stream);
 

@@ -190,12 +190,68 @@ static int64_t double_to_i64(double v) { /* UNPINNED: DuckDB TryCast double->int
   return (int64_t)nearbyint(v);
 }
 
+/* libduckdb casts a cell by the column's LOGICAL type (GetInternalCValue switches on the deprecated column type):
+ * integers / floats / HUGEINT / UHUGEINT by TryCast (failure -> 0), DECIMAL by TryCastFromDecimal (the stored integer
+ * divided by 10^scale), and DATE / TIME* / TIMESTAMP* / INTERVAL / UUID / ENUM have no cast to a number (TryCast throws,
+ * the C API catches and returns 0).  VARCHAR -> number parses the text in libduckdb; not restated: 0.  UNPINNED except
+ * the same-family integer / double / boolean reads (src/duckdb_arrow_test.mbt). */
+static int numeric_castable(const ora_column *c) {
+  switch (c->type_id) {
+    case T_BOOLEAN: case T_TINYINT: case T_SMALLINT: case T_INTEGER: case T_BIGINT: case T_UTINYINT: case T_USMALLINT:
+    case T_UINTEGER: case T_UBIGINT: case T_FLOAT: case T_DOUBLE: case T_HUGEINT: case T_UHUGEINT: case T_DECIMAL:
+      return 1;
+    default: return 0;
+  }
+}
+
+/* DuckDB Hugeint::TryCast<double> (CastBigintToFloating) */
+static double hugeint_to_double(uint64_t lo, int64_t hi) {
+  if (hi == -1) return -(double)(0xffffffffffffffffull - lo) - 1.0;
+  return (double)lo + (double)hi * 18446744073709551616.0;
+}
+static double int128_to_double(__int128 x) { return hugeint_to_double((uint64_t)x, (int64_t)(x >> 64)); }
+
+static const double DOUBLE_POW10[39] = {
+    1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19,
+    1e20, 1e21, 1e22, 1e23, 1e24, 1e25, 1e26, 1e27, 1e28, 1e29, 1e30, 1e31, 1e32, 1e33, 1e34, 1e35, 1e36, 1e37, 1e38};
+static __int128 pow10_i128(int scale) {
+  __int128 p = 1;
+  for (int k = 0; k < scale && k < 38; k++) p *= 10;
+  return p;
+}
+static __int128 decimal_stored(const ora_column *c, const uint8_t *p) {
+  switch (c->phys) {
+    case P_I16: { int16_t v; memcpy(&v, p, 2); return v; }
+    case P_I32: { int32_t v; memcpy(&v, p, 4); return v; }
+    case P_I64: { int64_t v; memcpy(&v, p, 8); return v; }
+    default: { ora_hugeint v; memcpy(&v, p, 16); return ((__int128)v.hi << 64) | (__int128)(unsigned __int128)v.lo; }
+  }
+}
+/* TryCastFromDecimal -> integer: round half away from zero, truncating division; out of range -> the cast fails -> 0 */
+static int64_t decimal_to_i64(const ora_column *c, const uint8_t *p) {
+  __int128 power = pow10_i128(c->dec_scale), x = decimal_stored(c, p);
+  __int128 rounding = (x < 0 ? -power : power) / 2;
+  __int128 q = (x + rounding) / power;
+  return (q >= -(__int128)9223372036854775807ll - 1 && q <= (__int128)9223372036854775807ll) ? (int64_t)q : 0;
+}
+/* TryCastDecimalToFloatingPoint: exact integers (|x| <= 2^53) or scale 0 divide directly, the rest split in two */
+static double decimal_to_double(const ora_column *c, const uint8_t *p) {
+  __int128 x = decimal_stored(c, p);
+  int scale = c->dec_scale < 0 ? 0 : (c->dec_scale > 38 ? 38 : c->dec_scale);
+  double dp = DOUBLE_POW10[scale];
+  if (scale == 0 || (x <= (__int128)9007199254740992ll && x >= -(__int128)9007199254740992ll)) return int128_to_double(x) / dp;
+  __int128 power = pow10_i128(scale);
+  return int128_to_double(x / power) + int128_to_double(x % power) / dp;
+}
+
 __attribute__((noinline)) int64_t ora_value_int64(ora_result *r, int32_t col, int64_t row) {
   if (!r->materialised) ora_materialise(r);
   if (col < 0 || col >= r->column_count || row < 0 || row >= r->nrows) return 0;
   if (r->dep_null[col][row]) return 0;
   const ora_column *c = &r->batch.cols[col];
   const uint8_t *p = r->dep_data[col] + (size_t)row * (size_t)PHYS_W[c->phys];
+  if (!numeric_castable(c)) return 0;
+  if (c->type_id == T_DECIMAL) return decimal_to_i64(c, p); /* UNPINNED */
   switch (c->phys) {
     case P_BOOL: return *(const uint8_t *)p ? 1 : 0;
     case P_I8: return *(const int8_t *)p;
@@ -211,6 +267,8 @@ __attribute__((noinline)) int64_t ora_value_int64(ora_result *r, int32_t col, in
     case P_I128: { ora_hugeint v; memcpy(&v, p, 16);                                                 /* UNPINNED */
       int fits = (v.hi == 0 && (int64_t)v.lo >= 0) || (v.hi == -1 && (int64_t)v.lo < 0);
       return fits ? (int64_t)v.lo : 0; }
+    case P_U128: { ora_hugeint v; memcpy(&v, p, 16);                                                 /* UNPINNED: UHUGEINT */
+      return (v.hi == 0 && v.lo <= 0x7fffffffffffffffull) ? (int64_t)v.lo : 0; }
     default: return 0;
   }
 }
@@ -221,11 +279,14 @@ __attribute__((noinline)) double ora_value_double(ora_result *r, int32_t col, in
   if (r->dep_null[col][row]) return 0.0;
   const ora_column *c = &r->batch.cols[col];
   const uint8_t *p = r->dep_data[col] + (size_t)row * (size_t)PHYS_W[c->phys];
+  if (!numeric_castable(c)) return 0.0;
+  if (c->type_id == T_DECIMAL) return decimal_to_double(c, p); /* UNPINNED */
   switch (c->phys) {
     case P_F64: { double v; memcpy(&v, p, 8); return v; }
     case P_F32: { float v; memcpy(&v, p, 4); return (double)v; }
     case P_U64: { uint64_t v; memcpy(&v, p, 8); return (double)v; }
-    case P_I128: case P_U128: case P_INTERVAL: case P_STRING: return 0.0;
+    case P_I128: { ora_hugeint v; memcpy(&v, p, 16); return hugeint_to_double(v.lo, v.hi); }          /* UNPINNED: what SUM() returns */
+    case P_U128: { ora_hugeint v; memcpy(&v, p, 16); return (double)v.lo + (double)(uint64_t)v.hi * 18446744073709551616.0; }
     default: return (double)ora_value_int64(r, col, row);
   }
 }
@@ -235,8 +296,11 @@ __attribute__((noinline)) int ora_value_boolean(ora_result *r, int32_t col, int6
   if (col < 0 || col >= r->column_count || row < 0 || row >= r->nrows) return 0;
   if (r->dep_null[col][row]) return 0;
   const ora_column *c = &r->batch.cols[col];
+  if (!numeric_castable(c)) return 0;
+  if (c->type_id == T_DECIMAL) return ora_value_int64(r, col, row) != 0; /* TryCastDecimalToNumeric<.., bool>: the rounded integer */
   if (c->phys == P_F32 || c->phys == P_F64) return ora_value_double(r, col, row) != 0.0;
   if (c->phys == P_U64) { uint64_t u; memcpy(&u, r->dep_data[col] + (size_t)row * 8, 8); return u != 0; }
+  if (c->phys == P_I128 || c->phys == P_U128) { ora_hugeint v; memcpy(&v, r->dep_data[col] + (size_t)row * 16, 16); return (v.lo | (uint64_t)v.hi) != 0; }
   return ora_value_int64(r, col, row) != 0;
 }
 
@@ -621,7 +685,8 @@ int64_t ora_decode_string(const uint8_t *data, int64_t len, int nullable, int64_
  * Appendix A): LSB validity bitmap, dense little-endian values, NULL slots zero, NULL strings
  * zero-length.  dst kinds mirror enum dmb_dst of include/duckdb_mb_gpu.h. */
 enum { D_SAME, D_I32_TRUNC, D_I64, D_F64, D_BOOL_BYTE, D_BOOL_BITS, D_I128, D_I32_SAT,
-       D_TS_US_FROM_S, D_TS_US_FROM_MS, D_TS_US_FROM_NS, D_MONTH_DAY_NANO, D_DATE_REF };
+       D_TS_US_FROM_S, D_TS_US_FROM_MS, D_TS_US_FROM_NS, D_MONTH_DAY_NANO, D_DATE_REF,
+       D_DEC_I64 = 17, D_DEC_I32_TRUNC = 18, D_DEC_F64 = 19, D_DEC_BOOL_BYTE = 20 };
 
 static int64_t load_i64(const ora_column *c, const uint8_t *p, int *ok) {
   *ok = 1;
@@ -640,6 +705,8 @@ static int64_t load_i64(const ora_column *c, const uint8_t *p, int *ok) {
     case P_I128: { ora_hugeint v; memcpy(&v, p, 16);
       int fits = (v.hi == 0 && (int64_t)v.lo >= 0) || (v.hi == -1 && (int64_t)v.lo < 0);
       if (!fits) { *ok = 0; return 0; } return (int64_t)v.lo; }
+    case P_U128: { ora_hugeint v; memcpy(&v, p, 16);
+      if (!(v.hi == 0 && v.lo <= 0x7fffffffffffffffull)) { *ok = 0; return 0; } return (int64_t)v.lo; }
     default: *ok = 0; return 0;
   }
 }
@@ -1095,15 +1162,22 @@ int ora_arrow_fixed(ora_result *r, int32_t col, int dst, uint8_t *out_values, ui
             if (c->phys == P_F64) memcpy(&x, p, 8);
             else if (c->phys == P_F32) { float f; memcpy(&f, p, 4); x = (double)f; }
             else if (c->phys == P_U64) { uint64_t u; memcpy(&u, p, 8); x = (double)u; }
+            else if (c->phys == P_I128) { ora_hugeint h; memcpy(&h, p, 16); x = hugeint_to_double(h.lo, h.hi); }
+            else if (c->phys == P_U128) { ora_hugeint h; memcpy(&h, p, 16); x = (double)h.lo + (double)(uint64_t)h.hi * 18446744073709551616.0; }
             else x = (double)load_i64(c, p, &ok);
           }
           memcpy(out_values + row * 8, &x, 8); break; }
+        case D_DEC_I64: { int64_t x = isnull ? 0 : decimal_to_i64(c, p); memcpy(out_values + row * 8, &x, 8); break; }
+        case D_DEC_I32_TRUNC: { int32_t x = isnull ? 0 : (int32_t)decimal_to_i64(c, p); memcpy(out_values + row * 4, &x, 4); break; }
+        case D_DEC_F64: { double x = isnull ? 0.0 : decimal_to_double(c, p); memcpy(out_values + row * 8, &x, 8); break; }
+        case D_DEC_BOOL_BYTE: out_values[row] = (uint8_t)(!isnull && decimal_to_i64(c, p) != 0); break;
         case D_BOOL_BYTE: {
           uint8_t x = 0;
           if (!isnull) {
             if (c->phys == P_F64) { double d; memcpy(&d, p, 8); x = d != 0.0; }
             else if (c->phys == P_F32) { float f; memcpy(&f, p, 4); x = f != 0.0f; }
             else if (c->phys == P_U64) { uint64_t u; memcpy(&u, p, 8); x = u != 0; }
+            else if (c->phys == P_I128 || c->phys == P_U128) { ora_hugeint h; memcpy(&h, p, 16); x = (h.lo | (uint64_t)h.hi) != 0; }
             else x = load_i64(c, p, &ok) != 0;
           }
           out_values[row] = x; break; }

@@ -51,11 +51,11 @@ def test_struct_layouts():
     assert C.sizeof(nat.ArrowArray) == 80 and C.sizeof(nat.ArrowSchema) == 72  # Arrow C Data Interface
     assert C.sizeof(nat.VecDesc) == 16
     assert C.sizeof(nat.FixedJob) == 64
-    assert C.sizeof(nat.StringJob) == 104
+    assert C.sizeof(nat.StringJob) == 112
     assert C.sizeof(nat.RevFixedJob) == 56
     assert C.sizeof(nat.RevStringJob) == 72
     assert C.sizeof(nat.HostColumn) == 72 and C.sizeof(nat.HostList) == 40 and C.sizeof(nat.HostBatch) == 32
-    assert C.sizeof(nat.EnumDict) == 24 and C.sizeof(nat.EnumJob) == 72 and C.sizeof(nat.ListJob) == 104
+    assert C.sizeof(nat.EnumDict) == 24 and C.sizeof(nat.EnumJob) == 72 and C.sizeof(nat.ListJob) == 112
     assert C.sizeof(nat.TypedColumn) == 56
 
 

@@ -61,8 +61,6 @@ def test_reference_getters_bit_exact(ctx, n, pattern):
             if c.phys in (ch.P_U128, ch.P_INTERVAL):
                 continue  # libduckdb casts of UUID/INTERVAL to numbers are errors; not on the path
             for kind in KINDS:
-                if c.phys == ch.P_I128 and kind in ("double", "bool"):
-                    continue  # oracle leaves these UNPINNED casts at 0; covered by the zero-fill test below
                 for nullable in (False, True):
                     got = res.raw_column(kind, col, nullable)
                     exp = ora.get_column(kind, col, nullable)
@@ -394,3 +392,35 @@ def test_typed_reference_vectors(ctx):
     zero[0, 15] = 0x80  # stored with the top bit flipped
     with _result(ctx, ch.ChunkBatch(one, [ch.fixed_column("h", ch.T_UUID, zero, one)])) as res:
         assert tr.typed_column(res, 0).value(0).as_string() == "00000000-0000-0000-0000-000000000000"
+
+
+def test_aliased_string_pointers_are_sized_by_a_second_launch(ctx):
+    """string_t entries of a flattened dictionary / constant vector point at the SAME heap bytes, so the column's bytes
+    are not bounded by 12 n + heap_len: the kernels must not write past the first-guess buffer (round-1 advice) and the
+    host sizes a second launch from the total the first one reports."""
+    n = 50_000
+    counts = ch.chunk_counts(n)
+    words = [b"the quick brown fox jumps over the lazy dog", b"lorem ipsum dolor sit amet, consectetur", b"short"]
+    col = ch.string_column("s", [words[i % 3] for i in range(3)] + [b"x"] * (n - 3), counts)
+    ent = col.data.reshape(-1, 16)
+    ent[:n] = ent[np.arange(n) % 3]  # every row is one of the three entries: 2/3 of them pointers into 82 heap bytes
+    batch = ch.ChunkBatch(counts, [col])
+    ora = oracle.OracleResult(batch)
+    eo, ed = ora.arrow_string(0, 0)
+    assert ed.shape[0] > 12 * n + col.heap.shape[0]
+    with _result(ctx, batch) as res:
+        (a,) = res.to_arrow()
+        assert np.array_equal(np.frombuffer(a.buffers()[1], dtype=np.int32)[: n + 1], eo)
+        assert bytes(a.buffers()[2])[: ed.shape[0]] == ed.tobytes()
+        assert res.raw_column("string", 0, True) == ora.get_column("string", 0, True)
+    # L0: the capacity check itself -- flag 8, nothing written past the capacity, exact total reported
+    from duckdb_mbt_b200 import device
+    db = device.DeviceBatch(batch)
+    cap = 12 * n + col.heap.shape[0]
+    so = db.plan_string(0, 0, data_capacity=cap)
+    so.data[cap:] = 0xEE
+    so.job.out_data_cap = cap
+    db.run_string(so)
+    assert db.string_error(so) & 8
+    assert int(device.to_numpy(so.total, np.uint64)[0]) == ed.shape[0]
+    assert bool((so.data[cap:] == 0xEE).all().item())

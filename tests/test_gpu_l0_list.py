@@ -24,7 +24,7 @@ def _dev(a: np.ndarray, pad: int = 64):
     return t
 
 
-def _run(lc, large):
+def _run(lc, large, with_sizes=False):
     L = nat.lib()
     n = int(lc.counts.sum())
     nch = lc.counts.shape[0]
@@ -46,6 +46,9 @@ def _run(lc, large):
                       d["child_data"].data_ptr(), d["child_validity"].data_ptr(), d["child_val_off"].data_ptr(),
                       out_off.data_ptr(), out_child.data_ptr(), out_bm.data_ptr(), ctr.data_ptr(), ctr.data_ptr() + 8,
                       lc.width, 1 if large else 0)
+    if with_sizes:
+        d["child_sizes"] = _dev(lc.child_sizes)
+        job.child_sizes = d["child_sizes"].data_ptr()
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     nat.check(L.dmb_dev_list_batch(C.byref(job), d["counts"].data_ptr(), d["row_off"].data_ptr(), nch, n, cap, scratch.data_ptr(), st), "list")
     torch.cuda.synchronize()
@@ -198,3 +201,20 @@ def test_list_and_enum_edge_cases_through_the_host_api():
             assert arr.null_count == 100 and len(arr.dictionary) == 0
             strs, valid = res.get_column_string_nullable(0)
             assert not any(valid)
+
+
+def test_list_entry_outside_its_child_vector_is_flagged_not_followed():
+    """round-1 advice: a malformed / stale entry (offset + length past duckdb_list_vector_get_size) must raise an error,
+    never read outside the staged child slab; host API: an error, not a result"""
+    from duckdb_mbt_b200 import arrow_result as ar
+    lc = list_cases.make_list_column(6000, 4, "full", 31, "contiguous", null_frac=0.0)
+    offs, child, bm, total, nulls, flags = _run(lc, False, with_sizes=True)
+    assert flags == 0 and total == lc.capacity
+    ent = lc.entries.view(np.uint64).reshape(-1, 2)
+    ent[2048 + 5] = (int(lc.child_sizes[1]) - 1, 7)  # chunk 1, row 5: reaches 6 elements past its child vector
+    offs, child, bm, total, nulls, flags = _run(lc, False, with_sizes=True)
+    assert flags & 8
+    batch = ch.ChunkBatch(lc.counts, [list_cases.as_column(lc, "l", ch.T_INTEGER)])
+    with ar.GpuContext(0) as ctx, ar.ArrowResult.from_chunks(ctx, batch) as res:
+        with pytest.raises(ar.DuckDBError, match="outside its chunk's child vector"):
+            res.to_arrow(0)

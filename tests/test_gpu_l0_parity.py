@@ -78,6 +78,8 @@ ALL_SPECS = (
     + [(c, ch.D_F64) for c in range(0, 11)] + [(c, ch.D_BOOL_BYTE) for c in range(0, 11)]
     + [(0, ch.D_BOOL_BITS)]
     + [(c, ch.D_I128) for c in (11, 12, 13, 14)]
+    + [(11, ch.D_F64), (11, ch.D_BOOL_BYTE), (20, ch.D_I64), (20, ch.D_I32_TRUNC), (20, ch.D_F64), (20, ch.D_BOOL_BYTE)]  # HUGEINT / 128-bit unsigned
+    + [(c, d) for c in (12, 13, 14) for d in (ch.D_DEC_I64, ch.D_DEC_I32_TRUNC, ch.D_DEC_F64, ch.D_DEC_BOOL_BYTE)]
     + [(c, ch.D_I32_SAT) for c in range(1, 9)]
     + [(16, ch.D_TS_US_FROM_S), (17, ch.D_TS_US_FROM_MS), (18, ch.D_TS_US_FROM_NS)]
     + [(19, ch.D_MONTH_DAY_NANO), (15, ch.D_DATE_REF), (4, ch.OP_VALIDITY_ONLY)]

@@ -432,3 +432,45 @@ def test_oracle_list_export_is_a_valid_arrow_list(layout, width):
     arr = pa.Array.from_buffers(pa.list_(pa.binary(width)), len(lc.valid), [pa.py_buffer(pbits), pa.py_buffer(offsets.tobytes())], children=[values])
     arr.validate(full=True)
     assert arr.to_pylist() == lc.expected
+
+
+# ------------------------------------------------------------------ casts by logical type (round-1 advice)
+def test_getters_cast_by_logical_type_known_answers():
+    """duckdb_value_int64 / _double / _boolean switch on the LOGICAL column type: DECIMAL is scaled (round half away
+    from zero for integers, value / 10^scale for double), HUGEINT (what SUM() returns) reads as a double, and DATE /
+    TIMESTAMP have no cast to a number, so they read as 0.  Known answers worked out by hand from DuckDB's
+    TryCastFromDecimal / Hugeint::TryCast (UNPINNED: libduckdb is not in this image)."""
+    dec = [123, 150, -150, -49, 50, 249, None, 10**17 + 5]          # DECIMAL(18,2): 1.23 1.50 -1.50 -0.49 0.50 2.49 NULL 1e15+0.05
+    huge = np.zeros((8, 16), dtype=np.uint8)
+    hv = [0, 1, -1, 2**64, -(2**64), 2**63, 2**100 + 12345, -(2**53) - 1]
+    for i, v in enumerate(hv):
+        huge[i] = np.frombuffer((v & (2**128 - 1)).to_bytes(16, "little"), dtype=np.uint8)
+    counts = ch.chunk_counts(8)
+    b = batch_of(("d", ch.T_DECIMAL, dec, 18, 2), ("day", ch.T_DATE, [19877] * 8), ("ts", ch.T_TIMESTAMP, [10**15] * 8))
+    b.columns.append(ch.fixed_column("h", ch.T_HUGEINT, huge, counts))
+    b.columns.append(ch.fixed_column("d38", ch.T_DECIMAL, huge, counts, dec_width=38, dec_scale=3))
+    r = oracle.OracleResult(b)
+    i64 = np.frombuffer(r.get_column("int64", 0)[4:], dtype="<i8")
+    assert i64.tolist() == [1, 2, -2, 0, 1, 2, 0, 10**15]
+    i32 = np.frombuffer(r.get_column("int32", 0)[4:], dtype="<i4")
+    assert i32.tolist() == [1, 2, -2, 0, 1, 2, 0, np.int64(10**15).astype(np.int32)]
+    f64 = np.frombuffer(r.get_column("double", 0)[4:], dtype="<f8")
+    assert f64.tolist() == [1.23, 1.5, -1.5, -0.49, 0.5, 2.49, 0.0, 1e15 + 0.05]
+    bl = np.frombuffer(r.get_column("bool", 0)[4:], dtype=np.uint8)
+    assert bl.tolist() == [1, 1, 1, 0, 1, 1, 0, 1]
+    for col in (1, 2):  # DATE, TIMESTAMP: no numeric cast in libduckdb -> 0
+        for kind, dt in (("int32", "<i4"), ("int64", "<i8"), ("double", "<f8")):
+            assert not np.frombuffer(r.get_column(kind, col)[4:], dtype=dt).any()
+    h64 = np.frombuffer(r.get_column("int64", 3)[4:], dtype="<i8")
+    assert h64.tolist() == [0, 1, -1, 0, 0, 0, 0, -(2**53) - 1]  # out of the int64 range: the cast fails -> 0
+    hf = np.frombuffer(r.get_column("double", 3)[4:], dtype="<f8")
+    assert hf.tolist() == [0.0, 1.0, -1.0, 2.0**64, -(2.0**64), 2.0**63, float(2**100 + 12345), float(-(2**53) - 1)]
+    # DECIMAL(38,3) on hugeint storage
+    d38 = np.frombuffer(r.get_column("int64", 4)[4:], dtype="<i8")
+    exp = []
+    for v in hv:
+        q = (abs(v) + 500) // 1000 * (1 if v >= 0 else -1)
+        exp.append(q if -(2**63) <= q < 2**63 else 0)
+    assert d38.tolist() == exp
+    d38f = np.frombuffer(r.get_column("double", 4)[4:], dtype="<f8")
+    assert d38f[1] == 0.001 and d38f[2] == -0.001 and d38f[5] == float(2**63 // 1000) + float(2**63 % 1000) / 1000.0
