@@ -256,6 +256,27 @@ class ArrowResult:
         valid = np.frombuffer(data, dtype=np.uint8, count=count, offset=8 + total) != 0
         return out, valid
 
+    def get_column_string_spans_nullable(self, col: int):
+        """The nullable string decoder's scan (:752-784) without building a String per row: (starts, ends, valid, blob)
+        with row i = blob[starts[i]:ends[i]].  Row i ends at the i-th NUL at or after byte 8 (or at the end of the blob)."""
+        data = self.raw_column("string", col, True)
+        count = self._count_ok(data, 8)
+        z = np.zeros(0, dtype=np.int64)
+        if not count:
+            return z, z, np.zeros(0, dtype=bool), data
+        total = _read_int32_le(data, 4)
+        if len(data) < 8 + total + count:
+            return z, z, np.zeros(0, dtype=bool), data
+        buf = np.frombuffer(data, dtype=np.uint8)
+        nul = np.flatnonzero(buf[8:] == 0)[:count].astype(np.int64) + 8
+        ends = np.full(count, len(data), dtype=np.int64)
+        ends[: nul.shape[0]] = nul
+        starts = np.empty(count, dtype=np.int64)
+        starts[0] = 8
+        starts[1:] = np.minimum(ends[:-1] + 1, len(data))
+        valid = np.frombuffer(data, dtype=np.uint8, count=count, offset=8 + total) != 0
+        return starts, ends, valid, data
+
     def get_column_string(self, col: int) -> List[str]:  # :546-575
         return self._decode_strings(self.raw_column("string", col), False)
 

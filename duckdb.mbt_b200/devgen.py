@@ -172,6 +172,37 @@ class GeneratedBatch(DeviceBatch):
         torch.cuda.synchronize(self.device)
         return ch.ChunkBatch(counts, cols)
 
+    def window_to_host(self, c0: int, c1: int) -> ch.ChunkBatch:
+        """Chunks [c0, c1) as a host ChunkBatch (pageable numpy): what a parity check hands to the CPU oracle.  Pointer
+        strings are re-pointed at a host copy of the window's heap span, so the oracle dereferences real addresses."""
+        k = c1 - c0
+        counts = self.counts.view(torch.int32)[c0:c1].cpu().numpy().astype(np.uint32)
+        cols = []
+        for j, c in enumerate(self.batch.columns):
+            w = c.width
+            data = self.data[j][c0 * VS * w: c1 * VS * w].cpu().numpy().copy()
+            validity, val_off = None, np.full(k, -1, dtype=np.int64)
+            if self.validity[j] is not None:
+                validity = self.validity[j][c0 * 256: c1 * 256].cpu().numpy().copy().view(np.uint64)
+                val_off = np.arange(k, dtype=np.int64) * ch.VALIDITY_WORDS
+            heap = None
+            if c.phys == ch.P_STRING:
+                ent = data.reshape(-1, 16)
+                lens = ent[:, 0:4].copy().view(np.uint32).reshape(-1)
+                ptrs = ent[:, 8:16].copy().view(np.uint64).reshape(-1)
+                isp = lens > 12
+                if isp.any():
+                    base = np.uint64(c.heap_base)
+                    lo = int(ptrs[isp].min() - base)
+                    hi = int((ptrs[isp] + lens[isp].astype(np.uint64)).max() - base)
+                    heap = np.zeros(hi - lo + 16, dtype=np.uint8)
+                    heap[: hi - lo] = self.heap[j][lo:hi].cpu().numpy()
+                    new = ptrs[isp] - (base + np.uint64(lo)) + np.uint64(heap.ctypes.data)
+                    ent[isp, 8:16] = new.view(np.uint8).reshape(-1, 8)
+            cols.append(ch.Column(c.name, c.type_id, c.phys, data, np.arange(k, dtype=np.uint64) * np.uint64(VS * w), validity, val_off,
+                                  c.dec_width, c.dec_scale, heap))
+        return ch.ChunkBatch(counts, cols)
+
     # ---- algorithmic bytes (SURVEY.md §8d)
     def alg_bytes_fixed(self, plan) -> int:
         total = 0

@@ -424,3 +424,13 @@ def test_aliased_string_pointers_are_sized_by_a_second_launch(ctx):
     assert db.string_error(so) & 8
     assert int(device.to_numpy(so.total, np.uint64)[0]) == ed.shape[0]
     assert bool((so.data[cap:] == 0xEE).all().item())
+
+
+def test_string_spans_decoder_equals_the_string_decoder(ctx):
+    batch = _with_strings(5000, "ragged", 77)
+    col = len(batch.columns) - 2
+    with _result(ctx, batch) as res:
+        strs, valid = res.get_column_string_nullable(col)
+        starts, ends, valid2, blob = res.get_column_string_spans_nullable(col)
+        assert np.array_equal(valid, valid2)
+        assert [blob[s:e].decode("utf-8", errors="replace") for s, e in zip(starts, ends)] == strs
