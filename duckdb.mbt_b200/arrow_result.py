@@ -14,6 +14,7 @@ No CPU fallback: every call goes through the CUDA library or raises.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import json
 from dataclasses import dataclass
@@ -176,6 +177,13 @@ class ArrowResult:
         fn = getattr(self.lib, f"duckdb_mb_arrow_get_column_{kind}{'_nullable' if nullable else ''}")
         return nat.moonbit_bytes(fn(self.handle, col))
 
+    def _blob(self, kind: str, col: int, nullable: bool = False) -> "nat.MoonbitBlob":
+        """the getter's Bytes viewed in place (a numpy uint8 array inside a `with` block): decoded without a second copy"""
+        if getattr(self, "lib", None) is None:  # a subclass that serves blobs itself (tests of the decoder rules)
+            return contextlib.nullcontext(self.raw_column(kind, col, nullable))
+        fn = getattr(self.lib, f"duckdb_mb_arrow_get_column_{kind}{'_nullable' if nullable else ''}")
+        return nat.MoonbitBlob(fn(self.handle, col))
+
     @staticmethod
     def _count_ok(data: bytes, header: int) -> int:
         if len(data) < header:
@@ -183,48 +191,60 @@ class ArrowResult:
         count = _read_int32_le(data, 0)
         return 0 if (count <= 0 or count > DECODER_ROW_CAP) else count
 
-    def _decode_fixed(self, data: bytes, width: int, dtype, nullable: bool):
+    def _decode_fixed(self, data, width: int, dtype, nullable: bool, copy: bool = True):
+        """data: the blob (bytes, or the in-place numpy view of _blob).  copy=False only when the caller derives a new
+        array from the values before the blob is freed."""
         count = self._count_ok(data, 4)
         if not count or len(data) < 4 + count * width + (count if nullable else 0):
             return (np.zeros(0, dtype=dtype), np.zeros(0, dtype=bool)) if nullable else np.zeros(0, dtype=dtype)
-        values = np.frombuffer(data, dtype=dtype, count=count, offset=4).copy()
+        values = np.frombuffer(data, dtype=dtype, count=count, offset=4)
+        if copy:
+            values = values.copy()
         if not nullable:
             return values
         valid = np.frombuffer(data, dtype=np.uint8, count=count, offset=4 + count * width) != 0
         return values, valid
 
     def get_column_int32(self, col: int) -> np.ndarray:  # :421-449
-        return self._decode_fixed(self.raw_column("int32", col), 4, np.dtype("<i4"), False)
+        with self._blob("int32", col) as b:
+            return self._decode_fixed(b, 4, np.dtype("<i4"), False)
 
     def get_column_int32_nullable(self, col: int):  # :619-652
-        return self._decode_fixed(self.raw_column("int32", col, True), 4, np.dtype("<i4"), True)
+        with self._blob("int32", col, True) as b:
+            return self._decode_fixed(b, 4, np.dtype("<i4"), True)
 
     def get_column_int64(self, col: int) -> np.ndarray:
         """MoonBit `Int` is 32-bit on the native target: the byte-assembled value keeps the low 32
         bits of each int64 (:465-505)."""
-        v = self._decode_fixed(self.raw_column("int64", col), 8, np.dtype("<i8"), False)
-        return v.astype(np.int32)  # wraps: low 32 bits
+        with self._blob("int64", col) as b:
+            v = self._decode_fixed(b, 8, np.dtype("<i8"), False, copy=False)
+            return v.astype(np.int32)  # wraps: low 32 bits
 
     def get_column_int64_nullable(self, col: int):  # :655-704
-        v, valid = self._decode_fixed(self.raw_column("int64", col, True), 8, np.dtype("<i8"), True)
-        return v.astype(np.int32), valid
+        with self._blob("int64", col, True) as b:
+            v, valid = self._decode_fixed(b, 8, np.dtype("<i8"), True, copy=False)
+            return v.astype(np.int32), valid
 
     def get_column_int64_exact(self, col: int, nullable: bool = False):
         """Additive: the full 64-bit values of the same blob."""
         return self._decode_fixed(self.raw_column("int64", col, nullable), 8, np.dtype("<i8"), nullable)
 
     def get_column_double(self, col: int) -> np.ndarray:  # :508-543
-        return self._decode_fixed(self.raw_column("double", col), 8, np.dtype("<f8"), False)
+        with self._blob("double", col) as b:
+            return self._decode_fixed(b, 8, np.dtype("<f8"), False)
 
     def get_column_double_nullable(self, col: int):  # :707-741
-        return self._decode_fixed(self.raw_column("double", col, True), 8, np.dtype("<f8"), True)
+        with self._blob("double", col, True) as b:
+            return self._decode_fixed(b, 8, np.dtype("<f8"), True)
 
     def get_column_bool(self, col: int) -> np.ndarray:  # :579-603
-        return self._decode_fixed(self.raw_column("bool", col), 1, np.uint8, False) != 0
+        with self._blob("bool", col) as b:
+            return self._decode_fixed(b, 1, np.uint8, False, copy=False) != 0
 
     def get_column_bool_nullable(self, col: int):  # :790-822
-        v, valid = self._decode_fixed(self.raw_column("bool", col, True), 1, np.uint8, True)
-        return v != 0, valid
+        with self._blob("bool", col, True) as b:
+            v, valid = self._decode_fixed(b, 1, np.uint8, True, copy=False)
+            return v != 0, valid
 
     def _decode_strings(self, data: bytes, nullable: bool):
         """NUL scan from byte 8 (:559-574, :752-784); lossy UTF-8 decode like decode_lossy."""
@@ -259,7 +279,8 @@ class ArrowResult:
     def get_column_string_spans_nullable(self, col: int):
         """The nullable string decoder's scan (:752-784) without building a String per row: (starts, ends, valid, blob)
         with row i = blob[starts[i]:ends[i]].  Row i ends at the i-th NUL at or after byte 8 (or at the end of the blob)."""
-        data = self.raw_column("string", col, True)
+        with self._blob("string", col, True) as view:
+            data = view.copy()  # the decoded column: one copy of the stream + the spans into it
         count = self._count_ok(data, 8)
         z = np.zeros(0, dtype=np.int64)
         if not count:
@@ -267,14 +288,13 @@ class ArrowResult:
         total = _read_int32_le(data, 4)
         if len(data) < 8 + total + count:
             return z, z, np.zeros(0, dtype=bool), data
-        buf = np.frombuffer(data, dtype=np.uint8)
-        nul = np.flatnonzero(buf[8:] == 0)[:count].astype(np.int64) + 8
+        nul = np.flatnonzero(data[8:] == 0)[:count].astype(np.int64) + 8
         ends = np.full(count, len(data), dtype=np.int64)
         ends[: nul.shape[0]] = nul
         starts = np.empty(count, dtype=np.int64)
         starts[0] = 8
         starts[1:] = np.minimum(ends[:-1] + 1, len(data))
-        valid = np.frombuffer(data, dtype=np.uint8, count=count, offset=8 + total) != 0
+        valid = data[8 + total: 8 + total + count] != 0
         return starts, ends, valid, data
 
     def get_column_string(self, col: int) -> List[str]:  # :546-575

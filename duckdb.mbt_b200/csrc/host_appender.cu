@@ -61,6 +61,8 @@ struct duckdb_mb_gpu_appender {
   std::vector<int32_t> type_ids;
   dmb_chunk_sink sink = nullptr;
   void *user = nullptr;
+  dmb_appender_flush_hook on_flush = nullptr;      // glue: duckdb_appender_flush after the chunks have been handed over
+  dmb_appender_destroy_hook on_destroy = nullptr;  // glue: duckdb_appender_destroy + free of `user`
   int state = kNotCreated;
   int cur_col = 0;
   int64_t row_count = 0, flushed_row_count = 0, buffered_rows = 0;
@@ -482,7 +484,17 @@ extern "C" duckdb_mb_gpu_appender *duckdb_mb_gpu_appender_create(duckdb_mb_gpu_c
   return a;
 }
 
-extern "C" void duckdb_mb_gpu_appender_destroy(duckdb_mb_gpu_appender *a) { delete a; }
+extern "C" void duckdb_mb_gpu_appender_destroy(duckdb_mb_gpu_appender *a) {
+  if (!a) return;
+  if (a->on_destroy) a->on_destroy(a->user);
+  delete a;
+}
+
+extern "C" void duckdb_mb_gpu_appender_set_hooks(duckdb_mb_gpu_appender *a, dmb_appender_flush_hook on_flush, dmb_appender_destroy_hook on_destroy) {
+  if (!a) return;
+  a->on_flush = on_flush;
+  a->on_destroy = on_destroy;
+}
 
 extern "C" moonbit_bytes_t duckdb_mb_gpu_appender_error(duckdb_mb_gpu_appender *a) {
   const char *msg = a ? a->error : "";
@@ -751,6 +763,7 @@ extern "C" int32_t duckdb_mb_gpu_appender_flush(duckdb_mb_gpu_appender *a) {
   if (!a) { set_error("null appender"); return 0; }
   if (a->state != kReady && a->state != kFlushed) return illegal(a, "flush");
   if (!flush_rows(a)) { a->state = kError; return 0; }
+  if (a->on_flush && !a->on_flush(a->user)) { fail(a, "flush: the sink's flush hook failed"); a->state = kError; return 0; }
   a->flushed_row_count = a->row_count;
   a->state = kFlushed;
   return 1;
@@ -778,4 +791,87 @@ extern "C" int32_t duckdb_mb_gpu_appender_link_bytes(duckdb_mb_gpu_appender *a, 
   out2[0] = a->bytes_h2d;
   out2[1] = a->bytes_d2h;
   return 1;
+}
+
+// =====================================================================================  L2 drop-in: the appender set
+// The reference's own symbols (src/duckdb_native.c:1083-1251, 1313-1533, 1735-1926; MoonBit externs
+// src/duckdb_native.mbt:44-110,134-144,165-217,266-288) with the reference's signatures: `duckdb_mb_appender` is this
+// library's appender handle, Bytes arrive as moonbit_bytes_t (length from the object header, Moonbit_array_length),
+// Array[Bytes] as moonbit_bytes_t*.  All parameters are #borrow: nothing is decref'd.  duckdb_mb_appender_create itself
+// needs libduckdb (duckdb_appender_create) and lives in glue/duckdb_gpu_glue.c.
+extern "C" void duckdb_mb_appender_destroy(duckdb_mb_appender *a) {  // :1083-1091
+  if (!a) return;
+  duckdb_mb_gpu_appender_close(a);  // complete rows still reach the table, like duckdb_appender_destroy's implicit flush
+  duckdb_mb_gpu_appender_destroy(a);
+}
+extern "C" moonbit_bytes_t duckdb_mb_appender_error(duckdb_mb_appender *a) { return duckdb_mb_gpu_appender_error(a); }  // :1093-1098
+extern "C" int32_t duckdb_mb_is_null_appender(duckdb_mb_appender *a) { return a == nullptr ? 1 : 0; }                    // :1253-1255
+extern "C" int32_t duckdb_mb_begin_row(duckdb_mb_appender *a) { return duckdb_mb_gpu_begin_row(a); }                     // :1100
+extern "C" int32_t duckdb_mb_append_int(duckdb_mb_appender *a, int32_t v) { return duckdb_mb_gpu_append_int(a, v); }     // :1116
+extern "C" int32_t duckdb_mb_append_bigint(duckdb_mb_appender *a, int64_t v) { return duckdb_mb_gpu_append_bigint(a, v); }  // :1132
+extern "C" int32_t duckdb_mb_append_double(duckdb_mb_appender *a, double v) { return duckdb_mb_gpu_append_double(a, v); }   // :1148
+extern "C" int32_t duckdb_mb_append_varchar(duckdb_mb_appender *a, moonbit_bytes_t value) {                              // :1164
+  if (!a) return 0;
+  if (!value) { fail(a, "append_varchar: null Bytes"); return 0; }
+  return duckdb_mb_gpu_append_varchar(a, value, Moonbit_array_length(value));
+}
+extern "C" int32_t duckdb_mb_append_bool(duckdb_mb_appender *a, bool v) { return duckdb_mb_gpu_append_bool(a, v ? 1 : 0); }  // :1189
+extern "C" int32_t duckdb_mb_append_null(duckdb_mb_appender *a) { return duckdb_mb_gpu_append_null(a); }                 // :1205
+extern "C" int32_t duckdb_mb_end_row(duckdb_mb_appender *a) { return duckdb_mb_gpu_end_row(a); }                         // :1221
+extern "C" int32_t duckdb_mb_flush(duckdb_mb_appender *a) { return a ? duckdb_mb_gpu_appender_flush(a) : 0; }            // :1237
+// exact days / micros into the vectors: the reference's approximate-string path (:1299-1367) is a defect, not a contract
+extern "C" int32_t duckdb_mb_append_date(duckdb_mb_appender *a, int32_t days) { return duckdb_mb_gpu_append_date(a, days); }            // :1313
+extern "C" int32_t duckdb_mb_append_timestamp(duckdb_mb_appender *a, int64_t micros) { return duckdb_mb_gpu_append_timestamp(a, micros); }  // :1350
+extern "C" int32_t duckdb_mb_append_blob(duckdb_mb_appender *a, moonbit_bytes_t data, int32_t length) {                  // :1397
+  if (!a) return 0;
+  if (!data || length < 0 || length > Moonbit_array_length(data)) { fail(a, "append_blob: bad length"); return 0; }
+  return duckdb_mb_gpu_append_blob(a, data, length);
+}
+extern "C" int32_t duckdb_mb_append_decimal(duckdb_mb_appender *a, uint8_t width, uint8_t scale, int64_t lower, int64_t upper) {  // :1447
+  return duckdb_mb_gpu_append_decimal(a, width, scale, lower, upper);
+}
+extern "C" int32_t duckdb_mb_append_interval(duckdb_mb_appender *a, int32_t months, int32_t days, int64_t micros) {      // :1511
+  return duckdb_mb_gpu_append_interval(a, months, days, micros);
+}
+
+namespace {
+// Array[Bytes] (moonbit_bytes_t *) -> pointer + length tables
+bool bytes_array(duckdb_mb_gpu_appender *a, const char *cmd, moonbit_bytes_t *items, int32_t count, std::vector<const uint8_t *> *ptrs,
+                 std::vector<int32_t> *lens) {
+  if (count < 0 || (count > 0 && !items)) { fail(a, "%s: bad arguments", cmd); return false; }
+  ptrs->resize((size_t)count);
+  lens->resize((size_t)count);
+  for (int32_t i = 0; i < count; ++i) {
+    if (!items[i]) { fail(a, "%s: element %d is null", cmd, i); return false; }
+    (*ptrs)[(size_t)i] = items[i];
+    (*lens)[(size_t)i] = Moonbit_array_length(items[i]);
+  }
+  return true;
+}
+}  // namespace
+
+extern "C" int32_t duckdb_mb_append_list_varchar(duckdb_mb_appender *a, moonbit_bytes_t *values, int32_t count) {        // :1735
+  if (!a) return 0;
+  std::vector<const uint8_t *> p;
+  std::vector<int32_t> l;
+  if (!bytes_array(a, "append_list_varchar", values, count, &p, &l)) return 0;
+  return duckdb_mb_gpu_append_list_varchar(a, p.data(), l.data(), count);
+}
+extern "C" int32_t duckdb_mb_append_struct_varchar(duckdb_mb_appender *a, moonbit_bytes_t *field_names, moonbit_bytes_t *field_values,
+                                                  int32_t field_count) {                                                 // :1792
+  if (!a) return 0;
+  std::vector<const uint8_t *> pn, pv;
+  std::vector<int32_t> ln, lv;
+  if (!bytes_array(a, "append_struct_varchar", field_names, field_count, &pn, &ln) ||
+      !bytes_array(a, "append_struct_varchar", field_values, field_count, &pv, &lv)) return 0;
+  return duckdb_mb_gpu_append_struct_varchar(a, pn.data(), ln.data(), pv.data(), lv.data(), field_count);
+}
+extern "C" int32_t duckdb_mb_append_map_varchar_varchar(duckdb_mb_appender *a, moonbit_bytes_t *keys, moonbit_bytes_t *values,
+                                                       int32_t entry_count) {                                            // :1860
+  if (!a) return 0;
+  std::vector<const uint8_t *> pk, pv;
+  std::vector<int32_t> lk, lv;
+  if (!bytes_array(a, "append_map_varchar_varchar", keys, entry_count, &pk, &lk) ||
+      !bytes_array(a, "append_map_varchar_varchar", values, entry_count, &pv, &lv)) return 0;
+  return duckdb_mb_gpu_append_map_varchar_varchar(a, pk.data(), lk.data(), pv.data(), lv.data(), entry_count);
 }

@@ -3,6 +3,8 @@
 #pragma once
 
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -38,8 +40,32 @@ class Pool {
   size_t held_ = 0;
 };
 
+// Persistent host threads for the stager's gather memcpy (a 60 M-row pageable batch is ~650 ring fills: creating
+// 15 threads per fill cost more than the copies).  run(n, fn) calls fn(i) for i in [0, n) on the caller + the workers.
+class WorkerPool {
+ public:
+  WorkerPool() {}
+  ~WorkerPool();
+  void set_threads(int total) { total_ = total < 1 ? 1 : total; }  // participants, the caller included
+  int threads() const { return total_; }
+  void run(int64_t n, const std::function<void(int64_t)> &fn);
+
+ private:
+  void worker();
+  int total_ = 1;
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_job_, cv_done_;
+  const std::function<void(int64_t)> *fn_ = nullptr;
+  int64_t n_ = 0;
+  std::atomic<int64_t> next_{0};
+  uint64_t generation_ = 0;
+  int active_ = 0;
+  bool stop_ = false;
+};
+
 constexpr int kStageBuffers = 4;
-constexpr size_t kStageBytes = 16u << 20;  // per ring buffer
+constexpr size_t kStageBytes = 32u << 20;  // per ring buffer
 
 // Everything a result / exported Arrow array needs to outlive the ctx handle.
 struct CtxCore {
@@ -51,6 +77,7 @@ struct CtxCore {
   cudaEvent_t ring_free[kStageBuffers] = {nullptr, nullptr, nullptr, nullptr};
   int ring_next = 0;
   int stage_threads = 1;
+  WorkerPool pool;
   std::mutex mu;  // one blocking call at a time per context
   ~CtxCore();
   bool bind() const { return check_cuda(cudaSetDevice(device), "cudaSetDevice") == 0; }
@@ -65,27 +92,15 @@ struct duckdb_mb_gpu_ctx {
 
 namespace dmb {
 
-// run fn(i) for i in [0, n) on up to `threads` host threads (gather memcpy into pinned staging)
+// run fn(i) for i in [0, n) on the context's host threads (gather memcpy into pinned staging, size passes)
 template <typename F>
-inline void parallel_for(int64_t n, int threads, F fn) {
-  if (threads <= 1 || n < 2) {
+inline void parallel_for(CtxCore &core, int64_t n, F fn) {
+  if (core.stage_threads <= 1 || n < 2) {
     for (int64_t i = 0; i < n; ++i) fn(i);
     return;
   }
-  if (threads > n) threads = (int)n;
-  std::atomic<int64_t> next{0};
-  std::vector<std::thread> pool;
-  pool.reserve(threads - 1);
-  auto work = [&]() {
-    for (;;) {
-      int64_t i = next.fetch_add(1);
-      if (i >= n) break;
-      fn(i);
-    }
-  };
-  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
-  work();
-  for (auto &t : pool) t.join();
+  const std::function<void(int64_t)> f = fn;
+  core.pool.run(n, f);
 }
 
 // Copy per-chunk host pieces into a device slab whose slot k starts at dst + k * slot_bytes.

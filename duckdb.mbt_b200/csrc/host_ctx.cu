@@ -84,6 +84,65 @@ void Pool::release_all() {
   }
 }
 
+WorkerPool::~WorkerPool() {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    stop_ = true;
+  }
+  cv_job_.notify_all();
+  for (auto &t : workers_) t.join();
+}
+
+void WorkerPool::worker() {
+  uint64_t seen = 0;
+  for (;;) {
+    const std::function<void(int64_t)> *fn;
+    int64_t n;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_job_.wait(lk, [&] { return stop_ || generation_ != seen; });
+      if (stop_) return;
+      seen = generation_;
+      fn = fn_;
+      n = n_;
+    }
+    for (;;) {
+      const int64_t i = next_.fetch_add(1);
+      if (i >= n) break;
+      (*fn)(i);
+    }
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      if (--active_ == 0) cv_done_.notify_one();
+    }
+  }
+}
+
+void WorkerPool::run(int64_t n, const std::function<void(int64_t)> &fn) {
+  const int want = total_ - 1;
+  if (want <= 0 || n < 2) {
+    for (int64_t i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  while ((int)workers_.size() < want) workers_.emplace_back([this] { worker(); });  // (one blocking call at a time per context)
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    fn_ = &fn;
+    n_ = n;
+    next_.store(0);
+    active_ = (int)workers_.size();
+    ++generation_;
+  }
+  cv_job_.notify_all();
+  for (;;) {
+    const int64_t i = next_.fetch_add(1);
+    if (i >= n) break;
+    fn(i);
+  }
+  std::unique_lock<std::mutex> lk(mu_);
+  cv_done_.wait(lk, [&] { return active_ == 0; });
+}
+
 CtxCore::~CtxCore() {
   cudaSetDevice(device);
   if (s_in) cudaStreamSynchronize(s_in);
@@ -143,7 +202,7 @@ int32_t stage_pieces(CtxCore &core, cudaStream_t stream, const void *const *src,
     uint8_t *buf = core.ring[b];
     const int64_t npieces = m - k;
     const int64_t group = 64;  // pieces per parallel task
-    parallel_for((npieces + group - 1) / group, core.stage_threads, [&](int64_t g) {
+    parallel_for(core, (npieces + group - 1) / group, [&](int64_t g) {
       const int64_t i1 = (g + 1) * group < npieces ? (g + 1) * group : npieces;
       for (int64_t i = g * group; i < i1; ++i) {
         const int64_t c = k + i;
@@ -194,7 +253,7 @@ int32_t stage_contiguous(CtxCore &core, cudaStream_t stream, void *dst, const vo
     const size_t sub = 1u << 20;
     const int64_t nsub = (int64_t)((piece + sub - 1) / sub);
     const uint8_t *s = (const uint8_t *)src + off;
-    parallel_for(nsub, core.stage_threads, [&](int64_t i) {
+    parallel_for(core, nsub, [&](int64_t i) {
       const size_t o = (size_t)i * sub;
       memcpy(buf + o, s + o, piece - o < sub ? piece - o : sub);
     });
@@ -226,7 +285,8 @@ extern "C" duckdb_mb_gpu_ctx *duckdb_mb_gpu_ctx_create(int32_t device) {
     return nullptr;
   const char *env = getenv("DMB_STAGE_THREADS");
   int t = env ? atoi(env) : (int)std::thread::hardware_concurrency();
-  core->stage_threads = t < 1 ? 1 : (t > 16 ? 16 : t);
+  core->stage_threads = t < 1 ? 1 : (t > 32 ? 32 : t);
+  core->pool.set_threads(core->stage_threads);
   duckdb_mb_gpu_ctx *ctx = new duckdb_mb_gpu_ctx();
   ctx->core = core;
   return ctx;

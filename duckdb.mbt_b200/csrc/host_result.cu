@@ -91,6 +91,11 @@ struct Col {
   uint64_t heap_host_base = 0, d_heap_len = 0;
   cudaEvent_t ev_staged = nullptr;
   std::shared_ptr<ArrowColOut> arrow;
+  // reference packed blob of this column, complete in pinned memory (getter prefetch): kind = GetterKind or 4 = string
+  int gc_kind = -1;
+  bool gc_nullable = false;
+  uint8_t *gc_blob = nullptr;
+  size_t gc_bytes = 0;
   TypedOut typed;
   TypedOut text;  // VARCHAR rendering of the column (QueryResult's string form)
 };
@@ -114,6 +119,9 @@ struct duckdb_mb_arrow_result {
   std::vector<void *> dev_keep, pin_keep;  // staged inputs / typed outputs: freed when the result dies
   std::vector<cudaEvent_t> events;
   bool arrow_ready = false;
+  bool getters_prefetched = false;
+  void *owner = nullptr;  // the glue's duckdb_result + chunk handles
+  void (*owner_destroy)(void *) = nullptr;
   double t_h2d = 0, t_kernels = 0, t_d2h = 0, t_total = 0;
   uint64_t bytes_h2d = 0, bytes_d2h = 0;
 };
@@ -149,6 +157,7 @@ void free_result(Result *r) {
     for (cudaEvent_t e : r->events) cudaEventDestroy(e);
     r->cols.clear();  // ArrowColOut buffers go back to the pinned pool unless an export still holds them
   }
+  if (r->owner_destroy) r->owner_destroy(r->owner);  // after the last use of the host chunk pointers
   delete r;
 }
 
@@ -242,7 +251,7 @@ int32_t stage_column(Result *r, int j) {
     } else {
       // scattered heap: size pass, then gather into a pinned arena while the string_t are staged
       arena_start.assign((size_t)nch + 1, 0);
-      parallel_for(nch, c.stage_threads, [&](int64_t k) {
+      parallel_for(c, nch, [&](int64_t k) {
         const dmb_string_t *e = reinterpret_cast<const dmb_string_t *>(col.data[(size_t)k]);
         const void *mask = col.validity.empty() ? nullptr : col.validity[(size_t)k];
         uint64_t sum = 0;
@@ -627,7 +636,7 @@ int32_t stage_list_child(Result *r, int j) {
   col.d_child_val_off = (int64_t *)keep_dev(r, (size_t)(nch + 1) * 8);
   if (!arena || !warena || !h_base || !h_voff || !h_sizes || !col.d_child_sizes || !col.d_child || !col.d_child_validity || !col.d_child_base || !col.d_child_val_off) return -1;
   memset(warena, 0, (size_t)(words + 2) * 8);
-  parallel_for(nch, c.stage_threads, [&](int64_t k) {
+  parallel_for(c, nch, [&](int64_t k) {
     const uint64_t sz = col.child_sizes[(size_t)k];
     if (sz) memcpy(arena + (size_t)col.child_base[(size_t)k] * W, col.child_data[(size_t)k], (size_t)sz * W);
     if (col.child_val_off[(size_t)k] >= 0) memcpy(warena + col.child_val_off[(size_t)k], col.child_validity[(size_t)k], (size_t)((sz + 63) / 64) * 8);
@@ -666,7 +675,7 @@ int32_t run_list(Result *r, Scope &sc, int j, int32_t child_op, bool child_as_st
   std::atomic<bool> outside{false};
   {
     std::vector<uint64_t> part((size_t)(nch > 0 ? nch : 1), 0);
-    parallel_for(nch, c.stage_threads, [&](int64_t k) {
+    parallel_for(c, nch, [&](int64_t k) {
       const uint64_t *e = reinterpret_cast<const uint64_t *>(col.data[(size_t)k]);
       const void *mask = col.validity.empty() ? nullptr : col.validity[(size_t)k];
       uint64_t sum = 0;
@@ -1294,6 +1303,163 @@ GetterOp getter_op(const Col &col, GetterKind kind) {
   }
 }
 
+// ---- device -> a pageable host buffer (a MoonBit Bytes payload) through the pinned ring: DMA of piece i+1 runs while the
+// host threads copy piece i out of the ring.  (cudaMemcpyAsync straight into pageable memory is staged by the driver in
+// small serialised pieces, ~5x slower.)
+int32_t d2h_pageable(CtxCore &c, cudaStream_t st, uint8_t *dst, const uint8_t *src_dev, size_t bytes) {
+  struct Piece { int b; size_t off, len; };
+  std::vector<Piece> inflight;
+  auto drain_one = [&]() -> int32_t {
+    const Piece p = inflight.front();
+    inflight.erase(inflight.begin());
+    if (check_cuda(cudaEventSynchronize(c.ring_free[p.b]), "getter D2H wait")) return -1;
+    const size_t sub = 2u << 20;
+    const int64_t nsub = (int64_t)((p.len + sub - 1) / sub);
+    const uint8_t *from = c.ring[p.b];
+    parallel_for(c, nsub, [&](int64_t i) {
+      const size_t o = (size_t)i * sub;
+      memcpy(dst + p.off + o, from + o, p.len - o < sub ? p.len - o : sub);
+    });
+    return 0;
+  };
+  for (size_t off = 0; off < bytes; off += kStageBytes) {
+    if ((int)inflight.size() >= kStageBuffers - 1 && drain_one()) return -1;
+    const size_t len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+    const int b = c.ring_acquire();
+    if (b < 0) return -1;
+    if (check_cuda(cudaMemcpyAsync(c.ring[b], src_dev + off, len, cudaMemcpyDeviceToHost, st), "getter D2H")) return -1;
+    if (check_cuda(cudaEventRecord(c.ring_free[b], st), "getter D2H record")) return -1;
+    inflight.push_back(Piece{b, off, len});
+  }
+  while (!inflight.empty())
+    if (drain_one()) return -1;
+  return 0;
+}
+
+void copy_out(CtxCore &c, uint8_t *dst, const uint8_t *src, size_t bytes) {  // pinned cache -> Bytes, on the host threads when large
+  const size_t sub = 2u << 20;
+  if (bytes <= 2 * sub) { memcpy(dst, src, bytes); return; }
+  parallel_for(c, (int64_t)((bytes + sub - 1) / sub), [&](int64_t i) {
+    const size_t o = (size_t)i * sub;
+    memcpy(dst + o, src + o, bytes - o < sub ? bytes - o : sub);
+  });
+}
+
+constexpr int kGetString = 4;
+// the getter the reference's schema picks for a column (src/duckdb_native.c:2314-2339): what a MoonBit caller will ask for
+int schema_getter_kind(const Col &col) {
+  switch (col.type_id) {
+    case DMB_TYPE_BOOLEAN: return kGetBool;
+    case DMB_TYPE_TINYINT: case DMB_TYPE_SMALLINT: case DMB_TYPE_INTEGER: return kGetInt32;
+    case DMB_TYPE_BIGINT: return kGetInt64;
+    case DMB_TYPE_FLOAT: case DMB_TYPE_DOUBLE: return kGetDouble;
+    default: return kGetString;
+  }
+}
+
+// The reference's callers read a result column by column, one blocking FFI call each.  On the first getter call of a
+// result that fits, EVERY column is converted in one pipelined pass -- copy-in of column j+1, kernel of column j and
+// copy-out of column j-1 overlap on the three streams, like materialise_arrow -- into complete blobs in pinned memory,
+// each for the getter its schema type selects (and the nullable flavour of the first call); the calls that follow are a
+// memcpy into the Bytes.  A call the prediction missed (another getter kind / flavour) takes the on-demand path below.
+constexpr uint64_t kGetterPrefetchCap = 1ull << 30;  // blob bytes held in pinned memory per result
+
+int32_t prefetch_getters(Result *r, bool nullable) {
+  r->getters_prefetched = true;  // one attempt
+  CtxCore &c = *r->core;
+  const int ncols = (int)r->cols.size();
+  const int64_t n = r->nrows;
+  static const int kWidth[] = {4, 8, 8, 1};
+  uint64_t estimate = 0;
+  for (const Col &col : r->cols) {
+    const int kind = schema_getter_kind(col);
+    if (kind == kGetString) {
+      if (!text_supported(col)) return 0;  // (the on-demand path reports the error for that column)
+      estimate += col.phys == DMB_PHYS_STRING ? col.heap_len + 14ull * (uint64_t)n : 50ull * (uint64_t)n;
+      if (col.phys == DMB_PHYS_STRING && col.heap_len == 0 && col.heap_base != (const uint8_t *)DMB_HEAP_INLINE_ONLY) estimate += 32ull * (uint64_t)n;  // scattered heap: unknown yet
+    } else {
+      estimate += 4 + (uint64_t)n * (uint64_t)(kWidth[kind] + 1);
+    }
+  }
+  if (ncols < 2 || estimate > kGetterPrefetchCap) return 0;
+  std::vector<FixedRun> fr((size_t)ncols);
+  std::vector<StringRun> sr((size_t)ncols);
+  std::vector<int> kinds((size_t)ncols, -1);
+  Scope sc(c);
+  const int32_t row_count = r->row_count;
+  for (int j = 0; j < ncols; ++j) {  // pass 1: stage + launch every column
+    const Col &col = r->cols[(size_t)j];
+    const int kind = schema_getter_kind(col);
+    if (kind == kGetString) {
+      if (run_string(r, sc, j, DMB_STR_REF_BLOB, false, nullable, &sr[(size_t)j])) return -1;
+    } else {
+      const GetterOp gop = getter_op(col, (GetterKind)kind);
+      if (run_fixed(r, sc, j, gop.op, kWidth[kind], false, nullable, &fr[(size_t)j], gop.param)) return -1;
+    }
+    kinds[(size_t)j] = kind;
+  }
+  for (int j = 0; j < ncols; ++j) {  // pass 2: the blobs, assembled in pinned memory by the copy engine
+    Col &col = r->cols[(size_t)j];
+    const int kind = kinds[(size_t)j];
+    if (kind == kGetString) {
+      StringRun &s = sr[(size_t)j];
+      if (check_cuda(cudaEventSynchronize(s.done), "string kernel wait")) return -1;
+      if (s.h_ctr[1] || s.h_ctr[3]) continue;  // flagged (error, or aliased pointers that need an exact-size relaunch): on demand
+      const uint64_t total_data_len = s.h_ctr[0] - s.h_ctr[2];
+      const int64_t total64 = 8 + (int64_t)total_data_len + (nullable ? row_count : 0);
+      if (total64 > 0x7fffffffll) continue;
+      uint8_t *blob = (uint8_t *)keep_pin(r, (size_t)total64);
+      if (!blob) return -1;
+      const int32_t tdl = (int32_t)total_data_len;
+      memcpy(blob, &row_count, 4);
+      memcpy(blob + 4, &tdl, 4);
+      if (check_cuda(cudaStreamWaitEvent(c.s_out, s.done, 0), "wait kernel")) return -1;
+      if (total_data_len && check_cuda(cudaMemcpyAsync(blob + 8, s.d_data, (size_t)total_data_len, cudaMemcpyDeviceToHost, c.s_out), "string data D2H")) return -1;
+      if (nullable && check_cuda(cudaMemcpyAsync(blob + 8 + total_data_len, s.validity.d_valid_bytes, (size_t)row_count, cudaMemcpyDeviceToHost, c.s_out), "validity D2H")) return -1;
+      r->bytes_d2h += total_data_len + (nullable ? (size_t)row_count : 0);
+      col.gc_blob = blob;
+      col.gc_bytes = (size_t)total64;
+    } else {
+      const int w = kWidth[kind];
+      const int64_t total64 = 4 + (int64_t)row_count * w + (nullable ? row_count : 0);
+      if (total64 > 0x7fffffffll) continue;
+      uint8_t *blob = (uint8_t *)keep_pin(r, (size_t)total64);
+      if (!blob) return -1;
+      FixedRun &f = fr[(size_t)j];
+      memcpy(blob, &row_count, 4);
+      const size_t vbytes = (size_t)row_count * (size_t)w;
+      if (check_cuda(cudaStreamWaitEvent(c.s_out, f.done, 0), "wait kernel")) return -1;
+      if (check_cuda(cudaMemcpyAsync(blob + 4, f.d_values, vbytes, cudaMemcpyDeviceToHost, c.s_out), "values D2H")) return -1;
+      if (nullable && check_cuda(cudaMemcpyAsync(blob + 4 + vbytes, f.d_valid_bytes, (size_t)row_count, cudaMemcpyDeviceToHost, c.s_out), "validity D2H")) return -1;
+      r->bytes_d2h += vbytes + (nullable ? (size_t)row_count : 0);
+      col.gc_blob = blob;
+      col.gc_bytes = (size_t)total64;
+    }
+    col.gc_kind = kind;
+    col.gc_nullable = nullable;
+  }
+  if (check_cuda(cudaStreamSynchronize(c.s_out), "getter prefetch sync")) {
+    for (Col &col : r->cols) col.gc_kind = -1;
+    return -1;
+  }
+  return 0;
+}
+
+// a prefetched blob that matches the call, copied into a fresh Bytes; NULL when there is none
+moonbit_bytes_t cached_blob(Result *r, int32_t col_idx, int kind, bool nullable) {
+  if (!r->getters_prefetched && r->row_count > 0) {
+    char saved[512];
+    snprintf(saved, sizeof(saved), "%s", duckdb_mb_gpu_last_error());
+    if (prefetch_getters(r, nullable)) set_error("%s", saved);  // a failed prefetch is not the caller's error: the on-demand path decides
+  }
+  const Col &col = r->cols[(size_t)col_idx];
+  if (col.gc_kind != kind || col.gc_nullable != nullable || !col.gc_blob) return nullptr;
+  moonbit_bytes_t blob = moonbit_make_bytes_raw((int32_t)col.gc_bytes);
+  if (!blob) return nullptr;
+  copy_out(*r->core, blob, col.gc_blob, col.gc_bytes);
+  return blob;
+}
+
 // [n:i32][values][validity bytes]  (src/duckdb_native.c:2359-2454, 2516-2546, 2572-2685, 2761-2797)
 moonbit_bytes_t getter_fixed(Result *r, int32_t col_idx, GetterKind kind, bool nullable) {
   if (!r) return empty_bytes();
@@ -1309,6 +1475,7 @@ moonbit_bytes_t getter_fixed(Result *r, int32_t col_idx, GetterKind kind, bool n
     set_error("result blob of %lld bytes exceeds the int32 length of MoonBit Bytes", (long long)total64);
     return empty_bytes();
   }
+  if (moonbit_bytes_t hit = cached_blob(r, col_idx, (int)kind, nullable)) return hit;
   const Col &col = r->cols[(size_t)col_idx];
   Scope sc(c);
   FixedRun f;
@@ -1319,10 +1486,8 @@ moonbit_bytes_t getter_fixed(Result *r, int32_t col_idx, GetterKind kind, bool n
   if (!blob) { set_error("out of memory"); return empty_bytes(); }
   memcpy(blob, &row_count, 4);
   const size_t vbytes = (size_t)row_count * (size_t)w;
-  bool ok = check_cuda(cudaMemcpyAsync(blob + 4, f.d_values, vbytes, cudaMemcpyDeviceToHost, c.s_compute), "values D2H") == 0;
-  if (ok && nullable)
-    ok = check_cuda(cudaMemcpyAsync(blob + 4 + vbytes, f.d_valid_bytes, (size_t)row_count, cudaMemcpyDeviceToHost, c.s_compute), "validity D2H") == 0;
-  if (ok) ok = check_cuda(cudaStreamSynchronize(c.s_compute), "getter sync") == 0;
+  bool ok = d2h_pageable(c, c.s_compute, blob + 4, f.d_values, vbytes) == 0;
+  if (ok && nullable) ok = d2h_pageable(c, c.s_compute, blob + 4 + vbytes, f.d_valid_bytes, (size_t)row_count) == 0;
   r->bytes_d2h += vbytes + (nullable ? (size_t)row_count : 0);
   if (!ok) { memset(blob, 0, (size_t)total64); }
   return blob;
@@ -1344,6 +1509,7 @@ moonbit_bytes_t getter_string(Result *r, int32_t col_idx, bool nullable) {
     set_error("get_column_string: libduckdb's text rendering of column type %d is not reproduced on the device", col.type_id);
     return empty_bytes();
   }
+  if (moonbit_bytes_t hit = cached_blob(r, col_idx, kGetString, nullable)) return hit;
   Scope sc(c);
   StringRun s;
   if (run_string_sync(r, sc, col_idx, DMB_STR_REF_BLOB, false, nullable, &s)) return empty_bytes();
@@ -1360,10 +1526,8 @@ moonbit_bytes_t getter_string(Result *r, int32_t col_idx, bool nullable) {
   memcpy(blob, &row_count, 4);
   memcpy(blob + 4, &tdl, 4);
   bool ok = true;
-  if (total_data_len) ok = check_cuda(cudaMemcpyAsync(blob + 8, s.d_data, (size_t)total_data_len, cudaMemcpyDeviceToHost, c.s_compute), "string data D2H") == 0;
-  if (ok && nullable)
-    ok = check_cuda(cudaMemcpyAsync(blob + 8 + total_data_len, s.validity.d_valid_bytes, (size_t)row_count, cudaMemcpyDeviceToHost, c.s_compute), "validity D2H") == 0;
-  if (ok) ok = check_cuda(cudaStreamSynchronize(c.s_compute), "getter sync") == 0;
+  if (total_data_len) ok = d2h_pageable(c, c.s_compute, blob + 8, s.d_data, (size_t)total_data_len) == 0;
+  if (ok && nullable) ok = d2h_pageable(c, c.s_compute, blob + 8 + total_data_len, s.validity.d_valid_bytes, (size_t)row_count) == 0;
   r->bytes_d2h += total_data_len + (nullable ? (size_t)row_count : 0);
   if (!ok) memset(blob + 8, 0, (size_t)total64 - 8);
   return blob;
@@ -1669,6 +1833,7 @@ extern "C" moonbit_bytes_t duckdb_mb_result_value(duckdb_mb_arrow_result *r, int
 struct duckdb_mb_stream {
   duckdb_mb_arrow_result *result;
   int64_t next_chunk;
+  bool owns_result = false;
 };
 struct duckdb_mb_chunk {
   duckdb_mb_stream *stream;
@@ -1699,7 +1864,22 @@ extern "C" duckdb_mb_stream *duckdb_mb_gpu_stream_from_result(duckdb_mb_arrow_re
   s->next_chunk = 0;
   return s;
 }
-extern "C" void duckdb_mb_stream_destroy(duckdb_mb_stream *s) { delete s; }
+extern "C" duckdb_mb_stream *duckdb_mb_gpu_stream_from_result_owned(duckdb_mb_arrow_result *r) {
+  duckdb_mb_stream *s = duckdb_mb_gpu_stream_from_result(r);
+  if (!s) { free_result(r); return nullptr; }
+  s->owns_result = true;
+  return s;
+}
+extern "C" void duckdb_mb_gpu_result_set_owner(duckdb_mb_arrow_result *r, void *owner, void (*destroy)(void *)) {
+  if (!r) return;
+  r->owner = owner;
+  r->owner_destroy = destroy;
+}
+extern "C" void duckdb_mb_stream_destroy(duckdb_mb_stream *s) {
+  if (!s) return;
+  if (s->owns_result) free_result(s->result);
+  delete s;
+}
 extern "C" int32_t duckdb_mb_is_null_stream(duckdb_mb_stream *s) { return s == nullptr ? 1 : 0; }
 extern "C" int32_t duckdb_mb_stream_column_count(duckdb_mb_stream *s) { return s ? s->result->column_count : 0; }
 extern "C" moonbit_bytes_t duckdb_mb_stream_column_name(duckdb_mb_stream *s, int32_t col) {

@@ -6,6 +6,8 @@ torch is used only as plumbing here (device allocations for the L0 tests / bench
 from __future__ import annotations
 
 import ctypes as C
+
+import numpy as np
 import os
 from typing import Optional
 
@@ -133,6 +135,13 @@ EXPORTED_SYMBOLS = [
     "duckdb_mb_stream_column_name", "duckdb_mb_stream_fetch_chunk", "duckdb_mb_chunk_destroy", "duckdb_mb_is_null_chunk",
     "duckdb_mb_chunk_row_count", "duckdb_mb_chunk_column_count", "duckdb_mb_chunk_is_null", "duckdb_mb_chunk_value",
     "duckdb_mb_bytes_to_double",
+    "duckdb_mb_gpu_result_set_owner", "duckdb_mb_gpu_stream_from_result_owned", "duckdb_mb_gpu_appender_set_hooks",
+    # the reference's appender symbols (src/duckdb_native.c:1083-1251, 1313-1533, 1735-1926)
+    "duckdb_mb_appender_destroy", "duckdb_mb_appender_error", "duckdb_mb_is_null_appender", "duckdb_mb_begin_row",
+    "duckdb_mb_append_int", "duckdb_mb_append_bigint", "duckdb_mb_append_double", "duckdb_mb_append_varchar", "duckdb_mb_append_bool",
+    "duckdb_mb_append_null", "duckdb_mb_end_row", "duckdb_mb_flush", "duckdb_mb_append_date", "duckdb_mb_append_timestamp",
+    "duckdb_mb_append_blob", "duckdb_mb_append_decimal", "duckdb_mb_append_interval", "duckdb_mb_append_list_varchar",
+    "duckdb_mb_append_struct_varchar", "duckdb_mb_append_map_varchar_varchar",
     "duckdb_mb_gpu_appender_create", "duckdb_mb_gpu_appender_destroy", "duckdb_mb_gpu_appender_error",
     "duckdb_mb_gpu_appender_state", "duckdb_mb_gpu_appender_row_count", "duckdb_mb_gpu_append_arrow_batch",
     "duckdb_mb_gpu_appender_flush", "duckdb_mb_gpu_appender_close", "duckdb_mb_gpu_appender_timings",
@@ -311,6 +320,28 @@ def last_error() -> str:
 def check(rc: int, what: str) -> None:
     if rc < 0:
         raise RuntimeError(f"{what}: {last_error()}")
+
+
+class MoonbitBlob:
+    """A moonbit_bytes_t viewed in place (no copy) as a numpy uint8 array; freed on exit.  The decoder mirror reads the
+    blob exactly once, like the MoonBit decoders do."""
+
+    def __init__(self, ptr: Optional[int]):
+        self.ptr = ptr
+        self.view = np.zeros(0, dtype=np.uint8)
+        if ptr:
+            n = C.c_uint32.from_address(ptr - 4).value
+            if n:
+                self.view = np.ctypeslib.as_array((C.c_uint8 * n).from_address(ptr))
+
+    def __enter__(self):
+        return self.view
+
+    def __exit__(self, *exc):
+        self.view = None
+        if self.ptr:
+            C.CDLL(None).free(C.c_void_p(self.ptr - 8))
+            self.ptr = None
 
 
 def moonbit_bytes(ptr: Optional[int]) -> bytes:

@@ -563,6 +563,14 @@ int32_t duckdb_mb_chunk_column_count(duckdb_mb_chunk *c);
 int32_t duckdb_mb_chunk_is_null(duckdb_mb_chunk *c, int32_t col, int32_t row);
 moonbit_bytes_t duckdb_mb_chunk_value(duckdb_mb_chunk *c, int32_t col, int32_t row);
 
+/* What the glue hangs on a result: the duckdb_result and the data chunks the batch's pointers refer to.  `destroy(owner)`
+ * runs when the result is destroyed (duckdb_mb_arrow_destroy / duckdb_mb_result_destroy, or the owning stream's destroy),
+ * after the last use of the host pointers. */
+void duckdb_mb_gpu_result_set_owner(duckdb_mb_arrow_result *r, void *owner, void (*destroy)(void *owner));
+/* like duckdb_mb_gpu_stream_from_result, but duckdb_mb_stream_destroy also destroys the result (the reference's stream
+ * owns its duckdb_result, src/duckdb_native.c:426-438); on failure the result is destroyed and NULL returned */
+duckdb_mb_stream *duckdb_mb_gpu_stream_from_result_owned(duckdb_mb_arrow_result *r);
+
 /* timings of the last materialise call, milliseconds: [0]=h2d [1]=kernels [2]=d2h [3]=total */
 int32_t duckdb_mb_gpu_result_timings(duckdb_mb_arrow_result *r, double *out4);
 /* bytes moved over the host link by the last materialise call: [0]=h2d [1]=d2h */
@@ -658,6 +666,47 @@ int32_t duckdb_mb_gpu_append_struct_varchar(duckdb_mb_gpu_appender *a, const uin
 int32_t duckdb_mb_gpu_append_map_varchar_varchar(duckdb_mb_gpu_appender *a, const uint8_t *const *keys, const int32_t *key_lens,
                                                  const uint8_t *const *values, const int32_t *value_lens, int32_t count);
 int32_t duckdb_mb_gpu_end_row(duckdb_mb_gpu_appender *a);                                     /* :1221 */
+
+/* hooks for a sink that owns a libduckdb appender (glue/duckdb_gpu_glue.c): on_flush runs after a flush has handed
+ * every buffered chunk to the sink (-> duckdb_appender_flush; return 0 on failure), on_destroy when the handle dies
+ * (-> duckdb_appender_destroy, free of `user`) */
+typedef int32_t (*dmb_appender_flush_hook)(void *user);
+typedef void (*dmb_appender_destroy_hook)(void *user);
+void duckdb_mb_gpu_appender_set_hooks(duckdb_mb_gpu_appender *a, dmb_appender_flush_hook on_flush, dmb_appender_destroy_hook on_destroy);
+
+/* ---- L2 drop-in, the appender set: the reference's own symbols and signatures (src/duckdb_native.c:1083-1251,
+ * 1313-1533, 1735-1926; externs src/duckdb_native.mbt:44-110,134-144,165-217,266-288).  `duckdb_mb_appender` is this
+ * library's handle; Bytes are moonbit_bytes_t (length from the object header), Array[Bytes] is moonbit_bytes_t*;
+ * every parameter is #borrow.  Same 1/0 + duckdb_mb_appender_error convention, with the protocol of
+ * src/duckdb_appender_state_machine.mbt enforced.  duckdb_mb_appender_create(conn, schema, table) needs libduckdb
+ * (duckdb_appender_create, column types): glue/duckdb_gpu_glue.c. */
+typedef struct duckdb_mb_gpu_appender duckdb_mb_appender;
+void duckdb_mb_appender_destroy(duckdb_mb_appender *a);                                       /* :1083 */
+moonbit_bytes_t duckdb_mb_appender_error(duckdb_mb_appender *a);                              /* :1093 */
+int32_t duckdb_mb_is_null_appender(duckdb_mb_appender *a);                                    /* :1253 */
+int32_t duckdb_mb_begin_row(duckdb_mb_appender *a);                                           /* :1100 */
+int32_t duckdb_mb_append_int(duckdb_mb_appender *a, int32_t value);                           /* :1116 */
+int32_t duckdb_mb_append_bigint(duckdb_mb_appender *a, int64_t value);                        /* :1132 */
+int32_t duckdb_mb_append_double(duckdb_mb_appender *a, double value);                         /* :1148 */
+int32_t duckdb_mb_append_varchar(duckdb_mb_appender *a, moonbit_bytes_t value);               /* :1164 */
+#ifdef __cplusplus
+int32_t duckdb_mb_append_bool(duckdb_mb_appender *a, bool value);                             /* :1189 */
+#else
+int32_t duckdb_mb_append_bool(duckdb_mb_appender *a, _Bool value);
+#endif
+int32_t duckdb_mb_append_null(duckdb_mb_appender *a);                                         /* :1205 */
+int32_t duckdb_mb_end_row(duckdb_mb_appender *a);                                             /* :1221 */
+int32_t duckdb_mb_flush(duckdb_mb_appender *a);                                               /* :1237 */
+int32_t duckdb_mb_append_date(duckdb_mb_appender *a, int32_t days);                           /* :1313 (exact days) */
+int32_t duckdb_mb_append_timestamp(duckdb_mb_appender *a, int64_t micros);                    /* :1350 (exact micros) */
+int32_t duckdb_mb_append_blob(duckdb_mb_appender *a, moonbit_bytes_t data, int32_t length);   /* :1397 */
+int32_t duckdb_mb_append_decimal(duckdb_mb_appender *a, uint8_t width, uint8_t scale, int64_t lower, int64_t upper); /* :1447 */
+int32_t duckdb_mb_append_interval(duckdb_mb_appender *a, int32_t months, int32_t days, int64_t micros);             /* :1511 */
+int32_t duckdb_mb_append_list_varchar(duckdb_mb_appender *a, moonbit_bytes_t *values, int32_t count);               /* :1735 */
+int32_t duckdb_mb_append_struct_varchar(duckdb_mb_appender *a, moonbit_bytes_t *field_names, moonbit_bytes_t *field_values,
+                                        int32_t field_count);                                                       /* :1792 */
+int32_t duckdb_mb_append_map_varchar_varchar(duckdb_mb_appender *a, moonbit_bytes_t *keys, moonbit_bytes_t *values,
+                                             int32_t entry_count);                                                  /* :1860 */
 
 #ifdef __cplusplus
 }

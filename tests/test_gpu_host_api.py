@@ -108,52 +108,58 @@ def test_schema_json_matches_reference_format(ctx):
 
 
 # ------------------------------------------------------------------ src/duckdb_arrow_test.mbt replayed
-def test_reference_arrow_tests_through_gpu(ctx):
+def reference_arrow_cases(make_result):
+    """src/duckdb_arrow_test.mbt:128-518 replayed; make_result(batch) -> ArrowResult (host API directly, or SQL-less
+    through the glue: tests/test_glue_mock.py)"""
     # :210-228 RANGE(5) via the int32 getter on a BIGINT column
-    with _result(ctx, batch_of(("range", ch.T_BIGINT, [0, 1, 2, 3, 4]))) as r:
+    with make_result(batch_of(("range", ch.T_BIGINT, [0, 1, 2, 3, 4]))) as r:
         assert r.get_column_int32(0).tolist() == [0, 1, 2, 3, 4]
     # :231-247
-    with _result(ctx, batch_of(("x", ch.T_BIGINT, [100]))) as r:
+    with make_result(batch_of(("x", ch.T_BIGINT, [100]))) as r:
         assert r.get_column_int64(0).tolist() == [100]
     # :250-269
-    with _result(ctx, batch_of(("x", ch.T_DOUBLE, [3.14]))) as r:
+    with make_result(batch_of(("x", ch.T_DOUBLE, [3.14]))) as r:
         assert abs(r.get_column_double(0)[0] - 3.14) < 0.01
     # :272-296
-    with _result(ctx, batch_of(("t", ch.T_BOOLEAN, [1]), ("f", ch.T_BOOLEAN, [0]))) as r:
+    with make_result(batch_of(("t", ch.T_BOOLEAN, [1]), ("f", ch.T_BOOLEAN, [0]))) as r:
         assert r.get_column_bool(0).tolist() == [True] and r.get_column_bool(1).tolist() == [False]
     # :299-315
-    with _result(ctx, batch_of(("s", ch.T_VARCHAR, ["hello"]))) as r:
+    with make_result(batch_of(("s", ch.T_VARCHAR, ["hello"]))) as r:
         assert r.get_column_string(0) == ["hello"]
     # :318-336
-    with _result(ctx, batch_of(("range", ch.T_BIGINT, list(range(100))))) as r:
+    with make_result(batch_of(("range", ch.T_BIGINT, list(range(100))))) as r:
         v = r.get_column_int32(0)
         assert len(v) == 100 and v[0] == 0 and v[99] == 99
     # :343-371 [1,NULL,3,NULL,5]
-    with _result(ctx, batch_of(("x", ch.T_INTEGER, [1, None, 3, None, 5]))) as r:
+    with make_result(batch_of(("x", ch.T_INTEGER, [1, None, 3, None, 5]))) as r:
         v, valid = r.get_column_int32_nullable(0)
         assert valid.tolist() == [True, False, True, False, True]
         assert v.tolist() == [1, 0, 3, 0, 5]
     # all null / no null
-    with _result(ctx, batch_of(("x", ch.T_INTEGER, [None, None, None]))) as r:
+    with make_result(batch_of(("x", ch.T_INTEGER, [None, None, None]))) as r:
         v, valid = r.get_column_int32_nullable(0)
         assert valid.tolist() == [False] * 3 and v.tolist() == [0, 0, 0]
     # strings ['a',NULL,'c',NULL,'e']
-    with _result(ctx, batch_of(("s", ch.T_VARCHAR, ["a", None, "c", None, "e"]))) as r:
+    with make_result(batch_of(("s", ch.T_VARCHAR, ["a", None, "c", None, "e"]))) as r:
         s, valid = r.get_column_string_nullable(0)
         assert valid.tolist() == [True, False, True, False, True]
         # the reference test checks values[0] and values[2] only (:450-453): `total` omits the NULL rows'
         # terminators (src/duckdb_native.c:2719-2729), so the tail of the stream ('e') is overwritten by validity bytes
         assert s[0] == "a" and s[2] == "c" and len(s) == 5
     # doubles / bools with nulls
-    with _result(ctx, batch_of(("d", ch.T_DOUBLE, [1.5, None, 3.5]), ("b", ch.T_BOOLEAN, [1, None, 0]))) as r:
+    with make_result(batch_of(("d", ch.T_DOUBLE, [1.5, None, 3.5]), ("b", ch.T_BOOLEAN, [1, None, 0]))) as r:
         d, dv = r.get_column_double_nullable(0)
         assert d.tolist() == [1.5, 0.0, 3.5] and dv.tolist() == [True, False, True]
         b, bv = r.get_column_bool_nullable(1)
         assert b.tolist() == [True, False, False] and bv.tolist() == [True, False, True]
     # schema type ids :128-203
-    with _result(ctx, batch_of(("a", ch.T_INTEGER, [1]), ("b", ch.T_BIGINT, [1]), ("c", ch.T_DOUBLE, [1.0]),
+    with make_result(batch_of(("a", ch.T_INTEGER, [1]), ("b", ch.T_BIGINT, [1]), ("c", ch.T_DOUBLE, [1.0]),
                                ("d", ch.T_BOOLEAN, [1]), ("e", ch.T_VARCHAR, ["x"]))) as r:
         assert [f.type_id for f in r.get_schema().fields] == ["int32", "int64", "double", "bool", "string"]
+
+
+def test_reference_arrow_tests_through_gpu(ctx):
+    reference_arrow_cases(lambda batch: _result(ctx, batch))
 
 
 def test_decoder_row_cap(ctx):
@@ -433,4 +439,4 @@ def test_string_spans_decoder_equals_the_string_decoder(ctx):
         strs, valid = res.get_column_string_nullable(col)
         starts, ends, valid2, blob = res.get_column_string_spans_nullable(col)
         assert np.array_equal(valid, valid2)
-        assert [blob[s:e].decode("utf-8", errors="replace") for s, e in zip(starts, ends)] == strs
+        assert [bytes(blob[s:e]).decode("utf-8", errors="replace") for s, e in zip(starts, ends)] == strs
