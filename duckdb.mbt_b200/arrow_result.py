@@ -344,8 +344,84 @@ class ArrowResult:
         struct = pa.Array._import_from_c(C.addressof(arr), C.addressof(sch))
         return [struct.field(i) for i in range(struct.type.num_fields)]
 
+    def to_stream(self, max_batch_rows: int = 0):
+        """pyarrow.RecordBatchReader over the Arrow C stream interface: record batches of at most `max_batch_rows` rows
+        (0: 16 M), converted one batch ahead of the consumer; a column with > 2^31 string bytes arrives as several utf8
+        batches.  The chunk vectors must stay alive until the reader is closed."""
+        import pyarrow as pa
+
+        st = nat.ArrowArrayStream()
+        if not self.lib.duckdb_mb_gpu_result_export_stream(self.handle, int(max_batch_rows), C.addressof(st)):
+            raise DuckDBError(nat.last_error())
+        reader = pa.RecordBatchReader._import_from_c(C.addressof(st))
+        reader._dmb_keep = (self._host_batch,)
+        return reader
+
     def to_record_batch(self):
         import pyarrow as pa
 
         arr, sch = self.export_c(-1)
         return pa.RecordBatch._import_from_c(C.addressof(arr), C.addressof(sch))
+
+
+class ShardedResult:
+    """One table over N GPU contexts: contiguous chunk ranges, one independent record batch per part, no
+    data-path collective; `string_bases` is the host exclusive scan that rebases utf8 offsets across the parts."""
+
+    def __init__(self, ctxs: Sequence[GpuContext], batch, pinned: bool = False, register_heap: bool = True):
+        self.lib = ctxs[0].lib
+        self.ctxs = list(ctxs)
+        self._hb = HostBatch(batch, pinned=pinned, register_heap=register_heap)
+        arr = (C.c_void_p * len(ctxs))(*[c.handle for c in ctxs])
+        self.handle = self.lib.duckdb_mb_gpu_result_from_chunks_sharded(arr, len(ctxs), C.byref(self._hb.struct))
+        if not self.handle:
+            raise DuckDBError(nat.last_error() or "sharded result failed")
+
+    @property
+    def part_count(self) -> int:
+        return self.lib.duckdb_mb_gpu_sharded_part_count(self.handle)
+
+    def first_row(self, i: int) -> int:
+        return self.lib.duckdb_mb_gpu_sharded_first_row(self.handle, i)
+
+    def materialise(self) -> None:
+        if not self.lib.duckdb_mb_gpu_sharded_materialise_arrow(self.handle):
+            raise DuckDBError(nat.last_error())
+
+    def part(self, i: int) -> ArrowResult:
+        """the i-th part as an ArrowResult (borrowed: do not close it)"""
+        h = self.lib.duckdb_mb_gpu_sharded_part(self.handle, i)
+        if not h:
+            raise IndexError(i)
+        r = ArrowResult(self.ctxs[0], h, self._hb)
+        r.close = lambda: None  # owned by the sharded handle
+        return r
+
+    def string_bases(self, col: int) -> List[int]:
+        out = (C.c_uint64 * (self.part_count + 1))()
+        if not self.lib.duckdb_mb_gpu_sharded_string_bases(self.handle, col, out):
+            raise DuckDBError(nat.last_error())
+        return [int(v) for v in out]
+
+    def to_stream(self):
+        """hands the parts over to a pyarrow.RecordBatchReader (one record batch per part)"""
+        import pyarrow as pa
+
+        st = nat.ArrowArrayStream()
+        if not self.lib.duckdb_mb_gpu_sharded_export_stream(self.handle, C.addressof(st)):
+            raise DuckDBError(nat.last_error())
+        self.handle = None  # the stream owns it now
+        reader = pa.RecordBatchReader._import_from_c(C.addressof(st))
+        reader._dmb_keep = (self._hb,)
+        return reader
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.duckdb_mb_gpu_sharded_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -70,6 +70,7 @@ struct Col {
   bool any_validity = false;
   const uint8_t *heap_base = nullptr;
   uint64_t heap_len = 0;
+  bool force_large = false;  // export as large_utf8 / large_binary whatever the size (all parts of a sharded table agree)
   std::shared_ptr<EnumDict> dict;  // ENUM
   // LIST: per-chunk child vectors
   bool is_list = false;
@@ -120,8 +121,7 @@ struct duckdb_mb_arrow_result {
   std::vector<cudaEvent_t> events;
   bool arrow_ready = false;
   bool getters_prefetched = false;
-  void *owner = nullptr;  // the glue's duckdb_result + chunk handles
-  void (*owner_destroy)(void *) = nullptr;
+  std::shared_ptr<void> owner;  // the glue's duckdb_result + chunk handles: shared with the result's slices (shards, stream parts)
   double t_h2d = 0, t_kernels = 0, t_d2h = 0, t_total = 0;
   uint64_t bytes_h2d = 0, bytes_d2h = 0;
 };
@@ -157,8 +157,7 @@ void free_result(Result *r) {
     for (cudaEvent_t e : r->events) cudaEventDestroy(e);
     r->cols.clear();  // ArrowColOut buffers go back to the pinned pool unless an export still holds them
   }
-  if (r->owner_destroy) r->owner_destroy(r->owner);  // after the last use of the host chunk pointers
-  delete r;
+  delete r;  // (drops the owner reference: after the last use of the host chunk pointers)
 }
 
 int32_t ensure_meta(Result *r) {
@@ -1013,7 +1012,7 @@ int32_t materialise_arrow(Result *r) {
     for (int k = 0; k < ncols; ++k) {
       const int j = order[(size_t)k];
       const Col &col = r->cols[(size_t)j];
-      const bool surely_large = col.phys == DMB_PHYS_STRING && col.heap_len > 0x7fffffffull;
+      const bool surely_large = col.phys == DMB_PHYS_STRING && (col.heap_len > 0x7fffffffull || col.force_large);
       if (launch_arrow_col(r, sc, j, surely_large ? DMB_STR_ARROW_LARGE : DMB_STR_ARROW_UTF8, &pend[(size_t)j])) return -1;
       if (k > 0 && drain(order[(size_t)k - 1])) return -1;
     }
@@ -1872,8 +1871,7 @@ extern "C" duckdb_mb_stream *duckdb_mb_gpu_stream_from_result_owned(duckdb_mb_ar
 }
 extern "C" void duckdb_mb_gpu_result_set_owner(duckdb_mb_arrow_result *r, void *owner, void (*destroy)(void *)) {
   if (!r) return;
-  r->owner = owner;
-  r->owner_destroy = destroy;
+  r->owner = destroy ? std::shared_ptr<void>(owner, destroy) : std::shared_ptr<void>();
 }
 extern "C" void duckdb_mb_stream_destroy(duckdb_mb_stream *s) {
   if (!s) return;
@@ -1917,4 +1915,333 @@ extern "C" double duckdb_mb_bytes_to_double(const char *bytes, int32_t offset) {
   double d;
   memcpy(&d, bytes + offset, sizeof(d));
   return d;
+}
+
+// =====================================================================================  one table over N GPUs / streams
+// the chunk list is cut into contiguous ranges of whole chunks; every range is an independent result on
+// its own context (own GPU, own host link, own host thread) and exports an independent record batch whose utf8 offsets
+// start at 0.  The only cross-GPU datum is one byte total per string column per part; their exclusive scan on the host
+// gives the base a part's offsets are shifted by when one logical column is wanted (no NCCL, NVLink unused).
+// The same slicing on ONE context is what feeds an ArrowArrayStream: record batches of a bounded number of rows, so a
+// column with more than 2^31 string bytes (BASELINE config C3) leaves as several utf8 batches.
+namespace dmb {
+namespace {
+
+// chunks [c0, c1) of `p` as a result of its own on `core` (pointer tables copied; the host vectors, dictionaries and the
+// glue's owner are shared)
+Result *slice_result(const Result *p, const std::shared_ptr<CtxCore> &core, int64_t c0, int64_t c1) {
+  std::unique_ptr<Result> r(new Result());
+  r->core = core;
+  r->owner = p->owner;
+  r->nchunks = c1 - c0;
+  r->pinned_input = p->pinned_input;
+  r->counts.assign(p->counts.begin() + c0, p->counts.begin() + c1);
+  r->row_off.assign((size_t)r->nchunks + 1, 0);
+  for (int64_t k = 0; k < r->nchunks; ++k) r->row_off[(size_t)k + 1] = r->row_off[(size_t)k] + r->counts[(size_t)k];
+  r->nrows = r->row_off[(size_t)r->nchunks];
+  r->column_count = p->column_count;
+  r->row_count = (int32_t)r->nrows;
+  r->cols.resize(p->cols.size());
+  for (size_t j = 0; j < p->cols.size(); ++j) {
+    const Col &pc = p->cols[j];
+    Col &col = r->cols[j];
+    col.name = pc.name;
+    col.type_id = pc.type_id;
+    col.phys = pc.phys;
+    col.dec_width = pc.dec_width;
+    col.dec_scale = pc.dec_scale;
+    col.width = pc.width;
+    col.force_large = pc.force_large;
+    col.dict = pc.dict ? std::make_shared<EnumDict>() : nullptr;  // device copies are per result: own dictionary object
+    if (pc.dict) {
+      col.dict->offsets = pc.dict->offsets;
+      col.dict->data = pc.dict->data;
+      col.dict->max_len = pc.dict->max_len;
+    }
+    col.data.assign(pc.data.begin() + c0, pc.data.begin() + c1);
+    if (!pc.validity.empty()) {
+      col.validity.assign(pc.validity.begin() + c0, pc.validity.begin() + c1);
+      for (const void *q : col.validity) col.any_validity |= q != nullptr;
+      if (!col.any_validity) col.validity.clear();
+    }
+    col.heap_base = pc.heap_base;
+    col.heap_len = pc.heap_len;
+    if (pc.phys == DMB_PHYS_STRING && pc.heap_len > 0 && pc.heap_base && pc.heap_base != (const uint8_t *)DMB_HEAP_INLINE_ONLY) {
+      // a registered contiguous heap: this part stages only the span its own pointers reach
+      std::vector<uint64_t> lo((size_t)(r->nchunks > 0 ? r->nchunks : 1), ~0ull), hi((size_t)(r->nchunks > 0 ? r->nchunks : 1), 0ull);
+      parallel_for(*core, r->nchunks, [&](int64_t k) {
+        const dmb_string_t *e = reinterpret_cast<const dmb_string_t *>(col.data[(size_t)k]);
+        const void *mask = col.validity.empty() ? nullptr : col.validity[(size_t)k];
+        uint64_t l = ~0ull, h = 0;
+        for (uint32_t i = 0; e && i < r->counts[(size_t)k]; ++i) {
+          if (!host_row_valid(mask, i) || e[i].length <= 12) continue;
+          l = e[i].tail.ptr < l ? e[i].tail.ptr : l;
+          h = e[i].tail.ptr + e[i].length > h ? e[i].tail.ptr + e[i].length : h;
+        }
+        lo[(size_t)k] = l;
+        hi[(size_t)k] = h;
+      });
+      uint64_t l = ~0ull, h = 0;
+      for (int64_t k = 0; k < r->nchunks; ++k) { l = lo[(size_t)k] < l ? lo[(size_t)k] : l; h = hi[(size_t)k] > h ? hi[(size_t)k] : h; }
+      const uint64_t b0 = (uint64_t)(uintptr_t)pc.heap_base, b1 = b0 + pc.heap_len;
+      if (h > l && l >= b0 && h <= b1) {  // (pointers outside the registered heap: keep the whole heap, the kernel reports them)
+        const uint64_t a = l & ~15ull;  // keep the staged copy 16-byte phase-aligned with the host heap
+        col.heap_base = (const uint8_t *)(uintptr_t)(a < b0 ? b0 : a);
+        col.heap_len = h - (uint64_t)(uintptr_t)col.heap_base;
+      } else if (h <= l) {
+        col.heap_base = (const uint8_t *)DMB_HEAP_INLINE_ONLY;  // no pointer string in this part
+        col.heap_len = 0;
+      }
+    }
+    if (pc.is_list) {
+      col.is_list = true;
+      col.child_type_id = pc.child_type_id;
+      col.child_phys = pc.child_phys;
+      col.child_dec_width = pc.child_dec_width;
+      col.child_dec_scale = pc.child_dec_scale;
+      col.child_width = pc.child_width;
+      col.child_data.assign(pc.child_data.begin() + c0, pc.child_data.begin() + c1);
+      col.child_sizes.assign(pc.child_sizes.begin() + c0, pc.child_sizes.begin() + c1);
+      if (!pc.child_validity.empty()) col.child_validity.assign(pc.child_validity.begin() + c0, pc.child_validity.begin() + c1);
+      col.child_base.assign((size_t)r->nchunks + 1, 0);
+      col.child_val_off.assign((size_t)(r->nchunks > 0 ? r->nchunks : 1), -1);
+      uint64_t words = 0;
+      for (int64_t k = 0; k < r->nchunks; ++k) {
+        col.child_base[(size_t)k + 1] = col.child_base[(size_t)k] + col.child_sizes[(size_t)k];
+        if (!col.child_validity.empty() && col.child_validity[(size_t)k]) {
+          col.child_val_off[(size_t)k] = (int64_t)words;
+          words += (col.child_sizes[(size_t)k] + 63) / 64 + 1;
+        }
+      }
+    }
+  }
+  return r.release();
+}
+
+}  // namespace
+}  // namespace dmb
+
+struct duckdb_mb_gpu_sharded {
+  std::vector<duckdb_mb_arrow_result *> parts;
+  std::vector<int64_t> first_row;  // [nparts + 1]
+  std::string error;
+  // stream state
+  size_t next = 0;
+  std::thread ahead;        // materialises part `next` while the consumer works on the one before
+  int32_t ahead_rc = 0;
+  std::string ahead_error;
+  bool ahead_running = false;
+};
+
+namespace dmb {
+namespace {
+
+typedef duckdb_mb_gpu_sharded Sharded;
+
+int32_t materialise_locked(Result *r, std::string *err) {
+  std::lock_guard<std::mutex> g(r->core->mu);
+  const int32_t rc = materialise_arrow(r);
+  if (rc && err) *err = duckdb_mb_gpu_last_error();  // (thread-local: read it on the thread that failed)
+  return rc;
+}
+
+// ---- ArrowArrayStream over the parts (Arrow C stream interface): one record batch per part, materialised one ahead
+int stream_get_schema(struct ArrowArrayStream *st, struct ArrowSchema *out) {
+  Sharded *s = reinterpret_cast<Sharded *>(st->private_data);
+  if (s->parts.empty()) { s->error = "empty stream"; return 22; }
+  // the schema is that of part 0 (every part agrees: same columns; string columns either all utf8 or all large_utf8)
+  Result *r = s->parts[0];
+  if (s->ahead_running) { s->ahead.join(); s->ahead_running = false; }
+  std::string err;
+  if (materialise_locked(r, &err)) { s->error = err; return 5; }
+  if (!duckdb_mb_gpu_result_export_arrow(r, -1, nullptr, out)) { s->error = duckdb_mb_gpu_last_error(); return 5; }
+  return 0;
+}
+
+int stream_get_next(struct ArrowArrayStream *st, struct ArrowArray *out) {
+  Sharded *s = reinterpret_cast<Sharded *>(st->private_data);
+  if (s->ahead_running) {
+    s->ahead.join();
+    s->ahead_running = false;
+    if (s->ahead_rc) { s->error = s->ahead_error; return 5; }
+  }
+  if (s->next >= s->parts.size()) {  // end of stream: a released array
+    memset(out, 0, sizeof(*out));
+    return 0;
+  }
+  Result *r = s->parts[s->next];
+  std::string err;
+  if (materialise_locked(r, &err)) { s->error = err; return 5; }
+  if (s->next > 0) {  // every batch must have the schema handed out by get_schema
+    Result *r0 = s->parts[0];
+    for (size_t j = 0; j < r->cols.size() && r0->arrow_ready; ++j)
+      if (r->cols[j].arrow->format != r0->cols[j].arrow->format) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "record batch %zu: column %zu is '%s' but the stream's schema says '%s'", s->next, j,
+                 r->cols[j].arrow->format.c_str(), r0->cols[j].arrow->format.c_str());
+        s->error = buf;
+        return 22;
+      }
+  }
+  if (!duckdb_mb_gpu_result_export_arrow(r, -1, out, nullptr)) { s->error = duckdb_mb_gpu_last_error(); return 5; }
+  // the exported array owns its pinned buffers: the part's device copies and pointer tables can go (part 0 stays: schema)
+  if (s->next > 0) { free_result(r); s->parts[s->next] = nullptr; }
+  ++s->next;
+  if (s->next < s->parts.size()) {  // start on the next part while the consumer reads this one
+    Result *nx = s->parts[s->next];
+    s->ahead_rc = 0;
+    s->ahead_running = true;
+    s->ahead = std::thread([s, nx] {
+      s->ahead_rc = materialise_locked(nx, &s->ahead_error);
+    });
+  }
+  return 0;
+}
+
+const char *stream_last_error(struct ArrowArrayStream *st) {
+  Sharded *s = reinterpret_cast<Sharded *>(st->private_data);
+  return s->error.empty() ? nullptr : s->error.c_str();
+}
+
+void stream_release(struct ArrowArrayStream *st) {
+  if (!st || !st->release) return;
+  Sharded *s = reinterpret_cast<Sharded *>(st->private_data);
+  if (s->ahead_running) { s->ahead.join(); s->ahead_running = false; }
+  for (Result *&p : s->parts) { if (p) free_result(p); p = nullptr; }
+  delete s;
+  st->release = nullptr;
+  st->private_data = nullptr;
+}
+
+}  // namespace
+}  // namespace dmb
+
+extern "C" duckdb_mb_gpu_sharded *duckdb_mb_gpu_result_shard(duckdb_mb_arrow_result *r, duckdb_mb_gpu_ctx *const *ctxs, int32_t nctx,
+                                                            int64_t max_rows_per_part) {
+  if (!r) { set_error("duckdb_mb_gpu_result_shard: null result"); return nullptr; }
+  std::vector<std::shared_ptr<CtxCore>> cores;
+  if (!ctxs || nctx <= 0) cores.push_back(r->core);
+  else
+    for (int32_t g = 0; g < nctx; ++g) {
+      if (!ctxs[g] || !ctxs[g]->core) { set_error("duckdb_mb_gpu_result_shard: context %d is null", g); return nullptr; }
+      cores.push_back(ctxs[g]->core);
+    }
+  const int64_t G = (int64_t)cores.size(), C = r->nchunks;
+  std::unique_ptr<Sharded> s(new Sharded());
+  // a string column that cannot be one utf8 batch in SOME part is large in every part (one schema for the table)
+  const int64_t per_gpu = C > 0 ? (C + G - 1) / G : 0;  // GPU g gets chunks [g * ceil(C / G), ...)
+  int64_t chunks_per_part = per_gpu;
+  if (max_rows_per_part > 0) {
+    const int64_t m = max_rows_per_part / DMB_VECTOR_SIZE;
+    chunks_per_part = m < 1 ? 1 : (m < per_gpu ? m : per_gpu);
+  }
+  s->first_row.push_back(0);
+  for (int64_t g = 0; g < G; ++g) {
+    const int64_t g0 = g * per_gpu < C ? g * per_gpu : C, g1 = g0 + per_gpu < C ? g0 + per_gpu : C;
+    for (int64_t c0 = g0; c0 < g1 || (C == 0 && g == 0 && s->parts.empty()); c0 += chunks_per_part > 0 ? chunks_per_part : 1) {
+      const int64_t c1 = c0 + chunks_per_part < g1 ? c0 + chunks_per_part : g1;
+      Result *part = slice_result(r, cores[(size_t)g], c0, c1 > c0 ? c1 : c0);
+      s->parts.push_back(part);
+      s->first_row.push_back(s->first_row.back() + part->nrows);
+      if (C == 0) break;
+    }
+  }
+  for (size_t j = 0; j < r->cols.size(); ++j) {
+    bool large = false;
+    for (Result *p : s->parts) {
+      const Col &c = p->cols[j];
+      large |= c.phys == DMB_PHYS_STRING && (c.heap_len > 0x7fffffffull || c.force_large);
+    }
+    if (large) for (Result *p : s->parts) p->cols[j].force_large = true;
+  }
+  return s.release();
+}
+
+extern "C" duckdb_mb_gpu_sharded *duckdb_mb_gpu_result_from_chunks_sharded(duckdb_mb_gpu_ctx *const *ctxs, int32_t nctx, const dmb_host_batch *batch) {
+  if (!ctxs || nctx <= 0 || !ctxs[0]) { set_error("duckdb_mb_gpu_result_from_chunks_sharded: no contexts"); return nullptr; }
+  duckdb_mb_arrow_result *whole = duckdb_mb_gpu_result_from_chunks(ctxs[0], batch);  // pointer tables only: nothing is staged
+  if (!whole) return nullptr;
+  duckdb_mb_gpu_sharded *s = duckdb_mb_gpu_result_shard(whole, ctxs, nctx, 0);
+  free_result(whole);
+  return s;
+}
+
+extern "C" void duckdb_mb_gpu_sharded_destroy(duckdb_mb_gpu_sharded *s) {
+  if (!s) return;
+  if (s->ahead_running) s->ahead.join();
+  for (Result *p : s->parts) if (p) free_result(p);
+  delete s;
+}
+
+extern "C" int32_t duckdb_mb_gpu_sharded_part_count(duckdb_mb_gpu_sharded *s) { return s ? (int32_t)s->parts.size() : 0; }
+extern "C" duckdb_mb_arrow_result *duckdb_mb_gpu_sharded_part(duckdb_mb_gpu_sharded *s, int32_t i) {
+  return (s && i >= 0 && (size_t)i < s->parts.size()) ? s->parts[(size_t)i] : nullptr;
+}
+extern "C" int64_t duckdb_mb_gpu_sharded_first_row(duckdb_mb_gpu_sharded *s, int32_t i) {
+  return (s && i >= 0 && (size_t)i < s->first_row.size()) ? s->first_row[(size_t)i] : -1;
+}
+
+// every part on its own host thread (parts that share a context take turns: one blocking call at a time per context)
+extern "C" int32_t duckdb_mb_gpu_sharded_materialise_arrow(duckdb_mb_gpu_sharded *s) {
+  if (!s) { set_error("null sharded result"); return 0; }
+  const size_t n = s->parts.size();
+  std::vector<int32_t> rc(n, 0);
+  std::vector<std::string> errs(n);
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < n; ++i) th.emplace_back([&, i] { rc[i] = materialise_locked(s->parts[i], &errs[i]); });
+  for (auto &t : th) t.join();
+  for (size_t i = 0; i < n; ++i)
+    if (rc[i]) { set_error("part %zu: %s", i, errs[i].c_str()); return 0; }
+  // one schema for the table: if a utf8 column overflowed int32 offsets in some part only, the other parts follow
+  if (n > 1)
+    for (size_t j = 0; j < s->parts[0]->cols.size(); ++j) {
+      bool any_large = false, any_small = false;
+      for (Result *p : s->parts) {
+        const std::string &f = p->cols[j].arrow->format;
+        any_large |= f == "U" || f == "Z";
+        any_small |= f == "u" || f == "z";
+      }
+      if (any_large && any_small) {
+        for (Result *p : s->parts) { p->cols[j].force_large = true; p->arrow_ready = false; }
+        return duckdb_mb_gpu_sharded_materialise_arrow(s);
+      }
+    }
+  return 1;
+}
+
+// host exclusive scan of the per-part utf8 byte totals of string column `col`: out[i] = base of part i, out[nparts] = total
+extern "C" int32_t duckdb_mb_gpu_sharded_string_bases(duckdb_mb_gpu_sharded *s, int32_t col, uint64_t *out) {
+  if (!s || !out) { set_error("null argument"); return 0; }
+  uint64_t acc = 0;
+  for (size_t i = 0; i < s->parts.size(); ++i) {
+    Result *p = s->parts[i];
+    if (!p || !p->arrow_ready || col < 0 || col >= p->column_count) { set_error("string_bases: part %zu is not materialised / bad column", i); return 0; }
+    const ArrowColOut &o = *p->cols[(size_t)col].arrow;
+    if (!o.data && o.data_bytes == 0 && o.format != "u" && o.format != "U" && o.format != "z" && o.format != "Z") { set_error("string_bases: column %d is not a string column", col); return 0; }
+    out[i] = acc;
+    acc += o.data_bytes;
+  }
+  out[s->parts.size()] = acc;
+  return 1;
+}
+
+// the parts as an ArrowArrayStream (one record batch each, in row order); the stream takes the handle over
+extern "C" int32_t duckdb_mb_gpu_sharded_export_stream(duckdb_mb_gpu_sharded *s, struct ArrowArrayStream *out) {
+  if (!s || !out) { set_error("null argument"); return 0; }
+  memset(out, 0, sizeof(*out));
+  out->get_schema = stream_get_schema;
+  out->get_next = stream_get_next;
+  out->get_last_error = stream_last_error;
+  out->release = stream_release;
+  out->private_data = s;
+  return 1;
+}
+
+// a result as a stream of record batches of at most max_batch_rows rows (<= 0: 16 M), converted one batch ahead of the
+// consumer.  Replaces the silent large_utf8 switch for columns with more than 2^31 string bytes: every batch is plain utf8.
+extern "C" int32_t duckdb_mb_gpu_result_export_stream(duckdb_mb_arrow_result *r, int64_t max_batch_rows, struct ArrowArrayStream *out) {
+  if (!r || !out) { set_error("null argument"); return 0; }
+  duckdb_mb_gpu_sharded *s = duckdb_mb_gpu_result_shard(r, nullptr, 0, max_batch_rows > 0 ? max_batch_rows : (16ll << 20));
+  if (!s) return 0;
+  return duckdb_mb_gpu_sharded_export_stream(s, out);
 }

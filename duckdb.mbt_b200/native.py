@@ -106,6 +106,11 @@ ArrowArray._fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offse
                        ("release", C.c_void_p), ("private_data", C.c_void_p)]
 
 
+class ArrowArrayStream(C.Structure):  # Arrow C stream interface: 5 pointers
+    _fields_ = [("get_schema", C.c_void_p), ("get_next", C.c_void_p), ("get_last_error", C.c_void_p), ("release", C.c_void_p),
+                ("private_data", C.c_void_p)]
+
+
 class TypedColumn(C.Structure):
     _fields_ = [("tag", C.c_int32), ("width", C.c_int32), ("length", C.c_int64), ("null_count", C.c_int64),
                 ("values", C.c_void_p), ("valid", C.c_void_p), ("offsets", C.c_void_p), ("data", C.c_void_p)]
@@ -136,6 +141,9 @@ EXPORTED_SYMBOLS = [
     "duckdb_mb_chunk_row_count", "duckdb_mb_chunk_column_count", "duckdb_mb_chunk_is_null", "duckdb_mb_chunk_value",
     "duckdb_mb_bytes_to_double",
     "duckdb_mb_gpu_result_set_owner", "duckdb_mb_gpu_stream_from_result_owned", "duckdb_mb_gpu_appender_set_hooks",
+    "duckdb_mb_gpu_result_from_chunks_sharded", "duckdb_mb_gpu_result_shard", "duckdb_mb_gpu_sharded_part_count", "duckdb_mb_gpu_sharded_part",
+    "duckdb_mb_gpu_sharded_first_row", "duckdb_mb_gpu_sharded_materialise_arrow", "duckdb_mb_gpu_sharded_string_bases",
+    "duckdb_mb_gpu_sharded_destroy", "duckdb_mb_gpu_sharded_export_stream", "duckdb_mb_gpu_result_export_stream",
     # the reference's appender symbols (src/duckdb_native.c:1083-1251, 1313-1533, 1735-1926)
     "duckdb_mb_appender_destroy", "duckdb_mb_appender_error", "duckdb_mb_is_null_appender", "duckdb_mb_begin_row",
     "duckdb_mb_append_int", "duckdb_mb_append_bigint", "duckdb_mb_append_double", "duckdb_mb_append_varchar", "duckdb_mb_append_bool",
@@ -231,6 +239,20 @@ def lib():
     L.duckdb_mb_gpu_result_materialise_arrow.argtypes = [vp]
     L.duckdb_mb_gpu_result_export_arrow.restype = i32
     L.duckdb_mb_gpu_result_export_arrow.argtypes = [vp, i32, vp, vp]
+    L.duckdb_mb_gpu_result_from_chunks_sharded.restype = vp
+    L.duckdb_mb_gpu_result_from_chunks_sharded.argtypes = [C.POINTER(vp), i32, vp]
+    L.duckdb_mb_gpu_result_shard.restype = vp
+    L.duckdb_mb_gpu_result_shard.argtypes = [vp, C.POINTER(vp), i32, i64]
+    L.duckdb_mb_gpu_sharded_part_count.argtypes = [vp]
+    L.duckdb_mb_gpu_sharded_part.restype = vp
+    L.duckdb_mb_gpu_sharded_part.argtypes = [vp, i32]
+    L.duckdb_mb_gpu_sharded_first_row.restype = i64
+    L.duckdb_mb_gpu_sharded_first_row.argtypes = [vp, i32]
+    L.duckdb_mb_gpu_sharded_materialise_arrow.argtypes = [vp]
+    L.duckdb_mb_gpu_sharded_string_bases.argtypes = [vp, i32, vp]
+    L.duckdb_mb_gpu_sharded_destroy.argtypes = [vp]
+    L.duckdb_mb_gpu_sharded_export_stream.argtypes = [vp, vp]
+    L.duckdb_mb_gpu_result_export_stream.argtypes = [vp, i64, vp]
     L.duckdb_mb_gpu_result_typed_column.restype = i32
     L.duckdb_mb_gpu_result_typed_column.argtypes = [vp, i32, C.POINTER(TypedColumn)]
     L.duckdb_mb_gpu_result_text_column.restype = i32

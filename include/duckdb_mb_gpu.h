@@ -494,6 +494,17 @@ struct ArrowArray {
 };
 #endif
 
+#ifndef ARROW_C_STREAM_INTERFACE
+#define ARROW_C_STREAM_INTERFACE
+struct ArrowArrayStream { /* Arrow C stream interface */
+  int (*get_schema)(struct ArrowArrayStream *, struct ArrowSchema *out);
+  int (*get_next)(struct ArrowArrayStream *, struct ArrowArray *out); /* released array (release == NULL) = end of stream */
+  const char *(*get_last_error)(struct ArrowArrayStream *);
+  void (*release)(struct ArrowArrayStream *);
+  void *private_data;
+};
+#endif
+
 /* DataChunk -> Arrow for every column: H2D (if not yet staged), kernels, D2H into pinned
  * buffers owned by the result.  Blocking.  Returns 1/0 (reference mutator convention). */
 int32_t duckdb_mb_gpu_result_materialise_arrow(duckdb_mb_arrow_result *r);
@@ -570,6 +581,32 @@ void duckdb_mb_gpu_result_set_owner(duckdb_mb_arrow_result *r, void *owner, void
 /* like duckdb_mb_gpu_stream_from_result, but duckdb_mb_stream_destroy also destroys the result (the reference's stream
  * owns its duckdb_result, src/duckdb_native.c:426-438); on failure the result is destroyed and NULL returned */
 duckdb_mb_stream *duckdb_mb_gpu_stream_from_result_owned(duckdb_mb_arrow_result *r);
+
+/* ---- one table over N GPUs, and record-batch streams.
+ * The chunk list is cut into contiguous ranges of whole chunks ("parts"): GPU g gets chunks [g * ceil(C / G), ...), and
+ * with max_rows_per_part > 0 a GPU's range is cut further into parts of at most that many rows.  Every part is a result
+ * of its own on its context (duckdb_mb_gpu_sharded_part: borrowed, usable with every duckdb_mb_gpu_result_* /
+ * duckdb_mb_arrow_* call); materialise runs one host thread per part.  The only cross-GPU datum is one byte total per
+ * string column per part: duckdb_mb_gpu_sharded_string_bases is their host exclusive scan (the base each part's utf8
+ * offsets are shifted by when one logical column is stitched; out has part_count + 1 entries).  No collective.
+ * The reference has no counterpart (one duckdb_result, one thread, src/duckdb_native.c:2219-2268). */
+typedef struct duckdb_mb_gpu_sharded duckdb_mb_gpu_sharded;
+duckdb_mb_gpu_sharded *duckdb_mb_gpu_result_from_chunks_sharded(duckdb_mb_gpu_ctx *const *ctxs, int32_t nctx, const dmb_host_batch *batch);
+duckdb_mb_gpu_sharded *duckdb_mb_gpu_result_shard(duckdb_mb_arrow_result *r, duckdb_mb_gpu_ctx *const *ctxs, int32_t nctx,
+                                                 int64_t max_rows_per_part); /* ctxs NULL: the result's own context */
+int32_t duckdb_mb_gpu_sharded_part_count(duckdb_mb_gpu_sharded *s);
+duckdb_mb_arrow_result *duckdb_mb_gpu_sharded_part(duckdb_mb_gpu_sharded *s, int32_t i);
+int64_t duckdb_mb_gpu_sharded_first_row(duckdb_mb_gpu_sharded *s, int32_t i); /* i = part_count: total rows */
+int32_t duckdb_mb_gpu_sharded_materialise_arrow(duckdb_mb_gpu_sharded *s);
+int32_t duckdb_mb_gpu_sharded_string_bases(duckdb_mb_gpu_sharded *s, int32_t col, uint64_t *out);
+void duckdb_mb_gpu_sharded_destroy(duckdb_mb_gpu_sharded *s);
+/* ArrowArrayStream (Arrow C stream interface): one record batch per part, in row order, converted one batch ahead of the
+ * consumer.  _sharded_export_stream hands the handle over to the stream (do not destroy it afterwards);
+ * _result_export_stream cuts a result into batches of at most max_batch_rows rows (<= 0: 16 M) on its own context, so a
+ * column with more than 2^31 string bytes (BASELINE config C3) leaves as several utf8 batches instead of one large_utf8
+ * array.  The host chunk vectors must stay alive until the stream is released (a glue owner is shared automatically). */
+int32_t duckdb_mb_gpu_sharded_export_stream(duckdb_mb_gpu_sharded *s, struct ArrowArrayStream *out);
+int32_t duckdb_mb_gpu_result_export_stream(duckdb_mb_arrow_result *r, int64_t max_batch_rows, struct ArrowArrayStream *out);
 
 /* timings of the last materialise call, milliseconds: [0]=h2d [1]=kernels [2]=d2h [3]=total */
 int32_t duckdb_mb_gpu_result_timings(duckdb_mb_arrow_result *r, double *out4);
