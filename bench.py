@@ -431,31 +431,44 @@ def torch_uint8():
 
 
 # ----------------------------------------------------------------------------- CPU baselines (oracle = the thing timed)
-def cpu_reference_pass(batch):
+def cpu_reference_pass(batch, split=None):
     """The reference path on one result: duckdb_mb_arrow_get_column_* per column (the getter the
     schema's type_id selects, src/duckdb_native.c:2314-2339) + the MoonBit decoder loops.
-    Returns seconds."""
+    Returns seconds; split (a dict) receives the seconds spent in the C getters ("getters_s": what produces the Bytes)
+    and in the decoders ("decode_s")."""
     import numpy as np
     import oracle
     from duckdb_mbt_b200 import chunks as ch
     t0 = time.perf_counter()
     ora = oracle.OracleResult(batch)
+    tg = td = 0.0
     for j, col in enumerate(batch.columns):
         if col.type_id in (ch.T_TINYINT, ch.T_SMALLINT, ch.T_INTEGER):
-            oracle.decode_int32(ora.get_column("int32", j, True), True)
+            kind, dec = "int32", oracle.decode_int32
         elif col.type_id == ch.T_BIGINT:
-            oracle.decode_int64_as_int(ora.get_column("int64", j, True), True)
+            kind, dec = "int64", oracle.decode_int64_as_int
         elif col.type_id in (ch.T_FLOAT, ch.T_DOUBLE):
-            oracle.decode_double(ora.get_column("double", j, True), True)
+            kind, dec = "double", oracle.decode_double
         elif col.type_id == ch.T_BOOLEAN:
-            oracle.decode_bool(ora.get_column("bool", j, True), True)
+            kind, dec = "bool", oracle.decode_bool
         else:  # everything else is "string" in the reference's schema: duckdb_value_varchar per cell
-            blob = ora.get_column("string", j, True)
+            kind, dec = "string", None
+        t1 = time.perf_counter()
+        blob = ora.get_column(kind, j, True)
+        t2 = time.perf_counter()
+        if dec is not None:
+            dec(blob, True)
+        else:
             n = max(len(blob), 1)
             buf = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, np.uint8)
             starts, ends, valid = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.uint8)
             oracle.lib().ora_decode_string(buf.ctypes.data, len(blob), 1, starts.ctypes.data, ends.ctypes.data, valid.ctypes.data)
+        tg += t2 - t1
+        td += time.perf_counter() - t2
     ora.close()
+    if split is not None:
+        split["getters_s"] = split.get("getters_s", 0.0) + tg
+        split["decode_s"] = split.get("decode_s", 0.0) + td
     return time.perf_counter() - t0
 
 
@@ -465,8 +478,9 @@ def _cpu_worker(args):
     import oracle
     oracle.lib()
     batch = ch.config_c2(rows, seed=seed)
-    times = [cpu_reference_pass(batch) for _ in range(passes)]
-    return times
+    split = {}
+    times = [cpu_reference_pass(batch, split) for _ in range(passes)]
+    return times, split
 
 
 def run_reference(args, rank, world):
@@ -484,9 +498,11 @@ def run_reference(args, rank, world):
         results = list(ex.map(_cpu_worker, [(rows, 20260103 + i, passes) for i in range(cores)]))
         wall = time.perf_counter() - t0
     # every worker converts its own <= 1M-row result `steps` times; aggregate over the timed passes
-    per_worker = [sum(t[args.warmup:]) for t in results]
+    per_worker = [sum(t[args.warmup:]) for t, _ in results]
     slowest = max(per_worker)
     value = cores * rows * args.steps / slowest
+    getters_s = max(sp.get("getters_s", 0.0) for _, sp in results) * args.steps / passes
+    decode_s = max(sp.get("decode_s", 0.0) for _, sp in results) * args.steps / passes
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * slowest / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -500,6 +516,11 @@ def run_reference(args, rank, world):
                          "sample": f"{cores} processes x {rows} rows x {args.steps} steps of the C2 table, generation untimed"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
+        # the same surface bench.py's e2e_getters leg times on the GPU arm, split the same way
+        "getters_split": {"getters_only_rows_per_s": cores * rows * args.steps / max(getters_s, 1e-9),
+                          "getters_ms_per_step": 1e3 * getters_s / args.steps, "decode_ms_per_step": 1e3 * decode_s / args.steps,
+                          "note": "getters = the C stub's per-cell loops that produce the Bytes blobs (equal outputs to the GPU arm's "
+                                  "c_abi_only figure, minus materialise); decode = the MoonBit decoder loops"},
     }
     print(json.dumps(line), flush=True)
 
@@ -888,19 +909,34 @@ def run_ours(args, rank, local_rank, world):
                 for i in range(min(n_res, layout.nchunks // per))]
         rows_res = sum(s.batch.nrows for s in subs)
 
+        import concurrent.futures as cf
+        tsplit = {"from_chunks_s": 0.0, "c_getters_s": 0.0, "decode_s": 0.0}
+        pool = cf.ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
+        fixed_fmt = {"int32": (4, "<i4"), "int64": (8, "<i8"), "double": (8, "<f8"), "bool": (1, np.uint8)}
+
+        def decode_one(res, kind, blob):
+            with blob as view:  # the decoder mirror (MoonBit-side work in the reference): numpy releases the GIL, columns decode in parallel
+                if kind == "string":
+                    return int(ar.decode_string_spans(view, True)[2].shape[0])
+                w, dt = fixed_fmt[kind]
+                return int(res._decode_fixed(view, w, np.dtype(dt), True)[1].shape[0])
+
         def getters_step():
             got = 0
             for s in subs:
+                t0 = time.perf_counter()
                 h = ctx.lib.duckdb_mb_gpu_result_from_chunks(ctx.handle, C.byref(s.struct))
                 res = ar.ArrowResult(ctx, h, s)
-                for j, col in enumerate(s.batch.columns):
+                t1 = time.perf_counter()
+                tsplit["from_chunks_s"] += t1 - t0
+                blobs = []
+                for j, col in enumerate(s.batch.columns):  # the C-ABI calls, one at a time like the reference's FFI
                     kind = getter_of.get(col.type_id, "string")
-                    if kind == "string":
-                        starts, ends, valid, _ = res.get_column_string_spans_nullable(j)
-                        got += int(valid.shape[0])
-                    else:
-                        v, valid = getattr(res, f"get_column_{kind}_nullable")(j)
-                        got += int(valid.shape[0])
+                    blobs.append((kind, res._blob(kind, j, True)))
+                t2 = time.perf_counter()
+                tsplit["c_getters_s"] += t2 - t1
+                got += sum(pool.map(lambda kb: decode_one(res, kb[0], kb[1]), blobs))
+                tsplit["decode_s"] += time.perf_counter() - t2
                 res.close()
             return got
 
@@ -909,15 +945,20 @@ def run_ours(args, rank, local_rank, world):
         barrier()
         t0 = time.perf_counter()
         kg = max(1, min(side_steps, 3))
+        for k_ in tsplit:
+            tsplit[k_] = 0.0
         for _ in range(kg):
             getters_step()
         secs = max_over_ranks(time.perf_counter() - t0)
         barrier()
         e2e_getters = {"value": world * rows_res * kg / secs, "unit": UNIT, "ms_per_step": 1e3 * secs / kg, "steps": kg,
                        "rows_per_step_per_gpu": rows_res, "results_per_step": len(subs),
+                       "ms_per_step_split": {k_: 1e3 * v_ / kg for k_, v_ in tsplit.items()},
+                       "c_abi_only_rows_per_s": world * rows_res * kg / max(tsplit["from_chunks_s"] + tsplit["c_getters_s"], 1e-9),
                        "what": "per <= 1 M-row result (the reference decoders' cap): duckdb_mb_gpu_result_from_chunks on the DuckDB "
                                "layout + the 16 duckdb_mb_arrow_get_column_*_nullable getters the schema selects + the decoder mirror "
-                               "(arrow_result.py) -- the surface --impl reference times on the CPU"}
+                               "(arrow_result.py, columns decoded on a thread pool) -- the surface --impl reference times on the CPU"}
+        pool.shutdown()
         del subs, hb2, layout
     elif not args.no_layout_leg:
         e2e_layout = {"skipped": f"host has {mem_available_gb():.0f} GB available, the leg needs ~{need_gb:.0f} GB more"}

@@ -280,22 +280,7 @@ class ArrowResult:
         """The nullable string decoder's scan (:752-784) without building a String per row: (starts, ends, valid, blob)
         with row i = blob[starts[i]:ends[i]].  Row i ends at the i-th NUL at or after byte 8 (or at the end of the blob)."""
         with self._blob("string", col, True) as view:
-            data = view.copy()  # the decoded column: one copy of the stream + the spans into it
-        count = self._count_ok(data, 8)
-        z = np.zeros(0, dtype=np.int64)
-        if not count:
-            return z, z, np.zeros(0, dtype=bool), data
-        total = _read_int32_le(data, 4)
-        if len(data) < 8 + total + count:
-            return z, z, np.zeros(0, dtype=bool), data
-        nul = np.flatnonzero(data[8:] == 0)[:count].astype(np.int64) + 8
-        ends = np.full(count, len(data), dtype=np.int64)
-        ends[: nul.shape[0]] = nul
-        starts = np.empty(count, dtype=np.int64)
-        starts[0] = 8
-        starts[1:] = np.minimum(ends[:-1] + 1, len(data))
-        valid = data[8 + total: 8 + total + count] != 0
-        return starts, ends, valid, data
+            return decode_string_spans(view, True)
 
     def get_column_string(self, col: int) -> List[str]:  # :546-575
         return self._decode_strings(self.raw_column("string", col), False)
@@ -353,15 +338,54 @@ class ArrowResult:
         st = nat.ArrowArrayStream()
         if not self.lib.duckdb_mb_gpu_result_export_stream(self.handle, int(max_batch_rows), C.addressof(st)):
             raise DuckDBError(nat.last_error())
-        reader = pa.RecordBatchReader._import_from_c(C.addressof(st))
-        reader._dmb_keep = (self._host_batch,)
-        return reader
+        return _keepalive_reader(pa.RecordBatchReader._import_from_c(C.addressof(st)), (self._host_batch,))
 
     def to_record_batch(self):
         import pyarrow as pa
 
         arr, sch = self.export_c(-1)
         return pa.RecordBatch._import_from_c(C.addressof(arr), C.addressof(sch))
+
+
+def _keepalive_reader(inner, keep):
+    """a RecordBatchReader over `inner` whose generator keeps the host chunk vectors alive until it is exhausted / closed"""
+    import pyarrow as pa
+
+    def batches(_keep=keep):
+        for b in inner:
+            yield b
+
+    return pa.RecordBatchReader.from_batches(inner.schema, batches())
+
+
+def _nul_positions(stream: np.ndarray, limit: int) -> np.ndarray:
+    """positions of the first `limit` NUL bytes of a uint8 array"""
+    return np.flatnonzero(stream == 0)[:limit].astype(np.int64)
+
+
+def decode_string_spans(view, nullable: bool):
+    """decoder mirror of the string blob [n:i32][total:i32][s0\\0 s1\\0 ...][valid bytes]: one copy of the stream + the spans
+    into it.  Row i ends at the i-th NUL at or after byte 8; only the `total` stream bytes are scanned when they hold a NUL
+    per row (every non-NULL layout), else the scan runs on into the validity bytes exactly like the reference's loop."""
+    data = np.array(view, dtype=np.uint8, copy=True)
+    z = np.zeros(0, dtype=np.int64)
+    count = ArrowResult._count_ok(data, 8)
+    if not count:
+        return z, z, np.zeros(0, dtype=bool), data
+    total = _read_int32_le(data, 4)
+    if nullable and len(data) < 8 + total + count:
+        return z, z, np.zeros(0, dtype=bool), data
+    nul = _nul_positions(data[8: 8 + total], count)
+    if nul.shape[0] < count:  # NULL rows' terminators are not counted in `total`: the reference's scan runs on
+        nul = _nul_positions(data[8:], count)
+    nul = nul + 8
+    ends = np.full(count, len(data), dtype=np.int64)
+    ends[: nul.shape[0]] = nul
+    starts = np.empty(count, dtype=np.int64)
+    starts[0] = 8
+    starts[1:] = np.minimum(ends[:-1] + 1, len(data))
+    valid = (data[8 + total: 8 + total + count] != 0) if nullable else np.ones(count, dtype=bool)
+    return starts, ends, valid, data
 
 
 class ShardedResult:
@@ -411,9 +435,7 @@ class ShardedResult:
         if not self.lib.duckdb_mb_gpu_sharded_export_stream(self.handle, C.addressof(st)):
             raise DuckDBError(nat.last_error())
         self.handle = None  # the stream owns it now
-        reader = pa.RecordBatchReader._import_from_c(C.addressof(st))
-        reader._dmb_keep = (self._hb,)
-        return reader
+        return _keepalive_reader(pa.RecordBatchReader._import_from_c(C.addressof(st)), (self._hb,))
 
     def close(self) -> None:
         if self.handle:

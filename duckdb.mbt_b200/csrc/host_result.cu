@@ -2138,12 +2138,19 @@ extern "C" duckdb_mb_gpu_sharded *duckdb_mb_gpu_result_shard(duckdb_mb_arrow_res
   s->first_row.push_back(0);
   for (int64_t g = 0; g < G; ++g) {
     const int64_t g0 = g * per_gpu < C ? g * per_gpu : C, g1 = g0 + per_gpu < C ? g0 + per_gpu : C;
-    for (int64_t c0 = g0; c0 < g1 || (C == 0 && g == 0 && s->parts.empty()); c0 += chunks_per_part > 0 ? chunks_per_part : 1) {
+    if (g0 >= g1) {  // fewer chunks than contexts: this context's part is an empty record batch
+      if (max_rows_per_part <= 0 || s->parts.empty()) {
+        Result *part = slice_result(r, cores[(size_t)g], g0, g0);
+        s->parts.push_back(part);
+        s->first_row.push_back(s->first_row.back());
+      }
+      continue;
+    }
+    for (int64_t c0 = g0; c0 < g1; c0 += chunks_per_part) {
       const int64_t c1 = c0 + chunks_per_part < g1 ? c0 + chunks_per_part : g1;
-      Result *part = slice_result(r, cores[(size_t)g], c0, c1 > c0 ? c1 : c0);
+      Result *part = slice_result(r, cores[(size_t)g], c0, c1);
       s->parts.push_back(part);
       s->first_row.push_back(s->first_row.back() + part->nrows);
-      if (C == 0) break;
     }
   }
   for (size_t j = 0; j < r->cols.size(); ++j) {

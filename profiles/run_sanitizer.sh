@@ -10,11 +10,11 @@ mkdir -p $out
 export DMB_SANITIZER=1
 SAN=/usr/local/cuda/bin/compute-sanitizer
 cd "$(dirname "$0")/.."
-timeout 1500 $SAN --tool memcheck --error-exitcode 9 --print-limit 20 --log-file $out/${tag}_memcheck.log \
+timeout 1200 $SAN --tool memcheck --error-exitcode 9 --print-limit 20 --log-file $out/${tag}_memcheck.log \
   python -m pytest tests -x -q -m gpu --ignore=tests/test_gpu_scale.py -p no:cacheprovider > $out/${tag}_memcheck_pytest.log 2>&1
 echo "memcheck exit: $?" | tee -a $out/${tag}_memcheck_pytest.log
 tail -5 $out/${tag}_memcheck.log
-timeout 1500 $SAN --tool racecheck --racecheck-report all --error-exitcode 9 --print-limit 20 --log-file $out/${tag}_racecheck.log \
+timeout 900 $SAN --tool racecheck --racecheck-report all --error-exitcode 9 --print-limit 20 --log-file $out/${tag}_racecheck.log \
   python -m pytest tests/test_gpu_l0_parity.py tests/test_gpu_l0_reverse.py tests/test_gpu_l0_list.py tests/test_gpu_enum.py tests/test_gpu_render.py \
   -x -q -m gpu -p no:cacheprovider > $out/${tag}_racecheck_pytest.log 2>&1
 echo "racecheck exit: $?" | tee -a $out/${tag}_racecheck_pytest.log
