@@ -562,9 +562,6 @@ struct PackTail {
   unsigned long long mbar_s[2];
   unsigned long long mbar_h[2];
   unsigned long long base[kMetaRing];
-  unsigned long long mbar_b[kMetaRing];  // L -> workers: base of tile k resolved
-  unsigned long long mbar_q[kMetaRing];  // workers -> L: tile k scanned (its look-back is due within an iteration)
-  unsigned long long mbar_f[kMetaRing];  // P -> L: tile k's aggregate is published (one phase per use)
   TileMeta meta[kMetaRing];
   PackPartials part[2];
   alignas(16) unsigned long long vmask[2][kVec / 64];  // validity words of the tile in S[slot] (bulk-copy destination)
@@ -625,7 +622,12 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // named barriers: `sync` waits, `arrive` only signals; n = arriving + waiting threads
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-enum { kBarWorkers = 1, kBarBase = 3, kBarPacked = 4 };
+// role <-> role hand-offs inside a CTA are NAMED BARRIERS (bar.arrive / bar.sync): a warp that waits on one is parked by
+// the hardware and issues nothing.  (As mbarrier.try_wait loops they took a quarter of the kernel's issue slots away
+// from the warps that were packing.)  F: worker warp 0 -> L, "tile k is scanned and its aggregate is out" (64 threads);
+// B: L -> workers, "tile k's base is resolved" (workers + 32).  Each comes as an alternating pair: the producer of
+// phase k + 2 cannot reach its arrive before the consumer has left phase k (see the order of front / back below).
+enum { kBarWorkers = 1, kBarBase = 3, kBarPacked = 4, kBarF0 = 5, kBarF1 = 6, kBarB0 = 7, kBarB1 = 8 };
 
 // bytes [b0, b1) of `v` into the word at `w` (the other bytes belong to neighbouring threads)
 __device__ __forceinline__ void store_bytes(uint32_t *w, uint32_t v, uint32_t b0, uint32_t b1) {
@@ -752,7 +754,6 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
     mbar_init(smem_u32(&pt.mbar_s[1]), 1);
     mbar_init(smem_u32(&pt.mbar_h[0]), 1);
     mbar_init(smem_u32(&pt.mbar_h[1]), 1);
-    for (int k = 0; k < kMetaRing; ++k) { mbar_init(smem_u32(&pt.mbar_f[k]), 1); mbar_init(smem_u32(&pt.mbar_b[k]), 1); mbar_init(smem_u32(&pt.mbar_q[k]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -847,14 +848,11 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
     // ------------------------------------------------------------ L: look-back
     for (int k = 0;; ++k) {
       const TileMeta &m = pt.meta[k & (kMetaRing - 1)];
-      mbar_wait(smem_u32(&pt.mbar_f[k & (kMetaRing - 1)]), (uint32_t)(k / kMetaRing) & 1u);  // tile k's aggregate is out
+      // a lazy look-back is a short one: by the time the workers have scanned tile k its predecessors' aggregates (often
+      // their prefixes) are out, and the result is not needed before tile k-1 is packed
+      bar_sync(kBarF0 + (k & 1), 64);  // tile k is scanned, its aggregate is published (or there is no tile k)
       const long long tile = m.tile;
       if (tile < 0) break;
-      // a lazy look-back is a short one: by the time the workers have scanned tile k its predecessors'
-      // aggregates (often their prefixes) are out, and the result is not needed before tile k-1 is packed
-#ifndef DMB_LOOK_EAGER
-      mbar_wait(smem_u32(&pt.mbar_q[k & (kMetaRing - 1)]), (uint32_t)(k / kMetaRing) & 1u);
-#endif
       if (lane == 0) DMB_PTRACE(k, 8);
 #ifdef DMB_STR_TRACE
       unsigned lb_stats = 0;
@@ -867,9 +865,9 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         if (tile > 0) atomicExch(status + tile, kFlagPrefix | ((base + m.total) & kValueMask));
         pt.base[k & (kMetaRing - 1)] = base;
         DMB_PTRACE(k, 15);
-        mbar_arrive(smem_u32(&pt.mbar_b[k & (kMetaRing - 1)]));  // the workers may place tile k
       }
       __syncwarp();
+      bar_arrive(kBarB0 + (k & 1), kWT + 32);  // the workers may place tile k
     }
     return;
   }
@@ -969,8 +967,6 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         // iteration earlier, made the look-backs behind it a little shorter but cost 3 % of the kernel: every row was read twice)
         m.total = total;
         atomicExch(status + m.tile, (m.tile == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)total);
-        mbar_arrive(smem_u32(&pt.mbar_f[j & (kMetaRing - 1)]));
-        mbar_arrive(smem_u32(&pt.mbar_q[j & (kMetaRing - 1)]));  // L: tile j's look-back is due
         if (HEAP && staged && hbytes) {
           const uint32_t mb = smem_u32(&pt.mbar_h[slot]);
           mbar_expect_tx(mb, hbytes);
@@ -978,13 +974,16 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         }
       }
     }
-    if (!nxt_valid && tid == 0) mbar_arrive(smem_u32(&pt.mbar_f[j & (kMetaRing - 1)]));  // L: no tile j
+    if (warp == 0) {  // L: tile j's look-back is due (or: there is no tile j)
+      __syncwarp();
+      bar_arrive(kBarF0 + (j & 1), 64);
+    }
     if (tid == 0) DMB_PTRACE(j, 2);
 
     // ---- back(tile j-1)
     uint64_t base = 0;
     if (cur_valid) {
-      mbar_wait(smem_u32(&pt.mbar_b[(j - 1) & (kMetaRing - 1)]), (uint32_t)((j - 1) / kMetaRing) & 1u);  // L has resolved tile j-1
+      bar_sync(kBarB0 + ((j - 1) & 1), kWT + 32);  // L has resolved tile j-1
       base = pt.base[(j - 1) & (kMetaRing - 1)];
     }
     if (tid == 0) DMB_PTRACE(j, 3);
