@@ -397,7 +397,14 @@ struct StringSource {
   size_t max_row_bytes = 0;                   // ENUM: longest label
   bool fused_enum = false;                    // ENUM with a small dictionary of short labels: indices -> utf8 in one launch (dmb_dev_enum_utf8)
   dmb_enum_job ejob{};
+  // a source that is not laid out in the result's chunks (BLOB text: dense rows cut into 2048-row pseudo chunks)
+  const uint32_t *counts = nullptr;
+  const int64_t *row_off = nullptr;
+  const uint64_t *validity = nullptr;
+  int64_t nchunks = -1;
 };
+
+int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool want_valid_bytes, struct StringRun *out, size_t exact_cap, bool as_text);
 
 // a column whose VARCHAR form the device produces: strings, the rendered scalar types, ENUM with its dictionary
 bool text_supported(const Col &col) {
@@ -406,10 +413,16 @@ bool text_supported(const Col &col) {
   return dmb_render_supported(col.type_id, col.phys) != 0;
 }
 
-int32_t string_source(Result *r, Scope &sc, int j, bool arrow_mode, StringSource *src) {
+// BLOB as text (getters, per-cell symbols, typed Value::String): the VARCHAR cast escapes the bytes.  Pass 1 turns the
+// column into its dense raw form (offsets + data), the escape kernel writes one string_t per row over a 4x heap, and the
+// caller's string pass runs over those rows as 2048-row pseudo chunks with pass 1's bitmap as their masks.
+int32_t blob_text_source(Result *r, Scope &sc, int j, StringSource *src);
+
+int32_t string_source(Result *r, Scope &sc, int j, bool arrow_mode, bool as_text, StringSource *src) {
   if (stage_column(r, j)) return -1;
   CtxCore &c = *r->core;
   Col &col = r->cols[(size_t)j];
+  if (col.phys == DMB_PHYS_STRING && col.type_id == DMB_TYPE_BLOB && as_text) return blob_text_source(r, sc, j, src);
   if (col.phys == DMB_PHYS_STRING) {
     src->in = (const dmb_string_t *)col.d_data;
     src->vecs = col.d_vecs;
@@ -515,9 +528,12 @@ int32_t string_source(Result *r, Scope &sc, int j, bool arrow_mode, StringSource
 }
 
 // exact_cap != 0: the data bytes the column is known to need (a first launch reported them, see kStrFlagDataCap)
-int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool want_valid_bytes, StringRun *out, size_t exact_cap = 0) {
+// as_text: the column's VARCHAR rendering is wanted (getters, text / typed columns): a BLOB is escaped; false: the Arrow
+// export, which keeps BLOB bytes as they are
+int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool want_valid_bytes, StringRun *out, size_t exact_cap = 0,
+                   bool as_text = true) {
   StringSource src;
-  if (string_source(r, sc, j, mode != DMB_STR_REF_BLOB, &src)) return -1;
+  if (string_source(r, sc, j, mode != DMB_STR_REF_BLOB, as_text, &src)) return -1;
   CtxCore &c = *r->core;
   Col &col = r->cols[(size_t)j];
   const int64_t n = r->nrows;
@@ -525,13 +541,14 @@ int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool
   out->offsets_bytes = (size_t)(n + 1) * (mode == DMB_STR_ARROW_LARGE ? 8 : 4);
   out->d_offsets = sc.dalloc(out->offsets_bytes + 64);
   // rendered text: at most one slot per row; ENUM: at most the longest label per row
+  const bool blob_text = src.nchunks >= 0;
   const size_t per_row = col.phys == DMB_PHYS_STRING ? 12 : (col.type_id == DMB_TYPE_ENUM ? (src.max_row_bytes > 12 ? src.max_row_bytes : 12) : (size_t)dmb_render_slot_bytes(col.type_id));
   // (string_t entries may alias heap bytes -- a flattened dictionary vector does -- so this is a first guess, not a bound:
   // the kernels check it and report the exact total, and the caller launches again with exact_cap)
-  out->data_cap = per_row * (size_t)n + (col.phys == DMB_PHYS_STRING ? (size_t)col.d_heap_len : 0) + (mode == DMB_STR_REF_BLOB ? (size_t)n : 0);
+  out->data_cap = per_row * (size_t)n + (col.phys == DMB_PHYS_STRING ? (size_t)(blob_text ? src.heap_len : col.d_heap_len) : 0) + (mode == DMB_STR_REF_BLOB ? (size_t)n : 0);
   if (exact_cap) { out->data_cap = exact_cap; out->exact = true; }
   out->d_data = (uint8_t *)sc.dalloc(out->data_cap + 64);
-  out->d_scratch = sc.dalloc(dmb_dev_string_scratch_bytes(r->nchunks));
+  out->d_scratch = sc.dalloc(dmb_dev_string_scratch_bytes(blob_text ? src.nchunks : r->nchunks));
   out->d_total = (unsigned long long *)sc.dalloc(8);
   out->h_ctr = (unsigned long long *)sc.palloc(32);
   if (!out->d_offsets || !out->d_data || !out->d_scratch || !out->d_total || !out->h_ctr) return -1;
@@ -542,7 +559,7 @@ int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool
   dmb_string_job job;
   memset(&job, 0, sizeof(job));
   job.in = src.in;
-  job.in_validity = col.d_validity;
+  job.in_validity = blob_text ? src.validity : col.d_validity;
   job.vecs = src.vecs;
   job.heap_dev = src.heap;
   job.heap_host_base = src.heap_host_base;
@@ -555,8 +572,9 @@ int32_t run_string(Result *r, Scope &sc, int j, int mode, bool want_bitmap, bool
   cudaEvent_t k0 = sc.event(true), k1 = sc.event(true), done = sc.event(false);
   if (!k0 || !k1 || !done) return -1;
   cudaEventRecord(k0, c.s_compute);
-  if (src.fused_enum ? dmb_dev_enum_utf8(&src.ejob, &job, r->d_counts, r->d_row_off, r->nchunks, n, out->d_scratch, c.s_compute)
-                     : dmb_dev_string_batch(&job, r->d_counts, r->d_row_off, r->nchunks, n, out->d_scratch, c.s_compute)) return -1;
+  if (blob_text ? dmb_dev_string_batch(&job, src.counts, src.row_off, src.nchunks, n, out->d_scratch, c.s_compute)
+      : src.fused_enum ? dmb_dev_enum_utf8(&src.ejob, &job, r->d_counts, r->d_row_off, r->nchunks, n, out->d_scratch, c.s_compute)
+                       : dmb_dev_string_batch(&job, r->d_counts, r->d_row_off, r->nchunks, n, out->d_scratch, c.s_compute)) return -1;
   cudaEventRecord(k1, c.s_compute);
   sc.kernel_spans.emplace_back(k0, k1);
   // the data length is needed on the host to size the device->host copy; flags travel with it
@@ -596,6 +614,53 @@ int32_t run_string_sync(Result *r, Scope &sc, int j, int mode, bool want_bitmap,
     return string_flags_error(flags | (out->h_ctr[3] ? (1ull << 63) : 0ull));
   }
   return -1;
+}
+
+int32_t blob_text_source(Result *r, Scope &sc, int j, StringSource *src) {
+  CtxCore &c = *r->core;
+  const int64_t n = r->nrows;
+  StringRun raw;  // pass 1: the BLOB bytes, dense (a BLOB column beyond 2 GiB cannot be one getter blob anyway)
+  if (run_string(r, sc, j, DMB_STR_ARROW_UTF8, true, false, &raw, 0, /*as_text=*/false)) return -1;
+  if (check_cuda(cudaEventSynchronize(raw.done), "blob pass wait")) return -1;
+  if ((raw.h_ctr[1] & kStrFlagDataCap) && !(raw.h_ctr[1] & ~kStrFlagDataCap)) {  // aliased pointers: sized exactly, once more
+    const size_t exact = (size_t)raw.h_ctr[0];
+    raw = StringRun();
+    if (run_string(r, sc, j, DMB_STR_ARROW_UTF8, true, false, &raw, exact, false)) return -1;
+    if (check_cuda(cudaEventSynchronize(raw.done), "blob pass wait")) return -1;
+  }
+  if (string_flags_error(raw.h_ctr[1])) return -1;
+  const uint64_t total = raw.h_ctr[0];
+  const int64_t nck = n > 0 ? (n + DMB_VECTOR_SIZE - 1) / DMB_VECTOR_SIZE : 0;
+  const size_t nslots = (size_t)(nck > 0 ? nck : 1) * DMB_VECTOR_SIZE;
+  dmb_string_t *d_str = (dmb_string_t *)sc.dalloc(nslots * sizeof(dmb_string_t));
+  uint8_t *d_heap = (uint8_t *)sc.dalloc((size_t)total * 4 + 64);
+  // the masks of the pseudo chunks: pass 1's bitmap, copied into whole 32-word masks (the kernels fetch whole tiles of mask words)
+  uint64_t *d_masks = (uint64_t *)sc.dalloc(nslots / 8 + 64);
+  if (!d_str || !d_heap || !d_masks) return -1;
+  if (check_cuda(cudaMemsetAsync(d_masks, 0, nslots / 8, c.s_compute), "blob masks memset")) return -1;
+  if (raw.validity.bitmap_bytes && check_cuda(cudaMemcpyAsync(d_masks, raw.validity.d_bitmap, raw.validity.bitmap_bytes, cudaMemcpyDeviceToDevice, c.s_compute), "blob masks copy")) return -1;
+  if (dmb_dev_blob_escape((const int32_t *)raw.d_offsets, raw.d_data, n, d_str, d_heap, 1ull << 42, c.s_compute)) return -1;
+  std::vector<uint32_t> cc((size_t)(nck > 0 ? nck : 1), DMB_VECTOR_SIZE);
+  std::vector<int64_t> ro((size_t)nck + 1);
+  std::vector<dmb_vec_desc> vd((size_t)(nck > 0 ? nck : 1));
+  if (nck) cc[(size_t)nck - 1] = (uint32_t)(n - (nck - 1) * DMB_VECTOR_SIZE);
+  for (int64_t k = 0; k < nck; ++k) {
+    ro[(size_t)k] = k * (int64_t)DMB_VECTOR_SIZE;
+    vd[(size_t)k].data_off = (uint64_t)k * DMB_VECTOR_SIZE * sizeof(dmb_string_t);
+    vd[(size_t)k].val_off = k * DMB_VALIDITY_WORDS;
+  }
+  ro[(size_t)nck] = n;
+  src->counts = (const uint32_t *)upload_job(sc, cc.data(), cc.size() * sizeof(uint32_t));
+  src->row_off = (const int64_t *)upload_job(sc, ro.data(), ro.size() * sizeof(int64_t));
+  src->vecs = (const dmb_vec_desc *)upload_job(sc, vd.data(), vd.size() * sizeof(dmb_vec_desc));
+  if (!src->counts || !src->row_off || !src->vecs) return -1;
+  src->in = d_str;
+  src->heap = d_heap;
+  src->heap_host_base = 1ull << 42;
+  src->heap_len = total * 4;
+  src->validity = d_masks;
+  src->nchunks = nck;
+  return 0;
 }
 
 // ------------------------------------------------------------------ LIST columns (kernels_list.cu)
@@ -861,7 +926,7 @@ int32_t launch_arrow_col(Result *r, Scope &sc, int j, int string_mode, Pending *
   }
   if (p->map.is_string) {
     p->sr = StringRun();
-    if (run_string(r, sc, j, string_mode, true, false, &p->sr, exact_cap)) return -1;
+    if (run_string(r, sc, j, string_mode, true, false, &p->sr, exact_cap, /*as_text=*/false)) return -1;
     p->out->format = string_mode == DMB_STR_ARROW_LARGE ? (col.type_id == DMB_TYPE_BLOB ? "Z" : "U") : p->map.format;
   } else {
     p->fr = FixedRun();
@@ -1767,10 +1832,6 @@ namespace {
 moonbit_bytes_t cell_text(Result *r, int32_t col, int64_t row) {
   if (!r || col < 0 || col >= r->column_count || row < 0 || row >= r->nrows) return empty_bytes();
   Col &c = r->cols[(size_t)col];
-  if (c.type_id == DMB_TYPE_BLOB) {  // duckdb_value_varchar escapes BLOB bytes (\xAA): not reproduced
-    set_error("column %d: libduckdb's text rendering of BLOB is not reproduced on the device", col);
-    return empty_bytes();
-  }
   dmb_typed_column t;
   {
     std::lock_guard<std::mutex> g(r->core->mu);

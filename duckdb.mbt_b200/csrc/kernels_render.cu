@@ -455,6 +455,57 @@ extern "C" int32_t dmb_render_slot_bytes(int32_t type_id) {
   return type_id == DMB_TYPE_INTERVAL ? DMB_RENDER_SLOT_BYTES_WIDE : DMB_RENDER_SLOT_BYTES;
 }
 
+namespace dmb {
+// BLOB -> its VARCHAR cast (DuckDB Blob::ToString): printable ASCII except backslash and the two quote characters is
+// copied, every other byte becomes \xHH (upper-case hex).  One thread per row of a DENSE utf8-style column (offsets +
+// data, what dmb_dev_string_batch produced from the BLOB column); row i's escaped bytes go to out_heap + 4 * offsets[i]
+// (a byte grows to at most four), the row's string_t refers to them.  Replaces libduckdb's duckdb_value_varchar on a BLOB
+// cell (src/duckdb_native.c:224-238, :2478, :2715).  UNPINNED: no reference test reads a BLOB as text.
+__global__ void __launch_bounds__(kThreads)
+blob_escape_kernel(const int32_t *__restrict__ offsets, const uint8_t *__restrict__ data, int64_t nrows, dmb_string_t *__restrict__ out,
+                   uint8_t *__restrict__ out_heap, uint64_t heap_host_base) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nrows; i += (int64_t)gridDim.x * kThreads) {
+    const uint32_t o0 = (uint32_t)offsets[i], o1 = (uint32_t)offsets[i + 1];
+    uint8_t *dst = out_heap + 4ull * o0;
+    uint32_t n = 0;
+    for (uint32_t q = o0; q < o1; ++q) {
+      const uint8_t c = data[q];
+      if (c >= 32 && c <= 126 && c != '\\' && c != '\'' && c != '"') {
+        dst[n++] = c;
+      } else {
+        const char *hex = "0123456789ABCDEF";
+        dst[n++] = '\\';
+        dst[n++] = 'x';
+        dst[n++] = (uint8_t)hex[c >> 4];
+        dst[n++] = (uint8_t)hex[c & 15];
+      }
+    }
+    uint4 e = make_uint4(n, 0, 0, 0);
+    uint8_t *eb = reinterpret_cast<uint8_t *>(&e);
+    if (n <= 12u) {
+      for (uint32_t k = 0; k < n; ++k) eb[4 + k] = dst[k];
+    } else {
+      for (uint32_t k = 0; k < 4; ++k) eb[4 + k] = dst[k];
+      const uint64_t p = heap_host_base + 4ull * o0;
+      e.z = (uint32_t)p;
+      e.w = (uint32_t)(p >> 32);
+    }
+    reinterpret_cast<uint4 *>(out)[i] = e;
+  }
+}
+
+}  // namespace dmb
+using namespace dmb;
+
+extern "C" int32_t dmb_dev_blob_escape(const int32_t *offsets, const uint8_t *data, int64_t nrows, dmb_string_t *out, uint8_t *out_heap,
+                                       uint64_t heap_host_base, void *stream) {
+  if (nrows <= 0) return 0;
+  const int64_t blocks = (nrows + kThreads - 1) / kThreads;
+  const int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
+  blob_escape_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(offsets, data, nrows, out, out_heap, heap_host_base);
+  return check_cuda(cudaGetLastError(), "blob_escape_kernel launch");
+}
+
 extern "C" int32_t dmb_render_supported(int32_t type_id, int32_t phys) {
   switch (type_id) {
     case DMB_TYPE_BOOLEAN: case DMB_TYPE_TINYINT: case DMB_TYPE_SMALLINT: case DMB_TYPE_INTEGER: case DMB_TYPE_BIGINT:

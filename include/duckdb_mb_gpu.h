@@ -254,6 +254,14 @@ int32_t dmb_render_supported(int32_t type_id, int32_t phys);
 int32_t dmb_render_slot_bytes(int32_t type_id); /* out_heap bytes per row for this type (48, INTERVAL: 80) */
 int32_t dmb_dev_render_text(const dmb_render_job *job, const uint32_t *counts, int64_t nchunks, void *stream);
 
+/* BLOB -> text: the VARCHAR cast of a BLOB cell (DuckDB Blob::ToString: printable ASCII except backslash and quotes as it
+ * is, every other byte as \xHH).  Input: the dense utf8-style form of the column (int32 offsets[n+1] + data, as produced by
+ * dmb_dev_string_batch); output: one string_t per row referring to out_heap (>= 4 * offsets[n] bytes; row i's text at
+ * out_heap + 4 * offsets[i]), ready for dmb_dev_string_batch.  Replaces libduckdb's duckdb_value_varchar on a BLOB cell
+ * (src/duckdb_native.c:224-238, :2478, :2715; chunk path :604-610).  UNPINNED. */
+int32_t dmb_dev_blob_escape(const int32_t *offsets, const uint8_t *data, int64_t nrows, dmb_string_t *out, uint8_t *out_heap,
+                            uint64_t heap_host_base, void *stream);
+
 /* K8: ENUM index vectors -> string_t that refer to the dictionary's labels (<= 12 bytes inlined, else
  * prefix + dict_host_base + offset), one 2048-entry slot per chunk; feed the result to
  * dmb_dev_string_batch with the dictionary bytes as the heap.  Rows whose validity bit is clear get a

@@ -310,6 +310,24 @@ __attribute__((noinline)) char *ora_value_varchar(ora_result *r, int32_t col, in
   if (col < 0 || col >= r->column_count || row < 0 || row >= r->nrows) return NULL;
   if (r->dep_null[col][row]) return NULL;
   const ora_column *c = &r->batch.cols[col];
+  if (c->phys == P_STRING && c->type_id == T_BLOB) {
+    /* duckdb_value_varchar of a BLOB cell is its VARCHAR cast, DuckDB Blob::ToString: printable ASCII except backslash and
+     * the quote characters as it is, every other byte as \xHH (upper-case hex).  The bytes come from the chunk vector (the
+     * deprecated column keeps {data, size}, so embedded NULs survive).  UNPINNED: no reference test reads a BLOB as text. */
+    int64_t k = 0;
+    while (k + 1 < r->batch.nchunks && r->row_off[k + 1] <= row) k++;
+    const ora_string_t *e = (const ora_string_t *)vec_data(c, k) + (row - r->row_off[k]);
+    const uint8_t *src = (const uint8_t *)string_t_data(e);
+    char *out = (char *)malloc((size_t)e->length * 4 + 1);
+    size_t n = 0;
+    for (uint32_t i = 0; i < e->length; i++) {
+      uint8_t ch = src[i];
+      if (ch >= 32 && ch <= 126 && ch != '\\' && ch != '\'' && ch != '"') out[n++] = (char)ch;
+      else { static const char hex[] = "0123456789ABCDEF"; out[n++] = '\\'; out[n++] = 'x'; out[n++] = hex[ch >> 4]; out[n++] = hex[ch & 15]; }
+    }
+    out[n] = 0;
+    return out;
+  }
   if (c->phys == P_STRING) {
     const char *s = ((char **)r->dep_data[col])[row];
     /* the deprecated column keeps a C string, so the copy stops at the first NUL */

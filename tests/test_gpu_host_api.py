@@ -440,3 +440,27 @@ def test_string_spans_decoder_equals_the_string_decoder(ctx):
         starts, ends, valid2, blob = res.get_column_string_spans_nullable(col)
         assert np.array_equal(valid, valid2)
         assert [bytes(blob[s:e]).decode("utf-8", errors="replace") for s, e in zip(starts, ends)] == strs
+
+
+def test_blob_cells_read_as_their_varchar_cast(ctx):
+    """BLOB through the text surfaces (string getter, per-cell value, typed Value::String): escaped like DuckDB's
+    Blob::ToString; the Arrow export keeps the raw bytes (binary)."""
+    from duckdb_mbt_b200 import native as nat
+    from duckdb_mbt_b200 import typed_result as tr
+    rng = np.random.default_rng(13)
+    n = 6000
+    vals = [None if rng.random() < 0.15 else bytes(rng.integers(0, 256, int(rng.integers(0, 40)), dtype=np.uint8)) for _ in range(n)]
+    vals[:3] = [b"abc", b"\x00\xff'q\"\\z", b""]
+    counts = ch.chunk_counts(n, "ragged", rng)
+    batch = ch.ChunkBatch(counts, [ch.string_column("b", vals, counts, type_id=ch.T_BLOB),
+                                   ch.fixed_column("i", ch.T_INTEGER, np.arange(n, dtype=np.int32), counts)])
+    ora = oracle.OracleResult(batch)
+    with _result(ctx, batch) as res:
+        for nullable in (True, False):
+            assert res.raw_column("string", 0, nullable) == ora.get_column("string", 0, nullable)
+        L = res.lib
+        L.duckdb_mb_result_value.restype = C.c_void_p
+        for row in (0, 1, 2, 17, n - 1):
+            assert nat.moonbit_bytes(L.duckdb_mb_result_value(C.c_void_p(res.handle), 0, row)) == ora.cell_value(0, row)
+        arr = res.to_arrow(0)
+        assert str(arr.type) == "binary" and arr.to_pylist() == vals

@@ -474,3 +474,14 @@ def test_getters_cast_by_logical_type_known_answers():
     assert d38.tolist() == exp
     d38f = np.frombuffer(r.get_column("double", 4)[4:], dtype="<f8")
     assert d38f[1] == 0.001 and d38f[2] == -0.001 and d38f[5] == float(2**63 // 1000) + float(2**63 % 1000) / 1000.0
+
+
+def test_blob_text_known_answers():
+    """duckdb_value_varchar of a BLOB is its VARCHAR cast (Blob::ToString): printable ASCII except backslash and the quote
+    characters as it is, every other byte as \\xHH (UNPINNED: no reference test reads a BLOB as text)."""
+    b = batch_of(("b", ch.T_BLOB, [b"abc", b"\x00\xff'q\"\\z", None, b"x" * 20 + b"\n", b""]))
+    r = oracle.OracleResult(b)
+    assert [r.cell_value(0, i) for i in range(5)] == [b"abc", b"\\x00\\xFF\\x27q\\x22\\x5Cz", b"", b"x" * 20 + b"\\x0A", b""]
+    strs, valid = oracle.decode_string(r.get_column("string", 0, True), True)
+    assert valid.tolist() == [True, True, False, True, True]
+    assert strs[0] == b"abc" and strs[1] == b"\\x00\\xFF\\x27q\\x22\\x5Cz"
