@@ -82,50 +82,79 @@ class HostBatch:
         self._cols = (nat.HostColumn * max(ncols, 1))()
         self._keep = []
         for j, col in enumerate(batch.columns):
-            base = col.data.ctypes.data
-            data_ptrs = (np.asarray(col.data_off, dtype=np.uint64) + np.uint64(base)).astype(np.uint64)
-            if data_ptrs.shape[0] == 0:
-                data_ptrs = np.zeros(1, dtype=np.uint64)
-            val_ptrs = None
-            if col.validity is not None and np.any(col.val_off >= 0):
-                vbase = col.validity.ctypes.data
-                vo = np.asarray(col.val_off, dtype=np.int64)
-                val_ptrs = np.where(vo >= 0, vbase + 8 * vo, 0).astype(np.uint64)
-            name = col.name.encode()
-            heap_base, heap_len = None, 0
-            if getattr(col, "heap", None) is not None and register_heap:
-                heap_base, heap_len = col.heap.ctypes.data, int(col.heap.shape[0])
-            elif getattr(col, "inline_only", False):
-                heap_base, heap_len = 1, 0  # DMB_HEAP_INLINE_ONLY
-            dict_ptr = None
-            if getattr(col, "dictionary", None) is not None:  # ENUM: dmb_enum_dict
-                from . import chunks as _ch
-                d_offs, d_data = _ch.enum_dict_arrays(col.dictionary)
-                ed = nat.EnumDict(len(col.dictionary), 0, d_offs.ctypes.data, d_data.ctypes.data)
-                self._keep.append((d_offs, d_data, ed))
-                dict_ptr = C.pointer(ed)
-            list_ptr = None
-            if getattr(col, "list_child_data", None) is not None:  # LIST: dmb_host_list
-                from . import chunks as _ch
-                cphys = _ch.phys_of_type(col.list_child_type, col.list_child_dec_width)
-                cw = _ch.PHYS_WIDTH[cphys]
-                cbase = col.list_child_data.ctypes.data
-                c_ptrs = (np.asarray(col.list_child_base, dtype=np.uint64) * np.uint64(cw) + np.uint64(cbase)).astype(np.uint64)
-                cv_ptrs = None
-                if col.list_child_validity is not None and np.any(np.asarray(col.list_child_val_off) >= 0):
-                    vo = np.asarray(col.list_child_val_off, dtype=np.int64)
-                    cv_ptrs = np.where(vo >= 0, col.list_child_validity.ctypes.data + 8 * vo, 0).astype(np.uint64)
-                sizes = np.ascontiguousarray(col.list_child_sizes, dtype=np.uint64)
-                hl = nat.HostList(col.list_child_type, cphys, col.list_child_dec_width, col.list_child_dec_scale, c_ptrs.ctypes.data,
-                                  cv_ptrs.ctypes.data if cv_ptrs is not None else None, sizes.ctypes.data)
-                self._keep.append((c_ptrs, cv_ptrs, sizes, hl))
-                list_ptr = C.pointer(hl)
-            self._keep.append((data_ptrs, val_ptrs, name))
-            self._cols[j] = nat.HostColumn(name, col.type_id, col.phys, col.dec_width, col.dec_scale,
-                                           C.cast(data_ptrs.ctypes.data, C.POINTER(C.c_void_p)),
-                                           C.cast(val_ptrs.ctypes.data, C.POINTER(C.c_void_p)) if val_ptrs is not None else None,
-                                           heap_base, heap_len, dict_ptr, list_ptr)
+            self._cols[j] = self._host_column(col, register_heap)
         self.struct = nat.HostBatch(ncols, nat_flags(pinned), nchunks, self.counts.ctypes.data, self._cols)
+
+
+def _ptr_table(slab, offsets, scale: int) -> np.ndarray:
+    base = slab.ctypes.data
+    return (np.asarray(offsets, dtype=np.uint64) * np.uint64(scale) + np.uint64(base)).astype(np.uint64)
+
+
+def _host_column(self, col, register_heap: bool = True) -> "nat.HostColumn":
+    """dmb_host_column of a chunks.Column (recursively for STRUCT fields and LIST / MAP children)"""
+    keep = self._keep
+    name = col.name.encode()
+    data_ptrs = None
+    if col.data is not None and np.asarray(col.data_off).shape[0]:
+        data_ptrs = _ptr_table(col.data, col.data_off, 1)
+    elif col.data is not None:
+        data_ptrs = np.zeros(1, dtype=np.uint64)
+    val_ptrs = None
+    if col.validity is not None and np.any(np.asarray(col.val_off) >= 0):
+        vo = np.asarray(col.val_off, dtype=np.int64)
+        val_ptrs = np.where(vo >= 0, col.validity.ctypes.data + 8 * vo, 0).astype(np.uint64)
+    heap_base, heap_len = None, 0
+    if getattr(col, "heap", None) is not None and register_heap:
+        heap_base, heap_len = col.heap.ctypes.data, int(col.heap.shape[0])
+    elif getattr(col, "inline_only", False):
+        heap_base, heap_len = 1, 0  # DMB_HEAP_INLINE_ONLY
+    dict_ptr = None
+    if getattr(col, "dictionary", None) is not None:  # ENUM: dmb_enum_dict
+        d_offs, d_data = ch.enum_dict_arrays(col.dictionary)
+        ed = nat.EnumDict(len(col.dictionary), 0, d_offs.ctypes.data, d_data.ctypes.data)
+        keep.append((d_offs, d_data, ed))
+        dict_ptr = C.pointer(ed)
+    list_ptr = None
+    child_col = getattr(col, "list_child_col", None)
+    if child_col is not None:  # LIST / MAP with a described child (VARCHAR, STRUCT, LIST)
+        sizes = np.ascontiguousarray(col.list_child_sizes, dtype=np.uint64)
+        cc = (nat.HostColumn * 1)()
+        cc[0] = _host_column(self, child_col, register_heap=False)  # child vectors own their heaps: never one registered region
+        hl = nat.HostList(child_col.type_id, child_col.phys, child_col.dec_width, child_col.dec_scale, None, None, sizes.ctypes.data,
+                          C.cast(cc, C.POINTER(nat.HostColumn)))
+        keep.append((sizes, cc, hl))
+        list_ptr = C.pointer(hl)
+    elif getattr(col, "list_child_data", None) is not None:  # LIST of a fixed-width child, flat form
+        cphys = ch.phys_of_type(col.list_child_type, col.list_child_dec_width)
+        cw = ch.PHYS_WIDTH[cphys]
+        c_ptrs = _ptr_table(col.list_child_data, col.list_child_base, cw)
+        cv_ptrs = None
+        if col.list_child_validity is not None and np.any(np.asarray(col.list_child_val_off) >= 0):
+            vo = np.asarray(col.list_child_val_off, dtype=np.int64)
+            cv_ptrs = np.where(vo >= 0, col.list_child_validity.ctypes.data + 8 * vo, 0).astype(np.uint64)
+        sizes = np.ascontiguousarray(col.list_child_sizes, dtype=np.uint64)
+        hl = nat.HostList(col.list_child_type, cphys, col.list_child_dec_width, col.list_child_dec_scale, c_ptrs.ctypes.data,
+                          cv_ptrs.ctypes.data if cv_ptrs is not None else None, sizes.ctypes.data, None)
+        keep.append((c_ptrs, cv_ptrs, sizes, hl))
+        list_ptr = C.pointer(hl)
+    struct_ptr = None
+    fields = getattr(col, "struct_fields", None)
+    if fields is not None:
+        fc = (nat.HostColumn * len(fields))()
+        for i, f in enumerate(fields):
+            fc[i] = _host_column(self, f, register_heap)
+        hs = nat.HostStruct(len(fields), 0, C.cast(fc, C.POINTER(nat.HostColumn)))
+        keep.append((fc, hs))
+        struct_ptr = C.pointer(hs)
+    keep.append((data_ptrs, val_ptrs, name))
+    return nat.HostColumn(name, col.type_id, col.phys, col.dec_width, col.dec_scale,
+                          C.cast(data_ptrs.ctypes.data, C.POINTER(C.c_void_p)) if data_ptrs is not None else None,
+                          C.cast(val_ptrs.ctypes.data, C.POINTER(C.c_void_p)) if val_ptrs is not None else None,
+                          heap_base, heap_len, dict_ptr, list_ptr, struct_ptr)
+
+
+HostBatch._host_column = _host_column
 
 
 def nat_flags(pinned: bool) -> int:

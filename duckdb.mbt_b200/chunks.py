@@ -31,6 +31,7 @@ T_TIMESTAMP, T_DATE, T_TIME, T_INTERVAL, T_HUGEINT, T_VARCHAR, T_BLOB, T_DECIMAL
 T_TIMESTAMP_S, T_TIMESTAMP_MS, T_TIMESTAMP_NS = 20, 21, 22
 T_ENUM = 23
 T_LIST = 24
+T_STRUCT, T_MAP = 25, 26
 T_UUID, T_TIME_TZ, T_TIMESTAMP_TZ, T_UHUGEINT, T_TIME_NS = 27, 30, 31, 32, 39
 
 # enum dmb_phys
@@ -93,6 +94,10 @@ class Column:
     list_child_sizes: Optional[np.ndarray] = None     # uint64 [nchunks]: duckdb_list_vector_get_size
     list_child_validity: Optional[np.ndarray] = None  # uint64 words
     list_child_val_off: Optional[np.ndarray] = None   # int64 [nchunks], -1 = NULL mask pointer
+    # nested types (dmb_host_struct / dmb_host_list.child_col).  A nested child is itself a Column whose vector of chunk k
+    # sits at data_off[k] / val_off[k] of its own slabs; under a LIST its chunk k vector holds list_child_sizes[k] elements.
+    struct_fields: Optional[List["Column"]] = None    # STRUCT: one Column per field (same rows as the parent)
+    list_child_col: Optional["Column"] = None         # LIST / MAP: the child described as a Column
 
     @property
     def width(self) -> int:

@@ -42,7 +42,9 @@ struct EnumDict {
 struct ArrowColOut {
   std::shared_ptr<CtxCore> core;
   std::shared_ptr<EnumDict> dict;  // dictionary-encoded export (ENUM)
-  std::shared_ptr<ArrowColOut> child;  // list<child> export (LIST)
+  std::vector<std::shared_ptr<ArrowColOut>> children;  // list<child> / map<entries>: one; struct<...>: one per field
+  int64_t flags = 2;                   // ARROW_FLAG_NULLABLE (map keys: 0)
+  bool no_values = false;              // struct: the validity buffer only
   std::string name, format;
   int64_t length = 0, null_count = 0;
   void *validity = nullptr, *values = nullptr, *data = nullptr;  // values = offsets for utf8
@@ -60,6 +62,33 @@ struct TypedOut {
   int32_t tag = DMB_VALUE_NULL, width = 0;
   int64_t null_count = 0;
   void *values = nullptr, *valid = nullptr, *offsets = nullptr, *data = nullptr;  // pinned
+};
+
+// ---- nested types.  The child level of a LIST / MAP column described by dmb_host_list.child_col:
+// every "leaf" is one vector family (one child vector per chunk, sizes[k] elements of it), staged as one flat slab.
+struct ListNode;
+struct Leaf {
+  std::string name;
+  int32_t type_id = 0, phys = 0, dec_width = 0, dec_scale = 0, width = 0;
+  std::vector<const void *> data;      // [nchunks]
+  std::vector<const void *> validity;  // [nchunks] or empty (no masks at all)
+  // staged
+  uint8_t *d_data = nullptr;
+  uint64_t *d_validity = nullptr;      // per-chunk padded masks (word offsets d_val_off), or one dense bitmap over the slab
+  int64_t *d_val_off = nullptr;
+  uint8_t *d_heap = nullptr;           // VARCHAR / BLOB leaves: the child vectors' strings, gathered by the stager
+  uint64_t heap_len = 0;
+};
+struct ListNode {
+  enum Kind { kLeaf = 0, kStruct = 1, kList = 2 };
+  int kind = kLeaf;
+  std::vector<uint64_t> sizes, base;   // per chunk; base has nchunks + 1 entries
+  std::vector<Leaf> leaves;            // kLeaf: one; kStruct: one per field; kList: the inner list's entries (16 bytes, rebased)
+  Leaf struct_validity;                // kStruct: the struct vectors' own masks (width 1 dummy payload)
+  bool has_struct_validity = false;
+  std::shared_ptr<ListNode> inner;     // kList: the level below
+  uint64_t *d_base = nullptr, *d_sizes = nullptr;
+  bool staged = false;
 };
 
 struct Col {
@@ -83,6 +112,12 @@ struct Col {
   uint64_t *d_child_validity = nullptr, *d_child_base = nullptr, *d_child_sizes = nullptr;
   int64_t *d_child_val_off = nullptr;
   bool child_staged = false;
+  // STRUCT: the fields are columns of their own, appended behind the visible ones (indices into Result::cols)
+  bool is_struct = false;
+  std::vector<int> kids;
+  // LIST / MAP whose child is described as a column (VARCHAR, STRUCT, LIST children)
+  std::shared_ptr<ListNode> node;
+  bool is_map = false;
   // device copy (lives as long as the result)
   bool staged = false;
   uint8_t *d_data = nullptr;
@@ -272,8 +307,9 @@ int32_t stage_column(Result *r, int j) {
       fixup = compact_fixup;
     }
   }
-  if (nch && stage_pieces(c, c.s_in, col.data.data(), r->counts.data(), (size_t)col.width, slot, nch, col.d_data,
-                          r->pinned_input, fixup, &cc, &r->bytes_h2d)) return -1;
+  if (nch && !col.is_struct &&  // (a STRUCT vector has no payload of its own: validity + descriptors only)
+      stage_pieces(c, c.s_in, col.data.data(), r->counts.data(), (size_t)col.width, slot, nch, col.d_data,
+                   r->pinned_input, fixup, &cc, &r->bytes_h2d)) return -1;
   if (fixup && arena_start[(size_t)nch]) {
     // every piece was gathered (host side) before its ring copy was issued, so the arena is complete
     if (check_cuda(cudaMemcpyAsync(col.d_heap, cc.arena, (size_t)arena_start[(size_t)nch], cudaMemcpyHostToDevice, c.s_in), "string arena H2D")) return -1;
@@ -837,6 +873,7 @@ int32_t run_list(Result *r, Scope &sc, int j, int32_t child_op, bool child_as_st
 struct ArrowMap {
   int32_t op = -1;      // fixed-width conversion, or -1 for strings
   bool is_string = false, is_list = false;
+  bool is_nested = false;  // STRUCT / MAP / LIST with a described child: converted synchronously (nested_to_arrow)
   std::string format, child_format;
   int32_t child_op = -1;
   bool child_as_stored = true;
@@ -878,7 +915,18 @@ bool arrow_map(const Col &col, ArrowMap *m) {
     case DMB_TYPE_ENUM:  // dictionary-encoded: the indices as stored, the labels as the dictionary (export_column)
       if (!col.dict) { set_error("ENUM column without a dictionary"); return false; }
       return same(col.phys == DMB_PHYS_U8 ? "C" : col.phys == DMB_PHYS_U16 ? "S" : "I");
+    case DMB_TYPE_STRUCT:
+      if (!col.is_struct) { set_error("STRUCT column without field vectors"); return false; }
+      m->is_nested = true;
+      m->format = "+s";
+      return true;
+    case DMB_TYPE_MAP:
+      if (!col.node || col.node->kind != ListNode::kStruct || col.node->leaves.size() != 2) { set_error("MAP column: the child must be STRUCT<key, value>"); return false; }
+      m->is_nested = true;
+      m->format = "+m";
+      return true;
     case DMB_TYPE_LIST: {  // list<child>, child copied as stored
+      if (col.node) { m->is_nested = true; m->format = "+l"; return true; }
       if (!col.is_list) { set_error("LIST column without child vectors"); return false; }
       Col child;
       child.type_id = col.child_type_id;
@@ -901,6 +949,629 @@ bool arrow_map(const Col &col, ArrowMap *m) {
   }
 }
 
+
+// ------------------------------------------------------------------ nested types: STRUCT, MAP, LIST of VARCHAR / STRUCT / LIST
+// (the reference rejects them on its chunk path, src/duckdb_native.c:271-303, and has no Arrow
+// mapping: the contract is the Arrow format, checked with pyarrow in tests/test_gpu_nested.py.)
+//   STRUCT          the fields are columns of their own (hidden behind the visible ones): each is converted like a
+//                   top-level column; the parent contributes its validity bitmap
+//   LIST<x>         level by level on DENSE arrays: list_emit_kernel gathers every leaf vector family of the child
+//                   level through the entries (one launch per leaf: offsets are recomputed, the entries are tiny next
+//                   to the children); a gathered leaf is a dense column, so
+//                     fixed width     -> its Arrow form (second pass of fixed_batch_kernel when it is not stored that way)
+//                     VARCHAR / BLOB  -> the string kernels over the gathered string_t as 2048-element pseudo chunks,
+//                                        the child vectors' heaps gathered into one arena by the stager
+//                     STRUCT          -> every field gathered with the same entries (+ the struct's own validity)
+//                     LIST            -> the gathered inner entries (rebased onto the grandchild slab by the stager) are
+//                                        the entries of the next level: the same kernel again, over pseudo chunks
+//   MAP             LIST<STRUCT<key, value>> exported as Arrow map<key, value>
+// These columns are converted synchronously inside launch_arrow_col (no copy-in / copy-out overlap): they are not the
+// hot path.
+void copy_bits(uint64_t *dst, uint64_t dst_bit, const uint64_t *src, uint64_t nbits) {  // src bits [0, nbits) -> dst bits [dst_bit, ...); dst pre-zeroed
+  for (uint64_t i = 0; i < nbits;) {
+    const uint64_t d = dst_bit + i;
+    const unsigned take = (unsigned)std::min<uint64_t>(std::min<uint64_t>(64 - (d & 63), 64 - (i & 63)), nbits - i);
+    uint64_t bits = src ? (src[i >> 6] >> (i & 63)) : ~0ull;
+    if (take < 64) bits &= (1ull << take) - 1ull;
+    dst[d >> 6] |= bits << (d & 63);
+    i += take;
+  }
+}
+
+bool leaf_from_column(const dmb_host_column &hc, int64_t nch, Leaf *leaf) {
+  leaf->name = hc.name ? hc.name : "";
+  leaf->type_id = hc.type_id;
+  leaf->phys = hc.phys;
+  leaf->dec_width = hc.dec_width;
+  leaf->dec_scale = hc.dec_scale;
+  leaf->width = dmb_phys_width(hc.phys);
+  if (leaf->width <= 0) { set_error("nested column '%s': bad physical type %d", leaf->name.c_str(), hc.phys); return false; }
+  if (hc.type_id == DMB_TYPE_ENUM) { set_error("nested column '%s': ENUM inside LIST / MAP is not supported", leaf->name.c_str()); return false; }
+  if (nch > 0 && !hc.data) { set_error("nested column '%s': no data pointers", leaf->name.c_str()); return false; }
+  leaf->data.assign(hc.data, hc.data + nch);
+  if (hc.validity) {
+    leaf->validity.assign((const void *const *)hc.validity, (const void *const *)hc.validity + nch);
+    bool any = false;
+    for (const void *p : leaf->validity) any |= p != nullptr;
+    if (!any) leaf->validity.clear();
+  }
+  return true;
+}
+
+// the child level of a LIST / MAP from its host description (dmb_host_list with child_col)
+std::shared_ptr<ListNode> build_node(const dmb_host_list *l, int64_t nch, int depth) {
+  if (depth > 4) { set_error("LIST nesting deeper than 4 levels"); return nullptr; }
+  const dmb_host_column *cc = l->child_col;
+  if (!cc || (nch > 0 && !l->child_sizes)) { set_error("LIST column: child_col / child_sizes missing"); return nullptr; }
+  auto node = std::make_shared<ListNode>();
+  node->sizes.assign(l->child_sizes, l->child_sizes + nch);
+  node->base.assign((size_t)nch + 1, 0);
+  for (int64_t k = 0; k < nch; ++k) node->base[(size_t)k + 1] = node->base[(size_t)k] + node->sizes[(size_t)k];
+  if (cc->type_id == DMB_TYPE_STRUCT) {
+    if (!cc->struct_ || cc->struct_->nfields <= 0 || !cc->struct_->fields) { set_error("LIST<STRUCT>: no fields"); return nullptr; }
+    node->kind = ListNode::kStruct;
+    for (int32_t f = 0; f < cc->struct_->nfields; ++f) {
+      const dmb_host_column &fc = cc->struct_->fields[f];
+      if (fc.type_id == DMB_TYPE_STRUCT || fc.type_id == DMB_TYPE_LIST || fc.type_id == DMB_TYPE_MAP) { set_error("LIST<STRUCT>: field '%s' is itself nested (not supported)", fc.name ? fc.name : ""); return nullptr; }
+      node->leaves.emplace_back();
+      if (!leaf_from_column(fc, nch, &node->leaves.back())) return nullptr;
+    }
+    if (cc->validity) {
+      node->struct_validity.validity.assign((const void *const *)cc->validity, (const void *const *)cc->validity + nch);
+      for (const void *p : node->struct_validity.validity) node->has_struct_validity |= p != nullptr;
+    }
+    node->struct_validity.width = 1;
+    node->struct_validity.phys = DMB_PHYS_U8;
+    node->struct_validity.type_id = DMB_TYPE_UTINYINT;
+  } else if (cc->type_id == DMB_TYPE_LIST) {
+    if (!cc->list) { set_error("LIST<LIST>: the inner list's child vectors are missing"); return nullptr; }
+    node->kind = ListNode::kList;
+    node->leaves.emplace_back();
+    dmb_host_column entries = *cc;
+    entries.phys = DMB_PHYS_U128;
+    if (!leaf_from_column(entries, nch, &node->leaves.back())) return nullptr;
+    dmb_host_list inner = *cc->list;
+    dmb_host_column flat;  // an inner list in the flat fixed-width form: wrap it as a column
+    if (!inner.child_col) {
+      memset(&flat, 0, sizeof(flat));
+      flat.name = "item";
+      flat.type_id = inner.child_type_id;
+      flat.phys = inner.child_phys;
+      flat.dec_width = inner.child_dec_width;
+      flat.dec_scale = inner.child_dec_scale;
+      flat.data = inner.child_data;
+      flat.validity = inner.child_validity;
+      inner.child_col = &flat;
+    }
+    node->inner = build_node(&inner, nch, depth + 1);
+    if (!node->inner) return nullptr;
+  } else {
+    node->kind = ListNode::kLeaf;
+    node->leaves.emplace_back();
+    if (!leaf_from_column(*cc, nch, &node->leaves.back())) return nullptr;
+  }
+  return node;
+}
+
+// chunks [c0, c1) of a node (slice_result)
+std::shared_ptr<ListNode> slice_node(const ListNode &p, int64_t c0, int64_t c1) {
+  auto n = std::make_shared<ListNode>();
+  n->kind = p.kind;
+  n->sizes.assign(p.sizes.begin() + c0, p.sizes.begin() + c1);
+  n->base.assign((size_t)(c1 - c0) + 1, 0);
+  for (int64_t k = 0; k < c1 - c0; ++k) n->base[(size_t)k + 1] = n->base[(size_t)k] + n->sizes[(size_t)k];
+  auto slice_leaf = [&](const Leaf &pl) {
+    Leaf l;
+    l.name = pl.name; l.type_id = pl.type_id; l.phys = pl.phys; l.dec_width = pl.dec_width; l.dec_scale = pl.dec_scale; l.width = pl.width;
+    if (!pl.data.empty()) l.data.assign(pl.data.begin() + c0, pl.data.begin() + c1);
+    if (!pl.validity.empty()) l.validity.assign(pl.validity.begin() + c0, pl.validity.begin() + c1);
+    return l;
+  };
+  for (const Leaf &pl : p.leaves) n->leaves.push_back(slice_leaf(pl));
+  n->struct_validity = slice_leaf(p.struct_validity);
+  n->has_struct_validity = p.has_struct_validity;
+  if (p.inner) n->inner = slice_node(*p.inner, c0, c1);
+  return n;
+}
+
+// host -> device: every leaf of the node as one flat slab.  dense_bits: the validity as ONE bitmap over the slab (levels
+// below the first: their entries were rebased onto the slab), else one padded mask per chunk.
+int32_t stage_node(Result *r, ListNode &node, bool dense_bits) {
+  if (node.staged) return 0;
+  CtxCore &c = *r->core;
+  const int64_t nch = r->nchunks;
+  const uint64_t total = node.base[(size_t)nch];
+  uint64_t *h_base = (uint64_t *)keep_pin(r, (size_t)(nch + 1) * 8), *h_sizes = (uint64_t *)keep_pin(r, (size_t)(nch + 1) * 8);
+  node.d_base = (uint64_t *)keep_dev(r, (size_t)(nch + 1) * 8);
+  node.d_sizes = (uint64_t *)keep_dev(r, (size_t)(nch + 1) * 8);
+  if (!h_base || !h_sizes || !node.d_base || !node.d_sizes) return -1;
+  memcpy(h_base, node.base.data(), (size_t)(nch + 1) * 8);
+  if (nch) memcpy(h_sizes, node.sizes.data(), (size_t)nch * 8);
+  if (check_cuda(cudaMemcpyAsync(node.d_base, h_base, (size_t)(nch + 1) * 8, cudaMemcpyHostToDevice, c.s_in), "list child base H2D")) return -1;
+  if (nch && check_cuda(cudaMemcpyAsync(node.d_sizes, h_sizes, (size_t)nch * 8, cudaMemcpyHostToDevice, c.s_in), "list child sizes H2D")) return -1;
+  auto stage_leaf = [&](Leaf &leaf, bool zero_payload, const ListNode *rebase_onto) -> int32_t {
+    const size_t W = (size_t)leaf.width;
+    uint8_t *arena = (uint8_t *)keep_pin(r, (size_t)total * W + 64);
+    leaf.d_data = (uint8_t *)keep_dev(r, (size_t)total * W + 64);
+    if (!arena || !leaf.d_data) return -1;
+    if (zero_payload) memset(arena, 0, (size_t)total * W);
+    // validity
+    std::vector<int64_t> voff((size_t)(nch > 0 ? nch : 1), -1);
+    uint64_t words = 0;
+    const bool any_mask = !leaf.validity.empty();
+    if (dense_bits) words = any_mask ? (total + 63) / 64 + 2 : 0;
+    else
+      for (int64_t k = 0; k < nch; ++k)
+        if (any_mask && leaf.validity[(size_t)k]) { voff[(size_t)k] = (int64_t)words; words += (node.sizes[(size_t)k] + 63) / 64 + 1; }
+    uint64_t *warena = words ? (uint64_t *)keep_pin(r, (size_t)(words + 2) * 8) : nullptr;
+    if (words) {
+      leaf.d_validity = (uint64_t *)keep_dev(r, (size_t)(words + 2) * 8);
+      if (!warena || !leaf.d_validity) return -1;
+      memset(warena, 0, (size_t)(words + 2) * 8);
+    }
+    // strings: where chunk k's heap bytes go in the arena (size pass), then gather + pointer rewrite
+    const bool is_string = leaf.phys == DMB_PHYS_STRING;
+    std::vector<uint64_t> hstart;
+    uint8_t *harena = nullptr;
+    const uint64_t fake_base = 1ull << 43;
+    if (is_string) {
+      hstart.assign((size_t)nch + 1, 0);
+      parallel_for(c, nch, [&](int64_t k) {
+        const dmb_string_t *e = reinterpret_cast<const dmb_string_t *>(leaf.data[(size_t)k]);
+        const void *mask = any_mask ? leaf.validity[(size_t)k] : nullptr;
+        uint64_t sum = 0;
+        for (uint64_t i = 0; e && i < node.sizes[(size_t)k]; ++i)
+          if (host_row_valid(mask, (uint32_t)i) && e[i].length > 12) sum += e[i].length;
+        hstart[(size_t)k + 1] = sum;
+      });
+      for (int64_t k = 0; k < nch; ++k) hstart[(size_t)k + 1] += hstart[(size_t)k];
+      leaf.heap_len = hstart[(size_t)nch];
+      harena = (uint8_t *)keep_pin(r, (size_t)leaf.heap_len + 32);
+      leaf.d_heap = (uint8_t *)keep_dev(r, (size_t)leaf.heap_len + 32);
+      if (!harena || !leaf.d_heap) return -1;
+    }
+    parallel_for(c, nch, [&](int64_t k) {
+      const uint64_t sz = node.sizes[(size_t)k];
+      uint8_t *dst = arena + (size_t)node.base[(size_t)k] * W;
+      if (sz && !zero_payload) memcpy(dst, leaf.data[(size_t)k], (size_t)sz * W);
+      const void *mask = any_mask ? leaf.validity[(size_t)k] : nullptr;
+      if (rebase_onto) {  // inner list entries: offsets become positions in the grandchild slab
+        uint64_t *e = reinterpret_cast<uint64_t *>(dst);
+        const uint64_t add = rebase_onto->base[(size_t)k];
+        for (uint64_t i = 0; i < sz; ++i) e[2 * i] += add;
+      }
+      if (is_string) {
+        dmb_string_t *e = reinterpret_cast<dmb_string_t *>(dst);
+        uint64_t pos = hstart[(size_t)k];
+        for (uint64_t i = 0; i < sz; ++i) {
+          if (!host_row_valid(mask, (uint32_t)i) || e[i].length <= 12) continue;
+          memcpy(harena + pos, reinterpret_cast<const void *>((uintptr_t)e[i].tail.ptr), e[i].length);
+          e[i].tail.ptr = fake_base + pos;
+          pos += e[i].length;
+        }
+      }
+      if (words && !dense_bits && voff[(size_t)k] >= 0) memcpy(warena + voff[(size_t)k], mask, (size_t)((sz + 63) / 64) * 8);
+    });
+    if (words && dense_bits)  // (serial: neighbouring chunks share words)
+      for (int64_t k = 0; k < nch; ++k)
+        copy_bits(warena, node.base[(size_t)k], reinterpret_cast<const uint64_t *>(leaf.validity[(size_t)k]), node.sizes[(size_t)k]);
+    if (total && check_cuda(cudaMemcpyAsync(leaf.d_data, arena, (size_t)total * W, cudaMemcpyHostToDevice, c.s_in), "nested child H2D")) return -1;
+    if (words && check_cuda(cudaMemcpyAsync(leaf.d_validity, warena, (size_t)words * 8, cudaMemcpyHostToDevice, c.s_in), "nested child masks H2D")) return -1;
+    if (!dense_bits) {
+      int64_t *h_voff = (int64_t *)keep_pin(r, (size_t)(nch + 1) * 8);
+      leaf.d_val_off = (int64_t *)keep_dev(r, (size_t)(nch + 1) * 8);
+      if (!h_voff || !leaf.d_val_off) return -1;
+      if (nch) memcpy(h_voff, voff.data(), (size_t)nch * 8);
+      if (nch && check_cuda(cudaMemcpyAsync(leaf.d_val_off, h_voff, (size_t)nch * 8, cudaMemcpyHostToDevice, c.s_in), "nested child mask offsets H2D")) return -1;
+    }
+    if (is_string && leaf.heap_len && check_cuda(cudaMemcpyAsync(leaf.d_heap, harena, (size_t)leaf.heap_len, cudaMemcpyHostToDevice, c.s_in), "nested child heap H2D")) return -1;
+    r->bytes_h2d += total * W + words * 8 + leaf.heap_len;
+    return 0;
+  };
+  for (Leaf &leaf : node.leaves)
+    if (stage_leaf(leaf, false, node.kind == ListNode::kList ? node.inner.get() : nullptr)) return -1;
+  if (node.kind == ListNode::kStruct && node.has_struct_validity && stage_leaf(node.struct_validity, true, nullptr)) return -1;
+  if (node.inner && stage_node(r, *node.inner, true)) return -1;
+  node.staged = true;
+  return 0;
+}
+
+// the entries a gather reads: the LIST column's own vectors, or (levels below) the dense inner entries as pseudo chunks
+struct EntrySrc {
+  const void *d_entries = nullptr;
+  const uint64_t *d_validity = nullptr;
+  const dmb_vec_desc *d_vecs = nullptr;
+  const uint32_t *d_counts = nullptr;
+  const int64_t *d_row_off = nullptr;
+  int64_t nchunks = 0, nrows = 0;
+  const uint64_t *d_child_base = nullptr, *d_child_sizes = nullptr;
+  uint64_t cap = 0;  // elements the gather produces (host pass)
+  bool dense_bits = false;
+};
+struct GatherOut {
+  void *d_offsets = nullptr;
+  uint8_t *d_child = nullptr;
+  uint64_t *d_bitmap = nullptr;  // whole 32-word masks: the next pass reads it as chunk masks
+  unsigned long long *h_ctr = nullptr;  // pinned: [0] elements [1] nulls [2] flags
+  cudaEvent_t done = nullptr;
+};
+
+// metadata of a dense array of n elements cut into 2048-element pseudo chunks (masks: words [32 k, 32 k + 32) of a bitmap)
+struct Pseudo {
+  const uint32_t *d_counts = nullptr;
+  const int64_t *d_row_off = nullptr;
+  const dmb_vec_desc *d_vecs = nullptr;
+  int64_t nchunks = 0;
+};
+int32_t make_pseudo(Scope &sc, uint64_t n, size_t elem_bytes, Pseudo *out) {
+  const int64_t nck = (int64_t)((n + DMB_VECTOR_SIZE - 1) / DMB_VECTOR_SIZE);
+  std::vector<uint32_t> cc((size_t)(nck > 0 ? nck : 1), DMB_VECTOR_SIZE);
+  std::vector<int64_t> ro((size_t)nck + 1);
+  std::vector<dmb_vec_desc> vd((size_t)(nck > 0 ? nck : 1));
+  if (nck) cc[(size_t)nck - 1] = (uint32_t)(n - (uint64_t)(nck - 1) * DMB_VECTOR_SIZE);
+  for (int64_t k = 0; k < nck; ++k) {
+    ro[(size_t)k] = k * (int64_t)DMB_VECTOR_SIZE;
+    vd[(size_t)k].data_off = (uint64_t)k * DMB_VECTOR_SIZE * elem_bytes;
+    vd[(size_t)k].val_off = k * DMB_VALIDITY_WORDS;
+  }
+  ro[(size_t)nck] = (int64_t)n;
+  out->d_counts = (const uint32_t *)upload_job(sc, cc.data(), cc.size() * sizeof(uint32_t));
+  out->d_row_off = (const int64_t *)upload_job(sc, ro.data(), ro.size() * sizeof(int64_t));
+  out->d_vecs = (const dmb_vec_desc *)upload_job(sc, vd.data(), vd.size() * sizeof(dmb_vec_desc));
+  out->nchunks = nck;
+  return (out->d_counts && out->d_row_off && out->d_vecs) ? 0 : -1;
+}
+
+int32_t gather_leaf(Result *r, Scope &sc, const EntrySrc &es, const Leaf &leaf, GatherOut *out) {
+  CtxCore &c = *r->core;
+  const uint64_t cap = es.cap;
+  if (cap > 0x7fffffffull) { set_error("nested column: %llu child elements exceed int32 offsets; use smaller batches", (unsigned long long)cap); return -1; }
+  out->d_offsets = sc.dalloc((size_t)(es.nrows + 1) * 4 + 64);
+  out->d_child = (uint8_t *)sc.dalloc((size_t)cap * (size_t)leaf.width + 64);
+  const size_t bm_words = (size_t)((cap + DMB_VECTOR_SIZE - 1) / DMB_VECTOR_SIZE * DMB_VALIDITY_WORDS + 2);
+  out->d_bitmap = (uint64_t *)sc.dalloc(bm_words * 8 + 256);
+  unsigned long long *d_ctr = (unsigned long long *)sc.dalloc(16);
+  void *d_scratch = sc.dalloc(dmb_dev_list_scratch_bytes(es.nchunks) + 16);
+  out->h_ctr = (unsigned long long *)sc.palloc(32);
+  out->done = sc.event(false);
+  if (!out->d_offsets || !out->d_child || !out->d_bitmap || !d_ctr || !d_scratch || !out->h_ctr || !out->done) return -1;
+  memset(out->h_ctr, 0, 32);
+  if (check_cuda(cudaMemsetAsync(out->d_bitmap, 0, bm_words * 8 + 256, c.s_compute), "nested bitmap memset")) return -1;
+  if (es.nrows == 0) {
+    if (check_cuda(cudaMemsetAsync(out->d_offsets, 0, 4, c.s_compute), "nested offsets memset")) return -1;
+    cudaEventRecord(out->done, c.s_compute);
+    return 0;
+  }
+  if (check_cuda(cudaMemsetAsync(d_ctr, 0, 16, c.s_compute), "nested counters memset")) return -1;
+  dmb_list_job job;
+  memset(&job, 0, sizeof(job));
+  job.in_entries = es.d_entries;
+  job.in_validity = es.d_validity;
+  job.vecs = es.d_vecs;
+  job.child_base = es.d_child_base;
+  job.child_data = leaf.d_data;
+  job.child_validity = leaf.d_validity;
+  job.child_val_off = leaf.d_val_off;
+  job.out_offsets = out->d_offsets;
+  job.out_child = out->d_child;
+  job.out_child_validity = out->d_bitmap;
+  job.total = d_ctr;
+  job.child_null_count = d_ctr + 1;
+  job.child_width = leaf.width;
+  job.large = es.dense_bits ? DMB_LIST_DENSE_CHILD_BITS : 0;
+  job.child_sizes = es.d_child_sizes;
+  cudaEvent_t k0 = sc.event(true), k1 = sc.event(true);
+  if (!k0 || !k1) return -1;
+  cudaEventRecord(k0, c.s_compute);
+  if (dmb_dev_list_batch(&job, es.d_counts, es.d_row_off, es.nchunks, es.nrows, (int64_t)cap, d_scratch, c.s_compute)) return -1;
+  cudaEventRecord(k1, c.s_compute);
+  sc.kernel_spans.emplace_back(k0, k1);
+  if (check_cuda(cudaMemcpyAsync(out->h_ctr, d_ctr, 16, cudaMemcpyDeviceToHost, c.s_compute), "nested counters D2H")) return -1;
+  if (check_cuda(cudaMemcpyAsync(out->h_ctr + 2, d_scratch, 8, cudaMemcpyDeviceToHost, c.s_compute), "nested flags D2H")) return -1;
+  cudaEventRecord(out->done, c.s_compute);
+  return 0;
+}
+
+int32_t check_gather(const GatherOut &g, uint64_t cap) {
+  if (check_cuda(cudaEventSynchronize(g.done), "nested gather wait")) return -1;
+  const unsigned long long f = g.h_ctr[2];
+  if (f & 8ull) { set_error("a LIST entry reaches outside its chunk's child vector (offset + length > duckdb_list_vector_get_size)"); return -1; }
+  if (f & 4ull) { set_error("a LIST chunk's look-back gave up waiting for its predecessors; run the call again"); return -1; }
+  if (f & 2ull) { set_error("a LIST chunk holds more than 4 G child elements"); return -1; }
+  if (f & 1ull) { set_error("LIST child elements exceed int32 offsets; use smaller batches"); return -1; }
+  if (g.h_ctr[0] != cap) { set_error("nested column: the device gathered %llu child elements, the host counted %llu", g.h_ctr[0], (unsigned long long)cap); return -1; }
+  return 0;
+}
+
+// a gathered leaf (dense, `cap` elements) -> its Arrow array in pinned memory.  Synchronous.
+std::shared_ptr<ArrowColOut> leaf_to_arrow(Result *r, Scope &sc, const Leaf &leaf, const GatherOut &g, uint64_t cap);
+
+std::shared_ptr<ArrowColOut> pinned_copy(Result *r, const std::shared_ptr<ArrowColOut> &o, const void *d_values, size_t values_bytes,
+                                         const void *d_validity, size_t validity_bytes, const void *d_data, size_t data_bytes) {
+  CtxCore &c = *r->core;
+  o->values_bytes = values_bytes;
+  o->validity_bytes = validity_bytes;
+  o->data_bytes = data_bytes;
+  o->values = c.pin.alloc(values_bytes + 64);
+  o->validity = c.pin.alloc(validity_bytes + 64);
+  if (d_data || data_bytes) o->data = c.pin.alloc(data_bytes + 64);
+  if (!o->values || !o->validity || ((d_data || data_bytes) && !o->data)) return nullptr;
+  memset(o->values, 0, values_bytes < 64 ? values_bytes + 8 : 64);  // (an empty offsets buffer still reads as [0])
+  if (values_bytes && d_values && check_cuda(cudaMemcpyAsync(o->values, d_values, values_bytes, cudaMemcpyDeviceToHost, c.s_compute), "nested values D2H")) return nullptr;
+  if (validity_bytes && d_validity && check_cuda(cudaMemcpyAsync(o->validity, d_validity, validity_bytes, cudaMemcpyDeviceToHost, c.s_compute), "nested bitmap D2H")) return nullptr;
+  if (data_bytes && d_data && check_cuda(cudaMemcpyAsync(o->data, d_data, data_bytes, cudaMemcpyDeviceToHost, c.s_compute), "nested data D2H")) return nullptr;
+  r->bytes_d2h += values_bytes + validity_bytes + data_bytes;
+  return o;
+}
+
+// one level: gather every leaf of `node` through `es`, convert, recurse.  Returns the Arrow child array of that level
+// (kLeaf: the leaf; kStruct: struct<fields>; kList: list<...>) and, through *offsets_owner, the gather whose offsets /
+// counters describe the level (the caller turns them into its own offsets buffer).
+std::shared_ptr<ArrowColOut> node_to_arrow(Result *r, Scope &sc, const EntrySrc &es, ListNode &node, uint64_t inner_cap, GatherOut *first);
+
+std::shared_ptr<ArrowColOut> leaf_to_arrow(Result *r, Scope &sc, const Leaf &leaf, const GatherOut &g, uint64_t cap) {
+  CtxCore &c = *r->core;
+  auto o = std::make_shared<ArrowColOut>();
+  o->core = r->core;
+  o->name = leaf.name;
+  o->length = (int64_t)cap;
+  o->null_count = (int64_t)g.h_ctr[1];
+  const size_t bm_bytes = (size_t)((cap + 7) / 8);
+  Col tmp;
+  tmp.type_id = leaf.type_id;
+  tmp.phys = leaf.phys;
+  tmp.dec_width = leaf.dec_width;
+  tmp.dec_scale = leaf.dec_scale;
+  ArrowMap m;
+  if (!arrow_map(tmp, &m) || m.is_nested || m.is_list) { set_error("nested column '%s': child type %d has no Arrow mapping here", leaf.name.c_str(), leaf.type_id); return nullptr; }
+  o->format = m.format;
+  if (m.is_string) {
+    // the gathered string_t are a dense column: 2048-element pseudo chunks, the gathered bitmap as their masks, the
+    // arena the stager gathered as the heap
+    Pseudo ps;
+    if (make_pseudo(sc, cap, sizeof(dmb_string_t), &ps)) return nullptr;
+    const size_t data_cap = 12 * (size_t)cap + (size_t)leaf.heap_len;
+    void *d_off = sc.dalloc((size_t)(cap + 1) * 4 + 64);
+    uint8_t *d_data = (uint8_t *)sc.dalloc(data_cap + 64);
+    void *d_scratch = sc.dalloc(dmb_dev_string_scratch_bytes(ps.nchunks > 0 ? ps.nchunks : 1));
+    unsigned long long *d_total = (unsigned long long *)sc.dalloc(8), *h = (unsigned long long *)sc.palloc(16);
+    if (!d_off || !d_data || !d_scratch || !d_total || !h) return nullptr;
+    h[0] = h[1] = 0;
+    if (check_cuda(cudaMemsetAsync(d_off, 0, 4, c.s_compute), "nested offsets memset") || check_cuda(cudaMemsetAsync(d_total, 0, 8, c.s_compute), "nested total memset")) return nullptr;
+    if (cap) {
+      dmb_string_job job;
+      memset(&job, 0, sizeof(job));
+      job.in = reinterpret_cast<const dmb_string_t *>(g.d_child);
+      job.in_validity = g.d_bitmap;
+      job.vecs = ps.d_vecs;
+      job.heap_dev = leaf.d_heap;
+      job.heap_host_base = 1ull << 43;
+      job.heap_len = leaf.heap_len;
+      job.out_offsets = d_off;
+      job.out_data = d_data;
+      job.total_bytes = d_total;
+      job.mode = DMB_STR_ARROW_UTF8;
+      job.out_data_cap = data_cap;
+      if (dmb_dev_string_batch(&job, ps.d_counts, ps.d_row_off, ps.nchunks, (int64_t)cap, d_scratch, c.s_compute)) return nullptr;
+      if (check_cuda(cudaMemcpyAsync(h, d_total, 8, cudaMemcpyDeviceToHost, c.s_compute), "nested total D2H")) return nullptr;
+      if (check_cuda(cudaMemcpyAsync(h + 1, (unsigned long long *)d_scratch + 1, 8, cudaMemcpyDeviceToHost, c.s_compute), "nested flags D2H")) return nullptr;
+      if (check_cuda(cudaStreamSynchronize(c.s_compute), "nested string sync")) return nullptr;
+      if (h[1] & kStrFlagOverflow) { set_error("nested column '%s': more than 2^31 string bytes; use smaller batches (record-batch stream)", leaf.name.c_str()); return nullptr; }
+      if (string_flags_error(h[1])) return nullptr;
+    }
+    return pinned_copy(r, o, d_off, (size_t)(cap + 1) * 4, g.d_bitmap, bm_bytes, d_data, (size_t)h[0]);
+  }
+  const bool as_stored = m.op == DMB_OP(leaf.phys, DMB_DST_SAME) || leaf.type_id == DMB_TYPE_HUGEINT;
+  if (as_stored || cap == 0) {
+    const int ow = dmb_op_out_width(m.op);
+    return pinned_copy(r, o, g.d_child, cap == 0 ? 0 : (size_t)cap * (size_t)(ow > 0 ? ow : leaf.width), g.d_bitmap, bm_bytes, nullptr, 0);
+  }
+  // BOOLEAN -> bits, DECIMAL -> decimal128, INTERVAL -> month_day_nano: fixed_batch_kernel over the dense child
+  const int32_t ow = dmb_op_out_width(m.op);
+  if (ow < 0) { set_error("nested column '%s': unsupported child conversion 0x%x", leaf.name.c_str(), m.op); return nullptr; }
+  Pseudo ps;
+  if (make_pseudo(sc, cap, (size_t)leaf.width, &ps)) return nullptr;
+  const size_t out_bytes = ow == 0 ? (size_t)((cap + 7) / 8) : (size_t)cap * (size_t)ow;
+  uint8_t *d_out = (uint8_t *)sc.dalloc(out_bytes + 64);
+  if (!d_out) return nullptr;
+  dmb_fixed_job fj;
+  memset(&fj, 0, sizeof(fj));
+  fj.in_data = g.d_child;
+  fj.in_validity = g.d_bitmap;
+  fj.vecs = ps.d_vecs;
+  fj.out_values = d_out;
+  fj.op = m.op;
+  void *fjd = upload_job(sc, &fj, sizeof(fj));
+  if (!fjd) return nullptr;
+  if (dmb_dev_fixed_batch((const dmb_fixed_job *)fjd, &fj, 1, ps.d_counts, ps.d_row_off, ps.nchunks, (int64_t)cap, c.s_compute)) return nullptr;
+  return pinned_copy(r, o, d_out, out_bytes, g.d_bitmap, bm_bytes, nullptr, 0);
+}
+
+std::shared_ptr<ArrowColOut> node_to_arrow(Result *r, Scope &sc, const EntrySrc &es, ListNode &node, uint64_t inner_cap, GatherOut *first) {
+  const uint64_t cap = es.cap;
+  const size_t bm_bytes = (size_t)((cap + 7) / 8);
+  if (node.kind == ListNode::kLeaf) {
+    if (gather_leaf(r, sc, es, node.leaves[0], first) || check_gather(*first, cap)) return nullptr;
+    return leaf_to_arrow(r, sc, node.leaves[0], *first, cap);
+  }
+  if (node.kind == ListNode::kStruct) {
+    auto o = std::make_shared<ArrowColOut>();
+    o->core = r->core;
+    o->name = "item";
+    o->format = "+s";
+    o->length = (int64_t)cap;
+    o->no_values = true;
+    for (size_t f = 0; f < node.leaves.size(); ++f) {
+      GatherOut g;
+      if (gather_leaf(r, sc, es, node.leaves[f], &g) || check_gather(g, cap)) return nullptr;
+      if (f == 0) *first = g;
+      auto ch = leaf_to_arrow(r, sc, node.leaves[f], g, cap);
+      if (!ch) return nullptr;
+      o->children.push_back(ch);
+    }
+    if (node.has_struct_validity) {
+      GatherOut gv;
+      if (gather_leaf(r, sc, es, node.struct_validity, &gv) || check_gather(gv, cap)) return nullptr;
+      o->null_count = (int64_t)gv.h_ctr[1];
+      return pinned_copy(r, o, nullptr, 0, gv.d_bitmap, bm_bytes, nullptr, 0);
+    }
+    o->validity = r->core->pin.alloc(64);  // no NULL structs: a NULL validity buffer would do, an all-ones one is as valid
+    o->values = r->core->pin.alloc(64);
+    o->validity_bytes = 0;
+    return (o->validity && o->values) ? o : nullptr;
+  }
+  // LIST<LIST<...>>: the gathered inner entries (already rebased onto the grandchild slab) are the next level's entries
+  GatherOut g;
+  if (gather_leaf(r, sc, es, node.leaves[0], &g) || check_gather(g, cap)) return nullptr;
+  *first = g;
+  CtxCore &c = *r->core;
+  Pseudo ps;
+  if (make_pseudo(sc, cap, 16, &ps)) return nullptr;
+  ListNode &in = *node.inner;
+  const uint64_t inner_total = in.base.back();
+  std::vector<uint64_t> zeros((size_t)ps.nchunks + 1, 0), sizes((size_t)(ps.nchunks > 0 ? ps.nchunks : 1), inner_total);
+  EntrySrc es2;
+  es2.d_entries = g.d_child;
+  es2.d_validity = g.d_bitmap;
+  es2.d_vecs = ps.d_vecs;
+  es2.d_counts = ps.d_counts;
+  es2.d_row_off = ps.d_row_off;
+  es2.nchunks = ps.nchunks;
+  es2.nrows = (int64_t)cap;
+  es2.d_child_base = (const uint64_t *)upload_job(sc, zeros.data(), zeros.size() * 8);
+  es2.d_child_sizes = (const uint64_t *)upload_job(sc, sizes.data(), sizes.size() * 8);
+  es2.cap = inner_cap;
+  es2.dense_bits = true;
+  if (!es2.d_child_base || !es2.d_child_sizes) return nullptr;
+  GatherOut g2;
+  auto child = node_to_arrow(r, sc, es2, in, 0, &g2);
+  if (!child) return nullptr;
+  if (child->name.empty()) child->name = "item";
+  auto o = std::make_shared<ArrowColOut>();
+  o->core = r->core;
+  o->name = "item";
+  o->format = "+l";
+  o->length = (int64_t)cap;
+  o->null_count = (int64_t)g.h_ctr[1];
+  o->children.push_back(child);
+  (void)c;
+  return pinned_copy(r, o, g2.d_offsets, (size_t)(cap + 1) * 4, g.d_bitmap, bm_bytes, nullptr, 0);
+}
+
+// host passes over the entries: how many elements each level's gather produces (sizes the outputs exactly and refuses
+// entries that reach outside their child vector before anything is launched)
+int32_t nested_caps(Result *r, const Col &col, uint64_t *cap1, uint64_t *cap2) {
+  CtxCore &c = *r->core;
+  const int64_t nch = r->nchunks;
+  const ListNode &node = *col.node;
+  std::vector<uint64_t> p1((size_t)(nch > 0 ? nch : 1), 0), p2((size_t)(nch > 0 ? nch : 1), 0);
+  std::atomic<bool> outside{false};
+  const bool nested = node.kind == ListNode::kList;
+  if (nested && node.inner->kind == ListNode::kList) { set_error("LIST nesting deeper than two levels is not supported"); return -1; }
+  parallel_for(c, nch, [&](int64_t k) {
+    const uint64_t *e = reinterpret_cast<const uint64_t *>(col.data[(size_t)k]);
+    const void *mask = col.validity.empty() ? nullptr : col.validity[(size_t)k];
+    const uint64_t csize = node.sizes[(size_t)k];
+    const uint64_t *ie = nested ? reinterpret_cast<const uint64_t *>(node.leaves[0].data[(size_t)k]) : nullptr;
+    const void *imask = (nested && !node.leaves[0].validity.empty()) ? node.leaves[0].validity[(size_t)k] : nullptr;
+    const uint64_t isize = nested ? node.inner->sizes[(size_t)k] : 0;
+    uint64_t s1 = 0, s2 = 0;
+    for (uint32_t i = 0; e && i < r->counts[(size_t)k]; ++i) {
+      if (!host_row_valid(mask, i)) continue;
+      const uint64_t off = e[2 * i], len = e[2 * i + 1];
+      if (off > csize || len > csize - off) { outside.store(true); continue; }
+      s1 += len;
+      for (uint64_t q = off; nested && q < off + len; ++q) {
+        if (imask && !((reinterpret_cast<const uint64_t *>(imask)[q >> 6] >> (q & 63)) & 1ull)) continue;
+        const uint64_t io = ie[2 * q], il = ie[2 * q + 1];
+        if (io > isize || il > isize - io) { outside.store(true); continue; }
+        s2 += il;
+      }
+    }
+    p1[(size_t)k] = s1;
+    p2[(size_t)k] = s2;
+  });
+  if (outside.load()) { set_error("nested column '%s': a list entry reaches outside its chunk's child vector", col.name.c_str()); return -1; }
+  *cap1 = *cap2 = 0;
+  for (int64_t k = 0; k < nch; ++k) { *cap1 += p1[(size_t)k]; *cap2 += p2[(size_t)k]; }
+  return 0;
+}
+
+struct Pending;
+int32_t launch_arrow_col(Result *r, Scope &sc, int j, int string_mode, Pending *p, size_t exact_cap);
+std::shared_ptr<ArrowColOut> convert_column_sync(Result *r, Scope &sc, int j);
+
+// STRUCT / MAP / LIST with a described child -> the finished Arrow array (synchronous)
+std::shared_ptr<ArrowColOut> nested_to_arrow(Result *r, Scope &sc, int j) {
+  CtxCore &c = *r->core;
+  const int64_t n = r->nrows;
+  // the parent's own validity bitmap + null count
+  FixedRun fr;
+  if (run_fixed(r, sc, j, DMB_OP_VALIDITY_ONLY, 0, true, false, &fr)) return nullptr;
+  unsigned long long *h_null = (unsigned long long *)sc.palloc(8);
+  if (!h_null) return nullptr;
+  *h_null = 0;
+  if (n && check_cuda(cudaMemcpyAsync(h_null, fr.d_null_count, 8, cudaMemcpyDeviceToHost, c.s_compute), "null count D2H")) return nullptr;
+  auto o = std::make_shared<ArrowColOut>();
+  o->core = r->core;
+  o->name = r->cols[(size_t)j].name;
+  o->length = n;
+  if (r->cols[(size_t)j].is_struct) {
+    o->format = "+s";
+    o->no_values = true;
+    const std::vector<int> kids = r->cols[(size_t)j].kids;  // (copy: converting a kid may touch r->cols)
+    for (int kid : kids) {
+      auto ch = convert_column_sync(r, sc, kid);
+      if (!ch) return nullptr;
+      o->children.push_back(ch);
+    }
+    if (!pinned_copy(r, o, nullptr, 0, fr.d_bitmap, n ? fr.bitmap_bytes : 0, nullptr, 0)) return nullptr;
+  } else {
+    Col &col = r->cols[(size_t)j];
+    ListNode &node = *col.node;
+    uint64_t cap1 = 0, cap2 = 0;
+    if (nested_caps(r, col, &cap1, &cap2)) return nullptr;
+    if (stage_node(r, node, false)) return nullptr;
+    cudaEvent_t e = sc.event(false);  // the child slabs were copied on the copy-in stream
+    if (!e) return nullptr;
+    cudaEventRecord(e, c.s_in);
+    if (check_cuda(cudaStreamWaitEvent(c.s_compute, e, 0), "wait nested children")) return nullptr;
+    EntrySrc es;
+    es.d_entries = col.d_data;
+    es.d_validity = col.d_validity;
+    es.d_vecs = col.d_vecs;
+    es.d_counts = r->d_counts;
+    es.d_row_off = r->d_row_off;
+    es.nchunks = r->nchunks;
+    es.nrows = n;
+    es.d_child_base = node.d_base;
+    es.d_child_sizes = node.d_sizes;
+    es.cap = cap1;
+    GatherOut g1;
+    auto child = node_to_arrow(r, sc, es, node, cap2, &g1);
+    if (!child) return nullptr;
+    const bool is_map = col.type_id == DMB_TYPE_MAP;
+    o->format = is_map ? "+m" : "+l";
+    if (is_map) {  // Arrow map<key, value>: entries struct and keys are non-nullable
+      child->name = "entries";
+      child->flags = 0;
+      if (child->children.size() == 2) {
+        if (child->children[0]->null_count != 0) { set_error("MAP column '%s': NULL keys", col.name.c_str()); return nullptr; }
+        child->children[0]->flags = 0;
+        if (child->children[0]->name.empty()) child->children[0]->name = "key";
+        if (child->children[1]->name.empty()) child->children[1]->name = "value";
+      }
+    } else if (child->name.empty()) {
+      child->name = "item";
+    }
+    o->children.push_back(child);
+    if (!pinned_copy(r, o, g1.d_offsets, (size_t)(n + 1) * 4, fr.d_bitmap, n ? fr.bitmap_bytes : 0, nullptr, 0)) return nullptr;
+  }
+  if (check_cuda(cudaStreamSynchronize(c.s_compute), "nested sync")) return nullptr;
+  o->null_count = (int64_t)*h_null;
+  return o;
+}
+
 struct Pending {  // one column between its kernel launch and its device->host copies
   ArrowMap map;
   FixedRun fr;
@@ -913,6 +1584,10 @@ struct Pending {  // one column between its kernel launch and its device->host c
 int32_t launch_arrow_col(Result *r, Scope &sc, int j, int string_mode, Pending *p, size_t exact_cap = 0) {
   Col &col = r->cols[(size_t)j];
   if (!arrow_map(col, &p->map)) return -1;
+  if (p->map.is_nested) {
+    p->out = nested_to_arrow(r, sc, j);
+    return p->out ? 0 : -1;
+  }
   p->out = std::make_shared<ArrowColOut>();
   p->out->core = r->core;
   p->out->name = col.name;
@@ -940,6 +1615,7 @@ int32_t launch_arrow_col(Result *r, Scope &sc, int j, int string_mode, Pending *
 // Returns 1 when a utf8 column overflowed int32 offsets and must be relaunched with large offsets.
 int32_t drain_arrow_col(Result *r, Scope &sc, Pending *p) {
   CtxCore &c = *r->core;
+  if (p->map.is_nested) return 0;  // converted (and copied out) at launch
   ArrowColOut &o = *p->out;
   const int64_t n = r->nrows;
   if (p->map.is_list) {
@@ -952,7 +1628,7 @@ int32_t drain_arrow_col(Result *r, Scope &sc, Pending *p) {
     ch->core = r->core;
     ch->name = "item";
     ch->format = p->map.child_format;
-    o.child = ch;
+    o.children.push_back(ch);
     if (!o.values || !o.validity) return -1;
     if (n == 0) {
       memset(o.values, 0, o.values_bytes);
@@ -1028,12 +1704,40 @@ int32_t drain_arrow_col(Result *r, Scope &sc, Pending *p) {
   return 0;
 }
 
+// drain + the two relaunch cases of a string column (1: utf8 offsets overflowed -> 64-bit offsets; 2: aliased string_t
+// pointers overflowed the first-guess data buffer -> sized exactly from the total the first launch reported)
+int32_t drain_with_redo(Result *r, Scope &sc, Pending *p, int j) {
+  int32_t rc = drain_arrow_col(r, sc, p);
+  for (int redo = 0; redo < 2 && (rc == 1 || rc == 2); ++redo) {
+    const int mode = rc == 1 ? DMB_STR_ARROW_LARGE : p->sr.mode;
+    const size_t exact = (size_t)p->sr.h_ctr[0];
+    *p = Pending();
+    if (launch_arrow_col(r, sc, j, mode, p, exact)) return -1;
+    rc = drain_arrow_col(r, sc, p);
+  }
+  return rc > 0 ? -1 : rc;
+}
+
+// one column, start to finish (STRUCT fields)
+std::shared_ptr<ArrowColOut> convert_column_sync(Result *r, Scope &sc, int j) {
+  CtxCore &c = *r->core;
+  Pending p;
+  const Col &col = r->cols[(size_t)j];
+  const bool surely_large = col.phys == DMB_PHYS_STRING && (col.heap_len > 0x7fffffffull || col.force_large);
+  if (launch_arrow_col(r, sc, j, surely_large ? DMB_STR_ARROW_LARGE : DMB_STR_ARROW_UTF8, &p)) return nullptr;
+  if (drain_with_redo(r, sc, &p, j)) return nullptr;
+  if (check_cuda(cudaStreamSynchronize(c.s_compute), "sync compute") || check_cuda(cudaStreamSynchronize(c.s_out), "sync copy-out")) return nullptr;
+  if (!p.map.is_string && !p.map.is_list && !p.map.is_nested && p.h_null) p.out->null_count = (int64_t)*p.h_null;
+  r->cols[(size_t)j].arrow = p.out;
+  return p.out;
+}
+
 int32_t materialise_arrow(Result *r) {
   if (r->arrow_ready) return 0;
   CtxCore &c = *r->core;
   if (!c.bind()) return -1;
   const double t0 = now_ms();
-  const int ncols = (int)r->cols.size();
+  const int ncols = r->column_count;  // (STRUCT fields live behind the visible columns and are converted by their parent)
   {
     std::vector<Pending> pend((size_t)ncols);  // declared first: the Scope drains the streams before these die
     Scope sc(c);
@@ -1044,19 +1748,7 @@ int32_t materialise_arrow(Result *r) {
     const bool restage = !r->meta_staged;
     cudaEventRecord(in0, c.s_in);
     cudaEventRecord(out0, c.s_out);
-    auto drain = [&](int j) -> int32_t {
-      int32_t rc = drain_arrow_col(r, sc, &pend[(size_t)j]);
-      for (int redo = 0; redo < 2 && (rc == 1 || rc == 2); ++redo) {
-        // 1: utf8 offsets overflowed -> 64-bit offsets; 2: aliased string_t pointers overflowed the first-guess data
-        // buffer -> sized exactly from the total the first launch reported (both can happen to one column)
-        const int mode = rc == 1 ? DMB_STR_ARROW_LARGE : pend[(size_t)j].sr.mode;
-        const size_t exact = (size_t)pend[(size_t)j].sr.h_ctr[0];
-        pend[(size_t)j] = Pending();
-        if (launch_arrow_col(r, sc, j, mode, &pend[(size_t)j], exact)) return -1;
-        rc = drain_arrow_col(r, sc, &pend[(size_t)j]);
-      }
-      return rc > 0 ? -1 : rc;
-    };
+    auto drain = [&](int j) -> int32_t { return drain_with_redo(r, sc, &pend[(size_t)j], j); };
     // Processing order: the copy-out stream trails the copy-in stream by one column, so the first
     // column's copy-in and the last column's copy-out are the only transfers that do not overlap.
     // Small columns go to both ends, the large ones to the middle ("pyramid").
@@ -1089,7 +1781,7 @@ int32_t materialise_arrow(Result *r) {
       return -1;
     for (int j = 0; j < ncols; ++j) {
       Pending &p = pend[(size_t)j];
-      if (!p.map.is_string && !p.map.is_list && p.h_null) p.out->null_count = (int64_t)*p.h_null;
+      if (!p.map.is_string && !p.map.is_list && !p.map.is_nested && p.h_null) p.out->null_count = (int64_t)*p.h_null;
       r->cols[(size_t)j].arrow = p.out;
     }
     float f = 0;
@@ -1159,12 +1851,14 @@ void export_column(const std::shared_ptr<ArrowColOut> &o, ArrowArray *a, ArrowSc
     a->buffers = p->buffers;
     a->release = release_array;
     a->private_data = p;
-    if (o->child) {  // LIST: one child array
-      a->n_buffers = 2;
-      ArrowArray *ca = (ArrowArray *)calloc(1, sizeof(ArrowArray));
-      export_column(o->child, ca, nullptr);
-      p->child_arrays.push_back(ca);
-      a->n_children = 1;
+    if (!o->children.empty()) {  // LIST / MAP: one child array; STRUCT: one per field
+      a->n_buffers = o->no_values ? 1 : 2;
+      for (const auto &chd : o->children) {
+        ArrowArray *ca = (ArrowArray *)calloc(1, sizeof(ArrowArray));
+        export_column(chd, ca, nullptr);
+        p->child_arrays.push_back(ca);
+      }
+      a->n_children = (int64_t)p->child_arrays.size();
       a->children = p->child_arrays.data();
     }
     if (o->dict) {  // ENUM: the labels as a utf8 dictionary array (no nulls), buffers shared with the result
@@ -1190,14 +1884,16 @@ void export_column(const std::shared_ptr<ArrowColOut> &o, ArrowArray *a, ArrowSc
     memset(s, 0, sizeof(*s));
     s->format = p->format.c_str();
     s->name = p->name.c_str();
-    s->flags = 2;  // ARROW_FLAG_NULLABLE
+    s->flags = o->flags;  // ARROW_FLAG_NULLABLE
     s->release = release_schema;
     s->private_data = p;
-    if (o->child) {
-      ArrowSchema *cs = (ArrowSchema *)calloc(1, sizeof(ArrowSchema));
-      export_column(o->child, nullptr, cs);
-      p->child_schemas.push_back(cs);
-      s->n_children = 1;
+    if (!o->children.empty()) {
+      for (const auto &chd : o->children) {
+        ArrowSchema *cs = (ArrowSchema *)calloc(1, sizeof(ArrowSchema));
+        export_column(chd, nullptr, cs);
+        p->child_schemas.push_back(cs);
+      }
+      s->n_children = (int64_t)p->child_schemas.size();
       s->children = p->child_schemas.data();
     }
     if (o->dict) {
@@ -1431,11 +2127,12 @@ constexpr uint64_t kGetterPrefetchCap = 1ull << 30;  // blob bytes held in pinne
 int32_t prefetch_getters(Result *r, bool nullable) {
   r->getters_prefetched = true;  // one attempt
   CtxCore &c = *r->core;
-  const int ncols = (int)r->cols.size();
+  const int ncols = r->column_count;
   const int64_t n = r->nrows;
   static const int kWidth[] = {4, 8, 8, 1};
   uint64_t estimate = 0;
-  for (const Col &col : r->cols) {
+  for (int jj = 0; jj < ncols; ++jj) {
+    const Col &col = r->cols[(size_t)jj];
     const int kind = schema_getter_kind(col);
     if (kind == kGetString) {
       if (!text_supported(col)) return 0;  // (the on-demand path reports the error for that column)
@@ -1600,6 +2297,118 @@ moonbit_bytes_t getter_string(Result *r, int32_t col_idx, bool nullable) {
 }  // namespace
 }  // namespace dmb
 
+
+namespace dmb {
+namespace {
+
+// One column of the batch -> r->cols[j] (already allocated).  STRUCT fields become columns of their own appended behind
+// the visible ones (Col::kids); a LIST / MAP whose child is described as a column gets a ListNode.
+bool fill_column(Result *r, int j, const dmb_host_column &hc, int64_t nch, const uint32_t *counts, int depth) {
+  if (depth > 4) { set_error("column '%s': STRUCT nesting deeper than 4 levels", hc.name ? hc.name : ""); return false; }
+  if (hc.type_id == DMB_TYPE_STRUCT) {
+    if (!hc.struct_ || hc.struct_->nfields <= 0 || !hc.struct_->fields) { set_error("column %d: STRUCT column without fields", j); return false; }
+    {
+      Col &col = r->cols[(size_t)j];
+      col.name = hc.name ? hc.name : "";
+      col.type_id = DMB_TYPE_STRUCT;
+      col.phys = DMB_PHYS_U8;  // no payload of its own: validity + descriptors only
+      col.width = 1;
+      col.is_struct = true;
+      col.data.assign((size_t)nch, nullptr);
+      if (hc.validity) {
+        col.validity.assign((const void *const *)hc.validity, (const void *const *)hc.validity + nch);
+        for (const void *p : col.validity) col.any_validity |= p != nullptr;
+        if (!col.any_validity) col.validity.clear();
+      }
+    }
+    for (int32_t f = 0; f < hc.struct_->nfields; ++f) {
+      const int kid = (int)r->cols.size();
+      r->cols.emplace_back();
+      r->cols[(size_t)j].kids.push_back(kid);
+      if (!fill_column(r, kid, hc.struct_->fields[f], nch, counts, depth + 1)) return false;
+    }
+    return true;
+  }
+  Col &col = r->cols[(size_t)j];
+    col.name = hc.name ? hc.name : "";
+    col.type_id = hc.type_id;
+    col.phys = hc.phys;
+    col.dec_width = hc.dec_width;
+    col.dec_scale = hc.dec_scale;
+    col.width = dmb_phys_width(hc.phys);
+    if (col.width <= 0) { set_error("column %d: bad physical type %d", j, hc.phys); return false; }
+    if (nch > 0 && !hc.data) { set_error("column %d: no data pointers", j); return false; }
+    col.data.assign(hc.data, hc.data + nch);
+    for (int64_t k = 0; k < nch; ++k)
+      if (counts[k] && !col.data[(size_t)k]) { set_error("column %d: chunk %lld has rows but a null data pointer", j, (long long)k); return false; }
+    if (hc.validity) {
+      col.validity.assign((const void *const *)hc.validity, (const void *const *)hc.validity + nch);
+      for (const void *p : col.validity) col.any_validity |= p != nullptr;
+      if (!col.any_validity) col.validity.clear();
+    }
+    col.heap_base = (const uint8_t *)hc.heap_base;
+    col.heap_len = hc.heap_len;
+    if (hc.type_id == DMB_TYPE_ENUM) {
+      if (hc.phys != DMB_PHYS_U8 && hc.phys != DMB_PHYS_U16 && hc.phys != DMB_PHYS_U32) { set_error("column %d: ENUM indices are uint8/uint16/uint32", j); return false; }
+      const dmb_enum_dict *d = hc.dict;
+      if (!d || !d->offsets || (d->size && d->offsets[d->size] && !d->data)) { set_error("column %d: ENUM column without a dictionary", j); return false; }
+      auto dict = std::make_shared<EnumDict>();
+      dict->offsets.assign(d->offsets, d->offsets + (size_t)d->size + 1);
+      if (dict->offsets[0] != 0 || dict->offsets[d->size] > 0x7fffffffu) { set_error("column %d: ENUM dictionary offsets must start at 0 and stay below 2 GiB", j); return false; }
+      for (uint32_t i = 0; i < d->size; ++i) {
+        if (dict->offsets[i + 1] < dict->offsets[i]) { set_error("column %d: ENUM dictionary offsets are not monotonic", j); return false; }
+        const uint32_t len = dict->offsets[i + 1] - dict->offsets[i];
+        if (len > dict->max_len) dict->max_len = len;
+      }
+      if (d->offsets[d->size]) dict->data.assign(d->data, d->data + d->offsets[d->size]);
+      col.dict = dict;
+    }
+    if (hc.type_id == DMB_TYPE_LIST && !(hc.list && hc.list->child_col)) {
+      const dmb_host_list *l = hc.list;
+      if (col.width != 16) { set_error("column %d: LIST vectors hold 16-byte list entries (phys DMB_PHYS_U128)", j); return false; }
+      if (!l || (nch > 0 && (!l->child_data || !l->child_sizes))) { set_error("column %d: LIST column without child vectors", j); return false; }
+      col.is_list = true;
+      col.child_type_id = l->child_type_id;
+      col.child_phys = l->child_phys;
+      col.child_dec_width = l->child_dec_width;
+      col.child_dec_scale = l->child_dec_scale;
+      col.child_width = dmb_phys_width(l->child_phys);
+      if (col.child_width <= 0 || l->child_phys == DMB_PHYS_STRING) { set_error("column %d: LIST child must be a fixed-width type (physical type %d)", j, l->child_phys); return false; }
+      col.child_data.assign(l->child_data, l->child_data + nch);
+      col.child_sizes.assign(l->child_sizes, l->child_sizes + nch);
+      if (l->child_validity) {
+        col.child_validity.assign((const void *const *)l->child_validity, (const void *const *)l->child_validity + nch);
+        bool any = false;
+        for (const void *p : col.child_validity) any |= p != nullptr;
+        if (!any) col.child_validity.clear();
+      }
+      col.child_base.assign((size_t)nch + 1, 0);
+      col.child_val_off.assign((size_t)(nch > 0 ? nch : 1), -1);
+      uint64_t words = 0;
+      for (int64_t k = 0; k < nch; ++k) {
+        if (col.child_sizes[(size_t)k] && !col.child_data[(size_t)k]) { set_error("column %d: chunk %lld has child elements but a null child pointer", j, (long long)k); return false; }
+        col.child_base[(size_t)k + 1] = col.child_base[(size_t)k] + col.child_sizes[(size_t)k];
+        if (!col.child_validity.empty() && col.child_validity[(size_t)k]) {
+          col.child_val_off[(size_t)k] = (int64_t)words;
+          words += (col.child_sizes[(size_t)k] + 63) / 64 + 1;
+        }
+      }
+    }
+    if ((hc.type_id == DMB_TYPE_LIST || hc.type_id == DMB_TYPE_MAP) && hc.list && hc.list->child_col) {
+    if (col.width != 16) { set_error("column %d: LIST / MAP vectors hold 16-byte list entries (phys DMB_PHYS_U128)", j); return false; }
+    col.node = build_node(hc.list, nch, 0);
+    if (!col.node) return false;
+    col.is_map = hc.type_id == DMB_TYPE_MAP;
+  } else if (hc.type_id == DMB_TYPE_MAP) {
+    set_error("column %d: MAP column without its STRUCT<key, value> child (dmb_host_list.child_col)", j);
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+}  // namespace dmb
+
 // =====================================================================================  L1
 extern "C" duckdb_mb_arrow_result *duckdb_mb_gpu_result_from_chunks(duckdb_mb_gpu_ctx *ctx, const dmb_host_batch *batch) {
   if (!ctx || !ctx->core) { set_error("duckdb_mb_gpu_result_from_chunks: null context"); return nullptr; }
@@ -1621,74 +2430,8 @@ extern "C" duckdb_mb_arrow_result *duckdb_mb_gpu_result_from_chunks(duckdb_mb_gp
   r->column_count = batch->ncols;
   r->row_count = (int32_t)r->nrows;  // idx_t -> int32_t, src/duckdb_native.c:2265
   r->cols.resize((size_t)batch->ncols);
-  for (int32_t j = 0; j < batch->ncols; ++j) {
-    const dmb_host_column &hc = batch->cols[j];
-    Col &col = r->cols[(size_t)j];
-    col.name = hc.name ? hc.name : "";
-    col.type_id = hc.type_id;
-    col.phys = hc.phys;
-    col.dec_width = hc.dec_width;
-    col.dec_scale = hc.dec_scale;
-    col.width = dmb_phys_width(hc.phys);
-    if (col.width <= 0) { set_error("column %d: bad physical type %d", j, hc.phys); return nullptr; }
-    if (batch->nchunks > 0 && !hc.data) { set_error("column %d: no data pointers", j); return nullptr; }
-    col.data.assign(hc.data, hc.data + batch->nchunks);
-    for (int64_t k = 0; k < batch->nchunks; ++k)
-      if (batch->counts[k] && !col.data[(size_t)k]) { set_error("column %d: chunk %lld has rows but a null data pointer", j, (long long)k); return nullptr; }
-    if (hc.validity) {
-      col.validity.assign((const void *const *)hc.validity, (const void *const *)hc.validity + batch->nchunks);
-      for (const void *p : col.validity) col.any_validity |= p != nullptr;
-      if (!col.any_validity) col.validity.clear();
-    }
-    col.heap_base = (const uint8_t *)hc.heap_base;
-    col.heap_len = hc.heap_len;
-    if (hc.type_id == DMB_TYPE_ENUM) {
-      if (hc.phys != DMB_PHYS_U8 && hc.phys != DMB_PHYS_U16 && hc.phys != DMB_PHYS_U32) { set_error("column %d: ENUM indices are uint8/uint16/uint32", j); return nullptr; }
-      const dmb_enum_dict *d = hc.dict;
-      if (!d || !d->offsets || (d->size && d->offsets[d->size] && !d->data)) { set_error("column %d: ENUM column without a dictionary", j); return nullptr; }
-      auto dict = std::make_shared<EnumDict>();
-      dict->offsets.assign(d->offsets, d->offsets + (size_t)d->size + 1);
-      if (dict->offsets[0] != 0 || dict->offsets[d->size] > 0x7fffffffu) { set_error("column %d: ENUM dictionary offsets must start at 0 and stay below 2 GiB", j); return nullptr; }
-      for (uint32_t i = 0; i < d->size; ++i) {
-        if (dict->offsets[i + 1] < dict->offsets[i]) { set_error("column %d: ENUM dictionary offsets are not monotonic", j); return nullptr; }
-        const uint32_t len = dict->offsets[i + 1] - dict->offsets[i];
-        if (len > dict->max_len) dict->max_len = len;
-      }
-      if (d->offsets[d->size]) dict->data.assign(d->data, d->data + d->offsets[d->size]);
-      col.dict = dict;
-    }
-    if (hc.type_id == DMB_TYPE_LIST) {
-      const dmb_host_list *l = hc.list;
-      if (col.width != 16) { set_error("column %d: LIST vectors hold 16-byte list entries (phys DMB_PHYS_U128)", j); return nullptr; }
-      if (!l || (batch->nchunks > 0 && (!l->child_data || !l->child_sizes))) { set_error("column %d: LIST column without child vectors", j); return nullptr; }
-      col.is_list = true;
-      col.child_type_id = l->child_type_id;
-      col.child_phys = l->child_phys;
-      col.child_dec_width = l->child_dec_width;
-      col.child_dec_scale = l->child_dec_scale;
-      col.child_width = dmb_phys_width(l->child_phys);
-      if (col.child_width <= 0 || l->child_phys == DMB_PHYS_STRING) { set_error("column %d: LIST child must be a fixed-width type (physical type %d)", j, l->child_phys); return nullptr; }
-      col.child_data.assign(l->child_data, l->child_data + batch->nchunks);
-      col.child_sizes.assign(l->child_sizes, l->child_sizes + batch->nchunks);
-      if (l->child_validity) {
-        col.child_validity.assign((const void *const *)l->child_validity, (const void *const *)l->child_validity + batch->nchunks);
-        bool any = false;
-        for (const void *p : col.child_validity) any |= p != nullptr;
-        if (!any) col.child_validity.clear();
-      }
-      col.child_base.assign((size_t)batch->nchunks + 1, 0);
-      col.child_val_off.assign((size_t)(batch->nchunks > 0 ? batch->nchunks : 1), -1);
-      uint64_t words = 0;
-      for (int64_t k = 0; k < batch->nchunks; ++k) {
-        if (col.child_sizes[(size_t)k] && !col.child_data[(size_t)k]) { set_error("column %d: chunk %lld has child elements but a null child pointer", j, (long long)k); return nullptr; }
-        col.child_base[(size_t)k + 1] = col.child_base[(size_t)k] + col.child_sizes[(size_t)k];
-        if (!col.child_validity.empty() && col.child_validity[(size_t)k]) {
-          col.child_val_off[(size_t)k] = (int64_t)words;
-          words += (col.child_sizes[(size_t)k] + 63) / 64 + 1;
-        }
-      }
-    }
-  }
+  for (int32_t j = 0; j < batch->ncols; ++j)
+    if (!fill_column(r.get(), j, batch->cols[j], batch->nchunks, batch->counts, 0)) return nullptr;
   return r.release();
 }
 
@@ -2054,6 +2797,10 @@ Result *slice_result(const Result *p, const std::shared_ptr<CtxCore> &core, int6
         col.heap_len = 0;
       }
     }
+    col.is_struct = pc.is_struct;
+    col.kids = pc.kids;  // (the hidden field columns are sliced like every other column, at the same indices)
+    col.is_map = pc.is_map;
+    if (pc.node) col.node = slice_node(*pc.node, c0, c1);
     if (pc.is_list) {
       col.is_list = true;
       col.child_type_id = pc.child_type_id;

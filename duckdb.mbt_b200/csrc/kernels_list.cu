@@ -306,8 +306,12 @@ list_emit_kernel(dmb_list_job job, BatchView b, unsigned long long *chunk_sum /*
     const uint64_t run_d = cmin;  // source element of output element e of a contiguous chunk: run_d + e
     // ---- gather the chunk's child elements, output-centric, in 32-aligned groups of OUTPUT elements
     const uint64_t child0 = __ldg(job.child_base + c);  // element index of the chunk's child vector in the staged slab
-    const int64_t cvo = job.child_val_off ? __ldg(job.child_val_off + c) : -1;
+    // child validity: one padded mask per chunk (bit = element index inside the chunk's child vector), or, for a
+    // second-level gather, ONE bitmap over the whole slab (bit = element index in the slab: cbit0 = the chunk's first element)
+    const bool dense_bits = (job.large & DMB_LIST_DENSE_CHILD_BITS) != 0;
+    const int64_t cvo = dense_bits ? 0 : (job.child_val_off ? __ldg(job.child_val_off + c) : -1);
     const uint64_t *cmask = (job.child_validity && cvo >= 0) ? job.child_validity + cvo : nullptr;
+    const uint64_t cbit0 = dense_bits ? child0 : 0ull;
     const uint64_t first = cbase & ~31ull, end = cbase + csum, stop = (end + 31ull) & ~31ull;
     uint32_t *bm32 = reinterpret_cast<uint32_t *>(job.out_child_validity);
     unsigned nulls = 0;
@@ -331,7 +335,7 @@ list_emit_kernel(dmb_list_job job, BatchView b, unsigned long long *chunk_sum /*
         const uint4 *sal = reinterpret_cast<const uint4 *>(s0 - m);
         const int ws = m >> 2;
         const uint32_t sh = (uint32_t)(m & 3) * 8u;
-        const uint64_t sbit0 = run_d + head;  // mask bit of the first element of vector 0
+        const uint64_t sbit0 = cbit0 + run_d + head;  // mask bit of the first element of vector 0
         uint4 *dal = reinterpret_cast<uint4 *>(dA);
 #pragma unroll 2
         for (uint32_t v = threadIdx.x; v < nvec; v += kThreads) {
@@ -358,7 +362,7 @@ list_emit_kernel(dmb_list_job job, BatchView b, unsigned long long *chunk_sum /*
         if (head == (uint32_t)csum) {  // no aligned vector at all: csum < 2 * R elements... or more when dE <= dA: walk them
           for (uint32_t q = threadIdx.x; q < (uint32_t)csum; q += kThreads) {
             const uint64_t src = run_d + q;
-            const bool valid = cm32 ? (load_bits32(cm32, (int64_t)src, 1) != 0u) : true;
+            const bool valid = cm32 ? (load_bits32(cm32, (int64_t)(cbit0 + src), 1) != 0u) : true;
             T v;
             memset(&v, 0, sizeof(T));
             if (valid) v = *reinterpret_cast<const T *>(srcb + (uint64_t)q * W);
@@ -366,7 +370,7 @@ list_emit_kernel(dmb_list_job job, BatchView b, unsigned long long *chunk_sum /*
           }
         } else if (e != 0xffffffffu) {
           const uint64_t src = run_d + e;
-          const bool valid = cm32 ? (load_bits32(cm32, (int64_t)src, 1) != 0u) : true;
+          const bool valid = cm32 ? (load_bits32(cm32, (int64_t)(cbit0 + src), 1) != 0u) : true;
           T v;
           memset(&v, 0, sizeof(T));
           if (valid) v = *reinterpret_cast<const T *>(srcb + (uint64_t)e * W);
@@ -379,7 +383,7 @@ list_emit_kernel(dmb_list_job job, BatchView b, unsigned long long *chunk_sum /*
         const uint64_t lo = Ew > cbase ? Ew : cbase, hi = Ew + 32 < end ? Ew + 32 : end;
         if (hi <= lo) continue;
         const int nb = (int)(hi - lo);
-        const uint32_t bits = cm32 ? load_bits32(cm32, (int64_t)(run_d + (lo - cbase)), nb) : (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
+        const uint32_t bits = cm32 ? load_bits32(cm32, (int64_t)(cbit0 + run_d + (lo - cbase)), nb) : (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
         nulls += (unsigned)(nb - __popc(bits));
         if (bm32) {
           if (nb == 32) bm32[Ew >> 5] = bits;
@@ -418,9 +422,9 @@ list_emit_kernel(dmb_list_job job, BatchView b, unsigned long long *chunk_sum /*
             src = s_src[lo] + (e - s_start[lo]);
           }
           // the element is read whether or not it is NULL (it is storage of the child vector): mask word and element in flight together
-          const uint64_t cw = cmask ? __ldg(cmask + (src >> 6)) : ~0ull;
+          const uint64_t cw = cmask ? __ldg(cmask + ((cbit0 + src) >> 6)) : ~0ull;
           v[u] = *reinterpret_cast<const T *>(reinterpret_cast<const uint8_t *>(job.child_data) + (child0 + src) * W);
-          valid[u] = (cw >> (src & 63)) & 1ull;
+          valid[u] = (cw >> ((cbit0 + src) & 63)) & 1ull;
         }
       }
 #pragma unroll
@@ -481,7 +485,7 @@ extern "C" int32_t dmb_dev_list_batch(const dmb_list_job *job, const uint32_t *c
   static const bool three_pass = getenv("DMB_LIST_THREE_PASS") != nullptr;  // A/B knob: the sum + scan + emit launches
   if (three_pass) {
     list_sum_kernel<<<grid, kThreads, 0, st>>>(*job, counts, nchunks, chunk_sum);
-    list_scan_kernel<<<1, kScanThreads, 0, st>>>(chunk_sum, chunk_base, nchunks, job->total, flags, job->large);
+    list_scan_kernel<<<1, kScanThreads, 0, st>>>(chunk_sum, chunk_base, nchunks, job->total, flags, job->large & 1);
   } else if (check_cuda(cudaMemsetAsync(chunk_sum, 0, (size_t)nchunks * 8, st), "list status memset")) {
     return -1;
   }
@@ -502,7 +506,7 @@ extern "C" int32_t dmb_dev_list_batch(const dmb_list_job *job, const uint32_t *c
   };
 #define DMB_LIST_LAUNCH(W)                                                                                          \
   do {                                                                                                              \
-    if (job->large) { if (launch(list_emit_kernel<W, true, false>, list_emit_kernel<W, true, true>)) return -1; }   \
+    if (job->large & 1) { if (launch(list_emit_kernel<W, true, false>, list_emit_kernel<W, true, true>)) return -1; }   \
     else { if (launch(list_emit_kernel<W, false, false>, list_emit_kernel<W, false, true>)) return -1; }            \
   } while (0)
   switch (w) {

@@ -71,15 +71,24 @@ class ListJob(C.Structure):
                 ("child_sizes", C.c_void_p)]
 
 
+class HostColumn(C.Structure):
+    pass
+
+
 class HostList(C.Structure):
     _fields_ = [("child_type_id", C.c_int32), ("child_phys", C.c_int32), ("child_dec_width", C.c_int32), ("child_dec_scale", C.c_int32),
-                ("child_data", C.c_void_p), ("child_validity", C.c_void_p), ("child_sizes", C.c_void_p)]
+                ("child_data", C.c_void_p), ("child_validity", C.c_void_p), ("child_sizes", C.c_void_p),
+                ("child_col", C.POINTER(HostColumn))]
 
 
-class HostColumn(C.Structure):
-    _fields_ = [("name", C.c_char_p), ("type_id", C.c_int32), ("phys", C.c_int32), ("dec_width", C.c_int32),
-                ("dec_scale", C.c_int32), ("data", C.POINTER(C.c_void_p)), ("validity", C.POINTER(C.c_void_p)),
-                ("heap_base", C.c_void_p), ("heap_len", C.c_uint64), ("dict", C.POINTER(EnumDict)), ("list", C.POINTER(HostList))]
+class HostStruct(C.Structure):
+    _fields_ = [("nfields", C.c_int32), ("reserved", C.c_int32), ("fields", C.POINTER(HostColumn))]
+
+
+HostColumn._fields_ = [("name", C.c_char_p), ("type_id", C.c_int32), ("phys", C.c_int32), ("dec_width", C.c_int32),
+                       ("dec_scale", C.c_int32), ("data", C.POINTER(C.c_void_p)), ("validity", C.POINTER(C.c_void_p)),
+                       ("heap_base", C.c_void_p), ("heap_len", C.c_uint64), ("dict", C.POINTER(EnumDict)), ("list", C.POINTER(HostList)),
+                       ("struct_", C.POINTER(HostStruct))]
 
 
 class HostBatch(C.Structure):
@@ -122,7 +131,7 @@ CHUNK_SINK = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_uint32, C.POINTER
 EXPORTED_SYMBOLS = [
     "dmb_dev_fixed_batch", "dmb_op_out_width", "dmb_phys_width", "dmb_dev_string_scratch_bytes",
     "dmb_dev_string_error", "dmb_dev_string_batch", "dmb_dev_rev_fixed_batch", "dmb_dev_rev_string_batch",
-    "dmb_dev_valid_bytes_to_masks", "dmb_dev_make_string_t", "dmb_render_supported", "dmb_render_slot_bytes", "dmb_dev_render_text", "dmb_dev_enum_to_string_t", "dmb_dev_enum_utf8", "dmb_dev_list_scratch_bytes", "dmb_dev_list_batch",
+    "dmb_dev_valid_bytes_to_masks", "dmb_dev_make_string_t", "dmb_dev_blob_escape", "dmb_render_supported", "dmb_render_slot_bytes", "dmb_dev_render_text", "dmb_dev_enum_to_string_t", "dmb_dev_enum_utf8", "dmb_dev_list_scratch_bytes", "dmb_dev_list_batch",
     "duckdb_mb_gpu_last_error", "duckdb_mb_gpu_device_count", "duckdb_mb_gpu_bind_numa", "duckdb_mb_gpu_ctx_create",
     "duckdb_mb_gpu_ctx_destroy", "duckdb_mb_gpu_ctx_sync", "duckdb_mb_gpu_host_alloc", "duckdb_mb_gpu_host_free",
     "duckdb_mb_gpu_result_from_chunks", "duckdb_mb_gpu_result_materialise_arrow",

@@ -58,6 +58,8 @@ enum dmb_type {
   DMB_TYPE_TIMESTAMP_NS = 22,
   DMB_TYPE_ENUM = 23,     /* uint8/16/32 indices into the type's dictionary (dmb_enum_dict) */
   DMB_TYPE_LIST = 24,     /* duckdb_list_entry vectors + one child vector per chunk (dmb_host_list) */
+  DMB_TYPE_STRUCT = 25,   /* a validity mask per chunk + one vector per field and chunk (dmb_host_struct) */
+  DMB_TYPE_MAP = 26,      /* LIST of STRUCT<key, value>: dmb_host_list whose child_col is a two-field STRUCT */
   DMB_TYPE_UUID = 27,
   DMB_TYPE_TIME_TZ = 30,
   DMB_TYPE_TIMESTAMP_TZ = 31,
@@ -313,12 +315,16 @@ typedef struct dmb_list_job {
   unsigned long long *total;        /* number of child elements written                         */
   unsigned long long *child_null_count;
   int32_t child_width;              /* 1 / 2 / 4 / 8 / 16                                       */
-  int32_t large;                    /* int64 offsets (large_list)                               */
+  int32_t large;                    /* bit 0: int64 offsets (large_list); bit 1 (DMB_LIST_DENSE_CHILD_BITS): child_validity
+                                       is ONE bitmap over the whole staged child slab (bit i = element i; child_val_off is
+                                       ignored) instead of one padded mask per chunk -- the form a second-level gather
+                                       (nested lists: entries already rebased onto the slab) reads */
   const uint64_t *child_sizes;      /* [nchunks] elements in each chunk's child vector, or NULL: entries are not
                                        range-checked.  A valid row whose offset + length reaches past its child
                                        vector raises flag 8 and contributes no elements (never read)            */
 } dmb_list_job;
 
+#define DMB_LIST_DENSE_CHILD_BITS 2
 size_t dmb_dev_list_scratch_bytes(int64_t nchunks);
 /* scratch[0] after the call: error flags (1: total exceeds int32 offsets, 2: a chunk with > 4 G child elements,
  * 4: a look-back gave up waiting, 8: a list entry outside its child vector) */
@@ -424,6 +430,7 @@ typedef struct dmb_enum_dict {
  * (list<child>; the child in the Arrow form of its type, as for a top-level column: BOOLEAN bit-packed, DECIMAL as
  * decimal128, INTERVAL as month_day_nano, the other fixed-width types as stored); the
  * reference rejects LIST on its chunk path (src/duckdb_native.c:271-303) and has no Arrow mapping for it. */
+struct dmb_host_column;
 typedef struct dmb_host_list {
   int32_t child_type_id;                  /* enum dmb_type */
   int32_t child_phys;                     /* enum dmb_phys */
@@ -431,7 +438,22 @@ typedef struct dmb_host_list {
   const void *const *child_data;          /* [nchunks] */
   const uint64_t *const *child_validity;  /* [nchunks], entries may be NULL; the array may be NULL */
   const uint64_t *child_sizes;            /* [nchunks] elements in each chunk's child vector */
+  /* Children that are not one fixed-width vector -- VARCHAR / BLOB (the child vectors' string heaps are gathered by the
+   * stager), STRUCT (MAP = LIST<STRUCT<key, value>>), LIST (nested lists) -- are described as a full column: data[k] /
+   * validity[k] / struct_ / list of child_col are those of chunk k's CHILD vector (child_sizes[k] elements of it:
+   * duckdb_list_vector_get_child / _get_size).  When child_col is set it wins over the four child_* type fields and the two
+   * pointer tables above.  NULL: the flat fixed-width form. */
+  const struct dmb_host_column *child_col;
 } dmb_host_list;
+
+/* STRUCT: what duckdb_struct_vector_get_child(v, i) returns for every field, chunk by chunk; the struct's own validity
+ * is the column's `validity` (its `data` is unused and may be NULL).  Arrow export only (struct<...>, fields exported like
+ * top-level columns); the reference rejects STRUCT on its chunk path (src/duckdb_native.c:271-303). */
+typedef struct dmb_host_struct {
+  int32_t nfields;
+  int32_t reserved;
+  const struct dmb_host_column *fields;   /* [nfields]; name = the field's name */
+} dmb_host_struct;
 
 /* One column of a host chunk batch: the pointers duckdb_vector_get_data /
  * duckdb_vector_get_validity return for each chunk (src/duckdb_native.c:529-530,547). */
@@ -449,7 +471,8 @@ typedef struct dmb_host_column {
   const void *heap_base;
   uint64_t heap_len;
   const dmb_enum_dict *dict;        /* ENUM columns: the dictionary (copied by result_from_chunks); else NULL */
-  const dmb_host_list *list;        /* LIST columns: the per-chunk child vectors (pointer tables copied); else NULL */
+  const dmb_host_list *list;        /* LIST / MAP columns: the per-chunk child vectors (pointer tables copied); else NULL */
+  const dmb_host_struct *struct_;   /* STRUCT columns: the per-field vectors; else NULL */
 } dmb_host_column;
 
 /* heap_base == DMB_HEAP_INLINE_ONLY (heap_len 0): the caller guarantees that every string of the

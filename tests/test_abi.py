@@ -54,7 +54,7 @@ def test_struct_layouts():
     assert C.sizeof(nat.StringJob) == 112
     assert C.sizeof(nat.RevFixedJob) == 56
     assert C.sizeof(nat.RevStringJob) == 72
-    assert C.sizeof(nat.HostColumn) == 72 and C.sizeof(nat.HostList) == 40 and C.sizeof(nat.HostBatch) == 32
+    assert C.sizeof(nat.HostColumn) == 80 and C.sizeof(nat.HostList) == 48 and C.sizeof(nat.HostStruct) == 16 and C.sizeof(nat.HostBatch) == 32
     assert C.sizeof(nat.EnumDict) == 24 and C.sizeof(nat.EnumJob) == 72 and C.sizeof(nat.ListJob) == 112
     assert C.sizeof(nat.TypedColumn) == 56
 
