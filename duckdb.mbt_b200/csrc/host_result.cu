@@ -1415,10 +1415,9 @@ std::shared_ptr<ArrowColOut> node_to_arrow(Result *r, Scope &sc, const EntrySrc 
       o->null_count = (int64_t)gv.h_ctr[1];
       return pinned_copy(r, o, nullptr, 0, gv.d_bitmap, bm_bytes, nullptr, 0);
     }
-    o->validity = r->core->pin.alloc(64);  // no NULL structs: a NULL validity buffer would do, an all-ones one is as valid
-    o->values = r->core->pin.alloc(64);
+    o->validity = nullptr;  // no NULL structs: no validity buffer (null_count 0)
     o->validity_bytes = 0;
-    return (o->validity && o->values) ? o : nullptr;
+    return o;
   }
   // LIST<LIST<...>>: the gathered inner entries (already rebased onto the grandchild slab) are the next level's entries
   GatherOut g;
@@ -2451,8 +2450,8 @@ extern "C" int32_t duckdb_mb_gpu_result_export_arrow(duckdb_mb_arrow_result *r, 
     export_column(r->cols[(size_t)col].arrow, out_array, out_schema);
     return 1;
   }
-  // whole batch: struct array, one child per column
-  const size_t nc = r->cols.size();
+  // whole batch: struct array, one child per (visible) column
+  const size_t nc = (size_t)r->column_count;
   if (out_array) {
     ExportPriv *p = new ExportPriv();
     memset(out_array, 0, sizeof(*out_array));
