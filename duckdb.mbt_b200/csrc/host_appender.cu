@@ -510,6 +510,7 @@ extern "C" int64_t duckdb_mb_gpu_appender_flushed_row_count(duckdb_mb_gpu_append
 
 extern "C" int32_t duckdb_mb_gpu_append_arrow_batch(duckdb_mb_gpu_appender *a, const struct ArrowArray *batch,
                                                     const struct ArrowSchema *schema) {
+  NvtxRange nvtx("dmb::append_arrow_batch");
   if (!a) { set_error("null appender"); return 0; }
   if (a->state != kReady && a->state != kFlushed) return illegal(a, "append_arrow_batch");  // legal where BeginRow is
   if (!batch || !schema || !schema->format || strcmp(schema->format, "+s") != 0) {

@@ -13,9 +13,19 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "dmb_common.cuh"
 
 namespace dmb {
+
+// NVTX range around a host-side phase (tracing).  Header-only NVTX v3: a no-op unless a profiler is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 // Size-bucketed cache of device or page-locked host allocations.  cudaMalloc / cudaHostAlloc cost
 // far more than a conversion (pinning runs at a few GB/s), so buffers are recycled across results

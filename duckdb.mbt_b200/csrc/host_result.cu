@@ -245,6 +245,7 @@ void compact_fixup(void *user, int64_t k, uint8_t *staged, size_t bytes) {
 int32_t stage_column(Result *r, int j) {
   Col &col = r->cols[(size_t)j];
   if (col.staged) return 0;
+  NvtxRange nvtx("dmb::stage_column");
   if (ensure_meta(r)) return -1;
   CtxCore &c = *r->core;
   const int64_t nch = r->nchunks;
@@ -1502,6 +1503,7 @@ std::shared_ptr<ArrowColOut> convert_column_sync(Result *r, Scope &sc, int j);
 
 // STRUCT / MAP / LIST with a described child -> the finished Arrow array (synchronous)
 std::shared_ptr<ArrowColOut> nested_to_arrow(Result *r, Scope &sc, int j) {
+  NvtxRange nvtx("dmb::nested_to_arrow");
   CtxCore &c = *r->core;
   const int64_t n = r->nrows;
   // the parent's own validity bitmap + null count
@@ -1733,6 +1735,7 @@ std::shared_ptr<ArrowColOut> convert_column_sync(Result *r, Scope &sc, int j) {
 
 int32_t materialise_arrow(Result *r) {
   if (r->arrow_ready) return 0;
+  NvtxRange nvtx("dmb::materialise_arrow");
   CtxCore &c = *r->core;
   if (!c.bind()) return -1;
   const double t0 = now_ms();
@@ -2125,6 +2128,7 @@ constexpr uint64_t kGetterPrefetchCap = 1ull << 30;  // blob bytes held in pinne
 
 int32_t prefetch_getters(Result *r, bool nullable) {
   r->getters_prefetched = true;  // one attempt
+  NvtxRange nvtx("dmb::prefetch_getters");
   CtxCore &c = *r->core;
   const int ncols = r->column_count;
   const int64_t n = r->nrows;

@@ -580,6 +580,9 @@ __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t
 // error flag and let the launch finish; the mbarrier waits inside a CTA depend only on that CTA's own warps and copy
 // engine transactions, so one that is still pending after 3x that long is a protocol bug: it traps.
 constexpr unsigned long long kWaitLimitNs = 4000000000ull;
+// the look-back's limit, adjustable from the host (dmb_dev_set_lookback_limit_ns): tests set it to 0 to see the error path
+// end in a reported flag and a usable context
+__device__ unsigned long long g_lookback_limit_ns = kWaitLimitNs;
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   // try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs out:
   // with the default (short) limit the retry loop alone took a third of the kernel's issue slots
@@ -686,7 +689,7 @@ __device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, in
         if (t0 == 0) t0 = now;
         // gave up (warp-uniform): flag it and go on with what has been summed -- the launch ends, the host reports the
         // flag and discards the outputs; the context stays usable (a trap would poison it for every other result)
-        if (__any_sync(0xffffffffu, now - t0 > kWaitLimitNs)) {
+        if (__any_sync(0xffffffffu, now - t0 > g_lookback_limit_ns)) {
           if (lane == 0) atomicOr(err_flags, (unsigned long long)kErrTimeout);
           state = 1;
           break;
@@ -1612,6 +1615,10 @@ extern "C" int32_t dmb_dev_string_trace(unsigned long long *out, int64_t n) {
   return (int32_t)cudaMemcpyFromSymbol(out, g_str_trace, sizeof(unsigned long long) * (size_t)n);
 }
 #endif
+
+extern "C" int32_t dmb_dev_set_lookback_limit_ns(unsigned long long ns) {
+  return check_cuda(cudaMemcpyToSymbol(g_lookback_limit_ns, &ns, sizeof(ns)), "set look-back limit");
+}
 
 extern "C" size_t dmb_dev_string_scratch_bytes(int64_t nchunks) {
   return (size_t)(2 + kStrTilesPerChunk * (nchunks > 0 ? nchunks : 0)) * sizeof(unsigned long long);

@@ -223,6 +223,9 @@ int32_t dmb_phys_width(int32_t phys);
  *             `in`, `out_data`, `heap_dev` 16-byte aligned; the heap copy followed by >= 16 readable bytes
  * Replaces src/duckdb_native.c:597-603 (string_t read) and :2474-2510 / :2699-2755. */
 size_t dmb_dev_string_scratch_bytes(int64_t nchunks);
+/* How long a tile's look-back waits for its predecessors before it gives up with flag 16 (default 4 s; the launch then
+ * ends normally, the host reports the error and the context stays usable).  Process-wide per device; a test knob. */
+int32_t dmb_dev_set_lookback_limit_ns(unsigned long long ns);
 /* error flags raised by the last string launch on `scratch` (0 = none); synchronises `stream`.
  * 1: a tile holds > 4 GiB  2: total exceeds int32 offsets  4: string_t pointer outside the heap
  * 8: total exceeds out_data_cap  16: a look-back gave up waiting (the outputs are not valid) */
