@@ -534,7 +534,24 @@ constexpr int kMetaRing = 4;
 #ifndef DMB_PACK_UNROLL
 #define DMB_PACK_UNROLL 2
 #endif
-constexpr int kPackUnroll = DMB_PACK_UNROLL;  // words in flight per thread in the pointer-row copy loop
+constexpr int kPackUnroll = DMB_PACK_UNROLL;  // words in flight per thread in the pointer-row copy loop (DMB_PACK_CHUNK=0 only)
+// A/B knobs of the pack kernel (all on by default; profiles/r02_string_pack_kernel_iterations.txt has what each one bought)
+#ifndef DMB_PACK_CHUNK
+#define DMB_PACK_CHUNK 1   // pointer rows are copied four words at a time, loads first
+#endif
+#ifndef DMB_PACK_SROT
+#define DMB_PACK_SROT 1    // string_t are read from S in a lane-rotated order (no bank conflicts), rotated back in registers
+#endif
+#ifndef DMB_PACK_WSUM4
+#define DMB_PACK_WSUM4 0   // the eight warp sums are read as two 16-byte vectors (needs PackPartials aligned to 16: that layout made ptxas spill)
+#endif
+#ifndef DMB_PACK_SEL
+#define DMB_PACK_SEL 1     // the inlined rows' last-word select as two bit tests
+#endif
+#ifndef DMB_PACK_UNIFY
+#define DMB_PACK_UNIFY 1   // inlined rows go through a per-thread scratch slot and the pointer rows' copy loop
+#endif
+constexpr uint32_t kPackScratchPerThread = DMB_PACK_UNIFY ? 12u : 0u;
 
 struct TileMeta {
   long long tile;            // -1: no more tiles
@@ -549,7 +566,7 @@ struct TileMeta {
 };
 
 constexpr int kPackMaxWarps = 16;
-struct PackPartials {
+struct alignas(DMB_PACK_WSUM4 ? 16 : 4) PackPartials {
   uint32_t warp_sum[kPackMaxWarps];
   uint32_t warp_hmin[kPackMaxWarps];
   uint32_t warp_hmax[kPackMaxWarps];
@@ -894,9 +911,33 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       if (pt.meta[j & (kMetaRing - 1)].has_mask) vword = pt.vmask[slot][(tid * R) >> 6] >> ((tid * R) & 63);
       int flags = 0;  // 2: bad heap pointer  4: oversized row
       uint32_t tsum = 0u, hmin = 0xffffffffu, hmax = 0u;
+      uint4 ent[R];
+      if (DMB_PACK_SROT && (R == 2 || R == 4)) {
+        // a thread's R string_t are 16 R consecutive bytes: read in row order, the eight lanes of a quarter warp would hit
+        // only 8 / R of the eight 16-byte bank groups.  Lane i starts at row (i / (8 / R)) mod R instead and the rows are
+        // rotated back in registers.
+        const int rot = R == 4 ? (lane >> 1) & 3 : (lane >> 2) & 1;
+        uint4 t[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) t[k] = s[(k + rot) & (R - 1)];
+        auto sel = [](bool c, const uint4 &a, const uint4 &b) { return make_uint4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w); };
+        if (R == 2) {
+          ent[0] = sel(rot != 0, t[1 % R], t[0]);
+          ent[1 % R] = sel(rot != 0, t[0], t[1 % R]);
+        } else {
+          uint4 u[R];
+#pragma unroll
+          for (int k = 0; k < R; ++k) u[k] = sel((rot & 1) != 0, t[(k + 3) & (R - 1)], t[k]);
+#pragma unroll
+          for (int k = 0; k < R; ++k) ent[k] = sel((rot & 2) != 0, u[(k + 2) & (R - 1)], u[k]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < R; ++k) ent[k] = s[k];
+      }
 #pragma unroll
       for (int k = 0; k < R; ++k) {
-        const uint4 e = s[k];
+        const uint4 e = ent[k];
         uint32_t lo16, hi16;
         const uint32_t l = row_bytes<HEAP>(job, e.x, e.z, e.w, ((vword >> k) & 1ull) && tid * R + k < nrows, flags, lo16, hi16);
         nxt.len[k] = l; nxt.y[k] = e.y; nxt.z[k] = e.z; nxt.w[k] = e.w;
@@ -921,8 +962,15 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       if (tid == 0) pp.not_one_run = 0u;
       bar_sync(kBarWorkers, kWT);  // (every warp has also finished packing tile j-2: H[slot] is free)
       uint32_t warp_excl = 0;
+      if (DMB_PACK_WSUM4 && NW == 8) {
+        const uint4 s0 = *reinterpret_cast<const uint4 *>(&pp.warp_sum[0]), s1 = *reinterpret_cast<const uint4 *>(&pp.warp_sum[4]);
+        const uint32_t ws[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-      for (int w = 0; w < NW; ++w) warp_excl += w < warp ? pp.warp_sum[w] : 0u;
+        for (int w = 0; w < 7; ++w) warp_excl += w < warp ? ws[w] : 0u;
+      } else {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) warp_excl += w < warp ? pp.warp_sum[w] : 0u;
+      }
       nxt.my_off = warp_excl + incl - tsum;
       if (HEAP) {
         // is the tile one run?  (every non-empty row a pointer row whose bytes follow its predecessor's in the heap)
@@ -1084,6 +1132,70 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         uint32_t wp = pos >> 2, fill = pos & 3u, acc = 0u;
         const uint32_t head = fill;                          // bytes of the first word that belong to earlier threads
         const uint32_t shared_wp = fill ? wp : 0xffffffffu;  // a first word that earlier threads also write
+#if DMB_PACK_UNIFY
+        // One code path for every row: an inlined row first drops its 12 payload bytes into the thread's own 12-byte slot of a
+        // scratch area behind H (3-word stride: conflict free) and is then copied like a pointer row whose bytes start there.
+        // (As two paths, a warp paid for both at every row slot as soon as one lane differed from the others.)
+        uint32_t *scr = reinterpret_cast<uint32_t *>(hbuf + 2u * hstride) + tid * 3;
+        const uint32_t scr_rel = (uint32_t)(reinterpret_cast<const uint8_t *>(scr) - reinterpret_cast<const uint8_t *>(hw));
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const uint32_t l = cur.len[k];
+          if (l == 0u) continue;
+          const uint32_t n = fill + l, nw = n >> 2;
+          uint32_t srel = cur.z[k] - hbase;  // the row's first byte, relative to hw
+          if (l <= 12u) {
+            scr[0] = cur.y[k];
+            scr[1] = cur.z[k];
+            scr[2] = cur.w[k];
+            srel = scr_rel;
+          }
+          // output word m of the row holds source bytes qp-4+4m .. +3
+          const uint32_t qp = srel + 4u - fill;
+          const uint32_t sq = 8u * (qp & 3u);
+          const uint32_t *sp = hw + (qp >> 2);
+          uint32_t prev = sp[0];
+          const uint32_t x0 = (__funnelshift_r(sp[-1], prev, sq) & ~low_bytes3(fill)) | acc;
+          if (nw == 0u) {
+            acc = x0 & low_bytes3(n);  // a short inlined row that does not complete the word
+          } else {
+            if (wp == shared_wp) store_bytes(ow + wp, x0, head, 4u); else ow[wp] = x0;
+            // the whole words after the first one: four per iteration, the loads of a group before its stores (the compiler
+            // may not move a shared-memory load over a shared-memory store), pointers bumped instead of indices recomputed
+            sp += 1;
+            uint32_t *op = ow + wp + 1;
+            uint32_t left = nw - 1u;
+#pragma unroll 1
+            for (; left >= 4u; left -= 4u) {
+              const uint32_t a0 = sp[0], a1 = sp[1], a2 = sp[2], a3 = sp[3];
+              op[0] = __funnelshift_r(prev, a0, sq);
+              op[1] = __funnelshift_r(a0, a1, sq);
+              op[2] = __funnelshift_r(a1, a2, sq);
+              op[3] = __funnelshift_r(a2, a3, sq);
+              prev = a3;
+              sp += 4;
+              op += 4;
+            }
+            if (left & 2u) {
+              const uint32_t a0 = sp[0], a1 = sp[1];
+              op[0] = __funnelshift_r(prev, a0, sq);
+              op[1] = __funnelshift_r(a0, a1, sq);
+              prev = a1;
+              sp += 2;
+              op += 2;
+            }
+            if (left & 1u) {
+              const uint32_t a0 = sp[0];
+              op[0] = __funnelshift_r(prev, a0, sq);
+              prev = a0;
+              sp += 1;
+            }
+            acc = (n & 3u) ? (__funnelshift_r(prev, sp[0], sq) & low_bytes3(n & 3u)) : 0u;
+          }
+          wp += nw;
+          fill = n & 3u;
+        }
+#else
 #pragma unroll
         for (int k = 0; k < R; ++k) {
           const uint32_t l = cur.len[k];
@@ -1102,17 +1214,71 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
             }
             if (nw >= 2u) ow[wp + 1] = x1;
             if (nw >= 3u) ow[wp + 2] = x2;
+#if DMB_PACK_SEL
+            // (nw <= 3; as a chain of equality tests this became a jump table)
+            acc = ((nw & 2u) ? ((nw & 1u) ? x3 : x2) : ((nw & 1u) ? x1 : x0)) & low_bytes3(n & 3u);
+#else
             acc = (nw == 0u ? x0 : (nw == 1u ? x1 : (nw == 2u ? x2 : x3))) & low_bytes3(n & 3u);
+#endif
           } else if (HEAP) {
             // pointer: the staged span.  Output word m of the row holds source bytes qp-4+4m .. +3
             const uint32_t qp = (cur.z[k] - hbase) + 4u - fill;
             const uint32_t sq = 8u * (qp & 3u);
             const uint32_t *s = hw + (qp >> 2);
             uint32_t prev = s[-1], nx = s[0];
+            uint32_t *o;
             const uint32_t x0 = (__funnelshift_r(prev, nx, sq) & ~low_bytes3(fill)) | acc;
             if (wp == shared_wp) store_bytes(ow + wp, x0, head, 4u); else ow[wp] = x0;  // l > 12: the word always completes
             prev = nx;
-            uint32_t *o = ow + wp;
+            o = ow + wp;
+#if DMB_PACK_CHUNK
+            // four words per iteration, the loads of a group before its stores (the compiler may not move a shared-memory
+            // load over a shared-memory store), pointers bumped instead of indices recomputed: 17 instructions per four
+            // words where the plain loop took 13 per two
+            {
+              const uint32_t *sp = s + 1;
+              uint32_t *op = o + 1;
+              uint32_t left = nw - 1u;  // whole words after the first one
+#pragma unroll 1
+              for (; left >= 4u; left -= 4u) {
+                const uint32_t a0 = sp[0], a1 = sp[1], a2 = sp[2], a3 = sp[3];
+                op[0] = __funnelshift_r(prev, a0, sq);
+                op[1] = __funnelshift_r(a0, a1, sq);
+                op[2] = __funnelshift_r(a1, a2, sq);
+                op[3] = __funnelshift_r(a2, a3, sq);
+                prev = a3;
+                sp += 4;
+                op += 4;
+              }
+              if (left & 2u) {
+                const uint32_t a0 = sp[0], a1 = sp[1];
+                op[0] = __funnelshift_r(prev, a0, sq);
+                op[1] = __funnelshift_r(a0, a1, sq);
+                prev = a1;
+                sp += 2;
+                op += 2;
+              }
+              if (left & 1u) {
+                const uint32_t a0 = sp[0];
+                op[0] = __funnelshift_r(prev, a0, sq);
+                prev = a0;
+                sp += 1;
+              }
+              acc = (n & 3u) ? (__funnelshift_r(prev, sp[0], sq) & low_bytes3(n & 3u)) : 0u;
+            }
+#else
+#ifdef DMB_EXP_NOCONFLICT  // (timing experiment, wrong bytes: the same loop on conflict-free addresses)
+            s = hw + lane; o = ow + lane;
+#pragma unroll kPackUnroll
+            for (uint32_t m = 1; m < nw; ++m) {
+              nx = s[32u * m];
+              o[32u * m] = __funnelshift_r(prev, nx, sq);
+              prev = nx;
+            }
+            acc = (n & 3u) ? (__funnelshift_r(prev, s[32u * nw], sq) & low_bytes3(n & 3u)) : 0u;
+#elif defined(DMB_EXP_NOCOPY)  // (timing experiment, wrong bytes: no interior words)
+            acc = (n & 3u) ? (__funnelshift_r(prev, s[nw], sq) & low_bytes3(n & 3u)) : 0u;
+#else
 #pragma unroll kPackUnroll
             for (uint32_t m = 1; m < nw; ++m) {
               nx = s[m];
@@ -1120,10 +1286,13 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
               prev = nx;
             }
             acc = (n & 3u) ? (__funnelshift_r(prev, s[nw], sq) & low_bytes3(n & 3u)) : 0u;
+#endif
+#endif
           }
           wp += nw;
           fill = n & 3u;
         }
+#endif
         if (fill) store_bytes(ow + wp, acc, wp == shared_wp ? head : 0u, fill);  // last word: the next thread owns its other bytes
         fence_proxy_async_smem();
         }
@@ -1681,7 +1850,7 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
     // persistent grid: as many CTAs as are resident at once (tiles are claimed from a ticket)
     auto launch_pack = [&](auto kernel, int rows_per_tile, int threads, uint32_t ob, uint32_t hb) -> int32_t {
       const int64_t nt = (int64_t)(kVec / rows_per_tile) * nchunks;
-      const size_t smem = (size_t)kPackTail + 2u * (size_t)rows_per_tile * 16u + ob + 2u * ((size_t)hb + 16u) + 128u;
+      const size_t smem = (size_t)kPackTail + 2u * (size_t)rows_per_tile * 16u + ob + 2u * ((size_t)hb + 16u) + (size_t)(threads - 64) * kPackScratchPerThread + 128u;
       if (check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "string_pack_kernel smem attribute")) return -1;
       int per_sm = 0;
       if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem), "string_pack_kernel occupancy")) return -1;
@@ -1720,7 +1889,7 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
     // Largest heap stage of a 512-row tile that still leaves three CTAs per SM (228 KiB of shared memory, 1 KiB
     // reserved per CTA; smem = tail + S[2] + O (= hb + 2048) + H[2]).  Measured on the C3 shape (30.8 heap bytes per
     // row): three CTAs 0.98 ms, two CTAs 1.21 ms, the run-gather kernel 1.17 ms per 50 M rows.
-    constexpr uint32_t kHb3 = ((233472u / 3u - 1024u - kPackTail - 2u * 512u * 16u - 2048u - 32u - 128u) / 3u) & ~127u;
+    constexpr uint32_t kHb3 = ((233472u / 3u - 1024u - kPackTail - 2u * 512u * 16u - 2048u - 32u - 128u - 256u * kPackScratchPerThread) / 3u) & ~127u;
     static const double min_slack = getenv("DMB_STR_PACK_MIN_SLACK") ? atof(getenv("DMB_STR_PACK_MIN_SLACK")) : 1.04;
     static const double hpr_limit = getenv("DMB_STR_PACK_HPR_LIMIT") ? atof(getenv("DMB_STR_PACK_HPR_LIMIT")) : ((double)kHb3 - 1024.0 - 128.0) / (512.0 * min_slack);
     if (heap_per_row <= hpr_limit) {
@@ -1740,7 +1909,7 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
       if (!wide && heap_per_row <= r4_limit) {
         uint32_t hb4 = ((uint32_t)(heap_per_row * 1024.0 * slack) + 1024u + 127u) & ~127u;
         if (hb4 < 2048u) hb4 = 2048u;
-        const uint32_t ob4 = hb4 + 4096u + 1024u * 4u;  // inlined rows add at most 12 bytes each: room for a third of the rows
+        const uint32_t ob4 = hb4 + 4096u + (DMB_PACK_UNIFY ? 2048u : 4096u);  // inlined rows add at most 12 bytes each: room for 6 (8) bytes per row (the scratch area took the rest of what three CTAs per SM leave)
         return large ? launch_pack(string_pack_kernel<true, 4, 8, true>, 1024, 8 * 32 + 64, ob4, hb4)
                      : launch_pack(string_pack_kernel<false, 4, 8, true>, 1024, 8 * 32 + 64, ob4, hb4);
       }
