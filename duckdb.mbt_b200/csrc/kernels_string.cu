@@ -548,10 +548,13 @@ constexpr int kPackUnroll = DMB_PACK_UNROLL;  // words in flight per thread in t
 #ifndef DMB_PACK_SEL
 #define DMB_PACK_SEL 1     // the inlined rows' last-word select as two bit tests
 #endif
+#ifndef DMB_PACK_GROUPS
+#define DMB_PACK_GROUPS 1  // two-level look-back (per-tile words for the nearest tiles, per-group sums / prefixes before them)
+#endif
 #ifndef DMB_PACK_UNIFY
 #define DMB_PACK_UNIFY 1   // inlined rows go through a per-thread scratch slot and the pointer rows' copy loop
 #endif
-constexpr uint32_t kPackScratchPerThread = DMB_PACK_UNIFY ? 12u : 0u;
+constexpr uint32_t kPackScratchPerThread = 12u;  // UNIFY kernels: one 12-byte slot per worker thread behind H
 
 struct TileMeta {
   long long tile;            // -1: no more tiles
@@ -663,14 +666,14 @@ __device__ __forceinline__ uint32_t low_bytes3(uint32_t n) { return (1u << (8u *
 // exclusive prefix of tile `tile` by decoupled look-back, executed by one warp; kLookWide status
 // words are in flight per lane, so one L2 round trip inspects 32*kLookWide predecessors; when a
 // needed word is not published yet only the unpublished ones are read again
-__device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, int64_t tile, int lane, unsigned *stats = nullptr) {
+__device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, int64_t tile, int lane, unsigned *stats = nullptr, int first_width = kLookFirst) {
   unsigned long long *err_flags = status - 1;  // scratch[1]
   uint64_t prefix = 0;
   unsigned rounds = 0, retries = 0;
   unsigned long long t0 = 0;
   if (tile > 0) {
     int64_t look = tile - 1;
-    int width = kLookFirst;  // (a narrow first round was tried: it costs a second L2 round trip more often than it saves traffic)
+    int width = first_width;  // 32 * width status words in the first round (see the call in string_pack_kernel's L warp)
     while (true) {
       uint64_t st[kLookWide];
 #pragma unroll
@@ -725,6 +728,102 @@ __device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, in
   return prefix;
 }
 
+// Two-level look-back of the pack kernel.  With ~450 persistent CTAs that claim tiles two iterations ahead, the nearest
+// predecessor whose PREFIX is out is typically 150-300 tiles back; a tile-by-tile look-back of 256 words per round then sits
+// on the edge between one L2 round trip and two, and the launch is bistable (late prefixes make every look-back longer,
+// which makes the prefixes later: 0.82 vs 1.15-1.47 ms per 60 M rows on all-pointer columns).  So tiles also add their
+// aggregate to a word per GROUP of 32 tiles (count in bits 56..61, sum below), and the last tile of a group publishes the
+// group's inclusive prefix: a look-back reads the <= 63 nearest tiles one by one and everything before them as groups,
+// 32 groups (1024 tiles) per round, all loads in flight together.
+constexpr unsigned long long kGroupOne = 1ull << 56;
+constexpr unsigned long long kGroupSumMask = kGroupOne - 1ull;
+__device__ __forceinline__ uint64_t lookback_groups(unsigned long long *status, const unsigned long long *gsum, const unsigned long long *gpre,
+                                                    int64_t tile, int lane) {
+  unsigned long long *err_flags = status - 1;  // scratch[1]
+  if (tile <= 0) return 0;
+  const int64_t g = tile >> 5;
+  const int64_t lo = g >= 1 ? 32 * (g - 1) : 0;  // tiles [lo, tile) are read one by one
+  const int64_t idx0 = tile - 1 - lane, idx1 = tile - 33 - lane;
+  const bool in0 = idx0 >= lo, in1 = idx1 >= lo;
+  int64_t hbase = g - 2;                         // groups hbase, hbase - 1, ... : one per lane
+  uint64_t st0 = 0, st1 = 0, ga = 0, gb = 0;
+  uint64_t prefix = 0;
+  unsigned long long t0 = 0;
+  auto give_up = [&]() -> bool {  // warp-uniform: true when the wait limit has passed (flagged; the host discards the outputs)
+    __nanosleep(200);
+    const unsigned long long now = global_ns();
+    if (t0 == 0) t0 = now;
+    if (__any_sync(0xffffffffu, now - t0 > g_lookback_limit_ns)) {
+      if (lane == 0) atomicOr(err_flags, (unsigned long long)kErrTimeout);
+      return true;
+    }
+    return false;
+  };
+  {
+    const int64_t h = hbase - lane;
+    if (h >= 0) { ga = ld_status(gpre + h); gb = ld_status(gsum + h); }
+  }
+  // ---- the nearest tiles
+  {
+    uint64_t v;
+    int state;  // 0: no prefix among them  1: a prefix closed the sum  2: a needed word is not published yet
+    while (true) {
+      if (in0 && (st0 >> 62) == 0) st0 = ld_status(status + idx0);
+      if (in1 && (st1 >> 62) == 0) st1 = ld_status(status + idx1);
+      v = 0;
+      state = 0;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint64_t st = j ? st1 : st0;
+        const bool in = j ? in1 : in0;
+        if (state == 0) {
+          const uint32_t ready = __ballot_sync(0xffffffffu, !in || (st >> 62) != 0);
+          const uint32_t is_p = __ballot_sync(0xffffffffu, in && (st >> 62) == 2);
+          const int first_p = is_p ? (__ffs(is_p) - 1) : 31;
+          const uint32_t need = first_p >= 31 ? 0xffffffffu : ((2u << first_p) - 1u);
+          if ((ready & need) != need) state = 2;
+          else {
+            if (in && lane <= first_p) v += st & kValueMask;
+            if (is_p) state = 1;
+          }
+        }
+      }
+      if (state != 2) break;
+      if (give_up()) { state = 1; break; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    prefix = v;
+    if (state == 1) return prefix;
+  }
+  // ---- the groups before them
+  while (true) {
+    const int64_t h = hbase - lane;
+    uint32_t is_p;
+    int first_p;
+    while (true) {
+      const bool pa = h < 0 || (ga >> 62) == 2;                    // the inclusive prefix through group h is out (before group 0: 0)
+      const bool cb = h >= 0 && ((gb >> 56) & 63ull) == 32ull;     // all 32 aggregates of group h are in its sum
+      is_p = __ballot_sync(0xffffffffu, pa);
+      first_p = is_p ? (__ffs(is_p) - 1) : 32;
+      const uint32_t need = first_p >= 32 ? 0xffffffffu : ((1u << first_p) - 1u);
+      const uint32_t compl_ = __ballot_sync(0xffffffffu, cb);
+      if ((compl_ & need) == need) break;
+      if (give_up()) return prefix;
+      if (h >= 0 && !pa && !cb) { ga = ld_status(gpre + h); gb = ld_status(gsum + h); }
+    }
+    uint64_t v = lane < first_p ? (gb & kGroupSumMask) : ((lane == first_p && h >= 0) ? (ga & kValueMask) : 0ull);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    prefix += v;
+    if (is_p) return prefix;
+    hbase -= 32;
+    ga = gb = 0;
+    const int64_t h2 = hbase - lane;
+    if (h2 >= 0) { ga = ld_status(gpre + h2); gb = ld_status(gsum + h2); }
+  }
+}
+
 // bytes a row contributes: 0 for NULL / past the chunk / an unusable pointer (flagged); P and the
 // workers must agree on this, it defines the tile totals
 template <bool HEAP>
@@ -751,7 +850,7 @@ struct RowState {
   uint32_t my_off;            // tile-local offset of the thread's first row
 };
 
-template <bool LARGE, int R, int NW, bool HEAP>
+template <bool LARGE, int R, int NW, bool HEAP, bool UNIFY = (DMB_PACK_UNIFY != 0)>
 __global__ void __launch_bounds__(NW * 32 + 64, NW == 8 ? (HEAP ? 3 : DMB_NOHEAP_CTAS) : 2)
 string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles,
                    uint32_t ostage_bytes, uint32_t hstage_bytes) {
@@ -879,10 +978,16 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       const uint64_t base = lookback_wide(status, tile, lane, &lb_stats);
       if (lane == 0 && blockIdx.x < 32 && k < 64) g_str_trace[((blockIdx.x * 64 + k) << 4) + 9] = lb_stats;
 #else
+#if DMB_PACK_GROUPS
+      const uint64_t base = lookback_groups(status, status + ntiles, status + ntiles + ((ntiles + 31) >> 5), tile, lane);
+#else
       const uint64_t base = lookback_wide(status, tile, lane);
+#endif
 #endif
       if (lane == 0) {
         if (tile > 0) atomicExch(status + tile, kFlagPrefix | ((base + m.total) & kValueMask));
+        // the last tile of a group of 32 also publishes the group's inclusive prefix, in an array of its own (32 groups = 256 bytes)
+        if (DMB_PACK_GROUPS && (tile & 31) == 31) atomicExch(status + ntiles + ((ntiles + 31) >> 5) + (tile >> 5), kFlagPrefix | ((base + m.total) & kValueMask));
         pt.base[k & (kMetaRing - 1)] = base;
         DMB_PTRACE(k, 15);
       }
@@ -1018,6 +1123,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         // iteration earlier, made the look-backs behind it a little shorter but cost 3 % of the kernel: every row was read twice)
         m.total = total;
         atomicExch(status + m.tile, (m.tile == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)total);
+        if (DMB_PACK_GROUPS) atomicAdd(status + ntiles + (m.tile >> 5), kGroupOne | (unsigned long long)total);  // (no return value: a reduction at L2)
         if (HEAP && staged && hbytes) {
           const uint32_t mb = smem_u32(&pt.mbar_h[slot]);
           mbar_expect_tx(mb, hbytes);
@@ -1132,7 +1238,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         uint32_t wp = pos >> 2, fill = pos & 3u, acc = 0u;
         const uint32_t head = fill;                          // bytes of the first word that belong to earlier threads
         const uint32_t shared_wp = fill ? wp : 0xffffffffu;  // a first word that earlier threads also write
-#if DMB_PACK_UNIFY
+        if constexpr (UNIFY) {
         // One code path for every row: an inlined row first drops its 12 payload bytes into the thread's own 12-byte slot of a
         // scratch area behind H (3-word stride: conflict free) and is then copied like a pointer row whose bytes start there.
         // (As two paths, a warp paid for both at every row slot as soon as one lane differed from the others.)
@@ -1195,7 +1301,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
           wp += nw;
           fill = n & 3u;
         }
-#else
+        } else {
 #pragma unroll
         for (int k = 0; k < R; ++k) {
           const uint32_t l = cur.len[k];
@@ -1292,7 +1398,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
           wp += nw;
           fill = n & 3u;
         }
-#endif
+        }
         if (fill) store_bytes(ow + wp, acc, wp == shared_wp ? head : 0u, fill);  // last word: the next thread owns its other bytes
         fence_proxy_async_smem();
         }
@@ -1789,8 +1895,10 @@ extern "C" int32_t dmb_dev_set_lookback_limit_ns(unsigned long long ns) {
   return check_cuda(cudaMemcpyToSymbol(g_lookback_limit_ns, &ns, sizeof(ns)), "set look-back limit");
 }
 
+// [0] ticket  [1] error flags  [2, 2 + ntiles) tile status  then, for the pack kernel, one sum word and one prefix word per group of 32 tiles
 extern "C" size_t dmb_dev_string_scratch_bytes(int64_t nchunks) {
-  return (size_t)(2 + kStrTilesPerChunk * (nchunks > 0 ? nchunks : 0)) * sizeof(unsigned long long);
+  const int64_t nt = (int64_t)kStrTilesPerChunk * (nchunks > 0 ? nchunks : 0);
+  return (size_t)(2 + nt + 2 * ((nt + 31) / 32)) * sizeof(unsigned long long);
 }
 
 extern "C" int32_t dmb_dev_enum_utf8(const dmb_enum_job *ejob, const dmb_string_job *job, const uint32_t *counts,
@@ -1848,9 +1956,9 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
   if (!no_pack && (job->mode == DMB_STR_ARROW_UTF8 || job->mode == DMB_STR_ARROW_LARGE) && job->heap_len < (1ull << 35)) {
     const bool large = job->mode == DMB_STR_ARROW_LARGE;
     // persistent grid: as many CTAs as are resident at once (tiles are claimed from a ticket)
-    auto launch_pack = [&](auto kernel, int rows_per_tile, int threads, uint32_t ob, uint32_t hb) -> int32_t {
+    auto launch_pack = [&](auto kernel, int rows_per_tile, int threads, uint32_t ob, uint32_t hb, bool unify = (DMB_PACK_UNIFY != 0)) -> int32_t {
       const int64_t nt = (int64_t)(kVec / rows_per_tile) * nchunks;
-      const size_t smem = (size_t)kPackTail + 2u * (size_t)rows_per_tile * 16u + ob + 2u * ((size_t)hb + 16u) + (size_t)(threads - 64) * kPackScratchPerThread + 128u;
+      const size_t smem = (size_t)kPackTail + 2u * (size_t)rows_per_tile * 16u + ob + 2u * ((size_t)hb + 16u) + (unify ? (size_t)(threads - 64) * kPackScratchPerThread : 0u) + 128u;
       if (check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "string_pack_kernel smem attribute")) return -1;
       int per_sm = 0;
       if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem), "string_pack_kernel occupancy")) return -1;
@@ -1889,7 +1997,10 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
     // Largest heap stage of a 512-row tile that still leaves three CTAs per SM (228 KiB of shared memory, 1 KiB
     // reserved per CTA; smem = tail + S[2] + O (= hb + 2048) + H[2]).  Measured on the C3 shape (30.8 heap bytes per
     // row): three CTAs 0.98 ms, two CTAs 1.21 ms, the run-gather kernel 1.17 ms per 50 M rows.
-    constexpr uint32_t kHb3 = ((233472u / 3u - 1024u - kPackTail - 2u * 512u * 16u - 2048u - 32u - 128u - 256u * kPackScratchPerThread) / 3u) & ~127u;
+    // kHb3u: the same with the unified kernel's scratch area (12 bytes per worker thread); columns whose stage would have to
+    // shrink for it (C3: 30.8 heap bytes per row) keep the two-path kernel and the larger stage
+    constexpr uint32_t kHb3 = ((233472u / 3u - 1024u - kPackTail - 2u * 512u * 16u - 2048u - 32u - 128u) / 3u) & ~127u;
+    constexpr uint32_t kHb3u = ((233472u / 3u - 1024u - kPackTail - 2u * 512u * 16u - 2048u - 32u - 128u - 256u * kPackScratchPerThread) / 3u) & ~127u;
     static const double min_slack = getenv("DMB_STR_PACK_MIN_SLACK") ? atof(getenv("DMB_STR_PACK_MIN_SLACK")) : 1.04;
     static const double hpr_limit = getenv("DMB_STR_PACK_HPR_LIMIT") ? atof(getenv("DMB_STR_PACK_HPR_LIMIT")) : ((double)kHb3 - 1024.0 - 128.0) / (512.0 * min_slack);
     if (heap_per_row <= hpr_limit) {
@@ -1914,7 +2025,10 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
                      : launch_pack(string_pack_kernel<false, 4, 8, true>, 1024, 8 * 32 + 64, ob4, hb4);
       }
       if (wide) return large ? launch_pack(string_pack_kernel<true, 2, 16, true>, 1024, 16 * 32 + 64, ob, hb) : launch_pack(string_pack_kernel<false, 2, 16, true>, 1024, 16 * 32 + 64, ob, hb);
-      return large ? launch_pack(string_pack_kernel<true, 2, 8, true>, 512, 8 * 32 + 64, ob, hb) : launch_pack(string_pack_kernel<false, 2, 8, true>, 512, 8 * 32 + 64, ob, hb);
+      static const int force_unify = getenv("DMB_STR_PACK_UNIFY") ? atoi(getenv("DMB_STR_PACK_UNIFY")) : -1;
+      const bool unify = force_unify >= 0 ? force_unify != 0 : (DMB_PACK_UNIFY != 0 && hb <= kHb3u);
+      if (!unify) return large ? launch_pack(string_pack_kernel<true, 2, 8, true, false>, 512, 8 * 32 + 64, ob, hb, false) : launch_pack(string_pack_kernel<false, 2, 8, true, false>, 512, 8 * 32 + 64, ob, hb, false);
+      return large ? launch_pack(string_pack_kernel<true, 2, 8, true, true>, 512, 8 * 32 + 64, ob, hb, true) : launch_pack(string_pack_kernel<false, 2, 8, true, true>, 512, 8 * 32 + 64, ob, hb, true);
     }
   }
   if (job->heap_len == 0 && !getenv("DMB_STR_NO_INLINE_KERNEL")) {  // no heap: inlined strings only, whole-vector tiles

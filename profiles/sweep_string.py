@@ -49,10 +49,13 @@ def main():
             e.record()
             torch.cuda.synchronize()
             ms.append(s.elapsed_time(e))
+        raw = [round(x, 3) for x in ms]
         ms.sort()
         alg = db.alg_bytes_string + (4 * (args.rows + 1) if large else 0)
         out = {"lib": os.path.basename(os.environ.get("DMB_LIB_PATH", "default")), "shape": name, "rows": args.rows,
                "ms_min": round(ms[0], 4), "ms_med": round(ms[len(ms) // 2], 4)}
+        if os.environ.get("SWEEP_RAW"):
+            out["ms_all"] = raw
         if alg:
             out["gb_per_s"] = round(alg / ms[len(ms) // 2] / 1e6, 1)
             out["frac"] = round(alg / ms[len(ms) // 2] / 1e6 / args.peak, 4)
