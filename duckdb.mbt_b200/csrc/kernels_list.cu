@@ -147,6 +147,10 @@ __device__ __forceinline__ typename RawVec<W>::type load_elem(const uint8_t *src
 // low 62 bits the value.  The grid is persistent and no larger than what is resident at once, CTA b takes chunks b,
 // b + grid, ...: every predecessor a look-back waits for belongs to a resident CTA that waits only on earlier chunks.
 constexpr unsigned long long kStatusMask = (1ull << 62) - 1ull;
+#ifndef DMB_LIST_GROUPS
+#define DMB_LIST_GROUPS 0  // the two-level look-back of the string kernels: built and measured, 0.266 vs 0.255 ms per 20 M rows here (the
+                           // chunk-by-chunk walk is not what bounds this kernel, the extra atomic per chunk shows), so it stays off
+#endif
 __device__ __forceinline__ unsigned long long list_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 // exclusive prefix of chunk c, executed by one warp (lane 0 looks at c-1, lane 1 at c-2, ...)
@@ -251,8 +255,20 @@ list_emit_kernel(dmb_list_job job, BatchView b, unsigned long long *chunk_sum /*
     if (ONEPASS) {
       csum = total;
       if (threadIdx.x < 32) {  // warp 0: publish the aggregate, resolve the base, publish the inclusive prefix
+#if DMB_LIST_GROUPS
+        // two-level look-back (dmb_common.cuh): per-chunk words for the <= 63 nearest chunks, per-group (32 chunks) sums and
+        // prefixes before them -- one L2 round trip where the 32-wide chunk-by-chunk walk needed one per 32 chunks
+        unsigned long long *gsum = chunk_sum + 2 * b.nchunks, *gpre = gsum + ((b.nchunks + 31) >> 5);
+        if (lane == 0) {
+          if (c > 0) atomicExch(chunk_sum + c, (1ull << 62) | (csum & kStatusMask));
+          atomicAdd(gsum + (c >> 5), kGroupOne | (csum & kGroupSumMask));
+        }
+        const uint64_t base = c > 0 ? lookback_groups(chunk_sum, gsum, gpre, c, lane, flags, 4ull, 2000000000ull) : 0ull;
+        if (lane == 0 && (c & 31) == 31) atomicExch(gpre + (c >> 5), (2ull << 62) | ((base + csum) & kStatusMask));
+#else
         if (lane == 0 && c > 0) atomicExch(chunk_sum + c, (1ull << 62) | (csum & kStatusMask));
         const uint64_t base = c > 0 ? list_lookback(chunk_sum, c, lane, flags) : 0ull;
+#endif
         if (lane == 0) {
           atomicExch(chunk_sum + c, (2ull << 62) | ((base + csum) & kStatusMask));
           s_cbase = base;
@@ -460,12 +476,14 @@ list_emit_kernel(dmb_list_job job, BatchView b, unsigned long long *chunk_sum /*
 using namespace dmb;
 
 extern "C" size_t dmb_dev_list_scratch_bytes(int64_t nchunks) {
-  return (size_t)(2 * (nchunks > 0 ? nchunks : 0) + 2) * sizeof(unsigned long long);
+  const int64_t n = nchunks > 0 ? nchunks : 0;
+  return (size_t)(2 * n + 2 + 2 * ((n + 31) / 32)) * sizeof(unsigned long long);
 }
 
 // scratch: [0] error flags (1: int32 offsets overflow, 2: a chunk with > 4 G child elements, 4: a look-back gave up
 // waiting, 8: a list entry reaches outside its chunk's child vector), [1] unused,
-// then chunk_sum[nchunks], chunk_base[nchunks].  out_child_validity must hold ceil(total / 64) + 1 words.
+// then chunk_sum[nchunks], chunk_base[nchunks], and a sum word + a prefix word per group of 32 chunks (the one-pass kernel's
+// two-level look-back).  out_child_validity must hold ceil(total / 64) + 1 words.
 extern "C" int32_t dmb_dev_list_batch(const dmb_list_job *job, const uint32_t *counts, const int64_t *row_off, int64_t nchunks,
                                       int64_t nrows, int64_t child_capacity, void *scratch, void *stream) {
   if (!job) { set_error("dmb_dev_list_batch: job is null"); return -1; }
@@ -486,7 +504,8 @@ extern "C" int32_t dmb_dev_list_batch(const dmb_list_job *job, const uint32_t *c
   if (three_pass) {
     list_sum_kernel<<<grid, kThreads, 0, st>>>(*job, counts, nchunks, chunk_sum);
     list_scan_kernel<<<1, kScanThreads, 0, st>>>(chunk_sum, chunk_base, nchunks, job->total, flags, job->large & 1);
-  } else if (check_cuda(cudaMemsetAsync(chunk_sum, 0, (size_t)nchunks * 8, st), "list status memset")) {
+  } else if (check_cuda(cudaMemsetAsync(chunk_sum, 0, (size_t)nchunks * 8, st), "list status memset") ||
+             check_cuda(cudaMemsetAsync(chunk_sum + 2 * nchunks, 0, (size_t)(2 * ((nchunks + 31) / 32)) * 8, st), "list group status memset")) {
     return -1;
   }
   auto launch = [&](auto kernel3, auto kernel1) -> int32_t {

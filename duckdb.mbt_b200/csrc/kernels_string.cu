@@ -42,9 +42,6 @@ constexpr int kStrPerThread = kStrTileRows / kThreads;  // 2 consecutive rows pe
 constexpr int kMapVecs = 2048;                          // output vectors per window (32 KiB of utf8 data)
 constexpr uint32_t kMaxRowBytes = 1u << 21;             // tile-local sums stay below 2^32 (<= 2048 rows * 2 MiB)
 
-constexpr uint64_t kFlagAggregate = 1ull << 62;
-constexpr uint64_t kFlagPrefix = 2ull << 62;
-constexpr uint64_t kValueMask = (1ull << 62) - 1ull;
 
 // scratch layout (uint64 words): [0] tile ticket  [1] error flags  [2..] tile status
 enum { kErrTileTooBig = 1, kErrOffsetOverflow = 2, kErrHeapRange = 4, kErrDataCap = 8, kErrTimeout = 16 };
@@ -84,9 +81,6 @@ struct StrSmem {
   long long ticket;
 };
 
-__device__ __forceinline__ uint64_t ld_status(const unsigned long long *p) {
-  return *reinterpret_cast<const volatile unsigned long long *>(p);
-}
 
 // (y:x) >> s bits, s in {0, 8, ..., 56}
 __device__ __forceinline__ uint64_t funnel64(uint64_t x, uint64_t y, uint32_t s) {
@@ -534,7 +528,7 @@ constexpr int kMetaRing = 4;
 #ifndef DMB_PACK_UNROLL
 #define DMB_PACK_UNROLL 2
 #endif
-constexpr int kPackUnroll = DMB_PACK_UNROLL;  // words in flight per thread in the pointer-row copy loop (DMB_PACK_CHUNK=0 only)
+[[maybe_unused]] constexpr int kPackUnroll = DMB_PACK_UNROLL;  // words in flight per thread in the pointer-row copy loop (DMB_PACK_CHUNK=0 only)
 // A/B knobs of the pack kernel (all on by default; profiles/r02_string_pack_kernel_iterations.txt has what each one bought)
 #ifndef DMB_PACK_CHUNK
 #define DMB_PACK_CHUNK 1   // pointer rows are copied four words at a time, loads first
@@ -595,7 +589,6 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 // A wait that cannot end must not hang the GPU.  Look-backs (the only waits on OTHER CTAs) give up after 4 s with an
 // error flag and let the launch finish; the mbarrier waits inside a CTA depend only on that CTA's own warps and copy
 // engine transactions, so one that is still pending after 3x that long is a protocol bug: it traps.
@@ -726,102 +719,6 @@ __device__ __forceinline__ uint64_t lookback_wide(unsigned long long *status, in
   }
   if (stats) *stats = rounds * 1000u + retries;
   return prefix;
-}
-
-// Two-level look-back of the pack kernel.  With ~450 persistent CTAs that claim tiles two iterations ahead, the nearest
-// predecessor whose PREFIX is out is typically 150-300 tiles back; a tile-by-tile look-back of 256 words per round then sits
-// on the edge between one L2 round trip and two, and the launch is bistable (late prefixes make every look-back longer,
-// which makes the prefixes later: 0.82 vs 1.15-1.47 ms per 60 M rows on all-pointer columns).  So tiles also add their
-// aggregate to a word per GROUP of 32 tiles (count in bits 56..61, sum below), and the last tile of a group publishes the
-// group's inclusive prefix: a look-back reads the <= 63 nearest tiles one by one and everything before them as groups,
-// 32 groups (1024 tiles) per round, all loads in flight together.
-constexpr unsigned long long kGroupOne = 1ull << 56;
-constexpr unsigned long long kGroupSumMask = kGroupOne - 1ull;
-__device__ __forceinline__ uint64_t lookback_groups(unsigned long long *status, const unsigned long long *gsum, const unsigned long long *gpre,
-                                                    int64_t tile, int lane) {
-  unsigned long long *err_flags = status - 1;  // scratch[1]
-  if (tile <= 0) return 0;
-  const int64_t g = tile >> 5;
-  const int64_t lo = g >= 1 ? 32 * (g - 1) : 0;  // tiles [lo, tile) are read one by one
-  const int64_t idx0 = tile - 1 - lane, idx1 = tile - 33 - lane;
-  const bool in0 = idx0 >= lo, in1 = idx1 >= lo;
-  int64_t hbase = g - 2;                         // groups hbase, hbase - 1, ... : one per lane
-  uint64_t st0 = 0, st1 = 0, ga = 0, gb = 0;
-  uint64_t prefix = 0;
-  unsigned long long t0 = 0;
-  auto give_up = [&]() -> bool {  // warp-uniform: true when the wait limit has passed (flagged; the host discards the outputs)
-    __nanosleep(200);
-    const unsigned long long now = global_ns();
-    if (t0 == 0) t0 = now;
-    if (__any_sync(0xffffffffu, now - t0 > g_lookback_limit_ns)) {
-      if (lane == 0) atomicOr(err_flags, (unsigned long long)kErrTimeout);
-      return true;
-    }
-    return false;
-  };
-  {
-    const int64_t h = hbase - lane;
-    if (h >= 0) { ga = ld_status(gpre + h); gb = ld_status(gsum + h); }
-  }
-  // ---- the nearest tiles
-  {
-    uint64_t v;
-    int state;  // 0: no prefix among them  1: a prefix closed the sum  2: a needed word is not published yet
-    while (true) {
-      if (in0 && (st0 >> 62) == 0) st0 = ld_status(status + idx0);
-      if (in1 && (st1 >> 62) == 0) st1 = ld_status(status + idx1);
-      v = 0;
-      state = 0;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint64_t st = j ? st1 : st0;
-        const bool in = j ? in1 : in0;
-        if (state == 0) {
-          const uint32_t ready = __ballot_sync(0xffffffffu, !in || (st >> 62) != 0);
-          const uint32_t is_p = __ballot_sync(0xffffffffu, in && (st >> 62) == 2);
-          const int first_p = is_p ? (__ffs(is_p) - 1) : 31;
-          const uint32_t need = first_p >= 31 ? 0xffffffffu : ((2u << first_p) - 1u);
-          if ((ready & need) != need) state = 2;
-          else {
-            if (in && lane <= first_p) v += st & kValueMask;
-            if (is_p) state = 1;
-          }
-        }
-      }
-      if (state != 2) break;
-      if (give_up()) { state = 1; break; }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    prefix = v;
-    if (state == 1) return prefix;
-  }
-  // ---- the groups before them
-  while (true) {
-    const int64_t h = hbase - lane;
-    uint32_t is_p;
-    int first_p;
-    while (true) {
-      const bool pa = h < 0 || (ga >> 62) == 2;                    // the inclusive prefix through group h is out (before group 0: 0)
-      const bool cb = h >= 0 && ((gb >> 56) & 63ull) == 32ull;     // all 32 aggregates of group h are in its sum
-      is_p = __ballot_sync(0xffffffffu, pa);
-      first_p = is_p ? (__ffs(is_p) - 1) : 32;
-      const uint32_t need = first_p >= 32 ? 0xffffffffu : ((1u << first_p) - 1u);
-      const uint32_t compl_ = __ballot_sync(0xffffffffu, cb);
-      if ((compl_ & need) == need) break;
-      if (give_up()) return prefix;
-      if (h >= 0 && !pa && !cb) { ga = ld_status(gpre + h); gb = ld_status(gsum + h); }
-    }
-    uint64_t v = lane < first_p ? (gb & kGroupSumMask) : ((lane == first_p && h >= 0) ? (ga & kValueMask) : 0ull);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    prefix += v;
-    if (is_p) return prefix;
-    hbase -= 32;
-    ga = gb = 0;
-    const int64_t h2 = hbase - lane;
-    if (h2 >= 0) { ga = ld_status(gpre + h2); gb = ld_status(gsum + h2); }
-  }
 }
 
 // bytes a row contributes: 0 for NULL / past the chunk / an unusable pointer (flagged); P and the
@@ -979,7 +876,7 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       if (lane == 0 && blockIdx.x < 32 && k < 64) g_str_trace[((blockIdx.x * 64 + k) << 4) + 9] = lb_stats;
 #else
 #if DMB_PACK_GROUPS
-      const uint64_t base = lookback_groups(status, status + ntiles, status + ntiles + ((ntiles + 31) >> 5), tile, lane);
+      const uint64_t base = lookback_groups(status, status + ntiles, status + ntiles + ((ntiles + 31) >> 5), tile, lane, status - 1, (unsigned long long)kErrTimeout, g_lookback_limit_ns);
 #else
       const uint64_t base = lookback_wide(status, tile, lane);
 #endif
@@ -1625,6 +1522,11 @@ string_inline_kernel(dmb_string_job job, BatchView b, unsigned long long *scratc
 //     bytes in the stage at tile-local positions (byte stores: no zeroing, no read-modify-write)
 //   * the stage leaves as 16-byte vectors aligned to the destination; the shift between tile-local
 //     and destination alignment is a funnel shift on the way out
+#ifndef DMB_SHORT_GROUPS
+#define DMB_SHORT_GROUPS 1  // ENUM form: the two-level look-back of the pack kernel (lookback_groups).  Measured per 60 M rows, groups vs
+                            // 256-wide tile-by-tile rounds: ENUM 0.307 vs 0.331 ms, l_shipmode shape 0.329 vs 0.335, one-byte strings 0.291 vs
+                            // 0.285 (the extra atomic per tile shows): the string_t form keeps the tile-by-tile walk
+#endif
 #ifndef DMB_SHORT_CTAS8
 #define DMB_SHORT_CTAS8 4
 #endif
@@ -1735,14 +1637,17 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   }
   if (tid == 0) {
     atomicExch(status + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)tile_total);
+    if (DMB_SHORT_GROUPS && EW) atomicAdd(status + ntiles + (tile >> 5), kGroupOne | (unsigned long long)tile_total);
     if (any_bad) atomicOr(scratch + 1, (unsigned long long)kErrHeapRange);
   }
 #ifdef DMB_SHORT_LB_FIRST
   // decoupled look-back (warp 0)
   if (warp == 0) {
-    const uint64_t prefix = lookback_wide(status, tile, lane);
+    const uint64_t prefix = (DMB_SHORT_GROUPS && EW) ? lookback_groups(status, status + ntiles, status + ntiles + ((ntiles + 31) >> 5), tile, lane, status - 1, (unsigned long long)kErrTimeout, g_lookback_limit_ns)
+                                             : lookback_wide(status, tile, lane);
     if (lane == 0) {
       if (tile > 0) atomicExch(status + tile, kFlagPrefix | ((prefix + tile_total) & kValueMask));
+      if (DMB_SHORT_GROUPS && EW && (tile & 31) == 31) atomicExch(status + ntiles + ((ntiles + 31) >> 5) + (tile >> 5), kFlagPrefix | ((prefix + tile_total) & kValueMask));
       base_sh = prefix;
     }
   }
@@ -1803,9 +1708,11 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   }
   // decoupled look-back (warp 0)
   if (warp == 0) {
-    const uint64_t prefix = lookback_wide(status, tile, lane);
+    const uint64_t prefix = (DMB_SHORT_GROUPS && EW) ? lookback_groups(status, status + ntiles, status + ntiles + ((ntiles + 31) >> 5), tile, lane, status - 1, (unsigned long long)kErrTimeout, g_lookback_limit_ns)
+                                             : lookback_wide(status, tile, lane);
     if (lane == 0) {
       if (tile > 0) atomicExch(status + tile, kFlagPrefix | ((prefix + tile_total) & kValueMask));
+      if (DMB_SHORT_GROUPS && EW && (tile & 31) == 31) atomicExch(status + ntiles + ((ntiles + 31) >> 5) + (tile >> 5), kFlagPrefix | ((prefix + tile_total) & kValueMask));
       base_sh = prefix;
     }
   }
