@@ -71,7 +71,9 @@ def test_host_side_helpers_without_a_gpu():
     assert L.dmb_op_out_width(ch.op(ch.P_I64, ch.D_TS_REF_FROM_NS)) == 8
     assert L.dmb_op_out_width(ch.op(ch.P_STRING, ch.D_SAME)) == -1
     assert L.dmb_op_out_width(ch.op(ch.P_F64, ch.D_I32_SAT)) == -1
-    assert L.dmb_dev_string_scratch_bytes(10) == (2 + 40) * 8
+    # ticket + error flags + 4 tile status words per chunk + a sum word and a prefix word per group of 32 tiles (two-level look-back)
+    assert L.dmb_dev_string_scratch_bytes(10) == (2 + 40 + 2 * 2) * 8
+    assert L.dmb_dev_list_scratch_bytes(10) == (2 + 2 * 10 + 2 * 1) * 8
     buf = (C.c_uint8 * 16)()
     C.memmove(buf, C.byref(C.c_double(3.14)), 8)
     C.memmove(C.addressof(buf) + 8, C.byref(C.c_double(-2.5)), 8)
