@@ -674,8 +674,11 @@ def run_ours(args, rank, local_rank, world):
     nd = db.nrows
     string_col_alg = {db.batch.columns[so.col].name: 16 * nd + db.meta[so.col]["ptr_len"] + 4 * (nd + 1) + db.meta[so.col]["total_len"]
                       for so in step.strings}
-    # which kernel a VARCHAR column goes to (kernels_string.cu, dmb_dev_string_batch): no heap -> string_short_kernel
-    string_col_kernel = {db.batch.columns[so.col].name: ("string_short_kernel" if db.meta[so.col]["ptr_len"] == 0 else "string_pack_kernel")
+    # which kernel a VARCHAR column goes to (kernels_string.cu, dmb_dev_string_batch): the persistent TMA pipeline
+    # string_pack_kernel; columns without a heap take its lean form (template argument HEAP = false), reported as a family
+    # of its own -- or the one-CTA-per-tile string_short_kernel when DMB_STR_SHORT_RPT selects it (A/B knob)
+    noheap_kernel = "string_short_kernel" if int(os.environ.get("DMB_STR_SHORT_RPT", "0") or 0) > 0 else "string_pack_kernel<no heap>"
+    string_col_kernel = {db.batch.columns[so.col].name: (noheap_kernel if db.meta[so.col]["ptr_len"] == 0 else "string_pack_kernel")
                          for so in step.strings}
     string_totals = [float(db.meta[so.col]["total_len"]) for so in step.strings]
     dev_ms_max = max_over_ranks(dev_ms)

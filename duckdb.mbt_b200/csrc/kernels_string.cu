@@ -536,9 +536,6 @@ constexpr int kMetaRing = 4;
 #ifndef DMB_PACK_SROT
 #define DMB_PACK_SROT 1    // string_t are read from S in a lane-rotated order (no bank conflicts), rotated back in registers
 #endif
-#ifndef DMB_PACK_WSUM4
-#define DMB_PACK_WSUM4 0   // the eight warp sums are read as two 16-byte vectors (needs PackPartials aligned to 16: that layout made ptxas spill)
-#endif
 #ifndef DMB_PACK_SEL
 #define DMB_PACK_SEL 1     // the inlined rows' last-word select as two bit tests
 #endif
@@ -563,7 +560,7 @@ struct TileMeta {
 };
 
 constexpr int kPackMaxWarps = 16;
-struct alignas(DMB_PACK_WSUM4 ? 16 : 4) PackPartials {
+struct PackPartials {
   uint32_t warp_sum[kPackMaxWarps];
   uint32_t warp_hmin[kPackMaxWarps];
   uint32_t warp_hmax[kPackMaxWarps];
@@ -894,6 +891,124 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
     return;
   }
 
+  // -------------------------------------------------------------- W, columns without a heap: the lean form
+  // Every string is inlined (<= 12 bytes, a pointer entry is an error), so the workers need none of the span / run / funnel
+  // machinery below.  Rows are owned STRIPED (stripe k of warp w = tile rows w*32*R + 32*k + lane): the string_t leave S
+  // with conflict-free 16-byte loads, two stripes' lengths share one 32-bit scan (a stripe sums to <= 384 < 2^16), offsets
+  // leave as coalesced 4-byte stores, and the bytes are placed one by one straight at their FINAL alignment in the stage (the
+  // base is known by then), which P sends out with bulk stores: no copy-out pass.  Same roles, barriers and look-back as
+  // the general form.  (The one-CTA-per-tile string_short_kernel does the same work in ~2 warp-instructions per row but sits
+  // on its dependent chain: ticket -> metadata -> string_t -> scan -> look-back -> stores; here P and L hide that chain.)
+  if constexpr (!HEAP) {
+    uint32_t c_len[R], c_y[R], c_z[R], c_w[R], c_off[R], c_lmax = 0u;
+    bool cur_valid = false;
+    const int row0 = warp * (32 * R) + lane;
+    for (int j = 0;; ++j) {
+      if (j > 0 && !cur_valid) break;
+      const int slot = j & 1;
+      mbar_wait(smem_u32(&pt.mbar_s[slot]), (uint32_t)(j >> 1) & 1u);
+      TileMeta &mj = pt.meta[j & (kMetaRing - 1)];
+      const bool nxt_valid = mj.tile >= 0;
+      uint32_t n_len[R], n_y[R], n_z[R], n_w[R], n_off[R], n_lmax = 0u;
+      if (nxt_valid) {
+        const int nrows = mj.nrows;
+        const bool has_mask = mj.has_mask != 0;
+        const uint4 *s = reinterpret_cast<const uint4 *>(sbuf + (uint32_t)slot * kSBytes);
+        int bad = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const int row = row0 + 32 * k;
+          const uint4 e = s[row];
+          bool live = row < nrows;
+          if (has_mask) live = live && ((pt.vmask[slot][row >> 6] >> (row & 63)) & 1ull);
+          uint32_t l = live ? e.x : 0u;
+          if (l > 12u) { bad = 1; l = 0u; }  // a pointer string, but the column registered no heap
+          n_len[k] = l; n_y[k] = e.y; n_z[k] = e.z; n_w[k] = e.w;
+          n_lmax = n_lmax > l ? n_lmax : l;
+        }
+        uint32_t carry = 0u;
+#pragma unroll
+        for (int k = 0; k < R; k += 2) {
+          const uint32_t both = n_len[k] | (n_len[k + 1] << 16);
+          uint32_t incl = both;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+          }
+          const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+          const uint32_t excl = incl - both;
+          n_off[k] = carry + (excl & 0xffffu);
+          carry += tot & 0xffffu;
+          n_off[k + 1] = carry + (excl >> 16);
+          carry += tot >> 16;
+        }
+        PackPartials &pp = pt.part[slot];
+        if (lane == 0) pp.warp_sum[warp] = carry;
+        if (bad) atomicOr(scratch + 1, (unsigned long long)kErrHeapRange);
+        n_lmax = __reduce_max_sync(0xffffffffu, n_lmax);
+        bar_sync(kBarWorkers, kWT);
+        uint32_t warp_excl = 0u;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) warp_excl += w < warp ? pp.warp_sum[w] : 0u;
+#pragma unroll
+        for (int k = 0; k < R; ++k) n_off[k] += warp_excl;
+        if (tid == 0) {
+          uint32_t total = 0u;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) total += pp.warp_sum[w];
+          mj.total = total;
+          mj.hmin = 0u;
+          mj.hbytes = 0u;
+          mj.staged = 1;
+          atomicExch(status + mj.tile, (mj.tile == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)total);
+          if (DMB_PACK_GROUPS) atomicAdd(status + ntiles + (mj.tile >> 5), kGroupOne | (unsigned long long)total);
+        }
+      }
+      if (warp == 0) {  // L: tile j's look-back is due (or: there is no tile j)
+        __syncwarp();
+        bar_arrive(kBarF0 + (j & 1), 64);
+      }
+      // ---- back(tile j-1)
+      uint64_t base = 0;
+      if (cur_valid) {
+        bar_sync(kBarB0 + ((j - 1) & 1), kWT + 32);  // L has resolved tile j-1
+        base = pt.base[(j - 1) & (kMetaRing - 1)];
+        const TileMeta &mc = pt.meta[(j - 1) & (kMetaRing - 1)];
+        const int nrows = mc.nrows;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const int row = row0 + 32 * k;
+          if (row < nrows) {
+            if (LARGE) __stcs(reinterpret_cast<long long *>(job.out_offsets) + mc.out_row0 + row, (long long)(base + c_off[k]));
+            else __stcs(reinterpret_cast<int32_t *>(job.out_offsets) + mc.out_row0 + row, (int32_t)((uint32_t)base + c_off[k]));
+          }
+        }
+      }
+      bar_sync(kBarBase, kWL);  // the stage is free (P has sent tile j-2)
+      if (cur_valid) {
+        const uint32_t mis = (uint32_t)(base & 15ull);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          if ((uint32_t)i < c_lmax) {  // warp-uniform: no issue slots for bytes past the warp's longest string
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+              const uint32_t wsel = i < 4 ? c_y[k] : (i < 8 ? c_z[k] : c_w[k]);
+              if ((uint32_t)i < c_len[k]) ostage[mis + c_off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
+            }
+          }
+        }
+        fence_proxy_async_smem();
+      }
+      bar_arrive(kBarPacked, kWL);
+#pragma unroll
+      for (int k = 0; k < R; ++k) { c_len[k] = n_len[k]; c_y[k] = n_y[k]; c_z[k] = n_z[k]; c_w[k] = n_w[k]; c_off[k] = n_off[k]; }
+      c_lmax = n_lmax;
+      cur_valid = nxt_valid;
+    }
+    return;
+  }
+
   // -------------------------------------------------------------- W: scan (front) and pack (back)
   RowState<R> cur, nxt;
   bool cur_valid = false;
@@ -964,15 +1079,8 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       if (tid == 0) pp.not_one_run = 0u;
       bar_sync(kBarWorkers, kWT);  // (every warp has also finished packing tile j-2: H[slot] is free)
       uint32_t warp_excl = 0;
-      if (DMB_PACK_WSUM4 && NW == 8) {
-        const uint4 s0 = *reinterpret_cast<const uint4 *>(&pp.warp_sum[0]), s1 = *reinterpret_cast<const uint4 *>(&pp.warp_sum[4]);
-        const uint32_t ws[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-        for (int w = 0; w < 7; ++w) warp_excl += w < warp ? ws[w] : 0u;
-      } else {
-#pragma unroll
-        for (int w = 0; w < NW; ++w) warp_excl += w < warp ? pp.warp_sum[w] : 0u;
-      }
+      for (int w = 0; w < NW; ++w) warp_excl += w < warp ? pp.warp_sum[w] : 0u;
       nxt.my_off = warp_excl + incl - tsum;
       if (HEAP) {
         // is the tile one run?  (every non-empty row a pointer row whose bytes follow its predecessor's in the heap)
@@ -1270,18 +1378,6 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
               acc = (n & 3u) ? (__funnelshift_r(prev, sp[0], sq) & low_bytes3(n & 3u)) : 0u;
             }
 #else
-#ifdef DMB_EXP_NOCONFLICT  // (timing experiment, wrong bytes: the same loop on conflict-free addresses)
-            s = hw + lane; o = ow + lane;
-#pragma unroll kPackUnroll
-            for (uint32_t m = 1; m < nw; ++m) {
-              nx = s[32u * m];
-              o[32u * m] = __funnelshift_r(prev, nx, sq);
-              prev = nx;
-            }
-            acc = (n & 3u) ? (__funnelshift_r(prev, s[32u * nw], sq) & low_bytes3(n & 3u)) : 0u;
-#elif defined(DMB_EXP_NOCOPY)  // (timing experiment, wrong bytes: no interior words)
-            acc = (n & 3u) ? (__funnelshift_r(prev, s[nw], sq) & low_bytes3(n & 3u)) : 0u;
-#else
 #pragma unroll kPackUnroll
             for (uint32_t m = 1; m < nw; ++m) {
               nx = s[m];
@@ -1289,7 +1385,6 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
               prev = nx;
             }
             acc = (n & 3u) ? (__funnelshift_r(prev, s[nw], sq) & low_bytes3(n & 3u)) : 0u;
-#endif
 #endif
           }
           wp += nw;
@@ -1539,12 +1634,13 @@ template <> struct EnumIndex<4> { typedef uint32_t type; };
 
 // ECTAS: CTAs per SM of the ENUM form, whose rows keep an index + a length in registers instead of a string_t
 // (6: 40 registers + 56 bytes of spills; 5: 48 registers; runtime choice DMB_ENUM_CTAS for A/B)
-template <bool LARGE, int RPT, int EW, int ECTAS = 6>
-__global__ void __launch_bounds__(kThreads, EW ? ECTAS : (RPT >= 8 ? DMB_SHORT_CTAS8 : 5))
+// NT: threads per CTA (256; 128 / 512 are measured variants: DMB_STR_SHORT_NT)
+template <bool LARGE, int RPT, int EW, int ECTAS = 6, int NT = kThreads>
+__global__ void __launch_bounds__(NT, EW ? ECTAS : (NT == 128 ? 8 : (NT == 512 ? 2 : (RPT >= 8 ? DMB_SHORT_CTAS8 : 5))))
 string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles, dmb_enum_job ej) {
-  constexpr int kRows = kThreads * RPT;
+  constexpr int kRows = NT * RPT;
   constexpr int kTilesPerChunk = kVec / kRows;
-  constexpr int kWarps = kThreads / 32;
+  constexpr int kWarps = NT / 32;
   __shared__ __align__(16) uint8_t stage[kRows * 12 + 32];
   __shared__ uint32_t warp_sum[kWarps];
   __shared__ uint64_t base_sh;
@@ -1578,7 +1674,7 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
     }
   }
   if (EW) {  // the labels as string_t, once per CTA (the index loads above are in flight meanwhile)
-    for (uint32_t t = tid; t < ej.dict_size; t += kThreads) s_tab[t] = enum_entry(ej, t);
+    for (uint32_t t = tid; t < ej.dict_size; t += NT) s_tab[t] = enum_entry(ej, t);
     __syncthreads();
   }
   int bad = 0;
@@ -1747,7 +1843,7 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   const uint32_t end = mis + tile_total;
   const uint32_t nvec = (end + 15u) >> 4;
   const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage);
-  for (uint32_t v = tid; v < nvec; v += kThreads) {
+  for (uint32_t v = tid; v < nvec; v += NT) {
     const uint32_t p = 16u * v;
     if (p >= mis && p + 16u <= end) {
       const uint32_t q = p - mis, sh = 8u * (q & 3u);
@@ -1880,18 +1976,24 @@ extern "C" int32_t dmb_dev_string_batch(const dmb_string_job *job, const uint32_
       return check_cuda(cudaGetLastError(), "string_pack_kernel launch");
     };
     static const int force_nw = getenv("DMB_STR_PACK_NW") ? atoi(getenv("DMB_STR_PACK_NW")) : 0;
-    static const int short_rpt = getenv("DMB_STR_SHORT_RPT") ? atoi(getenv("DMB_STR_SHORT_RPT")) : 8;
+    // columns without a heap: the pipeline's lean form on whole-vector tiles (16 worker warps x 4 rows) by default --
+    // 0.270 / 0.313 ms per 60 M one-byte / l_shipmode-shaped rows, against 0.287 / 0.334 for the one-CTA-per-tile
+    // string_short_kernel (DMB_STR_SHORT_RPT=8 or 4 selects that one for A/B) and 0.297 / 0.336 for 8 worker warps
+    static const int short_rpt = getenv("DMB_STR_SHORT_RPT") ? atoi(getenv("DMB_STR_SHORT_RPT")) : 0;
     if (job->heap_len == 0 && short_rpt > 0) {  // inlined strings only: one CTA per tile, prefix by look-back
-      auto launch_short = [&](auto kernel, int rows_per_tile) -> int32_t {
+      auto launch_short = [&](auto kernel, int rows_per_tile, int threads = kThreads) -> int32_t {
         const int64_t nt = (int64_t)(kVec / rows_per_tile) * nchunks;
-        kernel<<<(unsigned)nt, kThreads, 0, st>>>(*job, b, (unsigned long long *)scratch, nt, dmb_enum_job{});
+        kernel<<<(unsigned)nt, threads, 0, st>>>(*job, b, (unsigned long long *)scratch, nt, dmb_enum_job{});
         return check_cuda(cudaGetLastError(), "string_short_kernel launch");
       };
+      static const int short_nt = getenv("DMB_STR_SHORT_NT") ? atoi(getenv("DMB_STR_SHORT_NT")) : 0;  // (measured variants)
+      if (short_nt == 128) return large ? launch_short(string_short_kernel<true, 8, 0, 6, 128>, 1024, 128) : launch_short(string_short_kernel<false, 8, 0, 6, 128>, 1024, 128);
+      if (short_nt == 512) return large ? launch_short(string_short_kernel<true, 4, 0, 6, 512>, 2048, 512) : launch_short(string_short_kernel<false, 4, 0, 6, 512>, 2048, 512);
       if (short_rpt == 4) return large ? launch_short(string_short_kernel<true, 4, 0>, 1024) : launch_short(string_short_kernel<false, 4, 0>, 1024);
       return large ? launch_short(string_short_kernel<true, 8, 0>, 2048) : launch_short(string_short_kernel<false, 8, 0>, 2048);
     }
-    if (job->heap_len == 0) {  // (experiment: DMB_STR_SHORT_RPT=0) the pipeline below with 4 rows per thread
-      if (force_nw != 16) {
+    if (job->heap_len == 0) {  // the pipeline's lean form, 4 rows per thread
+      if (force_nw == 8) {
         const uint32_t ob = ((1024u * 12u + 64u) + 127u) & ~127u;
         return large ? launch_pack(string_pack_kernel<true, 4, 8, false>, 1024, 8 * 32 + 64, ob, 0u) : launch_pack(string_pack_kernel<false, 4, 8, false>, 1024, 8 * 32 + 64, ob, 0u);
       }

@@ -1,7 +1,7 @@
 """profiles/traffic.json (read by bench.py: roofline.traffic) from --set full captures of the kernel launches of one
 bench step: mean dram__bytes_read.sum + dram__bytes_write.sum per launch, per kernel family.
 usage: python profiles/make_traffic.py <out.txt> <rep> [<rep> ...]      (reports from profiles/run_bench_ncu.sh)"""
-import csv, json, os, subprocess, sys
+import csv, json, os, re, subprocess, sys
 
 txt, reps = sys.argv[1], sys.argv[2:]
 keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
@@ -22,6 +22,8 @@ with open(txt, 'w') as f:
                     f.write(f"  {k:72s} {r[hdr.index(k)]:>16s} {units[hdr.index(k)]}\n")
             b = sum(float(r[hdr.index(k)]) * mult[units[hdr.index(k)]] for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
             key = name.split('<')[0].replace('void ', '').strip()
+            if key == 'string_pack_kernel' and re.search(r'string_pack_kernel<\d+, \d+, \d+, 0', name):
+                key = 'string_pack_kernel<no heap>'  # the lean form for columns without a heap: a family of its own in bench.py
             fam.setdefault(key, []).append(b)
 out = {"rows": 60000000,
        "source": "ncu --set full --clock-control none -k regex:<family> python bench.py --steps 2 --warmup 1 --no-cpu (" + os.path.basename(txt) +

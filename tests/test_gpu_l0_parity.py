@@ -220,6 +220,22 @@ def test_string_few_heap_bytes_per_row(n, pattern):
     _check_string(dev, _bulk(n, lambda r, m: choices[r.integers(0, choices.shape[0], m)], 0.1, pattern, 13))
 
 
+@pytest.mark.parametrize("tiles", [31, 32, 33, 63, 64, 65, 96, 1025])
+@pytest.mark.parametrize("rows_per_tile,lens", [(512, (10, 44)), (1024, None)])
+def test_string_pack_lookback_group_boundaries(tiles, rows_per_tile, lens):
+    """The pack kernel's two-level look-back reads the <= 63 nearest tiles one by one and everything before them as groups
+    of 32 tiles (sum word + prefix word per group): tile counts on both sides of every boundary of that scheme, for the
+    512-row-tile kernel (l_comment shape) and the 1024-row-tile kernel (l_shipinstruct shape), int32 and int64 offsets."""
+    dev = _device_mod()
+    n = rows_per_tile * (tiles - 1) + 7  # the last tile is ragged
+    if lens is None:
+        choices = np.asarray([17, 11, 4, 16])
+        gen = lambda r, m: choices[r.integers(0, 4, m)]  # noqa: E731
+    else:
+        gen = lambda r, m: r.integers(lens[0], lens[1], m)  # noqa: E731
+    _check_string(dev, _bulk(n, gen, 0.05, "full", 500 + tiles), modes=(0, 1))
+
+
 def test_string_tiles_that_do_not_fit_the_stages():
     # short strings on average (the pack kernel is chosen), but some tiles hold long strings or point all over
     # the heap: those tiles take the row-by-row path inside the same launch
