@@ -521,9 +521,9 @@ constexpr int kLookWide = 8;          // status words in flight per lane in the 
 #define DMB_LOOK_FIRST 8
 #endif
 constexpr int kLookFirst = DMB_LOOK_FIRST;  // ... in its first round
-constexpr int kMetaRing = 4;
+constexpr int kMetaRing = 8;  // tiles j-1 (being sent) .. j+3 (ticket and metadata claimed) are alive at once
 #ifndef DMB_NOHEAP_CTAS
-#define DMB_NOHEAP_CTAS 4
+#define DMB_NOHEAP_CTAS 3  // 8-worker-warp form of the heap-less pipeline (DMB_STR_PACK_NW=8): 3 CTAs/SM = 64 registers, no spills (4: 48 + spills, slower)
 #endif
 #ifndef DMB_PACK_UNROLL
 #define DMB_PACK_UNROLL 2
@@ -557,6 +557,9 @@ struct TileMeta {
   uint32_t hmin;             // heap span start, 16-byte units from the heap base
   uint32_t hbytes;           // heap span bytes (multiple of 16)
   int32_t staged;            // the tile fits the stages
+  // written by P with the ticket: where the tile's string_t / validity words are (the bulk loads are issued later, when S frees)
+  const uint8_t *src;
+  const uint64_t *val;       // nullptr: no mask
 };
 
 constexpr int kPackMaxWarps = 16;
@@ -774,18 +777,17 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
   if (warp == NW) {
     // ------------------------------------------------------------ P: tickets, string_t bulk loads ...
     // claim tile k: ticket + chunk metadata, bulk load of its string_t (+ validity words) into S[k&1]
-    auto claim = [&](int k) -> long long {
+    // claim tile k: ticket + chunk metadata.  Done one tile EARLIER than the bulk load of its string_t (which has to wait for
+    // the S buffer): the ticket atomic and the dependent metadata loads (two L2 round trips) are then off the path between
+    // "S is free" and "the load is in flight" -- with two CTAs of 18 warps per SM (the heap-less form) the workers had
+    // spent 11 % of their stall samples waiting for S
+    auto claim = [&](int k) {
       TileMeta &m = pt.meta[k & (kMetaRing - 1)];
-      const int slot = k & 1;
-      const uint32_t mb = smem_u32(&pt.mbar_s[slot]);
       DMB_PTRACE(k, 14);
       long long tile = (long long)atomicAdd(scratch, 1ull);
       if (tile >= ntiles) tile = -1;
       m.tile = tile;
-      if (tile < 0) {  // no tile: complete the phase all the same, the others learn it from meta
-        mbar_arrive(mb);
-        return tile;
-      }
+      if (tile < 0) return;
       const int64_t c = tile / kTilesPerChunk;
       const int r_begin = (int)(tile % kTilesPerChunk) * kRows;
       const int count = (int)__ldg(b.counts + c);
@@ -795,19 +797,35 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       m.out_row0 = __ldg(b.row_off + c) + r_begin;
       m.nrows = nrows_tile;
       m.has_mask = vd.val_off >= 0;
+      m.src = reinterpret_cast<const uint8_t *>(job.in) + vd.data_off + (uint64_t)r_begin * 16u;
+      m.val = vd.val_off >= 0 ? job.in_validity + vd.val_off + (r_begin >> 6) : nullptr;
+    };
+    // bulk load of tile k's string_t (+ validity words) into S[k&1]
+    auto load = [&](int k) {
+      const TileMeta &m = pt.meta[k & (kMetaRing - 1)];
+      const int slot = k & 1;
+      const uint32_t mb = smem_u32(&pt.mbar_s[slot]);
+      if (m.tile < 0) {  // no tile: complete the phase all the same, the others learn it from meta
+        mbar_arrive(mb);
+        return;
+      }
       // a DuckDB vector always has STANDARD_VECTOR_SIZE entries of storage: the whole tile is readable
-      mbar_expect_tx(mb, kSBytes + (vd.val_off >= 0 ? (uint32_t)kRows / 8u : 0u));
-      bulk_load(smem_u32(sbuf + (uint32_t)slot * kSBytes),
-                reinterpret_cast<const uint8_t *>(job.in) + vd.data_off + (uint64_t)r_begin * 16u, kSBytes, mb);
-      if (vd.val_off >= 0) bulk_load(smem_u32(&pt.vmask[slot][0]), job.in_validity + vd.val_off + (r_begin >> 6), (uint32_t)kRows / 8u, mb);
+      mbar_expect_tx(mb, kSBytes + (m.val ? (uint32_t)kRows / 8u : 0u));
+      bulk_load(smem_u32(sbuf + (uint32_t)slot * kSBytes), m.src, kSBytes, mb);
+      if (m.val) bulk_load(smem_u32(&pt.vmask[slot][0]), m.val, (uint32_t)kRows / 8u, mb);
       DMB_PTRACE(k, 6);
-      return tile;
     };
     // ... and T: when the workers have packed a tile, send the stage to out_data with bulk stores and
     // hand the stage back.  Both jobs are triggered by the end of a worker iteration.
+    // Tickets run three tiles ahead, loads two (A/B in one run, 60 M rows: heap-less columns 0.270 -> 0.254 ms, all-pointer columns
+    // 0.772 -> 0.741 ms, l_comment / l_shipinstruct shapes unchanged within the box-to-box noise of +-1 %)
+    constexpr bool kEarlyTicket = true;
     if (lane == 0) {
       claim(0);
-      claim(1);  // claims run two tiles ahead, also past the end: the workers must meet a tile that says so
+      claim(1);  // (also past the end: the workers must meet a tile that says so)
+      if (kEarlyTicket) claim(2);
+      load(0);
+      load(1);
     }
     bar_arrive(kBarBase, kWL);  // the stage is free
     for (int j = 0;; ++j) {
@@ -849,8 +867,14 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       if (!more) break;
       bar_arrive(kBarBase, kWL);  // the stage is free
       if (lane == 0) {
-        // S[j&1] held tile j: the workers have scanned it (barrier above), and so has A
-        claim(j + 2);
+        // S[j&1] held tile j: the workers have scanned it (barrier above)
+        if (kEarlyTicket) {
+          load(j + 2);
+          claim(j + 3);
+        } else {
+          claim(j + 2);
+          load(j + 2);
+        }
       }
       __syncwarp();
     }
@@ -948,15 +972,19 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         if (bad) atomicOr(scratch + 1, (unsigned long long)kErrHeapRange);
         n_lmax = __reduce_max_sync(0xffffffffu, n_lmax);
         bar_sync(kBarWorkers, kWT);
-        uint32_t warp_excl = 0u;
+        // the NW warp sums: one load per lane + a shuffle scan (as NW loads + selects per thread this was 11 % of the kernel)
+        uint32_t wincl = lane < NW ? pp.warp_sum[lane] : 0u;
+        const uint32_t wown = wincl;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) warp_excl += w < warp ? pp.warp_sum[w] : 0u;
+        for (int d = 1; d < NW; d <<= 1) {
+          const uint32_t n = __shfl_up_sync(0xffffffffu, wincl, d);
+          if (lane >= d) wincl += n;
+        }
+        const uint32_t warp_excl = __shfl_sync(0xffffffffu, wincl - wown, warp);
+        const uint32_t total = __shfl_sync(0xffffffffu, wincl, NW - 1);
 #pragma unroll
         for (int k = 0; k < R; ++k) n_off[k] += warp_excl;
         if (tid == 0) {
-          uint32_t total = 0u;
-#pragma unroll
-          for (int w = 0; w < NW; ++w) total += pp.warp_sum[w];
           mj.total = total;
           mj.hmin = 0u;
           mj.hbytes = 0u;
@@ -976,12 +1004,13 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
         base = pt.base[(j - 1) & (kMetaRing - 1)];
         const TileMeta &mc = pt.meta[(j - 1) & (kMetaRing - 1)];
         const int nrows = mc.nrows;
+        long long *oo64 = reinterpret_cast<long long *>(job.out_offsets) + (mc.out_row0 + row0);
+        int32_t *oo32 = reinterpret_cast<int32_t *>(job.out_offsets) + (mc.out_row0 + row0);
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-          const int row = row0 + 32 * k;
-          if (row < nrows) {
-            if (LARGE) __stcs(reinterpret_cast<long long *>(job.out_offsets) + mc.out_row0 + row, (long long)(base + c_off[k]));
-            else __stcs(reinterpret_cast<int32_t *>(job.out_offsets) + mc.out_row0 + row, (int32_t)((uint32_t)base + c_off[k]));
+          if (row0 + 32 * k < nrows) {
+            if (LARGE) __stcs(oo64 + 32 * k, (long long)(base + c_off[k]));
+            else __stcs(oo32 + 32 * k, (int32_t)((uint32_t)base + c_off[k]));
           }
         }
       }
@@ -989,13 +1018,14 @@ string_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch,
       if (cur_valid) {
         const uint32_t mis = (uint32_t)(base & 15ull);
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {
-          if ((uint32_t)i < c_lmax) {  // warp-uniform: no issue slots for bytes past the warp's longest string
+        for (int k = 0; k < R; ++k) c_off[k] += mis;  // (the offsets have left: from here on, the stage byte of the row's first byte)
 #pragma unroll
-            for (int k = 0; k < R; ++k) {
-              const uint32_t wsel = i < 4 ? c_y[k] : (i < 8 ? c_z[k] : c_w[k]);
-              if ((uint32_t)i < c_len[k]) ostage[mis + c_off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
-            }
+        for (int i = 0; i < 12; ++i) {
+          if ((uint32_t)i >= c_lmax) break;  // warp-uniform: one test per byte position up to the warp's longest string, then out
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            const uint32_t wsel = i < 4 ? c_y[k] : (i < 8 ? c_z[k] : c_w[k]);
+            if ((uint32_t)i < c_len[k]) ostage[c_off[k] + i] = (uint8_t)(wsel >> (8 * (i & 3)));
           }
         }
         fence_proxy_async_smem();
