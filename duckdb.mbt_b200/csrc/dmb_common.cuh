@@ -196,7 +196,9 @@ __device__ __forceinline__ uint4 enum_entry(const dmb_enum_job &job, uint32_t id
   uint4 e = make_uint4(len, 0, 0, 0);
   if (len <= 12u) {
     uint32_t w[3] = {0u, 0u, 0u};
-    for (uint32_t k = 0; k < len; ++k) w[k >> 2] |= (uint32_t)__ldg(q + k) << (8u * (k & 3u));
+#pragma unroll
+    for (uint32_t k = 0; k < 12u; ++k)  // (unrolled: the byte loads are in flight together, one round trip instead of `len`)
+      if (k < len) w[k >> 2] |= (uint32_t)__ldg(q + k) << (8u * (k & 3u));
     e.y = w[0]; e.z = w[1]; e.w = w[2];
   } else {
     e.y = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16) | ((uint32_t)__ldg(q + 3) << 24);

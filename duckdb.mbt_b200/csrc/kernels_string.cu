@@ -1892,6 +1892,247 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
   }
 }
 
+// ------------------------------------------------------------------ ENUM indices -> utf8, one launch (dmb_dev_enum_utf8)
+// The ENUM form of string_short_kernel above is bound by instruction issue (ncu r03b: issue 81 %, DRAM 21 %, 141 thread
+// instructions per row: a byte load per index, up to 12 predicated byte stores per row, four 2x16-bit warp scans per thread).
+// This kernel keeps its structure -- one CTA per 2048-row vector, ticketed, the label table as string_t in shared memory,
+// bytes placed at tile-local positions while warp 0 resolves the prefix -- and removes the instructions:
+//   * a thread owns 8 CONSECUTIVE rows: its indices arrive as one 8 / 16 / 2 x 16-byte load, its validity bits as one byte of the mask
+//   * the 8 lengths stay packed in one register (4 bits each); one 32-bit warp scan of the per-thread sums
+//   * the thread's bytes are one contiguous stream: labels are appended to a running word with funnel shifts and leave as
+//     whole 32-bit words (<= 3 stores per row); only the first / last word of the stream, which the neighbouring threads
+//     share, is written byte by byte
+//   * the 8 consecutive offsets leave as two 16-byte stores
+#ifndef DMB_ENUM_PACK_CTAS
+#define DMB_ENUM_PACK_CTAS 6
+#endif
+template <bool LARGE, int EW>
+__global__ void __launch_bounds__(kThreads, DMB_ENUM_PACK_CTAS)
+enum_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles, dmb_enum_job ej) {
+  constexpr int kR = kVec / kThreads;  // 8 rows per thread
+  constexpr int kWarps = kThreads / 32;
+  __shared__ __align__(16) uint8_t stage[kVec * 12 + 32];
+  __shared__ uint4 s_tab[DMB_ENUM_FUSED_MAX_LABELS + 1];
+  __shared__ uint32_t warp_sum[kWarps];
+  __shared__ uint64_t base_sh;
+  __shared__ long long ticket_sh;
+  unsigned long long *status = scratch + 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tile = claim_tile(scratch, &ticket_sh);  // = chunk index; every predecessor is owned by a CTA that is running or done
+  if (tile >= ntiles) return;
+  const int count = (int)__ldg(b.counts + tile);
+  const dmb_vec_desc vd = ej.vecs[tile];
+  const uint64_t *mask = vd.val_off < 0 ? nullptr : ej.in_validity + vd.val_off;
+  const uint8_t *in_idx = reinterpret_cast<const uint8_t *>(ej.in_data) + vd.data_off;
+  const int i0 = tid * kR;
+
+  // ---- the thread's 8 indices, raw (the index under a NULL row is read and dropped)
+  uint32_t raw[EW == 4 ? 8 : (EW == 2 ? 4 : 2)];
+  {
+    constexpr int kWords = EW == 4 ? 8 : (EW == 2 ? 4 : 2);
+    const uint8_t *p = in_idx + (size_t)i0 * EW;
+    if (i0 + kR <= count && (reinterpret_cast<uintptr_t>(p) & (EW == 1 ? 7u : 15u)) == 0u) {
+      if (EW == 1) {
+        const uint2 v = ld_stream(reinterpret_cast<const uint2 *>(p));
+        raw[0] = v.x; raw[1] = v.y;
+      } else {
+#pragma unroll
+        for (int q = 0; q < kWords; q += 4) {
+          const uint4 v = ld_stream(reinterpret_cast<const uint4 *>(p) + q / 4);
+          raw[q] = v.x; raw[q + 1] = v.y; raw[q + 2] = v.z; raw[q + 3] = v.w;
+        }
+      }
+    } else {  // the vector's ragged end, or a vector that is only element-aligned
+      typedef typename EnumIndex<EW>::type I;
+#pragma unroll
+      for (int q = 0; q < kWords; ++q) raw[q] = 0u;
+#pragma unroll
+      for (int k = 0; k < kR; ++k) {
+        const uint32_t v = i0 + k < count ? (uint32_t)reinterpret_cast<const I *>(p)[k] : 0u;
+        if (EW == 4) raw[k] = v; else raw[(k * EW) >> 2] |= v << (8 * ((k * EW) & 3));
+      }
+    }
+  }
+  auto index_of = [&](int k) -> uint32_t {
+    if (EW == 4) return raw[k];
+    if (EW == 2) return (raw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+    return (raw[k >> 2] >> (8 * (k & 3))) & 0xffu;
+  };
+  uint32_t vbits = 0u;
+  if (i0 < count) {
+    vbits = mask ? (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(mask) + tid) : 0xffu;  // byte t of the mask = rows 8t .. 8t + 7
+    if (count - i0 < kR) vbits &= (1u << (count - i0)) - 1u;
+  }
+  // the labels as string_t, once per CTA (the index loads above are in flight meanwhile).  Word 0 of an entry is the label's
+  // length; a label too long for this kernel reads as length 0 + bit 30, and entry dict_size -- where every index past the
+  // dictionary is sent -- as length 0 + bit 31: the row loop needs no comparisons
+  for (uint32_t t = tid; t <= ej.dict_size; t += kThreads) {
+    uint4 e = make_uint4(0x80000000u, 0u, 0u, 0u);
+    if (t < ej.dict_size) {
+      e = enum_entry(ej, t);
+      if (e.x > 12u) e = make_uint4(0x40000000u, 0u, 0u, 0u);
+    }
+    s_tab[t] = e;
+  }
+  __syncthreads();
+
+  // ---- lengths (4 bits per row), the thread's sum, block scan
+  uint32_t lens = 0u, mine = 0u, seen = 0u;
+  unsigned bad_idx = 0;
+#pragma unroll
+  for (int k = 0; k < kR; ++k) {
+    const uint32_t ix = index_of(k);
+    uint32_t t = s_tab[ix < ej.dict_size ? ix : ej.dict_size].x;
+    t = ((vbits >> k) & 1u) ? t : 0u;  // (the index under a NULL row is looked up and dropped)
+    seen |= t;
+    bad_idx += t >> 31;  // an index past the dictionary: reported, rendered as the empty string
+    const uint32_t l = t & 15u;
+    lens |= l << (4 * k);
+    mine += l;
+  }
+  const int bad = (seen >> 30) & 1;  // a label too long for this kernel (the host sends such dictionaries the two-step way)
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += n;
+  }
+  if (lane == 31) warp_sum[warp] = incl;
+  if (bad_idx && ej.bad_index) atomicAdd(ej.bad_index, (unsigned long long)bad_idx);
+  const int any_bad = __syncthreads_or(bad);
+  uint32_t wincl = lane < kWarps ? warp_sum[lane] : 0u;
+  const uint32_t wown = wincl;
+#pragma unroll
+  for (int d = 1; d < kWarps; d <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, wincl, d);
+    if (lane >= d) wincl += n;
+  }
+  const uint32_t tile_total = __shfl_sync(0xffffffffu, wincl, kWarps - 1);
+  const uint32_t my_off = __shfl_sync(0xffffffffu, wincl - wown, warp) + incl - mine;  // tile-local byte offset of the thread's first row
+  if (tid == 0) {
+    atomicExch(status + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)tile_total);
+    atomicAdd(status + ntiles + (tile >> 5), kGroupOne | (unsigned long long)tile_total);
+    if (any_bad) atomicOr(scratch + 1, (unsigned long long)kErrHeapRange);
+  }
+
+  // ---- the thread's bytes: one stream from stage byte my_off on.  Whole words only in the loop: the first word of a stream
+  // that starts inside a word leaves with zeros in its low `head` bytes, and after the barrier the threads before write
+  // those bytes -- the unfinished tail of their own stream -- over them, byte by byte.
+  uint32_t *sw = reinterpret_cast<uint32_t *>(stage);
+  const uint32_t head = my_off & 3u;
+  uint32_t wp = my_off >> 2, fill = head, acc = 0u;
+  const uint32_t wp0 = wp;
+#pragma unroll
+  for (int k = 0; k < kR; ++k) {
+    const uint32_t l = (lens >> (4 * k)) & 15u;
+    if (l == 0u) continue;
+    const uint4 ent = s_tab[index_of(k)];
+    const uint32_t sft = 8u * fill;
+    const uint32_t x0 = acc | (ent.y << sft);
+    const uint32_t x1 = __funnelshift_l(ent.y, ent.z, sft);
+    const uint32_t x2 = __funnelshift_l(ent.z, ent.w, sft);
+    const uint32_t x3 = __funnelshift_l(ent.w, 0u, sft);
+    const uint32_t n = fill + l, nw = n >> 2;  // n <= 15: at most three words complete
+    if (nw >= 1u) sw[wp] = x0;
+    if (nw >= 2u) sw[wp + 1] = x1;
+    if (nw >= 3u) sw[wp + 2] = x2;
+    // bytes of the label past its length never leave: whole words hold only the first 4 nw <= n bytes, the rest is masked here
+    acc = ((nw & 2u) ? ((nw & 1u) ? x3 : x2) : ((nw & 1u) ? x1 : x0)) & low_bytes3(n & 3u);
+    wp += nw;
+    fill = n & 3u;
+  }
+  __syncthreads();
+  // the stream's unfinished tail: bytes [0, fill) of word wp, or [head, fill) when the whole stream lies inside its first word
+  if (fill) store_bytes(sw + wp, acc, wp == wp0 ? head : 0u, fill);
+  // ---- decoupled look-back (warp 0), after its own bytes are placed: the later it starts, the shorter it is
+  if (warp == 0) {
+    const uint64_t prefix = lookback_groups(status, status + ntiles, status + ntiles + ((ntiles + 31) >> 5), tile, lane, status - 1,
+                                            (unsigned long long)kErrTimeout, g_lookback_limit_ns);
+    if (lane == 0) {
+      if (tile > 0) atomicExch(status + tile, kFlagPrefix | ((prefix + tile_total) & kValueMask));
+      if ((tile & 31) == 31) atomicExch(status + ntiles + ((ntiles + 31) >> 5) + (tile >> 5), kFlagPrefix | ((prefix + tile_total) & kValueMask));
+      base_sh = prefix;
+    }
+  }
+  __syncthreads();
+  const uint64_t base = base_sh;
+  const int64_t out_row0 = __ldg(b.row_off + tile);
+  if (tid == 0) {
+    if (!LARGE && base + tile_total > 0x7fffffffull) atomicOr(scratch + 1, (unsigned long long)kErrOffsetOverflow);
+    if (tile == ntiles - 1) {
+      if (LARGE) reinterpret_cast<long long *>(job.out_offsets)[b.nrows] = (long long)(base + tile_total);
+      else reinterpret_cast<int32_t *>(job.out_offsets)[b.nrows] = (int32_t)(base + tile_total);
+      if (job.total_bytes) *job.total_bytes = base + tile_total;
+    }
+  }
+  // ---- offsets: 8 consecutive values per thread
+  if (i0 < count) {
+    uint64_t o = base + my_off;
+    if (LARGE) {
+      long long *oo = reinterpret_cast<long long *>(job.out_offsets) + out_row0 + i0;
+      if (i0 + kR <= count && (reinterpret_cast<uintptr_t>(oo) & 15u) == 0u) {
+#pragma unroll
+        for (int k = 0; k < kR; k += 2) {
+          const uint64_t o1 = o + ((lens >> (4 * k)) & 15u);
+          __stcs(reinterpret_cast<longlong2 *>(oo + k), make_longlong2((long long)o, (long long)o1));
+          o = o1 + ((lens >> (4 * k + 4)) & 15u);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kR; ++k) {
+          if (i0 + k < count) __stcs(oo + k, (long long)o);
+          o += (lens >> (4 * k)) & 15u;
+        }
+      }
+    } else {
+      int32_t *oo = reinterpret_cast<int32_t *>(job.out_offsets) + out_row0 + i0;
+      uint32_t o32 = (uint32_t)o;
+      if (i0 + kR <= count && (reinterpret_cast<uintptr_t>(oo) & 15u) == 0u) {
+#pragma unroll
+        for (int k = 0; k < kR; k += 4) {
+          const uint32_t o1 = o32 + ((lens >> (4 * k)) & 15u), o2 = o1 + ((lens >> (4 * k + 4)) & 15u), o3 = o2 + ((lens >> (4 * k + 8)) & 15u);
+          __stcs(reinterpret_cast<int4 *>(oo + k), make_int4((int)o32, (int)o1, (int)o2, (int)o3));
+          o32 = o3 + ((lens >> (4 * k + 12)) & 15u);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kR; ++k) {
+          if (i0 + k < count) __stcs(oo + k, (int32_t)o32);
+          o32 += (lens >> (4 * k)) & 15u;
+        }
+      }
+    }
+  }
+  if (tile_total == 0) return;
+  if (job.out_data_cap && base + tile_total > job.out_data_cap) {
+    if (tid == 0) atomicOr(scratch + 1, (unsigned long long)kErrDataCap);
+    return;
+  }
+  // ---- stage -> out_data: destination-aligned 16-byte vectors; vector v holds tile bytes [16v - mis, 16v - mis + 16)
+  uint8_t *gdst = job.out_data + base;
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
+  const uint32_t end = mis + tile_total;
+  const uint32_t v0 = mis ? 1u : 0u, v1 = end >> 4;  // whole vectors [v0, v1)
+  for (uint32_t v = v0 + tid; v < v1; v += kThreads) {
+    const uint32_t q = 16u * v - mis, sh = 8u * (q & 3u);
+    const uint32_t *s = sw + (q >> 2);
+    const uint32_t a0 = s[0], a1 = s[1], a2 = s[2], a3 = s[3], a4 = s[4];  // s[4]: inside the stage's 32 bytes of slack
+    uint4 o;
+    o.x = __funnelshift_r(a0, a1, sh);
+    o.y = __funnelshift_r(a1, a2, sh);
+    o.z = __funnelshift_r(a2, a3, sh);
+    o.w = __funnelshift_r(a3, a4, sh);
+    st_stream(reinterpret_cast<uint4 *>(gdst - mis) + v, o);
+  }
+  // the ragged first / last vector: the neighbouring tiles own their other bytes
+  if (warp == kWarps - 1) {
+    const uint32_t h1 = v1 > v0 ? 16u * v0 : end;  // (no whole vector: everything is ragged)
+    for (uint32_t q = mis + lane; q < h1; q += 32u) gdst[q - mis] = stage[q - mis];
+    if (v1 > v0)
+      for (uint32_t q = 16u * v1 + lane; q < end; q += 32u) gdst[q - mis] = stage[q - mis];
+  }
+}
+
 // bench/test helper: DuckDB-shaped string_t from lengths + heap offsets
 __global__ void __launch_bounds__(kThreads)
 make_string_t_kernel(const uint32_t *__restrict__ lengths, const uint64_t *__restrict__ heap_off,
@@ -1953,6 +2194,17 @@ extern "C" int32_t dmb_dev_enum_utf8(const dmb_enum_job *ejob, const dmb_string_
     kernel<<<(unsigned)nchunks, kThreads, 0, st>>>(*job, b, (unsigned long long *)scratch, nchunks, *ejob);
     return check_cuda(cudaGetLastError(), "string_short_kernel (ENUM) launch");
   };
+  // default: enum_pack_kernel (consecutive-row ownership, word-granular placement); DMB_ENUM_SHORT=1 keeps the ENUM form of
+  // string_short_kernel for A/B
+  static const bool enum_short = getenv("DMB_ENUM_SHORT") != nullptr;
+  if (!enum_short) {
+    switch (ejob->phys) {
+      case DMB_PHYS_U8: return large ? launch(enum_pack_kernel<true, 1>) : launch(enum_pack_kernel<false, 1>);
+      case DMB_PHYS_U16: return large ? launch(enum_pack_kernel<true, 2>) : launch(enum_pack_kernel<false, 2>);
+      case DMB_PHYS_U32: return large ? launch(enum_pack_kernel<true, 4>) : launch(enum_pack_kernel<false, 4>);
+      default: set_error("dmb_dev_enum_utf8: ENUM indices are uint8/uint16/uint32, not physical type %d", ejob->phys); return -1;
+    }
+  }
   static const int ctas = getenv("DMB_ENUM_CTAS") ? atoi(getenv("DMB_ENUM_CTAS")) : 6;
   if (ctas == 5) {
     switch (ejob->phys) {
