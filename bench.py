@@ -925,7 +925,19 @@ def run_ours(args, rank, local_rank, world):
                 return int(res._decode_fixed(view, w, np.dtype(dt), True)[1].shape[0])
 
         def getters_step():
+            """results one after the other through the C ABI; the decoder mirror of result i runs on the pool while the C ABI
+            converts result i + 1 (decode_s = the time the caller still had to wait for decoders)"""
             got = 0
+            pending = None
+
+            def finish(p):
+                res_p, futs = p
+                t = time.perf_counter()
+                n_ = sum(f.result() for f in futs)
+                tsplit["decode_s"] += time.perf_counter() - t
+                res_p.close()
+                return n_
+
             for s in subs:
                 t0 = time.perf_counter()
                 h = ctx.lib.duckdb_mb_gpu_result_from_chunks(ctx.handle, C.byref(s.struct))
@@ -936,11 +948,13 @@ def run_ours(args, rank, local_rank, world):
                 for j, col in enumerate(s.batch.columns):  # the C-ABI calls, one at a time like the reference's FFI
                     kind = getter_of.get(col.type_id, "string")
                     blobs.append((kind, res._blob(kind, j, True)))
-                t2 = time.perf_counter()
-                tsplit["c_getters_s"] += t2 - t1
-                got += sum(pool.map(lambda kb: decode_one(res, kb[0], kb[1]), blobs))
-                tsplit["decode_s"] += time.perf_counter() - t2
-                res.close()
+                tsplit["c_getters_s"] += time.perf_counter() - t1
+                futs = [pool.submit(decode_one, res, kb[0], kb[1]) for kb in blobs]
+                if pending is not None:
+                    got += finish(pending)
+                pending = (res, futs)
+            if pending is not None:
+                got += finish(pending)
             return got
 
         assert getters_step() == rows_res * len(layout.columns)
@@ -960,7 +974,8 @@ def run_ours(args, rank, local_rank, world):
                        "c_abi_only_rows_per_s": world * rows_res * kg / max(tsplit["from_chunks_s"] + tsplit["c_getters_s"], 1e-9),
                        "what": "per <= 1 M-row result (the reference decoders' cap): duckdb_mb_gpu_result_from_chunks on the DuckDB "
                                "layout + the 16 duckdb_mb_arrow_get_column_*_nullable getters the schema selects + the decoder mirror "
-                               "(arrow_result.py, columns decoded on a thread pool) -- the surface --impl reference times on the CPU"}
+                               "(arrow_result.py, columns decoded on a thread pool while the C ABI converts the next result) -- the surface "
+                               "--impl reference times on the CPU"}
         pool.shutdown()
         del subs, hb2, layout
     elif not args.no_layout_leg:

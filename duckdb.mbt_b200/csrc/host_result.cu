@@ -231,14 +231,27 @@ void compact_fixup(void *user, int64_t k, uint8_t *staged, size_t bytes) {
   const uint32_t n = (uint32_t)(bytes / sizeof(dmb_string_t));
   const void *mask = cc->col->validity.empty() ? nullptr : cc->col->validity[(size_t)k];
   uint64_t pos = cc->arena_start[k];
+  // Pointer strings that follow each other in memory (what a scan leaves in a vector's string heap) are copied as ONE run:
+  // per row that is a compare and an add instead of a ~27-byte memcpy of unpredictable size (the per-row form spent more
+  // host time on the two text columns of the C2 table than the gather of all sixteen columns took).
+  const uint8_t *run_src = nullptr;
+  uint64_t run_pos = pos, run_len = 0;
   for (uint32_t i = 0; i < n; ++i) {
     if (!host_row_valid(mask, i)) continue;  // payload under a NULL row is unspecified: never dereference it
     const uint32_t len = e[i].length;
     if (len <= 12) continue;
-    memcpy(cc->arena + pos, reinterpret_cast<const void *>((uintptr_t)e[i].tail.ptr), len);
+    const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)e[i].tail.ptr);
+    if ((uintptr_t)src != (uintptr_t)run_src + run_len) {  // (also the first pointer row: run_src is null)
+      if (run_len) memcpy(cc->arena + run_pos, run_src, (size_t)run_len);
+      run_src = src;
+      run_pos = pos;
+      run_len = 0;
+    }
+    run_len += len;
     e[i].tail.ptr = cc->fake_base + pos;
     pos += len;
   }
+  if (run_len) memcpy(cc->arena + run_pos, run_src, (size_t)run_len);
 }
 
 // copy one column's chunk vectors (payload, validity masks, descriptors, string heap) to HBM
@@ -1751,21 +1764,45 @@ int32_t materialise_arrow(Result *r) {
     cudaEventRecord(in0, c.s_in);
     cudaEventRecord(out0, c.s_out);
     auto drain = [&](int j) -> int32_t { return drain_with_redo(r, sc, &pend[(size_t)j], j); };
-    // Processing order: the copy-out stream trails the copy-in stream by one column, so the first
-    // column's copy-in and the last column's copy-out are the only transfers that do not overlap.
-    // Small columns go to both ends, the large ones to the middle ("pyramid").
-    std::vector<int> order((size_t)ncols), sorted((size_t)ncols);
+    // Processing order.  Copy-in and copy-out are two machines every column passes through in that order (the kernel in
+    // between is ~2 % of either): a two-machine flow shop, whose makespan Johnson's rule minimises -- columns that grow on
+    // the way (copy-in shorter than copy-out: DECIMAL -> decimal128) first, by increasing copy-in; the rest (VARCHAR: 16-byte
+    // string_t in, 4-byte offsets out) after them, by decreasing copy-out.  The copy-out stream then never waits for a long
+    // copy-in behind a short one, and the two ends that cannot overlap are the smallest transfers.  (Round 1's order --
+    // small columns at both ends, large ones in the middle -- left the copy-out stream idle behind the 2.5 GB copy-ins of the
+    // text columns: 266 vs 237 ms for the C2 table in the bytes / link-rate model, lower bound 231.)
+    std::vector<int> order((size_t)ncols);
     {
-      std::vector<uint64_t> weight((size_t)ncols);
+      std::vector<uint64_t> w_in((size_t)ncols), w_out((size_t)ncols);
+      const uint64_t n = (uint64_t)r->nrows;
       for (int j = 0; j < ncols; ++j) {
         const Col &col = r->cols[(size_t)j];
-        weight[(size_t)j] = (uint64_t)col.width * (uint64_t)r->nrows + col.heap_len + (col.is_list ? col.child_base.back() * (uint64_t)col.child_width : 0);
-        sorted[(size_t)j] = j;
+        ArrowMap m;
+        const uint64_t list_bytes = col.is_list ? col.child_base.back() * (uint64_t)col.child_width : 0;
+        w_in[(size_t)j] = (uint64_t)col.width * n + col.heap_len + list_bytes;
+        uint64_t out = w_in[(size_t)j];
+        if (arrow_map(col, &m) && !m.is_nested && !m.is_list) {
+          if (m.is_string) out = 4 * n + (col.heap_len ? col.heap_len : 4 * n);  // (inlined bytes are not known before the kernel: a guess)
+          else { const int32_t ow = dmb_op_out_width(m.op); out = ow > 0 ? (uint64_t)ow * n : n / 8; }
+        }
+        w_out[(size_t)j] = out;
+        order[(size_t)j] = j;
       }
-      std::stable_sort(sorted.begin(), sorted.end(), [&](int a, int b) { return weight[(size_t)a] < weight[(size_t)b]; });
-      int front = 0, back = ncols - 1;
-      for (int k = 0; k < ncols; ++k) {
-        if (k % 2 == 0) order[(size_t)front++] = sorted[(size_t)k]; else order[(size_t)back--] = sorted[(size_t)k];
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        const bool ga = w_in[(size_t)a] < w_out[(size_t)a], gb = w_in[(size_t)b] < w_out[(size_t)b];
+        if (ga != gb) return ga;                                       // the growing columns first ...
+        if (ga) return w_in[(size_t)a] < w_in[(size_t)b];              // ... by increasing copy-in
+        return w_out[(size_t)a] > w_out[(size_t)b];                    // the others by decreasing copy-out
+      });
+      static const bool pyramid = getenv("DMB_ORDER_PYRAMID") != nullptr;  // A/B knob: round 1's order
+      if (pyramid) {
+        std::vector<int> sorted((size_t)ncols);
+        for (int j = 0; j < ncols; ++j) sorted[(size_t)j] = j;
+        std::stable_sort(sorted.begin(), sorted.end(), [&](int a, int b) { return w_in[(size_t)a] < w_in[(size_t)b]; });
+        int front = 0, back = ncols - 1;
+        for (int k = 0; k < ncols; ++k) {
+          if (k % 2 == 0) order[(size_t)front++] = sorted[(size_t)k]; else order[(size_t)back--] = sorted[(size_t)k];
+        }
       }
     }
     for (int k = 0; k < ncols; ++k) {

@@ -1906,6 +1906,9 @@ string_short_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch
 #ifndef DMB_ENUM_PACK_CTAS
 #define DMB_ENUM_PACK_CTAS 6
 #endif
+#ifndef DMB_ENUM_LB_FIRST
+#define DMB_ENUM_LB_FIRST 0
+#endif
 template <bool LARGE, int EW>
 __global__ void __launch_bounds__(kThreads, DMB_ENUM_PACK_CTAS)
 enum_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, int64_t ntiles, dmb_enum_job ej) {
@@ -1921,6 +1924,7 @@ enum_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, i
   const int64_t tile = claim_tile(scratch, &ticket_sh);  // = chunk index; every predecessor is owned by a CTA that is running or done
   if (tile >= ntiles) return;
   const int count = (int)__ldg(b.counts + tile);
+  const int64_t out_row0 = __ldg(b.row_off + tile);  // (needed at the very end: as a load down there, 21 % of the stall samples sat on it)
   const dmb_vec_desc vd = ej.vecs[tile];
   const uint64_t *mask = vd.val_off < 0 ? nullptr : ej.in_validity + vd.val_off;
   const uint8_t *in_idx = reinterpret_cast<const uint8_t *>(ej.in_data) + vd.data_off;
@@ -2015,6 +2019,17 @@ enum_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, i
     if (any_bad) atomicOr(scratch + 1, (unsigned long long)kErrHeapRange);
   }
 
+#if DMB_ENUM_LB_FIRST
+  if (warp == 0) {  // (variant: warp 0 resolves the prefix before it places its own bytes)
+    const uint64_t prefix = lookback_groups(status, status + ntiles, status + ntiles + ((ntiles + 31) >> 5), tile, lane, status - 1,
+                                            (unsigned long long)kErrTimeout, g_lookback_limit_ns);
+    if (lane == 0) {
+      if (tile > 0) atomicExch(status + tile, kFlagPrefix | ((prefix + tile_total) & kValueMask));
+      if ((tile & 31) == 31) atomicExch(status + ntiles + ((ntiles + 31) >> 5) + (tile >> 5), kFlagPrefix | ((prefix + tile_total) & kValueMask));
+      base_sh = prefix;
+    }
+  }
+#endif
   // ---- the thread's bytes: one stream from stage byte my_off on.  Whole words only in the loop: the first word of a stream
   // that starts inside a word leaves with zeros in its low `head` bytes, and after the barrier the threads before write
   // those bytes -- the unfinished tail of their own stream -- over them, byte by byte.
@@ -2045,7 +2060,7 @@ enum_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, i
   // the stream's unfinished tail: bytes [0, fill) of word wp, or [head, fill) when the whole stream lies inside its first word
   if (fill) store_bytes(sw + wp, acc, wp == wp0 ? head : 0u, fill);
   // ---- decoupled look-back (warp 0), after its own bytes are placed: the later it starts, the shorter it is
-  if (warp == 0) {
+  if (!DMB_ENUM_LB_FIRST && warp == 0) {
     const uint64_t prefix = lookback_groups(status, status + ntiles, status + ntiles + ((ntiles + 31) >> 5), tile, lane, status - 1,
                                             (unsigned long long)kErrTimeout, g_lookback_limit_ns);
     if (lane == 0) {
@@ -2056,7 +2071,6 @@ enum_pack_kernel(dmb_string_job job, BatchView b, unsigned long long *scratch, i
   }
   __syncthreads();
   const uint64_t base = base_sh;
-  const int64_t out_row0 = __ldg(b.row_off + tile);
   if (tid == 0) {
     if (!LARGE && base + tile_total > 0x7fffffffull) atomicOr(scratch + 1, (unsigned long long)kErrOffsetOverflow);
     if (tile == ntiles - 1) {
