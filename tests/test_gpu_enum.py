@@ -232,3 +232,68 @@ def test_enum_fused_device_api_flags_long_labels_and_bad_indices(ctx):
     assert rc == 0 and flags != 0                                             # heap-range flag: a label the kernel cannot inline
     rc = run([b"a"], np.zeros(n, np.uint8), dict_size=257)[0]
     assert rc != 0 and "labels" in nat.last_error()
+
+
+@pytest.mark.parametrize("phys,shift,large", [(ch.P_U8, 0, False), (ch.P_U8, 3, True), (ch.P_U16, 0, False), (ch.P_U16, 1, False),
+                                              (ch.P_U32, 0, True), (ch.P_U32, 1, False)])
+def test_enum_fused_device_api_index_widths_alignment_and_masks(ctx, phys, shift, large):
+    """enum_pack_kernel at the device API: uint8 / uint16 / uint32 indices, vectors that start `shift` ELEMENTS past an aligned
+    address (the thread's eight indices are then read one by one instead of as one vector), ragged chunks (a count that is not
+    a multiple of 8, an empty chunk), validity masks with garbage indices under the NULL rows, int32 and int64 offsets."""
+    import ctypes as C
+    from duckdb_mbt_b200 import native as nat
+    L = nat.lib()
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(77 + phys + shift)
+    np_t = {ch.P_U8: np.uint8, ch.P_U16: np.uint16, ch.P_U32: np.uint32}[phys]
+    w = np.dtype(np_t).itemsize
+    counts_np = np.array([2048, 2043, 0, 2048, 1, 777], dtype=np.uint32)
+    nch, n = len(counts_np), int(counts_np.sum())
+    labels = [b"", b"a", b"bc", b"twelve bytes", b"seven_7", b"0123456789", b"xyz"]
+    k = len(labels)
+    idx_np = rng.integers(0, k, n)
+    valid = rng.random(n) >= 0.25
+    # vector c sits `shift` elements behind slot c of the slab; rows past a chunk's count and rows under a NULL hold garbage
+    slot = 2048 + 8
+    slab = rng.integers(k, 250, nch * slot + 64).astype(np_t)
+    masks = np.zeros((nch, 32), dtype=np.uint64)
+    row_off = np.zeros(nch + 1, dtype=np.int64)
+    np.cumsum(counts_np, out=row_off[1:])
+    for c in range(nch):
+        a, b = int(row_off[c]), int(row_off[c + 1])
+        v = valid[a:b]
+        vals = np.where(v, idx_np[a:b], rng.integers(k, 250, b - a)).astype(np_t)
+        slab[c * slot + shift: c * slot + shift + (b - a)] = vals
+        bits = np.zeros(2048, dtype=bool)
+        bits[: b - a] = v
+        bits[b - a:] = rng.random(2048 - (b - a)) > 0.5  # garbage past the count
+        masks[c] = np.packbits(bits, bitorder="little").view(np.uint64)
+    vecs_np = np.array([[(c * slot + shift) * w, c * 32] for c in range(nch)], dtype=np.int64)
+    d_offs, d_data = ch.enum_dict_arrays(labels)
+    t_offs = torch.from_numpy(d_offs.view(np.uint8).copy()).to(dev)
+    t_data = torch.from_numpy(np.concatenate([d_data, np.zeros(64, np.uint8)])).to(dev)
+    t_slab = torch.from_numpy(slab.view(np.uint8).copy()).to(dev)
+    t_masks = torch.from_numpy(masks.view(np.uint8).reshape(-1).copy()).to(dev)
+    t_counts = torch.from_numpy(counts_np.view(np.uint8).copy()).to(dev)
+    t_row_off = torch.from_numpy(row_off.view(np.uint8).copy()).to(dev)
+    t_vecs = torch.from_numpy(vecs_np.view(np.uint8).reshape(-1).copy()).to(dev)
+    bad = torch.zeros(1, dtype=torch.int64, device=dev)
+    ow = 8 if large else 4
+    offsets = torch.zeros(ow * (n + 1) + 64, dtype=torch.uint8, device=dev)
+    data = torch.zeros(12 * n + 64, dtype=torch.uint8, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    scratch = torch.empty(L.dmb_dev_string_scratch_bytes(nch), dtype=torch.uint8, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ejob = nat.EnumJob(t_slab.data_ptr(), t_masks.data_ptr(), t_vecs.data_ptr(), None, t_offs.data_ptr(), t_data.data_ptr(), 1 << 41,
+                       bad.data_ptr(), k, phys)
+    mode = 1 if large else 0  # DMB_STR_ARROW_LARGE / DMB_STR_ARROW_UTF8
+    sjob = nat.StringJob(None, None, None, None, 0, 0, offsets.data_ptr(), data.data_ptr(), None, None, None, total.data_ptr(), mode, 0)
+    rc = L.dmb_dev_enum_utf8(C.byref(ejob), C.byref(sjob), t_counts.data_ptr(), t_row_off.data_ptr(), nch, n, scratch.data_ptr(), stream)
+    assert rc == 0, nat.last_error()
+    assert L.dmb_dev_string_error(scratch.data_ptr(), stream) == 0, nat.last_error()
+    assert int(bad.item()) == 0  # garbage under NULL rows is never counted
+    exp_off, exp_data = _expected_utf8(labels, idx_np, valid)
+    got_off = offsets[: ow * (n + 1)].cpu().numpy().view("<i8" if large else "<i4").astype(np.int64)
+    assert np.array_equal(got_off, exp_off)
+    assert int(total.item()) == len(exp_data)
+    assert bytes(data[: len(exp_data)].cpu().numpy()) == exp_data
