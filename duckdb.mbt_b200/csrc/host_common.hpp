@@ -3,6 +3,7 @@
 #pragma once
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <map>
@@ -88,6 +89,8 @@ struct CtxCore {
   int ring_next = 0;
   int stage_threads = 1;
   WorkerPool pool;
+  // where a host-buffer call spends its wall time (ms, summed; printed per materialise when DMB_TRACE_STAGE is set)
+  double t_gather = 0, t_ring_wait = 0, t_drain_wait = 0, t_stage = 0, t_launch = 0;
   std::mutex mu;  // one blocking call at a time per context
   ~CtxCore();
   bool bind() const { return check_cuda(cudaSetDevice(device), "cudaSetDevice") == 0; }
@@ -101,6 +104,10 @@ struct duckdb_mb_gpu_ctx {
 };
 
 namespace dmb {
+
+inline double wall_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 // run fn(i) for i in [0, n) on the context's host threads (gather memcpy into pinned staging, size passes)
 template <typename F>
@@ -117,13 +124,17 @@ inline void parallel_for(CtxCore &core, int64_t n, F fn) {
 //   src[k]        host pointer of piece k (NULL: skipped)
 //   piece_bytes   bytes of piece k = counts[k] * row_bytes (row_bytes == 0: fixed `slot_bytes`)
 //   pinned        pieces are page-locked: runs of full, address-contiguous pieces go by direct DMA
-//   fixup         optional: called on the staged copy of piece k before it is sent (string_t
-//                 pointer rewriting); forces the bounce path
-// Everything else is gathered by host threads into the pinned ring and sent in 16 MiB pieces.
-typedef void (*stage_fixup_fn)(void *user, int64_t k, uint8_t *staged, size_t bytes);
+//   fixup         optional hooks on the staged copies (string_t compaction); forces the bounce path
+// Everything else is gathered by host threads into the pinned ring and sent in 32 MiB pieces.
+// The hook runs inside a gather task, right after the task's pieces [c0, c1) were copied to staged0 + (c - c0) * slot_bytes:
+// the copies are still in the core's cache when it reads and rewrites them.
+struct StageFixup {
+  void (*task)(void *user, int64_t c0, int64_t c1, uint8_t *staged0, size_t slot_bytes);
+  void *user;
+};
 int32_t stage_pieces(CtxCore &core, cudaStream_t stream, const void *const *src, const uint32_t *counts,
                      size_t row_bytes, size_t slot_bytes, int64_t nchunks, uint8_t *dst, bool pinned,
-                     stage_fixup_fn fixup, void *fixup_user, uint64_t *bytes_moved);
+                     const StageFixup *fixup, uint64_t *bytes_moved);
 
 // Allocations and events of ONE blocking call.  The destructor drains the three streams before
 // anything goes back to the pools, also on error paths.

@@ -165,15 +165,17 @@ int CtxCore::ring_acquire() {
   if (!ring[b]) {
     if (check_cuda(cudaHostAlloc((void **)&ring[b], kStageBytes, cudaHostAllocDefault), "staging ring cudaHostAlloc")) return -1;
     if (check_cuda(cudaEventCreateWithFlags(&ring_free[b], cudaEventDisableTiming), "staging ring event")) return -1;
-  } else if (check_cuda(cudaEventSynchronize(ring_free[b]), "staging ring wait")) {
-    return -1;
+  } else {
+    const double t0 = wall_ms();
+    if (check_cuda(cudaEventSynchronize(ring_free[b]), "staging ring wait")) return -1;
+    t_ring_wait += wall_ms() - t0;
   }
   return b;
 }
 
 int32_t stage_pieces(CtxCore &core, cudaStream_t stream, const void *const *src, const uint32_t *counts,
                      size_t row_bytes, size_t slot_bytes, int64_t nchunks, uint8_t *dst, bool pinned,
-                     stage_fixup_fn fixup, void *fixup_user, uint64_t *bytes_moved) {
+                     const StageFixup *fixup, uint64_t *bytes_moved) {
   auto piece = [&](int64_t k) -> size_t { return row_bytes ? (size_t)counts[k] * row_bytes : slot_bytes; };
   const int64_t per_buf = (int64_t)(kStageBytes / slot_bytes);
   if (per_buf < 1) { set_error("stage_pieces: slot of %zu bytes exceeds the staging buffer", slot_bytes); return -1; }
@@ -202,6 +204,7 @@ int32_t stage_pieces(CtxCore &core, cudaStream_t stream, const void *const *src,
     uint8_t *buf = core.ring[b];
     const int64_t npieces = m - k;
     const int64_t group = 64;  // pieces per parallel task
+    const double t_g0 = wall_ms();
     parallel_for(core, (npieces + group - 1) / group, [&](int64_t g) {
       const int64_t i1 = (g + 1) * group < npieces ? (g + 1) * group : npieces;
       for (int64_t i = g * group; i < i1; ++i) {
@@ -209,9 +212,10 @@ int32_t stage_pieces(CtxCore &core, cudaStream_t stream, const void *const *src,
         const size_t bytes = piece(c);
         if (!src[c] || !bytes) continue;
         memcpy(buf + (size_t)i * slot_bytes, src[c], bytes);
-        if (fixup) fixup(fixup_user, c, buf + (size_t)i * slot_bytes, bytes);
       }
+      if (fixup) fixup->task(fixup->user, k + g * group, k + i1, buf + (size_t)(g * group) * slot_bytes, slot_bytes);
     });
+    core.t_gather += wall_ms() - t_g0;
     int64_t last = m - 1;
     while (last > k && (!src[last] || piece(last) == 0)) --last;
     const size_t bytes = (size_t)(last - k) * slot_bytes + piece(last);

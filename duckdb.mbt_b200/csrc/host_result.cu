@@ -213,45 +213,105 @@ int32_t ensure_meta(Result *r) {
   return 0;
 }
 
-struct CompactCtx {  // string columns whose heap is scattered: compact into a pinned arena
-  const Col *col;
-  const uint64_t *arena_start;  // [nchunks+1] byte offset of chunk k's strings in the arena
-  uint8_t *arena;
-  uint64_t fake_base;
+// String columns whose heap nobody registered: the pointed-to bytes are compacted into pinned arena segments while the
+// string_t are staged.  A gather task (64 chunk vectors, 2 MB of string_t that are still in the core's cache) sums the bytes
+// of its pointer strings, reserves that many bytes of the arena, copies the strings there and rewrites the pointers -- one
+// pass over the string_t.  (Round 2 first sized the arena with a pass of its own over every string_t of the column, 59 ms of
+// a 355 ms step for the two text columns of the C2 table; a per-ring-buffer plan with a second pass over the buffer moved
+// those 59 ms into the gather instead of removing them: the 32 MiB buffer is no longer cached when the second pass comes.)
+// Arena positions are logical: segment s covers [base_s, base_s + cap_s) of one address range per column, the device heap is
+// allocated when the column is through and every segment's used bytes are copied to base_s in it.
+struct ArenaSeg {
+  uint8_t *pin;
+  uint64_t base, used, cap;
 };
+struct CompactCtx {
+  Result *r = nullptr;
+  const Col *col = nullptr;
+  int64_t nchunks = 0;
+  std::mutex mu;
+  std::vector<ArenaSeg> segs;
+  uint64_t fake_base = 0;
+  bool failed = false;
+};
+constexpr uint64_t kArenaSegMax = 256ull << 20, kArenaSegMin = 1ull << 20;
 
 inline bool host_row_valid(const void *mask, uint32_t row) {
   if (!mask) return true;
   return (reinterpret_cast<const uint64_t *>(mask)[row >> 6] >> (row & 63)) & 1ull;
 }
 
-void compact_fixup(void *user, int64_t k, uint8_t *staged, size_t bytes) {
-  CompactCtx *cc = reinterpret_cast<CompactCtx *>(user);
-  dmb_string_t *e = reinterpret_cast<dmb_string_t *>(staged);
-  const uint32_t n = (uint32_t)(bytes / sizeof(dmb_string_t));
-  const void *mask = cc->col->validity.empty() ? nullptr : cc->col->validity[(size_t)k];
-  uint64_t pos = cc->arena_start[k];
-  // Pointer strings that follow each other in memory (what a scan leaves in a vector's string heap) are copied as ONE run:
-  // per row that is a compare and an add instead of a ~27-byte memcpy of unpredictable size (the per-row form spent more
-  // host time on the two text columns of the C2 table than the gather of all sixteen columns took).
-  const uint8_t *run_src = nullptr;
-  uint64_t run_pos = pos, run_len = 0;
-  for (uint32_t i = 0; i < n; ++i) {
-    if (!host_row_valid(mask, i)) continue;  // payload under a NULL row is unspecified: never dereference it
-    const uint32_t len = e[i].length;
-    if (len <= 12) continue;
-    const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)e[i].tail.ptr);
-    if ((uintptr_t)src != (uintptr_t)run_src + run_len) {  // (also the first pointer row: run_src is null)
-      if (run_len) memcpy(cc->arena + run_pos, run_src, (size_t)run_len);
-      run_src = src;
-      run_pos = pos;
-      run_len = 0;
-    }
-    run_len += len;
-    e[i].tail.ptr = cc->fake_base + pos;
-    pos += len;
+// `bytes` of the arena for a task that covers `nch_task` chunks: logical position + where that is in pinned memory
+bool compact_reserve(CompactCtx *cc, uint64_t bytes, int64_t nch_task, uint64_t *pos, uint8_t **at) {
+  std::lock_guard<std::mutex> g(cc->mu);
+  if (cc->failed) return false;
+  if (cc->segs.empty() || cc->segs.back().used + bytes > cc->segs.back().cap) {
+    // a new segment: what the whole column needs if it goes on like this task (+ 10 %), between 1 MiB and 256 MiB; a task
+    // larger than that gets a segment of its own size
+    uint64_t want = bytes / (uint64_t)(nch_task > 0 ? nch_task : 1) * (uint64_t)cc->nchunks;
+    want += want / 10 + kArenaSegMin;
+    want = want > kArenaSegMax ? kArenaSegMax : want;
+    want = want < bytes ? bytes : want;
+    if (!cc->r->core->bind()) { cc->failed = true; return false; }  // (a worker thread: the pinned pool may have to allocate)
+    uint8_t *pin = (uint8_t *)keep_pin(cc->r, (size_t)want + 32);
+    if (!pin) { cc->failed = true; return false; }
+    const uint64_t base = cc->segs.empty() ? 0ull : cc->segs.back().base + cc->segs.back().cap;
+    cc->segs.push_back(ArenaSeg{pin, base, 0, want});
   }
-  if (run_len) memcpy(cc->arena + run_pos, run_src, (size_t)run_len);
+  ArenaSeg &seg = cc->segs.back();
+  *pos = seg.base + seg.used;
+  *at = seg.pin + seg.used;
+  seg.used += bytes;
+  return true;
+}
+
+void compact_task(void *user, int64_t c0, int64_t c1, uint8_t *staged0, size_t slot_bytes) {
+  CompactCtx *cc = reinterpret_cast<CompactCtx *>(user);
+  const Col &col = *cc->col;
+  const std::vector<uint32_t> &counts = cc->r->counts;
+  auto mask_of = [&](int64_t k) -> const void * { return col.validity.empty() ? nullptr : col.validity[(size_t)k]; };
+  // 1: bytes of the task's pointer strings (payload under a NULL row is unspecified: not counted, never followed)
+  uint64_t sum = 0;
+  for (int64_t k = c0; k < c1; ++k) {
+    if (!col.data[(size_t)k]) continue;
+    const dmb_string_t *e = reinterpret_cast<const dmb_string_t *>(staged0 + (size_t)(k - c0) * slot_bytes);
+    const void *mask = mask_of(k);
+    const uint32_t n = counts[(size_t)k];
+    for (uint32_t i = 0; i < n; ++i)
+      if (host_row_valid(mask, i) && e[i].length > 12) sum += e[i].length;
+  }
+  if (!sum) return;
+  // 2: that many bytes of the arena
+  uint64_t pos = 0;
+  uint8_t *at = nullptr;
+  if (!compact_reserve(cc, sum, c1 - c0, &pos, &at)) return;
+  // 3: copy + rewrite.  Pointer strings that follow each other in memory (what a scan leaves in a vector's string heap) are
+  // copied as ONE run: per row that is a compare and an add instead of a ~27-byte memcpy of unpredictable size.
+  uint8_t *arena = at - pos;  // arena + logical position = the byte's place in the segment
+  for (int64_t k = c0; k < c1; ++k) {
+    if (!col.data[(size_t)k]) continue;
+    dmb_string_t *e = reinterpret_cast<dmb_string_t *>(staged0 + (size_t)(k - c0) * slot_bytes);
+    const void *mask = mask_of(k);
+    const uint32_t n = counts[(size_t)k];
+    const uint8_t *run_src = nullptr;
+    uint64_t run_pos = pos, run_len = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      if (!host_row_valid(mask, i)) continue;
+      const uint32_t len = e[i].length;
+      if (len <= 12) continue;
+      const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)e[i].tail.ptr);
+      if ((uintptr_t)src != (uintptr_t)run_src + run_len) {  // (also the first pointer row: run_src is null)
+        if (run_len) memcpy(arena + run_pos, run_src, (size_t)run_len);
+        run_src = src;
+        run_pos = pos;
+        run_len = 0;
+      }
+      run_len += len;
+      e[i].tail.ptr = cc->fake_base + pos;
+      pos += len;
+    }
+    if (run_len) memcpy(arena + run_pos, run_src, (size_t)run_len);
+  }
 }
 
 // copy one column's chunk vectors (payload, validity masks, descriptors, string heap) to HBM
@@ -261,6 +321,7 @@ int32_t stage_column(Result *r, int j) {
   NvtxRange nvtx("dmb::stage_column");
   if (ensure_meta(r)) return -1;
   CtxCore &c = *r->core;
+  struct StageTimer { CtxCore &c; double t0; ~StageTimer() { c.t_stage += wall_ms() - t0; } } stage_timer{c, wall_ms()};
   const int64_t nch = r->nchunks;
   const size_t nslots = (size_t)(nch > 0 ? nch : 1);
   const size_t slot = (size_t)DMB_VECTOR_SIZE * (size_t)col.width;
@@ -280,9 +341,9 @@ int32_t stage_column(Result *r, int j) {
   if (nch && check_cuda(cudaMemcpyAsync(col.d_vecs, pv, sizeof(dmb_vec_desc) * (size_t)nch, cudaMemcpyHostToDevice, c.s_in), "vec desc H2D")) return -1;
   r->bytes_h2d += sizeof(dmb_vec_desc) * (size_t)nch;
 
-  stage_fixup_fn fixup = nullptr;
-  CompactCtx cc{};
-  std::vector<uint64_t> arena_start;
+  StageFixup fixup{compact_task, nullptr};
+  CompactCtx cc;
+  bool compact = false;
   if (col.phys == DMB_PHYS_STRING) {
     if (col.heap_base == (const uint8_t *)DMB_HEAP_INLINE_ONLY && col.heap_len == 0) {
       // the caller vouches for an all-inlined column: nothing to stage, the heap-less kernel checks every entry
@@ -297,41 +358,34 @@ int32_t stage_column(Result *r, int j) {
       col.heap_host_base = (uint64_t)(uintptr_t)col.heap_base;
       col.d_heap_len = col.heap_len;
     } else {
-      // scattered heap: size pass, then gather into a pinned arena while the string_t are staged
-      arena_start.assign((size_t)nch + 1, 0);
-      parallel_for(c, nch, [&](int64_t k) {
-        const dmb_string_t *e = reinterpret_cast<const dmb_string_t *>(col.data[(size_t)k]);
-        const void *mask = col.validity.empty() ? nullptr : col.validity[(size_t)k];
-        uint64_t sum = 0;
-        for (uint32_t i = 0; e && i < r->counts[(size_t)k]; ++i)
-          if (host_row_valid(mask, i) && e[i].length > 12) sum += e[i].length;
-        arena_start[(size_t)k + 1] = sum;
-      });
-      for (int64_t k = 0; k < nch; ++k) arena_start[(size_t)k + 1] += arena_start[(size_t)k];
-      const uint64_t total = arena_start[(size_t)nch];
-      uint8_t *arena = (uint8_t *)keep_pin(r, (size_t)total + 32);
-      col.d_heap = (uint8_t *)keep_dev(r, (size_t)total + 32);
-      if (!arena || !col.d_heap) return -1;
-      col.heap_host_base = 1ull << 40;
-      col.d_heap_len = total;
+      // scattered heap: gathered into pinned arena segments while the string_t are staged (CompactCtx)
+      cc.r = r;
       cc.col = &col;
-      cc.arena_start = arena_start.data();
-      cc.arena = arena;
-      cc.fake_base = col.heap_host_base;
-      fixup = compact_fixup;
+      cc.nchunks = nch > 0 ? nch : 1;
+      cc.fake_base = 1ull << 40;
+      fixup.user = &cc;
+      compact = true;
     }
   }
   if (nch && !col.is_struct &&  // (a STRUCT vector has no payload of its own: validity + descriptors only)
       stage_pieces(c, c.s_in, col.data.data(), r->counts.data(), (size_t)col.width, slot, nch, col.d_data,
-                   r->pinned_input, fixup, &cc, &r->bytes_h2d)) return -1;
-  if (fixup && arena_start[(size_t)nch]) {
-    // every piece was gathered (host side) before its ring copy was issued, so the arena is complete
-    if (check_cuda(cudaMemcpyAsync(col.d_heap, cc.arena, (size_t)arena_start[(size_t)nch], cudaMemcpyHostToDevice, c.s_in), "string arena H2D")) return -1;
-    r->bytes_h2d += arena_start[(size_t)nch];
+                   r->pinned_input, compact ? &fixup : nullptr, &r->bytes_h2d)) return -1;
+  if (compact) {
+    // every piece was gathered (host side) before its ring copy was issued, so the segments are complete
+    if (cc.failed) return -1;
+    const uint64_t total = cc.segs.empty() ? 0ull : cc.segs.back().base + cc.segs.back().used;
+    col.heap_host_base = cc.fake_base;
+    col.d_heap_len = total;
+    col.d_heap = (uint8_t *)keep_dev(r, (size_t)total + 32);
+    if (!col.d_heap) return -1;
+    for (const ArenaSeg &seg : cc.segs) {
+      if (seg.used && check_cuda(cudaMemcpyAsync(col.d_heap + seg.base, seg.pin, (size_t)seg.used, cudaMemcpyHostToDevice, c.s_in), "string arena H2D")) return -1;
+      r->bytes_h2d += seg.used;
+    }
   }
   if (col.any_validity && nch) {
     if (stage_pieces(c, c.s_in, col.validity.data(), nullptr, 0, 8 * (size_t)DMB_VALIDITY_WORDS, nch,
-                     (uint8_t *)col.d_validity, r->pinned_input, nullptr, nullptr, &r->bytes_h2d)) return -1;
+                     (uint8_t *)col.d_validity, r->pinned_input, nullptr, &r->bytes_h2d)) return -1;
   }
   cudaEvent_t e = nullptr;
   if (check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) return -1;
@@ -1763,7 +1817,13 @@ int32_t materialise_arrow(Result *r) {
     const bool restage = !r->meta_staged;
     cudaEventRecord(in0, c.s_in);
     cudaEventRecord(out0, c.s_out);
-    auto drain = [&](int j) -> int32_t { return drain_with_redo(r, sc, &pend[(size_t)j], j); };
+    auto drain = [&](int j) -> int32_t {
+      const double t_d0 = wall_ms();
+      const int32_t rc = drain_with_redo(r, sc, &pend[(size_t)j], j);
+      c.t_drain_wait += wall_ms() - t_d0;
+      return rc;
+    };
+    c.t_gather = c.t_ring_wait = c.t_drain_wait = c.t_stage = c.t_launch = 0;
     // Processing order.  Copy-in and copy-out are two machines every column passes through in that order (the kernel in
     // between is ~2 % of either): a two-machine flow shop, whose makespan Johnson's rule minimises -- columns that grow on
     // the way (copy-in shorter than copy-out: DECIMAL -> decimal128) first, by increasing copy-in; the rest (VARCHAR: 16-byte
@@ -1809,7 +1869,9 @@ int32_t materialise_arrow(Result *r) {
       const int j = order[(size_t)k];
       const Col &col = r->cols[(size_t)j];
       const bool surely_large = col.phys == DMB_PHYS_STRING && (col.heap_len > 0x7fffffffull || col.force_large);
+      const double t_l0 = wall_ms();
       if (launch_arrow_col(r, sc, j, surely_large ? DMB_STR_ARROW_LARGE : DMB_STR_ARROW_UTF8, &pend[(size_t)j])) return -1;
+      c.t_launch += wall_ms() - t_l0;
       if (k > 0 && drain(order[(size_t)k - 1])) return -1;
     }
     cudaEventRecord(in1, c.s_in);
@@ -1829,6 +1891,10 @@ int32_t materialise_arrow(Result *r) {
     r->t_kernels = sc.kernel_ms();
   }
   r->t_total = now_ms() - t0;
+  static const bool trace = getenv("DMB_TRACE_STAGE") != nullptr;
+  if (trace)
+    fprintf(stderr, "[dmb] materialise_arrow %.1f ms: gather + string compaction %.1f (of which waiting for a ring buffer %.1f), drain (kernel waits + D2H enqueue) %.1f, stage_column %.1f, launch_arrow_col (staging included) %.1f, h2d stream %.1f, d2h stream %.1f\n",
+            r->t_total, c.t_gather, c.t_ring_wait, c.t_drain_wait, c.t_stage, c.t_launch, r->t_h2d, r->t_d2h);
   r->arrow_ready = true;
   return 0;
 }
