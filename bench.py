@@ -829,6 +829,25 @@ def run_ours(args, rank, local_rank, world):
         del s5, evs, one
         torch.cuda.empty_cache()
 
+    # ---- beyond BASELINE.json's configs, inside the same clock-sampled region: LIST<INTEGER> -> Arrow
+    # list<int32> and ENUM -> utf8 at the device API (profiles/bench_configs.py builds the inputs in HBM; the ENUM output is
+    # compared bit for bit with the two-step path, the LIST totals with the generator's)
+    if not args.no_configs:
+        sys.path.insert(0, os.path.join(ROOT, "profiles"))
+        import bench_configs as bc
+        bc.QUIET = True
+        for name, fn, kernel in (("LIST", bc.clist, "list_emit_kernel"), ("ENUM", bc.cenum, "enum_pack_kernel")):
+            torch.cuda.empty_cache()
+            fn(1.0, None)
+            ln = bc.LINES[-1]
+            ms_max = max_over_ranks(ln["ms"])
+            configs[name] = {"rows": world * ln["rows"], "rows_per_gpu": ln["rows"], "ms": ms_max, "rows_per_s": world * ln["rows"] / ms_max * 1e3,
+                             "gb_per_s": ln["gb_per_s"], "frac": ln["gb_per_s"] / peak_gbs, "algorithmic_bytes_per_gpu": int(ln["alg_GB"] * 1e9),
+                             "kernel_split": {kernel: {"ms": ln["ms"], "gb_per_s": ln["gb_per_s"], "frac": ln["gb_per_s"] / peak_gbs}},
+                             "steps": 5, "workload": "beyond BASELINE.json (SURVEY.md 8f item 3), per GPU: " + ln["config"], "launches": 1,
+                             **{k_: v_ for k_, v_ in ln.items() if k_ in ("child_elements", "two_step_ms", "enum_to_string_t_kernel_ms", "heap_less_string_kernel_ms")}}
+        torch.cuda.empty_cache()
+
     # ---- e2e: host API, page-locked host buffers, H2D + kernels + D2H timed
     if e2e_rows != n:
         del step, db
