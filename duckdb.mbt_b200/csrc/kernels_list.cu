@@ -440,7 +440,8 @@ extern "C" size_t dmb_dev_list_scratch_bytes(int64_t nchunks) {
 
 // scratch: [0] error flags (1: int32 offsets overflow, 2: a chunk with > 4 G child elements, 4: a look-back gave up
 // waiting, 8: a list entry reaches outside its chunk's child vector), [1] unused,
-// then chunk_sum[nchunks], chunk_base[nchunks], and a sum word + a prefix word per group of 32 chunks (the one-pass kernel's
+// then one look-back status word per chunk (aggregate / inclusive prefix), nchunks words that are no longer used (round 1's
+// precomputed chunk bases; the size function is part of the ABI), and a sum word + a prefix word per group of 32 chunks (the
 // two-level look-back).  out_child_validity must hold ceil(total / 64) + 1 words.
 extern "C" int32_t dmb_dev_list_batch(const dmb_list_job *job, const uint32_t *counts, const int64_t *row_off, int64_t nchunks,
                                       int64_t nrows, int64_t child_capacity, void *scratch, void *stream) {

@@ -322,9 +322,11 @@ typedef struct dmb_list_job {
                                        is ONE bitmap over the whole staged child slab (bit i = element i; child_val_off is
                                        ignored) instead of one padded mask per chunk -- the form a second-level gather
                                        (nested lists: entries already rebased onto the slab) reads */
-  const uint64_t *child_sizes;      /* [nchunks] elements in each chunk's child vector, or NULL: entries are not
-                                       range-checked.  A valid row whose offset + length reaches past its child
-                                       vector raises flag 8 and contributes no elements (never read)            */
+  const uint64_t *child_sizes;      /* [nchunks] elements in each chunk's child vector, or NULL: entries are only
+                                       checked against 2^32 - 2 elements (the kernel keeps a row's offset and length
+                                       as 32-bit values; a child vector larger than that raises flag 2).  A valid row
+                                       whose offset + length reaches past its child vector raises flag 8 and
+                                       contributes no elements (never read)                                     */
 } dmb_list_job;
 
 #define DMB_LIST_DENSE_CHILD_BITS 2
