@@ -20,7 +20,8 @@ the per-GPU string byte totals (the host exclusive scan that rebases offsets acr
                2048-row vector, flags = 0, scattered per-chunk string heaps (heap_len = 0), no hints
   e2e_getters  the reference's own surface: 16 duckdb_mb_arrow_get_column_*_nullable calls + the decoder
                mirror per 1 M-row result (what --impl reference times on the CPU)
-  configs      C1 / C3 / C4 / C5 of BASELINE.json, device-resident, in the same clock-sampled region
+  configs      C1 / C3 / C4 / C5 of BASELINE.json, device-resident, in the same clock-sampled region; LIST / ENUM
+               (LIST<INTEGER> -> Arrow list<int32>, ENUM -> utf8) at the device API beside them
   roofline     the dominant kernel family of the C2 step: algorithmic bytes / its CUDA-event time
   cpu_baseline the oracle port of the reference's getters + decoders, 1 core, <= 1 M-row sample;
   cpu_columnar an -O3 -march=native OpenMP columnar conversion on all host cores (oracle/columnar.c)
